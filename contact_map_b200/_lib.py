@@ -1,0 +1,121 @@
+"""ctypes binding of ``libcmb200.so`` (the C ABI declared in ``include/cmb200.h``).
+
+The library is built in-tree (``contact_map_b200/libcmb200.so``) by ``build()``;
+there is no CPU fallback: if the library is missing and cannot be built, or no
+CUDA device is present when a context is created, a RuntimeError is raised.
+"""
+import ctypes
+import os
+import shutil
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+SO_PATH = os.path.join(_HERE, "libcmb200.so")
+_SOURCES = [os.path.join(_HERE, "csrc", f) for f in (
+    "cmb_api.cu", "cmb_math.cuh", "cmb_cells.cuh", "cmb_frames_small.cuh",
+    "cmb_frames_large.cuh", "cmb_aux_kernels.cuh")] + [os.path.join(_ROOT, "include", "cmb200.h")]
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+_LIB = None
+
+EXPORTS = [
+    "cmb_version", "cmb_last_error", "cmb_ctx_create", "cmb_ctx_destroy", "cmb_set_system",
+    "cmb_n_residues", "cmb_residue_map", "cmb_table_sizes", "cmb_path_kind", "cmb_accumulate",
+    "cmb_accumulate_host", "cmb_frame_contacts", "cmb_sort_keys", "cmb_export_nonzero",
+    "cmb_boundary_pairs", "cmb_set_option", "cmb_get_stat", "cmb_gather_atoms", "cmb_min_dist",
+    "cmb_nearest", "cmb_synth_frames",
+]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    return None
+
+
+def needs_build():
+    if not os.path.exists(SO_PATH):
+        return True
+    so_time = os.path.getmtime(SO_PATH)
+    return any(os.path.getmtime(src) > so_time for src in _SOURCES if os.path.exists(src))
+
+
+def build(force=False, verbose=False):
+    """Compile the CUDA extension for sm_100a with nvcc (cross-compiles without a GPU)."""
+    if not force and not needs_build():
+        return SO_PATH
+    nvcc = _nvcc()
+    if nvcc is None:
+        raise RuntimeError("libcmb200.so is missing or stale and nvcc was not found; "
+                           "contact_map_b200 has no CPU fallback")
+    tmp = SO_PATH + ".tmp%d" % os.getpid()
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp, _SOURCES[0]]
+    env = dict(os.environ)
+    env.pop("CC", None)        # the image exports a wrapper gcc; let nvcc pick the system one
+    env.pop("CXX", None)
+    proc = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), proc.stderr[-4000:]))
+    os.replace(tmp, SO_PATH)
+    if verbose:
+        print(proc.stderr)
+    return SO_PATH
+
+
+def lib():
+    """Load (building first if necessary) the shared library and declare signatures."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if needs_build():
+        build()
+    L = ctypes.CDLL(SO_PATH)
+    vp, i32, i64, u64, dbl, flt = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_uint64,
+                                   ctypes.c_double, ctypes.c_float)
+    L.cmb_version.restype = i32
+    L.cmb_last_error.restype = ctypes.c_char_p
+    L.cmb_last_error.argtypes = [vp]
+    L.cmb_ctx_create.restype = i32
+    L.cmb_ctx_create.argtypes = [i32, ctypes.POINTER(vp)]
+    L.cmb_ctx_destroy.restype = None
+    L.cmb_ctx_destroy.argtypes = [vp]
+    L.cmb_set_system.restype = i32
+    L.cmb_set_system.argtypes = [vp, i32, vp, vp, vp, dbl, i32]
+    L.cmb_n_residues.restype = i32
+    L.cmb_n_residues.argtypes = [vp]
+    L.cmb_residue_map.restype = i32
+    L.cmb_residue_map.argtypes = [vp, vp]
+    L.cmb_table_sizes.restype = i32
+    L.cmb_table_sizes.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64)]
+    L.cmb_path_kind.restype = i32
+    L.cmb_path_kind.argtypes = [vp]
+    L.cmb_accumulate.restype = i32
+    L.cmb_accumulate.argtypes = [vp, vp, vp, i64, vp, vp, vp]
+    L.cmb_accumulate_host.restype = i32
+    L.cmb_accumulate_host.argtypes = [vp, vp, vp, i64, i64, vp, vp]
+    L.cmb_frame_contacts.restype = i32
+    L.cmb_frame_contacts.argtypes = [vp, vp, vp, i64, i64, vp, i64, vp, i64, vp, vp, vp, vp]
+    L.cmb_sort_keys.restype = i32
+    L.cmb_sort_keys.argtypes = [vp, vp, i64, vp]
+    L.cmb_export_nonzero.restype = i32
+    L.cmb_export_nonzero.argtypes = [vp, vp, i64, i64, vp, vp, vp, vp]
+    L.cmb_boundary_pairs.restype = i32
+    L.cmb_boundary_pairs.argtypes = [vp, vp, vp, i64, i64, i32, vp, i64, vp, vp]
+    L.cmb_set_option.restype = i32
+    L.cmb_set_option.argtypes = [vp, ctypes.c_char_p, i64]
+    L.cmb_get_stat.restype = i32
+    L.cmb_get_stat.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(i64)]
+    L.cmb_gather_atoms.restype = i32
+    L.cmb_gather_atoms.argtypes = [vp, vp, i64, i32, vp, i32, vp, vp]
+    L.cmb_min_dist.restype = i32
+    L.cmb_min_dist.argtypes = [vp, vp, vp, i64, i32, vp, i32, vp, i32, i32, vp, vp, vp]
+    L.cmb_nearest.restype = i32
+    L.cmb_nearest.argtypes = [vp, vp, vp, i32, dbl, i32, i32, vp, vp, vp, vp, vp, vp]
+    L.cmb_synth_frames.restype = i32
+    L.cmb_synth_frames.argtypes = [vp, vp, vp, i32, vp, u64, flt, i32, i64, i64, vp, vp]
+    _LIB = L
+    return L

@@ -1,0 +1,628 @@
+// cmb_api.cu -- C ABI of libcmb200.so (see include/cmb200.h for the contract and the
+// reference interfaces each entry point replaces).
+#include <cub/device/device_radix_sort.cuh>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/cmb200.h"
+#include "cmb_aux_kernels.cuh"
+#include "cmb_frames_large.cuh"
+#include "cmb_frames_small.cuh"
+
+using namespace cmb;
+
+struct cmb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int max_smem_optin = 0;
+    std::string err;
+
+    // system
+    bool have_system = false;
+    int n = 0;
+    int n_res_c = 0;
+    float cutoff_f = 0.f;
+    int n_ignored = 0;
+    std::vector<int32_t> res_map;     // compact -> global residue index
+    int2* d_meta = nullptr;
+    int path = 0;                     // 0 fused shared-memory kernel, 1 global-memory cell path
+
+    // fused-kernel launch configuration
+    int fs_maxc = 4096;
+    int fs_bm_words = 0;
+    int fs_bm_in_smem = 1;
+    int fs_smem = 0;
+    int fs_ctas_per_sm = 1;
+
+    // scratch, two slots so that two in-flight launches never share it
+    unsigned int* d_bitmap[2] = {nullptr, nullptr};
+    size_t bitmap_bytes[2] = {0, 0};
+    unsigned long long* d_counters[2] = {nullptr, nullptr};   // 4 x u64 each
+    int slot = 0;
+
+    // large path scratch
+    LargeScratch large[2];
+
+    // host pipeline
+    float* d_stage_xyz[2] = {nullptr, nullptr};
+    float* d_stage_box[2] = {nullptr, nullptr};
+    size_t stage_xyz_bytes = 0, stage_box_bytes = 0;
+    cudaStream_t streams[2] = {nullptr, nullptr};
+
+    // sort / min-dist scratch
+    void* d_tmp = nullptr;
+    size_t tmp_bytes = 0;
+
+    // options / stats
+    int count_tests = 0;
+    int last_slot = 0;
+    std::map<std::string, int64_t> stats;
+};
+
+static std::string g_create_err;
+
+static int fail(cmb_ctx* ctx, int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    else g_create_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                         \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess)                                                           \
+            return fail(ctx, CMB_ERR_CUDA, "%s failed: %s (%s:%d)", #call,               \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                     \
+    } while (0)
+
+static int ensure_bytes(cmb_ctx* ctx, void** ptr, size_t* have, size_t need)
+{
+    if (*have >= need && *ptr) return CMB_OK;
+    if (*ptr) CK(cudaFree(*ptr));
+    *ptr = nullptr;
+    *have = 0;
+    size_t want = need + need / 4 + 256;
+    CK(cudaMalloc(ptr, want));
+    *have = want;
+    return CMB_OK;
+}
+
+extern "C" int cmb_version(void) { return 100; }
+
+extern "C" const char* cmb_last_error(const cmb_ctx* ctx)
+{
+    return ctx ? ctx->err.c_str() : g_create_err.c_str();
+}
+
+extern "C" int cmb_ctx_create(int device, cmb_ctx** out)
+{
+    cmb_ctx* ctx = nullptr;
+    if (!out) return fail(nullptr, CMB_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, CMB_ERR_CUDA, "no CUDA device available (%s); libcmb200 has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(nullptr, CMB_ERR_ARG, "device %d out of range", device);
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(nullptr, CMB_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return fail(nullptr, CMB_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major < 10)
+        return fail(nullptr, CMB_ERR_CUDA, "device %d is sm_%d%d; libcmb200 is built for sm_100a only", device,
+                    prop.major, prop.minor);
+    ctx = new cmb_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    for (int s = 0; s < 2; s++) {
+        if (cudaMalloc(&ctx->d_counters[s], 4 * sizeof(unsigned long long)) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&ctx->streams[s], cudaStreamNonBlocking) != cudaSuccess) {
+            delete ctx;
+            return fail(nullptr, CMB_ERR_CUDA, "context allocation failed");
+        }
+    }
+    *out = ctx;
+    return CMB_OK;
+}
+
+extern "C" void cmb_ctx_destroy(cmb_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaFree(ctx->d_meta);
+    for (int s = 0; s < 2; s++) {
+        cudaFree(ctx->d_bitmap[s]);
+        cudaFree(ctx->d_counters[s]);
+        cudaFree(ctx->d_stage_xyz[s]);
+        cudaFree(ctx->d_stage_box[s]);
+        if (ctx->streams[s]) cudaStreamDestroy(ctx->streams[s]);
+        large_scratch_free(ctx->large[s]);
+    }
+    cudaFree(ctx->d_tmp);
+    delete ctx;
+}
+
+extern "C" int cmb_set_option(cmb_ctx* ctx, const char* name, int64_t value)
+{
+    if (!ctx || !name) return CMB_ERR_ARG;
+    if (!strcmp(name, "count_tests")) { ctx->count_tests = value != 0; return CMB_OK; }
+    if (!strcmp(name, "max_cells")) {
+        if (value < 8 || value > 32768) return fail(ctx, CMB_ERR_ARG, "max_cells out of range");
+        ctx->fs_maxc = (int)value;
+        return CMB_OK;
+    }
+    if (!strcmp(name, "force_path")) { ctx->stats["force_path"] = value; return CMB_OK; }
+    return fail(ctx, CMB_ERR_ARG, "unknown option %s", name);
+}
+
+extern "C" int cmb_get_stat(cmb_ctx* ctx, const char* name, int64_t* value)
+{
+    if (!ctx || !name || !value) return CMB_ERR_ARG;
+    if (!strcmp(name, "pair_tests")) {
+        unsigned long long h[4];
+        CK(cudaSetDevice(ctx->device));
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(h, ctx->d_counters[ctx->last_slot], sizeof(h), cudaMemcpyDeviceToHost));
+        *value = (int64_t)h[3];
+        return CMB_OK;
+    }
+    if (!strcmp(name, "sm_count")) { *value = ctx->sm_count; return CMB_OK; }
+    if (!strcmp(name, "ctas_per_sm")) { *value = ctx->fs_ctas_per_sm; return CMB_OK; }
+    if (!strcmp(name, "smem_bytes")) { *value = ctx->fs_smem; return CMB_OK; }
+    if (!strcmp(name, "max_cells")) { *value = ctx->fs_maxc; return CMB_OK; }
+    if (!strcmp(name, "kernel_launches")) { *value = ctx->stats["kernel_launches"]; return CMB_OK; }
+    return fail(ctx, CMB_ERR_ARG, "unknown stat %s", name);
+}
+
+// ---------------------------------------------------------------------------------
+// system set-up
+// ---------------------------------------------------------------------------------
+static int configure_small_path(cmb_ctx* ctx)
+{
+    const int n = ctx->n;
+    const long long bits = (long long)ctx->n_res_c * ctx->n_res_c;
+    ctx->fs_bm_words = (int)((bits + 31) / 32);
+    // residue bitmap in shared memory when it leaves room for two CTAs per SM
+    int maxc = ctx->fs_maxc;
+    FsLayout with_bm = fs_layout(n, maxc, ctx->fs_bm_words);
+    const int budget_two = (ctx->max_smem_optin + 1024) / 2 - 1024;
+    ctx->fs_bm_in_smem = 1;
+    if (with_bm.total > ctx->max_smem_optin || (ctx->fs_bm_words * 4 > 48 * 1024 && with_bm.total > budget_two))
+        ctx->fs_bm_in_smem = 0;
+    FsLayout L = fs_layout(n, maxc, ctx->fs_bm_in_smem ? ctx->fs_bm_words : 0);
+    while (L.total > ctx->max_smem_optin && maxc > 64) {
+        maxc /= 2;
+        L = fs_layout(n, maxc, ctx->fs_bm_in_smem ? ctx->fs_bm_words : 0);
+    }
+    if (L.total > ctx->max_smem_optin) return fail(ctx, CMB_ERR_LIMIT, "system does not fit the fused kernel");
+    ctx->fs_maxc = maxc;
+    ctx->fs_smem = L.total;
+    CK(cudaFuncSetAttribute(k_frames_small, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    int nb = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_frames_small, FS_THREADS, (size_t)L.total));
+    if (nb < 1) return fail(ctx, CMB_ERR_LIMIT, "fused kernel cannot be resident (smem %d)", L.total);
+    ctx->fs_ctas_per_sm = nb;
+    return CMB_OK;
+}
+
+extern "C" int cmb_set_system(cmb_ctx* ctx, int n_used, const int32_t* atom_res, const int32_t* atom_chain,
+                              const uint8_t* role, double cutoff, int n_ignored)
+{
+    if (!ctx) return CMB_ERR_ARG;
+    if (n_used <= 0 || !atom_res || !atom_chain || !role) return fail(ctx, CMB_ERR_ARG, "bad system arrays");
+    if (n_ignored < 0) return fail(ctx, CMB_ERR_ARG, "n_ignored must be >= 0");
+    if (!(cutoff > 0.0)) return fail(ctx, CMB_ERR_ARG, "cutoff must be positive");
+    if (n_used >= (1 << 20)) return fail(ctx, CMB_ERR_LIMIT, "more than 2^20 used atoms");
+    CK(cudaSetDevice(ctx->device));
+
+    // compact residue ids (rank among the used residues)
+    std::vector<int32_t> uniq(atom_res, atom_res + n_used);
+    std::sort(uniq.begin(), uniq.end());
+    uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+    ctx->res_map = uniq;
+    ctx->n_res_c = (int)uniq.size();
+
+    // exclusion key: |ekey_a - ekey_b| <= n_ignored  <=>  same chain and |res_a - res_b| <= n_ignored.
+    // Chains are laid out one after another on the key axis with gaps of n_ignored + 1.
+    std::map<int32_t, std::pair<int32_t, int32_t>> span;   // chain -> (min res, max res)
+    for (int i = 0; i < n_used; i++) {
+        auto it = span.find(atom_chain[i]);
+        if (it == span.end()) span[atom_chain[i]] = {atom_res[i], atom_res[i]};
+        else {
+            it->second.first = std::min(it->second.first, atom_res[i]);
+            it->second.second = std::max(it->second.second, atom_res[i]);
+        }
+    }
+    std::map<int32_t, long long> chain_base;
+    long long cursor = 0;
+    for (auto& kv : span) {
+        chain_base[kv.first] = cursor - kv.second.first;
+        cursor += (long long)(kv.second.second - kv.second.first) + n_ignored + 1;
+        if (cursor > 0x3fffffffll) return fail(ctx, CMB_ERR_LIMIT, "residue index span too large");
+    }
+    std::vector<int2> meta(n_used);
+    for (int i = 0; i < n_used; i++) {
+        const int rc = (int)(std::lower_bound(uniq.begin(), uniq.end(), atom_res[i]) - uniq.begin());
+        const int ekey = (int)(chain_base[atom_chain[i]] + atom_res[i]);
+        meta[i].x = ekey;
+        meta[i].y = rc | ((int)(role[i] & 3u) << 30);
+    }
+    if (ctx->d_meta) CK(cudaFree(ctx->d_meta));
+    ctx->d_meta = nullptr;
+    CK(cudaMalloc(&ctx->d_meta, sizeof(int2) * (size_t)n_used));
+    CK(cudaMemcpy(ctx->d_meta, meta.data(), sizeof(int2) * (size_t)n_used, cudaMemcpyHostToDevice));
+
+    ctx->n = n_used;
+    ctx->cutoff_f = (float)cutoff;
+    ctx->n_ignored = n_ignored;
+    ctx->have_system = false;
+    int64_t force = ctx->stats.count("force_path") ? ctx->stats["force_path"] : -1;
+    ctx->path = (n_used <= FS_MAX_ATOMS) ? 0 : 1;
+    if (force == 1) ctx->path = 1;
+    if (ctx->path == 0) {
+        int rc = configure_small_path(ctx);
+        if (rc != CMB_OK) return rc;
+    }
+    ctx->have_system = true;
+    return CMB_OK;
+}
+
+extern "C" int cmb_n_residues(const cmb_ctx* ctx) { return ctx && ctx->have_system ? ctx->n_res_c : CMB_ERR_STATE; }
+
+extern "C" int cmb_residue_map(const cmb_ctx* ctx, int32_t* out)
+{
+    if (!ctx || !ctx->have_system || !out) return CMB_ERR_STATE;
+    memcpy(out, ctx->res_map.data(), sizeof(int32_t) * ctx->res_map.size());
+    return CMB_OK;
+}
+
+extern "C" int cmb_table_sizes(const cmb_ctx* ctx, int64_t* atom_elems, int64_t* res_elems)
+{
+    if (!ctx || !ctx->have_system) return CMB_ERR_STATE;
+    if (atom_elems) *atom_elems = (int64_t)ctx->n * ctx->n;
+    if (res_elems) *res_elems = (int64_t)ctx->n_res_c * ctx->n_res_c;
+    return CMB_OK;
+}
+
+extern "C" int cmb_path_kind(const cmb_ctx* ctx) { return ctx && ctx->have_system ? ctx->path : CMB_ERR_STATE; }
+
+// ---------------------------------------------------------------------------------
+// frame kernels
+// ---------------------------------------------------------------------------------
+struct FrameJob {
+    const float* xyz; const float* box; long long n_frames; long long frame0;
+    unsigned int* atom_table; unsigned int* res_table;
+    unsigned long long* atom_keys; long long atom_cap;
+    unsigned long long* res_keys; long long res_cap;
+    unsigned long long* ext_counters;      // caller-provided device counters or nullptr
+    float4* boundary; long long boundary_cap; int boundary_ulps;
+};
+
+static float advance_float(float v, int steps)
+{
+    int32_t bits;
+    memcpy(&bits, &v, 4);
+    bits += steps;
+    float out;
+    memcpy(&out, &bits, 4);
+    return out;
+}
+
+static int launch_frames(cmb_ctx* ctx, const FrameJob& job, int slot, cudaStream_t stream)
+{
+    if (!ctx->have_system) return fail(ctx, CMB_ERR_STATE, "cmb_set_system has not been called");
+    if (job.n_frames <= 0) return CMB_OK;
+    if (!job.xyz) return fail(ctx, CMB_ERR_ARG, "xyz is NULL");
+    if (job.frame0 + job.n_frames >= (1ll << 24) && (job.atom_keys || job.res_keys))
+        return fail(ctx, CMB_ERR_LIMIT, "frame ids in emitted keys are limited to 2^24 per call");
+    CK(cudaSetDevice(ctx->device));
+    unsigned long long* counters = job.ext_counters ? job.ext_counters : ctx->d_counters[slot];
+    if (!job.ext_counters) CK(cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned long long), stream));
+    ctx->last_slot = slot;
+
+    const float c2 = ctx->cutoff_f * ctx->cutoff_f;   // float multiply, as in MDTraj
+    if (ctx->path == 0) {
+        FrameParams p;
+        memset(&p, 0, sizeof(p));
+        p.xyz = job.xyz; p.box = job.box; p.n_frames = job.n_frames; p.frame0 = job.frame0;
+        p.n = ctx->n; p.meta = ctx->d_meta;
+        p.cutoff = ctx->cutoff_f; p.c2 = c2;
+        p.boundary_ulps = job.boundary_ulps;
+        p.c2_hi = job.boundary_ulps > 0 ? advance_float(c2, job.boundary_ulps) : c2;
+        p.n_ignored = ctx->n_ignored; p.n_res_c = ctx->n_res_c;
+        p.maxc = ctx->fs_maxc; p.bm_words = ctx->fs_bm_words; p.bm_in_smem = ctx->fs_bm_in_smem;
+        p.atom_table = job.atom_table; p.res_table = job.res_table;
+        p.atom_keys = job.atom_keys; p.atom_cap = job.atom_cap;
+        p.res_keys = job.res_keys; p.res_cap = job.res_cap;
+        p.counters = counters;
+        p.boundary = job.boundary; p.boundary_cap = job.boundary_cap;
+        p.count_tests = ctx->count_tests;
+        long long grid = (long long)ctx->sm_count * ctx->fs_ctas_per_sm;
+        if (grid > job.n_frames) grid = job.n_frames;
+        if (!p.bm_in_smem) {
+            size_t need = (size_t)grid * (size_t)p.bm_words * 4;
+            int rc = ensure_bytes(ctx, (void**)&ctx->d_bitmap[slot], &ctx->bitmap_bytes[slot], need);
+            if (rc) return rc;
+            p.g_bitmap = ctx->d_bitmap[slot];
+        }
+        k_frames_small<<<(unsigned)grid, FS_THREADS, ctx->fs_smem, stream>>>(p);
+        CK(cudaGetLastError());
+        ctx->stats["kernel_launches"] += 1;
+        return CMB_OK;
+    }
+    // global-memory cell path
+    LargeJob lj;
+    lj.xyz = job.xyz; lj.box = job.box; lj.n_frames = job.n_frames; lj.frame0 = job.frame0;
+    lj.n = ctx->n; lj.meta = ctx->d_meta; lj.cutoff = ctx->cutoff_f; lj.c2 = c2;
+    lj.boundary_ulps = job.boundary_ulps;
+    lj.c2_hi = job.boundary_ulps > 0 ? advance_float(c2, job.boundary_ulps) : c2;
+    lj.n_ignored = ctx->n_ignored; lj.n_res_c = ctx->n_res_c;
+    lj.atom_table = job.atom_table; lj.res_table = job.res_table;
+    lj.atom_keys = job.atom_keys; lj.atom_cap = job.atom_cap;
+    lj.res_keys = job.res_keys; lj.res_cap = job.res_cap;
+    lj.counters = counters; lj.boundary = job.boundary; lj.boundary_cap = job.boundary_cap;
+    lj.count_tests = ctx->count_tests;
+    std::string err;
+    int launches = 0;
+    int rc = large_run(lj, ctx->large[slot], ctx->sm_count, stream, err, launches);
+    ctx->stats["kernel_launches"] += launches;
+    if (rc != CMB_OK) return fail(ctx, rc, "%s", err.c_str());
+    return CMB_OK;
+}
+
+extern "C" int cmb_accumulate(cmb_ctx* ctx, const float* d_xyz, const float* d_box, int64_t n_frames,
+                              uint32_t* d_atom_table, uint32_t* d_res_table, void* stream)
+{
+    if (!ctx) return CMB_ERR_ARG;
+    FrameJob job;
+    memset(&job, 0, sizeof(job));
+    job.xyz = d_xyz; job.box = d_box; job.n_frames = n_frames;
+    job.atom_table = d_atom_table; job.res_table = d_res_table;
+    ctx->slot ^= 1;
+    return launch_frames(ctx, job, ctx->slot, (cudaStream_t)stream);
+}
+
+extern "C" int cmb_accumulate_host(cmb_ctx* ctx, const float* h_xyz, const float* h_box, int64_t n_frames,
+                                   int64_t chunk_frames, uint32_t* d_atom_table, uint32_t* d_res_table)
+{
+    if (!ctx) return CMB_ERR_ARG;
+    if (!ctx->have_system) return fail(ctx, CMB_ERR_STATE, "cmb_set_system has not been called");
+    if (n_frames <= 0) return CMB_OK;
+    if (!h_xyz) return fail(ctx, CMB_ERR_ARG, "xyz is NULL");
+    CK(cudaSetDevice(ctx->device));
+    const size_t frame_bytes = (size_t)ctx->n * 12;
+    if (chunk_frames <= 0) {
+        chunk_frames = (int64_t)((32ull << 20) / frame_bytes);
+        // at least four chunks so copies and kernels overlap, but keep every SM busy
+        const int64_t quarter = (n_frames + 3) / 4;
+        if (chunk_frames > quarter) chunk_frames = quarter;
+        const int64_t fill = (int64_t)ctx->sm_count * std::max(1, ctx->fs_ctas_per_sm) * 2;
+        if (chunk_frames < fill) chunk_frames = fill;
+    }
+    if (chunk_frames > n_frames) chunk_frames = n_frames;
+    const size_t need_xyz = (size_t)chunk_frames * frame_bytes;
+    const size_t need_box = (size_t)chunk_frames * 36;
+    if (ctx->stage_xyz_bytes < need_xyz) {
+        for (int s = 0; s < 2; s++) {
+            if (ctx->d_stage_xyz[s]) CK(cudaFree(ctx->d_stage_xyz[s]));
+            ctx->d_stage_xyz[s] = nullptr;
+            CK(cudaMalloc(&ctx->d_stage_xyz[s], need_xyz + 256));
+        }
+        ctx->stage_xyz_bytes = need_xyz;
+    }
+    if (h_box && ctx->stage_box_bytes < need_box) {
+        for (int s = 0; s < 2; s++) {
+            if (ctx->d_stage_box[s]) CK(cudaFree(ctx->d_stage_box[s]));
+            ctx->d_stage_box[s] = nullptr;
+            CK(cudaMalloc(&ctx->d_stage_box[s], need_box + 256));
+        }
+        ctx->stage_box_bytes = need_box;
+    }
+    int c = 0;
+    for (int64_t f0 = 0; f0 < n_frames; f0 += chunk_frames, c++) {
+        const int s = c & 1;
+        const int64_t nf = std::min<int64_t>(chunk_frames, n_frames - f0);
+        // stream order on streams[s] serialises reuse of staging buffer s
+        CK(cudaMemcpyAsync(ctx->d_stage_xyz[s], h_xyz + (size_t)f0 * ctx->n * 3, (size_t)nf * frame_bytes,
+                           cudaMemcpyHostToDevice, ctx->streams[s]));
+        if (h_box)
+            CK(cudaMemcpyAsync(ctx->d_stage_box[s], h_box + (size_t)f0 * 9, (size_t)nf * 36,
+                               cudaMemcpyHostToDevice, ctx->streams[s]));
+        FrameJob job;
+        memset(&job, 0, sizeof(job));
+        job.xyz = ctx->d_stage_xyz[s]; job.box = h_box ? ctx->d_stage_box[s] : nullptr;
+        job.n_frames = nf; job.frame0 = f0;
+        job.atom_table = d_atom_table; job.res_table = d_res_table;
+        int rc = launch_frames(ctx, job, s, ctx->streams[s]);
+        if (rc != CMB_OK) return rc;
+    }
+    CK(cudaStreamSynchronize(ctx->streams[0]));
+    CK(cudaStreamSynchronize(ctx->streams[1]));
+    return CMB_OK;
+}
+
+extern "C" int cmb_frame_contacts(cmb_ctx* ctx, const float* d_xyz, const float* d_box, int64_t n_frames,
+                                  int64_t frame0, uint64_t* d_atom_keys, int64_t atom_cap,
+                                  uint64_t* d_res_keys, int64_t res_cap, uint64_t* d_counts,
+                                  uint32_t* d_atom_table, uint32_t* d_res_table, void* stream)
+{
+    if (!ctx) return CMB_ERR_ARG;
+    if (!d_counts) return fail(ctx, CMB_ERR_ARG, "d_counts is NULL");
+    FrameJob job;
+    memset(&job, 0, sizeof(job));
+    job.xyz = d_xyz; job.box = d_box; job.n_frames = n_frames; job.frame0 = frame0;
+    job.atom_table = d_atom_table; job.res_table = d_res_table;
+    job.atom_keys = (unsigned long long*)d_atom_keys; job.atom_cap = d_atom_keys ? atom_cap : 0;
+    job.res_keys = (unsigned long long*)d_res_keys; job.res_cap = d_res_keys ? res_cap : 0;
+    job.ext_counters = (unsigned long long*)d_counts;
+    ctx->slot ^= 1;
+    return launch_frames(ctx, job, ctx->slot, (cudaStream_t)stream);
+}
+
+extern "C" int cmb_boundary_pairs(cmb_ctx* ctx, const float* d_xyz, const float* d_box, int64_t n_frames,
+                                  int64_t frame0, int ulps, void* d_records, int64_t cap, uint64_t* d_n,
+                                  void* stream)
+{
+    if (!ctx) return CMB_ERR_ARG;
+    if (ulps < 1 || !d_records || !d_n) return fail(ctx, CMB_ERR_ARG, "bad boundary arguments");
+    // the kernel writes the record count to counters[2]; give it a private 4-slot block
+    CK(cudaSetDevice(ctx->device));
+    ctx->slot ^= 1;
+    FrameJob job;
+    memset(&job, 0, sizeof(job));
+    job.xyz = d_xyz; job.box = d_box; job.n_frames = n_frames; job.frame0 = frame0;
+    job.boundary = (float4*)d_records; job.boundary_cap = cap; job.boundary_ulps = ulps;
+    int rc = launch_frames(ctx, job, ctx->slot, (cudaStream_t)stream);
+    if (rc != CMB_OK) return rc;
+    CK(cudaMemcpyAsync(d_n, ctx->d_counters[ctx->slot] + 2, sizeof(unsigned long long),
+                       cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return CMB_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// sort / export / gather / synth
+// ---------------------------------------------------------------------------------
+extern "C" int cmb_sort_keys(cmb_ctx* ctx, uint64_t* d_keys, int64_t n, void* stream)
+{
+    if (!ctx) return CMB_ERR_ARG;
+    if (n <= 1) return CMB_OK;
+    if (n > 0x7fffffffll) return fail(ctx, CMB_ERR_LIMIT, "too many keys for one sort");
+    CK(cudaSetDevice(ctx->device));
+    size_t tmp = 0;
+    unsigned long long* keys = (unsigned long long*)d_keys;
+    CK(cub::DeviceRadixSort::SortKeys(nullptr, tmp, keys, keys, (int)n, 0, 64, (cudaStream_t)stream));
+    const size_t alt = ((size_t)n * 8 + 255) & ~(size_t)255;
+    int rc = ensure_bytes(ctx, &ctx->d_tmp, &ctx->tmp_bytes, alt + tmp);
+    if (rc) return rc;
+    unsigned long long* out = (unsigned long long*)ctx->d_tmp;
+    CK(cub::DeviceRadixSort::SortKeys((char*)ctx->d_tmp + alt, tmp, keys, out, (int)n, 0, 64,
+                                      (cudaStream_t)stream));
+    CK(cudaMemcpyAsync(keys, out, (size_t)n * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    ctx->stats["kernel_launches"] += 1;
+    return CMB_OK;
+}
+
+extern "C" int cmb_export_nonzero(cmb_ctx* ctx, const uint32_t* d_table, int64_t n_elems, int64_t cap,
+                                  int64_t* d_idx, uint32_t* d_cnt, uint64_t* d_n, void* stream)
+{
+    if (!ctx) return CMB_ERR_ARG;
+    if (!d_table || !d_idx || !d_cnt || !d_n || n_elems < 0) return fail(ctx, CMB_ERR_ARG, "bad export arguments");
+    if (((uintptr_t)d_table & 15) != 0) return fail(ctx, CMB_ERR_ARG, "table must be 16-byte aligned");
+    CK(cudaSetDevice(ctx->device));
+    if (n_elems == 0) return CMB_OK;
+    long long blocks = (n_elems / 4 + 255) / 256;
+    const long long maxb = (long long)ctx->sm_count * 8;
+    if (blocks > maxb) blocks = maxb;
+    if (blocks < 1) blocks = 1;
+    k_export_nonzero<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        d_table, n_elems, cap, (long long*)d_idx, d_cnt, (unsigned long long*)d_n);
+    CK(cudaGetLastError());
+    ctx->stats["kernel_launches"] += 1;
+    return CMB_OK;
+}
+
+extern "C" int cmb_gather_atoms(cmb_ctx* ctx, const float* d_xyz_full, int64_t n_frames, int n_total,
+                                const int32_t* d_used, int n_used, float* d_out, void* stream)
+{
+    if (!ctx) return CMB_ERR_ARG;
+    if (!d_xyz_full || !d_used || !d_out || n_total <= 0 || n_used <= 0) return fail(ctx, CMB_ERR_ARG, "bad gather arguments");
+    if (n_frames <= 0) return CMB_OK;
+    CK(cudaSetDevice(ctx->device));
+    long long total = n_frames * (long long)n_used;
+    long long blocks = std::min<long long>((total + 255) / 256, (long long)ctx->sm_count * 16);
+    k_gather_atoms<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(d_xyz_full, n_frames, n_total, d_used,
+                                                                        n_used, d_out);
+    CK(cudaGetLastError());
+    ctx->stats["kernel_launches"] += 1;
+    return CMB_OK;
+}
+
+extern "C" int cmb_synth_frames(cmb_ctx* ctx, const float* d_base, const int32_t* d_atom_group, int n_atoms,
+                                const float* d_box9, uint64_t seed, float amplitude, int image_shifts,
+                                int64_t frame0, int64_t n_frames, float* d_out, void* stream)
+{
+    if (!ctx) return CMB_ERR_ARG;
+    if (!d_base || !d_out || n_atoms <= 0) return fail(ctx, CMB_ERR_ARG, "bad synth arguments");
+    if (image_shifts && (!d_atom_group || !d_box9)) return fail(ctx, CMB_ERR_ARG, "image shifts need groups and a box");
+    if (n_frames <= 0) return CMB_OK;
+    CK(cudaSetDevice(ctx->device));
+    long long total = n_frames * (long long)n_atoms;
+    long long blocks = std::min<long long>((total + 255) / 256, (long long)ctx->sm_count * 16);
+    k_synth_frames<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        d_base, d_atom_group, n_atoms, d_box9, (unsigned long long)seed, amplitude, image_shifts, frame0,
+        n_frames, d_out);
+    CK(cudaGetLastError());
+    ctx->stats["kernel_launches"] += 1;
+    return CMB_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// min-distance analyses
+// ---------------------------------------------------------------------------------
+extern "C" int cmb_min_dist(cmb_ctx* ctx, const float* d_xyz, const float* d_box, int64_t n_frames,
+                            int n_atoms, const int32_t* d_query, int n_q, const int32_t* d_haystack, int n_h,
+                            int orthogonal, float* d_min, int64_t* d_arg, void* stream)
+{
+    if (!ctx) return CMB_ERR_ARG;
+    if (!d_xyz || !d_query || !d_haystack || !d_min || !d_arg || n_q <= 0 || n_h <= 0 || n_atoms <= 0)
+        return fail(ctx, CMB_ERR_ARG, "bad min_dist arguments");
+    if (n_frames <= 0) return CMB_OK;
+    CK(cudaSetDevice(ctx->device));
+    const int n_chunks = (n_h + MD_HCHUNK - 1) / MD_HCHUNK;
+    const int64_t fmax = 32768;   // gridDim.y limit is 65535
+    for (int64_t f0 = 0; f0 < n_frames; f0 += fmax) {
+        const int64_t nf = std::min<int64_t>(fmax, n_frames - f0);
+        const size_t need = (size_t)nf * n_chunks * (sizeof(float) + sizeof(long long)) + 256;
+        int rc = ensure_bytes(ctx, &ctx->d_tmp, &ctx->tmp_bytes, need);
+        if (rc) return rc;
+        long long* part_idx = (long long*)ctx->d_tmp;
+        float* part_d = (float*)((char*)ctx->d_tmp + (size_t)nf * n_chunks * sizeof(long long));
+        dim3 grid((unsigned)n_chunks, (unsigned)nf);
+        k_min_dist_partial<<<grid, MD_THREADS, 0, (cudaStream_t)stream>>>(
+            d_xyz + (size_t)f0 * n_atoms * 3, d_box ? d_box + (size_t)f0 * 9 : nullptr, n_atoms, d_query, n_q,
+            d_haystack, n_h, orthogonal, part_d, part_idx);
+        CK(cudaGetLastError());
+        k_min_dist_final<<<(unsigned)((nf + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+            part_d, part_idx, n_chunks, nf, d_min + f0, (long long*)d_arg + f0);
+        CK(cudaGetLastError());
+        ctx->stats["kernel_launches"] += 2;
+    }
+    return CMB_OK;
+}
+
+extern "C" int cmb_nearest(cmb_ctx* ctx, const float* d_xyz_frame, const float* d_box9, int n_atoms,
+                           double cutoff, int orthogonal, int excl_mode, const int32_t* d_atom_res,
+                           const int64_t* d_excl_ptr, const int32_t* d_excl_idx, int32_t* d_nearest,
+                           float* d_dist, void* stream)
+{
+    if (!ctx) return CMB_ERR_ARG;
+    if (!d_xyz_frame || !d_nearest || !d_dist || n_atoms <= 0) return fail(ctx, CMB_ERR_ARG, "bad nearest arguments");
+    if (excl_mode == 1 && !d_atom_res) return fail(ctx, CMB_ERR_ARG, "excl_mode 1 needs atom_res");
+    if (excl_mode == 2 && (!d_excl_ptr || !d_excl_idx)) return fail(ctx, CMB_ERR_ARG, "excl_mode 2 needs CSR lists");
+    if (excl_mode < 0 || excl_mode > 2) return fail(ctx, CMB_ERR_ARG, "bad excl_mode");
+    CK(cudaSetDevice(ctx->device));
+    const float cf = (float)cutoff;
+    const float c2 = cf * cf;
+    k_nearest<<<(unsigned)((n_atoms + NA_THREADS - 1) / NA_THREADS), NA_THREADS, 0, (cudaStream_t)stream>>>(
+        d_xyz_frame, d_box9, n_atoms, c2, orthogonal, excl_mode, d_atom_res, (const long long*)d_excl_ptr,
+        d_excl_idx, d_nearest, d_dist);
+    CK(cudaGetLastError());
+    ctx->stats["kernel_launches"] += 1;
+    return CMB_OK;
+}

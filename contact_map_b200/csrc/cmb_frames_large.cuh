@@ -1,0 +1,325 @@
+// cmb_frames_large.cuh -- global-memory cell path for systems that do not fit the
+// fused shared-memory kernel (n_used > 6144, e.g. the 100k-atom solvated system).
+//
+// Same adjudication code as the fused kernel (cmb_cells.cuh::cell_task); the cell
+// arrays and the cell-sorted float4 copy of the frame live in HBM/L2 instead of
+// shared memory, and the whole GPU works on ONE frame at a time:
+//   kl_prepare  grid of the frame (+ bounding box for open boundaries), zero counters
+//   kl_bin      cell id + rank per atom (L2 atomics on the cell histogram)
+//   kl_scan     exclusive scan over cells + occupied-cell list (single CTA)
+//   kl_scatter  cell-sorted float4 {x,y,z,atom}
+//   kl_pairs    persistent CTAs, one warp per occupied cell (global task counter)
+// Per-frame residue de-duplication (contact_map.py:601-607,740) uses a frame-stamp
+// table instead of a bitmap: frames are processed in stream order, so
+// atomicMax(stamp[slot], seq) < seq identifies the first hit of a residue pair in
+// the current frame.
+#pragma once
+#include <string>
+
+#include "cmb_cells.cuh"
+
+namespace cmb {
+
+constexpr int LG_MAXC = 1 << 21;
+constexpr int LG_PAIR_THREADS = 256;
+
+struct LargeScratch {
+    int cap_atoms = 0;
+    GridS* d_grid = nullptr;
+    int* d_cellcnt = nullptr;      // [LG_MAXC + 1]
+    int* d_cellptr = nullptr;      // [LG_MAXC + 1]
+    int* d_occ = nullptr;          // [LG_MAXC]
+    int* d_misc = nullptr;         // [0] n_occ, [1] task counter
+    int* d_atomcell = nullptr;     // [n]
+    int* d_atomrank = nullptr;     // [n]
+    float4* d_sorted = nullptr;    // [n]
+    unsigned int* d_stamp = nullptr;
+    size_t stamp_elems = 0;
+    unsigned int seq = 0;
+};
+
+inline void large_scratch_free(LargeScratch& S)
+{
+    cudaFree(S.d_grid); cudaFree(S.d_cellcnt); cudaFree(S.d_cellptr); cudaFree(S.d_occ);
+    cudaFree(S.d_misc); cudaFree(S.d_atomcell); cudaFree(S.d_atomrank); cudaFree(S.d_sorted);
+    cudaFree(S.d_stamp);
+    S = LargeScratch();
+}
+
+struct LargeJob {
+    const float* xyz; const float* box; long long n_frames; long long frame0;
+    int n; const int2* meta; float cutoff; float c2; float c2_hi; int boundary_ulps;
+    int n_ignored; int n_res_c;
+    unsigned int* atom_table; unsigned int* res_table;
+    unsigned long long* atom_keys; long long atom_cap;
+    unsigned long long* res_keys; long long res_cap;
+    unsigned long long* counters; float4* boundary; long long boundary_cap; int count_tests;
+};
+
+struct StampSink {
+    unsigned int* stamp;            // nullptr: residues not requested
+    unsigned int* res_table;
+    unsigned long long* res_keys;
+    long long res_cap;
+    unsigned long long* counters;
+    unsigned int seq;
+    unsigned int n_res_c;
+    long long frame_id;
+    __device__ __forceinline__ void residue(int rlo, int rhi)
+    {
+        if (stamp == nullptr) return;
+        const size_t slot = (size_t)rlo * n_res_c + (size_t)rhi;
+        if (*(volatile unsigned int*)&stamp[slot] == seq) return;
+        const unsigned old = atomicMax(&stamp[slot], seq);
+        if (old < seq) {
+            if (res_table != nullptr) atomicAdd(&res_table[slot], 1u);
+            if (res_keys != nullptr) {
+                const unsigned long long w = atomicAdd(&counters[1], 1ull);
+                if ((long long)w < res_cap)
+                    res_keys[w] = ((unsigned long long)frame_id << 40) | ((unsigned long long)rlo << 20) |
+                                  (unsigned long long)rhi;
+            }
+        }
+    }
+};
+
+__global__ void __launch_bounds__(1024) kl_prepare(const float* __restrict__ x, int n,
+                                                   const float* __restrict__ box9, float cutoff,
+                                                   GridS* __restrict__ grid, int* __restrict__ cellcnt,
+                                                   int* __restrict__ misc)
+{
+    __shared__ float red[6 * 32];
+    __shared__ GridS Gs;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float lo[3] = {0.f, 0.f, 0.f}, hi[3] = {0.f, 0.f, 0.f};
+    if (box9 == nullptr) {
+        float l0 = 3.0e38f, l1 = 3.0e38f, l2 = 3.0e38f, h0 = -3.0e38f, h1 = -3.0e38f, h2 = -3.0e38f;
+        for (int i = tid; i < n; i += 1024) {
+            const float px = x[3 * (size_t)i], py = x[3 * (size_t)i + 1], pz = x[3 * (size_t)i + 2];
+            l0 = fminf(l0, px); h0 = fmaxf(h0, px);
+            l1 = fminf(l1, py); h1 = fmaxf(h1, py);
+            l2 = fminf(l2, pz); h2 = fmaxf(h2, pz);
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            l0 = fminf(l0, __shfl_xor_sync(0xffffffffu, l0, d));
+            l1 = fminf(l1, __shfl_xor_sync(0xffffffffu, l1, d));
+            l2 = fminf(l2, __shfl_xor_sync(0xffffffffu, l2, d));
+            h0 = fmaxf(h0, __shfl_xor_sync(0xffffffffu, h0, d));
+            h1 = fmaxf(h1, __shfl_xor_sync(0xffffffffu, h1, d));
+            h2 = fmaxf(h2, __shfl_xor_sync(0xffffffffu, h2, d));
+        }
+        if (lane == 0) {
+            red[warp] = l0; red[32 + warp] = l1; red[64 + warp] = l2;
+            red[96 + warp] = h0; red[128 + warp] = h1; red[160 + warp] = h2;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < 32; w++) {
+                red[0] = fminf(red[0], red[w]); red[32] = fminf(red[32], red[32 + w]);
+                red[64] = fminf(red[64], red[64 + w]); red[96] = fmaxf(red[96], red[96 + w]);
+                red[128] = fmaxf(red[128], red[128 + w]); red[160] = fmaxf(red[160], red[160 + w]);
+            }
+            lo[0] = red[0]; lo[1] = red[32]; lo[2] = red[64];
+            hi[0] = red[96]; hi[1] = red[128]; hi[2] = red[160];
+        }
+    }
+    if (tid == 0) {
+        make_grid(Gs, box9, (double)cutoff, LG_MAXC, lo, hi);
+        *grid = Gs;
+        misc[0] = 0;
+        misc[1] = 0;
+    }
+    __syncthreads();
+    const int ncell = Gs.ncell;
+    for (int c = tid; c <= ncell; c += 1024) cellcnt[c] = 0;
+}
+
+__global__ void __launch_bounds__(256) kl_bin(const float* __restrict__ x, int n,
+                                              const GridS* __restrict__ grid, int* __restrict__ cellcnt,
+                                              int* __restrict__ atomcell, int* __restrict__ atomrank)
+{
+    const GridS G = *grid;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int c = cell_of(G, __ldg(&x[3 * (size_t)i]), __ldg(&x[3 * (size_t)i + 1]), __ldg(&x[3 * (size_t)i + 2]));
+        atomcell[i] = c;
+        atomrank[i] = atomicAdd(&cellcnt[c], 1);
+    }
+}
+
+__global__ void __launch_bounds__(1024) kl_scan(const GridS* __restrict__ grid, int n,
+                                                const int* __restrict__ cellcnt, int* __restrict__ cellptr,
+                                                int* __restrict__ occ, int* __restrict__ misc)
+{
+    __shared__ int s_sum[32], s_occ[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ncell = grid->ncell;
+    const int cpt = (ncell + 1023) / 1024;
+    const int c0 = min(tid * cpt, ncell), c1 = min(c0 + cpt, ncell);
+    int sum = 0, nocc = 0;
+    for (int c = c0; c < c1; c++) {
+        const int v = cellcnt[c];
+        sum += v;
+        nocc += (v != 0);
+    }
+    int isum = sum, iocc = nocc;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int a = __shfl_up_sync(0xffffffffu, isum, d);
+        const int b = __shfl_up_sync(0xffffffffu, iocc, d);
+        if (lane >= d) { isum += a; iocc += b; }
+    }
+    if (lane == 31) { s_sum[warp] = isum; s_occ[warp] = iocc; }
+    __syncthreads();
+    if (warp == 0) {
+        int a = s_sum[lane], b = s_occ[lane];
+        int ia = a, ib = b;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, ia, d);
+            const int v = __shfl_up_sync(0xffffffffu, ib, d);
+            if (lane >= d) { ia += u; ib += v; }
+        }
+        s_sum[lane] = ia - a;
+        s_occ[lane] = ib - b;
+        if (lane == 31) misc[0] = ib;
+    }
+    __syncthreads();
+    int run = isum - sum + s_sum[warp];
+    int ocur = iocc - nocc + s_occ[warp];
+    for (int c = c0; c < c1; c++) {
+        const int v = cellcnt[c];
+        cellptr[c] = run;
+        if (v) occ[ocur++] = c;
+        run += v;
+    }
+    if (tid == 0) cellptr[ncell] = n;
+}
+
+__global__ void __launch_bounds__(256) kl_scatter(const float* __restrict__ x, int n,
+                                                  const int* __restrict__ cellptr,
+                                                  const int* __restrict__ atomcell,
+                                                  const int* __restrict__ atomrank,
+                                                  float4* __restrict__ sorted)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int pos = cellptr[atomcell[i]] + atomrank[i];
+        sorted[pos] = make_float4(__ldg(&x[3 * (size_t)i]), __ldg(&x[3 * (size_t)i + 1]),
+                                  __ldg(&x[3 * (size_t)i + 2]), __int_as_float(i));
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void lg_pair_loop(const TaskParams& tp, const NlBox& B, const GridS& G,
+                                             const float4* sorted, const int* cellptr, const int* occ,
+                                             int n_occ, int* task_counter, int* wscr, StampSink& sink,
+                                             unsigned long long& n_tests)
+{
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        int k = 0;
+        if (lane == 0) k = atomicAdd(task_counter, 1);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k >= n_occ) break;
+        cell_task<MODE, int, StampSink>(tp, B, G, sorted, cellptr, __ldg(&occ[k]), wscr, sink, n_tests);
+    }
+}
+
+__global__ void __launch_bounds__(LG_PAIR_THREADS) kl_pairs(TaskParams tp, StampSink sink,
+                                                            const float* __restrict__ box9,
+                                                            const GridS* __restrict__ grid,
+                                                            const float4* __restrict__ sorted,
+                                                            const int* __restrict__ cellptr,
+                                                            const int* __restrict__ occ, int* misc)
+{
+    __shared__ int wscr_all[(LG_PAIR_THREADS / 32) * 64];
+    int* wscr = wscr_all + (threadIdx.x >> 5) * 64;
+    const GridS G = *grid;
+    const NlBox B = make_nlbox(box9);
+    const int n_occ = misc[0];
+    unsigned long long n_tests = 0;
+    if (B.mode == BOX_ORTHO)
+        lg_pair_loop<BOX_ORTHO>(tp, B, G, sorted, cellptr, occ, n_occ, &misc[1], wscr, sink, n_tests);
+    else if (B.mode == BOX_TRICLINIC)
+        lg_pair_loop<BOX_TRICLINIC>(tp, B, G, sorted, cellptr, occ, n_occ, &misc[1], wscr, sink, n_tests);
+    else
+        lg_pair_loop<BOX_NONE>(tp, B, G, sorted, cellptr, occ, n_occ, &misc[1], wscr, sink, n_tests);
+    if (tp.count_tests) {
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) n_tests += __shfl_xor_sync(0xffffffffu, n_tests, d);
+        if ((threadIdx.x & 31) == 0 && n_tests) atomicAdd(&tp.counters[3], n_tests);
+    }
+}
+
+#define LG_CK(call)                                                                  \
+    do {                                                                             \
+        cudaError_t e_ = (call);                                                     \
+        if (e_ != cudaSuccess) {                                                     \
+            err = std::string(#call) + " failed: " + cudaGetErrorString(e_);         \
+            return -2;                                                               \
+        }                                                                            \
+    } while (0)
+
+inline int large_run(const LargeJob& job, LargeScratch& S, int sm_count, cudaStream_t stream,
+                     std::string& err, int& launches)
+{
+    const int n = job.n;
+    if (S.cap_atoms < n) {
+        cudaFree(S.d_atomcell); cudaFree(S.d_atomrank); cudaFree(S.d_sorted);
+        S.d_atomcell = S.d_atomrank = nullptr; S.d_sorted = nullptr;
+        LG_CK(cudaMalloc(&S.d_atomcell, sizeof(int) * (size_t)n));
+        LG_CK(cudaMalloc(&S.d_atomrank, sizeof(int) * (size_t)n));
+        LG_CK(cudaMalloc(&S.d_sorted, sizeof(float4) * (size_t)n));
+        S.cap_atoms = n;
+    }
+    if (!S.d_grid) {
+        LG_CK(cudaMalloc(&S.d_grid, sizeof(GridS)));
+        LG_CK(cudaMalloc(&S.d_cellcnt, sizeof(int) * (size_t)(LG_MAXC + 1)));
+        LG_CK(cudaMalloc(&S.d_cellptr, sizeof(int) * (size_t)(LG_MAXC + 1)));
+        LG_CK(cudaMalloc(&S.d_occ, sizeof(int) * (size_t)LG_MAXC));
+        LG_CK(cudaMalloc(&S.d_misc, sizeof(int) * 4));
+    }
+    const bool want_res = (job.res_table != nullptr) || (job.res_keys != nullptr);
+    const size_t need_stamp = (size_t)job.n_res_c * (size_t)job.n_res_c;
+    if (want_res && S.stamp_elems < need_stamp) {
+        cudaFree(S.d_stamp);
+        S.d_stamp = nullptr;
+        LG_CK(cudaMalloc(&S.d_stamp, sizeof(unsigned int) * need_stamp));
+        LG_CK(cudaMemsetAsync(S.d_stamp, 0, sizeof(unsigned int) * need_stamp, stream));
+        S.stamp_elems = need_stamp;
+        S.seq = 0;
+    }
+    const int atom_blocks = std::min((n + 255) / 256, sm_count * 8);
+    for (long long f = 0; f < job.n_frames; f++) {
+        const float* x = job.xyz + (size_t)f * (size_t)n * 3;
+        const float* box9 = job.box ? job.box + (size_t)f * 9 : nullptr;
+        if (want_res) {
+            if (S.seq == 0xffffffffu) {
+                LG_CK(cudaMemsetAsync(S.d_stamp, 0, sizeof(unsigned int) * S.stamp_elems, stream));
+                S.seq = 0;
+            }
+            S.seq++;
+        }
+        kl_prepare<<<1, 1024, 0, stream>>>(x, n, box9, job.cutoff, S.d_grid, S.d_cellcnt, S.d_misc);
+        kl_bin<<<atom_blocks, 256, 0, stream>>>(x, n, S.d_grid, S.d_cellcnt, S.d_atomcell, S.d_atomrank);
+        kl_scan<<<1, 1024, 0, stream>>>(S.d_grid, n, S.d_cellcnt, S.d_cellptr, S.d_occ, S.d_misc);
+        kl_scatter<<<atom_blocks, 256, 0, stream>>>(x, n, S.d_cellptr, S.d_atomcell, S.d_atomrank, S.d_sorted);
+        TaskParams tp;
+        tp.meta = job.meta; tp.n = n; tp.n_ignored = job.n_ignored; tp.c2 = job.c2; tp.c2_hi = job.c2_hi;
+        tp.boundary_ulps = job.boundary_ulps; tp.atom_table = job.atom_table; tp.atom_keys = job.atom_keys;
+        tp.atom_cap = job.atom_cap; tp.counters = job.counters; tp.boundary = job.boundary;
+        tp.boundary_cap = job.boundary_cap; tp.frame_id = job.frame0 + f; tp.count_tests = job.count_tests;
+        StampSink sink;
+        sink.stamp = want_res ? S.d_stamp : nullptr;
+        sink.res_table = job.res_table; sink.res_keys = job.res_keys; sink.res_cap = job.res_cap;
+        sink.counters = job.counters; sink.seq = S.seq; sink.n_res_c = (unsigned)job.n_res_c;
+        sink.frame_id = job.frame0 + f;
+        kl_pairs<<<sm_count * 4, LG_PAIR_THREADS, 0, stream>>>(tp, sink, box9, S.d_grid, S.d_sorted,
+                                                               S.d_cellptr, S.d_occ, S.d_misc);
+        launches += 5;
+    }
+    LG_CK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace cmb

@@ -1,0 +1,396 @@
+// cmb_frames_small.cuh -- fused per-frame contact kernel for systems whose used
+// atoms fit in one CTA's shared memory (n_used <= 6144).
+//
+// Replaces, per frame (reference file:line under /root/reference/contact_map/):
+//   md.compute_neighborlist(used_traj, cutoff, frame)      contact_map.py:575
+//   the Python set algebra of ContactObject._contact_map   contact_map.py:582-607
+//   Counter.update / Counter += of ContactFrequency        contact_map.py:739-740
+//   per-frame pair sets of _build_contacts                 contact_trajectory.py:32-44
+//
+// One persistent CTA per frame slot (grid = SMs x resident CTAs, frame-strided):
+//   1. the frame's fp32 xyz (12*n bytes, contiguous in HBM) is pulled into shared
+//      memory with ONE 1-D TMA bulk copy (cp.async.bulk -> UBLKCP) signalled on an
+//      mbarrier; the copy of the NEXT frame is issued as soon as the scatter pass
+//      has consumed the buffer, so it overlaps the pair phase;
+//   2. atoms are binned into >= cutoff-wide cells of the (orthorhombic/triclinic/
+//      open) cell grid: shared-memory histogram, block scan, scatter into a
+//      cell-sorted float4 array {x, y, z, atom};
+//   3. one warp per occupied cell: the candidate atoms of the half-shell
+//      (neighbour cells with id >= own) are held in registers (4 per lane), the
+//      cell's own atoms are broadcast from shared memory, and every candidate pair
+//      is adjudicated with MDTraj's exact float32 arithmetic on the RAW
+//      coordinates (cmb_math.cuh);
+//   4. hits pass role + residue-exclusion tests and are (a) RED-added into the
+//      dense uint32 atom-pair table, (b) OR'd into a per-frame residue-pair bitmap
+//      in shared memory that is popcount-flushed into the residue table at frame
+//      end (per-frame set semantics), and/or (c) ballot-compacted into 64-bit
+//      (frame, a, b) keys for ContactTrajectory.
+#pragma once
+#include "cmb_cells.cuh"
+
+namespace cmb {
+
+constexpr int FS_THREADS = 512;
+constexpr int FS_WARPS = FS_THREADS / 32;
+constexpr int FS_APT = 12;                       // atoms per thread in the binning passes
+constexpr int FS_MAX_ATOMS = FS_THREADS * FS_APT;   // 6144
+constexpr int FS_HEADER_BYTES = 1024;
+
+struct FrameParams {
+    const float* xyz;            // [n_frames][n][3] fp32, device
+    const float* box;            // [n_frames][9] fp32 row vectors, device, or nullptr
+    long long n_frames;
+    long long frame0;            // id of frame 0 of this call (for emitted keys)
+    int n;                       // used atoms
+    const int2* meta;            // [n] {ekey, res_c | role << 30}
+    float cutoff;
+    float c2;                    // cutoff_f * cutoff_f
+    float c2_hi;                 // c2 advanced by `boundary_ulps` float steps (== c2 if off)
+    int boundary_ulps;
+    int n_ignored;
+    int n_res_c;                 // compact residue count (bitmap is n_res_c x n_res_c bits)
+    int maxc;                    // cell capacity of the shared-memory arrays
+    int bm_words;                // bitmap words
+    int bm_in_smem;
+    unsigned int* g_bitmap;      // [gridDim.x][bm_words] scratch when the bitmap is not in smem
+    unsigned int* atom_table;    // [n][n] uint32 (entry [lo][hi]) or nullptr
+    unsigned int* res_table;     // [n_res_c][n_res_c] uint32 or nullptr
+    unsigned long long* atom_keys;   // emitted (frame<<40 | lo<<20 | hi) or nullptr
+    long long atom_cap;
+    unsigned long long* res_keys;    // emitted (frame<<40 | rlo<<20 | rhi) or nullptr
+    long long res_cap;
+    unsigned long long* counters;    // [0] atom keys, [1] residue keys, [2] boundary records, [3] pair tests
+    float4* boundary;            // records {frame, lo, hi, d2} (ints bit-cast) or nullptr
+    long long boundary_cap;
+    int count_tests;             // accumulate executed pair tests into counters[3]
+};
+
+// ----- mbarrier / TMA bulk helpers (sm_90+ PTX; SASS: SYNCS / UBLKCP) -------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ----- shared-memory layout ------------------------------------------------------
+struct FsLayout {
+    int raw_off, sorted_off, cell_off, occ_off, bm_off, wscr_off, total;
+};
+
+__host__ __device__ inline int fs_align(int x, int a) { return (x + a - 1) / a * a; }
+
+__host__ __device__ inline FsLayout fs_layout(int n, int maxc, int bm_words_smem)
+{
+    FsLayout L;
+    int off = FS_HEADER_BYTES;
+    L.raw_off = off;
+    off += fs_align(12 * n + 32, 128);
+    L.sorted_off = off;
+    off += fs_align(16 * n, 128);
+    L.cell_off = off;
+    off += fs_align(2 * (maxc + 2), 128);
+    L.occ_off = off;
+    off += fs_align(2 * (maxc < n ? maxc : n) + 2, 128);
+    L.bm_off = off;
+    off += fs_align(4 * bm_words_smem, 128);
+    L.wscr_off = off;
+    off += FS_WARPS * 64 * 4;
+    L.total = off;
+    return L;
+}
+
+// ----- residue sink: per-frame bitmap (shared or global), flushed at frame end -----
+struct BitmapSink {
+    unsigned int* bitmap;
+    unsigned n_res_c;
+    __device__ __forceinline__ void residue(int rlo, int rhi)
+    {
+        const unsigned bit = (unsigned)rlo * n_res_c + (unsigned)rhi;
+        const unsigned msk = 1u << (bit & 31);
+        unsigned int* wp = &bitmap[bit >> 5];
+        if (!(*(volatile unsigned int*)wp & msk)) atomicOr(wp, msk);
+    }
+};
+
+template <int MODE>
+__device__ __forceinline__ void fs_pair_phase(const TaskParams& tp, const NlBox& B, const GridS& G,
+                                              const float4* sorted, const unsigned short* cellptr,
+                                              const unsigned short* occ, int n_occ, int* task_counter,
+                                              int* wscr, BitmapSink& sink, unsigned long long& n_tests)
+{
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        int k = 0;
+        if (lane == 0) k = atomicAdd(task_counter, 1);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k >= n_occ) break;
+        cell_task<MODE, unsigned short, BitmapSink>(tp, B, G, sorted, cellptr, (int)occ[k], wscr, sink, n_tests);
+    }
+}
+
+__global__ void __launch_bounds__(FS_THREADS, 1) k_frames_small(const FrameParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int n = p.n;
+    const FsLayout L = fs_layout(n, p.maxc, p.bm_in_smem ? p.bm_words : 0);
+
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem);
+    int* task_counter = reinterpret_cast<int*>(smem + 8);
+    int* n_occ_s = reinterpret_cast<int*>(smem + 12);
+    float* red = reinterpret_cast<float*>(smem + 64);                 // 6 * 32 floats
+    unsigned int* scan_s = reinterpret_cast<unsigned int*>(smem + 64);   // overlays `red`
+    GridS* Gs = reinterpret_cast<GridS*>(smem + 64 + 6 * 32 * 4);
+    unsigned char* raw = smem + L.raw_off;
+    float4* sorted = reinterpret_cast<float4*>(smem + L.sorted_off);
+    unsigned int* cell32 = reinterpret_cast<unsigned int*>(smem + L.cell_off);
+    unsigned short* cell16 = reinterpret_cast<unsigned short*>(smem + L.cell_off);
+    unsigned short* occ = reinterpret_cast<unsigned short*>(smem + L.occ_off);
+    unsigned int* bitmap = p.bm_in_smem ? reinterpret_cast<unsigned int*>(smem + L.bm_off)
+                                        : p.g_bitmap + (size_t)blockIdx.x * (size_t)p.bm_words;
+    int* wscr = reinterpret_cast<int*>(smem + L.wscr_off) + warp * 64;
+
+    if (tid == 0) {
+        mbar_init(mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int w = tid; w < p.bm_words; w += FS_THREADS) bitmap[w] = 0u;
+    __syncthreads();
+
+    unsigned long long n_tests = 0;
+    uint32_t parity = 0;
+    const long long stride = gridDim.x;
+    long long f = blockIdx.x;
+
+    // prologue: fetch this CTA's first frame
+    auto issue_load = [&](long long frame) {
+        const unsigned long long addr = (unsigned long long)(p.xyz + (size_t)frame * (size_t)n * 3);
+        const unsigned long long a0 = addr & ~15ull;
+        const uint32_t lead = (uint32_t)(addr - a0);
+        const uint32_t bytes = (lead + 12u * (uint32_t)n + 15u) & ~15u;
+        mbar_expect_tx(mbar, bytes);
+        tma_bulk_g2s(raw, reinterpret_cast<const void*>(a0), bytes, mbar);
+    };
+    if (tid == 0 && f < p.n_frames) issue_load(f);
+
+    for (; f < p.n_frames; f += stride) {
+        const float* box9 = p.box ? p.box + (size_t)f * 9 : nullptr;
+        const NlBox B = make_nlbox(box9);
+        const unsigned long long addr = (unsigned long long)(p.xyz + (size_t)f * (size_t)n * 3);
+        const float* xr = reinterpret_cast<const float*>(raw + (addr & 15ull));
+
+        mbar_wait(mbar, parity);
+        parity ^= 1u;
+
+        // ---- open boundaries: bounding box of the frame ---------------------------
+        float lo[3] = {0.f, 0.f, 0.f}, hi[3] = {0.f, 0.f, 0.f};
+        if (box9 == nullptr) {
+            float l0 = 3.0e38f, l1 = 3.0e38f, l2 = 3.0e38f, h0 = -3.0e38f, h1 = -3.0e38f, h2 = -3.0e38f;
+            for (int i = tid; i < n; i += FS_THREADS) {
+                const float x = xr[3 * i], y = xr[3 * i + 1], z = xr[3 * i + 2];
+                l0 = fminf(l0, x); h0 = fmaxf(h0, x);
+                l1 = fminf(l1, y); h1 = fmaxf(h1, y);
+                l2 = fminf(l2, z); h2 = fmaxf(h2, z);
+            }
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) {
+                l0 = fminf(l0, __shfl_xor_sync(0xffffffffu, l0, d));
+                l1 = fminf(l1, __shfl_xor_sync(0xffffffffu, l1, d));
+                l2 = fminf(l2, __shfl_xor_sync(0xffffffffu, l2, d));
+                h0 = fmaxf(h0, __shfl_xor_sync(0xffffffffu, h0, d));
+                h1 = fmaxf(h1, __shfl_xor_sync(0xffffffffu, h1, d));
+                h2 = fmaxf(h2, __shfl_xor_sync(0xffffffffu, h2, d));
+            }
+            if (lane == 0) {
+                red[warp] = l0; red[32 + warp] = l1; red[64 + warp] = l2;
+                red[96 + warp] = h0; red[128 + warp] = h1; red[160 + warp] = h2;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                for (int w = 1; w < FS_WARPS; w++) {
+                    red[0] = fminf(red[0], red[w]); red[32] = fminf(red[32], red[32 + w]);
+                    red[64] = fminf(red[64], red[64 + w]); red[96] = fmaxf(red[96], red[96 + w]);
+                    red[128] = fmaxf(red[128], red[128 + w]); red[160] = fmaxf(red[160], red[160 + w]);
+                }
+                lo[0] = red[0]; lo[1] = red[32]; lo[2] = red[64];
+                hi[0] = red[96]; hi[1] = red[128]; hi[2] = red[160];
+            }
+        }
+        if (tid == 0) {
+            make_grid(*Gs, box9, (double)p.cutoff, p.maxc, lo, hi);
+            *task_counter = 0;
+        }
+        __syncthreads();
+        const GridS G = *Gs;
+
+        // ---- pass A: histogram (u16 counters packed in u32 words) -----------------
+        for (int w = tid; w < (G.ncell + 3) / 2; w += FS_THREADS) cell32[w] = 0u;
+        __syncthreads();
+        int my_cell[FS_APT], my_rank[FS_APT];
+#pragma unroll
+        for (int k = 0; k < FS_APT; k++) {
+            const int i = tid + k * FS_THREADS;
+            my_cell[k] = -1; my_rank[k] = 0;
+            if (i < n) {
+                const int c = cell_of(G, xr[3 * i], xr[3 * i + 1], xr[3 * i + 2]);
+                const unsigned sh = (c & 1) * 16;
+                const unsigned old = atomicAdd(&cell32[c >> 1], 1u << sh);
+                my_cell[k] = c;
+                my_rank[k] = (int)((old >> sh) & 0xffffu);
+            }
+        }
+        __syncthreads();
+
+        // ---- pass B: exclusive scan over cells (+ occupied-cell list) --------------
+        {
+            const int cpt = (G.ncell + FS_THREADS - 1) / FS_THREADS;
+            const int c0 = tid * cpt;
+            const int c1 = min(c0 + cpt, G.ncell);
+            unsigned sum = 0, nocc = 0;
+            for (int c = c0; c < c1; c++) {
+                const unsigned v = cell16[c];
+                sum += v;
+                nocc += (v != 0);
+            }
+            unsigned packed = sum | (nocc << 16);
+            unsigned incl = packed;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += v;
+            }
+            __syncthreads();              // `red` (overlaid by scan_s) no longer needed
+            if (lane == 31) scan_s[warp] = incl;
+            __syncthreads();
+            if (warp == 0) {
+                unsigned v = lane < FS_WARPS ? scan_s[lane] : 0u;
+                unsigned iv = v;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const unsigned u = __shfl_up_sync(0xffffffffu, iv, d);
+                    if (lane >= d) iv += u;
+                }
+                if (lane < FS_WARPS) scan_s[lane] = iv - v;
+                if (lane == FS_WARPS - 1) *n_occ_s = (int)(iv >> 16);
+            }
+            __syncthreads();
+            const unsigned excl = incl - packed + scan_s[warp];
+            unsigned run = excl & 0xffffu, ocur = excl >> 16;
+            for (int c = c0; c < c1; c++) {
+                const unsigned v = cell16[c];
+                cell16[c] = (unsigned short)run;
+                if (v) occ[ocur++] = (unsigned short)c;
+                run += v;
+            }
+            if (tid == 0) cell16[G.ncell] = (unsigned short)n;
+        }
+        __syncthreads();
+
+        // ---- pass C: scatter into the cell-sorted float4 array -----------------------
+#pragma unroll
+        for (int k = 0; k < FS_APT; k++) {
+            const int i = tid + k * FS_THREADS;
+            if (i < n) {
+                const int pos = (int)cell16[my_cell[k]] + my_rank[k];
+                sorted[pos] = make_float4(xr[3 * i], xr[3 * i + 1], xr[3 * i + 2], __int_as_float(i));
+            }
+        }
+        __syncthreads();
+        // raw buffer is free: prefetch this CTA's next frame under the pair phase
+        if (tid == 0 && f + stride < p.n_frames) {
+            fence_proxy_async();
+            issue_load(f + stride);
+        }
+
+        // ---- pass D: pair phase, one warp per occupied cell ---------------------------
+        const int n_occ = *n_occ_s;
+        const long long frame_id = p.frame0 + f;
+        TaskParams tp;
+        tp.meta = p.meta; tp.n = n; tp.n_ignored = p.n_ignored; tp.c2 = p.c2; tp.c2_hi = p.c2_hi;
+        tp.boundary_ulps = p.boundary_ulps; tp.atom_table = p.atom_table; tp.atom_keys = p.atom_keys;
+        tp.atom_cap = p.atom_cap; tp.counters = p.counters; tp.boundary = p.boundary;
+        tp.boundary_cap = p.boundary_cap; tp.frame_id = frame_id; tp.count_tests = p.count_tests;
+        BitmapSink sink{bitmap, (unsigned)p.n_res_c};
+        if (B.mode == BOX_ORTHO)
+            fs_pair_phase<BOX_ORTHO>(tp, B, G, sorted, cell16, occ, n_occ, task_counter, wscr, sink, n_tests);
+        else if (B.mode == BOX_TRICLINIC)
+            fs_pair_phase<BOX_TRICLINIC>(tp, B, G, sorted, cell16, occ, n_occ, task_counter, wscr, sink, n_tests);
+        else
+            fs_pair_phase<BOX_NONE>(tp, B, G, sorted, cell16, occ, n_occ, task_counter, wscr, sink, n_tests);
+        __syncthreads();
+
+        // ---- pass E: flush the per-frame residue bitmap ------------------------------
+        for (int w = tid; w < p.bm_words; w += FS_THREADS) {
+            unsigned v = bitmap[w];
+            if (v) {
+                bitmap[w] = 0u;
+                if (p.res_table != nullptr) {
+                    unsigned t = v;
+                    while (t) {
+                        const int b = __ffs(t) - 1;
+                        t &= t - 1;
+                        atomicAdd(&p.res_table[(size_t)w * 32 + b], 1u);
+                    }
+                }
+                if (p.res_keys != nullptr) {
+                    const unsigned long long wbase = atomicAdd(&p.counters[1], (unsigned long long)__popc(v));
+                    unsigned t = v;
+                    unsigned long long o = 0;
+                    while (t) {
+                        const int b = __ffs(t) - 1;
+                        t &= t - 1;
+                        const unsigned bit = (unsigned)w * 32u + (unsigned)b;
+                        const unsigned rlo = bit / (unsigned)p.n_res_c, rhi = bit % (unsigned)p.n_res_c;
+                        if ((long long)(wbase + o) < p.res_cap)
+                            p.res_keys[wbase + o] = ((unsigned long long)frame_id << 40) |
+                                                    ((unsigned long long)rlo << 20) | (unsigned long long)rhi;
+                        o++;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (p.count_tests) {
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) n_tests += __shfl_xor_sync(0xffffffffu, n_tests, d);
+        if (lane == 0 && n_tests) atomicAdd(&p.counters[3], n_tests);
+    }
+}
+
+}  // namespace cmb

@@ -1,0 +1,325 @@
+"""Device engine: thin Python layer over the C ABI (``include/cmb200.h``).
+
+PyTorch is used only for device memory, streams and (in ``parallel.py``)
+``torch.distributed``; every computation is a hand-written sm_100a kernel behind
+``libcmb200.so``.  There is no CPU fallback: constructing an engine without a
+CUDA device raises RuntimeError.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def _ptr(t):
+    """Raw address of a torch tensor / numpy array / None."""
+    if t is None:
+        return None
+    if isinstance(t, torch.Tensor):
+        return ctypes.c_void_p(t.data_ptr())
+    return ctypes.c_void_p(t.ctypes.data)
+
+
+def _stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class ContactEngine(object):
+    """One engine per (process, device).  Not thread safe."""
+
+    def __init__(self, device=None):
+        if not torch.cuda.is_available():
+            raise EngineError("contact_map_b200 needs a CUDA device (sm_100a); there is no CPU "
+                              "fallback")
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device("cuda", int(device) if not isinstance(device, torch.device)
+                                   else device.index or 0)
+        self._L = _lib.lib()
+        handle = ctypes.c_void_p()
+        rc = self._L.cmb_ctx_create(self.device.index, ctypes.byref(handle))
+        if rc != 0:
+            raise EngineError("cmb_ctx_create failed (%d): %s"
+                              % (rc, self._L.cmb_last_error(None).decode()))
+        self._ctx = handle
+        self.n_used = 0
+        self.n_res_c = 0
+        self.residue_map = None
+        self._keepalive = []
+
+    # ------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._L.cmb_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:     # interpreter shutdown
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise EngineError("%s failed (%d): %s"
+                              % (what, rc, self._L.cmb_last_error(self._ctx).decode()))
+
+    # ------------------------------------------------------------------
+    def set_option(self, name, value):
+        self._check(self._L.cmb_set_option(self._ctx, name.encode(), int(value)), "cmb_set_option")
+
+    def get_stat(self, name):
+        out = ctypes.c_int64(0)
+        self._check(self._L.cmb_get_stat(self._ctx, name.encode(), ctypes.byref(out)), "cmb_get_stat")
+        return int(out.value)
+
+    def set_system(self, atom_res, atom_chain, role, cutoff, n_ignored):
+        atom_res = np.ascontiguousarray(atom_res, dtype=np.int32)
+        atom_chain = np.ascontiguousarray(atom_chain, dtype=np.int32)
+        role = np.ascontiguousarray(role, dtype=np.uint8)
+        n = atom_res.shape[0]
+        if atom_chain.shape[0] != n or role.shape[0] != n:
+            raise ValueError("system arrays must have the same length")
+        self._check(self._L.cmb_set_system(self._ctx, n, _ptr(atom_res), _ptr(atom_chain),
+                                           _ptr(role), float(cutoff), int(n_ignored)),
+                    "cmb_set_system")
+        self.n_used = n
+        self.n_res_c = int(self._L.cmb_n_residues(self._ctx))
+        rmap = np.empty(self.n_res_c, dtype=np.int32)
+        self._check(self._L.cmb_residue_map(self._ctx, _ptr(rmap)), "cmb_residue_map")
+        self.residue_map = rmap
+        self.path_kind = int(self._L.cmb_path_kind(self._ctx))
+
+    def new_tables(self):
+        """Zeroed device count tables (int32 views of the uint32 tables of the ABI)."""
+        a, r = ctypes.c_int64(0), ctypes.c_int64(0)
+        self._check(self._L.cmb_table_sizes(self._ctx, ctypes.byref(a), ctypes.byref(r)),
+                    "cmb_table_sizes")
+        atom = torch.zeros(int(a.value), dtype=torch.int32, device=self.device)
+        res = torch.zeros(int(r.value), dtype=torch.int32, device=self.device)
+        return atom, res
+
+    # ------------------------------------------------------------------
+    def _dev_inputs(self, xyz, box):
+        if not (isinstance(xyz, torch.Tensor) and xyz.is_cuda):
+            raise TypeError("device path needs CUDA tensors")
+        if xyz.dtype != torch.float32 or not xyz.is_contiguous():
+            raise TypeError("xyz must be a contiguous float32 tensor")
+        if xyz.dim() != 3 or xyz.shape[1] != self.n_used or xyz.shape[2] != 3:
+            raise ValueError("xyz must have shape [n_frames, %d, 3]" % self.n_used)
+        if box is not None:
+            if box.dtype != torch.float32 or not box.is_contiguous() or not box.is_cuda:
+                raise TypeError("box must be a contiguous float32 CUDA tensor")
+            if box.shape[0] != xyz.shape[0] or box.numel() != xyz.shape[0] * 9:
+                raise ValueError("box must have shape [n_frames, 3, 3]")
+        return xyz, box
+
+    def accumulate(self, xyz, box, atom_table, res_table):
+        """Add the frames of a DEVICE trajectory into the tables (asynchronous)."""
+        xyz, box = self._dev_inputs(xyz, box)
+        with torch.cuda.device(self.device):
+            self._check(self._L.cmb_accumulate(self._ctx, _ptr(xyz), _ptr(box), xyz.shape[0],
+                                               _ptr(atom_table), _ptr(res_table),
+                                               _stream_ptr(self.device)), "cmb_accumulate")
+
+    def accumulate_host(self, xyz, box, atom_table, res_table, chunk_frames=0):
+        """Add the frames of a HOST trajectory (numpy or CPU tensor; pinned is fastest)."""
+        xyz_np = xyz.numpy() if isinstance(xyz, torch.Tensor) else xyz
+        box_np = box.numpy() if isinstance(box, torch.Tensor) else box
+        if xyz_np.dtype != np.float32 or not xyz_np.flags["C_CONTIGUOUS"]:
+            raise TypeError("xyz must be C-contiguous float32")
+        if xyz_np.ndim != 3 or xyz_np.shape[1] != self.n_used or xyz_np.shape[2] != 3:
+            raise ValueError("xyz must have shape [n_frames, %d, 3]" % self.n_used)
+        if box_np is not None:
+            if box_np.dtype != np.float32 or not box_np.flags["C_CONTIGUOUS"]:
+                raise TypeError("box must be C-contiguous float32")
+            if box_np.size != xyz_np.shape[0] * 9:
+                raise ValueError("box must have shape [n_frames, 3, 3]")
+        torch.cuda.current_stream(self.device).synchronize()   # tables may still be zero-filling
+        self._check(self._L.cmb_accumulate_host(self._ctx, _ptr(xyz_np), _ptr(box_np),
+                                                xyz_np.shape[0], int(chunk_frames),
+                                                _ptr(atom_table), _ptr(res_table)),
+                    "cmb_accumulate_host")
+
+    def export_nonzero(self, table):
+        """(flat index int64[], count uint32[]) of the non-zero entries, sorted by index."""
+        nnz = int(torch.count_nonzero(table).item())
+        if nnz == 0:
+            return np.empty(0, dtype=np.int64), np.empty(0, dtype=np.uint32)
+        idx = torch.empty(nnz, dtype=torch.int64, device=self.device)
+        cnt = torch.empty(nnz, dtype=torch.int32, device=self.device)
+        n_out = torch.zeros(1, dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self._L.cmb_export_nonzero(self._ctx, _ptr(table), table.numel(), nnz,
+                                                   _ptr(idx), _ptr(cnt), _ptr(n_out),
+                                                   _stream_ptr(self.device)), "cmb_export_nonzero")
+        got = int(n_out.item())
+        if got != nnz:
+            raise EngineError("export found %d entries, expected %d" % (got, nnz))
+        idx_h = idx.cpu().numpy()
+        cnt_h = cnt.cpu().numpy().view(np.uint32)
+        order = np.argsort(idx_h, kind="stable")
+        return idx_h[order], cnt_h[order]
+
+    def frame_contacts(self, xyz, box, frame0=0, atom_table=None, res_table=None,
+                       want_atoms=True, want_residues=True, cap_hint=None):
+        """Per-frame contact keys of a DEVICE trajectory.
+
+        Returns (atom_keys, res_keys): sorted uint64 numpy arrays with
+        key = (frame0 + f) << 40 | lo << 20 | hi.
+        """
+        xyz, box = self._dev_inputs(xyz, box)
+        n_frames = xyz.shape[0]
+        cap_a = int(cap_hint or max(1024, n_frames * 64)) if want_atoms else 0
+        cap_r = int(cap_hint or max(1024, n_frames * 64)) if want_residues else 0
+        if atom_table is not None or res_table is not None:
+            # tables must only be touched once: size the key buffers with a dry run first
+            counts = self._frame_contacts_once(xyz, box, frame0, None, 0, None, 0, None, None,
+                                               count_only=(want_atoms, want_residues))
+            cap_a, cap_r = (int(counts[0]) if want_atoms else 0), (int(counts[1]) if want_residues else 0)
+        while True:
+            ak = torch.empty(max(cap_a, 1), dtype=torch.int64, device=self.device) if want_atoms else None
+            rk = torch.empty(max(cap_r, 1), dtype=torch.int64, device=self.device) if want_residues else None
+            counts = self._frame_contacts_once(xyz, box, frame0, ak, cap_a, rk, cap_r,
+                                               atom_table, res_table)
+            na, nr = int(counts[0]), int(counts[1])
+            if (not want_atoms or na <= cap_a) and (not want_residues or nr <= cap_r):
+                break
+            if atom_table is not None or res_table is not None:
+                raise EngineError("key buffers overflowed after sizing pass")
+            cap_a, cap_r = (max(cap_a, na) if want_atoms else 0), (max(cap_r, nr) if want_residues else 0)
+        out = []
+        for keys, n_keys in ((ak, na), (rk, nr)):
+            if keys is None:
+                out.append(None)
+                continue
+            keys = keys[:n_keys]
+            if n_keys > 1:
+                with torch.cuda.device(self.device):
+                    self._check(self._L.cmb_sort_keys(self._ctx, _ptr(keys), n_keys,
+                                                      _stream_ptr(self.device)), "cmb_sort_keys")
+            out.append(keys.cpu().numpy().view(np.uint64))
+        return out[0], out[1]
+
+    def _frame_contacts_once(self, xyz, box, frame0, ak, cap_a, rk, cap_r, atom_table, res_table,
+                             count_only=None):
+        counts = torch.zeros(4, dtype=torch.int64, device=self.device)
+        if count_only is not None:
+            # capacity 0 with a non-NULL pointer: keys are counted but never written
+            dummy = torch.empty(1, dtype=torch.int64, device=self.device)
+            ak = dummy if count_only[0] else None
+            rk = dummy if count_only[1] else None
+            cap_a = cap_r = 0
+        with torch.cuda.device(self.device):
+            self._check(self._L.cmb_frame_contacts(self._ctx, _ptr(xyz), _ptr(box), xyz.shape[0],
+                                                   int(frame0), _ptr(ak), int(cap_a), _ptr(rk),
+                                                   int(cap_r), _ptr(counts), _ptr(atom_table),
+                                                   _ptr(res_table), _stream_ptr(self.device)),
+                        "cmb_frame_contacts")
+        return counts.cpu().numpy()
+
+    def boundary_pairs(self, xyz, box, ulps=1, frame0=0, cap=1 << 16):
+        """Eligible pairs whose d2 is within `ulps` float steps of cutoff^2.
+
+        Returns a structured numpy array with fields frame, a, b (int32) and d2 (float32).
+        """
+        xyz, box = self._dev_inputs(xyz, box)
+        dt = np.dtype([("frame", np.int32), ("a", np.int32), ("b", np.int32), ("d2", np.float32)])
+        while True:
+            rec = torch.zeros(cap * 4, dtype=torch.int32, device=self.device)
+            n_out = torch.zeros(1, dtype=torch.int64, device=self.device)
+            with torch.cuda.device(self.device):
+                self._check(self._L.cmb_boundary_pairs(self._ctx, _ptr(xyz), _ptr(box), xyz.shape[0],
+                                                       int(frame0), int(ulps), _ptr(rec), cap,
+                                                       _ptr(n_out), _stream_ptr(self.device)),
+                            "cmb_boundary_pairs")
+            n = int(n_out.item())
+            if n <= cap:
+                break
+            cap = n
+        out = rec.cpu().numpy()[:n * 4].view(dt)
+        return np.sort(out, order=["frame", "a", "b"])
+
+    def gather_atoms(self, xyz_full, used):
+        """Device ``_atom_slice``: [F, n_total, 3] -> [F, len(used), 3]."""
+        if xyz_full.dtype != torch.float32 or not xyz_full.is_contiguous() or not xyz_full.is_cuda:
+            raise TypeError("xyz_full must be a contiguous float32 CUDA tensor")
+        used_t = torch.as_tensor(np.ascontiguousarray(used, dtype=np.int32), device=self.device)
+        out = torch.empty((xyz_full.shape[0], used_t.numel(), 3), dtype=torch.float32,
+                          device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self._L.cmb_gather_atoms(self._ctx, _ptr(xyz_full), xyz_full.shape[0],
+                                                 xyz_full.shape[1], _ptr(used_t), used_t.numel(),
+                                                 _ptr(out), _stream_ptr(self.device)),
+                        "cmb_gather_atoms")
+        return out
+
+    def min_dist(self, xyz, box, query, haystack, orthogonal):
+        """Per-frame minimum distance and first arg-min pair index (query-major product)."""
+        if xyz.dtype != torch.float32 or not xyz.is_contiguous() or not xyz.is_cuda:
+            raise TypeError("xyz must be a contiguous float32 CUDA tensor")
+        q = torch.as_tensor(np.ascontiguousarray(query, dtype=np.int32), device=self.device)
+        h = torch.as_tensor(np.ascontiguousarray(haystack, dtype=np.int32), device=self.device)
+        n_frames, n_atoms = xyz.shape[0], xyz.shape[1]
+        dmin = torch.empty(n_frames, dtype=torch.float32, device=self.device)
+        darg = torch.empty(n_frames, dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self._L.cmb_min_dist(self._ctx, _ptr(xyz), _ptr(box), n_frames, n_atoms,
+                                             _ptr(q), q.numel(), _ptr(h), h.numel(),
+                                             int(bool(orthogonal)), _ptr(dmin), _ptr(darg),
+                                             _stream_ptr(self.device)), "cmb_min_dist")
+        return dmin, darg
+
+    def nearest(self, xyz_frame, box9, cutoff, orthogonal, excl_mode, atom_res=None,
+                excl_ptr=None, excl_idx=None):
+        n_atoms = xyz_frame.shape[0]
+        nearest = torch.empty(n_atoms, dtype=torch.int32, device=self.device)
+        dist = torch.empty(n_atoms, dtype=torch.float32, device=self.device)
+        keep = []
+        def dev(a, dtype):
+            if a is None:
+                return None
+            t = torch.as_tensor(np.ascontiguousarray(a, dtype=dtype), device=self.device)
+            keep.append(t)
+            return t
+        res_t, ptr_t, idx_t = dev(atom_res, np.int32), dev(excl_ptr, np.int64), dev(excl_idx, np.int32)
+        with torch.cuda.device(self.device):
+            self._check(self._L.cmb_nearest(self._ctx, _ptr(xyz_frame), _ptr(box9), n_atoms,
+                                            float(cutoff), int(bool(orthogonal)), int(excl_mode),
+                                            _ptr(res_t), _ptr(ptr_t), _ptr(idx_t), _ptr(nearest),
+                                            _ptr(dist), _stream_ptr(self.device)), "cmb_nearest")
+        torch.cuda.current_stream(self.device).synchronize()
+        return nearest, dist
+
+    def synth_frames(self, base, groups, box9, seed, amplitude, image_shifts, frame0, n_frames):
+        """Device synthetic generator; bit-identical to ``synth.make_frames``."""
+        n_atoms = base.shape[0]
+        out = torch.empty((n_frames, n_atoms, 3), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self._L.cmb_synth_frames(self._ctx, _ptr(base), _ptr(groups), n_atoms,
+                                                 _ptr(box9), int(seed), float(amplitude),
+                                                 int(bool(image_shifts)), int(frame0), int(n_frames),
+                                                 _ptr(out), _stream_ptr(self.device)),
+                        "cmb_synth_frames")
+        return out
+
+
+_ENGINES = {}
+
+
+def get_engine(device=None):
+    """Process-wide engine cache (one context per device)."""
+    if not torch.cuda.is_available():
+        raise EngineError("contact_map_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    if device is None:
+        device = torch.cuda.current_device()
+    key = int(device.index if isinstance(device, torch.device) else device)
+    if key not in _ENGINES:
+        _ENGINES[key] = ContactEngine(key)
+    return _ENGINES[key]

@@ -1,0 +1,165 @@
+/*
+ * cmb200.h -- C ABI of libcmb200.so, the B200 (sm_100a) contact-map engine.
+ *
+ * Plain pointers and sizes only; no torch / C++ types.  Device pointers are raw
+ * CUDA device addresses (e.g. torch.Tensor.data_ptr()); `stream` is a
+ * cudaStream_t passed as void* (0 = default stream).  All functions return 0 on
+ * success or a negative error code; cmb_last_error() gives the message.  The
+ * library never exits/aborts and has no CPU fallback: without a CUDA device every
+ * compute entry point fails with CMB_ERR_CUDA.
+ *
+ * The reference (dwhswenson/contact_map) has no FFI of its own: its only native
+ * boundary is MDTraj's Cython API, and its extension hooks are the two private
+ * methods its Dask runner overrides.  Each entry point below names the reference
+ * interface (file:line under /root/reference/contact_map/) it replaces.
+ */
+#ifndef CMB200_H
+#define CMB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CMB_OK 0
+#define CMB_ERR_ARG (-1)      /* bad argument */
+#define CMB_ERR_CUDA (-2)     /* CUDA runtime error (message has the detail) */
+#define CMB_ERR_STATE (-3)    /* call order violated (e.g. no system set) */
+#define CMB_ERR_LIMIT (-4)    /* system exceeds what this build supports */
+
+typedef struct cmb_ctx cmb_ctx;
+
+int cmb_version(void);
+const char* cmb_last_error(const cmb_ctx* ctx);   /* ctx may be NULL: last create error */
+
+/* One context per (process, device); not thread safe. */
+int cmb_ctx_create(int device, cmb_ctx** out);
+void cmb_ctx_destroy(cmb_ctx* ctx);
+
+/*
+ * Describe the system (host pointers, copied).  Replaces the per-object set-up of
+ * ContactObject.__init__ (contact_map.py:120-150), residue_neighborhood /
+ * _residue_ignore_atom_idxs (contact_map.py:41-60,442-461) and the indexer tables
+ * (atom_indexer.py:32-106) -- all collapsed into per-used-atom arrays:
+ *   atom_res[i]    global residue index of used atom i
+ *   atom_chain[i]  chain index of that residue
+ *   role[i]        bit0 = in query, bit1 = in haystack
+ * A pair {a,b} is eligible iff (a in Q and b in H) or (b in Q and a in H), and not
+ * (chain equal and |res_a - res_b| <= n_ignored).  cutoff is narrowed to float
+ * exactly as MDTraj does.  n_ignored must be >= 0.
+ */
+int cmb_set_system(cmb_ctx* ctx, int n_used, const int32_t* atom_res, const int32_t* atom_chain,
+                   const uint8_t* role, double cutoff, int n_ignored);
+
+/* Number of distinct residues among the used atoms (R_c) and their global indices. */
+int cmb_n_residues(const cmb_ctx* ctx);
+int cmb_residue_map(const cmb_ctx* ctx, int32_t* out_global_res /* [R_c] */);
+/* Table sizes in uint32 elements: atoms n_used*n_used (entry [lo*n+hi], lo<hi used
+ * indices), residues R_c*R_c (entry [rlo*R_c+rhi], compact residue ids). */
+int cmb_table_sizes(const cmb_ctx* ctx, int64_t* atom_elems, int64_t* res_elems);
+/* 0 = fused shared-memory path (n_used <= 6144), 1 = global-memory cell path. */
+int cmb_path_kind(const cmb_ctx* ctx);
+
+/*
+ * ContactFrequency._build_contact_map (contact_map.py:717-744): add n_frames frames
+ * into caller-owned DEVICE tables (uint32, zero-initialised by the caller).
+ *   d_xyz  [n_frames][n_used][3] fp32 (already sliced to the used atoms, see
+ *          cmb_gather_atoms);  d_box [n_frames][9] fp32 row vectors, or NULL for a
+ *          trajectory without unit cell.
+ * Asynchronous on `stream`.
+ */
+int cmb_accumulate(cmb_ctx* ctx, const float* d_xyz, const float* d_box, int64_t n_frames,
+                   uint32_t* d_atom_table, uint32_t* d_res_table, void* stream);
+
+/*
+ * Same, with HOST coordinates (pinned memory recommended): frames are staged
+ * through two device buffers, host->device copies overlapping the kernels.
+ * chunk_frames <= 0 picks a chunk of about 32 MiB.  Synchronous.
+ */
+int cmb_accumulate_host(cmb_ctx* ctx, const float* h_xyz, const float* h_box, int64_t n_frames,
+                        int64_t chunk_frames, uint32_t* d_atom_table, uint32_t* d_res_table);
+
+/*
+ * contact_trajectory._build_contacts (contact_trajectory.py:7-44): per-frame contact
+ * sets as unordered 64-bit keys  (frame0+f) << 40 | lo << 20 | hi  (used-atom
+ * indices for atoms, compact residue ids for residues).  d_counts[0]/[1] (device
+ * uint64, zeroed by the caller) receive the number of atom / residue keys produced;
+ * keys beyond the capacities are dropped (the caller retries with larger buffers).
+ * Either key buffer may be NULL.  Optionally also accumulates into tables (may be NULL).
+ */
+int cmb_frame_contacts(cmb_ctx* ctx, const float* d_xyz, const float* d_box, int64_t n_frames,
+                       int64_t frame0, uint64_t* d_atom_keys, int64_t atom_cap,
+                       uint64_t* d_res_keys, int64_t res_cap, uint64_t* d_counts,
+                       uint32_t* d_atom_table, uint32_t* d_res_table, void* stream);
+
+/* In-place ascending radix sort of 64-bit keys (frame-major, then lo, then hi). */
+int cmb_sort_keys(cmb_ctx* ctx, uint64_t* d_keys, int64_t n, void* stream);
+
+/*
+ * Sparse export of a count table: flat indices and counts of the non-zero entries
+ * (unordered).  *d_n (device uint64, zeroed by the caller) receives the number found;
+ * entries beyond cap are dropped.  Replaces the Counter objects of
+ * contact_map.py:724-744 as the result container.
+ */
+int cmb_export_nonzero(cmb_ctx* ctx, const uint32_t* d_table, int64_t n_elems, int64_t cap,
+                       int64_t* d_idx, uint32_t* d_cnt, uint64_t* d_n, void* stream);
+
+/*
+ * north_star: "any pair within 1 ulp of the cutoff enumerated and reported".
+ * Records {frame, lo, hi, d2} (int32,int32,int32,float32 = 16 bytes) of eligible
+ * pairs whose d2 is within `ulps` float steps of cutoff^2.
+ */
+int cmb_boundary_pairs(cmb_ctx* ctx, const float* d_xyz, const float* d_box, int64_t n_frames,
+                       int64_t frame0, int ulps, void* d_records, int64_t cap, uint64_t* d_n,
+                       void* stream);
+
+/* Executed candidate-pair tests of the last accumulate / frame_contacts call when
+ * enabled with cmb_set_option(ctx, "count_tests", 1) (bench metric; synchronises). */
+int cmb_set_option(cmb_ctx* ctx, const char* name, int64_t value);
+int cmb_get_stat(cmb_ctx* ctx, const char* name, int64_t* value);
+
+/*
+ * _atom_slice (atom_indexer.py:5-22): out[f][i][:] = xyz[f][used[i]][:] on device.
+ */
+int cmb_gather_atoms(cmb_ctx* ctx, const float* d_xyz_full, int64_t n_frames, int n_total,
+                     const int32_t* d_used, int n_used, float* d_out, void* stream);
+
+/*
+ * MinimumDistanceCounter._compute_from_atom_pairs (min_dist.py:142-168) for the
+ * query-major product query x haystack (min_dist.py:138): per frame the minimum
+ * float32 distance (compute_distances arithmetic) and the FIRST pair index
+ * (q_pos * n_h + h_pos) attaining it.  d_xyz is the FULL trajectory
+ * [n_frames][n_atoms][3]; orthogonal = np.allclose(unitcell_angles, 90).
+ */
+int cmb_min_dist(cmb_ctx* ctx, const float* d_xyz, const float* d_box, int64_t n_frames,
+                 int n_atoms, const int32_t* d_query, int n_q, const int32_t* d_haystack, int n_h,
+                 int orthogonal, float* d_min, int64_t* d_arg, void* stream);
+
+/*
+ * NearestAtoms._calculate_nearest (min_dist.py:47-70) for one frame: for every atom
+ * the nearest allowed neighbour within the cutoff (neighbour-list arithmetic for the
+ * cutoff test, compute_distances arithmetic for the value; ties -> lower index).
+ * excl_mode 0: only the atom itself is excluded (excluded == {});
+ *           1: atoms of the same residue (excluded is None), d_atom_res[n_atoms];
+ *           2: CSR lists d_excl_ptr[n_atoms+1] / d_excl_idx.
+ * d_nearest[i] = -1 where no allowed neighbour exists.
+ */
+int cmb_nearest(cmb_ctx* ctx, const float* d_xyz_frame, const float* d_box9, int n_atoms,
+                double cutoff, int orthogonal, int excl_mode, const int32_t* d_atom_res,
+                const int64_t* d_excl_ptr, const int32_t* d_excl_idx, int32_t* d_nearest,
+                float* d_dist, void* stream);
+
+/*
+ * Bit-reproducible synthetic trajectory generator, device side:
+ * x = base + A * (2u - 1) + image shift per residue, u = splitmix64 hash.  Matches
+ * contact_map_b200/synth.py bit for bit.
+ */
+int cmb_synth_frames(cmb_ctx* ctx, const float* d_base, const int32_t* d_atom_group, int n_atoms,
+                     const float* d_box9, uint64_t seed, float amplitude, int image_shifts,
+                     int64_t frame0, int64_t n_frames, float* d_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMB200_H */
