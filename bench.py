@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""Benchmark of the contact-map hot path on B200 (BASELINE.json metric / config).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # reference CPU path (oracle port)
+
+Workload (config.workload): "S1" = BASELINE.json configs[1], synthetic KRAS-sized protein,
+2700 heavy atoms, 10 000 frames, orthorhombic PBC, query = haystack = all atoms, cutoff
+0.45 nm, n_neighbors_ignored = 2.  A "step" is one full ContactFrequency pass over the 10 000
+frames: zero the count tables, bin + screen + accumulate every frame, (N > 1: one NCCL
+all-reduce of the tables), sparse export of both tables.  Multi-GPU runs shard by frame with
+fixed per-GPU work (weak scaling): every rank owns 10 000 different frames.
+
+`value` is measured with CUDA events, inputs resident in HBM (generated on device by the
+bit-reproducible generator).  `e2e` goes through the public API
+(`ChunkedContactFrequency(trajectory)`) with the coordinates in PINNED HOST memory: host->device
+copies, kernels, reduce, export and the device->host read of the sparse result are all inside
+the timed region.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "frames/sec for ContactFrequency @0.45 nm"
+N_FRAMES = 10000
+CUTOFF = 0.45
+N_IGNORED = 2
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=N_FRAMES, help="frames per GPU (default 10000)")
+    ap.add_argument("--cpu-frames", type=int, default=0, help="frames of the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args, world):
+    return {
+        "workload": "S1: synthetic KRAS-sized protein, 2700 heavy atoms (270 residues x 10), "
+                    "%d frames per GPU, orthorhombic PBC 7.0x7.5x8.0 nm, query=haystack=all, "
+                    "cutoff 0.45 nm, n_neighbors_ignored 2 (BASELINE.json configs[1])" % args.frames,
+        "frames_per_gpu": args.frames,
+        "n_atoms": 2700,
+        "cutoff_nm": CUTOFF,
+        "n_neighbors_ignored": N_IGNORED,
+        "sharding": "frames (rank r owns frames [r*F, (r+1)*F)), one NCCL all-reduce of the count tables"
+                    if world > 1 else "single GPU",
+        "l2": "inputs larger than L2: %.0f MB of coordinates per pass vs 126 MB L2" % (args.frames * 2700 * 12 / 1e6),
+    }
+
+
+# -------------------------------------------------------------------------------------
+# clocks
+# -------------------------------------------------------------------------------------
+class ClockSampler(object):
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.lines = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.FIELDS,
+                 "--format=csv,noheader,nounits", "-lms", "20"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[5:9]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# -------------------------------------------------------------------------------------
+# CPU legs (the oracle is the reference's CPU path restated; this is the one place bench.py
+# may execute oracle/)
+# -------------------------------------------------------------------------------------
+def cpu_reference_rate(system, n_frames, n_workers):
+    """frames/s of the reference CPU path (oracle port) on `n_frames` frames of the workload.
+    n_workers == 1: the serial ContactFrequency loop; > 1: the Dask-equivalent runner
+    (default_slices -> map over a process pool -> Counter reduce)."""
+    from oracle import refpath
+    top = system.topology
+    xyz = system.frames(0, n_frames)
+    box = np.broadcast_to(system.box, (n_frames, 3, 3)).copy()
+    everyone = list(range(top.n_atoms))
+    args = (xyz, box, top.atom_residue, top.residue_chain, everyone, everyone, CUTOFF, N_IGNORED)
+    if n_workers == 1:
+        t0 = time.perf_counter()
+        atoms, residues = refpath.contact_frequency(*args)
+        dt = time.perf_counter() - t0
+    else:
+        import multiprocessing as mp
+        os.environ["OMP_NUM_THREADS"] = "1"
+        with mp.get_context("fork").Pool(n_workers) as pool:
+            pool.map(abs, range(n_workers))      # spin the workers up outside the timed region
+            t0 = time.perf_counter()
+            atoms, residues = refpath.chunked_contact_frequency(*args, n_workers=n_workers, pool=pool)
+            dt = time.perf_counter() - t0
+    return n_frames / dt, dt, len(atoms), len(residues)
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU implementation of the path (oracle port; MDTraj and
+    dask are not installable here) with all host cores, on a bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from contact_map_b200 import synth
+    from oracle import clib
+    system = synth.kras_like()
+    cores = len(os.sched_getaffinity(0))
+    workers = max(1, cores)
+    frames = args.cpu_frames or max(workers * 4, 32)
+    rates = []
+    for _ in range(args.warmup):
+        cpu_reference_rate(system, max(workers, 8), workers)
+    t_total = 0.0
+    for _ in range(args.steps):
+        rate, dt, _, _ = cpu_reference_rate(system, frames, workers)
+        rates.append(rate)
+        t_total += dt
+    value = frames * args.steps / t_total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": {
+            "value": value, "unit": "frames/s", "cores": workers, "kind": "port",
+            "sample": "%d frames of S1 per step; reference Python set/Counter algorithm restated "
+                      "(oracle/refpath.py) over the C restatement of MDTraj's neighbour list, run as the "
+                      "Dask-equivalent runner: default_slices -> %d worker processes -> Counter reduce "
+                      "(oracle C lib OpenMP threads per worker: 1)" % (frames, workers),
+        },
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "oracle_threads_available": clib.max_threads(),
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# -------------------------------------------------------------------------------------
+# GPU arm
+# -------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    warnings.simplefilter("ignore", PendingDeprecationWarning)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    device = torch.device("cuda", local_rank)
+
+    import contact_map_b200 as cm
+    from contact_map_b200 import parallel, synth
+    from contact_map_b200.engine import get_engine
+
+    system = synth.kras_like()
+    top = system.topology
+    n = top.n_atoms
+    F = args.frames
+    frame0 = rank * F
+    engine = get_engine(local_rank)
+    atom_res, atom_chain = top.atom_residue_chain()
+    role = np.full(n, 3, dtype=np.uint8)          # every atom is query and haystack
+    engine.set_system(atom_res, atom_chain, role, CUTOFF, N_IGNORED)
+    engine.set_option("count_tests", 0)
+
+    # inputs resident in HBM, generated on device (bit-identical to synth.make_frames)
+    d_base = torch.as_tensor(system.base, device=device)
+    d_groups = torch.as_tensor(system.groups.astype(np.int32), device=device)
+    d_box9 = torch.as_tensor(system.box.reshape(9), device=device)
+    d_xyz = engine.synth_frames(d_base, d_groups, d_box9, system.seed, system.amplitude, True, frame0, F)
+    d_box = d_box9.reshape(1, 3, 3).expand(F, 3, 3).contiguous()
+    atom_t, res_t = engine.new_tables()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    kern_events = []
+
+    def step(record):
+        atom_t.zero_()
+        res_t.zero_()
+        if record:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        engine.accumulate(d_xyz, d_box, atom_t, res_t)
+        if record:
+            e1.record()
+            kern_events.append((e0, e1))
+        parallel.reduce_tables([atom_t, res_t])
+        return engine.export_nonzero(atom_t), engine.export_nonzero(res_t)
+
+    for _ in range(max(args.warmup, 3)):      # timing rule: at least 3 warm-up steps
+        out = step(False)
+    n_atom_pairs, n_res_pairs = len(out[0][0]), len(out[1][0])
+
+    launches0 = engine.get_stat("kernel_launches")
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(args.steps):
+        step(True)
+    stop.record()
+    barrier()
+    clocks = sampler.stop()
+    elapsed_ms = start.elapsed_time(stop)
+    launches = engine.get_stat("kernel_launches") - launches0
+    kernel_ms = statistics.mean(e0.elapsed_time(e1) for e0, e1 in kern_events)
+    if world > 1:
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    value = world * F * args.steps / (elapsed_ms / 1e3)
+
+    # executed pair tests of one pass (separate, untimed launch with the counter switched on)
+    engine.set_option("count_tests", 1)
+    atom_t.zero_()
+    res_t.zero_()
+    engine.accumulate(d_xyz, d_box, atom_t, res_t)
+    pair_tests = engine.get_stat("pair_tests")
+    engine.set_option("count_tests", 0)
+
+    # ---- end to end through the public API, host buffers -------------------------------
+    e2e = None
+    if not args.no_e2e:
+        h_xyz = torch.empty((F, n, 3), dtype=torch.float32, pin_memory=True)
+        h_xyz.copy_(d_xyz)
+        h_box = torch.empty((F, 3, 3), dtype=torch.float32, pin_memory=True)
+        h_box.copy_(d_box)
+        torch.cuda.synchronize()
+        traj = cm.Trajectory(h_xyz.numpy(), top, h_box.numpy())   # views of the pinned buffers
+        assert traj.xyz.ctypes.data == h_xyz.data_ptr()
+        everyone = np.arange(n)
+
+        def e2e_step():
+            m = cm.ChunkedContactFrequency(traj, query=everyone, haystack=everyone, cutoff=CUTOFF,
+                                           n_neighbors_ignored=N_IGNORED, presharded=True)
+            return m
+
+        for _ in range(2):
+            m = e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            m = e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        na, nr = len(m._table_of("atom")), len(m._table_of("residue"))
+        e2e = {"value": world * F * args.steps / dt, "unit": "frames/s",
+               "h2d_bytes_per_step": int(F * (n * 12 + 36)),
+               "d2h_bytes_per_step": int((na + nr) * 12 + 16),
+               "ms_per_step": 1e3 * dt / args.steps,
+               "api": "ChunkedContactFrequency(trajectory with pinned host xyz, presharded=True) -> "
+                      "cmb_accumulate_host (chunked H2D overlapped with kernels) -> all-reduce -> sparse export -> D2H"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel -------------------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    alg_bytes = F * (12 * n + 36)
+    achieved = alg_bytes / (kernel_ms / 1e3) / 1e9
+    traffic = None
+    traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_path):
+        traffic = json.load(open(traffic_path)).get("k_frames_small_dram_bytes_per_launch")
+    sm_count = engine.get_stat("sm_count")
+    sm_mhz = clocks.get("sm_mhz") or 1965.0
+    # FP32 view: executed pair tests x 23 separately rounded fp32 ops (orthorhombic) per test
+    fp32_lane_ops = pair_tests * 23.0 / (kernel_ms / 1e3)
+    fp32_peak = sm_count * 128 * sm_mhz * 1e6
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": traffic, "kernel": "k_frames_small", "kernel_ms": kernel_ms,
+        "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+        "note": "HBM is the designated roofline (SURVEY 8d) but the kernel is FP32-issue bound: "
+                "see fp32_pipe",
+        "fp32_pipe": {"executed_pair_tests_per_launch": pair_tests,
+                      "lane_ops_per_test": 23, "achieved_lane_ops_per_s": fp32_lane_ops,
+                      "peak_lane_ops_per_s": fp32_peak, "frac": fp32_lane_ops / fp32_peak,
+                      "peak_definition": "%d SMs x 128 FP32 lanes x %.0f MHz (median SM clock under load), "
+                                         "non-FMA ops" % (sm_count, sm_mhz)},
+    }
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        frames_cpu = args.cpu_frames or 64
+        rate, dt, _, _ = cpu_reference_rate(system, frames_cpu, 1)
+        cpu_baseline = {"value": rate, "unit": "frames/s", "cores": 1, "kind": "port",
+                        "sample": "first %d frames of S1 (%.1f s): reference Python set/Counter loop restated "
+                                  "(oracle/refpath.py) over the C restatement of MDTraj's neighbour list "
+                                  "(oracle/cm_oracle.c); serial ContactFrequency, as the reference runs it"
+                                  % (frames_cpu, dt)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, world),
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "atom_pairs_screened_per_s": {"logical_nQ_x_nH": value * n * n,
+                                      "executed_tests": world * pair_tests * args.steps / (elapsed_ms / 1e3)},
+        "result": {"distinct_atom_pairs": n_atom_pairs, "distinct_residue_pairs": n_res_pairs},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,78 @@
+"""Frame sharding across GPUs: one process per GPU, ``torch.distributed`` for the plumbing.
+
+The reference's only parallel strategy is data parallelism over frames with a Python-level
+reduce (``dask_run``: /root/reference/contact_map/dask_runner.py:11-37; partition
+``frequency_task.default_slices`` :49-67; reduce ``reduce_all_results`` :125-141, i.e.
+``Counter`` addition).  Here every rank owns the frame blocks ``k`` with ``k % world == rank``,
+accumulates them into count tables of IDENTICAL layout, and the partial tables are summed
+with ONE all-reduce (NCCL over NVLink/NVSwitch on GPUs; gloo in the CPU tests).  Integer
+addition is associative, so the result is independent of the partition.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .frequency_task import default_slices
+
+
+def world():
+    """(rank, world_size) of the default process group, (0, 1) when not initialised."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def rank_slices(n_frames, n_blocks=None, rank=None, world_size=None):
+    """Frame slices of this rank: the reference partition ``default_slices(n_frames, n_blocks)``
+    dealt round-robin to the ranks.  ``n_blocks`` defaults to the world size."""
+    r, w = world()
+    rank = r if rank is None else rank
+    world_size = w if world_size is None else world_size
+    slices = default_slices(n_frames, n_blocks or world_size)
+    return [s for k, s in enumerate(slices) if k % world_size == rank]
+
+
+def reduce_tables(tables, group=None):
+    """Sum count tables over all ranks, in place, with a single all-reduce.
+
+    ``tables`` is a list of int32 tensors (views of the uint32 tables).  They are packed into
+    one flat buffer so exactly one collective is issued; two's-complement addition makes the
+    int32 view exact for uint32 counts."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return tables
+    flat = torch.cat([t.reshape(-1) for t in tables]) if len(tables) > 1 else tables[0].reshape(-1)
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    if len(tables) > 1:
+        offset = 0
+        for t in tables:
+            t.copy_(flat[offset:offset + t.numel()].reshape(t.shape))
+            offset += t.numel()
+    return tables
+
+
+def reduce_frame_count(n_frames, device, group=None):
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return int(n_frames)
+    t = torch.tensor([int(n_frames)], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return int(t.item())
+
+
+def gather_keys(keys, device, group=None):
+    """Concatenate per-rank uint64 key arrays on every rank (ContactTrajectory: no reduction,
+    rank-ordered concatenation; the keys carry global frame numbers, so a sort restores
+    frame order)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return keys
+    w = dist.get_world_size(group)
+    local = torch.as_tensor(keys.view(np.int64), device=device)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(w)]
+    dist.all_gather(sizes, torch.tensor([local.numel()], dtype=torch.int64, device=device), group=group)
+    sizes = [int(s.item()) for s in sizes]
+    cap = max(max(sizes), 1)
+    padded = torch.zeros(cap, dtype=torch.int64, device=device)
+    padded[:local.numel()] = local
+    parts = [torch.empty(cap, dtype=torch.int64, device=device) for _ in range(w)]
+    dist.all_gather(parts, padded, group=group)
+    merged = torch.cat([p[:s] for p, s in zip(parts, sizes)]).cpu().numpy().view(np.uint64)
+    return np.sort(merged)

@@ -155,7 +155,9 @@ def solvated_triclinic(n_atoms=100000, seed=1003, amplitude=0.03, lattice=47):
     triclinic cell; first 2700 sites form a 270x10 'protein' (chain 0), the rest 3-atom
     'solvent' residues (chain 1)."""
     rng = np.random.default_rng(seed)
+    # the cell shrinks with the lattice so the site density (about 116 atoms/nm^3) is fixed
     cell = np.array([[10.2, 0.0, 0.0], [3.4, 9.6, 0.0], [-3.4, 3.2, 9.1]], dtype=np.float64)
+    cell = cell * (lattice / 47.0)
     idx = np.arange(n_atoms)
     frac = np.stack([(idx % lattice), (idx // lattice) % lattice, idx // (lattice * lattice)],
                     axis=1).astype(np.float64)

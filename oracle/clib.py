@@ -53,6 +53,8 @@ def lib():
     L.orc_nl_d2.argtypes = [c_f, c_f, c_f]
     L.orc_neighborlist_csr.restype = ctypes.c_int64
     L.orc_neighborlist_csr.argtypes = [c_f, ctypes.c_int, c_f, ctypes.c_double, c_i64, c_i32]
+    L.orc_neighborlist_csr_cells.restype = ctypes.c_int64
+    L.orc_neighborlist_csr_cells.argtypes = [c_f, ctypes.c_int, c_f, ctypes.c_double, c_i64, c_i32]
     sig = [c_f, ctypes.c_int, c_f, ctypes.c_double, c_i32, c_i32, c_u8, ctypes.c_int,
            ctypes.c_int64, c_i32, c_i32]
     L.orc_contacts_frame.restype = ctypes.c_int64
@@ -109,19 +111,21 @@ def nl_d2(pi, pj, box=None):
                                  _p(b, ctypes.c_float)))
 
 
-def neighborlist(xyz_frame, box, cutoff):
-    """MDTraj-style neighbour list of one frame: list of int arrays (one per atom)."""
+def neighborlist(xyz_frame, box, cutoff, cells=True):
+    """MDTraj-style neighbour list of one frame: list of int arrays (one per atom).
+    cells=True prunes candidates with a cell grid (identical result, see the tests)."""
     x = _f32(xyz_frame)
     n = x.shape[0]
     b = _box9(box)
     ptr = np.zeros(n + 1, dtype=np.int64)
-    L = lib()
-    total = L.orc_neighborlist_csr(_p(x, ctypes.c_float), n, _p(b, ctypes.c_float),
-                                   float(cutoff), _p(ptr, ctypes.c_int64), None)
+    fn = lib().orc_neighborlist_csr_cells if cells else lib().orc_neighborlist_csr
+    total = fn(_p(x, ctypes.c_float), n, _p(b, ctypes.c_float), float(cutoff),
+               _p(ptr, ctypes.c_int64), None)
     idx = np.empty(max(int(total), 1), dtype=np.int32)
-    L.orc_neighborlist_csr(_p(x, ctypes.c_float), n, _p(b, ctypes.c_float), float(cutoff),
-                           _p(ptr, ctypes.c_int64), _p(idx, ctypes.c_int32))
-    return [idx[ptr[i]:ptr[i + 1]].astype(np.int64) for i in range(n)]
+    fn(_p(x, ctypes.c_float), n, _p(b, ctypes.c_float), float(cutoff),
+       _p(ptr, ctypes.c_int64), _p(idx, ctypes.c_int32))
+    idx64 = idx.astype(np.int64)
+    return [idx64[ptr[i]:ptr[i + 1]] for i in range(n)]
 
 
 def contacts_frame(xyz_frame, box, cutoff, res, chain, role, n_ignored, cells=False):

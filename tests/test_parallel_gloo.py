@@ -1,0 +1,86 @@
+"""CPU, world_size 2 over gloo: the multi-rank frame sharding + single all-reduce of the tables.
+
+The per-rank partial tables are produced by the ORACLE here (no GPU in this container); what is
+under test is the product's partition (`parallel.rank_slices`) and reduce (`parallel.reduce_tables`,
+`reduce_frame_count`, `gather_keys`).
+"""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from contact_map_b200 import parallel, synth
+        from oracle import clib
+        from tests.helpers import system_arrays
+        rng = np.random.default_rng(11)
+        system = synth.random_system(rng, 80, n_chains=2, box_kind="ortho", extent=1.2)
+        n_frames = 7
+        xyz = system.frames(0, n_frames)
+        box = np.broadcast_to(system.box, (n_frames, 3, 3)).copy()
+        res, chain, role = system_arrays(system)
+        n_res = system.topology.n_residues
+        atom = np.zeros((80, 80), dtype=np.uint32)
+        resc = np.zeros((n_res, n_res), dtype=np.uint32)
+        mine = 0
+        keys = []
+        for s in parallel.rank_slices(n_frames, n_blocks=3):
+            a, r = clib.accumulate_dense(xyz[s], box[s], 0.45, res, chain, role, 2, n_res)
+            atom += a
+            resc += r
+            mine += s.stop - s.start
+            for f in range(s.start, s.stop):
+                pairs = clib.contacts_frame(xyz[f], box[f], 0.45, res, chain, role, 2)
+                keys.append((np.uint64(f) << np.uint64(40)) | (pairs[:, 0].astype(np.uint64) << np.uint64(20))
+                            | pairs[:, 1].astype(np.uint64))
+        t_atom = torch.from_numpy(atom.view(np.int32).reshape(-1).copy())
+        t_res = torch.from_numpy(resc.view(np.int32).reshape(-1).copy())
+        parallel.reduce_tables([t_atom, t_res])
+        total_frames = parallel.reduce_frame_count(mine, torch.device("cpu"))
+        all_keys = parallel.gather_keys(np.sort(np.concatenate(keys)) if keys else np.empty(0, np.uint64),
+                                        torch.device("cpu"))
+        np.savez(os.path.join(out_dir, "rank%d.npz" % rank), atom=t_atom.numpy(), res=t_res.numpy(),
+                 frames=total_frames, keys=all_keys.view(np.int64))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_reduce_equals_single(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    from contact_map_b200 import synth
+    from oracle import clib
+    from tests.helpers import system_arrays
+    rng = np.random.default_rng(11)
+    system = synth.random_system(rng, 80, n_chains=2, box_kind="ortho", extent=1.2)
+    xyz = system.frames(0, 7)
+    box = np.broadcast_to(system.box, (7, 3, 3)).copy()
+    res, chain, role = system_arrays(system)
+    atom, resc = clib.accumulate_dense(xyz, box, 0.45, res, chain, role, 2, system.topology.n_residues)
+    want_keys = []
+    for f in range(7):
+        pairs = clib.contacts_frame(xyz[f], box[f], 0.45, res, chain, role, 2)
+        want_keys.append((np.uint64(f) << np.uint64(40)) | (pairs[:, 0].astype(np.uint64) << np.uint64(20))
+                         | pairs[:, 1].astype(np.uint64))
+    want_keys = np.concatenate(want_keys)
+    for rank in range(2):
+        got = np.load(os.path.join(str(tmp_path), "rank%d.npz" % rank))
+        assert np.array_equal(got["atom"].view(np.uint32).reshape(80, 80), atom)
+        assert np.array_equal(got["res"].view(np.uint32).reshape(resc.shape), resc)
+        assert int(got["frames"]) == 7
+        assert np.array_equal(got["keys"].view(np.uint64), want_keys)
+    assert atom.sum() > 0
