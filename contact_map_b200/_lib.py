@@ -11,7 +11,8 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-SO_PATH = os.path.join(_HERE, "libcmb200.so")
+# CMB200_SO selects an alternative build (kernel-tuning experiments); the default is in-tree
+SO_PATH = os.environ.get("CMB200_SO") or os.path.join(_HERE, "libcmb200.so")
 _SOURCES = [os.path.join(_HERE, "csrc", f) for f in (
     "cmb_api.cu", "cmb_math.cuh", "cmb_cells.cuh", "cmb_frames_small.cuh",
     "cmb_frames_large.cuh", "cmb_aux_kernels.cuh")] + [os.path.join(_ROOT, "include", "cmb200.h")]
@@ -38,6 +39,8 @@ def _nvcc():
 
 
 def needs_build():
+    if os.environ.get("CMB200_SO"):
+        return False
     if not os.path.exists(SO_PATH):
         return True
     so_time = os.path.getmtime(SO_PATH)

@@ -31,7 +31,9 @@ struct cmb_ctx {
     float cutoff_f = 0.f;
     int n_ignored = 0;
     std::vector<int32_t> res_map;     // compact -> global residue index
-    int2* d_meta = nullptr;
+    int2* d_meta = nullptr;           // {ekey, res_c | role << 30}   (global-memory cell path)
+    unsigned int* d_meta32 = nullptr; // packed word of the fused kernel (cmb_frames_small.cuh)
+    bool all_roles = true;            // every used atom is both query and haystack
     int path = 0;                     // 0 fused shared-memory kernel, 1 global-memory cell path
 
     // fused-kernel launch configuration
@@ -146,6 +148,7 @@ extern "C" void cmb_ctx_destroy(cmb_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaFree(ctx->d_meta);
+    cudaFree(ctx->d_meta32);
     for (int s = 0; s < 2; s++) {
         cudaFree(ctx->d_bitmap[s]);
         cudaFree(ctx->d_counters[s]);
@@ -213,9 +216,14 @@ static int configure_small_path(cmb_ctx* ctx)
     if (L.total > ctx->max_smem_optin) return fail(ctx, CMB_ERR_LIMIT, "system does not fit the fused kernel");
     ctx->fs_maxc = maxc;
     ctx->fs_smem = L.total;
-    CK(cudaFuncSetAttribute(k_frames_small, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    CK(cudaFuncSetAttribute(k_frames_small<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    CK(cudaFuncSetAttribute(k_frames_small<FS_ROLES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    CK(cudaFuncSetAttribute(k_frames_small<FS_EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    CK(cudaFuncSetAttribute(k_frames_small<FS_EMIT | FS_ROLES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    CK(cudaFuncSetAttribute(k_frames_small<FS_BOUNDARY | FS_ROLES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    CK(cudaFuncSetAttribute(k_frames_small<FS_COUNT | FS_ROLES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
     int nb = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_frames_small, FS_THREADS, (size_t)L.total));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_frames_small<0>, FS_THREADS, (size_t)L.total));
     if (nb < 1) return fail(ctx, CMB_ERR_LIMIT, "fused kernel cannot be resident (smem %d)", L.total);
     ctx->fs_ctas_per_sm = nb;
     return CMB_OK;
@@ -239,41 +247,63 @@ extern "C" int cmb_set_system(cmb_ctx* ctx, int n_used, const int32_t* atom_res,
     ctx->n_res_c = (int)uniq.size();
 
     // exclusion key: |ekey_a - ekey_b| <= n_ignored  <=>  same chain and |res_a - res_b| <= n_ignored.
-    // Chains are laid out one after another on the key axis with gaps of n_ignored + 1.
-    std::map<int32_t, std::pair<int32_t, int32_t>> span;   // chain -> (min res, max res)
-    for (int i = 0; i < n_used; i++) {
-        auto it = span.find(atom_chain[i]);
-        if (it == span.end()) span[atom_chain[i]] = {atom_res[i], atom_res[i]};
-        else {
-            it->second.first = std::min(it->second.first, atom_res[i]);
-            it->second.second = std::max(it->second.second, atom_res[i]);
+    // Used residues are laid out on the key axis chain after chain; inside a chain consecutive used
+    // residues advance the key by min(gap, n_ignored + 1), a new chain by n_ignored + 1.  Gaps larger
+    // than n_ignored are thereby compressed without changing the predicate, which keeps the keys small.
+    std::vector<std::pair<int32_t, int32_t>> chain_res;   // (chain, residue) of every used residue
+    {
+        std::map<int32_t, int32_t> res_chain;
+        for (int i = 0; i < n_used; i++) {
+            auto it = res_chain.find(atom_res[i]);
+            if (it == res_chain.end()) res_chain[atom_res[i]] = atom_chain[i];
+            else if (it->second != atom_chain[i])
+                return fail(ctx, CMB_ERR_ARG, "residue %d is assigned to two chains", atom_res[i]);
         }
+        for (auto& kv : res_chain) chain_res.push_back({kv.second, kv.first});
+        std::sort(chain_res.begin(), chain_res.end());
     }
-    std::map<int32_t, long long> chain_base;
+    std::map<int32_t, long long> ekey_of_res;
     long long cursor = 0;
-    for (auto& kv : span) {
-        chain_base[kv.first] = cursor - kv.second.first;
-        cursor += (long long)(kv.second.second - kv.second.first) + n_ignored + 1;
-        if (cursor > 0x3fffffffll) return fail(ctx, CMB_ERR_LIMIT, "residue index span too large");
+    for (size_t k = 0; k < chain_res.size(); k++) {
+        if (k > 0) {
+            const bool same_chain = chain_res[k].first == chain_res[k - 1].first;
+            const long long gap = (long long)chain_res[k].second - chain_res[k - 1].second;
+            cursor += same_chain ? std::min<long long>(gap, (long long)n_ignored + 1) : (long long)n_ignored + 1;
+        }
+        ekey_of_res[chain_res[k].second] = cursor;
     }
+    if (cursor > 0x3fffffffll) return fail(ctx, CMB_ERR_LIMIT, "exclusion key range too large");
+    const long long ekey_max = cursor;
     std::vector<int2> meta(n_used);
+    std::vector<unsigned int> meta32(n_used);
+    bool all_roles = true;
     for (int i = 0; i < n_used; i++) {
         const int rc = (int)(std::lower_bound(uniq.begin(), uniq.end(), atom_res[i]) - uniq.begin());
-        const int ekey = (int)(chain_base[atom_chain[i]] + atom_res[i]);
+        const int ekey = (int)ekey_of_res[atom_res[i]];
         meta[i].x = ekey;
         meta[i].y = rc | ((int)(role[i] & 3u) << 30);
+        meta32[i] = ((unsigned)ekey & FS_EKEY_MASK) | (((unsigned)rc & FS_RES_MASK) << FS_EKEY_BITS) |
+                    ((unsigned)(role[i] & 3u) << 30);
+        if ((role[i] & 3u) != 3u) all_roles = false;
     }
+    ctx->all_roles = all_roles;
     if (ctx->d_meta) CK(cudaFree(ctx->d_meta));
     ctx->d_meta = nullptr;
     CK(cudaMalloc(&ctx->d_meta, sizeof(int2) * (size_t)n_used));
     CK(cudaMemcpy(ctx->d_meta, meta.data(), sizeof(int2) * (size_t)n_used, cudaMemcpyHostToDevice));
+    if (ctx->d_meta32) CK(cudaFree(ctx->d_meta32));
+    ctx->d_meta32 = nullptr;
+    CK(cudaMalloc(&ctx->d_meta32, sizeof(unsigned int) * (size_t)n_used));
+    CK(cudaMemcpy(ctx->d_meta32, meta32.data(), sizeof(unsigned int) * (size_t)n_used, cudaMemcpyHostToDevice));
 
     ctx->n = n_used;
     ctx->cutoff_f = (float)cutoff;
     ctx->n_ignored = n_ignored;
     ctx->have_system = false;
     int64_t force = ctx->stats.count("force_path") ? ctx->stats["force_path"] : -1;
-    ctx->path = (n_used <= FS_MAX_ATOMS) ? 0 : 1;
+    // the fused kernel packs ekey (17 bits) and the compact residue id (13 bits) into one word
+    ctx->path = (n_used <= FS_MAX_ATOMS && ekey_max <= (long long)FS_EKEY_MASK &&
+                 (long long)ctx->n_res_c <= (long long)FS_RES_MASK) ? 0 : 1;
     if (force == 1) ctx->path = 1;
     if (ctx->path == 0) {
         int rc = configure_small_path(ctx);
@@ -341,7 +371,7 @@ static int launch_frames(cmb_ctx* ctx, const FrameJob& job, int slot, cudaStream
         FrameParams p;
         memset(&p, 0, sizeof(p));
         p.xyz = job.xyz; p.box = job.box; p.n_frames = job.n_frames; p.frame0 = job.frame0;
-        p.n = ctx->n; p.meta = ctx->d_meta;
+        p.n = ctx->n; p.meta32 = ctx->d_meta32;
         p.cutoff = ctx->cutoff_f; p.c2 = c2;
         p.boundary_ulps = job.boundary_ulps;
         p.c2_hi = job.boundary_ulps > 0 ? advance_float(c2, job.boundary_ulps) : c2;
@@ -352,7 +382,6 @@ static int launch_frames(cmb_ctx* ctx, const FrameJob& job, int slot, cudaStream
         p.res_keys = job.res_keys; p.res_cap = job.res_cap;
         p.counters = counters;
         p.boundary = job.boundary; p.boundary_cap = job.boundary_cap;
-        p.count_tests = ctx->count_tests;
         long long grid = (long long)ctx->sm_count * ctx->fs_ctas_per_sm;
         if (grid > job.n_frames) grid = job.n_frames;
         if (!p.bm_in_smem) {
@@ -361,7 +390,21 @@ static int launch_frames(cmb_ctx* ctx, const FrameJob& job, int slot, cudaStream
             if (rc) return rc;
             p.g_bitmap = ctx->d_bitmap[slot];
         }
-        k_frames_small<<<(unsigned)grid, FS_THREADS, ctx->fs_smem, stream>>>(p);
+        const bool emit = job.atom_keys != nullptr || job.res_keys != nullptr;
+        const unsigned g = (unsigned)grid;
+        const size_t sm = (size_t)ctx->fs_smem;
+        if (job.boundary_ulps > 0)
+            k_frames_small<FS_BOUNDARY | FS_ROLES><<<g, FS_THREADS, sm, stream>>>(p);
+        else if (ctx->count_tests && !emit)
+            k_frames_small<FS_COUNT | FS_ROLES><<<g, FS_THREADS, sm, stream>>>(p);
+        else if (emit && ctx->all_roles)
+            k_frames_small<FS_EMIT><<<g, FS_THREADS, sm, stream>>>(p);
+        else if (emit)
+            k_frames_small<FS_EMIT | FS_ROLES><<<g, FS_THREADS, sm, stream>>>(p);
+        else if (ctx->all_roles)
+            k_frames_small<0><<<g, FS_THREADS, sm, stream>>>(p);
+        else
+            k_frames_small<FS_ROLES><<<g, FS_THREADS, sm, stream>>>(p);
         CK(cudaGetLastError());
         ctx->stats["kernel_launches"] += 1;
         return CMB_OK;

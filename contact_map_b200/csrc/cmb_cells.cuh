@@ -20,6 +20,9 @@ struct GridS {
     double o[3];
     int nx, ny, nz, ncell;
     int periodic;
+    // c / nx == __umulhi(c << 6, magic_x) for c < 2^16 (ceil(2^26 / nx)); same for ny
+    unsigned magic_x, magic_y;
+    int distinct;    // the 27 stencil cells of any cell are pairwise distinct (no dedup needed)
 };
 
 // ----- per-frame cell grid (one thread) ------------------------------------------
@@ -94,6 +97,9 @@ __device__ inline void make_grid(GridS& G, const float* box9, double cutoff, int
     }
     fit_cells(G.nx, G.ny, G.nz, maxc);
     G.ncell = G.nx * G.ny * G.nz;
+    G.magic_x = ((1u << 26) + (unsigned)G.nx - 1u) / (unsigned)G.nx;
+    G.magic_y = ((1u << 26) + (unsigned)G.ny - 1u) / (unsigned)G.ny;
+    G.distinct = !G.periodic || (G.nx >= 3 && G.ny >= 3 && G.nz >= 3);
 }
 
 __device__ __forceinline__ int cell_of(const GridS& G, float x, float y, float z)

@@ -7,23 +7,23 @@
 //   Counter.update / Counter += of ContactFrequency        contact_map.py:739-740
 //   per-frame pair sets of _build_contacts                 contact_trajectory.py:32-44
 //
-// One persistent CTA per frame slot (grid = SMs x resident CTAs, frame-strided):
+// Persistent CTAs (grid = SMs x resident CTAs), frames dealt round-robin:
 //   1. the frame's fp32 xyz (12*n bytes, contiguous in HBM) is pulled into shared
 //      memory with ONE 1-D TMA bulk copy (cp.async.bulk -> UBLKCP) signalled on an
 //      mbarrier; the copy of the NEXT frame is issued as soon as the scatter pass
 //      has consumed the buffer, so it overlaps the pair phase;
-//   2. atoms are binned into >= cutoff-wide cells of the (orthorhombic/triclinic/
-//      open) cell grid: shared-memory histogram, block scan, scatter into a
-//      cell-sorted float4 array {x, y, z, atom};
-//   3. one warp per occupied cell: the candidate atoms of the half-shell
+//   2. atoms are binned into >= cutoff-wide cells of the (orthorhombic / triclinic /
+//      open) cell grid: u16 shared-memory histogram, block scan, scatter into a
+//      cell-sorted float4 array {x, y, z, packed meta} (+ u16 atom index);
+//   3. one warp per occupied cell: the candidate atoms of the half shell
 //      (neighbour cells with id >= own) are held in registers (4 per lane), the
 //      cell's own atoms are broadcast from shared memory, and every candidate pair
 //      is adjudicated with MDTraj's exact float32 arithmetic on the RAW
 //      coordinates (cmb_math.cuh);
-//   4. hits pass role + residue-exclusion tests and are (a) RED-added into the
+//   4. hits that pass the role + residue-exclusion tests are (a) RED-added into the
 //      dense uint32 atom-pair table, (b) OR'd into a per-frame residue-pair bitmap
 //      in shared memory that is popcount-flushed into the residue table at frame
-//      end (per-frame set semantics), and/or (c) ballot-compacted into 64-bit
+//      end (per-frame set semantics), and/or (c) warp-ballot compacted into 64-bit
 //      (frame, a, b) keys for ContactTrajectory.
 #pragma once
 #include "cmb_cells.cuh"
@@ -32,9 +32,23 @@ namespace cmb {
 
 constexpr int FS_THREADS = 512;
 constexpr int FS_WARPS = FS_THREADS / 32;
-constexpr int FS_APT = 12;                       // atoms per thread in the binning passes
+constexpr int FS_APT = 12;                          // atoms per thread in the binning passes
 constexpr int FS_MAX_ATOMS = FS_THREADS * FS_APT;   // 6144
 constexpr int FS_HEADER_BYTES = 1024;
+constexpr int FS_KSLOT = 4;                         // register-resident candidates per lane
+constexpr int FS_CAND = 32 * FS_KSLOT;              // candidates per chunk
+constexpr int FS_HITQ = 64;                         // per-warp queue of compacted hits
+
+// packed per-atom meta word: ekey [0,17) | compact residue [17,30) | role [30,32)
+constexpr unsigned FS_EKEY_BITS = 17;
+constexpr unsigned FS_EKEY_MASK = (1u << FS_EKEY_BITS) - 1u;
+constexpr unsigned FS_RES_MASK = (1u << 13) - 1u;
+
+// kernel variants (template FLAGS)
+constexpr int FS_EMIT = 1;        // emit (frame, a, b) keys
+constexpr int FS_BOUNDARY = 2;    // report pairs within boundary_ulps of the cutoff
+constexpr int FS_COUNT = 4;       // count executed pair tests
+constexpr int FS_ROLES = 8;       // query / haystack are not "all atoms": test the roles
 
 struct FrameParams {
     const float* xyz;            // [n_frames][n][3] fp32, device
@@ -42,10 +56,10 @@ struct FrameParams {
     long long n_frames;
     long long frame0;            // id of frame 0 of this call (for emitted keys)
     int n;                       // used atoms
-    const int2* meta;            // [n] {ekey, res_c | role << 30}
+    const unsigned int* meta32;  // [n] packed meta words
     float cutoff;
     float c2;                    // cutoff_f * cutoff_f
-    float c2_hi;                 // c2 advanced by `boundary_ulps` float steps (== c2 if off)
+    float c2_hi;                 // c2 advanced by `boundary_ulps` float steps
     int boundary_ulps;
     int n_ignored;
     int n_res_c;                 // compact residue count (bitmap is n_res_c x n_res_c bits)
@@ -62,7 +76,6 @@ struct FrameParams {
     unsigned long long* counters;    // [0] atom keys, [1] residue keys, [2] boundary records, [3] pair tests
     float4* boundary;            // records {frame, lo, hi, d2} (ints bit-cast) or nullptr
     long long boundary_cap;
-    int count_tests;             // accumulate executed pair tests into counters[3]
 };
 
 // ----- mbarrier / TMA bulk helpers (sm_90+ PTX; SASS: SYNCS / UBLKCP) -------------
@@ -108,7 +121,7 @@ __device__ __forceinline__ void fence_proxy_async()
 
 // ----- shared-memory layout ------------------------------------------------------
 struct FsLayout {
-    int raw_off, sorted_off, cell_off, occ_off, bm_off, wscr_off, total;
+    int raw_off, sorted_off, sidx_off, cell_off, occ_off, bm_off, cand_off, hitq_off, total;
 };
 
 __host__ __device__ inline int fs_align(int x, int a) { return (x + a - 1) / a * a; }
@@ -121,48 +134,245 @@ __host__ __device__ inline FsLayout fs_layout(int n, int maxc, int bm_words_smem
     off += fs_align(12 * n + 32, 128);
     L.sorted_off = off;
     off += fs_align(16 * n, 128);
+    L.sidx_off = off;
+    off += fs_align(2 * n, 128);
     L.cell_off = off;
     off += fs_align(2 * (maxc + 2), 128);
     L.occ_off = off;
     off += fs_align(2 * (maxc < n ? maxc : n) + 2, 128);
     L.bm_off = off;
     off += fs_align(4 * bm_words_smem, 128);
-    L.wscr_off = off;
-    off += FS_WARPS * 64 * 4;
+    L.cand_off = off;
+    off += FS_WARPS * FS_CAND * 2;
+    L.hitq_off = off;
+    off += FS_WARPS * FS_HITQ * 4;
     L.total = off;
     return L;
 }
 
-// ----- residue sink: per-frame bitmap (shared or global), flushed at frame end -----
-struct BitmapSink {
-    unsigned int* bitmap;
-    unsigned n_res_c;
-    __device__ __forceinline__ void residue(int rlo, int rhi)
-    {
-        const unsigned bit = (unsigned)rlo * n_res_c + (unsigned)rhi;
-        const unsigned msk = 1u << (bit & 31);
-        unsigned int* wp = &bitmap[bit >> 5];
-        if (!(*(volatile unsigned int*)wp & msk)) atomicOr(wp, msk);
-    }
+// everything the pair phase needs, in one place
+struct FsPairCtx {
+    const float4* sorted;            // [n] {x, y, z, meta32}
+    const unsigned short* sidx;      // [n] atom index of each sorted position
+    const unsigned short* cellptr;   // [ncell + 1]
+    unsigned int* bitmap;            // residue-pair bitmap of this CTA
+    unsigned int* hitq;              // this warp's queue of hits (ipos | jpos << 16)
+    long long frame_id;
 };
 
-template <int MODE>
-__device__ __forceinline__ void fs_pair_phase(const TaskParams& tp, const NlBox& B, const GridS& G,
-                                              const float4* sorted, const unsigned short* cellptr,
-                                              const unsigned short* occ, int n_occ, int* task_counter,
-                                              int* wscr, BitmapSink& sink, unsigned long long& n_tests)
+// Account one hit (sorted positions ipos < jpos): atom-pair table + residue-pair bitmap.
+__device__ __forceinline__ void fs_on_hit(const FrameParams& p, const FsPairCtx& cx, int ipos, int jpos)
+{
+    const int ia = cx.sidx[ipos], ib = cx.sidx[jpos];
+    const int a = min(ia, ib), b = max(ia, ib);
+    if (p.atom_table != nullptr) atomicAdd(&p.atom_table[(size_t)a * (size_t)p.n + (size_t)b], 1u);
+    const unsigned mi = __float_as_uint(cx.sorted[ipos].w), mj = __float_as_uint(cx.sorted[jpos].w);
+    const unsigned ra = (mi >> FS_EKEY_BITS) & FS_RES_MASK, rb = (mj >> FS_EKEY_BITS) & FS_RES_MASK;
+    const unsigned bit = min(ra, rb) * (unsigned)p.n_res_c + max(ra, rb);
+    const unsigned msk = 1u << (bit & 31);
+    unsigned int* wp = &cx.bitmap[bit >> 5];
+    if (!(*(volatile unsigned int*)wp & msk)) atomicOr(wp, msk);
+}
+
+// Warp-ballot compaction: the hits of one slot iteration (about 5 % of the lanes) are appended
+// to the warp's shared-memory queue and accounted 32 at a time with all lanes busy.
+__device__ __forceinline__ void fs_queue_hits(const FrameParams& p, const FsPairCtx& cx, bool hit,
+                                              int ipos, int jpos, int& qn)
+{
+    const unsigned hm = __ballot_sync(0xffffffffu, hit);
+    if (hm == 0u) return;
+    const int lane = threadIdx.x & 31;
+    if (hit) cx.hitq[qn + __popc(hm & ((1u << lane) - 1u))] = (unsigned)ipos | ((unsigned)jpos << 16);
+    qn += __popc(hm);
+    if (qn >= 32) {
+        __syncwarp();
+        const unsigned e = cx.hitq[lane];
+        const unsigned rest = (32 + lane < qn) ? cx.hitq[32 + lane] : 0u;
+        __syncwarp();
+        cx.hitq[lane] = rest;
+        qn -= 32;
+        fs_on_hit(p, cx, (int)(e & 0xffffu), (int)(e >> 16));
+    }
+}
+
+__device__ __forceinline__ void fs_drain_hits(const FrameParams& p, const FsPairCtx& cx, int& qn)
+{
+    __syncwarp();
+    const int lane = threadIdx.x & 31;
+    if (lane < qn) {
+        const unsigned e = cx.hitq[lane];
+        fs_on_hit(p, cx, (int)(e & 0xffffu), (int)(e >> 16));
+    }
+    qn = 0;
+    __syncwarp();
+}
+
+// all (own atom) x (NK register slots) tests of one candidate chunk
+template <int MODE, int NK, int FLAGS>
+__device__ __forceinline__ void fs_inner(const FrameParams& p, const NlBox& B, const FsPairCtx& cx,
+                                         int cstart, int cend, const float (&xj)[FS_KSLOT],
+                                         const float (&yj)[FS_KSLOT], const float (&zj)[FS_KSLOT],
+                                         const unsigned (&mj)[FS_KSLOT], const int (&jpos)[FS_KSLOT], int& qn)
 {
     const int lane = threadIdx.x & 31;
+    for (int ipos = cstart; ipos < cend; ipos++) {
+        const float4 pi = cx.sorted[ipos];
+        const unsigned mi = __float_as_uint(pi.w);
+#pragma unroll
+        for (int k = 0; k < NK; k++) {
+            // tested in the direction lower sorted position -> higher; the arithmetic is
+            // antisymmetric for every pair that can be a hit ("direction")
+            const float d2 = nl_d2<MODE>(pi.x, pi.y, pi.z, xj[k], yj[k], zj[k], B);
+            int de = (int)(mi & FS_EKEY_MASK) - (int)(mj[k] & FS_EKEY_MASK);
+            de = de < 0 ? -de : de;
+            bool elig = (de > p.n_ignored) && (jpos[k] > ipos);
+            if (FLAGS & FS_ROLES) {
+                const unsigned ri = mi >> 30, rj = mj[k] >> 30;
+                elig = elig && (((ri & (rj >> 1)) | (rj & (ri >> 1))) & 1u);
+            }
+            if (FLAGS & FS_BOUNDARY) {
+                if (elig && d2 <= p.c2_hi) {
+                    int diff = __float_as_int(d2) - __float_as_int(p.c2);
+                    diff = diff < 0 ? -diff : diff;
+                    if (diff <= p.boundary_ulps) {
+                        const int ia = cx.sidx[ipos], ib = cx.sidx[jpos[k]];
+                        const unsigned long long w = atomicAdd(&p.counters[2], 1ull);
+                        if ((long long)w < p.boundary_cap)
+                            p.boundary[w] = make_float4(__int_as_float((int)cx.frame_id),
+                                                        __int_as_float(min(ia, ib)),
+                                                        __int_as_float(max(ia, ib)), d2);
+                    }
+                }
+            }
+            const bool hit = elig && (d2 <= p.c2);
+            if (FLAGS & FS_EMIT) {
+                // warp-ballot compaction of this slot's hits into the key stream
+                const unsigned hm = __ballot_sync(0xffffffffu, hit);
+                if (hm) {
+                    const int leader = __ffs(hm) - 1;
+                    unsigned long long wbase = 0;
+                    if (lane == leader) wbase = atomicAdd(&p.counters[0], (unsigned long long)__popc(hm));
+                    wbase = __shfl_sync(0xffffffffu, wbase, leader);
+                    if (hit) {
+                        const unsigned long long w = wbase + __popc(hm & ((1u << lane) - 1u));
+                        const int ia = cx.sidx[ipos], ib = cx.sidx[jpos[k]];
+                        if ((long long)w < p.atom_cap)
+                            p.atom_keys[w] = ((unsigned long long)cx.frame_id << 40) |
+                                             ((unsigned long long)min(ia, ib) << 20) |
+                                             (unsigned long long)max(ia, ib);
+                    }
+                }
+            }
+            fs_queue_hits(p, cx, hit, ipos, jpos[k], qn);
+        }
+    }
+}
+
+// One warp adjudicates all candidate pairs of one occupied cell `c`.
+template <int MODE, int FLAGS>
+__device__ __forceinline__ void fs_cell_task(const FrameParams& p, const NlBox& B, const GridS& G,
+                                             const FsPairCtx& cx, int c, unsigned short* cand,
+                                             unsigned long long& n_tests, int& qn)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    const int cyz = (int)__umulhi((unsigned)c << 6, G.magic_x);
+    const int cxx = c - cyz * G.nx;
+    const int cz = (int)__umulhi((unsigned)cyz << 6, G.magic_y);
+    const int cy = cyz - cz * G.ny;
+
+    // neighbour cells: lanes 0..26 of the stencil, kept only if their id >= own id
+    int myD = -1;
+    if (lane < 27) {
+        const int l9 = lane / 9, l3 = (lane - l9 * 9) / 3;
+        int x = cxx + (lane - l9 * 9 - l3 * 3) - 1;
+        int y = cy + l3 - 1;
+        int z = cz + l9 - 1;
+        if (G.periodic) {
+            x = x < 0 ? x + G.nx : (x >= G.nx ? x - G.nx : x);
+            y = y < 0 ? y + G.ny : (y >= G.ny ? y - G.ny : y);
+            z = z < 0 ? z + G.nz : (z >= G.nz ? z - G.nz : z);
+        }
+        const bool ok = (x >= 0 && x < G.nx && y >= 0 && y < G.ny && z >= 0 && z < G.nz);
+        if (ok) myD = (z * G.ny + y) * G.nx + x;
+    }
+    bool keep = (myD >= c);
+    if (!G.distinct) {   // grids with < 3 cells along a dimension: drop duplicate stencil cells
+        const unsigned same = __match_any_sync(FULL, myD);
+        keep = keep && ((__ffs(same) - 1) == lane);
+    }
+    int mystart = 0, mycnt = 0;
+    if (keep) {
+        mystart = (int)cx.cellptr[myD];
+        mycnt = (int)cx.cellptr[myD + 1] - mystart;
+    }
+    int incl = mycnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += v;
+    }
+    const int M = __shfl_sync(FULL, incl, 31);
+    const int off = incl - mycnt;
+    const int cstart = (int)cx.cellptr[c], cend = (int)cx.cellptr[c + 1];
+
+    for (int base = 0; base < M; base += FS_CAND) {
+        __syncwarp();
+        {   // expand this lane's neighbour cell into the per-warp candidate list
+            const int r0 = max(0, base - off), r1 = min(mycnt, base + FS_CAND - off);
+            for (int r = r0; r < r1; r++) cand[off + r - base] = (unsigned short)(mystart + r);
+        }
+        __syncwarp();
+        float xj[FS_KSLOT], yj[FS_KSLOT], zj[FS_KSLOT];
+        unsigned mj[FS_KSLOT];
+        int jpos[FS_KSLOT];
+#pragma unroll
+        for (int k = 0; k < FS_KSLOT; k++) {
+            const int s = k * 32 + lane;
+            jpos[k] = -1; mj[k] = 0u; xj[k] = yj[k] = zj[k] = 0.f;
+            if (base + s < M) {
+                const int pos = cand[s];
+                const float4 q = cx.sorted[pos];
+                xj[k] = q.x; yj[k] = q.y; zj[k] = q.z;
+                mj[k] = __float_as_uint(q.w);
+                jpos[k] = pos;
+            }
+        }
+        const int left = M - base;
+        if (FLAGS & FS_COUNT) {
+            if (lane == 0) n_tests += (unsigned long long)(cend - cstart) * (unsigned long long)min(left, FS_CAND);
+        }
+        if (left > 96) fs_inner<MODE, 4, FLAGS>(p, B, cx, cstart, cend, xj, yj, zj, mj, jpos, qn);
+        else if (left > 64) fs_inner<MODE, 3, FLAGS>(p, B, cx, cstart, cend, xj, yj, zj, mj, jpos, qn);
+        else if (left > 32) fs_inner<MODE, 2, FLAGS>(p, B, cx, cstart, cend, xj, yj, zj, mj, jpos, qn);
+        else fs_inner<MODE, 1, FLAGS>(p, B, cx, cstart, cend, xj, yj, zj, mj, jpos, qn);
+    }
+}
+
+template <int MODE, int FLAGS>
+__device__ __forceinline__ void fs_pair_phase(const FrameParams& p, const NlBox& B, const GridS& G,
+                                           const FsPairCtx& cx, const unsigned short* occ, int n_occ,
+                                           int* task_counter, unsigned short* cand,
+                                           unsigned long long& n_tests)
+{
+    const int lane = threadIdx.x & 31;
+    int qn = 0;      // hits waiting in this warp's queue
     for (;;) {
         int k = 0;
         if (lane == 0) k = atomicAdd(task_counter, 1);
         k = __shfl_sync(0xffffffffu, k, 0);
         if (k >= n_occ) break;
-        cell_task<MODE, unsigned short, BitmapSink>(tp, B, G, sorted, cellptr, (int)occ[k], wscr, sink, n_tests);
+        fs_cell_task<MODE, FLAGS>(p, B, G, cx, (int)occ[k], cand, n_tests, qn);
     }
+    fs_drain_hits(p, cx, qn);
 }
 
-__global__ void __launch_bounds__(FS_THREADS, 1) k_frames_small(const FrameParams p)
+#ifndef FS_MIN_CTAS
+#define FS_MIN_CTAS 2
+#endif
+
+template <int FLAGS>
+__global__ void __launch_bounds__(FS_THREADS, FS_MIN_CTAS) k_frames_small(const FrameParams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x;
@@ -173,17 +383,19 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_frames_small(const FrameParam
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem);
     int* task_counter = reinterpret_cast<int*>(smem + 8);
     int* n_occ_s = reinterpret_cast<int*>(smem + 12);
-    float* red = reinterpret_cast<float*>(smem + 64);                 // 6 * 32 floats
+    float* red = reinterpret_cast<float*>(smem + 64);                    // 6 * 32 floats
     unsigned int* scan_s = reinterpret_cast<unsigned int*>(smem + 64);   // overlays `red`
     GridS* Gs = reinterpret_cast<GridS*>(smem + 64 + 6 * 32 * 4);
     unsigned char* raw = smem + L.raw_off;
     float4* sorted = reinterpret_cast<float4*>(smem + L.sorted_off);
+    unsigned short* sidx = reinterpret_cast<unsigned short*>(smem + L.sidx_off);
     unsigned int* cell32 = reinterpret_cast<unsigned int*>(smem + L.cell_off);
     unsigned short* cell16 = reinterpret_cast<unsigned short*>(smem + L.cell_off);
     unsigned short* occ = reinterpret_cast<unsigned short*>(smem + L.occ_off);
     unsigned int* bitmap = p.bm_in_smem ? reinterpret_cast<unsigned int*>(smem + L.bm_off)
                                         : p.g_bitmap + (size_t)blockIdx.x * (size_t)p.bm_words;
-    int* wscr = reinterpret_cast<int*>(smem + L.wscr_off) + warp * 64;
+    unsigned short* cand = reinterpret_cast<unsigned short*>(smem + L.cand_off) + warp * FS_CAND;
+    unsigned int* hitq = reinterpret_cast<unsigned int*>(smem + L.hitq_off) + warp * FS_HITQ;
 
     if (tid == 0) {
         mbar_init(mbar, 1);
@@ -197,7 +409,6 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_frames_small(const FrameParam
     const long long stride = gridDim.x;
     long long f = blockIdx.x;
 
-    // prologue: fetch this CTA's first frame
     auto issue_load = [&](long long frame) {
         const unsigned long long addr = (unsigned long long)(p.xyz + (size_t)frame * (size_t)n * 3);
         const unsigned long long a0 = addr & ~15ull;
@@ -294,8 +505,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_frames_small(const FrameParam
                 const unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
                 if (lane >= d) incl += v;
             }
-            __syncthreads();              // `red` (overlaid by scan_s) no longer needed
-            if (lane == 31) scan_s[warp] = incl;
+            if (lane == 31) scan_s[warp] = incl;     // `red` was consumed before the barriers above
             __syncthreads();
             if (warp == 0) {
                 unsigned v = lane < FS_WARPS ? scan_s[lane] : 0u;
@@ -321,13 +531,15 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_frames_small(const FrameParam
         }
         __syncthreads();
 
-        // ---- pass C: scatter into the cell-sorted float4 array -----------------------
+        // ---- pass C: scatter into the cell-sorted arrays ------------------------------
 #pragma unroll
         for (int k = 0; k < FS_APT; k++) {
             const int i = tid + k * FS_THREADS;
             if (i < n) {
                 const int pos = (int)cell16[my_cell[k]] + my_rank[k];
-                sorted[pos] = make_float4(xr[3 * i], xr[3 * i + 1], xr[3 * i + 2], __int_as_float(i));
+                sorted[pos] = make_float4(xr[3 * i], xr[3 * i + 1], xr[3 * i + 2],
+                                          __uint_as_float(__ldg(&p.meta32[i])));
+                sidx[pos] = (unsigned short)i;
             }
         }
         __syncthreads();
@@ -338,20 +550,16 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_frames_small(const FrameParam
         }
 
         // ---- pass D: pair phase, one warp per occupied cell ---------------------------
+        FsPairCtx cx;
+        cx.sorted = sorted; cx.sidx = sidx; cx.cellptr = cell16; cx.bitmap = bitmap; cx.hitq = hitq;
+        cx.frame_id = p.frame0 + f;
         const int n_occ = *n_occ_s;
-        const long long frame_id = p.frame0 + f;
-        TaskParams tp;
-        tp.meta = p.meta; tp.n = n; tp.n_ignored = p.n_ignored; tp.c2 = p.c2; tp.c2_hi = p.c2_hi;
-        tp.boundary_ulps = p.boundary_ulps; tp.atom_table = p.atom_table; tp.atom_keys = p.atom_keys;
-        tp.atom_cap = p.atom_cap; tp.counters = p.counters; tp.boundary = p.boundary;
-        tp.boundary_cap = p.boundary_cap; tp.frame_id = frame_id; tp.count_tests = p.count_tests;
-        BitmapSink sink{bitmap, (unsigned)p.n_res_c};
         if (B.mode == BOX_ORTHO)
-            fs_pair_phase<BOX_ORTHO>(tp, B, G, sorted, cell16, occ, n_occ, task_counter, wscr, sink, n_tests);
+            fs_pair_phase<BOX_ORTHO, FLAGS>(p, B, G, cx, occ, n_occ, task_counter, cand, n_tests);
         else if (B.mode == BOX_TRICLINIC)
-            fs_pair_phase<BOX_TRICLINIC>(tp, B, G, sorted, cell16, occ, n_occ, task_counter, wscr, sink, n_tests);
+            fs_pair_phase<BOX_TRICLINIC, FLAGS>(p, B, G, cx, occ, n_occ, task_counter, cand, n_tests);
         else
-            fs_pair_phase<BOX_NONE>(tp, B, G, sorted, cell16, occ, n_occ, task_counter, wscr, sink, n_tests);
+            fs_pair_phase<BOX_NONE, FLAGS>(p, B, G, cx, occ, n_occ, task_counter, cand, n_tests);
         __syncthreads();
 
         // ---- pass E: flush the per-frame residue bitmap ------------------------------
@@ -367,7 +575,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_frames_small(const FrameParam
                         atomicAdd(&p.res_table[(size_t)w * 32 + b], 1u);
                     }
                 }
-                if (p.res_keys != nullptr) {
+                if ((FLAGS & FS_EMIT) && p.res_keys != nullptr) {
                     const unsigned long long wbase = atomicAdd(&p.counters[1], (unsigned long long)__popc(v));
                     unsigned t = v;
                     unsigned long long o = 0;
@@ -377,7 +585,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_frames_small(const FrameParam
                         const unsigned bit = (unsigned)w * 32u + (unsigned)b;
                         const unsigned rlo = bit / (unsigned)p.n_res_c, rhi = bit % (unsigned)p.n_res_c;
                         if ((long long)(wbase + o) < p.res_cap)
-                            p.res_keys[wbase + o] = ((unsigned long long)frame_id << 40) |
+                            p.res_keys[wbase + o] = ((unsigned long long)cx.frame_id << 40) |
                                                     ((unsigned long long)rlo << 20) | (unsigned long long)rhi;
                         o++;
                     }
@@ -386,7 +594,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_frames_small(const FrameParam
         }
         __syncthreads();
     }
-    if (p.count_tests) {
+    if (FLAGS & FS_COUNT) {
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) n_tests += __shfl_xor_sync(0xffffffffu, n_tests, d);
         if (lane == 0 && n_tests) atomicAdd(&p.counters[3], n_tests);
