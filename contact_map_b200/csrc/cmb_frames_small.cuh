@@ -269,6 +269,13 @@ __device__ __forceinline__ void fs_inner(const FrameParams& p, const NlBox& B, c
 }
 
 // One warp adjudicates all candidate pairs of one occupied cell `c`.
+//
+// Candidates are the atoms of the stencil cells with id >= c (every unordered cell pair is
+// visited once).  Cells are numbered x-fastest, so for an INTERIOR cell (no periodic wrap, no
+// grid edge) they form five contiguous runs of the cell-sorted array:
+//     (cx..cx+1, cy, cz), (cx-1..cx+1, cy+1, cz), (cx-1..cx+1, cy-1..cy+1, cz+1)
+// and a candidate slot maps to its sorted position with four compares.  Edge cells take the
+// generic route: stencil lanes, de-duplication, warp scan, per-warp candidate list.
 template <int MODE, int FLAGS>
 __device__ __forceinline__ void fs_cell_task(const FrameParams& p, const NlBox& B, const GridS& G,
                                              const FsPairCtx& cx, int c, unsigned short* cand,
@@ -280,58 +287,87 @@ __device__ __forceinline__ void fs_cell_task(const FrameParams& p, const NlBox& 
     const int cxx = c - cyz * G.nx;
     const int cz = (int)__umulhi((unsigned)cyz << 6, G.magic_y);
     const int cy = cyz - cz * G.ny;
-
-    // neighbour cells: lanes 0..26 of the stencil, kept only if their id >= own id
-    int myD = -1;
-    if (lane < 27) {
-        const int l9 = lane / 9, l3 = (lane - l9 * 9) / 3;
-        int x = cxx + (lane - l9 * 9 - l3 * 3) - 1;
-        int y = cy + l3 - 1;
-        int z = cz + l9 - 1;
-        if (G.periodic) {
-            x = x < 0 ? x + G.nx : (x >= G.nx ? x - G.nx : x);
-            y = y < 0 ? y + G.ny : (y >= G.ny ? y - G.ny : y);
-            z = z < 0 ? z + G.nz : (z >= G.nz ? z - G.nz : z);
-        }
-        const bool ok = (x >= 0 && x < G.nx && y >= 0 && y < G.ny && z >= 0 && z < G.nz);
-        if (ok) myD = (z * G.ny + y) * G.nx + x;
-    }
-    bool keep = (myD >= c);
-    if (!G.distinct) {   // grids with < 3 cells along a dimension: drop duplicate stencil cells
-        const unsigned same = __match_any_sync(FULL, myD);
-        keep = keep && ((__ffs(same) - 1) == lane);
-    }
-    int mystart = 0, mycnt = 0;
-    if (keep) {
-        mystart = (int)cx.cellptr[myD];
-        mycnt = (int)cx.cellptr[myD + 1] - mystart;
-    }
-    int incl = mycnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int v = __shfl_up_sync(FULL, incl, d);
-        if (lane >= d) incl += v;
-    }
-    const int M = __shfl_sync(FULL, incl, 31);
-    const int off = incl - mycnt;
     const int cstart = (int)cx.cellptr[c], cend = (int)cx.cellptr[c + 1];
 
+    const bool interior = (cxx >= 1) && (cxx <= G.nx - 2) && (cy >= 1) && (cy <= G.ny - 2) &&
+                          (cz >= 1) && (cz <= G.nz - 2);
+    int M;
+    // interior: run r covers slots [o_r, o_{r+1}) and sorted positions slot + a_r
+    int o1 = 0, o2 = 0, o3 = 0, o4 = 0, a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+    // generic: this lane's stencil cell
+    int mystart = 0, mycnt = 0, off = 0;
+    if (interior) {
+        const int nxy = G.nx * G.ny;
+        const int b1 = c + G.nx - 1, b2 = c + nxy - G.nx - 1, b3 = c + nxy - 1, b4 = c + nxy + G.nx - 1;
+        const int s0 = cstart, e0 = (int)cx.cellptr[c + 2];
+        const int s1 = (int)cx.cellptr[b1], e1 = (int)cx.cellptr[b1 + 3];
+        const int s2 = (int)cx.cellptr[b2], e2 = (int)cx.cellptr[b2 + 3];
+        const int s3 = (int)cx.cellptr[b3], e3 = (int)cx.cellptr[b3 + 3];
+        const int s4 = (int)cx.cellptr[b4], e4 = (int)cx.cellptr[b4 + 3];
+        o1 = e0 - s0; o2 = o1 + (e1 - s1); o3 = o2 + (e2 - s2); o4 = o3 + (e3 - s3);
+        M = o4 + (e4 - s4);
+        a0 = s0; a1 = s1 - o1; a2 = s2 - o2; a3 = s3 - o3; a4 = s4 - o4;
+    } else {
+        int myD = -1;
+        if (lane < 27) {
+            const int l9 = lane / 9, l3 = (lane - l9 * 9) / 3;
+            int x = cxx + (lane - l9 * 9 - l3 * 3) - 1;
+            int y = cy + l3 - 1;
+            int z = cz + l9 - 1;
+            if (G.periodic) {
+                x = x < 0 ? x + G.nx : (x >= G.nx ? x - G.nx : x);
+                y = y < 0 ? y + G.ny : (y >= G.ny ? y - G.ny : y);
+                z = z < 0 ? z + G.nz : (z >= G.nz ? z - G.nz : z);
+            }
+            const bool ok = (x >= 0 && x < G.nx && y >= 0 && y < G.ny && z >= 0 && z < G.nz);
+            if (ok) myD = (z * G.ny + y) * G.nx + x;
+        }
+        bool keep = (myD >= c);
+        if (!G.distinct) {   // grids with < 3 cells along a dimension: drop duplicate stencil cells
+            const unsigned same = __match_any_sync(FULL, myD);
+            keep = keep && ((__ffs(same) - 1) == lane);
+        }
+        if (keep) {
+            mystart = (int)cx.cellptr[myD];
+            mycnt = (int)cx.cellptr[myD + 1] - mystart;
+        }
+        int incl = mycnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl += v;
+        }
+        M = __shfl_sync(FULL, incl, 31);
+        off = incl - mycnt;
+    }
+
     for (int base = 0; base < M; base += FS_CAND) {
-        __syncwarp();
-        {   // expand this lane's neighbour cell into the per-warp candidate list
+        if (!interior) {
+            __syncwarp();
+            // expand this lane's stencil cell into the per-warp candidate list
             const int r0 = max(0, base - off), r1 = min(mycnt, base + FS_CAND - off);
             for (int r = r0; r < r1; r++) cand[off + r - base] = (unsigned short)(mystart + r);
+            __syncwarp();
         }
-        __syncwarp();
         float xj[FS_KSLOT], yj[FS_KSLOT], zj[FS_KSLOT];
         unsigned mj[FS_KSLOT];
         int jpos[FS_KSLOT];
 #pragma unroll
         for (int k = 0; k < FS_KSLOT; k++) {
-            const int s = k * 32 + lane;
+            const int s = base + k * 32 + lane;
             jpos[k] = -1; mj[k] = 0u; xj[k] = yj[k] = zj[k] = 0.f;
-            if (base + s < M) {
-                const int pos = cand[s];
+            if (s < M) {
+                int pos;
+                if (interior) {
+                    int adj = a0;
+                    adj = s >= o1 ? a1 : adj;
+                    adj = s >= o2 ? a2 : adj;
+                    adj = s >= o3 ? a3 : adj;
+                    adj = s >= o4 ? a4 : adj;
+                    pos = s + adj;
+                } else {
+                    pos = cand[s - base];
+                }
                 const float4 q = cx.sorted[pos];
                 xj[k] = q.x; yj[k] = q.y; zj[k] = q.z;
                 mj[k] = __float_as_uint(q.w);

@@ -1,0 +1,181 @@
+"""GPU: the global-memory cell path, the device generator, the boundary report and
+size-independent properties at BASELINE.json's full sizes."""
+import numpy as np
+import pytest
+import torch
+
+from contact_map_b200 import synth
+from oracle import clib
+from tests.helpers import system_arrays, dense_from_export, keys_to_frames
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(engine, system, frame0, n_frames):
+    dev = engine.device
+    xyz = engine.synth_frames(torch.as_tensor(system.base, device=dev),
+                              torch.as_tensor(system.groups.astype(np.int32), device=dev),
+                              None if system.box is None else torch.as_tensor(system.box.reshape(9), device=dev),
+                              system.seed, system.amplitude, system.image_shifts, frame0, n_frames)
+    box = None if system.box is None else \
+        torch.as_tensor(system.box, device=dev).reshape(1, 3, 3).expand(n_frames, 3, 3).contiguous()
+    return xyz, box
+
+
+@pytest.mark.parametrize("which", ["s1", "s3", "open"])
+def test_device_generator_bit_identical_to_host(engine, which):
+    if which == "s1":
+        system = synth.kras_like()
+    elif which == "s3":
+        system = synth.solvated_triclinic(n_atoms=5000, lattice=18)
+    else:
+        system = synth.random_system(np.random.default_rng(2), 300, box_kind="none")
+    xyz, _ = _dev(engine, system, 37, 5)
+    host = system.frames(37, 5)
+    assert np.array_equal(xyz.cpu().numpy().view(np.uint32), host.view(np.uint32))
+
+
+@pytest.mark.parametrize("box_kind", ["ortho", "triclinic", "none"])
+def test_large_path_forced_on_small_systems(engine, box_kind):
+    """The global-memory cell path (kl_* kernels) against the oracle and the fused kernel."""
+    rng = np.random.default_rng(77)
+    system = synth.random_system(rng, 700, n_chains=3, box_kind=box_kind, extent=2.4)
+    query = np.sort(rng.choice(700, size=500, replace=False))
+    hay = np.sort(rng.choice(700, size=600, replace=False))
+    res, chain, role = system_arrays(system, query, hay)
+    n_frames = 4
+    xyz = system.frames(0, n_frames)
+    box = None if system.box is None else np.broadcast_to(system.box, (n_frames, 3, 3)).copy()
+    ref_atom, ref_res = clib.accumulate_dense(xyz, box, 0.45, res, chain, role, 2, system.topology.n_residues)
+    d_xyz = torch.as_tensor(xyz, device=engine.device)
+    d_box = None if box is None else torch.as_tensor(box, device=engine.device)
+    results = []
+    for force in (1, 0):
+        engine.set_option("force_path", force)
+        engine.set_system(res, chain, role, 0.45, 2)
+        assert engine.path_kind == force
+        atom_t, res_t = engine.new_tables()
+        engine.accumulate(d_xyz, d_box, atom_t, res_t)
+        idx, cnt = engine.export_nonzero(atom_t)
+        got = dense_from_export(idx, cnt, 700)
+        assert np.array_equal(got, ref_atom)
+        ridx, rcnt = engine.export_nonzero(res_t)
+        rmap = engine.residue_map
+        assert np.array_equal(dense_from_export(ridx, rcnt, engine.n_res_c), ref_res[np.ix_(rmap, rmap)])
+        akeys, rkeys = engine.frame_contacts(d_xyz, d_box)
+        results.append((akeys, rkeys))
+        assert len(akeys) == int(ref_atom.sum()) and len(rkeys) == int(ref_res.sum())
+    engine.set_option("force_path", -1)
+    assert np.array_equal(results[0][0], results[1][0]) and np.array_equal(results[0][1], results[1][1])
+
+
+def test_large_system_matches_oracle(engine):
+    """n_used > 6144: S3-like solvated triclinic system (12 000 atoms), two frames."""
+    system = synth.solvated_triclinic(n_atoms=12000, lattice=23)
+    res, chain, role = system_arrays(system)
+    n = system.n_atoms
+    engine.set_system(res, chain, role, 0.45, 2)
+    assert engine.path_kind == 1
+    xyz, box = _dev(engine, system, 0, 2)
+    akeys, rkeys = engine.frame_contacts(xyz, box)
+    frame, lo, hi = keys_to_frames(akeys)
+    h_xyz = xyz.cpu().numpy()
+    for f in range(2):
+        want = clib.contacts_frame(h_xyz[f], system.box, 0.45, res, chain, role, 2, cells=True)
+        sel = frame == f
+        assert np.array_equal(np.stack([lo[sel], hi[sel]], axis=1), want)
+        assert len(want) > 50000
+    # tables == sum of the per-frame keys
+    atom_t, res_t = engine.new_tables()
+    engine.accumulate(xyz, box, atom_t, res_t)
+    assert int(atom_t.sum().item()) == len(akeys)
+    assert int(res_t.sum().item()) == len(rkeys)
+    idx, cnt = engine.export_nonzero(atom_t)
+    flat, counts = np.unique(lo * n + hi, return_counts=True)
+    assert np.array_equal(idx, flat) and np.array_equal(cnt, counts.astype(np.uint32))
+
+
+def test_boundary_report_matches_oracle(engine):
+    """north_star: pairs within 1 ulp of the cutoff are enumerated.  A dense jittered system has
+    a few such pairs at ulps=64; the lists must agree exactly with the oracle's."""
+    system = synth.kras_like()
+    res, chain, role = system_arrays(system)
+    engine.set_system(res, chain, role, 0.45, 2)
+    n_frames = 6
+    xyz, box = _dev(engine, system, 0, n_frames)
+    h = xyz.cpu().numpy()
+    for ulps in (1, 64):
+        rec = engine.boundary_pairs(xyz, box, ulps=ulps)
+        want = []
+        for f in range(n_frames):
+            a, b, d2 = clib.boundary_pairs(h[f], system.box, 0.45, res, chain, role, 2, ulps=ulps)
+            want.extend((f, int(x), int(y), float(z)) for x, y, z in zip(a, b, d2))
+        got = [(int(r["frame"]), int(r["a"]), int(r["b"]), float(r["d2"])) for r in rec]
+        assert got == sorted(want)
+    assert len(got) > 0
+
+
+def test_full_size_properties_s1(engine):
+    """BASELINE configs[1] at full size (10 000 frames): partition invariance, host == device,
+    table mass == number of per-frame keys, oracle spot checks."""
+    system = synth.kras_like()
+    res, chain, role = system_arrays(system)
+    n = system.n_atoms
+    engine.set_system(res, chain, role, 0.45, 2)
+    F = 10000
+    xyz, box = _dev(engine, system, 0, F)
+    total_a, total_r = engine.new_tables()
+    engine.accumulate(xyz, box, total_a, total_r)
+    # (1) partition invariance: three uneven shards into one pair of tables
+    part_a, part_r = engine.new_tables()
+    for a, b in ((0, 1), (1, 4097), (4097, F)):
+        engine.accumulate(xyz[a:b], box[a:b], part_a, part_r)
+    assert torch.equal(part_a, total_a) and torch.equal(part_r, total_r)
+    # (2) frame order does not matter
+    perm = torch.randperm(F, device=engine.device, generator=torch.Generator(engine.device).manual_seed(1))
+    perm_a, perm_r = engine.new_tables()
+    engine.accumulate(xyz[perm].contiguous(), box[perm].contiguous(), perm_a, perm_r)
+    assert torch.equal(perm_a, total_a) and torch.equal(perm_r, total_r)
+    # (3) host-buffer entry point == device entry point
+    host_a, host_r = engine.new_tables()
+    engine.accumulate_host(xyz.cpu().numpy(), box.cpu().numpy(), host_a, host_r)
+    assert torch.equal(host_a, total_a) and torch.equal(host_r, total_r)
+    # (4) mass: sum of the tables == number of per-frame keys; counts bounded by F
+    akeys, rkeys = engine.frame_contacts(xyz[:2000], box[:2000])
+    sub_a, sub_r = engine.new_tables()
+    engine.accumulate(xyz[:2000], box[:2000], sub_a, sub_r)
+    assert int(sub_a.sum().item()) == len(akeys) and int(sub_r.sum().item()) == len(rkeys)
+    assert int(total_a.max().item()) <= F and int(total_r.max().item()) <= F
+    # (5) strictly upper-triangular, nothing inside the exclusion band
+    idx, cnt = engine.export_nonzero(total_a)
+    lo, hi = idx // n, idx % n
+    assert np.all(lo < hi) and np.all(np.abs(res[lo] - res[hi]) > 2)
+    # (6) oracle on sampled frames
+    h = xyz[[0, 1, F // 2, F - 1]].cpu().numpy()
+    frame, klo, khi = keys_to_frames(engine.frame_contacts(xyz[[0, 1, F // 2, F - 1]].contiguous(),
+                                                           box[:4].contiguous())[0])
+    for f in range(4):
+        want = clib.contacts_frame(h[f], system.box, 0.45, res, chain, role, 2, cells=True)
+        sel = frame == f
+        assert np.array_equal(np.stack([klo[sel], khi[sel]], axis=1), want)
+
+
+def test_binding_system_s2_matches_oracle(engine):
+    """BASELINE configs[2]: query = partner chain, haystack = receptor (first 48 frames vs oracle)."""
+    system = synth.binding_system()
+    res, chain, role = system_arrays(system, system.query, system.haystack)
+    engine.set_system(res, chain, role, 0.45, 2)
+    F = 48
+    xyz, box = _dev(engine, system, 0, F)
+    atom_t, res_t = engine.new_tables()
+    engine.accumulate(xyz, box, atom_t, res_t)
+    idx, cnt = engine.export_nonzero(atom_t)
+    n = system.n_atoms
+    h_xyz, h_box = xyz.cpu().numpy(), box.cpu().numpy()
+    ref_atom, ref_res = clib.accumulate_dense(h_xyz, h_box, 0.45, res, chain, role, 2,
+                                              system.topology.n_residues)
+    assert np.array_equal(dense_from_export(idx, cnt, n), ref_atom)
+    assert ref_atom.sum() > 100
+    # every contact joins the partner (query) with the receptor (haystack)
+    lo, hi = idx // n, idx % n
+    assert np.all((role[lo] | role[hi]) == 3) and np.all(role[lo] != role[hi])
