@@ -341,7 +341,8 @@ def run_ours(args):
     traffic = None
     traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_path):
-        traffic = json.load(open(traffic_path)).get("k_frames_small_dram_bytes_per_launch")
+        per_frame = json.load(open(traffic_path)).get("k_frames_small_dram_bytes_per_frame")
+        traffic = None if per_frame is None else per_frame * F    # ncu capture, scaled to this launch
     sm_count = engine.get_stat("sm_count")
     sm_mhz = clocks.get("sm_mhz") or 1965.0
     # FP32 view: executed pair tests x 23 separately rounded fp32 ops (orthorhombic) per test
