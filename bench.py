@@ -209,9 +209,22 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     device = torch.device("cuda", local_rank)
+    if world > 1:
+        # NCCL prints its version banner on stdout at communicator creation; keep stdout for the
+        # single JSON line by pointing fd 1 at stderr until the first collective has run
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=device)
+            warm = torch.zeros(1, device=device)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     import contact_map_b200 as cm
     from contact_map_b200 import parallel, synth
@@ -254,7 +267,7 @@ def run_ours(args):
             e1.record()
             kern_events.append((e0, e1))
         parallel.reduce_tables([atom_t, res_t])
-        return engine.export_nonzero(atom_t), engine.export_nonzero(res_t)
+        return engine.export_many([atom_t, res_t])
 
     for _ in range(max(args.warmup, 3)):      # timing rule: at least 3 warm-up steps
         out = step(False)

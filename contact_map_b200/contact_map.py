@@ -390,10 +390,9 @@ def _used_coordinates(xyz, box, used, n_total, engine):
 def _tables_to_pairs(engine, atom_table, res_table, used):
     """Sparse export of the device tables -> (atom PairTable, residue PairTable) in REAL indices."""
     n = engine.n_used
-    idx, cnt = engine.export_nonzero(atom_table)
+    (idx, cnt), (ridx, rcnt) = engine.export_many([atom_table, res_table])
     atoms = PairTable(used[idx // n], used[idx % n], cnt.astype(np.int64))
     rc = engine.n_res_c
-    ridx, rcnt = engine.export_nonzero(res_table)
     rmap = engine.residue_map.astype(np.int64)
     residues = PairTable(rmap[ridx // rc], rmap[ridx % rc], rcnt.astype(np.int64))
     return atoms, residues

@@ -149,23 +149,68 @@ class ContactEngine(object):
 
     def export_nonzero(self, table):
         """(flat index int64[], count uint32[]) of the non-zero entries, sorted by index."""
-        nnz = int(torch.count_nonzero(table).item())
-        if nnz == 0:
-            return np.empty(0, dtype=np.int64), np.empty(0, dtype=np.uint32)
-        idx = torch.empty(nnz, dtype=torch.int64, device=self.device)
-        cnt = torch.empty(nnz, dtype=torch.int32, device=self.device)
-        n_out = torch.zeros(1, dtype=torch.int64, device=self.device)
+        return self.export_many([table])[0]
+
+    def export_many(self, tables):
+        """Sparse export of several count tables with ONE host synchronisation.
+
+        Every table is scanned by ``cmb_export_nonzero`` into capacity-sized device buffers; the
+        counters and the buffers are copied to pinned host memory asynchronously and the stream
+        is synchronised once.  Capacities come from the previous export of a table of the same
+        size (first use: ``count_nonzero``); an overflow triggers one exact retry.
+        Returns [(flat index int64[], count uint32[]), ...], each sorted by index.
+        """
+        hints = self.__dict__.setdefault("_export_hint", {})
+        stream = torch.cuda.current_stream(self.device)
+        jobs = []
         with torch.cuda.device(self.device):
-            self._check(self._L.cmb_export_nonzero(self._ctx, _ptr(table), table.numel(), nnz,
-                                                   _ptr(idx), _ptr(cnt), _ptr(n_out),
-                                                   _stream_ptr(self.device)), "cmb_export_nonzero")
-        got = int(n_out.item())
-        if got != nnz:
-            raise EngineError("export found %d entries, expected %d" % (got, nnz))
-        idx_h = idx.cpu().numpy()
-        cnt_h = cnt.cpu().numpy().view(np.uint32)
-        order = np.argsort(idx_h, kind="stable")
-        return idx_h[order], cnt_h[order]
+            for t in tables:
+                numel = t.numel()
+                cap = hints.get(numel)
+                if cap is None:
+                    cap = int(torch.count_nonzero(t).item())
+                cap = max(16, min(numel, cap + cap // 4 + 1024))
+                jobs.append(self._export_launch(t, cap, len(jobs)))
+            stream.synchronize()
+            out = []
+            for slot, (t, job) in enumerate(zip(tables, jobs)):
+                n = int(job["h_n"][0])
+                if n > job["cap"]:            # capacity guess too small: exact retry
+                    job = self._export_launch(t, n, slot)
+                    stream.synchronize()
+                    n = int(job["h_n"][0])
+                hints[t.numel()] = n
+                idx_h = job["h_idx"][:n].numpy().copy()
+                cnt_h = job["h_cnt"][:n].numpy().view(np.uint32).copy()
+                order = np.argsort(idx_h, kind="stable")
+                out.append((idx_h[order], cnt_h[order]))
+        return out
+
+    def _export_launch(self, table, cap, slot):
+        # staging buffers are keyed by (table size, position in the call) and reused across calls
+        pool = self.__dict__.setdefault("_export_pool", {})
+        buf = pool.get((table.numel(), slot))
+        if buf is None or buf["cap"] < cap:
+            buf = {
+                "cap": cap,
+                "d_idx": torch.empty(cap, dtype=torch.int64, device=self.device),
+                "d_cnt": torch.empty(cap, dtype=torch.int32, device=self.device),
+                "d_n": torch.zeros(1, dtype=torch.int64, device=self.device),
+                "h_idx": torch.empty(cap, dtype=torch.int64, pin_memory=True),
+                "h_cnt": torch.empty(cap, dtype=torch.int32, pin_memory=True),
+                "h_n": torch.zeros(1, dtype=torch.int64, pin_memory=True),
+            }
+            if len(pool) > 8:
+                pool.clear()
+            pool[(table.numel(), slot)] = buf
+        buf["d_n"].zero_()
+        self._check(self._L.cmb_export_nonzero(self._ctx, _ptr(table), table.numel(), buf["cap"],
+                                               _ptr(buf["d_idx"]), _ptr(buf["d_cnt"]), _ptr(buf["d_n"]),
+                                               _stream_ptr(self.device)), "cmb_export_nonzero")
+        buf["h_n"].copy_(buf["d_n"], non_blocking=True)
+        buf["h_idx"].copy_(buf["d_idx"], non_blocking=True)
+        buf["h_cnt"].copy_(buf["d_cnt"], non_blocking=True)
+        return buf
 
     def frame_contacts(self, xyz, box, frame0=0, atom_table=None, res_table=None,
                        want_atoms=True, want_residues=True, cap_hint=None):
