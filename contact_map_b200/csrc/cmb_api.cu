@@ -421,6 +421,7 @@ static int launch_frames(cmb_ctx* ctx, const FrameJob& job, int slot, cudaStream
     lj.res_keys = job.res_keys; lj.res_cap = job.res_cap;
     lj.counters = counters; lj.boundary = job.boundary; lj.boundary_cap = job.boundary_cap;
     lj.count_tests = ctx->count_tests;
+    lj.all_roles = ctx->all_roles ? 1 : 0;
     std::string err;
     int launches = 0;
     int rc = large_run(lj, ctx->large[slot], ctx->sm_count, stream, err, launches);

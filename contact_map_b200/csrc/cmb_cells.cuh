@@ -121,168 +121,296 @@ __device__ __forceinline__ int cell_of(const GridS& G, float x, float y, float z
 }
 
 
-// ----- pair eligibility ----------------------------------------------------------
-// meta = {ekey, res_c | role << 30}; role bit0 = query, bit1 = haystack
-__device__ __forceinline__ bool pair_allowed(int2 mi, int2 mj, int n_ignored)
-{
-    const unsigned ri = (unsigned)mi.y >> 30, rj = (unsigned)mj.y >> 30;
-    const unsigned role_ok = (ri & (rj >> 1)) | (rj & (ri >> 1));
-    int de = mi.x - mj.x;
-    de = de < 0 ? -de : de;
-    return (role_ok & 1u) && (de > n_ignored);
-}
+// =================================================================================
+// Pair phase shared by both paths.
+//
+// The frame's atoms are cell-sorted into `sorted[pos] = {x, y, z, word}` where `word` packs the
+// exclusion key (low bits) and the role bits (bit 30 = query, bit 31 = haystack); `sidx[pos]` is
+// the atom index.  A `Traits` type fixes the integer widths of the two paths:
+//   pos_t       element type of cellptr / sidx / the per-warp candidate list
+//   EKEY_MASK   mask of the exclusion key inside `word`
+//   decode()    cell id -> (cx, cy, cz)
+//   hit_t       queue entry of one hit, with pack()/ipos()/jpos()
+// and a `Sink` object accounts one hit (atom table, residue de-duplication).
+// =================================================================================
+constexpr int CT_KSLOT = 4;                 // register-resident candidates per lane
+constexpr int CT_CAND = 32 * CT_KSLOT;      // candidates per chunk
+constexpr int CT_HITQ = 64;                 // per-warp queue of compacted hits
 
-// Everything a cell task needs besides the geometry.
-struct TaskParams {
-    const int2* meta;            // [n] {ekey, res_c | role << 30}
-    int n;
+// kernel variants (template FLAGS)
+constexpr int CT_EMIT = 1;        // emit (frame, a, b) keys
+constexpr int CT_BOUNDARY = 2;    // report pairs within boundary_ulps of the cutoff
+constexpr int CT_COUNT = 4;       // count executed pair tests
+constexpr int CT_ROLES = 8;       // query / haystack are not "all atoms": test the roles
+
+// hot-loop parameters (everything a cell task needs besides the geometry)
+struct PairParams {
+    int n;                           // used atoms
     int n_ignored;
-    float c2;                    // cutoff_f * cutoff_f
-    float c2_hi;                 // c2 advanced by boundary_ulps float steps (== c2 when off)
+    float c2;                        // cutoff_f * cutoff_f
+    float c2_hi;                     // c2 advanced by boundary_ulps float steps
     int boundary_ulps;
-    unsigned int* atom_table;    // [n][n] uint32 (entry [lo][hi]) or nullptr
+    unsigned int* atom_table;        // [n][n] uint32 (entry [lo][hi]) or nullptr
     unsigned long long* atom_keys;   // emitted (frame<<40 | lo<<20 | hi) or nullptr
     long long atom_cap;
     unsigned long long* counters;    // [0] atom keys, [1] residue keys, [2] boundary records, [3] pair tests
-    float4* boundary;            // records {frame, lo, hi, d2} (ints bit-cast) or nullptr
+    float4* boundary;                // records {frame, lo, hi, d2} (ints bit-cast) or nullptr
     long long boundary_cap;
     long long frame_id;
-    int count_tests;
 };
 
-constexpr int CT_KSLOT = 4;      // register-resident candidates per lane
+template <typename Traits>
+struct PairCtx {
+    const float4* sorted;                       // [n] {x, y, z, word}
+    const typename Traits::pos_t* sidx;         // [n] atom index of each sorted position
+    const typename Traits::pos_t* cellptr;      // [ncell + 1]
+    typename Traits::pos_t* cand;               // this warp's candidate list [CT_CAND]
+    typename Traits::hit_t* hitq;               // this warp's hit queue [CT_HITQ]
+};
 
-// One warp adjudicates all candidate pairs of one occupied cell `c`:
-//  * the <= 27 stencil cells are enumerated by lanes 0..26, de-duplicated (grids with
-//    fewer than 3 cells along a dimension) and kept only if their id >= c, so every
-//    unordered cell pair is visited once;
-//  * candidates (own cell + kept neighbours) are loaded CT_KSLOT per lane into
-//    registers, the cell's own atoms are broadcast one by one;
-//  * sorted position order (jpos > ipos) removes self pairs and double visits.
-// CellT: element type of the exclusive cell prefix (`cellptr[ncell+1]`).
-// Sink: object with  __device__ void residue(int rlo, int rhi)  called for every hit.
-template <int MODE, typename CellT, typename Sink>
-__device__ __forceinline__ void cell_task(const TaskParams& p, const NlBox& B, const GridS& G,
-                                          const float4* __restrict__ sorted,
-                                          const CellT* __restrict__ cellptr, int c, int* wscr,
-                                          Sink& sink, unsigned long long& n_tests)
+// Warp-ballot compaction: the hits of one slot iteration (a few % of the lanes) are appended to
+// the warp's queue and accounted 32 at a time with all lanes busy.
+template <typename Traits, typename Sink>
+__device__ __forceinline__ void ct_queue_hits(const PairCtx<Traits>& cx, Sink& sink, bool hit, int ipos,
+                                              int jpos, int& qn)
+{
+    const unsigned hm = __ballot_sync(0xffffffffu, hit);
+    if (hm == 0u) return;
+    const int lane = threadIdx.x & 31;
+    if (hit) cx.hitq[qn + __popc(hm & ((1u << lane) - 1u))] = Traits::pack(ipos, jpos);
+    qn += __popc(hm);
+    if (qn >= 32) {
+        __syncwarp();
+        const typename Traits::hit_t e = cx.hitq[lane];
+        typename Traits::hit_t rest = Traits::pack(0, 0);
+        if (32 + lane < qn) rest = cx.hitq[32 + lane];
+        __syncwarp();
+        cx.hitq[lane] = rest;
+        qn -= 32;
+        sink.account(Traits::ipos(e), Traits::jpos(e));
+    }
+}
+
+template <typename Traits, typename Sink>
+__device__ __forceinline__ void ct_drain_hits(const PairCtx<Traits>& cx, Sink& sink, int& qn)
+{
+    __syncwarp();
+    const int lane = threadIdx.x & 31;
+    if (lane < qn) {
+        const typename Traits::hit_t e = cx.hitq[lane];
+        sink.account(Traits::ipos(e), Traits::jpos(e));
+    }
+    qn = 0;
+    __syncwarp();
+}
+
+// all (own atom) x (NK register slots) tests of one candidate chunk
+template <typename Traits, typename Sink, int MODE, int NK, int FLAGS>
+__device__ __forceinline__ void ct_inner(const PairParams& p, const NlBox& B, const PairCtx<Traits>& cx,
+                                         Sink& sink, int cstart, int cend, const float (&xj)[CT_KSLOT],
+                                         const float (&yj)[CT_KSLOT], const float (&zj)[CT_KSLOT],
+                                         const unsigned (&mj)[CT_KSLOT], const int (&jpos)[CT_KSLOT], int& qn)
 {
     const int lane = threadIdx.x & 31;
-    const unsigned FULL = 0xffffffffu;
-    const int cx = c % G.nx;
-    const int cyz = c / G.nx;
-    const int cy = cyz % G.ny;
-    const int cz = cyz / G.ny;
-
-    int myD = -1;
-    if (lane < 27) {
-        int x = cx + (lane % 3) - 1;
-        int y = cy + ((lane / 3) % 3) - 1;
-        int z = cz + (lane / 9) - 1;
-        if (G.periodic) {
-            x = x < 0 ? x + G.nx : (x >= G.nx ? x - G.nx : x);
-            y = y < 0 ? y + G.ny : (y >= G.ny ? y - G.ny : y);
-            z = z < 0 ? z + G.nz : (z >= G.nz ? z - G.nz : z);
-        }
-        const bool ok = (x >= 0 && x < G.nx && y >= 0 && y < G.ny && z >= 0 && z < G.nz);
-        if (ok) myD = (z * G.ny + y) * G.nx + x;
-    }
-    const unsigned same = __match_any_sync(FULL, myD);
-    const bool keep = (myD >= c) && ((__ffs(same) - 1) == lane);
-    int mystart = 0, mycnt = 0;
-    if (keep) {
-        mystart = (int)cellptr[myD];
-        mycnt = (int)cellptr[myD + 1] - mystart;
-    }
-    int incl = mycnt;
+    for (int ipos = cstart; ipos < cend; ipos++) {
+        const float4 pi = cx.sorted[ipos];
+        const unsigned mi = __float_as_uint(pi.w);
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int v = __shfl_up_sync(FULL, incl, d);
-        if (lane >= d) incl += v;
-    }
-    const int M = __shfl_sync(FULL, incl, 31);
-    const int off = incl - mycnt;
-    __syncwarp();
-    wscr[lane] = off;                  // candidate-slot offset of this neighbour cell
-    wscr[32 + lane] = mystart - off;   // slot s -> sorted position s + wscr[32+t]
-    __syncwarp();
-
-    const int cstart = (int)cellptr[c], cend = (int)cellptr[c + 1];
-
-    for (int base = 0; base < M; base += 32 * CT_KSLOT) {
-        float xj[CT_KSLOT], yj[CT_KSLOT], zj[CT_KSLOT];
-        int jpos[CT_KSLOT], jidx[CT_KSLOT];
-        int2 mj[CT_KSLOT];
-#pragma unroll
-        for (int k = 0; k < CT_KSLOT; k++) {
-            const int s = base + k * 32 + lane;
-            jpos[k] = -1; jidx[k] = 0; xj[k] = yj[k] = zj[k] = 0.f; mj[k] = make_int2(0, 0);
-            if (s < M) {
-                int t = 0;
-#pragma unroll
-                for (int step = 16; step >= 1; step >>= 1)
-                    if (wscr[t + step] <= s) t += step;
-                const int pos = s + wscr[32 + t];
-                const float4 q = sorted[pos];
-                xj[k] = q.x; yj[k] = q.y; zj[k] = q.z;
-                jidx[k] = __float_as_int(q.w);
-                jpos[k] = pos;
-                mj[k] = __ldg(&p.meta[jidx[k]]);
+        for (int k = 0; k < NK; k++) {
+            // tested in the direction lower sorted position -> higher; the arithmetic is
+            // antisymmetric for every pair that can be a hit ("direction")
+            const float d2 = nl_d2<MODE>(pi.x, pi.y, pi.z, xj[k], yj[k], zj[k], B);
+            int de = (int)(mi & Traits::EKEY_MASK) - (int)(mj[k] & Traits::EKEY_MASK);
+            de = de < 0 ? -de : de;
+            bool elig = (de > p.n_ignored) && (jpos[k] > ipos);
+            if (FLAGS & CT_ROLES) {
+                const unsigned ri = mi >> 30, rj = mj[k] >> 30;
+                elig = elig && (((ri & (rj >> 1)) | (rj & (ri >> 1))) & 1u);
             }
-        }
-        const int nk = min(CT_KSLOT, (M - base + 31) >> 5);
-        if (p.count_tests && lane == 0)
-            n_tests += (unsigned long long)(cend - cstart) * (unsigned long long)min(M - base, 32 * CT_KSLOT);
-
-        for (int ipos = cstart; ipos < cend; ipos++) {
-            const float4 pi = sorted[ipos];
-            const int iidx = __float_as_int(pi.w);
-            const int2 mi = __ldg(&p.meta[iidx]);
-#pragma unroll
-            for (int k = 0; k < CT_KSLOT; k++) {
-                if (k < nk) {
-                    // tested in the direction lower sorted position -> higher; the arithmetic is
-                    // antisymmetric for every pair that can be a hit ("direction")
-                    const float d2 = nl_d2<MODE>(pi.x, pi.y, pi.z, xj[k], yj[k], zj[k], B);
-                    const bool near = (d2 <= p.c2_hi) && (jpos[k] > ipos) && pair_allowed(mi, mj[k], p.n_ignored);
-                    const bool hit = near && (d2 <= p.c2);
-                    const int a = min(iidx, jidx[k]), b = max(iidx, jidx[k]);
-                    if (p.boundary_ulps > 0 && near) {
-                        int diff = __float_as_int(d2) - __float_as_int(p.c2);
-                        diff = diff < 0 ? -diff : diff;
-                        if (diff <= p.boundary_ulps && p.boundary != nullptr) {
-                            const unsigned long long w = atomicAdd(&p.counters[2], 1ull);
-                            if ((long long)w < p.boundary_cap)
-                                p.boundary[w] = make_float4(__int_as_float((int)p.frame_id), __int_as_float(a),
-                                                            __int_as_float(b), d2);
-                        }
-                    }
-                    if (p.atom_keys != nullptr) {
-                        // warp-ballot compaction of this slot's hits into the key stream
-                        const unsigned hm = __ballot_sync(FULL, hit);
-                        if (hm) {
-                            const int leader = __ffs(hm) - 1;
-                            unsigned long long wbase = 0;
-                            if (lane == leader) wbase = atomicAdd(&p.counters[0], (unsigned long long)__popc(hm));
-                            wbase = __shfl_sync(FULL, wbase, leader);
-                            if (hit) {
-                                const unsigned long long w = wbase + __popc(hm & ((1u << lane) - 1u));
-                                if ((long long)w < p.atom_cap)
-                                    p.atom_keys[w] = ((unsigned long long)p.frame_id << 40) |
-                                                     ((unsigned long long)a << 20) | (unsigned long long)b;
-                            }
-                        }
-                    }
-                    if (hit) {
-                        if (p.atom_table != nullptr)
-                            atomicAdd(&p.atom_table[(size_t)a * (size_t)p.n + (size_t)b], 1u);
-                        const int ra = mi.y & 0x3fffffff, rb = mj[k].y & 0x3fffffff;
-                        sink.residue(min(ra, rb), max(ra, rb));
+            if (FLAGS & CT_BOUNDARY) {
+                if (elig && d2 <= p.c2_hi) {
+                    int diff = __float_as_int(d2) - __float_as_int(p.c2);
+                    diff = diff < 0 ? -diff : diff;
+                    if (diff <= p.boundary_ulps) {
+                        const int ia = (int)cx.sidx[ipos], ib = (int)cx.sidx[jpos[k]];
+                        const unsigned long long w = atomicAdd(&p.counters[2], 1ull);
+                        if ((long long)w < p.boundary_cap)
+                            p.boundary[w] = make_float4(__int_as_float((int)p.frame_id),
+                                                        __int_as_float(min(ia, ib)),
+                                                        __int_as_float(max(ia, ib)), d2);
                     }
                 }
             }
+            const bool hit = elig && (d2 <= p.c2);
+            if (FLAGS & CT_EMIT) {
+                // warp-ballot compaction of this slot's hits into the key stream
+                const unsigned hm = __ballot_sync(0xffffffffu, hit);
+                if (hm) {
+                    const int leader = __ffs(hm) - 1;
+                    unsigned long long wbase = 0;
+                    if (lane == leader) wbase = atomicAdd(&p.counters[0], (unsigned long long)__popc(hm));
+                    wbase = __shfl_sync(0xffffffffu, wbase, leader);
+                    if (hit) {
+                        const unsigned long long w = wbase + __popc(hm & ((1u << lane) - 1u));
+                        const int ia = (int)cx.sidx[ipos], ib = (int)cx.sidx[jpos[k]];
+                        if ((long long)w < p.atom_cap)
+                            p.atom_keys[w] = ((unsigned long long)p.frame_id << 40) |
+                                             ((unsigned long long)min(ia, ib) << 20) |
+                                             (unsigned long long)max(ia, ib);
+                    }
+                }
+            }
+            ct_queue_hits<Traits, Sink>(cx, sink, hit, ipos, jpos[k], qn);
         }
     }
+}
+
+// One warp adjudicates all candidate pairs of one occupied cell `c`.
+//
+// Candidates are the atoms of the stencil cells with id >= c (every unordered cell pair is
+// visited once).  Cells are numbered x-fastest, so for an INTERIOR cell (no periodic wrap, no
+// grid edge) they form five contiguous runs of the cell-sorted array:
+//     (cx..cx+1, cy, cz), (cx-1..cx+1, cy+1, cz), (cx-1..cx+1, cy-1..cy+1, cz+1)
+// and a candidate slot maps to its sorted position with four compares.  Edge cells take the
+// generic route: 27 stencil lanes, de-duplication (grids with < 3 cells along a dimension),
+// warp scan, per-warp candidate list.  Sorted-position order (jpos > ipos) removes self pairs
+// and double visits inside the own cell.
+template <typename Traits, typename Sink, int MODE, int FLAGS>
+__device__ __forceinline__ void ct_cell_task(const PairParams& p, const NlBox& B, const GridS& G,
+                                             const PairCtx<Traits>& cx, Sink& sink, int c,
+                                             unsigned long long& n_tests, int& qn)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    int cxx, cy, cz;
+    Traits::decode(c, G, cxx, cy, cz);
+    const int cstart = (int)cx.cellptr[c], cend = (int)cx.cellptr[c + 1];
+
+    const bool interior = (cxx >= 1) && (cxx <= G.nx - 2) && (cy >= 1) && (cy <= G.ny - 2) &&
+                          (cz >= 1) && (cz <= G.nz - 2);
+    int M;
+    // interior: run r covers slots [o_r, o_{r+1}) and sorted positions slot + a_r
+    int o1 = 0, o2 = 0, o3 = 0, o4 = 0, a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+    // generic: this lane's stencil cell
+    int mystart = 0, mycnt = 0, off = 0;
+    if (interior) {
+        const int nxy = G.nx * G.ny;
+        const int b1 = c + G.nx - 1, b2 = c + nxy - G.nx - 1, b3 = c + nxy - 1, b4 = c + nxy + G.nx - 1;
+        const int s0 = cstart, e0 = (int)cx.cellptr[c + 2];
+        const int s1 = (int)cx.cellptr[b1], e1 = (int)cx.cellptr[b1 + 3];
+        const int s2 = (int)cx.cellptr[b2], e2 = (int)cx.cellptr[b2 + 3];
+        const int s3 = (int)cx.cellptr[b3], e3 = (int)cx.cellptr[b3 + 3];
+        const int s4 = (int)cx.cellptr[b4], e4 = (int)cx.cellptr[b4 + 3];
+        o1 = e0 - s0; o2 = o1 + (e1 - s1); o3 = o2 + (e2 - s2); o4 = o3 + (e3 - s3);
+        M = o4 + (e4 - s4);
+        a0 = s0; a1 = s1 - o1; a2 = s2 - o2; a3 = s3 - o3; a4 = s4 - o4;
+    } else {
+        int myD = -1;
+        if (lane < 27) {
+            const int l9 = lane / 9, l3 = (lane - l9 * 9) / 3;
+            int x = cxx + (lane - l9 * 9 - l3 * 3) - 1;
+            int y = cy + l3 - 1;
+            int z = cz + l9 - 1;
+            if (G.periodic) {
+                x = x < 0 ? x + G.nx : (x >= G.nx ? x - G.nx : x);
+                y = y < 0 ? y + G.ny : (y >= G.ny ? y - G.ny : y);
+                z = z < 0 ? z + G.nz : (z >= G.nz ? z - G.nz : z);
+            }
+            const bool ok = (x >= 0 && x < G.nx && y >= 0 && y < G.ny && z >= 0 && z < G.nz);
+            if (ok) myD = (z * G.ny + y) * G.nx + x;
+        }
+        bool keep = (myD >= c);
+        if (!G.distinct) {
+            const unsigned same = __match_any_sync(FULL, myD);
+            keep = keep && ((__ffs(same) - 1) == lane);
+        }
+        if (keep) {
+            mystart = (int)cx.cellptr[myD];
+            mycnt = (int)cx.cellptr[myD + 1] - mystart;
+        }
+        int incl = mycnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl += v;
+        }
+        M = __shfl_sync(FULL, incl, 31);
+        off = incl - mycnt;
+    }
+
+    for (int base = 0; base < M; base += CT_CAND) {
+        if (!interior) {
+            __syncwarp();
+            // expand this lane's stencil cell into the per-warp candidate list
+            const int r0 = max(0, base - off), r1 = min(mycnt, base + CT_CAND - off);
+            for (int r = r0; r < r1; r++) cx.cand[off + r - base] = (typename Traits::pos_t)(mystart + r);
+            __syncwarp();
+        }
+        float xj[CT_KSLOT], yj[CT_KSLOT], zj[CT_KSLOT];
+        unsigned mj[CT_KSLOT];
+        int jpos[CT_KSLOT];
+#pragma unroll
+        for (int k = 0; k < CT_KSLOT; k++) {
+            const int s = base + k * 32 + lane;
+            jpos[k] = -1; mj[k] = 0u; xj[k] = yj[k] = zj[k] = 0.f;
+            if (s < M) {
+                int pos;
+                if (interior) {
+                    int adj = a0;
+                    adj = s >= o1 ? a1 : adj;
+                    adj = s >= o2 ? a2 : adj;
+                    adj = s >= o3 ? a3 : adj;
+                    adj = s >= o4 ? a4 : adj;
+                    pos = s + adj;
+                } else {
+                    pos = (int)cx.cand[s - base];
+                }
+                const float4 q = cx.sorted[pos];
+                xj[k] = q.x; yj[k] = q.y; zj[k] = q.z;
+                mj[k] = __float_as_uint(q.w);
+                jpos[k] = pos;
+            }
+        }
+        const int left = M - base;
+        if (FLAGS & CT_COUNT) {
+            if (lane == 0) n_tests += (unsigned long long)(cend - cstart) * (unsigned long long)min(left, CT_CAND);
+        }
+        if (left > 96) ct_inner<Traits, Sink, MODE, 4, FLAGS>(p, B, cx, sink, cstart, cend, xj, yj, zj, mj, jpos, qn);
+        else if (left > 64) ct_inner<Traits, Sink, MODE, 3, FLAGS>(p, B, cx, sink, cstart, cend, xj, yj, zj, mj, jpos, qn);
+        else if (left > 32) ct_inner<Traits, Sink, MODE, 2, FLAGS>(p, B, cx, sink, cstart, cend, xj, yj, zj, mj, jpos, qn);
+        else ct_inner<Traits, Sink, MODE, 1, FLAGS>(p, B, cx, sink, cstart, cend, xj, yj, zj, mj, jpos, qn);
+    }
+}
+
+// Warps pull occupied cells from a task counter until the frame is exhausted.
+template <typename Traits, typename Sink, int MODE, int FLAGS, typename OccT>
+__device__ __forceinline__ void ct_pair_phase(const PairParams& p, const NlBox& B, const GridS& G,
+                                              const PairCtx<Traits>& cx, Sink& sink, const OccT* occ,
+                                              int n_occ, int* task_counter, unsigned long long& n_tests)
+{
+    const int lane = threadIdx.x & 31;
+    int qn = 0;      // hits waiting in this warp's queue
+    for (;;) {
+        int k = 0;
+        if (lane == 0) k = atomicAdd(task_counter, 1);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k >= n_occ) break;
+        ct_cell_task<Traits, Sink, MODE, FLAGS>(p, B, G, cx, sink, (int)occ[k], n_tests, qn);
+    }
+    ct_drain_hits<Traits, Sink>(cx, sink, qn);
+}
+
+template <typename Traits, typename Sink, int FLAGS, typename OccT>
+__device__ __forceinline__ void ct_pair_phase_dyn(const PairParams& p, const NlBox& B, const GridS& G,
+                                                  const PairCtx<Traits>& cx, Sink& sink, const OccT* occ,
+                                                  int n_occ, int* task_counter, unsigned long long& n_tests)
+{
+    if (B.mode == BOX_ORTHO)
+        ct_pair_phase<Traits, Sink, BOX_ORTHO, FLAGS, OccT>(p, B, G, cx, sink, occ, n_occ, task_counter, n_tests);
+    else if (B.mode == BOX_TRICLINIC)
+        ct_pair_phase<Traits, Sink, BOX_TRICLINIC, FLAGS, OccT>(p, B, G, cx, sink, occ, n_occ, task_counter, n_tests);
+    else
+        ct_pair_phase<Traits, Sink, BOX_NONE, FLAGS, OccT>(p, B, G, cx, sink, occ, n_occ, task_counter, n_tests);
 }
 
 }  // namespace cmb

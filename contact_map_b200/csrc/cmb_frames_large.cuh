@@ -33,6 +33,7 @@ struct LargeScratch {
     int* d_atomcell = nullptr;     // [n]
     int* d_atomrank = nullptr;     // [n]
     float4* d_sorted = nullptr;    // [n]
+    int* d_sidx = nullptr;         // [n]
     unsigned int* d_stamp = nullptr;
     size_t stamp_elems = 0;
     unsigned int seq = 0;
@@ -41,7 +42,7 @@ struct LargeScratch {
 inline void large_scratch_free(LargeScratch& S)
 {
     cudaFree(S.d_grid); cudaFree(S.d_cellcnt); cudaFree(S.d_cellptr); cudaFree(S.d_occ);
-    cudaFree(S.d_misc); cudaFree(S.d_atomcell); cudaFree(S.d_atomrank); cudaFree(S.d_sorted);
+    cudaFree(S.d_misc); cudaFree(S.d_atomcell); cudaFree(S.d_atomrank); cudaFree(S.d_sorted); cudaFree(S.d_sidx);
     cudaFree(S.d_stamp);
     S = LargeScratch();
 }
@@ -54,20 +55,53 @@ struct LargeJob {
     unsigned long long* atom_keys; long long atom_cap;
     unsigned long long* res_keys; long long res_cap;
     unsigned long long* counters; float4* boundary; long long boundary_cap; int count_tests;
+    int all_roles;
 };
 
+// ----- traits + hit sink of the global-memory path -------------------------------------
+struct LargeTraits {
+    typedef int pos_t;
+    typedef uint2 hit_t;                            // {ipos, jpos}
+    static constexpr unsigned EKEY_MASK = 0x3fffffffu;
+    static __device__ __forceinline__ hit_t pack(int ipos, int jpos)
+    {
+        return make_uint2((unsigned)ipos, (unsigned)jpos);
+    }
+    static __device__ __forceinline__ int ipos(hit_t e) { return (int)e.x; }
+    static __device__ __forceinline__ int jpos(hit_t e) { return (int)e.y; }
+    static __device__ __forceinline__ void decode(int c, const GridS& G, int& cx, int& cy, int& cz)
+    {
+        const int cyz = c / G.nx;
+        cx = c - cyz * G.nx;
+        cz = cyz / G.ny;
+        cy = cyz - cz * G.ny;
+    }
+};
+
+// Account one hit: RED into the dense atom table; per-frame residue de-duplication through the
+// frame-stamp table (frames run in stream order, so atomicMax(stamp, seq) < seq is the first hit
+// of that residue pair in the current frame).
 struct StampSink {
+    const int* sidx;
+    const int2* meta;               // [n] {ekey, res_c | role << 30}
+    unsigned int* atom_table;
     unsigned int* stamp;            // nullptr: residues not requested
     unsigned int* res_table;
     unsigned long long* res_keys;
     long long res_cap;
     unsigned long long* counters;
     unsigned int seq;
+    unsigned int n;
     unsigned int n_res_c;
     long long frame_id;
-    __device__ __forceinline__ void residue(int rlo, int rhi)
+    __device__ __forceinline__ void account(int ipos, int jpos)
     {
+        const int ia = sidx[ipos], ib = sidx[jpos];
+        const int a = min(ia, ib), b = max(ia, ib);
+        if (atom_table != nullptr) atomicAdd(&atom_table[(size_t)a * (size_t)n + (size_t)b], 1u);
         if (stamp == nullptr) return;
+        const int ra = __ldg(&meta[ia]).y & 0x3fffffff, rb = __ldg(&meta[ib]).y & 0x3fffffff;
+        const int rlo = min(ra, rb), rhi = max(ra, rb);
         const size_t slot = (size_t)rlo * n_res_c + (size_t)rhi;
         if (*(volatile unsigned int*)&stamp[slot] == seq) return;
         const unsigned old = atomicMax(&stamp[slot], seq);
@@ -200,54 +234,42 @@ __global__ void __launch_bounds__(256) kl_scatter(const float* __restrict__ x, i
                                                   const int* __restrict__ cellptr,
                                                   const int* __restrict__ atomcell,
                                                   const int* __restrict__ atomrank,
-                                                  float4* __restrict__ sorted)
+                                                  const int2* __restrict__ meta,
+                                                  float4* __restrict__ sorted, int* __restrict__ sidx)
 {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int pos = cellptr[atomcell[i]] + atomrank[i];
+        const int2 m = __ldg(&meta[i]);
+        const unsigned word = ((unsigned)m.x & LargeTraits::EKEY_MASK) | ((unsigned)m.y & 0xc0000000u);
         sorted[pos] = make_float4(__ldg(&x[3 * (size_t)i]), __ldg(&x[3 * (size_t)i + 1]),
-                                  __ldg(&x[3 * (size_t)i + 2]), __int_as_float(i));
+                                  __ldg(&x[3 * (size_t)i + 2]), __uint_as_float(word));
+        sidx[pos] = i;
     }
 }
 
-template <int MODE>
-__device__ __forceinline__ void lg_pair_loop(const TaskParams& tp, const NlBox& B, const GridS& G,
-                                             const float4* sorted, const int* cellptr, const int* occ,
-                                             int n_occ, int* task_counter, int* wscr, StampSink& sink,
-                                             unsigned long long& n_tests)
+template <int FLAGS>
+__global__ void __launch_bounds__(LG_PAIR_THREADS, 4) kl_pairs(PairParams pp, StampSink sink,
+                                                               const float* __restrict__ box9,
+                                                               const GridS* __restrict__ grid,
+                                                               const float4* __restrict__ sorted,
+                                                               const int* __restrict__ sidx,
+                                                               const int* __restrict__ cellptr,
+                                                               const int* __restrict__ occ, int* misc)
 {
-    const int lane = threadIdx.x & 31;
-    for (;;) {
-        int k = 0;
-        if (lane == 0) k = atomicAdd(task_counter, 1);
-        k = __shfl_sync(0xffffffffu, k, 0);
-        if (k >= n_occ) break;
-        cell_task<MODE, int, StampSink>(tp, B, G, sorted, cellptr, __ldg(&occ[k]), wscr, sink, n_tests);
-    }
-}
-
-__global__ void __launch_bounds__(LG_PAIR_THREADS) kl_pairs(TaskParams tp, StampSink sink,
-                                                            const float* __restrict__ box9,
-                                                            const GridS* __restrict__ grid,
-                                                            const float4* __restrict__ sorted,
-                                                            const int* __restrict__ cellptr,
-                                                            const int* __restrict__ occ, int* misc)
-{
-    __shared__ int wscr_all[(LG_PAIR_THREADS / 32) * 64];
-    int* wscr = wscr_all + (threadIdx.x >> 5) * 64;
+    __shared__ int cand_all[(LG_PAIR_THREADS / 32) * CT_CAND];
+    __shared__ uint2 hitq_all[(LG_PAIR_THREADS / 32) * CT_HITQ];
+    const int warp = threadIdx.x >> 5;
     const GridS G = *grid;
     const NlBox B = make_nlbox(box9);
-    const int n_occ = misc[0];
+    PairCtx<LargeTraits> cx;
+    cx.sorted = sorted; cx.sidx = sidx; cx.cellptr = cellptr;
+    cx.cand = cand_all + warp * CT_CAND; cx.hitq = hitq_all + warp * CT_HITQ;
     unsigned long long n_tests = 0;
-    if (B.mode == BOX_ORTHO)
-        lg_pair_loop<BOX_ORTHO>(tp, B, G, sorted, cellptr, occ, n_occ, &misc[1], wscr, sink, n_tests);
-    else if (B.mode == BOX_TRICLINIC)
-        lg_pair_loop<BOX_TRICLINIC>(tp, B, G, sorted, cellptr, occ, n_occ, &misc[1], wscr, sink, n_tests);
-    else
-        lg_pair_loop<BOX_NONE>(tp, B, G, sorted, cellptr, occ, n_occ, &misc[1], wscr, sink, n_tests);
-    if (tp.count_tests) {
+    ct_pair_phase_dyn<LargeTraits, StampSink, FLAGS, int>(pp, B, G, cx, sink, occ, misc[0], &misc[1], n_tests);
+    if (FLAGS & CT_COUNT) {
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) n_tests += __shfl_xor_sync(0xffffffffu, n_tests, d);
-        if ((threadIdx.x & 31) == 0 && n_tests) atomicAdd(&tp.counters[3], n_tests);
+        if ((threadIdx.x & 31) == 0 && n_tests) atomicAdd(&pp.counters[3], n_tests);
     }
 }
 
@@ -265,11 +287,12 @@ inline int large_run(const LargeJob& job, LargeScratch& S, int sm_count, cudaStr
 {
     const int n = job.n;
     if (S.cap_atoms < n) {
-        cudaFree(S.d_atomcell); cudaFree(S.d_atomrank); cudaFree(S.d_sorted);
-        S.d_atomcell = S.d_atomrank = nullptr; S.d_sorted = nullptr;
+        cudaFree(S.d_atomcell); cudaFree(S.d_atomrank); cudaFree(S.d_sorted); cudaFree(S.d_sidx);
+        S.d_atomcell = S.d_atomrank = S.d_sidx = nullptr; S.d_sorted = nullptr;
         LG_CK(cudaMalloc(&S.d_atomcell, sizeof(int) * (size_t)n));
         LG_CK(cudaMalloc(&S.d_atomrank, sizeof(int) * (size_t)n));
         LG_CK(cudaMalloc(&S.d_sorted, sizeof(float4) * (size_t)n));
+        LG_CK(cudaMalloc(&S.d_sidx, sizeof(int) * (size_t)n));
         S.cap_atoms = n;
     }
     if (!S.d_grid) {
@@ -303,19 +326,36 @@ inline int large_run(const LargeJob& job, LargeScratch& S, int sm_count, cudaStr
         kl_prepare<<<1, 1024, 0, stream>>>(x, n, box9, job.cutoff, S.d_grid, S.d_cellcnt, S.d_misc);
         kl_bin<<<atom_blocks, 256, 0, stream>>>(x, n, S.d_grid, S.d_cellcnt, S.d_atomcell, S.d_atomrank);
         kl_scan<<<1, 1024, 0, stream>>>(S.d_grid, n, S.d_cellcnt, S.d_cellptr, S.d_occ, S.d_misc);
-        kl_scatter<<<atom_blocks, 256, 0, stream>>>(x, n, S.d_cellptr, S.d_atomcell, S.d_atomrank, S.d_sorted);
-        TaskParams tp;
-        tp.meta = job.meta; tp.n = n; tp.n_ignored = job.n_ignored; tp.c2 = job.c2; tp.c2_hi = job.c2_hi;
-        tp.boundary_ulps = job.boundary_ulps; tp.atom_table = job.atom_table; tp.atom_keys = job.atom_keys;
-        tp.atom_cap = job.atom_cap; tp.counters = job.counters; tp.boundary = job.boundary;
-        tp.boundary_cap = job.boundary_cap; tp.frame_id = job.frame0 + f; tp.count_tests = job.count_tests;
+        kl_scatter<<<atom_blocks, 256, 0, stream>>>(x, n, S.d_cellptr, S.d_atomcell, S.d_atomrank, job.meta,
+                                                    S.d_sorted, S.d_sidx);
+        PairParams pp;
+        pp.n = n; pp.n_ignored = job.n_ignored; pp.c2 = job.c2; pp.c2_hi = job.c2_hi;
+        pp.boundary_ulps = job.boundary_ulps; pp.atom_table = job.atom_table; pp.atom_keys = job.atom_keys;
+        pp.atom_cap = job.atom_cap; pp.counters = job.counters; pp.boundary = job.boundary;
+        pp.boundary_cap = job.boundary_cap; pp.frame_id = job.frame0 + f;
         StampSink sink;
+        sink.sidx = S.d_sidx; sink.meta = job.meta; sink.atom_table = job.atom_table;
         sink.stamp = want_res ? S.d_stamp : nullptr;
         sink.res_table = job.res_table; sink.res_keys = job.res_keys; sink.res_cap = job.res_cap;
-        sink.counters = job.counters; sink.seq = S.seq; sink.n_res_c = (unsigned)job.n_res_c;
-        sink.frame_id = job.frame0 + f;
-        kl_pairs<<<sm_count * 4, LG_PAIR_THREADS, 0, stream>>>(tp, sink, box9, S.d_grid, S.d_sorted,
-                                                               S.d_cellptr, S.d_occ, S.d_misc);
+        sink.counters = job.counters; sink.seq = S.seq; sink.n = (unsigned)n;
+        sink.n_res_c = (unsigned)job.n_res_c; sink.frame_id = job.frame0 + f;
+        const int pg = sm_count * 4;
+        const bool emit = job.atom_keys != nullptr;
+        if (job.boundary_ulps > 0)
+            kl_pairs<CT_BOUNDARY | CT_ROLES><<<pg, LG_PAIR_THREADS, 0, stream>>>(
+                pp, sink, box9, S.d_grid, S.d_sorted, S.d_sidx, S.d_cellptr, S.d_occ, S.d_misc);
+        else if (job.count_tests && !emit)
+            kl_pairs<CT_COUNT | CT_ROLES><<<pg, LG_PAIR_THREADS, 0, stream>>>(
+                pp, sink, box9, S.d_grid, S.d_sorted, S.d_sidx, S.d_cellptr, S.d_occ, S.d_misc);
+        else if (emit)
+            kl_pairs<CT_EMIT | CT_ROLES><<<pg, LG_PAIR_THREADS, 0, stream>>>(
+                pp, sink, box9, S.d_grid, S.d_sorted, S.d_sidx, S.d_cellptr, S.d_occ, S.d_misc);
+        else if (job.all_roles)
+            kl_pairs<0><<<pg, LG_PAIR_THREADS, 0, stream>>>(
+                pp, sink, box9, S.d_grid, S.d_sorted, S.d_sidx, S.d_cellptr, S.d_occ, S.d_misc);
+        else
+            kl_pairs<CT_ROLES><<<pg, LG_PAIR_THREADS, 0, stream>>>(
+                pp, sink, box9, S.d_grid, S.d_sorted, S.d_sidx, S.d_cellptr, S.d_occ, S.d_misc);
         launches += 5;
     }
     LG_CK(cudaGetLastError());

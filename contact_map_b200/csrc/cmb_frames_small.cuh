@@ -35,20 +35,19 @@ constexpr int FS_WARPS = FS_THREADS / 32;
 constexpr int FS_APT = 12;                          // atoms per thread in the binning passes
 constexpr int FS_MAX_ATOMS = FS_THREADS * FS_APT;   // 6144
 constexpr int FS_HEADER_BYTES = 1024;
-constexpr int FS_KSLOT = 4;                         // register-resident candidates per lane
-constexpr int FS_CAND = 32 * FS_KSLOT;              // candidates per chunk
-constexpr int FS_HITQ = 64;                         // per-warp queue of compacted hits
+constexpr int FS_CAND = CT_CAND;
+constexpr int FS_HITQ = CT_HITQ;
 
 // packed per-atom meta word: ekey [0,17) | compact residue [17,30) | role [30,32)
 constexpr unsigned FS_EKEY_BITS = 17;
 constexpr unsigned FS_EKEY_MASK = (1u << FS_EKEY_BITS) - 1u;
 constexpr unsigned FS_RES_MASK = (1u << 13) - 1u;
 
-// kernel variants (template FLAGS)
-constexpr int FS_EMIT = 1;        // emit (frame, a, b) keys
-constexpr int FS_BOUNDARY = 2;    // report pairs within boundary_ulps of the cutoff
-constexpr int FS_COUNT = 4;       // count executed pair tests
-constexpr int FS_ROLES = 8;       // query / haystack are not "all atoms": test the roles
+// kernel variants (template FLAGS), see cmb_cells.cuh
+constexpr int FS_EMIT = CT_EMIT;
+constexpr int FS_BOUNDARY = CT_BOUNDARY;
+constexpr int FS_COUNT = CT_COUNT;
+constexpr int FS_ROLES = CT_ROLES;
 
 struct FrameParams {
     const float* xyz;            // [n_frames][n][3] fp32, device
@@ -150,258 +149,48 @@ __host__ __device__ inline FsLayout fs_layout(int n, int maxc, int bm_words_smem
     return L;
 }
 
-// everything the pair phase needs, in one place
-struct FsPairCtx {
-    const float4* sorted;            // [n] {x, y, z, meta32}
-    const unsigned short* sidx;      // [n] atom index of each sorted position
-    const unsigned short* cellptr;   // [ncell + 1]
-    unsigned int* bitmap;            // residue-pair bitmap of this CTA
-    unsigned int* hitq;              // this warp's queue of hits (ipos | jpos << 16)
-    long long frame_id;
+// ----- traits + hit sink of the fused path ------------------------------------------
+struct SmallTraits {
+    typedef unsigned short pos_t;
+    typedef unsigned int hit_t;                     // ipos | jpos << 16
+    static constexpr unsigned EKEY_MASK = FS_EKEY_MASK;
+    static __device__ __forceinline__ hit_t pack(int ipos, int jpos)
+    {
+        return (unsigned)ipos | ((unsigned)jpos << 16);
+    }
+    static __device__ __forceinline__ int ipos(hit_t e) { return (int)(e & 0xffffu); }
+    static __device__ __forceinline__ int jpos(hit_t e) { return (int)(e >> 16); }
+    static __device__ __forceinline__ void decode(int c, const GridS& G, int& cx, int& cy, int& cz)
+    {
+        const int cyz = (int)__umulhi((unsigned)c << 6, G.magic_x);     // c < 2^16
+        cx = c - cyz * G.nx;
+        cz = (int)__umulhi((unsigned)cyz << 6, G.magic_y);
+        cy = cyz - cz * G.ny;
+    }
 };
 
-// Account one hit (sorted positions ipos < jpos): atom-pair table + residue-pair bitmap.
-__device__ __forceinline__ void fs_on_hit(const FrameParams& p, const FsPairCtx& cx, int ipos, int jpos)
-{
-    const int ia = cx.sidx[ipos], ib = cx.sidx[jpos];
-    const int a = min(ia, ib), b = max(ia, ib);
-    if (p.atom_table != nullptr) atomicAdd(&p.atom_table[(size_t)a * (size_t)p.n + (size_t)b], 1u);
-    const unsigned mi = __float_as_uint(cx.sorted[ipos].w), mj = __float_as_uint(cx.sorted[jpos].w);
-    const unsigned ra = (mi >> FS_EKEY_BITS) & FS_RES_MASK, rb = (mj >> FS_EKEY_BITS) & FS_RES_MASK;
-    const unsigned bit = min(ra, rb) * (unsigned)p.n_res_c + max(ra, rb);
-    const unsigned msk = 1u << (bit & 31);
-    unsigned int* wp = &cx.bitmap[bit >> 5];
-    if (!(*(volatile unsigned int*)wp & msk)) atomicOr(wp, msk);
-}
-
-// Warp-ballot compaction: the hits of one slot iteration (about 5 % of the lanes) are appended
-// to the warp's shared-memory queue and accounted 32 at a time with all lanes busy.
-__device__ __forceinline__ void fs_queue_hits(const FrameParams& p, const FsPairCtx& cx, bool hit,
-                                              int ipos, int jpos, int& qn)
-{
-    const unsigned hm = __ballot_sync(0xffffffffu, hit);
-    if (hm == 0u) return;
-    const int lane = threadIdx.x & 31;
-    if (hit) cx.hitq[qn + __popc(hm & ((1u << lane) - 1u))] = (unsigned)ipos | ((unsigned)jpos << 16);
-    qn += __popc(hm);
-    if (qn >= 32) {
-        __syncwarp();
-        const unsigned e = cx.hitq[lane];
-        const unsigned rest = (32 + lane < qn) ? cx.hitq[32 + lane] : 0u;
-        __syncwarp();
-        cx.hitq[lane] = rest;
-        qn -= 32;
-        fs_on_hit(p, cx, (int)(e & 0xffffu), (int)(e >> 16));
+// Account one hit (sorted positions ipos < jpos): RED into the atom-pair table, test-then-OR
+// into the per-frame residue-pair bitmap (shared or global), flushed at frame end.
+struct BitmapSink {
+    const float4* sorted;
+    const unsigned short* sidx;
+    unsigned int* atom_table;
+    unsigned int* bitmap;
+    unsigned n;
+    unsigned n_res_c;
+    __device__ __forceinline__ void account(int ipos, int jpos)
+    {
+        const int ia = sidx[ipos], ib = sidx[jpos];
+        const int a = min(ia, ib), b = max(ia, ib);
+        if (atom_table != nullptr) atomicAdd(&atom_table[(size_t)a * (size_t)n + (size_t)b], 1u);
+        const unsigned mi = __float_as_uint(sorted[ipos].w), mj = __float_as_uint(sorted[jpos].w);
+        const unsigned ra = (mi >> FS_EKEY_BITS) & FS_RES_MASK, rb = (mj >> FS_EKEY_BITS) & FS_RES_MASK;
+        const unsigned bit = min(ra, rb) * n_res_c + max(ra, rb);
+        const unsigned msk = 1u << (bit & 31);
+        unsigned int* wp = &bitmap[bit >> 5];
+        if (!(*(volatile unsigned int*)wp & msk)) atomicOr(wp, msk);
     }
-}
-
-__device__ __forceinline__ void fs_drain_hits(const FrameParams& p, const FsPairCtx& cx, int& qn)
-{
-    __syncwarp();
-    const int lane = threadIdx.x & 31;
-    if (lane < qn) {
-        const unsigned e = cx.hitq[lane];
-        fs_on_hit(p, cx, (int)(e & 0xffffu), (int)(e >> 16));
-    }
-    qn = 0;
-    __syncwarp();
-}
-
-// all (own atom) x (NK register slots) tests of one candidate chunk
-template <int MODE, int NK, int FLAGS>
-__device__ __forceinline__ void fs_inner(const FrameParams& p, const NlBox& B, const FsPairCtx& cx,
-                                         int cstart, int cend, const float (&xj)[FS_KSLOT],
-                                         const float (&yj)[FS_KSLOT], const float (&zj)[FS_KSLOT],
-                                         const unsigned (&mj)[FS_KSLOT], const int (&jpos)[FS_KSLOT], int& qn)
-{
-    const int lane = threadIdx.x & 31;
-    for (int ipos = cstart; ipos < cend; ipos++) {
-        const float4 pi = cx.sorted[ipos];
-        const unsigned mi = __float_as_uint(pi.w);
-#pragma unroll
-        for (int k = 0; k < NK; k++) {
-            // tested in the direction lower sorted position -> higher; the arithmetic is
-            // antisymmetric for every pair that can be a hit ("direction")
-            const float d2 = nl_d2<MODE>(pi.x, pi.y, pi.z, xj[k], yj[k], zj[k], B);
-            int de = (int)(mi & FS_EKEY_MASK) - (int)(mj[k] & FS_EKEY_MASK);
-            de = de < 0 ? -de : de;
-            bool elig = (de > p.n_ignored) && (jpos[k] > ipos);
-            if (FLAGS & FS_ROLES) {
-                const unsigned ri = mi >> 30, rj = mj[k] >> 30;
-                elig = elig && (((ri & (rj >> 1)) | (rj & (ri >> 1))) & 1u);
-            }
-            if (FLAGS & FS_BOUNDARY) {
-                if (elig && d2 <= p.c2_hi) {
-                    int diff = __float_as_int(d2) - __float_as_int(p.c2);
-                    diff = diff < 0 ? -diff : diff;
-                    if (diff <= p.boundary_ulps) {
-                        const int ia = cx.sidx[ipos], ib = cx.sidx[jpos[k]];
-                        const unsigned long long w = atomicAdd(&p.counters[2], 1ull);
-                        if ((long long)w < p.boundary_cap)
-                            p.boundary[w] = make_float4(__int_as_float((int)cx.frame_id),
-                                                        __int_as_float(min(ia, ib)),
-                                                        __int_as_float(max(ia, ib)), d2);
-                    }
-                }
-            }
-            const bool hit = elig && (d2 <= p.c2);
-            if (FLAGS & FS_EMIT) {
-                // warp-ballot compaction of this slot's hits into the key stream
-                const unsigned hm = __ballot_sync(0xffffffffu, hit);
-                if (hm) {
-                    const int leader = __ffs(hm) - 1;
-                    unsigned long long wbase = 0;
-                    if (lane == leader) wbase = atomicAdd(&p.counters[0], (unsigned long long)__popc(hm));
-                    wbase = __shfl_sync(0xffffffffu, wbase, leader);
-                    if (hit) {
-                        const unsigned long long w = wbase + __popc(hm & ((1u << lane) - 1u));
-                        const int ia = cx.sidx[ipos], ib = cx.sidx[jpos[k]];
-                        if ((long long)w < p.atom_cap)
-                            p.atom_keys[w] = ((unsigned long long)cx.frame_id << 40) |
-                                             ((unsigned long long)min(ia, ib) << 20) |
-                                             (unsigned long long)max(ia, ib);
-                    }
-                }
-            }
-            fs_queue_hits(p, cx, hit, ipos, jpos[k], qn);
-        }
-    }
-}
-
-// One warp adjudicates all candidate pairs of one occupied cell `c`.
-//
-// Candidates are the atoms of the stencil cells with id >= c (every unordered cell pair is
-// visited once).  Cells are numbered x-fastest, so for an INTERIOR cell (no periodic wrap, no
-// grid edge) they form five contiguous runs of the cell-sorted array:
-//     (cx..cx+1, cy, cz), (cx-1..cx+1, cy+1, cz), (cx-1..cx+1, cy-1..cy+1, cz+1)
-// and a candidate slot maps to its sorted position with four compares.  Edge cells take the
-// generic route: stencil lanes, de-duplication, warp scan, per-warp candidate list.
-template <int MODE, int FLAGS>
-__device__ __forceinline__ void fs_cell_task(const FrameParams& p, const NlBox& B, const GridS& G,
-                                             const FsPairCtx& cx, int c, unsigned short* cand,
-                                             unsigned long long& n_tests, int& qn)
-{
-    const int lane = threadIdx.x & 31;
-    const unsigned FULL = 0xffffffffu;
-    const int cyz = (int)__umulhi((unsigned)c << 6, G.magic_x);
-    const int cxx = c - cyz * G.nx;
-    const int cz = (int)__umulhi((unsigned)cyz << 6, G.magic_y);
-    const int cy = cyz - cz * G.ny;
-    const int cstart = (int)cx.cellptr[c], cend = (int)cx.cellptr[c + 1];
-
-    const bool interior = (cxx >= 1) && (cxx <= G.nx - 2) && (cy >= 1) && (cy <= G.ny - 2) &&
-                          (cz >= 1) && (cz <= G.nz - 2);
-    int M;
-    // interior: run r covers slots [o_r, o_{r+1}) and sorted positions slot + a_r
-    int o1 = 0, o2 = 0, o3 = 0, o4 = 0, a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
-    // generic: this lane's stencil cell
-    int mystart = 0, mycnt = 0, off = 0;
-    if (interior) {
-        const int nxy = G.nx * G.ny;
-        const int b1 = c + G.nx - 1, b2 = c + nxy - G.nx - 1, b3 = c + nxy - 1, b4 = c + nxy + G.nx - 1;
-        const int s0 = cstart, e0 = (int)cx.cellptr[c + 2];
-        const int s1 = (int)cx.cellptr[b1], e1 = (int)cx.cellptr[b1 + 3];
-        const int s2 = (int)cx.cellptr[b2], e2 = (int)cx.cellptr[b2 + 3];
-        const int s3 = (int)cx.cellptr[b3], e3 = (int)cx.cellptr[b3 + 3];
-        const int s4 = (int)cx.cellptr[b4], e4 = (int)cx.cellptr[b4 + 3];
-        o1 = e0 - s0; o2 = o1 + (e1 - s1); o3 = o2 + (e2 - s2); o4 = o3 + (e3 - s3);
-        M = o4 + (e4 - s4);
-        a0 = s0; a1 = s1 - o1; a2 = s2 - o2; a3 = s3 - o3; a4 = s4 - o4;
-    } else {
-        int myD = -1;
-        if (lane < 27) {
-            const int l9 = lane / 9, l3 = (lane - l9 * 9) / 3;
-            int x = cxx + (lane - l9 * 9 - l3 * 3) - 1;
-            int y = cy + l3 - 1;
-            int z = cz + l9 - 1;
-            if (G.periodic) {
-                x = x < 0 ? x + G.nx : (x >= G.nx ? x - G.nx : x);
-                y = y < 0 ? y + G.ny : (y >= G.ny ? y - G.ny : y);
-                z = z < 0 ? z + G.nz : (z >= G.nz ? z - G.nz : z);
-            }
-            const bool ok = (x >= 0 && x < G.nx && y >= 0 && y < G.ny && z >= 0 && z < G.nz);
-            if (ok) myD = (z * G.ny + y) * G.nx + x;
-        }
-        bool keep = (myD >= c);
-        if (!G.distinct) {   // grids with < 3 cells along a dimension: drop duplicate stencil cells
-            const unsigned same = __match_any_sync(FULL, myD);
-            keep = keep && ((__ffs(same) - 1) == lane);
-        }
-        if (keep) {
-            mystart = (int)cx.cellptr[myD];
-            mycnt = (int)cx.cellptr[myD + 1] - mystart;
-        }
-        int incl = mycnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int v = __shfl_up_sync(FULL, incl, d);
-            if (lane >= d) incl += v;
-        }
-        M = __shfl_sync(FULL, incl, 31);
-        off = incl - mycnt;
-    }
-
-    for (int base = 0; base < M; base += FS_CAND) {
-        if (!interior) {
-            __syncwarp();
-            // expand this lane's stencil cell into the per-warp candidate list
-            const int r0 = max(0, base - off), r1 = min(mycnt, base + FS_CAND - off);
-            for (int r = r0; r < r1; r++) cand[off + r - base] = (unsigned short)(mystart + r);
-            __syncwarp();
-        }
-        float xj[FS_KSLOT], yj[FS_KSLOT], zj[FS_KSLOT];
-        unsigned mj[FS_KSLOT];
-        int jpos[FS_KSLOT];
-#pragma unroll
-        for (int k = 0; k < FS_KSLOT; k++) {
-            const int s = base + k * 32 + lane;
-            jpos[k] = -1; mj[k] = 0u; xj[k] = yj[k] = zj[k] = 0.f;
-            if (s < M) {
-                int pos;
-                if (interior) {
-                    int adj = a0;
-                    adj = s >= o1 ? a1 : adj;
-                    adj = s >= o2 ? a2 : adj;
-                    adj = s >= o3 ? a3 : adj;
-                    adj = s >= o4 ? a4 : adj;
-                    pos = s + adj;
-                } else {
-                    pos = cand[s - base];
-                }
-                const float4 q = cx.sorted[pos];
-                xj[k] = q.x; yj[k] = q.y; zj[k] = q.z;
-                mj[k] = __float_as_uint(q.w);
-                jpos[k] = pos;
-            }
-        }
-        const int left = M - base;
-        if (FLAGS & FS_COUNT) {
-            if (lane == 0) n_tests += (unsigned long long)(cend - cstart) * (unsigned long long)min(left, FS_CAND);
-        }
-        if (left > 96) fs_inner<MODE, 4, FLAGS>(p, B, cx, cstart, cend, xj, yj, zj, mj, jpos, qn);
-        else if (left > 64) fs_inner<MODE, 3, FLAGS>(p, B, cx, cstart, cend, xj, yj, zj, mj, jpos, qn);
-        else if (left > 32) fs_inner<MODE, 2, FLAGS>(p, B, cx, cstart, cend, xj, yj, zj, mj, jpos, qn);
-        else fs_inner<MODE, 1, FLAGS>(p, B, cx, cstart, cend, xj, yj, zj, mj, jpos, qn);
-    }
-}
-
-template <int MODE, int FLAGS>
-__device__ __forceinline__ void fs_pair_phase(const FrameParams& p, const NlBox& B, const GridS& G,
-                                           const FsPairCtx& cx, const unsigned short* occ, int n_occ,
-                                           int* task_counter, unsigned short* cand,
-                                           unsigned long long& n_tests)
-{
-    const int lane = threadIdx.x & 31;
-    int qn = 0;      // hits waiting in this warp's queue
-    for (;;) {
-        int k = 0;
-        if (lane == 0) k = atomicAdd(task_counter, 1);
-        k = __shfl_sync(0xffffffffu, k, 0);
-        if (k >= n_occ) break;
-        fs_cell_task<MODE, FLAGS>(p, B, G, cx, (int)occ[k], cand, n_tests, qn);
-    }
-    fs_drain_hits(p, cx, qn);
-}
+};
 
 #ifndef FS_MIN_CTAS
 #define FS_MIN_CTAS 2
@@ -586,16 +375,17 @@ __global__ void __launch_bounds__(FS_THREADS, FS_MIN_CTAS) k_frames_small(const 
         }
 
         // ---- pass D: pair phase, one warp per occupied cell ---------------------------
-        FsPairCtx cx;
-        cx.sorted = sorted; cx.sidx = sidx; cx.cellptr = cell16; cx.bitmap = bitmap; cx.hitq = hitq;
-        cx.frame_id = p.frame0 + f;
-        const int n_occ = *n_occ_s;
-        if (B.mode == BOX_ORTHO)
-            fs_pair_phase<BOX_ORTHO, FLAGS>(p, B, G, cx, occ, n_occ, task_counter, cand, n_tests);
-        else if (B.mode == BOX_TRICLINIC)
-            fs_pair_phase<BOX_TRICLINIC, FLAGS>(p, B, G, cx, occ, n_occ, task_counter, cand, n_tests);
-        else
-            fs_pair_phase<BOX_NONE, FLAGS>(p, B, G, cx, occ, n_occ, task_counter, cand, n_tests);
+        const long long frame_id = p.frame0 + f;
+        PairParams pp;
+        pp.n = n; pp.n_ignored = p.n_ignored; pp.c2 = p.c2; pp.c2_hi = p.c2_hi;
+        pp.boundary_ulps = p.boundary_ulps; pp.atom_table = p.atom_table; pp.atom_keys = p.atom_keys;
+        pp.atom_cap = p.atom_cap; pp.counters = p.counters; pp.boundary = p.boundary;
+        pp.boundary_cap = p.boundary_cap; pp.frame_id = frame_id;
+        PairCtx<SmallTraits> cx;
+        cx.sorted = sorted; cx.sidx = sidx; cx.cellptr = cell16; cx.cand = cand; cx.hitq = hitq;
+        BitmapSink sink{sorted, sidx, p.atom_table, bitmap, (unsigned)n, (unsigned)p.n_res_c};
+        ct_pair_phase_dyn<SmallTraits, BitmapSink, FLAGS, unsigned short>(pp, B, G, cx, sink, occ, *n_occ_s,
+                                                                          task_counter, n_tests);
         __syncthreads();
 
         // ---- pass E: flush the per-frame residue bitmap ------------------------------
@@ -621,7 +411,7 @@ __global__ void __launch_bounds__(FS_THREADS, FS_MIN_CTAS) k_frames_small(const 
                         const unsigned bit = (unsigned)w * 32u + (unsigned)b;
                         const unsigned rlo = bit / (unsigned)p.n_res_c, rhi = bit % (unsigned)p.n_res_c;
                         if ((long long)(wbase + o) < p.res_cap)
-                            p.res_keys[wbase + o] = ((unsigned long long)cx.frame_id << 40) |
+                            p.res_keys[wbase + o] = ((unsigned long long)frame_id << 40) |
                                                     ((unsigned long long)rlo << 20) | (unsigned long long)rhi;
                         o++;
                     }
