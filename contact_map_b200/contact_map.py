@@ -102,19 +102,35 @@ class ContactObject(object):
         if haystack is None:
             haystack = topology.select("not water and symbol != 'H'")
         self._cutoff = cutoff
-        self._query = set(int(q) for q in query)
-        self._haystack = set(int(h) for h in haystack)
+        # same containers as the reference (sets of plain ints), built through numpy
+        q_arr = np.unique(np.asarray(list(query) if not isinstance(query, np.ndarray) else query,
+                                     dtype=np.int64))
+        h_arr = np.unique(np.asarray(list(haystack) if not isinstance(haystack, np.ndarray) else haystack,
+                                     dtype=np.int64))
+        self._query = set(q_arr.tolist())
+        self._haystack = set(h_arr.tolist())
         atom_res, _ = topology_arrays(topology)
-        self._query_res_idx = set(int(r) for r in np.unique(atom_res[sorted(self._query)]))
-        self._haystack_res_idx = set(int(r) for r in np.unique(atom_res[sorted(self._haystack)]))
-        all_atoms = sorted(self._query | self._haystack)
-        self._all_atoms = tuple(all_atoms)
-        self._all_residues = set(int(r) for r in np.unique(atom_res[all_atoms]))
+        self._query_res_idx = set(np.unique(atom_res[q_arr]).tolist())
+        self._haystack_res_idx = set(np.unique(atom_res[h_arr]).tolist())
+        all_arr = np.union1d(q_arr, h_arr)
+        self._all_atoms = tuple(all_arr.tolist())
+        self._all_residues = set(np.unique(atom_res[all_arr]).tolist())
         self._use_atom_slice = self._set_atom_slice(self._all_atoms)
-        if getattr(self, "indexer", None) is None:
-            self.indexer = AtomIndexer(topology, self._query, self._haystack, self._all_atoms,
-                                       self._use_atom_slice)
+        if getattr(self, "_indexer", None) is None:
+            self._indexer = None          # built on first access (two dicts over all atoms)
         self._n_neighbors_ignored = n_neighbors_ignored
+
+    @property
+    def indexer(self):
+        """Real <-> used atom index maps (reference ``indexer`` attribute), built lazily."""
+        if self._indexer is None:
+            self._indexer = AtomIndexer(self._topology, self._query, self._haystack, self._all_atoms,
+                                        self._use_atom_slice)
+        return self._indexer
+
+    @indexer.setter
+    def indexer(self, value):
+        self._indexer = value
 
     def _set_atom_slice(self, all_atoms):
         if self._class_use_atom_slice is None:

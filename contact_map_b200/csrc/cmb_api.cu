@@ -34,6 +34,7 @@ struct cmb_ctx {
     int2* d_meta = nullptr;           // {ekey, res_c | role << 30}   (global-memory cell path)
     unsigned int* d_meta32 = nullptr; // packed word of the fused kernel (cmb_frames_small.cuh)
     bool all_roles = true;            // every used atom is both query and haystack
+    int meta_cap = 0;
     int path = 0;                     // 0 fused shared-memory kernel, 1 global-memory cell path
 
     // fused-kernel launch configuration
@@ -251,18 +252,22 @@ extern "C" int cmb_set_system(cmb_ctx* ctx, int n_used, const int32_t* atom_res,
     // residues advance the key by min(gap, n_ignored + 1), a new chain by n_ignored + 1.  Gaps larger
     // than n_ignored are thereby compressed without changing the predicate, which keeps the keys small.
     std::vector<std::pair<int32_t, int32_t>> chain_res;   // (chain, residue) of every used residue
+    std::vector<int32_t> chain_of_uniq(uniq.size(), 0);
+    std::vector<int> rc_of_atom(n_used);
     {
-        std::map<int32_t, int32_t> res_chain;
+        std::vector<char> seen(uniq.size(), 0);
         for (int i = 0; i < n_used; i++) {
-            auto it = res_chain.find(atom_res[i]);
-            if (it == res_chain.end()) res_chain[atom_res[i]] = atom_chain[i];
-            else if (it->second != atom_chain[i])
+            const int rc = (int)(std::lower_bound(uniq.begin(), uniq.end(), atom_res[i]) - uniq.begin());
+            rc_of_atom[i] = rc;
+            if (!seen[rc]) { seen[rc] = 1; chain_of_uniq[rc] = atom_chain[i]; }
+            else if (chain_of_uniq[rc] != atom_chain[i])
                 return fail(ctx, CMB_ERR_ARG, "residue %d is assigned to two chains", atom_res[i]);
         }
-        for (auto& kv : res_chain) chain_res.push_back({kv.second, kv.first});
+        chain_res.reserve(uniq.size());
+        for (size_t k = 0; k < uniq.size(); k++) chain_res.push_back({chain_of_uniq[k], uniq[k]});
         std::sort(chain_res.begin(), chain_res.end());
     }
-    std::map<int32_t, long long> ekey_of_res;
+    std::vector<long long> ekey_of_rc(uniq.size(), 0);
     long long cursor = 0;
     for (size_t k = 0; k < chain_res.size(); k++) {
         if (k > 0) {
@@ -270,7 +275,8 @@ extern "C" int cmb_set_system(cmb_ctx* ctx, int n_used, const int32_t* atom_res,
             const long long gap = (long long)chain_res[k].second - chain_res[k - 1].second;
             cursor += same_chain ? std::min<long long>(gap, (long long)n_ignored + 1) : (long long)n_ignored + 1;
         }
-        ekey_of_res[chain_res[k].second] = cursor;
+        const size_t rc = (size_t)(std::lower_bound(uniq.begin(), uniq.end(), chain_res[k].second) - uniq.begin());
+        ekey_of_rc[rc] = cursor;
     }
     if (cursor > 0x3fffffffll) return fail(ctx, CMB_ERR_LIMIT, "exclusion key range too large");
     const long long ekey_max = cursor;
@@ -278,8 +284,8 @@ extern "C" int cmb_set_system(cmb_ctx* ctx, int n_used, const int32_t* atom_res,
     std::vector<unsigned int> meta32(n_used);
     bool all_roles = true;
     for (int i = 0; i < n_used; i++) {
-        const int rc = (int)(std::lower_bound(uniq.begin(), uniq.end(), atom_res[i]) - uniq.begin());
-        const int ekey = (int)ekey_of_res[atom_res[i]];
+        const int rc = rc_of_atom[i];
+        const int ekey = (int)ekey_of_rc[rc];
         meta[i].x = ekey;
         meta[i].y = rc | ((int)(role[i] & 3u) << 30);
         meta32[i] = ((unsigned)ekey & FS_EKEY_MASK) | (((unsigned)rc & FS_RES_MASK) << FS_EKEY_BITS) |
@@ -287,13 +293,17 @@ extern "C" int cmb_set_system(cmb_ctx* ctx, int n_used, const int32_t* atom_res,
         if ((role[i] & 3u) != 3u) all_roles = false;
     }
     ctx->all_roles = all_roles;
-    if (ctx->d_meta) CK(cudaFree(ctx->d_meta));
-    ctx->d_meta = nullptr;
-    CK(cudaMalloc(&ctx->d_meta, sizeof(int2) * (size_t)n_used));
+    // earlier launches (possibly on non-blocking streams) may still read the old tables
+    CK(cudaDeviceSynchronize());
+    if (ctx->meta_cap < n_used) {            // device buffers are reused across systems
+        if (ctx->d_meta) CK(cudaFree(ctx->d_meta));
+        if (ctx->d_meta32) CK(cudaFree(ctx->d_meta32));
+        ctx->d_meta = nullptr; ctx->d_meta32 = nullptr; ctx->meta_cap = 0;
+        CK(cudaMalloc(&ctx->d_meta, sizeof(int2) * (size_t)n_used));
+        CK(cudaMalloc(&ctx->d_meta32, sizeof(unsigned int) * (size_t)n_used));
+        ctx->meta_cap = n_used;
+    }
     CK(cudaMemcpy(ctx->d_meta, meta.data(), sizeof(int2) * (size_t)n_used, cudaMemcpyHostToDevice));
-    if (ctx->d_meta32) CK(cudaFree(ctx->d_meta32));
-    ctx->d_meta32 = nullptr;
-    CK(cudaMalloc(&ctx->d_meta32, sizeof(unsigned int) * (size_t)n_used));
     CK(cudaMemcpy(ctx->d_meta32, meta32.data(), sizeof(unsigned int) * (size_t)n_used, cudaMemcpyHostToDevice));
 
     ctx->n = n_used;

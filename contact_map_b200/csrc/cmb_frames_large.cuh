@@ -80,7 +80,10 @@ struct LargeTraits {
 
 // Account one hit: RED into the dense atom table; per-frame residue de-duplication through the
 // frame-stamp table (frames run in stream order, so atomicMax(stamp, seq) < seq is the first hit
-// of that residue pair in the current frame).
+// of that residue pair in the current frame).  The atomicMax result is only consumed at the NEXT
+// call (software pipelining): the L2 round trip of the stamp table overlaps the pair tests in
+// between instead of stalling the warp.  Lanes of one drain that hit the same residue pair are
+// merged first (__match_any_sync), which removes most of the atomics for 3-atom solvent residues.
 struct StampSink {
     const int* sidx;
     const int2* meta;               // [n] {ekey, res_c | role << 30}
@@ -94,25 +97,42 @@ struct StampSink {
     unsigned int n;
     unsigned int n_res_c;
     long long frame_id;
+    // pipeline state of this lane
+    unsigned int pend_old;
+    unsigned int pend_lo, pend_hi;
+    int pending;
+
+    __device__ __forceinline__ void resolve()
+    {
+        if (pending && pend_old < seq) {
+            const size_t slot = (size_t)pend_lo * n_res_c + (size_t)pend_hi;
+            if (res_table != nullptr) atomicAdd(&res_table[slot], 1u);
+            if (res_keys != nullptr) {
+                const unsigned long long w = atomicAdd(&counters[1], 1ull);
+                if ((long long)w < res_cap)
+                    res_keys[w] = ((unsigned long long)frame_id << 40) | ((unsigned long long)pend_lo << 20) |
+                                  (unsigned long long)pend_hi;
+            }
+        }
+        pending = 0;
+    }
+
+    // called by a converged set of lanes (a full warp in the queue path, lanes < qn in the drain)
     __device__ __forceinline__ void account(int ipos, int jpos)
     {
         const int ia = sidx[ipos], ib = sidx[jpos];
         const int a = min(ia, ib), b = max(ia, ib);
         if (atom_table != nullptr) atomicAdd(&atom_table[(size_t)a * (size_t)n + (size_t)b], 1u);
         if (stamp == nullptr) return;
+        resolve();                                   // consume the previous call's atomicMax
         const int ra = __ldg(&meta[ia]).y & 0x3fffffff, rb = __ldg(&meta[ib]).y & 0x3fffffff;
-        const int rlo = min(ra, rb), rhi = max(ra, rb);
-        const size_t slot = (size_t)rlo * n_res_c + (size_t)rhi;
-        if (*(volatile unsigned int*)&stamp[slot] == seq) return;
-        const unsigned old = atomicMax(&stamp[slot], seq);
-        if (old < seq) {
-            if (res_table != nullptr) atomicAdd(&res_table[slot], 1u);
-            if (res_keys != nullptr) {
-                const unsigned long long w = atomicAdd(&counters[1], 1ull);
-                if ((long long)w < res_cap)
-                    res_keys[w] = ((unsigned long long)frame_id << 40) | ((unsigned long long)rlo << 20) |
-                                  (unsigned long long)rhi;
-            }
+        const unsigned rlo = (unsigned)min(ra, rb), rhi = (unsigned)max(ra, rb);
+        const unsigned slot32 = rlo * n_res_c + rhi;     // R_c^2 < 2^32 (checked on the host)
+        const unsigned peers = __match_any_sync(__activemask(), slot32);
+        if ((__ffs(peers) - 1) == (int)(threadIdx.x & 31)) {
+            pend_old = atomicMax(&stamp[(size_t)slot32], seq);
+            pend_lo = rlo; pend_hi = rhi;
+            pending = 1;
         }
     }
 };
@@ -248,7 +268,7 @@ __global__ void __launch_bounds__(256) kl_scatter(const float* __restrict__ x, i
 }
 
 template <int FLAGS>
-__global__ void __launch_bounds__(LG_PAIR_THREADS, 4) kl_pairs(PairParams pp, StampSink sink,
+__global__ void __launch_bounds__(LG_PAIR_THREADS, 4) kl_pairs(PairParams pp, StampSink sink_in,
                                                                const float* __restrict__ box9,
                                                                const GridS* __restrict__ grid,
                                                                const float4* __restrict__ sorted,
@@ -265,7 +285,10 @@ __global__ void __launch_bounds__(LG_PAIR_THREADS, 4) kl_pairs(PairParams pp, St
     cx.sorted = sorted; cx.sidx = sidx; cx.cellptr = cellptr;
     cx.cand = cand_all + warp * CT_CAND; cx.hitq = hitq_all + warp * CT_HITQ;
     unsigned long long n_tests = 0;
+    StampSink sink = sink_in;
+    sink.pending = 0; sink.pend_old = 0u; sink.pend_lo = sink.pend_hi = 0u;
     ct_pair_phase_dyn<LargeTraits, StampSink, FLAGS, int>(pp, B, G, cx, sink, occ, misc[0], &misc[1], n_tests);
+    sink.resolve();
     if (FLAGS & CT_COUNT) {
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) n_tests += __shfl_xor_sync(0xffffffffu, n_tests, d);
@@ -303,6 +326,10 @@ inline int large_run(const LargeJob& job, LargeScratch& S, int sm_count, cudaStr
         LG_CK(cudaMalloc(&S.d_misc, sizeof(int) * 4));
     }
     const bool want_res = (job.res_table != nullptr) || (job.res_keys != nullptr);
+    if (want_res && (unsigned long long)job.n_res_c * (unsigned long long)job.n_res_c >= (1ull << 32)) {
+        err = "more than 65535 used residues: residue table index exceeds 32 bits";
+        return -4;
+    }
     const size_t need_stamp = (size_t)job.n_res_c * (size_t)job.n_res_c;
     if (want_res && S.stamp_elems < need_stamp) {
         cudaFree(S.d_stamp);
@@ -339,6 +366,7 @@ inline int large_run(const LargeJob& job, LargeScratch& S, int sm_count, cudaStr
         sink.res_table = job.res_table; sink.res_keys = job.res_keys; sink.res_cap = job.res_cap;
         sink.counters = job.counters; sink.seq = S.seq; sink.n = (unsigned)n;
         sink.n_res_c = (unsigned)job.n_res_c; sink.frame_id = job.frame0 + f;
+        sink.pending = 0; sink.pend_old = 0u; sink.pend_lo = sink.pend_hi = 0u;
         const int pg = sm_count * 4;
         const bool emit = job.atom_keys != nullptr;
         if (job.boundary_ulps > 0)
