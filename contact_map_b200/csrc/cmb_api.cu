@@ -278,7 +278,8 @@ extern "C" int cmb_set_system(cmb_ctx* ctx, int n_used, const int32_t* atom_res,
         const size_t rc = (size_t)(std::lower_bound(uniq.begin(), uniq.end(), chain_res[k].second) - uniq.begin());
         ekey_of_rc[rc] = cursor;
     }
-    if (cursor > 0x3fffffffll) return fail(ctx, CMB_ERR_LIMIT, "exclusion key range too large");
+    // keys travel as floats in the cell-sorted records: they must be exactly representable
+    if (cursor >= (1ll << 24)) return fail(ctx, CMB_ERR_LIMIT, "exclusion key range too large (>= 2^24)");
     const long long ekey_max = cursor;
     std::vector<int2> meta(n_used);
     std::vector<unsigned int> meta32(n_used);

@@ -124,11 +124,12 @@ __device__ __forceinline__ int cell_of(const GridS& G, float x, float y, float z
 // =================================================================================
 // Pair phase shared by both paths.
 //
-// The frame's atoms are cell-sorted into `sorted[pos] = {x, y, z, word}` where `word` packs the
-// exclusion key (low bits) and the role bits (bit 30 = query, bit 31 = haystack); `sidx[pos]` is
-// the atom index.  A `Traits` type fixes the integer widths of the two paths:
+// The frame's atoms are cell-sorted into `sorted[pos] = {x, y, z, ekey}` where `ekey` is the
+// exclusion key AS A FLOAT (exact: keys are < 2^24), so the residue-exclusion test is one FADD and
+// one FSETP on |.|; `sidx[pos]` is the atom index, through which the rare consumers (hits, role
+// test) reach the per-atom meta words.  A `Traits` type fixes the integer widths of the two paths:
 //   pos_t       element type of cellptr / sidx / the per-warp candidate list
-//   EKEY_MASK   mask of the exclusion key inside `word`
+//   role()      role bits (bit0 = query, bit1 = haystack) of an atom
 //   decode()    cell id -> (cx, cy, cz)
 //   hit_t       queue entry of one hit, with pack()/ipos()/jpos()
 // and a `Sink` object accounts one hit (atom table, residue de-duplication).
@@ -146,7 +147,8 @@ constexpr int CT_ROLES = 8;       // query / haystack are not "all atoms": test 
 // hot-loop parameters (everything a cell task needs besides the geometry)
 struct PairParams {
     int n;                           // used atoms
-    int n_ignored;
+    float n_ignored_f;               // n_ignored as a float
+    const void* meta;                // per-atom meta words (layout known to Traits / Sink)
     float c2;                        // cutoff_f * cutoff_f
     float c2_hi;                     // c2 advanced by boundary_ulps float steps
     int boundary_ulps;
@@ -209,24 +211,23 @@ template <typename Traits, typename Sink, int MODE, int NK, int FLAGS>
 __device__ __forceinline__ void ct_inner(const PairParams& p, const NlBox& B, const PairCtx<Traits>& cx,
                                          Sink& sink, int cstart, int cend, const float (&xj)[CT_KSLOT],
                                          const float (&yj)[CT_KSLOT], const float (&zj)[CT_KSLOT],
-                                         const unsigned (&mj)[CT_KSLOT], const int (&jpos)[CT_KSLOT], int& qn)
+                                         const float (&ej)[CT_KSLOT], const unsigned (&rj)[CT_KSLOT],
+                                         const int (&jpos)[CT_KSLOT], int& qn)
 {
     const int lane = threadIdx.x & 31;
     for (int ipos = cstart; ipos < cend; ipos++) {
         const float4 pi = cx.sorted[ipos];
-        const unsigned mi = __float_as_uint(pi.w);
+        unsigned ri = 3u;
+        if (FLAGS & CT_ROLES) ri = Traits::role(p.meta, (int)cx.sidx[ipos]);
 #pragma unroll
         for (int k = 0; k < NK; k++) {
             // tested in the direction lower sorted position -> higher; the arithmetic is
             // antisymmetric for every pair that can be a hit ("direction")
             const float d2 = nl_d2<MODE>(pi.x, pi.y, pi.z, xj[k], yj[k], zj[k], B);
-            int de = (int)(mi & Traits::EKEY_MASK) - (int)(mj[k] & Traits::EKEY_MASK);
-            de = de < 0 ? -de : de;
-            bool elig = (de > p.n_ignored) && (jpos[k] > ipos);
-            if (FLAGS & CT_ROLES) {
-                const unsigned ri = mi >> 30, rj = mj[k] >> 30;
-                elig = elig && (((ri & (rj >> 1)) | (rj & (ri >> 1))) & 1u);
-            }
+            // |ekey_i - ekey_j| > n_ignored  (exact small integers held as floats)
+            bool elig = (fabsf(__fsub_rn(pi.w, ej[k])) > p.n_ignored_f) && (jpos[k] > ipos);
+            if (FLAGS & CT_ROLES)
+                elig = elig && (((ri & (rj[k] >> 1)) | (rj[k] & (ri >> 1))) & 1u);
             if (FLAGS & CT_BOUNDARY) {
                 if (elig && d2 <= p.c2_hi) {
                     int diff = __float_as_int(d2) - __float_as_int(p.c2);
@@ -346,13 +347,13 @@ __device__ __forceinline__ void ct_cell_task(const PairParams& p, const NlBox& B
             for (int r = r0; r < r1; r++) cx.cand[off + r - base] = (typename Traits::pos_t)(mystart + r);
             __syncwarp();
         }
-        float xj[CT_KSLOT], yj[CT_KSLOT], zj[CT_KSLOT];
-        unsigned mj[CT_KSLOT];
+        float xj[CT_KSLOT], yj[CT_KSLOT], zj[CT_KSLOT], ej[CT_KSLOT];
+        unsigned rj[CT_KSLOT];
         int jpos[CT_KSLOT];
 #pragma unroll
         for (int k = 0; k < CT_KSLOT; k++) {
             const int s = base + k * 32 + lane;
-            jpos[k] = -1; mj[k] = 0u; xj[k] = yj[k] = zj[k] = 0.f;
+            jpos[k] = -1; rj[k] = 3u; xj[k] = yj[k] = zj[k] = ej[k] = 0.f;
             if (s < M) {
                 int pos;
                 if (interior) {
@@ -366,8 +367,8 @@ __device__ __forceinline__ void ct_cell_task(const PairParams& p, const NlBox& B
                     pos = (int)cx.cand[s - base];
                 }
                 const float4 q = cx.sorted[pos];
-                xj[k] = q.x; yj[k] = q.y; zj[k] = q.z;
-                mj[k] = __float_as_uint(q.w);
+                xj[k] = q.x; yj[k] = q.y; zj[k] = q.z; ej[k] = q.w;
+                if (FLAGS & CT_ROLES) rj[k] = Traits::role(p.meta, (int)cx.sidx[pos]);
                 jpos[k] = pos;
             }
         }
@@ -375,10 +376,10 @@ __device__ __forceinline__ void ct_cell_task(const PairParams& p, const NlBox& B
         if (FLAGS & CT_COUNT) {
             if (lane == 0) n_tests += (unsigned long long)(cend - cstart) * (unsigned long long)min(left, CT_CAND);
         }
-        if (left > 96) ct_inner<Traits, Sink, MODE, 4, FLAGS>(p, B, cx, sink, cstart, cend, xj, yj, zj, mj, jpos, qn);
-        else if (left > 64) ct_inner<Traits, Sink, MODE, 3, FLAGS>(p, B, cx, sink, cstart, cend, xj, yj, zj, mj, jpos, qn);
-        else if (left > 32) ct_inner<Traits, Sink, MODE, 2, FLAGS>(p, B, cx, sink, cstart, cend, xj, yj, zj, mj, jpos, qn);
-        else ct_inner<Traits, Sink, MODE, 1, FLAGS>(p, B, cx, sink, cstart, cend, xj, yj, zj, mj, jpos, qn);
+        if (left > 96) ct_inner<Traits, Sink, MODE, 4, FLAGS>(p, B, cx, sink, cstart, cend, xj, yj, zj, ej, rj, jpos, qn);
+        else if (left > 64) ct_inner<Traits, Sink, MODE, 3, FLAGS>(p, B, cx, sink, cstart, cend, xj, yj, zj, ej, rj, jpos, qn);
+        else if (left > 32) ct_inner<Traits, Sink, MODE, 2, FLAGS>(p, B, cx, sink, cstart, cend, xj, yj, zj, ej, rj, jpos, qn);
+        else ct_inner<Traits, Sink, MODE, 1, FLAGS>(p, B, cx, sink, cstart, cend, xj, yj, zj, ej, rj, jpos, qn);
     }
 }
 

@@ -62,7 +62,10 @@ struct LargeJob {
 struct LargeTraits {
     typedef int pos_t;
     typedef uint2 hit_t;                            // {ipos, jpos}
-    static constexpr unsigned EKEY_MASK = 0x3fffffffu;
+    static __device__ __forceinline__ unsigned role(const void* meta, int atom)
+    {
+        return (unsigned)__ldg(reinterpret_cast<const int2*>(meta) + atom).y >> 30;
+    }
     static __device__ __forceinline__ hit_t pack(int ipos, int jpos)
     {
         return make_uint2((unsigned)ipos, (unsigned)jpos);
@@ -259,10 +262,8 @@ __global__ void __launch_bounds__(256) kl_scatter(const float* __restrict__ x, i
 {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int pos = cellptr[atomcell[i]] + atomrank[i];
-        const int2 m = __ldg(&meta[i]);
-        const unsigned word = ((unsigned)m.x & LargeTraits::EKEY_MASK) | ((unsigned)m.y & 0xc0000000u);
         sorted[pos] = make_float4(__ldg(&x[3 * (size_t)i]), __ldg(&x[3 * (size_t)i + 1]),
-                                  __ldg(&x[3 * (size_t)i + 2]), __uint_as_float(word));
+                                  __ldg(&x[3 * (size_t)i + 2]), (float)__ldg(&meta[i]).x);
         sidx[pos] = i;
     }
 }
@@ -356,7 +357,7 @@ inline int large_run(const LargeJob& job, LargeScratch& S, int sm_count, cudaStr
         kl_scatter<<<atom_blocks, 256, 0, stream>>>(x, n, S.d_cellptr, S.d_atomcell, S.d_atomrank, job.meta,
                                                     S.d_sorted, S.d_sidx);
         PairParams pp;
-        pp.n = n; pp.n_ignored = job.n_ignored; pp.c2 = job.c2; pp.c2_hi = job.c2_hi;
+        pp.n = n; pp.n_ignored_f = (float)job.n_ignored; pp.meta = job.meta; pp.c2 = job.c2; pp.c2_hi = job.c2_hi;
         pp.boundary_ulps = job.boundary_ulps; pp.atom_table = job.atom_table; pp.atom_keys = job.atom_keys;
         pp.atom_cap = job.atom_cap; pp.counters = job.counters; pp.boundary = job.boundary;
         pp.boundary_cap = job.boundary_cap; pp.frame_id = job.frame0 + f;

@@ -14,7 +14,7 @@
 //      has consumed the buffer, so it overlaps the pair phase;
 //   2. atoms are binned into >= cutoff-wide cells of the (orthorhombic / triclinic /
 //      open) cell grid: u16 shared-memory histogram, block scan, scatter into a
-//      cell-sorted float4 array {x, y, z, packed meta} (+ u16 atom index);
+//      cell-sorted float4 array {x, y, z, exclusion key} (+ u16 atom index);
 //   3. one warp per occupied cell: the candidate atoms of the half shell
 //      (neighbour cells with id >= own) are held in registers (4 per lane), the
 //      cell's own atoms are broadcast from shared memory, and every candidate pair
@@ -153,7 +153,10 @@ __host__ __device__ inline FsLayout fs_layout(int n, int maxc, int bm_words_smem
 struct SmallTraits {
     typedef unsigned short pos_t;
     typedef unsigned int hit_t;                     // ipos | jpos << 16
-    static constexpr unsigned EKEY_MASK = FS_EKEY_MASK;
+    static __device__ __forceinline__ unsigned role(const void* meta, int atom)
+    {
+        return __ldg(reinterpret_cast<const unsigned int*>(meta) + atom) >> 30;
+    }
     static __device__ __forceinline__ hit_t pack(int ipos, int jpos)
     {
         return (unsigned)ipos | ((unsigned)jpos << 16);
@@ -172,7 +175,7 @@ struct SmallTraits {
 // Account one hit (sorted positions ipos < jpos): RED into the atom-pair table, test-then-OR
 // into the per-frame residue-pair bitmap (shared or global), flushed at frame end.
 struct BitmapSink {
-    const float4* sorted;
+    const unsigned int* meta32;
     const unsigned short* sidx;
     unsigned int* atom_table;
     unsigned int* bitmap;
@@ -183,7 +186,7 @@ struct BitmapSink {
         const int ia = sidx[ipos], ib = sidx[jpos];
         const int a = min(ia, ib), b = max(ia, ib);
         if (atom_table != nullptr) atomicAdd(&atom_table[(size_t)a * (size_t)n + (size_t)b], 1u);
-        const unsigned mi = __float_as_uint(sorted[ipos].w), mj = __float_as_uint(sorted[jpos].w);
+        const unsigned mi = __ldg(&meta32[ia]), mj = __ldg(&meta32[ib]);
         const unsigned ra = (mi >> FS_EKEY_BITS) & FS_RES_MASK, rb = (mj >> FS_EKEY_BITS) & FS_RES_MASK;
         const unsigned bit = min(ra, rb) * n_res_c + max(ra, rb);
         const unsigned msk = 1u << (bit & 31);
@@ -363,7 +366,7 @@ __global__ void __launch_bounds__(FS_THREADS, FS_MIN_CTAS) k_frames_small(const 
             if (i < n) {
                 const int pos = (int)cell16[my_cell[k]] + my_rank[k];
                 sorted[pos] = make_float4(xr[3 * i], xr[3 * i + 1], xr[3 * i + 2],
-                                          __uint_as_float(__ldg(&p.meta32[i])));
+                                          (float)(__ldg(&p.meta32[i]) & FS_EKEY_MASK));
                 sidx[pos] = (unsigned short)i;
             }
         }
@@ -377,13 +380,13 @@ __global__ void __launch_bounds__(FS_THREADS, FS_MIN_CTAS) k_frames_small(const 
         // ---- pass D: pair phase, one warp per occupied cell ---------------------------
         const long long frame_id = p.frame0 + f;
         PairParams pp;
-        pp.n = n; pp.n_ignored = p.n_ignored; pp.c2 = p.c2; pp.c2_hi = p.c2_hi;
+        pp.n = n; pp.n_ignored_f = (float)p.n_ignored; pp.meta = p.meta32; pp.c2 = p.c2; pp.c2_hi = p.c2_hi;
         pp.boundary_ulps = p.boundary_ulps; pp.atom_table = p.atom_table; pp.atom_keys = p.atom_keys;
         pp.atom_cap = p.atom_cap; pp.counters = p.counters; pp.boundary = p.boundary;
         pp.boundary_cap = p.boundary_cap; pp.frame_id = frame_id;
         PairCtx<SmallTraits> cx;
         cx.sorted = sorted; cx.sidx = sidx; cx.cellptr = cell16; cx.cand = cand; cx.hitq = hitq;
-        BitmapSink sink{sorted, sidx, p.atom_table, bitmap, (unsigned)n, (unsigned)p.n_res_c};
+        BitmapSink sink{p.meta32, sidx, p.atom_table, bitmap, (unsigned)n, (unsigned)p.n_res_c};
         ct_pair_phase_dyn<SmallTraits, BitmapSink, FLAGS, unsigned short>(pp, B, G, cx, sink, occ, *n_occ_s,
                                                                           task_counter, n_tests);
         __syncthreads();

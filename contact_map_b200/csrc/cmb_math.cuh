@@ -7,9 +7,10 @@
 // them with SSE intrinsics, which never contract): __fmul_rn / __fadd_rn / __fsub_rn
 // are used so nvcc cannot fuse them into FFMA regardless of -fmad.
 //
-// rint() and floor() are evaluated with the 1.5*2^23 magic constant on the FP32
-// pipe instead of FRND on the quarter-rate XU pipe; for |x| < 2^22 the result is
-// bit-identical to rintf()/floorf() under round-to-nearest-even.
+// rint() and floor() compile to FRND (cvt.rni / cvt.rmi f32 -> f32) on the XU pipe: one issue
+// slot each, exact for every input.  The kernels are issue-bound on the FMA/ALU pipes while the
+// XU pipe is mostly idle, so this is cheaper than the two-FADD 1.5*2^23 trick (kept below for
+// reference; it is bit-identical for |x| < 2^22).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -50,6 +51,7 @@ __device__ __forceinline__ NlBox make_nlbox(const float* __restrict__ box9)
 
 #define CMB_MAGIC 12582912.0f   /* 1.5 * 2^23 */
 
+#ifdef CMB_USE_MAGIC_ROUND
 // rintf(x), round-half-even, exact for |x| < 2^22
 __device__ __forceinline__ float rint_magic(float x)
 {
@@ -62,6 +64,10 @@ __device__ __forceinline__ float floor_magic(float x)
     float r = rint_magic(x);
     return (r > x) ? __fadd_rn(r, -1.0f) : r;
 }
+#else
+__device__ __forceinline__ float rint_magic(float x) { return rintf(x); }     // FRND.F32
+__device__ __forceinline__ float floor_magic(float x) { return floorf(x); }   // FRND.F32.FLOOR
+#endif
 
 // (x*x + y*y) + z*z with every op rounded (dpps ordering)
 __device__ __forceinline__ float dot3_exact(float x, float y, float z)
