@@ -1,13 +1,13 @@
 // cmb_frames_large.cuh -- global-memory cell path for systems that do not fit the
 // fused shared-memory kernel (n_used > 6144, e.g. the 100k-atom solvated system).
 //
-// Same adjudication code as the fused kernel (cmb_cells.cuh::cell_task); the cell
-// arrays and the cell-sorted float4 copy of the frame live in HBM/L2 instead of
+// Same pair-phase code as the fused kernel (cmb_cells.cuh::ct_pair_phase, LargeTraits); the
+// cell arrays and the cell-sorted float4 copy of the frame live in HBM/L2 instead of
 // shared memory, and the whole GPU works on ONE frame at a time:
 //   kl_prepare  grid of the frame (+ bounding box for open boundaries), zero counters
 //   kl_bin      cell id + rank per atom (L2 atomics on the cell histogram)
 //   kl_scan     exclusive scan over cells + occupied-cell list (single CTA)
-//   kl_scatter  cell-sorted float4 {x,y,z,atom}
+//   kl_scatter  cell-sorted float4 {x, y, z, exclusion key} + atom index
 //   kl_pairs    persistent CTAs, one warp per occupied cell (global task counter)
 // Per-frame residue de-duplication (contact_map.py:601-607,740) uses a frame-stamp
 // table instead of a bitmap: frames are processed in stream order, so
