@@ -25,7 +25,7 @@ _LIB = None
 EXPORTS = [
     "cmb_version", "cmb_last_error", "cmb_ctx_create", "cmb_ctx_destroy", "cmb_set_system",
     "cmb_n_residues", "cmb_residue_map", "cmb_table_sizes", "cmb_path_kind", "cmb_accumulate",
-    "cmb_accumulate_host", "cmb_frame_contacts", "cmb_sort_keys", "cmb_export_nonzero",
+    "cmb_accumulate_host", "cmb_accumulate_host_gather", "cmb_frame_contacts", "cmb_sort_keys", "cmb_export_nonzero",
     "cmb_boundary_pairs", "cmb_set_option", "cmb_get_stat", "cmb_gather_atoms", "cmb_min_dist",
     "cmb_nearest", "cmb_synth_frames",
 ]
@@ -100,6 +100,8 @@ def lib():
     L.cmb_accumulate.argtypes = [vp, vp, vp, i64, vp, vp, vp]
     L.cmb_accumulate_host.restype = i32
     L.cmb_accumulate_host.argtypes = [vp, vp, vp, i64, i64, vp, vp]
+    L.cmb_accumulate_host_gather.restype = i32
+    L.cmb_accumulate_host_gather.argtypes = [vp, vp, i32, vp, vp, i64, i64, i32, vp, vp]
     L.cmb_frame_contacts.restype = i32
     L.cmb_frame_contacts.argtypes = [vp, vp, vp, i64, i64, vp, i64, vp, i64, vp, vp, vp, vp]
     L.cmb_sort_keys.restype = i32

@@ -374,9 +374,10 @@ def _engine_system(contact_object, engine):
     return used
 
 
-def _used_coordinates(xyz, box, used, n_total, engine):
+def _used_coordinates(xyz, box, used, n_total, engine, keep_full_host=False):
     """Slice the coordinates to the used atoms (reference atom_indexer._atom_slice) and say
-    whether they live on the device."""
+    whether they live on the device.  ``keep_full_host``: leave a host array that still holds all
+    atoms untouched (the caller streams it through ``accumulate_host_gather``)."""
     on_device = torch is not None and isinstance(xyz, torch.Tensor) and xyz.is_cuda
     if on_device:
         xyz = xyz.contiguous()
@@ -392,7 +393,7 @@ def _used_coordinates(xyz, box, used, n_total, engine):
     xyz = np.asarray(xyz)
     if xyz.dtype != np.float32:
         xyz = xyz.astype(np.float32)
-    if used.shape[0] < n_total:
+    if used.shape[0] < n_total and not (keep_full_host and xyz.flags["C_CONTIGUOUS"]):
         xyz = np.ascontiguousarray(xyz[:, used])
     elif not xyz.flags["C_CONTIGUOUS"]:
         xyz = np.ascontiguousarray(xyz)
@@ -457,11 +458,14 @@ class ContactFrequency(ContactObject):
         engine = get_engine()
         used = _engine_system(self, engine)
         xyz, box = _split_trajectory(trajectory)
-        xyz, box, on_device = _used_coordinates(xyz, box, used, self.topology.n_atoms, engine)
+        xyz, box, on_device = _used_coordinates(xyz, box, used, self.topology.n_atoms, engine,
+                                                keep_full_host=True)
         atom_table, res_table = engine.new_tables()
         if xyz.shape[0] > 0:
             if on_device:
                 engine.accumulate(xyz, box, atom_table, res_table)
+            elif xyz.shape[1] != used.shape[0]:     # host array with all atoms: fused gather
+                engine.accumulate_host_gather(xyz, used, box, atom_table, res_table)
             else:
                 engine.accumulate_host(xyz, box, atom_table, res_table)
         self._device_tables = (atom_table, res_table, used)

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/cmb200.h"
@@ -57,6 +58,9 @@ struct cmb_ctx {
     float* d_stage_xyz[2] = {nullptr, nullptr};
     float* d_stage_box[2] = {nullptr, nullptr};
     size_t stage_xyz_bytes = 0, stage_box_bytes = 0;
+    float* h_pinned[2] = {nullptr, nullptr};      // gather staging (cmb_accumulate_host_gather)
+    size_t pinned_bytes = 0;
+    cudaEvent_t copy_done[2] = {nullptr, nullptr};
     cudaStream_t streams[2] = {nullptr, nullptr};
 
     // sort / min-dist scratch
@@ -155,6 +159,8 @@ extern "C" void cmb_ctx_destroy(cmb_ctx* ctx)
         cudaFree(ctx->d_counters[s]);
         cudaFree(ctx->d_stage_xyz[s]);
         cudaFree(ctx->d_stage_box[s]);
+        if (ctx->h_pinned[s]) cudaFreeHost(ctx->h_pinned[s]);
+        if (ctx->copy_done[s]) cudaEventDestroy(ctx->copy_done[s]);
         if (ctx->streams[s]) cudaStreamDestroy(ctx->streams[s]);
         large_scratch_free(ctx->large[s]);
     }
@@ -453,14 +459,8 @@ extern "C" int cmb_accumulate(cmb_ctx* ctx, const float* d_xyz, const float* d_b
     return launch_frames(ctx, job, ctx->slot, (cudaStream_t)stream);
 }
 
-extern "C" int cmb_accumulate_host(cmb_ctx* ctx, const float* h_xyz, const float* h_box, int64_t n_frames,
-                                   int64_t chunk_frames, uint32_t* d_atom_table, uint32_t* d_res_table)
+static int64_t pick_chunk(const cmb_ctx* ctx, int64_t n_frames, int64_t chunk_frames)
 {
-    if (!ctx) return CMB_ERR_ARG;
-    if (!ctx->have_system) return fail(ctx, CMB_ERR_STATE, "cmb_set_system has not been called");
-    if (n_frames <= 0) return CMB_OK;
-    if (!h_xyz) return fail(ctx, CMB_ERR_ARG, "xyz is NULL");
-    CK(cudaSetDevice(ctx->device));
     const size_t frame_bytes = (size_t)ctx->n * 12;
     if (chunk_frames <= 0) {
         chunk_frames = (int64_t)((32ull << 20) / frame_bytes);
@@ -471,7 +471,13 @@ extern "C" int cmb_accumulate_host(cmb_ctx* ctx, const float* h_xyz, const float
         if (chunk_frames < fill) chunk_frames = fill;
     }
     if (chunk_frames > n_frames) chunk_frames = n_frames;
-    const size_t need_xyz = (size_t)chunk_frames * frame_bytes;
+    if (chunk_frames < 1) chunk_frames = 1;
+    return chunk_frames;
+}
+
+static int ensure_staging(cmb_ctx* ctx, int64_t chunk_frames, bool with_box)
+{
+    const size_t need_xyz = (size_t)chunk_frames * (size_t)ctx->n * 12;
     const size_t need_box = (size_t)chunk_frames * 36;
     if (ctx->stage_xyz_bytes < need_xyz) {
         for (int s = 0; s < 2; s++) {
@@ -481,7 +487,7 @@ extern "C" int cmb_accumulate_host(cmb_ctx* ctx, const float* h_xyz, const float
         }
         ctx->stage_xyz_bytes = need_xyz;
     }
-    if (h_box && ctx->stage_box_bytes < need_box) {
+    if (with_box && ctx->stage_box_bytes < need_box) {
         for (int s = 0; s < 2; s++) {
             if (ctx->d_stage_box[s]) CK(cudaFree(ctx->d_stage_box[s]));
             ctx->d_stage_box[s] = nullptr;
@@ -489,6 +495,21 @@ extern "C" int cmb_accumulate_host(cmb_ctx* ctx, const float* h_xyz, const float
         }
         ctx->stage_box_bytes = need_box;
     }
+    return CMB_OK;
+}
+
+extern "C" int cmb_accumulate_host(cmb_ctx* ctx, const float* h_xyz, const float* h_box, int64_t n_frames,
+                                   int64_t chunk_frames, uint32_t* d_atom_table, uint32_t* d_res_table)
+{
+    if (!ctx) return CMB_ERR_ARG;
+    if (!ctx->have_system) return fail(ctx, CMB_ERR_STATE, "cmb_set_system has not been called");
+    if (n_frames <= 0) return CMB_OK;
+    if (!h_xyz) return fail(ctx, CMB_ERR_ARG, "xyz is NULL");
+    CK(cudaSetDevice(ctx->device));
+    const size_t frame_bytes = (size_t)ctx->n * 12;
+    chunk_frames = pick_chunk(ctx, n_frames, chunk_frames);
+    int rc0 = ensure_staging(ctx, chunk_frames, h_box != nullptr);
+    if (rc0 != CMB_OK) return rc0;
     int c = 0;
     for (int64_t f0 = 0; f0 < n_frames; f0 += chunk_frames, c++) {
         const int s = c & 1;
@@ -496,6 +517,91 @@ extern "C" int cmb_accumulate_host(cmb_ctx* ctx, const float* h_xyz, const float
         // stream order on streams[s] serialises reuse of staging buffer s
         CK(cudaMemcpyAsync(ctx->d_stage_xyz[s], h_xyz + (size_t)f0 * ctx->n * 3, (size_t)nf * frame_bytes,
                            cudaMemcpyHostToDevice, ctx->streams[s]));
+        if (h_box)
+            CK(cudaMemcpyAsync(ctx->d_stage_box[s], h_box + (size_t)f0 * 9, (size_t)nf * 36,
+                               cudaMemcpyHostToDevice, ctx->streams[s]));
+        FrameJob job;
+        memset(&job, 0, sizeof(job));
+        job.xyz = ctx->d_stage_xyz[s]; job.box = h_box ? ctx->d_stage_box[s] : nullptr;
+        job.n_frames = nf; job.frame0 = f0;
+        job.atom_table = d_atom_table; job.res_table = d_res_table;
+        int rc = launch_frames(ctx, job, s, ctx->streams[s]);
+        if (rc != CMB_OK) return rc;
+    }
+    CK(cudaStreamSynchronize(ctx->streams[0]));
+    CK(cudaStreamSynchronize(ctx->streams[1]));
+    return CMB_OK;
+}
+
+// pack out[f][i][:] = full[f][used[i]][:] for frames [f0, f0 + nf), split over host threads
+static void gather_chunk(const float* full, int n_total, const int32_t* used, int n_used, int64_t f0,
+                         int64_t nf, float* out, int n_threads)
+{
+    auto work = [=](int64_t a, int64_t b) {
+        for (int64_t f = a; f < b; f++) {
+            const float* src = full + (size_t)(f0 + f) * (size_t)n_total * 3;
+            float* dst = out + (size_t)f * (size_t)n_used * 3;
+            int i = 0;
+            while (i < n_used) {                 // copy maximal runs of consecutive atom indices
+                int j = i + 1;
+                while (j < n_used && used[j] == used[j - 1] + 1) j++;
+                memcpy(dst + (size_t)i * 3, src + (size_t)used[i] * 3, (size_t)(j - i) * 12);
+                i = j;
+            }
+        }
+    };
+    if (n_threads <= 1 || nf < 2 * n_threads) { work(0, nf); return; }
+    std::vector<std::thread> pool;
+    const int64_t per = (nf + n_threads - 1) / n_threads;
+    for (int t = 0; t < n_threads; t++) {
+        const int64_t a = t * per, b = std::min<int64_t>(nf, a + per);
+        if (a < b) pool.emplace_back(work, a, b);
+    }
+    for (auto& th : pool) th.join();
+}
+
+extern "C" int cmb_accumulate_host_gather(cmb_ctx* ctx, const float* h_xyz_full, int n_total,
+                                          const int32_t* h_used, const float* h_box, int64_t n_frames,
+                                          int64_t chunk_frames, int n_threads, uint32_t* d_atom_table,
+                                          uint32_t* d_res_table)
+{
+    if (!ctx) return CMB_ERR_ARG;
+    if (!ctx->have_system) return fail(ctx, CMB_ERR_STATE, "cmb_set_system has not been called");
+    if (n_frames <= 0) return CMB_OK;
+    if (!h_xyz_full || !h_used || n_total < ctx->n) return fail(ctx, CMB_ERR_ARG, "bad gather arguments");
+    for (int i = 0; i < ctx->n; i++)
+        if (h_used[i] < 0 || h_used[i] >= n_total || (i > 0 && h_used[i] <= h_used[i - 1]))
+            return fail(ctx, CMB_ERR_ARG, "used atom indices must be ascending and inside [0, n_total)");
+    CK(cudaSetDevice(ctx->device));
+    if (n_threads <= 0) {
+        n_threads = (int)std::thread::hardware_concurrency();
+        if (n_threads > 16) n_threads = 16;
+        if (n_threads < 1) n_threads = 1;
+    }
+    const size_t frame_bytes = (size_t)ctx->n * 12;
+    chunk_frames = pick_chunk(ctx, n_frames, chunk_frames);
+    int rc0 = ensure_staging(ctx, chunk_frames, h_box != nullptr);
+    if (rc0 != CMB_OK) return rc0;
+    const size_t need_pinned = (size_t)chunk_frames * frame_bytes;
+    if (ctx->pinned_bytes < need_pinned) {
+        for (int s = 0; s < 2; s++) {
+            if (ctx->h_pinned[s]) CK(cudaFreeHost(ctx->h_pinned[s]));
+            ctx->h_pinned[s] = nullptr;
+            CK(cudaMallocHost(&ctx->h_pinned[s], need_pinned));
+        }
+        ctx->pinned_bytes = need_pinned;
+    }
+    for (int s = 0; s < 2; s++)
+        if (!ctx->copy_done[s]) CK(cudaEventCreateWithFlags(&ctx->copy_done[s], cudaEventDisableTiming));
+    int c = 0;
+    for (int64_t f0 = 0; f0 < n_frames; f0 += chunk_frames, c++) {
+        const int s = c & 1;
+        const int64_t nf = std::min<int64_t>(chunk_frames, n_frames - f0);
+        if (c >= 2) CK(cudaEventSynchronize(ctx->copy_done[s]));   // pinned buffer s is free again
+        gather_chunk(h_xyz_full, n_total, h_used, ctx->n, f0, nf, ctx->h_pinned[s], n_threads);
+        CK(cudaMemcpyAsync(ctx->d_stage_xyz[s], ctx->h_pinned[s], (size_t)nf * frame_bytes,
+                           cudaMemcpyHostToDevice, ctx->streams[s]));
+        CK(cudaEventRecord(ctx->copy_done[s], ctx->streams[s]));
         if (h_box)
             CK(cudaMemcpyAsync(ctx->d_stage_box[s], h_box + (size_t)f0 * 9, (size_t)nf * 36,
                                cudaMemcpyHostToDevice, ctx->streams[s]));

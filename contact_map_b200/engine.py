@@ -147,6 +147,27 @@ class ContactEngine(object):
                                                 _ptr(atom_table), _ptr(res_table)),
                     "cmb_accumulate_host")
 
+    def accumulate_host_gather(self, xyz_full, used, box, atom_table, res_table, chunk_frames=0,
+                               n_threads=0):
+        """Like :meth:`accumulate_host` for a HOST trajectory that still holds ALL atoms: the used
+        atoms (ascending indices) are gathered by host threads into pinned staging while earlier
+        chunks are copied and processed (fused ``_atom_slice``)."""
+        xyz_np = xyz_full.numpy() if isinstance(xyz_full, torch.Tensor) else xyz_full
+        box_np = box.numpy() if isinstance(box, torch.Tensor) else box
+        if xyz_np.dtype != np.float32 or not xyz_np.flags["C_CONTIGUOUS"] or xyz_np.ndim != 3:
+            raise TypeError("xyz must be C-contiguous float32 [n_frames, n_total, 3]")
+        used = np.ascontiguousarray(used, dtype=np.int32)
+        if used.shape[0] != self.n_used:
+            raise ValueError("len(used) must equal the number of used atoms of the system")
+        if box_np is not None and (box_np.dtype != np.float32 or not box_np.flags["C_CONTIGUOUS"]
+                                   or box_np.size != xyz_np.shape[0] * 9):
+            raise TypeError("box must be C-contiguous float32 [n_frames, 3, 3]")
+        torch.cuda.current_stream(self.device).synchronize()
+        self._check(self._L.cmb_accumulate_host_gather(self._ctx, _ptr(xyz_np), xyz_np.shape[1], _ptr(used),
+                                                       _ptr(box_np), xyz_np.shape[0], int(chunk_frames),
+                                                       int(n_threads), _ptr(atom_table), _ptr(res_table)),
+                    "cmb_accumulate_host_gather")
+
     def export_nonzero(self, table):
         """(flat index int64[], count uint32[]) of the non-zero entries, sorted by index."""
         return self.export_many([table])[0]

@@ -81,6 +81,17 @@ int cmb_accumulate_host(cmb_ctx* ctx, const float* h_xyz, const float* h_box, in
                         int64_t chunk_frames, uint32_t* d_atom_table, uint32_t* d_res_table);
 
 /*
+ * Trajectory ingest: like cmb_accumulate_host, but h_xyz_full holds ALL atoms,
+ * [n_frames][n_total][3], and the used atoms (h_used[n_used], ascending atom indices) are gathered
+ * on the fly: host threads pack chunk k+1 into pinned staging while chunk k is copied and
+ * processed.  Fuses the reference's _atom_slice copy (atom_indexer.py:5-22, `xyz[:, indices]`)
+ * into the streaming pipeline.  n_threads <= 0 picks a default.  Synchronous.
+ */
+int cmb_accumulate_host_gather(cmb_ctx* ctx, const float* h_xyz_full, int n_total, const int32_t* h_used,
+                               const float* h_box, int64_t n_frames, int64_t chunk_frames, int n_threads,
+                               uint32_t* d_atom_table, uint32_t* d_res_table);
+
+/*
  * contact_trajectory._build_contacts (contact_trajectory.py:7-44): per-frame contact
  * sets as unordered 64-bit keys  (frame0+f) << 40 | lo << 20 | hi  (used-atom
  * indices for atoms, compact residue ids for residues).  d_counts[0]/[1] (device

@@ -98,3 +98,24 @@ def test_host_path_and_frame_keys(engine, case_id):
         rs = rframe == f
         got = set(zip(rmap[rlo[rs]].tolist(), rmap[rhi[rs]].tolist()))
         assert got == want
+
+
+@pytest.mark.parametrize("case_id,n_threads", [(0, 1), (2, 4), (7, 0)])
+def test_host_gather_path(engine, case_id, n_threads):
+    """cmb_accumulate_host_gather (fused _atom_slice, atom_indexer.py:5-22): a host trajectory that
+    holds extra atoms gives the same tables as the pre-sliced one."""
+    case = CASES[case_id]
+    n, cutoff, n_ign, n_frames = case[0], case[2], case[3], case[4]
+    system, xyz, box, (atom_res, atom_chain, role), (ref_atom, _) = _run_case(engine, case, 100 + case_id)
+    rng = np.random.default_rng(7 + case_id)
+    n_total = n + 37
+    used = np.sort(rng.choice(n_total, size=n, replace=False)).astype(np.int32)
+    full = rng.normal(size=(n_frames, n_total, 3)).astype(np.float32)
+    full[:, used] = xyz
+    engine.set_system(atom_res, atom_chain, role, cutoff, n_ign)
+    atom_t, res_t = engine.new_tables()
+    engine.accumulate_host_gather(full, used, box, atom_t, res_t, chunk_frames=2, n_threads=n_threads)
+    idx, cnt = engine.export_nonzero(atom_t)
+    assert np.array_equal(dense_from_export(idx, cnt, n), ref_atom)
+    with pytest.raises(Exception):
+        engine.accumulate_host_gather(full, used[::-1].copy(), box, atom_t, res_t)
