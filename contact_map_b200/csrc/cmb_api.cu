@@ -391,7 +391,6 @@ static int launch_frames(cmb_ctx* ctx, const FrameJob& job, int slot, cudaStream
         p.n = ctx->n; p.meta32 = ctx->d_meta32;
         p.cutoff = ctx->cutoff_f; p.c2 = c2;
         p.boundary_ulps = job.boundary_ulps;
-        p.c2_hi = job.boundary_ulps > 0 ? advance_float(c2, job.boundary_ulps) : c2;
         p.n_ignored = ctx->n_ignored; p.n_res_c = ctx->n_res_c;
         p.maxc = ctx->fs_maxc; p.bm_words = ctx->fs_bm_words; p.bm_in_smem = ctx->fs_bm_in_smem;
         p.atom_table = job.atom_table; p.res_table = job.res_table;
@@ -431,7 +430,6 @@ static int launch_frames(cmb_ctx* ctx, const FrameJob& job, int slot, cudaStream
     lj.xyz = job.xyz; lj.box = job.box; lj.n_frames = job.n_frames; lj.frame0 = job.frame0;
     lj.n = ctx->n; lj.meta = ctx->d_meta; lj.cutoff = ctx->cutoff_f; lj.c2 = c2;
     lj.boundary_ulps = job.boundary_ulps;
-    lj.c2_hi = job.boundary_ulps > 0 ? advance_float(c2, job.boundary_ulps) : c2;
     lj.n_ignored = ctx->n_ignored; lj.n_res_c = ctx->n_res_c;
     lj.atom_table = job.atom_table; lj.res_table = job.res_table;
     lj.atom_keys = job.atom_keys; lj.atom_cap = job.atom_cap;

@@ -18,6 +18,7 @@ namespace cmb {
 struct GridS {
     double m[9];     // fractional transform: s_k = sum_r (p_r - o_r) * m[r*3+k]
     double o[3];
+    double h[9];     // unit cell rows (periodic grids): wrapped position = p - floor(s) . h
     int nx, ny, nz, ncell;
     int periodic;
     // c / nx == __umulhi(c << 6, magic_x) for c < 2^16 (ceil(2^26 / nx)); same for ny
@@ -59,6 +60,7 @@ __device__ inline void make_grid(GridS& G, const float* box9, double cutoff, int
         const double det = h[0] * (h[4] * h[8] - h[5] * h[7]) - h[1] * (h[3] * h[8] - h[5] * h[6]) +
                            h[2] * (h[3] * h[7] - h[4] * h[6]);
         const double id = 1.0 / det;
+        for (int k = 0; k < 9; k++) G.h[k] = h[k];
         G.m[0] = (h[4] * h[8] - h[5] * h[7]) * id;
         G.m[1] = (h[2] * h[7] - h[1] * h[8]) * id;
         G.m[2] = (h[1] * h[5] - h[2] * h[4]) * id;
@@ -82,7 +84,7 @@ __device__ inline void make_grid(GridS& G, const float* box9, double cutoff, int
         G.periodic = 1;
     } else {
         int nc[3];
-        for (int k = 0; k < 9; k++) G.m[k] = 0.0;
+        for (int k = 0; k < 9; k++) { G.m[k] = 0.0; G.h[k] = 0.0; }
         for (int k = 0; k < 3; k++) {
             const double ext = (double)hi[k] - (double)lo[k];
             G.o[k] = (double)lo[k];
@@ -102,14 +104,21 @@ __device__ inline void make_grid(GridS& G, const float* box9, double cutoff, int
     G.distinct = !G.periodic || (G.nx >= 3 && G.ny >= 3 && G.nz >= 3);
 }
 
-__device__ __forceinline__ int cell_of(const GridS& G, float x, float y, float z)
+// Cell of an atom; on periodic grids (x, y, z) is replaced by the position wrapped into the
+// primary cell image (fp64, rounded once to fp32).  The cell only selects candidates and the
+// wrapped position only feeds the screening distance: neither ever decides an ambiguous pair.
+__device__ __forceinline__ int cell_wrap(const GridS& G, float& x, float& y, float& z)
 {
     const double px = (double)x - G.o[0], py = (double)y - G.o[1], pz = (double)z - G.o[2];
     double sx = px * G.m[0] + py * G.m[3] + pz * G.m[6];
     double sy = px * G.m[1] + py * G.m[4] + pz * G.m[7];
     double sz = px * G.m[2] + py * G.m[5] + pz * G.m[8];
     if (G.periodic) {
-        sx -= floor(sx); sy -= floor(sy); sz -= floor(sz);
+        const double fx = floor(sx), fy = floor(sy), fz = floor(sz);
+        sx -= fx; sy -= fy; sz -= fz;
+        x = (float)(px - (fx * G.h[0] + fy * G.h[3] + fz * G.h[6]));
+        y = (float)(py - (fx * G.h[1] + fy * G.h[4] + fz * G.h[7]));
+        z = (float)(pz - (fx * G.h[2] + fy * G.h[5] + fz * G.h[8]));
     }
     int cx = (int)(sx * (double)G.nx);
     int cy = (int)(sy * (double)G.ny);
@@ -124,19 +133,31 @@ __device__ __forceinline__ int cell_of(const GridS& G, float x, float y, float z
 // =================================================================================
 // Pair phase shared by both paths.
 //
-// The frame's atoms are cell-sorted into `sorted[pos] = {x, y, z, ekey}` where `ekey` is the
-// exclusion key AS A FLOAT (exact: keys are < 2^24), so the residue-exclusion test is one FADD and
-// one FSETP on |.|; `sidx[pos]` is the atom index, through which the rare consumers (hits, role
-// test) reach the per-atom meta words.  A `Traits` type fixes the integer widths of the two paths:
-//   pos_t       element type of cellptr / sidx / the per-warp candidate list
-//   role()      role bits (bit0 = query, bit1 = haystack) of an atom
-//   decode()    cell id -> (cx, cy, cz)
-//   hit_t       queue entry of one hit, with pack()/ipos()/jpos()
-// and a `Sink` object accounts one hit (atom table, residue de-duplication).
+// Screening and adjudication are split:
+//   * the frame's atoms are cell-sorted into `sorted[pos] = {wx, wy, wz, bits}`: the position
+//     WRAPPED into the primary cell image (fp64 in the binning pass, rounded to fp32) and
+//     `bits = atom index | role << 30`;
+//   * one warp per occupied cell; every candidate pair of the half-shell stencil costs 3 FADD +
+//     3 FFMA + 1 SHF: t = dx*dx + dy*dy + dz*dz - c2_hi on the wrapped coordinates (+ the lattice
+//     shift of the candidate's stencil cell), whose sign bit is funnel-shifted into a per-lane
+//     bit mask (one bit per own atom of the cell, one mask per register-resident candidate);
+//   * after the own-atom loop the non-zero masks are pushed to a per-warp shared-memory ring
+//     and accounted 32 pairs at a time with all lanes busy: d2a <= c2_lo is a certain contact,
+//     anything else that passed the screen is AMBIGUOUS and is decided by MDTraj's exact
+//     non-fused fp32 arithmetic on the RAW coordinates (cmb_math.cuh::nl_d2).
+//     [c2_lo, c2_hi] = c2 -/+ a rigorous per-frame bound on |d2_exact - d2_screen|
+//     (frame_margins); when the bound cannot be established (fewer than 3 cells along a
+//     periodic dimension, non-triangular box, huge coordinates) the band is everything and
+//     every candidate is adjudicated exactly.
+// A `Traits` type fixes the integer widths of the two paths (cell pointers, candidate list
+// entries, ring entries); a `Sink` object owns the per-atom meta words and accounts one hit
+// (atom table, per-frame residue de-duplication).
 // =================================================================================
-constexpr int CT_KSLOT = 4;                 // register-resident candidates per lane
+constexpr int CT_KSLOT = 3;                 // register-resident candidates per lane
 constexpr int CT_CAND = 32 * CT_KSLOT;      // candidates per chunk
-constexpr int CT_HITQ = 64;                 // per-warp queue of compacted hits
+constexpr int CT_QCAP = 64;                 // per-warp ring of screened (candidate, own-atom mask) entries
+constexpr int CT_NOSHIFT = 13;              // shift id of "no lattice shift"
+constexpr float CT_FAR = 1.0e18f;           // coordinate of an empty candidate slot
 
 // kernel variants (template FLAGS)
 constexpr int CT_EMIT = 1;        // emit (frame, a, b) keys
@@ -147,12 +168,12 @@ constexpr int CT_ROLES = 8;       // query / haystack are not "all atoms": test 
 // hot-loop parameters (everything a cell task needs besides the geometry)
 struct PairParams {
     int n;                           // used atoms
-    float n_ignored_f;               // n_ignored as a float
-    const void* meta;                // per-atom meta words (layout known to Traits / Sink)
+    int n_ignored;
     float c2;                        // cutoff_f * cutoff_f
-    float c2_hi;                     // c2 advanced by boundary_ulps float steps
+    float c2_lo, c2_hi;              // certain-contact / screening thresholds of this frame
     int boundary_ulps;
-    unsigned int* atom_table;        // [n][n] uint32 (entry [lo][hi]) or nullptr
+    const float* xyz_frame;          // RAW coordinates of this frame [n][3] (global memory)
+    const float* box9;               // unit cell rows of this frame (global memory) or nullptr
     unsigned long long* atom_keys;   // emitted (frame<<40 | lo<<20 | hi) or nullptr
     long long atom_cap;
     unsigned long long* counters;    // [0] atom keys, [1] residue keys, [2] boundary records, [3] pair tests
@@ -163,255 +184,412 @@ struct PairParams {
 
 template <typename Traits>
 struct PairCtx {
-    const float4* sorted;                       // [n] {x, y, z, word}
-    const typename Traits::pos_t* sidx;         // [n] atom index of each sorted position
+    const float4* sorted;                       // [n] {wx, wy, wz, bits}: atom index, role (+ exclusion
+                                                // key in the fused kernel), layout known to Traits
+    const float* ekey;                          // [n] exclusion key per sorted position (global path)
     const typename Traits::pos_t* cellptr;      // [ncell + 1]
-    typename Traits::pos_t* cand;               // this warp's candidate list [CT_CAND]
-    typename Traits::hit_t* hitq;               // this warp's hit queue [CT_HITQ]
+    typename Traits::cand_t* cand;              // this warp's candidate list [CT_CAND]
+    typename Traits::hit_t* hitq;               // this warp's ring [CT_QCAP]
+    unsigned int* qcnt;                         // this warp's ring write counter (shared memory)
+    const float4* shift;                        // [27] lattice shift of each wrap combination
 };
 
-// Warp-ballot compaction: the hits of one slot iteration (a few % of the lanes) are appended to
-// the warp's queue and accounted 32 at a time with all lanes busy.
-template <typename Traits, typename Sink>
-__device__ __forceinline__ void ct_queue_hits(const PairCtx<Traits>& cx, Sink& sink, bool hit, int ipos,
-                                              int jpos, int& qn)
+// screening distance, as recomputed when a screened pair is accounted
+__device__ __forceinline__ float d2_screen(float xi, float yi, float zi, float xj, float yj, float zj)
 {
-    const unsigned hm = __ballot_sync(0xffffffffu, hit);
-    if (hm == 0u) return;
-    const int lane = threadIdx.x & 31;
-    if (hit) cx.hitq[qn + __popc(hm & ((1u << lane) - 1u))] = Traits::pack(ipos, jpos);
-    qn += __popc(hm);
-    if (qn >= 32) {
-        __syncwarp();
-        const typename Traits::hit_t e = cx.hitq[lane];
-        typename Traits::hit_t rest = Traits::pack(0, 0);
-        if (32 + lane < qn) rest = cx.hitq[32 + lane];
-        __syncwarp();
-        cx.hitq[lane] = rest;
-        qn -= 32;
-        sink.account(Traits::ipos(e), Traits::jpos(e));
+    const float dx = __fsub_rn(xj, xi), dy = __fsub_rn(yj, yi), dz = __fsub_rn(zj, zi);
+    return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+}
+
+// ring slot reservation: one ATOMS per pushing lane (opaque to the compiler's warp aggregation)
+__device__ __forceinline__ unsigned ring_reserve(unsigned int* qcnt)
+{
+    unsigned old;
+    asm volatile("atom.shared.add.u32 %0, [%1], 1;"
+                 : "=r"(old)
+                 : "r"((unsigned)__cvta_generic_to_shared(qcnt))
+                 : "memory");
+    return old;
+}
+
+// Per-frame thresholds.  A = max |raw coordinate| of the frame, box9 = unit cell rows or nullptr.
+// Bound on |d2_exact - d2_screen| for pairs whose distance is near the cutoff:
+// per-component error of the exact chain <= 8u * (largest intermediate magnitude), of the
+// screening chain <= 10u * (sum of |box entries|) (wrapped position, shift, subtraction);
+// both chains resolve the same periodic image when the stencil cells are distinct, the box is
+// lower triangular and the image counts stay far below 2^23.  The rounding of either
+// accumulation order of the squares is covered by the 24u c^2 term.
+__device__ inline void frame_margins(const float* box9, int distinct, double A, float c2, double cutoff,
+                                     int extra_ulps, float& c2_lo, float& c2_hi)
+{
+    const double u = 5.9604644775390625e-8;   // 2^-24
+    bool ok = true;
+    double e;
+    if (box9 == nullptr) {
+        e = 4.0 * u * A;
+    } else {
+        const double ax = box9[0], ay = box9[1], az = box9[2], bx = fabs((double)box9[3]), by = box9[4],
+                     bz = box9[5], cx = fabs((double)box9[6]), cy = fabs((double)box9[7]), cz = box9[8];
+        ok = distinct && ay == 0.0 && az == 0.0 && bz == 0.0 && ax > 0.0 && by > 0.0 && cz > 0.0;
+        const double sc = 2.0 * A / cz + 2.0;
+        const double sb = (2.0 * A + sc * cy) / by + 2.0;
+        const double sa = (2.0 * A + sc * cx + sb * bx) / ax + 2.0;
+        ok = ok && sa < 1.0e5 && sb < 1.0e5 && sc < 1.0e5;
+        const double mx = 2.0 * A + sc * cx + sb * bx + sa * ax;
+        const double my = 2.0 * A + sc * cy + sb * by;
+        const double mz = 2.0 * A + sc * cz;
+        const double mmax = fmax(mx, fmax(my, mz));
+        const double S = ax + bx + by + cx + cy + cz;
+        e = 8.0 * u * mmax + 10.0 * u * S + 1.0e-15 * mmax;
+    }
+    const double c = cutoff * 1.01;
+    const double bound = 1.7320508075688772 * e * (2.0 * c + 2.0 * e) + 24.0 * u * c * c;
+    const double M = 2.0 * bound;
+    ok = ok && (M < 0.25 * (double)c2);
+    if (!ok) {
+        c2_lo = -3.0e38f;
+        c2_hi = 3.0e38f;
+        return;
+    }
+    c2_lo = __double2float_rd((double)c2 - M);
+    c2_hi = __double2float_ru((double)c2 + M);
+    if (extra_ulps > 0) {
+        c2_lo = fminf(c2_lo, __int_as_float(__float_as_int(c2) - extra_ulps - 1));
+        c2_hi = fmaxf(c2_hi, __int_as_float(__float_as_int(c2) + extra_ulps + 1));
     }
 }
 
-template <typename Traits, typename Sink>
-__device__ __forceinline__ void ct_drain_hits(const PairCtx<Traits>& cx, Sink& sink, int& qn)
+// lattice shift of wrap combination id = (wx+1) + 3(wy+1) + 9(wz+1), w in {-1,0,1}: an atom of a
+// stencil cell reached through a periodic wrap appears at (wrapped position) + shift
+__device__ inline float4 lattice_shift(const float* box9, int id)
 {
-    __syncwarp();
-    const int lane = threadIdx.x & 31;
-    if (lane < qn) {
-        const typename Traits::hit_t e = cx.hitq[lane];
-        sink.account(Traits::ipos(e), Traits::jpos(e));
-    }
-    qn = 0;
-    __syncwarp();
+    if (box9 == nullptr) return make_float4(0.f, 0.f, 0.f, 0.f);
+    const double wx = (double)(id % 3 - 1), wy = (double)((id / 3) % 3 - 1), wz = (double)(id / 9 - 1);
+    return make_float4((float)(wx * box9[0] + wy * box9[3] + wz * box9[6]),
+                       (float)(wx * box9[1] + wy * box9[4] + wz * box9[7]),
+                       (float)(wx * box9[2] + wy * box9[5] + wz * box9[8]), 0.f);
 }
 
-// all (own atom) x (NK register slots) tests of one candidate chunk
-template <typename Traits, typename Sink, int MODE, int NK, int FLAGS>
-__device__ __forceinline__ void ct_inner(const PairParams& p, const NlBox& B, const PairCtx<Traits>& cx,
-                                         Sink& sink, int cstart, int cend, const float (&xj)[CT_KSLOT],
-                                         const float (&yj)[CT_KSLOT], const float (&zj)[CT_KSLOT],
-                                         const float (&ej)[CT_KSLOT], const unsigned (&rj)[CT_KSLOT],
-                                         const int (&jpos)[CT_KSLOT], int& qn)
+__device__ __forceinline__ int box_mode(const float* __restrict__ box9)
+{
+    if (box9 == nullptr) return BOX_NONE;
+    const bool tri = (box9[1] != 0.f) || (box9[2] != 0.f) || (box9[3] != 0.f) || (box9[5] != 0.f) ||
+                     (box9[6] != 0.f) || (box9[7] != 0.f);
+    return tri ? BOX_TRICLINIC : BOX_ORTHO;
+}
+
+// Account one screened pair (sorted positions ipos < jpos, shift id of jpos' stencil cell);
+// `active` is false for the idle lanes of a partial drain.  Called by all 32 lanes.
+template <typename Traits, typename Sink, int MODE, int FLAGS>
+__device__ __forceinline__ void ct_account(const PairParams& p, const PairCtx<Traits>& cx, Sink& sink, int ipos,
+                                           int jpos, int id, bool active)
 {
     const int lane = threadIdx.x & 31;
-    for (int ipos = cstart; ipos < cend; ipos++) {
+    const float4 wi = cx.sorted[ipos], wj = cx.sorted[jpos], sh = cx.shift[id];
+    const float d2a = d2_screen(wi.x, wi.y, wi.z, __fadd_rn(wj.x, sh.x), __fadd_rn(wj.y, sh.y),
+                                __fadd_rn(wj.z, sh.z));
+    const unsigned bi = __float_as_uint(wi.w), bj = __float_as_uint(wj.w);
+    const int ia = Traits::atom(bi), ib = Traits::atom(bj);
+    sink.prepare(ia, ib);                      // (the residue exclusion was part of the screen)
+    bool elig = active;
+    if (FLAGS & CT_ROLES) {
+        const unsigned ri = Traits::role(bi), rj = Traits::role(bj);
+        elig = elig && (((ri & (rj >> 1)) | (rj & (ri >> 1))) & 1u);
+    }
+    bool hit = elig && (d2a <= p.c2_lo);
+    if (elig && !hit) {
+        // ambiguous: MDTraj's arithmetic on the raw coordinates, direction lower -> higher sorted
+        // position (antisymmetric for every pair that can be a hit, DESIGN.md "direction")
+        const NlBox B = make_nlbox(p.box9);
+        const float* pa = p.xyz_frame + 3 * (size_t)ia;
+        const float* pb = p.xyz_frame + 3 * (size_t)ib;
+        const float d2 = nl_d2<MODE>(__ldg(pa), __ldg(pa + 1), __ldg(pa + 2), __ldg(pb), __ldg(pb + 1),
+                                     __ldg(pb + 2), B);
+        hit = d2 <= p.c2;
+        if (FLAGS & CT_BOUNDARY) {
+            int diff = __float_as_int(d2) - __float_as_int(p.c2);
+            diff = diff < 0 ? -diff : diff;
+            if (diff <= p.boundary_ulps) {
+                const unsigned long long w = atomicAdd(&p.counters[2], 1ull);
+                if ((long long)w < p.boundary_cap)
+                    p.boundary[w] = make_float4(__int_as_float((int)p.frame_id), __int_as_float(min(ia, ib)),
+                                                __int_as_float(max(ia, ib)), d2);
+            }
+        }
+    }
+    if (FLAGS & CT_EMIT) {
+        if (p.atom_keys != nullptr) {
+            // warp-ballot compaction of this batch's hits into the key stream
+            const unsigned hm = __ballot_sync(0xffffffffu, hit);
+            if (hm) {
+                const int leader = __ffs(hm) - 1;
+                unsigned long long wbase = 0;
+                if (lane == leader) wbase = atomicAdd(&p.counters[0], (unsigned long long)__popc(hm));
+                wbase = __shfl_sync(0xffffffffu, wbase, leader);
+                if (hit) {
+                    const unsigned long long w = wbase + __popc(hm & ((1u << lane) - 1u));
+                    if ((long long)w < p.atom_cap)
+                        p.atom_keys[w] = ((unsigned long long)p.frame_id << 40) |
+                                         ((unsigned long long)min(ia, ib) << 20) | (unsigned long long)max(ia, ib);
+                }
+            }
+        }
+    }
+    if (hit) sink.account(ia, ib);
+}
+
+// Pop up to 32 ring entries (one per lane); an entry is (own-atom base, candidate, mask of own
+// atoms): the lane accounts the lowest own atom of its mask and pushes the rest back.
+template <typename Traits, typename Sink, int MODE, int FLAGS>
+__device__ __forceinline__ void ct_drain(const PairParams& p, const PairCtx<Traits>& cx, Sink& sink,
+                                         unsigned& head, unsigned left)
+{
+    const int lane = threadIdx.x & 31;
+    const bool active = (unsigned)lane < left;
+    const typename Traits::hit_t e = cx.hitq[(head + (active ? lane : 0)) & (CT_QCAP - 1)];
+    head += left < 32u ? left : 32u;
+    const unsigned m = Traits::e_mask(e);
+    const int bit = __ffs(m) - 1;
+    const unsigned rest = m & (m - 1u);
+    __syncwarp();
+    if (active && rest) cx.hitq[ring_reserve(cx.qcnt) & (CT_QCAP - 1)] = Traits::with_mask(e, rest);
+    ct_account<Traits, Sink, MODE, FLAGS>(p, cx, sink, Traits::e_ibase(e) + bit, Traits::e_jpos(e),
+                                          Traits::e_id(e), active);
+}
+
+// drain while more than `keep` entries are waiting (keep = 31: full batches only; 0: everything)
+template <typename Traits, typename Sink, int MODE, int FLAGS>
+__device__ __forceinline__ void ct_drain_while(const PairParams& p, const PairCtx<Traits>& cx, Sink& sink,
+                                               unsigned& head, unsigned keep)
+{
+    for (;;) {
+        __syncwarp();
+        const unsigned left = *(volatile unsigned int*)cx.qcnt - head;
+        if (left <= keep) break;
+        ct_drain<Traits, Sink, MODE, FLAGS>(p, cx, sink, head, left);
+    }
+}
+
+// Screening loop: own atoms [g0, g1) (at most 32, highest first so that bit b of a mask is own
+// atom g0 + b) against NK register-resident candidates per lane.  Per pair: 3 FADD + 3 FFMA for
+// t = d2 - c2_hi, 2 FADD + 1 FMNMX for the residue exclusion (q = n_ignored + 0.5 - |ekey_i -
+// ekey_j| is negative iff the pair is NOT excluded; keys are small integers, exact in fp32), and
+// one SHF that shifts the sign of max(t, q) into the mask.
+template <typename Traits, int NK, int FLAGS>
+__device__ __forceinline__ void ct_screen(const PairCtx<Traits>& cx, int g0, int g1, float neg_c2_hi, float nq,
+                                          const float (&xj)[CT_KSLOT], const float (&yj)[CT_KSLOT],
+                                          const float (&zj)[CT_KSLOT], const float (&ej)[CT_KSLOT], bool any_q,
+                                          bool any_h, unsigned (&m)[CT_KSLOT])
+{
+    for (int ipos = g1 - 1; ipos >= g0; ipos--) {
         const float4 pi = cx.sorted[ipos];
-        unsigned ri = 3u;
-        if (FLAGS & CT_ROLES) ri = Traits::role(p.meta, (int)cx.sidx[ipos]);
+        const float ei = Traits::ekey_f(cx, ipos, __float_as_uint(pi.w));
+        if (FLAGS & CT_ROLES) {
+            const unsigned ri = Traits::role(__float_as_uint(pi.w));
+            if (!(((ri & 1u) && any_h) || ((ri & 2u) && any_q))) {
+#pragma unroll
+                for (int k = 0; k < NK; k++) m[k] <<= 1;
+                continue;
+            }
+        }
 #pragma unroll
         for (int k = 0; k < NK; k++) {
-            // tested in the direction lower sorted position -> higher; the arithmetic is
-            // antisymmetric for every pair that can be a hit ("direction")
-            const float d2 = nl_d2<MODE>(pi.x, pi.y, pi.z, xj[k], yj[k], zj[k], B);
-            // |ekey_i - ekey_j| > n_ignored  (exact small integers held as floats)
-            bool elig = (fabsf(__fsub_rn(pi.w, ej[k])) > p.n_ignored_f) && (jpos[k] > ipos);
-            if (FLAGS & CT_ROLES)
-                elig = elig && (((ri & (rj[k] >> 1)) | (rj[k] & (ri >> 1))) & 1u);
-            if (FLAGS & CT_BOUNDARY) {
-                if (elig && d2 <= p.c2_hi) {
-                    int diff = __float_as_int(d2) - __float_as_int(p.c2);
-                    diff = diff < 0 ? -diff : diff;
-                    if (diff <= p.boundary_ulps) {
-                        const int ia = (int)cx.sidx[ipos], ib = (int)cx.sidx[jpos[k]];
-                        const unsigned long long w = atomicAdd(&p.counters[2], 1ull);
-                        if ((long long)w < p.boundary_cap)
-                            p.boundary[w] = make_float4(__int_as_float((int)p.frame_id),
-                                                        __int_as_float(min(ia, ib)),
-                                                        __int_as_float(max(ia, ib)), d2);
-                    }
-                }
-            }
-            const bool hit = elig && (d2 <= p.c2);
-            if (FLAGS & CT_EMIT) {
-                // warp-ballot compaction of this slot's hits into the key stream
-                const unsigned hm = __ballot_sync(0xffffffffu, hit);
-                if (hm) {
-                    const int leader = __ffs(hm) - 1;
-                    unsigned long long wbase = 0;
-                    if (lane == leader) wbase = atomicAdd(&p.counters[0], (unsigned long long)__popc(hm));
-                    wbase = __shfl_sync(0xffffffffu, wbase, leader);
-                    if (hit) {
-                        const unsigned long long w = wbase + __popc(hm & ((1u << lane) - 1u));
-                        const int ia = (int)cx.sidx[ipos], ib = (int)cx.sidx[jpos[k]];
-                        if ((long long)w < p.atom_cap)
-                            p.atom_keys[w] = ((unsigned long long)p.frame_id << 40) |
-                                             ((unsigned long long)min(ia, ib) << 20) |
-                                             (unsigned long long)max(ia, ib);
-                    }
-                }
-            }
-            ct_queue_hits<Traits, Sink>(cx, sink, hit, ipos, jpos[k], qn);
+            const float dx = __fsub_rn(xj[k], pi.x), dy = __fsub_rn(yj[k], pi.y), dz = __fsub_rn(zj[k], pi.z);
+            const float t = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmaf_rn(dx, dx, neg_c2_hi)));
+            const float q = __fsub_rn(nq, fabsf(__fsub_rn(ej[k], ei)));
+            m[k] = __funnelshift_l(__float_as_uint(fmaxf(t, q)), m[k], 1);   // sign: d2 < c2_hi, not excluded
         }
     }
 }
 
-// One warp adjudicates all candidate pairs of one occupied cell `c`.
+// One warp screens all candidate pairs of one occupied cell `c`.
 //
 // Candidates are the atoms of the stencil cells with id >= c (every unordered cell pair is
-// visited once).  Cells are numbered x-fastest, so for an INTERIOR cell (no periodic wrap, no
-// grid edge) they form five contiguous runs of the cell-sorted array:
+// visited once), own cell first.  Cells are numbered x-fastest, so for an INTERIOR cell (no
+// periodic wrap, no grid edge) they form five contiguous runs of the cell-sorted array:
 //     (cx..cx+1, cy, cz), (cx-1..cx+1, cy+1, cz), (cx-1..cx+1, cy-1..cy+1, cz+1)
 // and a candidate slot maps to its sorted position with four compares.  Edge cells take the
-// generic route: 27 stencil lanes, de-duplication (grids with < 3 cells along a dimension),
-// warp scan, per-warp candidate list.  Sorted-position order (jpos > ipos) removes self pairs
-// and double visits inside the own cell.
+// generic route: 27 stencil lanes (lane 0 = own cell), de-duplication (grids with < 3 cells
+// along a dimension), warp scan, per-warp candidate list whose entries carry the wrap flags of
+// their stencil cell (-> lattice shift added when the candidate is loaded).
+// Own-cell candidates occupy the first slots in sorted order, so "each unordered pair once, no
+// self pair" is `slot > own index`, applied to the masks before they are pushed to the ring.
 template <typename Traits, typename Sink, int MODE, int FLAGS>
-__device__ __forceinline__ void ct_cell_task(const PairParams& p, const NlBox& B, const GridS& G,
-                                             const PairCtx<Traits>& cx, Sink& sink, int c,
-                                             unsigned long long& n_tests, int& qn)
+__device__ __forceinline__ void ct_cell_task(const PairParams& p, const GridS& G, const PairCtx<Traits>& cx,
+                                             Sink& sink, int c, unsigned long long& n_tests, unsigned& head)
 {
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
-    int cxx, cy, cz;
-    Traits::decode(c, G, cxx, cy, cz);
     const int cstart = (int)cx.cellptr[c], cend = (int)cx.cellptr[c + 1];
 
-    const bool interior = (cxx >= 1) && (cxx <= G.nx - 2) && (cy >= 1) && (cy <= G.ny - 2) &&
-                          (cz >= 1) && (cz <= G.nz - 2);
-    int M;
-    // interior: run r covers slots [o_r, o_{r+1}) and sorted positions slot + a_r
-    int o1 = 0, o2 = 0, o3 = 0, o4 = 0, a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
-    // generic: this lane's stencil cell
-    int mystart = 0, mycnt = 0, off = 0;
-    if (interior) {
-        const int nxy = G.nx * G.ny;
-        const int b1 = c + G.nx - 1, b2 = c + nxy - G.nx - 1, b3 = c + nxy - 1, b4 = c + nxy + G.nx - 1;
-        const int s0 = cstart, e0 = (int)cx.cellptr[c + 2];
-        const int s1 = (int)cx.cellptr[b1], e1 = (int)cx.cellptr[b1 + 3];
-        const int s2 = (int)cx.cellptr[b2], e2 = (int)cx.cellptr[b2 + 3];
-        const int s3 = (int)cx.cellptr[b3], e3 = (int)cx.cellptr[b3 + 3];
-        const int s4 = (int)cx.cellptr[b4], e4 = (int)cx.cellptr[b4 + 3];
-        o1 = e0 - s0; o2 = o1 + (e1 - s1); o3 = o2 + (e2 - s2); o4 = o3 + (e3 - s3);
-        M = o4 + (e4 - s4);
-        a0 = s0; a1 = s1 - o1; a2 = s2 - o2; a3 = s3 - o3; a4 = s4 - o4;
-    } else {
-        int myD = -1;
-        if (lane < 27) {
-            const int l9 = lane / 9, l3 = (lane - l9 * 9) / 3;
-            int x = cxx + (lane - l9 * 9 - l3 * 3) - 1;
-            int y = cy + l3 - 1;
-            int z = cz + l9 - 1;
-            if (G.periodic) {
-                x = x < 0 ? x + G.nx : (x >= G.nx ? x - G.nx : x);
-                y = y < 0 ? y + G.ny : (y >= G.ny ? y - G.ny : y);
-                z = z < 0 ? z + G.nz : (z >= G.nz ? z - G.nz : z);
-            }
-            const bool ok = (x >= 0 && x < G.nx && y >= 0 && y < G.ny && z >= 0 && z < G.nz);
-            if (ok) myD = (z * G.ny + y) * G.nx + x;
-        }
-        bool keep = (myD >= c);
-        if (!G.distinct) {
-            const unsigned same = __match_any_sync(FULL, myD);
-            keep = keep && ((__ffs(same) - 1) == lane);
-        }
-        if (keep) {
-            mystart = (int)cx.cellptr[myD];
-            mycnt = (int)cx.cellptr[myD + 1] - mystart;
-        }
-        int incl = mycnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int v = __shfl_up_sync(FULL, incl, d);
-            if (lane >= d) incl += v;
-        }
-        M = __shfl_sync(FULL, incl, 31);
-        off = incl - mycnt;
-    }
-
-    for (int base = 0; base < M; base += CT_CAND) {
-        if (!interior) {
-            __syncwarp();
-            // expand this lane's stencil cell into the per-warp candidate list
-            const int r0 = max(0, base - off), r1 = min(mycnt, base + CT_CAND - off);
-            for (int r = r0; r < r1; r++) cx.cand[off + r - base] = (typename Traits::pos_t)(mystart + r);
-            __syncwarp();
-        }
+    for (int base = 0;; base += CT_CAND) {
+        // ---- candidates of this chunk (everything is re-derived per chunk so that nothing of it
+        //      stays live across the screening loop; a second chunk is rare) ------------------
         float xj[CT_KSLOT], yj[CT_KSLOT], zj[CT_KSLOT], ej[CT_KSLOT];
-        unsigned rj[CT_KSLOT];
-        int jpos[CT_KSLOT];
+        unsigned jp[CT_KSLOT];
+        unsigned roles_or = 0u;
+        int M;
+        {
+            int cxx, cy, cz;
+            Traits::decode(c, G, cxx, cy, cz);
+            const bool interior = (cxx >= 1) && (cxx <= G.nx - 2) && (cy >= 1) && (cy <= G.ny - 2) &&
+                                  (cz >= 1) && (cz <= G.nz - 2);
+            if (interior) {
+                // run r covers slots [o_r, o_{r+1}) and sorted positions slot + a_r
+                const int nxy = G.nx * G.ny;
+                const int b1 = c + G.nx - 1, b2 = c + nxy - G.nx - 1, b3 = c + nxy - 1, b4 = c + nxy + G.nx - 1;
+                const int s0 = cstart, e0 = (int)cx.cellptr[c + 2];
+                const int s1 = (int)cx.cellptr[b1], e1 = (int)cx.cellptr[b1 + 3];
+                const int s2 = (int)cx.cellptr[b2], e2 = (int)cx.cellptr[b2 + 3];
+                const int s3 = (int)cx.cellptr[b3], e3 = (int)cx.cellptr[b3 + 3];
+                const int s4 = (int)cx.cellptr[b4], e4 = (int)cx.cellptr[b4 + 3];
+                const int o1 = e0 - s0, o2 = o1 + (e1 - s1), o3 = o2 + (e2 - s2), o4 = o3 + (e3 - s3);
+                M = o4 + (e4 - s4);
+                const int a0 = s0, a1 = s1 - o1, a2 = s2 - o2, a3 = s3 - o3, a4 = s4 - o4;
 #pragma unroll
-        for (int k = 0; k < CT_KSLOT; k++) {
-            const int s = base + k * 32 + lane;
-            jpos[k] = -1; rj[k] = 3u; xj[k] = yj[k] = zj[k] = ej[k] = 0.f;
-            if (s < M) {
-                int pos;
-                if (interior) {
+                for (int k = 0; k < CT_KSLOT; k++) {
+                    const int s = base + k * 32 + lane;
                     int adj = a0;
                     adj = s >= o1 ? a1 : adj;
                     adj = s >= o2 ? a2 : adj;
                     adj = s >= o3 ? a3 : adj;
                     adj = s >= o4 ? a4 : adj;
-                    pos = s + adj;
-                } else {
-                    pos = (int)cx.cand[s - base];
+                    const int pos = s < M ? s + adj : cstart;       // empty slots: any valid position
+                    const float4 q = cx.sorted[pos];
+                    const unsigned bits = __float_as_uint(q.w);
+                    xj[k] = s < M ? q.x : CT_FAR; yj[k] = q.y; zj[k] = q.z;
+                    ej[k] = Traits::ekey_f(cx, pos, bits);
+                    jp[k] = Traits::jp(pos, CT_NOSHIFT);
+                    if (FLAGS & CT_ROLES) roles_or |= s < M ? Traits::role(bits) : 0u;
                 }
-                const float4 q = cx.sorted[pos];
-                xj[k] = q.x; yj[k] = q.y; zj[k] = q.z; ej[k] = q.w;
-                if (FLAGS & CT_ROLES) rj[k] = Traits::role(p.meta, (int)cx.sidx[pos]);
-                jpos[k] = pos;
+            } else {
+                // a wrap along x happens at one side only (grids with >= 3 cells; coarser periodic
+                // grids are adjudicated exactly and never use the shift)
+                const int idx_x = (cxx == 0) ? -1 : 1, idx_y = (cy == 0) ? -3 : 3, idx_z = (cz == 0) ? -9 : 9;
+                int myD = -1, mywrap = 0;
+                if (lane < 27) {
+                    const int si = lane == 0 ? 13 : (lane == 13 ? 0 : lane);     // own cell first
+                    const int l9 = si / 9, l3 = (si - l9 * 9) / 3;
+                    int x = cxx + (si - l9 * 9 - l3 * 3) - 1;
+                    int y = cy + l3 - 1;
+                    int z = cz + l9 - 1;
+                    if (G.periodic) {
+                        if (x < 0) { x += G.nx; mywrap |= 1; } else if (x >= G.nx) { x -= G.nx; mywrap |= 1; }
+                        if (y < 0) { y += G.ny; mywrap |= 2; } else if (y >= G.ny) { y -= G.ny; mywrap |= 2; }
+                        if (z < 0) { z += G.nz; mywrap |= 4; } else if (z >= G.nz) { z -= G.nz; mywrap |= 4; }
+                    }
+                    const bool ok = (x >= 0 && x < G.nx && y >= 0 && y < G.ny && z >= 0 && z < G.nz);
+                    if (ok) myD = (z * G.ny + y) * G.nx + x;
+                }
+                bool keep = (myD >= c);
+                if (!G.distinct) {
+                    const unsigned same = __match_any_sync(FULL, myD);
+                    keep = keep && ((__ffs(same) - 1) == lane);
+                }
+                int mystart = 0, mycnt = 0;
+                if (keep) {
+                    mystart = (int)cx.cellptr[myD];
+                    mycnt = (int)cx.cellptr[myD + 1] - mystart;
+                }
+                int incl = mycnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int v = __shfl_up_sync(FULL, incl, d);
+                    if (lane >= d) incl += v;
+                }
+                M = __shfl_sync(FULL, incl, 31);
+                const int off = incl - mycnt;
+                __syncwarp();
+                // expand this lane's stencil cell into the per-warp candidate list
+                const int r0 = max(0, base - off), r1 = min(mycnt, base + CT_CAND - off);
+                for (int r = r0; r < r1; r++) cx.cand[off + r - base] = Traits::cand(mystart + r, mywrap);
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < CT_KSLOT; k++) {
+                    const int s = base + k * 32 + lane;
+                    const typename Traits::cand_t ce = s < M ? cx.cand[s - base] : Traits::cand(cstart, 0);
+                    const int pos = Traits::cand_pos(ce);
+                    const int wb = Traits::cand_wrap(ce);
+                    const int id = CT_NOSHIFT + ((wb & 1) ? idx_x : 0) + ((wb & 2) ? idx_y : 0) +
+                                   ((wb & 4) ? idx_z : 0);
+                    const float4 q = cx.sorted[pos];
+                    const float4 sh = cx.shift[id];
+                    const unsigned bits = __float_as_uint(q.w);
+                    xj[k] = s < M ? __fadd_rn(q.x, sh.x) : CT_FAR;
+                    yj[k] = __fadd_rn(q.y, sh.y); zj[k] = __fadd_rn(q.z, sh.z);
+                    ej[k] = Traits::ekey_f(cx, pos, bits);
+                    jp[k] = Traits::jp(pos, id);
+                    if (FLAGS & CT_ROLES) roles_or |= s < M ? Traits::role(bits) : 0u;
+                }
             }
+        }
+        bool any_q = true, any_h = true;
+        if (FLAGS & CT_ROLES) {
+            any_q = __any_sync(FULL, roles_or & 1u);
+            any_h = __any_sync(FULL, roles_or & 2u);
         }
         const int left = M - base;
         if (FLAGS & CT_COUNT) {
             if (lane == 0) n_tests += (unsigned long long)(cend - cstart) * (unsigned long long)min(left, CT_CAND);
         }
-        if (left > 96) ct_inner<Traits, Sink, MODE, 4, FLAGS>(p, B, cx, sink, cstart, cend, xj, yj, zj, ej, rj, jpos, qn);
-        else if (left > 64) ct_inner<Traits, Sink, MODE, 3, FLAGS>(p, B, cx, sink, cstart, cend, xj, yj, zj, ej, rj, jpos, qn);
-        else if (left > 32) ct_inner<Traits, Sink, MODE, 2, FLAGS>(p, B, cx, sink, cstart, cend, xj, yj, zj, ej, rj, jpos, qn);
-        else ct_inner<Traits, Sink, MODE, 1, FLAGS>(p, B, cx, sink, cstart, cend, xj, yj, zj, ej, rj, jpos, qn);
+        const float neg_c2_hi = -p.c2_hi, nq = (float)p.n_ignored + 0.5f;
+        for (int g0 = cstart; g0 < cend; g0 += 32) {
+            const int g1 = min(g0 + 32, cend);
+            unsigned m[CT_KSLOT];
+#pragma unroll
+            for (int k = 0; k < CT_KSLOT; k++) m[k] = 0u;
+            if (left > 64) ct_screen<Traits, 3, FLAGS>(cx, g0, g1, neg_c2_hi, nq, xj, yj, zj, ej, any_q, any_h, m);
+            else if (left > 32) ct_screen<Traits, 2, FLAGS>(cx, g0, g1, neg_c2_hi, nq, xj, yj, zj, ej, any_q, any_h, m);
+            else ct_screen<Traits, 1, FLAGS>(cx, g0, g1, neg_c2_hi, nq, xj, yj, zj, ej, any_q, any_h, m);
+            // push the non-empty masks (one code site for all slots: the accounting code behind
+            // ct_drain_while is large)
+#pragma unroll 1
+            for (int k = 0; k < CT_KSLOT; k++) {
+                unsigned mk = k == 0 ? m[0] : (k == 1 ? m[1] : m[2]);
+                const unsigned jpk = k == 0 ? jp[0] : (k == 1 ? jp[1] : jp[2]);
+                const int s = base + 32 * k + lane;
+                const int v = s - (g0 - cstart);          // own atoms g0 + b with b < v pair with this slot
+                if (s >= M || v <= 0) mk = 0u;
+                else if (v < 32) mk &= (1u << v) - 1u;
+                if (mk) cx.hitq[ring_reserve(cx.qcnt) & (CT_QCAP - 1)] = Traits::entry(g0, jpk, mk);
+                ct_drain_while<Traits, Sink, MODE, FLAGS>(p, cx, sink, head, 31u);
+            }
+        }
+        if (left <= CT_CAND) break;
     }
 }
 
 // Warps pull occupied cells from a task counter until the frame is exhausted.
 template <typename Traits, typename Sink, int MODE, int FLAGS, typename OccT>
-__device__ __forceinline__ void ct_pair_phase(const PairParams& p, const NlBox& B, const GridS& G,
-                                              const PairCtx<Traits>& cx, Sink& sink, const OccT* occ,
-                                              int n_occ, int* task_counter, unsigned long long& n_tests)
+__device__ __forceinline__ void ct_pair_phase(const PairParams& p, const GridS& G, const PairCtx<Traits>& cx,
+                                              Sink& sink, const OccT* occ, int n_occ, int* task_counter,
+                                              unsigned long long& n_tests)
 {
     const int lane = threadIdx.x & 31;
-    int qn = 0;      // hits waiting in this warp's queue
+    __syncwarp();
+    unsigned head = *(volatile unsigned int*)cx.qcnt;      // ring is empty between frames
     for (;;) {
         int k = 0;
         if (lane == 0) k = atomicAdd(task_counter, 1);
         k = __shfl_sync(0xffffffffu, k, 0);
         if (k >= n_occ) break;
-        ct_cell_task<Traits, Sink, MODE, FLAGS>(p, B, G, cx, sink, (int)occ[k], n_tests, qn);
+        ct_cell_task<Traits, Sink, MODE, FLAGS>(p, G, cx, sink, (int)occ[k], n_tests, head);
     }
-    ct_drain_hits<Traits, Sink>(cx, sink, qn);
+    ct_drain_while<Traits, Sink, MODE, FLAGS>(p, cx, sink, head, 0u);
 }
 
 template <typename Traits, typename Sink, int FLAGS, typename OccT>
-__device__ __forceinline__ void ct_pair_phase_dyn(const PairParams& p, const NlBox& B, const GridS& G,
-                                                  const PairCtx<Traits>& cx, Sink& sink, const OccT* occ,
-                                                  int n_occ, int* task_counter, unsigned long long& n_tests)
+__device__ __forceinline__ void ct_pair_phase_dyn(const PairParams& p, const GridS& G, const PairCtx<Traits>& cx,
+                                                  Sink& sink, const OccT* occ, int n_occ, int* task_counter,
+                                                  unsigned long long& n_tests)
 {
-    if (B.mode == BOX_ORTHO)
-        ct_pair_phase<Traits, Sink, BOX_ORTHO, FLAGS, OccT>(p, B, G, cx, sink, occ, n_occ, task_counter, n_tests);
-    else if (B.mode == BOX_TRICLINIC)
-        ct_pair_phase<Traits, Sink, BOX_TRICLINIC, FLAGS, OccT>(p, B, G, cx, sink, occ, n_occ, task_counter, n_tests);
+    const int mode = box_mode(p.box9);
+    if (mode == BOX_ORTHO)
+        ct_pair_phase<Traits, Sink, BOX_ORTHO, FLAGS, OccT>(p, G, cx, sink, occ, n_occ, task_counter, n_tests);
+    else if (mode == BOX_TRICLINIC)
+        ct_pair_phase<Traits, Sink, BOX_TRICLINIC, FLAGS, OccT>(p, G, cx, sink, occ, n_occ, task_counter, n_tests);
     else
-        ct_pair_phase<Traits, Sink, BOX_NONE, FLAGS, OccT>(p, B, G, cx, sink, occ, n_occ, task_counter, n_tests);
+        ct_pair_phase<Traits, Sink, BOX_NONE, FLAGS, OccT>(p, G, cx, sink, occ, n_occ, task_counter, n_tests);
 }
 
 }  // namespace cmb

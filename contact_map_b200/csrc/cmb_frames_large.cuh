@@ -5,9 +5,10 @@
 // cell arrays and the cell-sorted float4 copy of the frame live in HBM/L2 instead of
 // shared memory, and the whole GPU works on ONE frame at a time:
 //   kl_prepare  grid of the frame (+ bounding box for open boundaries), zero counters
-//   kl_bin      cell id + rank per atom (L2 atomics on the cell histogram)
+//   kl_bin      cell id + rank + wrapped position per atom (L2 atomics on the cell histogram),
+//               max |coordinate| of the frame
 //   kl_scan     exclusive scan over cells + occupied-cell list (single CTA)
-//   kl_scatter  cell-sorted float4 {x, y, z, exclusion key} + atom index
+//   kl_scatter  cell-sorted float4 {wrapped x, y, z, atom index | role << 30}
 //   kl_pairs    persistent CTAs, one warp per occupied cell (global task counter)
 // Per-frame residue de-duplication (contact_map.py:601-607,740) uses a frame-stamp
 // table instead of a bitmap: frames are processed in stream order, so
@@ -29,11 +30,11 @@ struct LargeScratch {
     int* d_cellcnt = nullptr;      // [LG_MAXC + 1]
     int* d_cellptr = nullptr;      // [LG_MAXC + 1]
     int* d_occ = nullptr;          // [LG_MAXC]
-    int* d_misc = nullptr;         // [0] n_occ, [1] task counter
-    int* d_atomcell = nullptr;     // [n]
+    int* d_misc = nullptr;         // [0] n_occ, [1] task counter, [2] max |coordinate| (float bits)
+    float4* d_wrapped = nullptr;   // [n] {wrapped x, y, z, cell id}
     int* d_atomrank = nullptr;     // [n]
     float4* d_sorted = nullptr;    // [n]
-    int* d_sidx = nullptr;         // [n]
+    float* d_sorted_ekey = nullptr;  // [n]
     unsigned int* d_stamp = nullptr;
     size_t stamp_elems = 0;
     unsigned int seq = 0;
@@ -42,14 +43,14 @@ struct LargeScratch {
 inline void large_scratch_free(LargeScratch& S)
 {
     cudaFree(S.d_grid); cudaFree(S.d_cellcnt); cudaFree(S.d_cellptr); cudaFree(S.d_occ);
-    cudaFree(S.d_misc); cudaFree(S.d_atomcell); cudaFree(S.d_atomrank); cudaFree(S.d_sorted); cudaFree(S.d_sidx);
+    cudaFree(S.d_misc); cudaFree(S.d_wrapped); cudaFree(S.d_atomrank); cudaFree(S.d_sorted); cudaFree(S.d_sorted_ekey);
     cudaFree(S.d_stamp);
     S = LargeScratch();
 }
 
 struct LargeJob {
     const float* xyz; const float* box; long long n_frames; long long frame0;
-    int n; const int2* meta; float cutoff; float c2; float c2_hi; int boundary_ulps;
+    int n; const int2* meta; float cutoff; float c2; int boundary_ulps;
     int n_ignored; int n_res_c;
     unsigned int* atom_table; unsigned int* res_table;
     unsigned long long* atom_keys; long long atom_cap;
@@ -61,17 +62,31 @@ struct LargeJob {
 // ----- traits + hit sink of the global-memory path -------------------------------------
 struct LargeTraits {
     typedef int pos_t;
-    typedef uint2 hit_t;                            // {ipos, jpos}
-    static __device__ __forceinline__ unsigned role(const void* meta, int atom)
+    typedef unsigned int cand_t;                    // sorted position [0,20) | wrap flags [20,23)
+    typedef uint4 hit_t;          // {own base, jpos [0,20) | shift id [20,25), own-atom mask, -}
+    static __device__ __forceinline__ cand_t cand(int pos, int wrap)
     {
-        return (unsigned)__ldg(reinterpret_cast<const int2*>(meta) + atom).y >> 30;
+        return (unsigned)pos | ((unsigned)wrap << 20);
     }
-    static __device__ __forceinline__ hit_t pack(int ipos, int jpos)
+    static __device__ __forceinline__ int cand_pos(cand_t e) { return (int)(e & 0xfffffu); }
+    static __device__ __forceinline__ int cand_wrap(cand_t e) { return (int)(e >> 20); }
+    static __device__ __forceinline__ unsigned jp(int jpos, int id) { return (unsigned)jpos | ((unsigned)id << 20); }
+    static __device__ __forceinline__ hit_t entry(int ibase, unsigned jp, unsigned mask)
     {
-        return make_uint2((unsigned)ipos, (unsigned)jpos);
+        return make_uint4((unsigned)ibase, jp, mask, 0u);
     }
-    static __device__ __forceinline__ int ipos(hit_t e) { return (int)e.x; }
-    static __device__ __forceinline__ int jpos(hit_t e) { return (int)e.y; }
+    static __device__ __forceinline__ hit_t with_mask(hit_t e, unsigned mask) { return make_uint4(e.x, e.y, mask, 0u); }
+    static __device__ __forceinline__ int e_ibase(hit_t e) { return (int)e.x; }
+    static __device__ __forceinline__ int e_jpos(hit_t e) { return (int)(e.y & 0xfffffu); }
+    static __device__ __forceinline__ int e_id(hit_t e) { return (int)(e.y >> 20); }
+    static __device__ __forceinline__ unsigned e_mask(hit_t e) { return e.z; }
+    // sorted[].w bits: atom index [0,30) | role [30,32); exclusion keys in a separate array
+    static __device__ __forceinline__ int atom(unsigned bits) { return (int)(bits & 0x3fffffffu); }
+    static __device__ __forceinline__ unsigned role(unsigned bits) { return bits >> 30; }
+    static __device__ __forceinline__ float ekey_f(const PairCtx<LargeTraits>& cx, int pos, unsigned)
+    {
+        return __ldg(cx.ekey + pos);
+    }
     static __device__ __forceinline__ void decode(int c, const GridS& G, int& cx, int& cy, int& cz)
     {
         const int cyz = c / G.nx;
@@ -81,14 +96,14 @@ struct LargeTraits {
     }
 };
 
-// Account one hit: RED into the dense atom table; per-frame residue de-duplication through the
-// frame-stamp table (frames run in stream order, so atomicMax(stamp, seq) < seq is the first hit
-// of that residue pair in the current frame).  The atomicMax result is only consumed at the NEXT
-// call (software pipelining): the L2 round trip of the stamp table overlaps the pair tests in
-// between instead of stalling the warp.  Lanes of one drain that hit the same residue pair are
-// merged first (__match_any_sync), which removes most of the atomics for 3-atom solvent residues.
+// Residue exclusion + accounting of one hit: RED into the dense atom table; per-frame residue
+// de-duplication through the frame-stamp table (frames run in stream order, so
+// atomicMax(stamp, seq) < seq is the first hit of that residue pair in the current frame).  The
+// atomicMax result is only consumed at the NEXT call (software pipelining): the L2 round trip of
+// the stamp table overlaps the pair tests in between instead of stalling the warp.  Lanes of one
+// drain that hit the same residue pair are merged first (__match_any_sync), which removes most of
+// the atomics for 3-atom solvent residues.
 struct StampSink {
-    const int* sidx;
     const int2* meta;               // [n] {ekey, res_c | role << 30}
     unsigned int* atom_table;
     unsigned int* stamp;            // nullptr: residues not requested
@@ -104,6 +119,7 @@ struct StampSink {
     unsigned int pend_old;
     unsigned int pend_lo, pend_hi;
     int pending;
+    int ra, rb;                     // compact residues of the pair handed to prepare()
 
     __device__ __forceinline__ void resolve()
     {
@@ -120,15 +136,19 @@ struct StampSink {
         pending = 0;
     }
 
-    // called by a converged set of lanes (a full warp in the queue path, lanes < qn in the drain)
-    __device__ __forceinline__ void account(int ipos, int jpos)
+    __device__ __forceinline__ void prepare(int ia, int ib)
     {
-        const int ia = sidx[ipos], ib = sidx[jpos];
+        ra = __ldg(&meta[ia]).y & 0x3fffffff;
+        rb = __ldg(&meta[ib]).y & 0x3fffffff;
+    }
+
+    // called by the lanes of one drain whose pair is a hit
+    __device__ __forceinline__ void account(int ia, int ib)
+    {
         const int a = min(ia, ib), b = max(ia, ib);
         if (atom_table != nullptr) atomicAdd(&atom_table[(size_t)a * (size_t)n + (size_t)b], 1u);
         if (stamp == nullptr) return;
         resolve();                                   // consume the previous call's atomicMax
-        const int ra = __ldg(&meta[ia]).y & 0x3fffffff, rb = __ldg(&meta[ib]).y & 0x3fffffff;
         const unsigned rlo = (unsigned)min(ra, rb), rhi = (unsigned)max(ra, rb);
         const unsigned slot32 = rlo * n_res_c + rhi;     // R_c^2 < 2^32 (checked on the host)
         const unsigned peers = __match_any_sync(__activemask(), slot32);
@@ -186,6 +206,7 @@ __global__ void __launch_bounds__(1024) kl_prepare(const float* __restrict__ x, 
         *grid = Gs;
         misc[0] = 0;
         misc[1] = 0;
+        misc[2] = 0;
     }
     __syncthreads();
     const int ncell = Gs.ncell;
@@ -194,14 +215,22 @@ __global__ void __launch_bounds__(1024) kl_prepare(const float* __restrict__ x, 
 
 __global__ void __launch_bounds__(256) kl_bin(const float* __restrict__ x, int n,
                                               const GridS* __restrict__ grid, int* __restrict__ cellcnt,
-                                              int* __restrict__ atomcell, int* __restrict__ atomrank)
+                                              float4* __restrict__ wrapped, int* __restrict__ atomrank,
+                                              int* __restrict__ misc)
 {
     const GridS G = *grid;
+    float amax = 0.f;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int c = cell_of(G, __ldg(&x[3 * (size_t)i]), __ldg(&x[3 * (size_t)i + 1]), __ldg(&x[3 * (size_t)i + 2]));
-        atomcell[i] = c;
+        float px = __ldg(&x[3 * (size_t)i]), py = __ldg(&x[3 * (size_t)i + 1]), pz = __ldg(&x[3 * (size_t)i + 2]);
+        amax = fmaxf(amax, fmaxf(fabsf(px), fmaxf(fabsf(py), fabsf(pz))));
+        const int c = cell_wrap(G, px, py, pz);
+        wrapped[i] = make_float4(px, py, pz, __int_as_float(c));
         atomrank[i] = atomicAdd(&cellcnt[c], 1);
     }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, d));
+    // non-negative floats order like their bit patterns
+    if ((threadIdx.x & 31) == 0 && amax > 0.f) atomicMax(&misc[2], __float_as_int(amax));
 }
 
 __global__ void __launch_bounds__(1024) kl_scan(const GridS* __restrict__ grid, int n,
@@ -253,42 +282,58 @@ __global__ void __launch_bounds__(1024) kl_scan(const GridS* __restrict__ grid, 
     if (tid == 0) cellptr[ncell] = n;
 }
 
-__global__ void __launch_bounds__(256) kl_scatter(const float* __restrict__ x, int n,
-                                                  const int* __restrict__ cellptr,
-                                                  const int* __restrict__ atomcell,
+__global__ void __launch_bounds__(256) kl_scatter(int n, const int* __restrict__ cellptr,
+                                                  const float4* __restrict__ wrapped,
                                                   const int* __restrict__ atomrank,
                                                   const int2* __restrict__ meta,
-                                                  float4* __restrict__ sorted, int* __restrict__ sidx)
+                                                  float4* __restrict__ sorted, float* __restrict__ sorted_ekey)
 {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int pos = cellptr[atomcell[i]] + atomrank[i];
-        sorted[pos] = make_float4(__ldg(&x[3 * (size_t)i]), __ldg(&x[3 * (size_t)i + 1]),
-                                  __ldg(&x[3 * (size_t)i + 2]), (float)__ldg(&meta[i]).x);
-        sidx[pos] = i;
+        const float4 w = wrapped[i];
+        const int pos = cellptr[__float_as_int(w.w)] + atomrank[i];
+        const int2 mw = __ldg(&meta[i]);
+        const unsigned bits = (unsigned)i | ((unsigned)mw.y & (3u << 30));
+        sorted[pos] = make_float4(w.x, w.y, w.z, __uint_as_float(bits));
+        sorted_ekey[pos] = (float)mw.x;          // keys are < 2^24 (checked on the host): exact
     }
 }
 
 template <int FLAGS>
 __global__ void __launch_bounds__(LG_PAIR_THREADS, 4) kl_pairs(PairParams pp, StampSink sink_in,
-                                                               const float* __restrict__ box9,
+                                                               const float* __restrict__ box9, float cutoff,
                                                                const GridS* __restrict__ grid,
                                                                const float4* __restrict__ sorted,
-                                                               const int* __restrict__ sidx,
+                                                               const float* __restrict__ sorted_ekey,
                                                                const int* __restrict__ cellptr,
                                                                const int* __restrict__ occ, int* misc)
 {
-    __shared__ int cand_all[(LG_PAIR_THREADS / 32) * CT_CAND];
-    __shared__ uint2 hitq_all[(LG_PAIR_THREADS / 32) * CT_HITQ];
+    __shared__ unsigned int cand_all[(LG_PAIR_THREADS / 32) * CT_CAND];
+    __shared__ uint4 hitq_all[(LG_PAIR_THREADS / 32) * CT_QCAP];
+    __shared__ unsigned int qcnt_all[LG_PAIR_THREADS / 32];
+    __shared__ float4 shift_s[27];
+    __shared__ float thresh_s[2];
+    __shared__ GridS G;
     const int warp = threadIdx.x >> 5;
-    const GridS G = *grid;
-    const NlBox B = make_nlbox(box9);
+    if (threadIdx.x == 64) G = *grid;
+    __syncthreads();
+    if (threadIdx.x < 27) shift_s[threadIdx.x] = lattice_shift(box9, threadIdx.x);
+    if (threadIdx.x == 32) {
+        float lo, hi;
+        frame_margins(box9, G.distinct, (double)__int_as_float(misc[2]), pp.c2, (double)cutoff, pp.boundary_ulps,
+                      lo, hi);
+        thresh_s[0] = lo; thresh_s[1] = hi;
+    }
+    if ((threadIdx.x & 31) == 0) qcnt_all[warp] = 0u;
+    __syncthreads();
+    pp.c2_lo = thresh_s[0]; pp.c2_hi = thresh_s[1];
     PairCtx<LargeTraits> cx;
-    cx.sorted = sorted; cx.sidx = sidx; cx.cellptr = cellptr;
-    cx.cand = cand_all + warp * CT_CAND; cx.hitq = hitq_all + warp * CT_HITQ;
+    cx.sorted = sorted; cx.ekey = sorted_ekey; cx.cellptr = cellptr;
+    cx.cand = cand_all + warp * CT_CAND; cx.hitq = hitq_all + warp * CT_QCAP;
+    cx.qcnt = qcnt_all + warp; cx.shift = shift_s;
     unsigned long long n_tests = 0;
     StampSink sink = sink_in;
     sink.pending = 0; sink.pend_old = 0u; sink.pend_lo = sink.pend_hi = 0u;
-    ct_pair_phase_dyn<LargeTraits, StampSink, FLAGS, int>(pp, B, G, cx, sink, occ, misc[0], &misc[1], n_tests);
+    ct_pair_phase_dyn<LargeTraits, StampSink, FLAGS, int>(pp, G, cx, sink, occ, misc[0], &misc[1], n_tests);
     sink.resolve();
     if (FLAGS & CT_COUNT) {
 #pragma unroll
@@ -311,12 +356,12 @@ inline int large_run(const LargeJob& job, LargeScratch& S, int sm_count, cudaStr
 {
     const int n = job.n;
     if (S.cap_atoms < n) {
-        cudaFree(S.d_atomcell); cudaFree(S.d_atomrank); cudaFree(S.d_sorted); cudaFree(S.d_sidx);
-        S.d_atomcell = S.d_atomrank = S.d_sidx = nullptr; S.d_sorted = nullptr;
-        LG_CK(cudaMalloc(&S.d_atomcell, sizeof(int) * (size_t)n));
+        cudaFree(S.d_wrapped); cudaFree(S.d_atomrank); cudaFree(S.d_sorted); cudaFree(S.d_sorted_ekey);
+        S.d_atomrank = nullptr; S.d_sorted = nullptr; S.d_wrapped = nullptr; S.d_sorted_ekey = nullptr;
+        LG_CK(cudaMalloc(&S.d_sorted_ekey, sizeof(float) * (size_t)n));
+        LG_CK(cudaMalloc(&S.d_wrapped, sizeof(float4) * (size_t)n));
         LG_CK(cudaMalloc(&S.d_atomrank, sizeof(int) * (size_t)n));
         LG_CK(cudaMalloc(&S.d_sorted, sizeof(float4) * (size_t)n));
-        LG_CK(cudaMalloc(&S.d_sidx, sizeof(int) * (size_t)n));
         S.cap_atoms = n;
     }
     if (!S.d_grid) {
@@ -352,39 +397,39 @@ inline int large_run(const LargeJob& job, LargeScratch& S, int sm_count, cudaStr
             S.seq++;
         }
         kl_prepare<<<1, 1024, 0, stream>>>(x, n, box9, job.cutoff, S.d_grid, S.d_cellcnt, S.d_misc);
-        kl_bin<<<atom_blocks, 256, 0, stream>>>(x, n, S.d_grid, S.d_cellcnt, S.d_atomcell, S.d_atomrank);
+        kl_bin<<<atom_blocks, 256, 0, stream>>>(x, n, S.d_grid, S.d_cellcnt, S.d_wrapped, S.d_atomrank, S.d_misc);
         kl_scan<<<1, 1024, 0, stream>>>(S.d_grid, n, S.d_cellcnt, S.d_cellptr, S.d_occ, S.d_misc);
-        kl_scatter<<<atom_blocks, 256, 0, stream>>>(x, n, S.d_cellptr, S.d_atomcell, S.d_atomrank, job.meta,
-                                                    S.d_sorted, S.d_sidx);
+        kl_scatter<<<atom_blocks, 256, 0, stream>>>(n, S.d_cellptr, S.d_wrapped, S.d_atomrank, job.meta, S.d_sorted,
+                                                    S.d_sorted_ekey);
         PairParams pp;
-        pp.n = n; pp.n_ignored_f = (float)job.n_ignored; pp.meta = job.meta; pp.c2 = job.c2; pp.c2_hi = job.c2_hi;
-        pp.boundary_ulps = job.boundary_ulps; pp.atom_table = job.atom_table; pp.atom_keys = job.atom_keys;
-        pp.atom_cap = job.atom_cap; pp.counters = job.counters; pp.boundary = job.boundary;
-        pp.boundary_cap = job.boundary_cap; pp.frame_id = job.frame0 + f;
+        pp.n = n; pp.n_ignored = job.n_ignored; pp.c2 = job.c2; pp.c2_lo = pp.c2_hi = job.c2;
+        pp.boundary_ulps = job.boundary_ulps; pp.xyz_frame = x; pp.box9 = box9;
+        pp.atom_keys = job.atom_keys; pp.atom_cap = job.atom_cap; pp.counters = job.counters;
+        pp.boundary = job.boundary; pp.boundary_cap = job.boundary_cap; pp.frame_id = job.frame0 + f;
         StampSink sink;
-        sink.sidx = S.d_sidx; sink.meta = job.meta; sink.atom_table = job.atom_table;
+        sink.meta = job.meta; sink.atom_table = job.atom_table;
         sink.stamp = want_res ? S.d_stamp : nullptr;
         sink.res_table = job.res_table; sink.res_keys = job.res_keys; sink.res_cap = job.res_cap;
         sink.counters = job.counters; sink.seq = S.seq; sink.n = (unsigned)n;
         sink.n_res_c = (unsigned)job.n_res_c; sink.frame_id = job.frame0 + f;
-        sink.pending = 0; sink.pend_old = 0u; sink.pend_lo = sink.pend_hi = 0u;
+        sink.pending = 0; sink.pend_old = 0u; sink.pend_lo = sink.pend_hi = 0u; sink.ra = sink.rb = 0;
         const int pg = sm_count * 4;
         const bool emit = job.atom_keys != nullptr;
         if (job.boundary_ulps > 0)
             kl_pairs<CT_BOUNDARY | CT_ROLES><<<pg, LG_PAIR_THREADS, 0, stream>>>(
-                pp, sink, box9, S.d_grid, S.d_sorted, S.d_sidx, S.d_cellptr, S.d_occ, S.d_misc);
+                pp, sink, box9, job.cutoff, S.d_grid, S.d_sorted, S.d_sorted_ekey, S.d_cellptr, S.d_occ, S.d_misc);
         else if (job.count_tests && !emit)
             kl_pairs<CT_COUNT | CT_ROLES><<<pg, LG_PAIR_THREADS, 0, stream>>>(
-                pp, sink, box9, S.d_grid, S.d_sorted, S.d_sidx, S.d_cellptr, S.d_occ, S.d_misc);
+                pp, sink, box9, job.cutoff, S.d_grid, S.d_sorted, S.d_sorted_ekey, S.d_cellptr, S.d_occ, S.d_misc);
         else if (emit)
             kl_pairs<CT_EMIT | CT_ROLES><<<pg, LG_PAIR_THREADS, 0, stream>>>(
-                pp, sink, box9, S.d_grid, S.d_sorted, S.d_sidx, S.d_cellptr, S.d_occ, S.d_misc);
+                pp, sink, box9, job.cutoff, S.d_grid, S.d_sorted, S.d_sorted_ekey, S.d_cellptr, S.d_occ, S.d_misc);
         else if (job.all_roles)
             kl_pairs<0><<<pg, LG_PAIR_THREADS, 0, stream>>>(
-                pp, sink, box9, S.d_grid, S.d_sorted, S.d_sidx, S.d_cellptr, S.d_occ, S.d_misc);
+                pp, sink, box9, job.cutoff, S.d_grid, S.d_sorted, S.d_sorted_ekey, S.d_cellptr, S.d_occ, S.d_misc);
         else
             kl_pairs<CT_ROLES><<<pg, LG_PAIR_THREADS, 0, stream>>>(
-                pp, sink, box9, S.d_grid, S.d_sorted, S.d_sidx, S.d_cellptr, S.d_occ, S.d_misc);
+                pp, sink, box9, job.cutoff, S.d_grid, S.d_sorted, S.d_sorted_ekey, S.d_cellptr, S.d_occ, S.d_misc);
         launches += 5;
     }
     LG_CK(cudaGetLastError());

@@ -14,12 +14,13 @@
 //      has consumed the buffer, so it overlaps the pair phase;
 //   2. atoms are binned into >= cutoff-wide cells of the (orthorhombic / triclinic /
 //      open) cell grid: u16 shared-memory histogram, block scan, scatter into a
-//      cell-sorted float4 array {x, y, z, exclusion key} (+ u16 atom index);
+//      cell-sorted float4 array {wrapped x, y, z, atom index | role << 30};
 //   3. one warp per occupied cell: the candidate atoms of the half shell
-//      (neighbour cells with id >= own) are held in registers (4 per lane), the
-//      cell's own atoms are broadcast from shared memory, and every candidate pair
-//      is adjudicated with MDTraj's exact float32 arithmetic on the RAW
-//      coordinates (cmb_math.cuh);
+//      (neighbour cells with id >= own) are held in registers (3 per lane), the
+//      cell's own atoms are broadcast from shared memory, every candidate pair is
+//      SCREENED with an FMA distance on the wrapped coordinates, and the few pairs the
+//      per-frame error bound cannot decide are adjudicated with MDTraj's exact float32
+//      arithmetic on the RAW coordinates (cmb_cells.cuh, cmb_math.cuh);
 //   4. hits that pass the role + residue-exclusion tests are (a) RED-added into the
 //      dense uint32 atom-pair table, (b) OR'd into a per-frame residue-pair bitmap
 //      in shared memory that is popcount-flushed into the residue table at frame
@@ -34,12 +35,15 @@ constexpr int FS_THREADS = 512;
 constexpr int FS_WARPS = FS_THREADS / 32;
 constexpr int FS_APT = 12;                          // atoms per thread in the binning passes
 constexpr int FS_MAX_ATOMS = FS_THREADS * FS_APT;   // 6144
-constexpr int FS_HEADER_BYTES = 1024;
+constexpr int FS_HEADER_BYTES = 2048;
 constexpr int FS_CAND = CT_CAND;
-constexpr int FS_HITQ = CT_HITQ;
+constexpr int FS_QCAP = CT_QCAP;
+// header layout (bytes): mbarrier 0, task counter 8, occupied cells 12, thresholds 16/20,
+// ring counters 32, per-warp max|coordinate| 96, reduction scratch 256, grid 1024, shifts 1536
+constexpr int FS_H_QCNT = 32, FS_H_AMAX = 96, FS_H_RED = 256, FS_H_GRID = 1024, FS_H_SHIFT = 1536;
 
-// packed per-atom meta word: ekey [0,17) | compact residue [17,30) | role [30,32)
-constexpr unsigned FS_EKEY_BITS = 17;
+// packed per-atom meta word: ekey [0,16) | compact residue [16,29) | role [30,32)
+constexpr unsigned FS_EKEY_BITS = 16;
 constexpr unsigned FS_EKEY_MASK = (1u << FS_EKEY_BITS) - 1u;
 constexpr unsigned FS_RES_MASK = (1u << 13) - 1u;
 
@@ -58,7 +62,6 @@ struct FrameParams {
     const unsigned int* meta32;  // [n] packed meta words
     float cutoff;
     float c2;                    // cutoff_f * cutoff_f
-    float c2_hi;                 // c2 advanced by `boundary_ulps` float steps
     int boundary_ulps;
     int n_ignored;
     int n_res_c;                 // compact residue count (bitmap is n_res_c x n_res_c bits)
@@ -120,7 +123,7 @@ __device__ __forceinline__ void fence_proxy_async()
 
 // ----- shared-memory layout ------------------------------------------------------
 struct FsLayout {
-    int raw_off, sorted_off, sidx_off, cell_off, occ_off, bm_off, cand_off, hitq_off, total;
+    int raw_off, sorted_off, cell_off, occ_off, bm_off, cand_off, hitq_off, total;
 };
 
 __host__ __device__ inline int fs_align(int x, int a) { return (x + a - 1) / a * a; }
@@ -133,8 +136,6 @@ __host__ __device__ inline FsLayout fs_layout(int n, int maxc, int bm_words_smem
     off += fs_align(12 * n + 32, 128);
     L.sorted_off = off;
     off += fs_align(16 * n, 128);
-    L.sidx_off = off;
-    off += fs_align(2 * n, 128);
     L.cell_off = off;
     off += fs_align(2 * (maxc + 2), 128);
     L.occ_off = off;
@@ -144,7 +145,7 @@ __host__ __device__ inline FsLayout fs_layout(int n, int maxc, int bm_words_smem
     L.cand_off = off;
     off += FS_WARPS * FS_CAND * 2;
     L.hitq_off = off;
-    off += FS_WARPS * FS_HITQ * 4;
+    off += FS_WARPS * FS_QCAP * 8;
     L.total = off;
     return L;
 }
@@ -152,17 +153,38 @@ __host__ __device__ inline FsLayout fs_layout(int n, int maxc, int bm_words_smem
 // ----- traits + hit sink of the fused path ------------------------------------------
 struct SmallTraits {
     typedef unsigned short pos_t;
-    typedef unsigned int hit_t;                     // ipos | jpos << 16
-    static __device__ __forceinline__ unsigned role(const void* meta, int atom)
+    typedef unsigned short cand_t;                  // sorted position [0,13) | wrap flags [13,16)
+    typedef uint2 hit_t;          // {own base [0,13) | jpos [13,26) | shift id [26,31), own-atom mask}
+    static __device__ __forceinline__ cand_t cand(int pos, int wrap)
     {
-        return __ldg(reinterpret_cast<const unsigned int*>(meta) + atom) >> 30;
+        return (cand_t)((unsigned)pos | ((unsigned)wrap << 13));
     }
-    static __device__ __forceinline__ hit_t pack(int ipos, int jpos)
+    static __device__ __forceinline__ int cand_pos(cand_t e) { return (int)(e & 0x1fffu); }
+    static __device__ __forceinline__ int cand_wrap(cand_t e) { return (int)(e >> 13); }
+    static __device__ __forceinline__ unsigned jp(int jpos, int id)
     {
-        return (unsigned)ipos | ((unsigned)jpos << 16);
+        return ((unsigned)jpos << 13) | ((unsigned)id << 26);
     }
-    static __device__ __forceinline__ int ipos(hit_t e) { return (int)(e & 0xffffu); }
-    static __device__ __forceinline__ int jpos(hit_t e) { return (int)(e >> 16); }
+    static __device__ __forceinline__ hit_t entry(int ibase, unsigned jp, unsigned mask)
+    {
+        return make_uint2((unsigned)ibase | jp, mask);
+    }
+    static __device__ __forceinline__ hit_t with_mask(hit_t e, unsigned mask) { return make_uint2(e.x, mask); }
+    static __device__ __forceinline__ int e_ibase(hit_t e) { return (int)(e.x & 0x1fffu); }
+    static __device__ __forceinline__ int e_jpos(hit_t e) { return (int)((e.x >> 13) & 0x1fffu); }
+    static __device__ __forceinline__ int e_id(hit_t e) { return (int)(e.x >> 26); }
+    static __device__ __forceinline__ unsigned e_mask(hit_t e) { return e.y; }
+    // sorted[].w bits: atom index [0,13) | role [14,16) | exclusion key [16,32)
+    static __device__ __forceinline__ unsigned bits(int atom, unsigned role, unsigned ekey)
+    {
+        return (unsigned)atom | (role << 14) | (ekey << 16);
+    }
+    static __device__ __forceinline__ int atom(unsigned bits) { return (int)(bits & 0x1fffu); }
+    static __device__ __forceinline__ unsigned role(unsigned bits) { return (bits >> 14) & 3u; }
+    static __device__ __forceinline__ float ekey_f(const PairCtx<SmallTraits>&, int, unsigned bits)
+    {
+        return (float)(bits >> 16);
+    }
     static __device__ __forceinline__ void decode(int c, const GridS& G, int& cx, int& cy, int& cz)
     {
         const int cyz = (int)__umulhi((unsigned)c << 6, G.magic_x);     // c < 2^16
@@ -172,22 +194,24 @@ struct SmallTraits {
     }
 };
 
-// Account one hit (sorted positions ipos < jpos): RED into the atom-pair table, test-then-OR
-// into the per-frame residue-pair bitmap (shared or global), flushed at frame end.
+// Residue exclusion + accounting of one hit: RED into the atom-pair table, test-then-OR into the
+// per-frame residue-pair bitmap (shared or global), flushed at frame end.
 struct BitmapSink {
     const unsigned int* meta32;
-    const unsigned short* sidx;
     unsigned int* atom_table;
     unsigned int* bitmap;
     unsigned n;
     unsigned n_res_c;
-    __device__ __forceinline__ void account(int ipos, int jpos)
+    unsigned ra, rb;          // compact residues of the pair handed to prepare()
+    __device__ __forceinline__ void prepare(int ia, int ib)
     {
-        const int ia = sidx[ipos], ib = sidx[jpos];
+        ra = (__ldg(&meta32[ia]) >> FS_EKEY_BITS) & FS_RES_MASK;
+        rb = (__ldg(&meta32[ib]) >> FS_EKEY_BITS) & FS_RES_MASK;
+    }
+    __device__ __forceinline__ void account(int ia, int ib)
+    {
         const int a = min(ia, ib), b = max(ia, ib);
         if (atom_table != nullptr) atomicAdd(&atom_table[(size_t)a * (size_t)n + (size_t)b], 1u);
-        const unsigned mi = __ldg(&meta32[ia]), mj = __ldg(&meta32[ib]);
-        const unsigned ra = (mi >> FS_EKEY_BITS) & FS_RES_MASK, rb = (mj >> FS_EKEY_BITS) & FS_RES_MASK;
         const unsigned bit = min(ra, rb) * n_res_c + max(ra, rb);
         const unsigned msk = 1u << (bit & 31);
         unsigned int* wp = &bitmap[bit >> 5];
@@ -211,24 +235,29 @@ __global__ void __launch_bounds__(FS_THREADS, FS_MIN_CTAS) k_frames_small(const 
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem);
     int* task_counter = reinterpret_cast<int*>(smem + 8);
     int* n_occ_s = reinterpret_cast<int*>(smem + 12);
-    float* red = reinterpret_cast<float*>(smem + 64);                    // 6 * 32 floats
-    unsigned int* scan_s = reinterpret_cast<unsigned int*>(smem + 64);   // overlays `red`
-    GridS* Gs = reinterpret_cast<GridS*>(smem + 64 + 6 * 32 * 4);
+    float* thresh_s = reinterpret_cast<float*>(smem + 16);                 // {c2_lo, c2_hi} of the frame
+    unsigned int* qcnt = reinterpret_cast<unsigned int*>(smem + FS_H_QCNT) + warp;
+    float* amax_s = reinterpret_cast<float*>(smem + FS_H_AMAX);
+    float* red = reinterpret_cast<float*>(smem + FS_H_RED);                // 6 * 32 floats
+    unsigned int* scan_s = reinterpret_cast<unsigned int*>(smem + FS_H_RED);   // overlays `red`
+    GridS* Gs = reinterpret_cast<GridS*>(smem + FS_H_GRID);
+    float4* shift_s = reinterpret_cast<float4*>(smem + FS_H_SHIFT);        // [27]
+    static_assert(sizeof(GridS) <= FS_H_SHIFT - FS_H_GRID, "grid does not fit its header slot");
     unsigned char* raw = smem + L.raw_off;
     float4* sorted = reinterpret_cast<float4*>(smem + L.sorted_off);
-    unsigned short* sidx = reinterpret_cast<unsigned short*>(smem + L.sidx_off);
     unsigned int* cell32 = reinterpret_cast<unsigned int*>(smem + L.cell_off);
     unsigned short* cell16 = reinterpret_cast<unsigned short*>(smem + L.cell_off);
     unsigned short* occ = reinterpret_cast<unsigned short*>(smem + L.occ_off);
     unsigned int* bitmap = p.bm_in_smem ? reinterpret_cast<unsigned int*>(smem + L.bm_off)
                                         : p.g_bitmap + (size_t)blockIdx.x * (size_t)p.bm_words;
     unsigned short* cand = reinterpret_cast<unsigned short*>(smem + L.cand_off) + warp * FS_CAND;
-    unsigned int* hitq = reinterpret_cast<unsigned int*>(smem + L.hitq_off) + warp * FS_HITQ;
+    uint2* hitq = reinterpret_cast<uint2*>(smem + L.hitq_off) + warp * FS_QCAP;
 
     if (tid == 0) {
         mbar_init(mbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (lane == 0) *qcnt = 0u;
     for (int w = tid; w < p.bm_words; w += FS_THREADS) bitmap[w] = 0u;
     __syncthreads();
 
@@ -249,9 +278,8 @@ __global__ void __launch_bounds__(FS_THREADS, FS_MIN_CTAS) k_frames_small(const 
 
     for (; f < p.n_frames; f += stride) {
         const float* box9 = p.box ? p.box + (size_t)f * 9 : nullptr;
-        const NlBox B = make_nlbox(box9);
         const unsigned long long addr = (unsigned long long)(p.xyz + (size_t)f * (size_t)n * 3);
-        const float* xr = reinterpret_cast<const float*>(raw + (addr & 15ull));
+        float* xr = reinterpret_cast<float*>(raw + (addr & 15ull));
 
         mbar_wait(mbar, parity);
         parity ^= 1u;
@@ -295,25 +323,42 @@ __global__ void __launch_bounds__(FS_THREADS, FS_MIN_CTAS) k_frames_small(const 
             *task_counter = 0;
         }
         __syncthreads();
-        const GridS G = *Gs;
+        const GridS& G = *Gs;      // constant until the next frame (shared memory)
 
-        // ---- pass A: histogram (u16 counters packed in u32 words) -----------------
+        // ---- pass A: histogram (u16 counters packed in u32 words); on periodic grids the raw
+        //      buffer is overwritten with the wrapped positions ----------------------------
         for (int w = tid; w < (G.ncell + 3) / 2; w += FS_THREADS) cell32[w] = 0u;
         __syncthreads();
-        int my_cell[FS_APT], my_rank[FS_APT];
+        unsigned my_cr[FS_APT];              // cell | rank << 16 of this thread's atoms
+        float amax = 0.f;
 #pragma unroll
         for (int k = 0; k < FS_APT; k++) {
             const int i = tid + k * FS_THREADS;
-            my_cell[k] = -1; my_rank[k] = 0;
+            my_cr[k] = 0u;
             if (i < n) {
-                const int c = cell_of(G, xr[3 * i], xr[3 * i + 1], xr[3 * i + 2]);
+                float x = xr[3 * i], y = xr[3 * i + 1], z = xr[3 * i + 2];
+                amax = fmaxf(amax, fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z))));
+                const int c = cell_wrap(G, x, y, z);
+                if (G.periodic) { xr[3 * i] = x; xr[3 * i + 1] = y; xr[3 * i + 2] = z; }
                 const unsigned sh = (c & 1) * 16;
                 const unsigned old = atomicAdd(&cell32[c >> 1], 1u << sh);
-                my_cell[k] = c;
-                my_rank[k] = (int)((old >> sh) & 0xffffu);
+                my_cr[k] = (unsigned)c | (((old >> sh) & 0xffffu) << 16);
             }
         }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, d));
+        if (lane == 0) amax_s[warp] = amax;
         __syncthreads();
+
+        // screening thresholds and lattice shifts of the frame (idle lanes of the scan below)
+        if (tid == 32) {
+            float A = 0.f;
+            for (int w = 0; w < FS_WARPS; w++) A = fmaxf(A, amax_s[w]);
+            float c2_lo, c2_hi;
+            frame_margins(box9, G.distinct, (double)A, p.c2, (double)p.cutoff, p.boundary_ulps, c2_lo, c2_hi);
+            thresh_s[0] = c2_lo; thresh_s[1] = c2_hi;
+        }
+        if (tid >= 64 && tid < 64 + 27) shift_s[tid - 64] = lattice_shift(box9, tid - 64);
 
         // ---- pass B: exclusive scan over cells (+ occupied-cell list) --------------
         {
@@ -359,15 +404,15 @@ __global__ void __launch_bounds__(FS_THREADS, FS_MIN_CTAS) k_frames_small(const 
         }
         __syncthreads();
 
-        // ---- pass C: scatter into the cell-sorted arrays ------------------------------
+        // ---- pass C: scatter into the cell-sorted array -------------------------------
 #pragma unroll
         for (int k = 0; k < FS_APT; k++) {
             const int i = tid + k * FS_THREADS;
             if (i < n) {
-                const int pos = (int)cell16[my_cell[k]] + my_rank[k];
+                const int pos = (int)cell16[my_cr[k] & 0xffffu] + (int)(my_cr[k] >> 16);
+                const unsigned mw = __ldg(&p.meta32[i]);
                 sorted[pos] = make_float4(xr[3 * i], xr[3 * i + 1], xr[3 * i + 2],
-                                          (float)(__ldg(&p.meta32[i]) & FS_EKEY_MASK));
-                sidx[pos] = (unsigned short)i;
+                                          __uint_as_float(SmallTraits::bits(i, mw >> 30, mw & FS_EKEY_MASK)));
             }
         }
         __syncthreads();
@@ -380,14 +425,15 @@ __global__ void __launch_bounds__(FS_THREADS, FS_MIN_CTAS) k_frames_small(const 
         // ---- pass D: pair phase, one warp per occupied cell ---------------------------
         const long long frame_id = p.frame0 + f;
         PairParams pp;
-        pp.n = n; pp.n_ignored_f = (float)p.n_ignored; pp.meta = p.meta32; pp.c2 = p.c2; pp.c2_hi = p.c2_hi;
-        pp.boundary_ulps = p.boundary_ulps; pp.atom_table = p.atom_table; pp.atom_keys = p.atom_keys;
-        pp.atom_cap = p.atom_cap; pp.counters = p.counters; pp.boundary = p.boundary;
-        pp.boundary_cap = p.boundary_cap; pp.frame_id = frame_id;
+        pp.n = n; pp.n_ignored = p.n_ignored; pp.c2 = p.c2; pp.c2_lo = thresh_s[0]; pp.c2_hi = thresh_s[1];
+        pp.boundary_ulps = p.boundary_ulps; pp.xyz_frame = p.xyz + (size_t)f * (size_t)n * 3; pp.box9 = box9;
+        pp.atom_keys = p.atom_keys; pp.atom_cap = p.atom_cap; pp.counters = p.counters;
+        pp.boundary = p.boundary; pp.boundary_cap = p.boundary_cap; pp.frame_id = frame_id;
         PairCtx<SmallTraits> cx;
-        cx.sorted = sorted; cx.sidx = sidx; cx.cellptr = cell16; cx.cand = cand; cx.hitq = hitq;
-        BitmapSink sink{p.meta32, sidx, p.atom_table, bitmap, (unsigned)n, (unsigned)p.n_res_c};
-        ct_pair_phase_dyn<SmallTraits, BitmapSink, FLAGS, unsigned short>(pp, B, G, cx, sink, occ, *n_occ_s,
+        cx.sorted = sorted; cx.cellptr = cell16; cx.cand = cand; cx.hitq = hitq; cx.qcnt = qcnt;
+        cx.shift = shift_s; cx.ekey = nullptr;
+        BitmapSink sink{p.meta32, p.atom_table, bitmap, (unsigned)n, (unsigned)p.n_res_c, 0u, 0u};
+        ct_pair_phase_dyn<SmallTraits, BitmapSink, FLAGS, unsigned short>(pp, G, cx, sink, occ, *n_occ_s,
                                                                           task_counter, n_tests);
         __syncthreads();
 
