@@ -173,7 +173,7 @@ extern "C" int cmb_set_option(cmb_ctx* ctx, const char* name, int64_t value)
     if (!ctx || !name) return CMB_ERR_ARG;
     if (!strcmp(name, "count_tests")) { ctx->count_tests = value != 0; return CMB_OK; }
     if (!strcmp(name, "max_cells")) {
-        if (value < 8 || value > 32768) return fail(ctx, CMB_ERR_ARG, "max_cells out of range");
+        if (value < 8 || value > 16383) return fail(ctx, CMB_ERR_ARG, "max_cells out of range");
         ctx->fs_maxc = (int)value;
         return CMB_OK;
     }

@@ -130,6 +130,16 @@ __device__ __forceinline__ int cell_wrap(const GridS& G, float& x, float& y, flo
 }
 
 
+// interior cell: no periodic wrap and no grid edge anywhere in its 27-cell stencil
+__device__ __forceinline__ bool cell_interior(const GridS& G, int cx, int cy, int cz)
+{
+    return (cx >= 1) && (cx <= G.nx - 2) && (cy >= 1) && (cy <= G.ny - 2) && (cz >= 1) && (cz <= G.nz - 2);
+}
+
+// two x-adjacent occupied interior cells are merged into one task when they are sparsely
+// populated (their candidate set, ~19 cells, then still fits the register-resident slots)
+constexpr int CT_PAIR_MAX_OWN = 13;
+
 // =================================================================================
 // Pair phase shared by both paths.
 //
@@ -153,7 +163,7 @@ __device__ __forceinline__ int cell_wrap(const GridS& G, float& x, float& y, flo
 // entries, ring entries); a `Sink` object owns the per-atom meta words and accounts one hit
 // (atom table, per-frame residue de-duplication).
 // =================================================================================
-constexpr int CT_KSLOT = 3;                 // register-resident candidates per lane
+constexpr int CT_KSLOT = 4;                 // register-resident candidates per lane
 constexpr int CT_CAND = 32 * CT_KSLOT;      // candidates per chunk
 constexpr int CT_QCAP = 64;                 // per-warp ring of screened (candidate, own-atom mask) entries
 constexpr int CT_NOSHIFT = 13;              // shift id of "no lattice shift"
@@ -190,7 +200,6 @@ struct PairCtx {
     const typename Traits::pos_t* cellptr;      // [ncell + 1]
     typename Traits::cand_t* cand;              // this warp's candidate list [CT_CAND]
     typename Traits::hit_t* hitq;               // this warp's ring [CT_QCAP]
-    unsigned int* qcnt;                         // this warp's ring write counter (shared memory)
     const float4* shift;                        // [27] lattice shift of each wrap combination
 };
 
@@ -201,15 +210,19 @@ __device__ __forceinline__ float d2_screen(float xi, float yi, float zi, float x
     return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
 }
 
-// ring slot reservation: one ATOMS per pushing lane (opaque to the compiler's warp aggregation)
-__device__ __forceinline__ unsigned ring_reserve(unsigned int* qcnt)
+// Per-warp ring of screened entries: head / tail live in (warp-uniform) registers, pushes are
+// warp-aggregated with one ballot (no atomics, no shared counter).
+struct Ring {
+    unsigned head, tail;
+};
+
+template <typename Traits>
+__device__ __forceinline__ void ring_push(const PairCtx<Traits>& cx, Ring& ring, unsigned ltmask, bool want,
+                                          const typename Traits::hit_t& e)
 {
-    unsigned old;
-    asm volatile("atom.shared.add.u32 %0, [%1], 1;"
-                 : "=r"(old)
-                 : "r"((unsigned)__cvta_generic_to_shared(qcnt))
-                 : "memory");
-    return old;
+    const unsigned nz = __ballot_sync(0xffffffffu, want);
+    if (want) cx.hitq[(ring.tail + __popc(nz & ltmask)) & (CT_QCAP - 1)] = e;
+    ring.tail += __popc(nz);
 }
 
 // Per-frame thresholds.  A = max |raw coordinate| of the frame, box9 = unit cell rows or nullptr.
@@ -247,8 +260,9 @@ __device__ inline void frame_margins(const float* box9, int distinct, double A, 
     const double M = 2.0 * bound;
     ok = ok && (M < 0.25 * (double)c2);
     if (!ok) {
-        c2_lo = -3.0e38f;
-        c2_hi = 3.0e38f;
+        // adjudicate everything exactly; still below CT_FAR^2, so that empty slots never pass
+        c2_lo = -1.0e30f;
+        c2_hi = 1.0e30f;
         return;
     }
     c2_lo = __double2float_rd((double)c2 - M);
@@ -341,33 +355,22 @@ __device__ __forceinline__ void ct_account(const PairParams& p, const PairCtx<Tr
 // Pop up to 32 ring entries (one per lane); an entry is (own-atom base, candidate, mask of own
 // atoms): the lane accounts the lowest own atom of its mask and pushes the rest back.
 template <typename Traits, typename Sink, int MODE, int FLAGS>
-__device__ __forceinline__ void ct_drain(const PairParams& p, const PairCtx<Traits>& cx, Sink& sink,
-                                         unsigned& head, unsigned left)
+__device__ __forceinline__ void ct_drain(const PairParams& p, const PairCtx<Traits>& cx, Sink& sink, Ring& ring,
+                                         unsigned ltmask)
 {
     const int lane = threadIdx.x & 31;
+    const unsigned left = ring.tail - ring.head;
     const bool active = (unsigned)lane < left;
-    const typename Traits::hit_t e = cx.hitq[(head + (active ? lane : 0)) & (CT_QCAP - 1)];
-    head += left < 32u ? left : 32u;
+    __syncwarp();
+    const typename Traits::hit_t e = cx.hitq[(ring.head + (active ? lane : 0)) & (CT_QCAP - 1)];
+    ring.head += left < 32u ? left : 32u;
     const unsigned m = Traits::e_mask(e);
     const int bit = __ffs(m) - 1;
     const unsigned rest = m & (m - 1u);
     __syncwarp();
-    if (active && rest) cx.hitq[ring_reserve(cx.qcnt) & (CT_QCAP - 1)] = Traits::with_mask(e, rest);
+    ring_push<Traits>(cx, ring, ltmask, active && rest != 0u, Traits::with_mask(e, rest));
     ct_account<Traits, Sink, MODE, FLAGS>(p, cx, sink, Traits::e_ibase(e) + bit, Traits::e_jpos(e),
                                           Traits::e_id(e), active);
-}
-
-// drain while more than `keep` entries are waiting (keep = 31: full batches only; 0: everything)
-template <typename Traits, typename Sink, int MODE, int FLAGS>
-__device__ __forceinline__ void ct_drain_while(const PairParams& p, const PairCtx<Traits>& cx, Sink& sink,
-                                               unsigned& head, unsigned keep)
-{
-    for (;;) {
-        __syncwarp();
-        const unsigned left = *(volatile unsigned int*)cx.qcnt - head;
-        if (left <= keep) break;
-        ct_drain<Traits, Sink, MODE, FLAGS>(p, cx, sink, head, left);
-    }
 }
 
 // Screening loop: own atoms [g0, g1) (at most 32, highest first so that bit b of a mask is own
@@ -402,25 +405,31 @@ __device__ __forceinline__ void ct_screen(const PairCtx<Traits>& cx, int g0, int
     }
 }
 
-// One warp screens all candidate pairs of one occupied cell `c`.
+// One warp screens all candidate pairs of one task: an occupied cell `c`, or (TASK_PAIR) the two
+// x-adjacent interior cells c, c + 1 of a sparsely populated region (halves the per-task set-up
+// where a cell holds only a handful of atoms).
 //
 // Candidates are the atoms of the stencil cells with id >= c (every unordered cell pair is
-// visited once), own cell first.  Cells are numbered x-fastest, so for an INTERIOR cell (no
-// periodic wrap, no grid edge) they form five contiguous runs of the cell-sorted array:
-//     (cx..cx+1, cy, cz), (cx-1..cx+1, cy+1, cz), (cx-1..cx+1, cy-1..cy+1, cz+1)
-// and a candidate slot maps to its sorted position with four compares.  Edge cells take the
-// generic route: 27 stencil lanes (lane 0 = own cell), de-duplication (grids with < 3 cells
-// along a dimension), warp scan, per-warp candidate list whose entries carry the wrap flags of
-// their stencil cell (-> lattice shift added when the candidate is loaded).
+// visited once), own cell(s) first.  Cells are numbered x-fastest, so for an INTERIOR task (no
+// periodic wrap, no grid edge) they form five contiguous runs of the cell-sorted array
+//     (cx..cx+L, cy, cz), (cx-1..cx+L, cy+1, cz), (cx-1..cx+L, cy-1..cy+1, cz+1)       L = 1 or 2
+// and a candidate slot maps to its sorted position with four compares (for L = 2 the runs also
+// cover cells two columns away from one of the own cells: wasted but harmless tests).  Edge
+// cells take the generic route: 27 stencil lanes (lane 0 = own cell), de-duplication (grids with
+// < 3 cells along a dimension), warp scan, per-warp candidate list whose entries carry the wrap
+// flags of their stencil cell (-> lattice shift added when the candidate is loaded).
 // Own-cell candidates occupy the first slots in sorted order, so "each unordered pair once, no
 // self pair" is `slot > own index`, applied to the masks before they are pushed to the ring.
 template <typename Traits, typename Sink, int MODE, int FLAGS>
 __device__ __forceinline__ void ct_cell_task(const PairParams& p, const GridS& G, const PairCtx<Traits>& cx,
-                                             Sink& sink, int c, unsigned long long& n_tests, unsigned& head)
+                                             Sink& sink, unsigned task, unsigned long long& n_tests, Ring& ring)
 {
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
-    const int cstart = (int)cx.cellptr[c], cend = (int)cx.cellptr[c + 1];
+    const unsigned ltmask = (1u << lane) - 1u;
+    const int c = (int)(task & Traits::TASK_CMASK);
+    const int L = (task & Traits::TASK_PAIR) ? 2 : 1;
+    const int cstart = (int)cx.cellptr[c], cend = (int)cx.cellptr[c + L];
 
     for (int base = 0;; base += CT_CAND) {
         // ---- candidates of this chunk (everything is re-derived per chunk so that nothing of it
@@ -429,98 +438,94 @@ __device__ __forceinline__ void ct_cell_task(const PairParams& p, const GridS& G
         unsigned jp[CT_KSLOT];
         unsigned roles_or = 0u;
         int M;
-        {
+        if (task & Traits::TASK_INTERIOR) {
+            // run r covers slots [o_r, o_{r+1}) and sorted positions slot + a_r
+            const int nx = G.nx, nxy = G.nx * G.ny;
+            const int b1 = c + nx - 1, b2 = c + nxy - nx - 1, b3 = c + nxy - 1, b4 = c + nxy + nx - 1;
+            const int s0 = cstart, e0 = (int)cx.cellptr[c + 1 + L];
+            const int s1 = (int)cx.cellptr[b1], e1 = (int)cx.cellptr[b1 + 2 + L];
+            const int s2 = (int)cx.cellptr[b2], e2 = (int)cx.cellptr[b2 + 2 + L];
+            const int s3 = (int)cx.cellptr[b3], e3 = (int)cx.cellptr[b3 + 2 + L];
+            const int s4 = (int)cx.cellptr[b4], e4 = (int)cx.cellptr[b4 + 2 + L];
+            const int o1 = e0 - s0, o2 = o1 + (e1 - s1), o3 = o2 + (e2 - s2), o4 = o3 + (e3 - s3);
+            M = o4 + (e4 - s4);
+            const int a0 = s0, a1 = s1 - o1, a2 = s2 - o2, a3 = s3 - o3, a4 = s4 - o4;
+#pragma unroll
+            for (int k = 0; k < CT_KSLOT; k++) {
+                const int s = base + k * 32 + lane;
+                int adj = a0;
+                adj = s >= o1 ? a1 : adj;
+                adj = s >= o2 ? a2 : adj;
+                adj = s >= o3 ? a3 : adj;
+                adj = s >= o4 ? a4 : adj;
+                const int pos = s < M ? s + adj : cstart;       // empty slots: any valid position
+                const float4 q = cx.sorted[pos];
+                const unsigned bits = __float_as_uint(q.w);
+                xj[k] = s < M ? q.x : CT_FAR; yj[k] = q.y; zj[k] = q.z;
+                ej[k] = Traits::ekey_f(cx, pos, bits);
+                jp[k] = Traits::jp(pos, CT_NOSHIFT);
+                if (FLAGS & CT_ROLES) roles_or |= s < M ? Traits::role(bits) : 0u;
+            }
+        } else {
             int cxx, cy, cz;
             Traits::decode(c, G, cxx, cy, cz);
-            const bool interior = (cxx >= 1) && (cxx <= G.nx - 2) && (cy >= 1) && (cy <= G.ny - 2) &&
-                                  (cz >= 1) && (cz <= G.nz - 2);
-            if (interior) {
-                // run r covers slots [o_r, o_{r+1}) and sorted positions slot + a_r
-                const int nxy = G.nx * G.ny;
-                const int b1 = c + G.nx - 1, b2 = c + nxy - G.nx - 1, b3 = c + nxy - 1, b4 = c + nxy + G.nx - 1;
-                const int s0 = cstart, e0 = (int)cx.cellptr[c + 2];
-                const int s1 = (int)cx.cellptr[b1], e1 = (int)cx.cellptr[b1 + 3];
-                const int s2 = (int)cx.cellptr[b2], e2 = (int)cx.cellptr[b2 + 3];
-                const int s3 = (int)cx.cellptr[b3], e3 = (int)cx.cellptr[b3 + 3];
-                const int s4 = (int)cx.cellptr[b4], e4 = (int)cx.cellptr[b4 + 3];
-                const int o1 = e0 - s0, o2 = o1 + (e1 - s1), o3 = o2 + (e2 - s2), o4 = o3 + (e3 - s3);
-                M = o4 + (e4 - s4);
-                const int a0 = s0, a1 = s1 - o1, a2 = s2 - o2, a3 = s3 - o3, a4 = s4 - o4;
+            // a wrap along x happens at one side only (grids with >= 3 cells; coarser periodic
+            // grids are adjudicated exactly and never use the shift)
+            const int idx_x = (cxx == 0) ? -1 : 1, idx_y = (cy == 0) ? -3 : 3, idx_z = (cz == 0) ? -9 : 9;
+            int myD = -1, mywrap = 0;
+            if (lane < 27) {
+                const int si = lane == 0 ? 13 : (lane == 13 ? 0 : lane);     // own cell first
+                const int l9 = si / 9, l3 = (si - l9 * 9) / 3;
+                int x = cxx + (si - l9 * 9 - l3 * 3) - 1;
+                int y = cy + l3 - 1;
+                int z = cz + l9 - 1;
+                if (G.periodic) {
+                    if (x < 0) { x += G.nx; mywrap |= 1; } else if (x >= G.nx) { x -= G.nx; mywrap |= 1; }
+                    if (y < 0) { y += G.ny; mywrap |= 2; } else if (y >= G.ny) { y -= G.ny; mywrap |= 2; }
+                    if (z < 0) { z += G.nz; mywrap |= 4; } else if (z >= G.nz) { z -= G.nz; mywrap |= 4; }
+                }
+                const bool ok = (x >= 0 && x < G.nx && y >= 0 && y < G.ny && z >= 0 && z < G.nz);
+                if (ok) myD = (z * G.ny + y) * G.nx + x;
+            }
+            bool keep = (myD >= c);
+            if (!G.distinct) {
+                const unsigned same = __match_any_sync(FULL, myD);
+                keep = keep && ((__ffs(same) - 1) == lane);
+            }
+            int mystart = 0, mycnt = 0;
+            if (keep) {
+                mystart = (int)cx.cellptr[myD];
+                mycnt = (int)cx.cellptr[myD + 1] - mystart;
+            }
+            int incl = mycnt;
 #pragma unroll
-                for (int k = 0; k < CT_KSLOT; k++) {
-                    const int s = base + k * 32 + lane;
-                    int adj = a0;
-                    adj = s >= o1 ? a1 : adj;
-                    adj = s >= o2 ? a2 : adj;
-                    adj = s >= o3 ? a3 : adj;
-                    adj = s >= o4 ? a4 : adj;
-                    const int pos = s < M ? s + adj : cstart;       // empty slots: any valid position
-                    const float4 q = cx.sorted[pos];
-                    const unsigned bits = __float_as_uint(q.w);
-                    xj[k] = s < M ? q.x : CT_FAR; yj[k] = q.y; zj[k] = q.z;
-                    ej[k] = Traits::ekey_f(cx, pos, bits);
-                    jp[k] = Traits::jp(pos, CT_NOSHIFT);
-                    if (FLAGS & CT_ROLES) roles_or |= s < M ? Traits::role(bits) : 0u;
-                }
-            } else {
-                // a wrap along x happens at one side only (grids with >= 3 cells; coarser periodic
-                // grids are adjudicated exactly and never use the shift)
-                const int idx_x = (cxx == 0) ? -1 : 1, idx_y = (cy == 0) ? -3 : 3, idx_z = (cz == 0) ? -9 : 9;
-                int myD = -1, mywrap = 0;
-                if (lane < 27) {
-                    const int si = lane == 0 ? 13 : (lane == 13 ? 0 : lane);     // own cell first
-                    const int l9 = si / 9, l3 = (si - l9 * 9) / 3;
-                    int x = cxx + (si - l9 * 9 - l3 * 3) - 1;
-                    int y = cy + l3 - 1;
-                    int z = cz + l9 - 1;
-                    if (G.periodic) {
-                        if (x < 0) { x += G.nx; mywrap |= 1; } else if (x >= G.nx) { x -= G.nx; mywrap |= 1; }
-                        if (y < 0) { y += G.ny; mywrap |= 2; } else if (y >= G.ny) { y -= G.ny; mywrap |= 2; }
-                        if (z < 0) { z += G.nz; mywrap |= 4; } else if (z >= G.nz) { z -= G.nz; mywrap |= 4; }
-                    }
-                    const bool ok = (x >= 0 && x < G.nx && y >= 0 && y < G.ny && z >= 0 && z < G.nz);
-                    if (ok) myD = (z * G.ny + y) * G.nx + x;
-                }
-                bool keep = (myD >= c);
-                if (!G.distinct) {
-                    const unsigned same = __match_any_sync(FULL, myD);
-                    keep = keep && ((__ffs(same) - 1) == lane);
-                }
-                int mystart = 0, mycnt = 0;
-                if (keep) {
-                    mystart = (int)cx.cellptr[myD];
-                    mycnt = (int)cx.cellptr[myD + 1] - mystart;
-                }
-                int incl = mycnt;
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(FULL, incl, d);
+                if (lane >= d) incl += v;
+            }
+            M = __shfl_sync(FULL, incl, 31);
+            const int off = incl - mycnt;
+            __syncwarp();
+            // expand this lane's stencil cell into the per-warp candidate list
+            const int r0 = max(0, base - off), r1 = min(mycnt, base + CT_CAND - off);
+            for (int r = r0; r < r1; r++) cx.cand[off + r - base] = Traits::cand(mystart + r, mywrap);
+            __syncwarp();
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int v = __shfl_up_sync(FULL, incl, d);
-                    if (lane >= d) incl += v;
-                }
-                M = __shfl_sync(FULL, incl, 31);
-                const int off = incl - mycnt;
-                __syncwarp();
-                // expand this lane's stencil cell into the per-warp candidate list
-                const int r0 = max(0, base - off), r1 = min(mycnt, base + CT_CAND - off);
-                for (int r = r0; r < r1; r++) cx.cand[off + r - base] = Traits::cand(mystart + r, mywrap);
-                __syncwarp();
-#pragma unroll
-                for (int k = 0; k < CT_KSLOT; k++) {
-                    const int s = base + k * 32 + lane;
-                    const typename Traits::cand_t ce = s < M ? cx.cand[s - base] : Traits::cand(cstart, 0);
-                    const int pos = Traits::cand_pos(ce);
-                    const int wb = Traits::cand_wrap(ce);
-                    const int id = CT_NOSHIFT + ((wb & 1) ? idx_x : 0) + ((wb & 2) ? idx_y : 0) +
-                                   ((wb & 4) ? idx_z : 0);
-                    const float4 q = cx.sorted[pos];
-                    const float4 sh = cx.shift[id];
-                    const unsigned bits = __float_as_uint(q.w);
-                    xj[k] = s < M ? __fadd_rn(q.x, sh.x) : CT_FAR;
-                    yj[k] = __fadd_rn(q.y, sh.y); zj[k] = __fadd_rn(q.z, sh.z);
-                    ej[k] = Traits::ekey_f(cx, pos, bits);
-                    jp[k] = Traits::jp(pos, id);
-                    if (FLAGS & CT_ROLES) roles_or |= s < M ? Traits::role(bits) : 0u;
-                }
+            for (int k = 0; k < CT_KSLOT; k++) {
+                const int s = base + k * 32 + lane;
+                const typename Traits::cand_t ce = s < M ? cx.cand[s - base] : Traits::cand(cstart, 0);
+                const int pos = Traits::cand_pos(ce);
+                const int wb = Traits::cand_wrap(ce);
+                const int id = CT_NOSHIFT + ((wb & 1) ? idx_x : 0) + ((wb & 2) ? idx_y : 0) +
+                               ((wb & 4) ? idx_z : 0);
+                const float4 q = cx.sorted[pos];
+                const float4 sh = cx.shift[id];
+                const unsigned bits = __float_as_uint(q.w);
+                xj[k] = s < M ? __fadd_rn(q.x, sh.x) : CT_FAR;
+                yj[k] = __fadd_rn(q.y, sh.y); zj[k] = __fadd_rn(q.z, sh.z);
+                ej[k] = Traits::ekey_f(cx, pos, bits);
+                jp[k] = Traits::jp(pos, id);
+                if (FLAGS & CT_ROLES) roles_or |= s < M ? Traits::role(bits) : 0u;
             }
         }
         bool any_q = true, any_h = true;
@@ -538,44 +543,81 @@ __device__ __forceinline__ void ct_cell_task(const PairParams& p, const GridS& G
             unsigned m[CT_KSLOT];
 #pragma unroll
             for (int k = 0; k < CT_KSLOT; k++) m[k] = 0u;
-            if (left > 64) ct_screen<Traits, 3, FLAGS>(cx, g0, g1, neg_c2_hi, nq, xj, yj, zj, ej, any_q, any_h, m);
+            if (left > 96) ct_screen<Traits, 4, FLAGS>(cx, g0, g1, neg_c2_hi, nq, xj, yj, zj, ej, any_q, any_h, m);
+            else if (left > 64) ct_screen<Traits, 3, FLAGS>(cx, g0, g1, neg_c2_hi, nq, xj, yj, zj, ej, any_q, any_h, m);
             else if (left > 32) ct_screen<Traits, 2, FLAGS>(cx, g0, g1, neg_c2_hi, nq, xj, yj, zj, ej, any_q, any_h, m);
             else ct_screen<Traits, 1, FLAGS>(cx, g0, g1, neg_c2_hi, nq, xj, yj, zj, ej, any_q, any_h, m);
-            // push the non-empty masks (one code site for all slots: the accounting code behind
-            // ct_drain_while is large)
-#pragma unroll 1
+            // own-cell slots: own atoms g0 + b with b < v pair with slot s (each unordered pair once,
+            // no self pair).  Empty slots never pass the screen (CT_FAR).
+            if (base == 0 && g0 == cstart) {
+                m[0] &= ltmask;                       // v = lane; slots >= 32 pair with every own atom
+            } else {
+#pragma unroll
+                for (int k = 0; k < CT_KSLOT; k++) {
+                    const int v = base + 32 * k + lane - (g0 - cstart);
+                    if (v <= 0) m[k] = 0u;
+                    else if (v < 32) m[k] &= (1u << v) - 1u;
+                }
+            }
+            // push the non-empty masks to the ring: all at once when they fit (the usual case),
+            // else slot by slot with full batches accounted in between.  ONE accounting site:
+            // the code behind ct_drain is large.
+            unsigned nz[CT_KSLOT], total = 0u;
+#pragma unroll
             for (int k = 0; k < CT_KSLOT; k++) {
-                unsigned mk = k == 0 ? m[0] : (k == 1 ? m[1] : m[2]);
-                const unsigned jpk = k == 0 ? jp[0] : (k == 1 ? jp[1] : jp[2]);
-                const int s = base + 32 * k + lane;
-                const int v = s - (g0 - cstart);          // own atoms g0 + b with b < v pair with this slot
-                if (s >= M || v <= 0) mk = 0u;
-                else if (v < 32) mk &= (1u << v) - 1u;
-                if (mk) cx.hitq[ring_reserve(cx.qcnt) & (CT_QCAP - 1)] = Traits::entry(g0, jpk, mk);
-                ct_drain_while<Traits, Sink, MODE, FLAGS>(p, cx, sink, head, 31u);
+                nz[k] = __ballot_sync(FULL, m[k] != 0u);
+                total += (unsigned)__popc(nz[k]);
+            }
+            int done = 0;
+            if (ring.tail - ring.head + total <= (unsigned)CT_QCAP) {
+                unsigned at = ring.tail;
+#pragma unroll
+                for (int k = 0; k < CT_KSLOT; k++) {
+                    if (m[k] != 0u)
+                        cx.hitq[(at + __popc(nz[k] & ltmask)) & (CT_QCAP - 1)] = Traits::entry(g0, jp[k], m[k]);
+                    at += (unsigned)__popc(nz[k]);
+                }
+                ring.tail = at;
+                done = CT_KSLOT;
+            }
+            for (;;) {
+                while (ring.tail - ring.head > 31u) ct_drain<Traits, Sink, MODE, FLAGS>(p, cx, sink, ring, ltmask);
+                if (done >= CT_KSLOT) break;
+                // (rare) next slot on its own: at most 32 entries, the ring holds at most 31
+                unsigned mk = m[0], jpk = jp[0];
+#pragma unroll
+                for (int k = 1; k < CT_KSLOT; k++) {
+                    mk = done == k ? m[k] : mk;
+                    jpk = done == k ? jp[k] : jpk;
+                }
+                ring_push<Traits>(cx, ring, ltmask, mk != 0u, Traits::entry(g0, jpk, mk));
+                done++;
             }
         }
         if (left <= CT_CAND) break;
     }
 }
 
-// Warps pull occupied cells from a task counter until the frame is exhausted.
+// Warps pull tasks from a task counter until the frame is exhausted.
 template <typename Traits, typename Sink, int MODE, int FLAGS, typename OccT>
 __device__ __forceinline__ void ct_pair_phase(const PairParams& p, const GridS& G, const PairCtx<Traits>& cx,
                                               Sink& sink, const OccT* occ, int n_occ, int* task_counter,
                                               unsigned long long& n_tests)
 {
     const int lane = threadIdx.x & 31;
-    __syncwarp();
-    unsigned head = *(volatile unsigned int*)cx.qcnt;      // ring is empty between frames
+    Ring ring;
+    ring.head = ring.tail = 0u;
     for (;;) {
         int k = 0;
         if (lane == 0) k = atomicAdd(task_counter, 1);
         k = __shfl_sync(0xffffffffu, k, 0);
         if (k >= n_occ) break;
-        ct_cell_task<Traits, Sink, MODE, FLAGS>(p, G, cx, sink, (int)occ[k], n_tests, head);
+        const unsigned task = (unsigned)occ[k];
+        if (task == Traits::TASK_EMPTY) continue;
+        ct_cell_task<Traits, Sink, MODE, FLAGS>(p, G, cx, sink, task, n_tests, ring);
     }
-    ct_drain_while<Traits, Sink, MODE, FLAGS>(p, cx, sink, head, 0u);
+    const unsigned ltmask = (1u << lane) - 1u;
+    while (ring.tail != ring.head) ct_drain<Traits, Sink, MODE, FLAGS>(p, cx, sink, ring, ltmask);
 }
 
 template <typename Traits, typename Sink, int FLAGS, typename OccT>

@@ -64,6 +64,9 @@ struct LargeTraits {
     typedef int pos_t;
     typedef unsigned int cand_t;                    // sorted position [0,20) | wrap flags [20,23)
     typedef uint4 hit_t;          // {own base, jpos [0,20) | shift id [20,25), own-atom mask, -}
+    // task word: cell [0,28) | interior | pair
+    static constexpr unsigned TASK_CMASK = 0x0fffffffu, TASK_INTERIOR = 0x10000000u, TASK_PAIR = 0x20000000u,
+                              TASK_EMPTY = 0xffffffffu;
     static __device__ __forceinline__ cand_t cand(int pos, int wrap)
     {
         return (unsigned)pos | ((unsigned)wrap << 20);
@@ -273,10 +276,15 @@ __global__ void __launch_bounds__(1024) kl_scan(const GridS* __restrict__ grid, 
     __syncthreads();
     int run = isum - sum + s_sum[warp];
     int ocur = iocc - nocc + s_occ[warp];
+    const GridS& G = *grid;
     for (int c = c0; c < c1; c++) {
         const int v = cellcnt[c];
         cellptr[c] = run;
-        if (v) occ[ocur++] = c;
+        if (v) {
+            int cx, cy, cz;
+            LargeTraits::decode(c, G, cx, cy, cz);
+            occ[ocur++] = (int)((unsigned)c | (cell_interior(G, cx, cy, cz) ? LargeTraits::TASK_INTERIOR : 0u));
+        }
         run += v;
     }
     if (tid == 0) cellptr[ncell] = n;
@@ -309,7 +317,6 @@ __global__ void __launch_bounds__(LG_PAIR_THREADS, 4) kl_pairs(PairParams pp, St
 {
     __shared__ unsigned int cand_all[(LG_PAIR_THREADS / 32) * CT_CAND];
     __shared__ uint4 hitq_all[(LG_PAIR_THREADS / 32) * CT_QCAP];
-    __shared__ unsigned int qcnt_all[LG_PAIR_THREADS / 32];
     __shared__ float4 shift_s[27];
     __shared__ float thresh_s[2];
     __shared__ GridS G;
@@ -323,13 +330,12 @@ __global__ void __launch_bounds__(LG_PAIR_THREADS, 4) kl_pairs(PairParams pp, St
                       lo, hi);
         thresh_s[0] = lo; thresh_s[1] = hi;
     }
-    if ((threadIdx.x & 31) == 0) qcnt_all[warp] = 0u;
     __syncthreads();
     pp.c2_lo = thresh_s[0]; pp.c2_hi = thresh_s[1];
     PairCtx<LargeTraits> cx;
     cx.sorted = sorted; cx.ekey = sorted_ekey; cx.cellptr = cellptr;
     cx.cand = cand_all + warp * CT_CAND; cx.hitq = hitq_all + warp * CT_QCAP;
-    cx.qcnt = qcnt_all + warp; cx.shift = shift_s;
+    cx.shift = shift_s;
     unsigned long long n_tests = 0;
     StampSink sink = sink_in;
     sink.pending = 0; sink.pend_old = 0u; sink.pend_lo = sink.pend_hi = 0u;

@@ -31,9 +31,12 @@
 
 namespace cmb {
 
-constexpr int FS_THREADS = 512;
+#ifndef FS_THREADS_CFG
+#define FS_THREADS_CFG 512
+#endif
+constexpr int FS_THREADS = FS_THREADS_CFG;
 constexpr int FS_WARPS = FS_THREADS / 32;
-constexpr int FS_APT = 12;                          // atoms per thread in the binning passes
+constexpr int FS_APT = 6144 / FS_THREADS;           // atoms per thread in the binning passes
 constexpr int FS_MAX_ATOMS = FS_THREADS * FS_APT;   // 6144
 constexpr int FS_HEADER_BYTES = 2048;
 constexpr int FS_CAND = CT_CAND;
@@ -155,6 +158,9 @@ struct SmallTraits {
     typedef unsigned short pos_t;
     typedef unsigned short cand_t;                  // sorted position [0,13) | wrap flags [13,16)
     typedef uint2 hit_t;          // {own base [0,13) | jpos [13,26) | shift id [26,31), own-atom mask}
+    // task word: cell [0,14) | interior | pair
+    static constexpr unsigned TASK_CMASK = 0x3fffu, TASK_INTERIOR = 0x4000u, TASK_PAIR = 0x8000u,
+                              TASK_EMPTY = 0xffffu;
     static __device__ __forceinline__ cand_t cand(int pos, int wrap)
     {
         return (cand_t)((unsigned)pos | ((unsigned)wrap << 13));
@@ -236,7 +242,6 @@ __global__ void __launch_bounds__(FS_THREADS, FS_MIN_CTAS) k_frames_small(const 
     int* task_counter = reinterpret_cast<int*>(smem + 8);
     int* n_occ_s = reinterpret_cast<int*>(smem + 12);
     float* thresh_s = reinterpret_cast<float*>(smem + 16);                 // {c2_lo, c2_hi} of the frame
-    unsigned int* qcnt = reinterpret_cast<unsigned int*>(smem + FS_H_QCNT) + warp;
     float* amax_s = reinterpret_cast<float*>(smem + FS_H_AMAX);
     float* red = reinterpret_cast<float*>(smem + FS_H_RED);                // 6 * 32 floats
     unsigned int* scan_s = reinterpret_cast<unsigned int*>(smem + FS_H_RED);   // overlays `red`
@@ -257,7 +262,6 @@ __global__ void __launch_bounds__(FS_THREADS, FS_MIN_CTAS) k_frames_small(const 
         mbar_init(mbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (lane == 0) *qcnt = 0u;
     for (int w = tid; w < p.bm_words; w += FS_THREADS) bitmap[w] = 0u;
     __syncthreads();
 
@@ -394,12 +398,32 @@ __global__ void __launch_bounds__(FS_THREADS, FS_MIN_CTAS) k_frames_small(const 
             __syncthreads();
             const unsigned excl = incl - packed + scan_s[warp];
             unsigned run = excl & 0xffffu, ocur = excl >> 16;
+            // task list: one task per occupied cell, or per two x-adjacent sparsely populated
+            // interior cells of this thread's range.  (The pair merge makes the list shorter than
+            // the occupied-cell count the scan reserved: unused entries are marked empty.)
+            int cxx, cy, cz;
+            SmallTraits::decode(c0, G, cxx, cy, cz);
+            unsigned prev = 0u;           // count of the previous cell if it can still take a partner
+            const unsigned oend = ocur + nocc;
             for (int c = c0; c < c1; c++) {
                 const unsigned v = cell16[c];
                 cell16[c] = (unsigned short)run;
-                if (v) occ[ocur++] = (unsigned short)c;
                 run += v;
+                const bool inter = cell_interior(G, cxx, cy, cz);
+                if (v) {
+                    if (prev && inter && prev + v <= (unsigned)CT_PAIR_MAX_OWN) {
+                        occ[ocur - 1] |= (unsigned short)SmallTraits::TASK_PAIR;
+                        prev = 0u;
+                    } else {
+                        occ[ocur++] = (unsigned short)((unsigned)c | (inter ? SmallTraits::TASK_INTERIOR : 0u));
+                        prev = inter ? v : 0u;
+                    }
+                } else {
+                    prev = 0u;
+                }
+                if (++cxx == G.nx) { cxx = 0; if (++cy == G.ny) { cy = 0; cz++; } }
             }
+            while (ocur < oend) occ[ocur++] = (unsigned short)0xffffu;      // empty task
             if (tid == 0) cell16[G.ncell] = (unsigned short)n;
         }
         __syncthreads();
@@ -430,7 +454,7 @@ __global__ void __launch_bounds__(FS_THREADS, FS_MIN_CTAS) k_frames_small(const 
         pp.atom_keys = p.atom_keys; pp.atom_cap = p.atom_cap; pp.counters = p.counters;
         pp.boundary = p.boundary; pp.boundary_cap = p.boundary_cap; pp.frame_id = frame_id;
         PairCtx<SmallTraits> cx;
-        cx.sorted = sorted; cx.cellptr = cell16; cx.cand = cand; cx.hitq = hitq; cx.qcnt = qcnt;
+        cx.sorted = sorted; cx.cellptr = cell16; cx.cand = cand; cx.hitq = hitq;
         cx.shift = shift_s; cx.ekey = nullptr;
         BitmapSink sink{p.meta32, p.atom_table, bitmap, (unsigned)n, (unsigned)p.n_res_c, 0u, 0u};
         ct_pair_phase_dyn<SmallTraits, BitmapSink, FLAGS, unsigned short>(pp, G, cx, sink, occ, *n_occ_s,
