@@ -182,14 +182,16 @@ struct PairParams {
     float c2;                        // cutoff_f * cutoff_f
     float c2_lo, c2_hi;              // certain-contact / screening thresholds of this frame
     int boundary_ulps;
-    const float* xyz_frame;          // RAW coordinates of this frame [n][3] (global memory)
-    const float* box9;               // unit cell rows of this frame (global memory) or nullptr
+    // the frame: addressed through its index so that only one register stays live in the hot loop
+    const float* xyz;                // RAW coordinates [frames][n][3] (global memory)
+    const float* box;                // unit cell rows [frames][9] (global memory) or nullptr
+    int f;                           // index of the frame in xyz / box
+    long long frame0;                // id of frame 0 (emitted keys, boundary records)
     unsigned long long* atom_keys;   // emitted (frame<<40 | lo<<20 | hi) or nullptr
     long long atom_cap;
     unsigned long long* counters;    // [0] atom keys, [1] residue keys, [2] boundary records, [3] pair tests
     float4* boundary;                // records {frame, lo, hi, d2} (ints bit-cast) or nullptr
     long long boundary_cap;
-    long long frame_id;
 };
 
 template <typename Traits>
@@ -314,9 +316,10 @@ __device__ __forceinline__ void ct_account(const PairParams& p, const PairCtx<Tr
     if (elig && !hit) {
         // ambiguous: MDTraj's arithmetic on the raw coordinates, direction lower -> higher sorted
         // position (antisymmetric for every pair that can be a hit, DESIGN.md "direction")
-        const NlBox B = make_nlbox(p.box9);
-        const float* pa = p.xyz_frame + 3 * (size_t)ia;
-        const float* pb = p.xyz_frame + 3 * (size_t)ib;
+        const NlBox B = make_nlbox(p.box ? p.box + (size_t)p.f * 9 : nullptr);
+        const float* frame = p.xyz + (size_t)p.f * (size_t)p.n * 3;
+        const float* pa = frame + 3 * (size_t)ia;
+        const float* pb = frame + 3 * (size_t)ib;
         const float d2 = nl_d2<MODE>(__ldg(pa), __ldg(pa + 1), __ldg(pa + 2), __ldg(pb), __ldg(pb + 1),
                                      __ldg(pb + 2), B);
         hit = d2 <= p.c2;
@@ -326,7 +329,7 @@ __device__ __forceinline__ void ct_account(const PairParams& p, const PairCtx<Tr
             if (diff <= p.boundary_ulps) {
                 const unsigned long long w = atomicAdd(&p.counters[2], 1ull);
                 if ((long long)w < p.boundary_cap)
-                    p.boundary[w] = make_float4(__int_as_float((int)p.frame_id), __int_as_float(min(ia, ib)),
+                    p.boundary[w] = make_float4(__int_as_float((int)(p.frame0 + p.f)), __int_as_float(min(ia, ib)),
                                                 __int_as_float(max(ia, ib)), d2);
             }
         }
@@ -343,7 +346,7 @@ __device__ __forceinline__ void ct_account(const PairParams& p, const PairCtx<Tr
                 if (hit) {
                     const unsigned long long w = wbase + __popc(hm & ((1u << lane) - 1u));
                     if ((long long)w < p.atom_cap)
-                        p.atom_keys[w] = ((unsigned long long)p.frame_id << 40) |
+                        p.atom_keys[w] = ((unsigned long long)(p.frame0 + p.f) << 40) |
                                          ((unsigned long long)min(ia, ib) << 20) | (unsigned long long)max(ia, ib);
                 }
             }
@@ -384,6 +387,7 @@ __device__ __forceinline__ void ct_screen(const PairCtx<Traits>& cx, int g0, int
                                           const float (&zj)[CT_KSLOT], const float (&ej)[CT_KSLOT], bool any_q,
                                           bool any_h, unsigned (&m)[CT_KSLOT])
 {
+#pragma unroll 2
     for (int ipos = g1 - 1; ipos >= g0; ipos--) {
         const float4 pi = cx.sorted[ipos];
         const float ei = Traits::ekey_f(cx, ipos, __float_as_uint(pi.w));
@@ -565,17 +569,22 @@ __device__ __forceinline__ void ct_cell_task(const PairParams& p, const GridS& G
             unsigned nz[CT_KSLOT], total = 0u;
 #pragma unroll
             for (int k = 0; k < CT_KSLOT; k++) {
-                nz[k] = __ballot_sync(FULL, m[k] != 0u);
-                total += (unsigned)__popc(nz[k]);
+                nz[k] = 0u;
+                if (k == 0 || left > 32 * k) {                   // slots beyond `left` are empty
+                    nz[k] = __ballot_sync(FULL, m[k] != 0u);
+                    total += (unsigned)__popc(nz[k]);
+                }
             }
             int done = 0;
             if (ring.tail - ring.head + total <= (unsigned)CT_QCAP) {
                 unsigned at = ring.tail;
 #pragma unroll
                 for (int k = 0; k < CT_KSLOT; k++) {
-                    if (m[k] != 0u)
-                        cx.hitq[(at + __popc(nz[k] & ltmask)) & (CT_QCAP - 1)] = Traits::entry(g0, jp[k], m[k]);
-                    at += (unsigned)__popc(nz[k]);
+                    if (nz[k] != 0u) {
+                        if (m[k] != 0u)
+                            cx.hitq[(at + __popc(nz[k] & ltmask)) & (CT_QCAP - 1)] = Traits::entry(g0, jp[k], m[k]);
+                        at += (unsigned)__popc(nz[k]);
+                    }
                 }
                 ring.tail = at;
                 done = CT_KSLOT;
@@ -609,7 +618,7 @@ __device__ __forceinline__ void ct_pair_phase(const PairParams& p, const GridS& 
     ring.head = ring.tail = 0u;
     for (;;) {
         int k = 0;
-        if (lane == 0) k = atomicAdd(task_counter, 1);
+        if (lane == 0) k = Traits::next_task(task_counter);
         k = __shfl_sync(0xffffffffu, k, 0);
         if (k >= n_occ) break;
         const unsigned task = (unsigned)occ[k];
@@ -625,7 +634,7 @@ __device__ __forceinline__ void ct_pair_phase_dyn(const PairParams& p, const Gri
                                                   Sink& sink, const OccT* occ, int n_occ, int* task_counter,
                                                   unsigned long long& n_tests)
 {
-    const int mode = box_mode(p.box9);
+    const int mode = box_mode(p.box ? p.box + (size_t)p.f * 9 : nullptr);
     if (mode == BOX_ORTHO)
         ct_pair_phase<Traits, Sink, BOX_ORTHO, FLAGS, OccT>(p, G, cx, sink, occ, n_occ, task_counter, n_tests);
     else if (mode == BOX_TRICLINIC)

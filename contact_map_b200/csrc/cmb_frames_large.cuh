@@ -83,6 +83,12 @@ struct LargeTraits {
     static __device__ __forceinline__ int e_jpos(hit_t e) { return (int)(e.y & 0xfffffu); }
     static __device__ __forceinline__ int e_id(hit_t e) { return (int)(e.y >> 20); }
     static __device__ __forceinline__ unsigned e_mask(hit_t e) { return e.z; }
+    static __device__ __forceinline__ int next_task(int* counter)        // task counter in global memory
+    {
+        int old;
+        asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(counter) : "memory");
+        return old;
+    }
     // sorted[].w bits: atom index [0,30) | role [30,32); exclusion keys in a separate array
     static __device__ __forceinline__ int atom(unsigned bits) { return (int)(bits & 0x3fffffffu); }
     static __device__ __forceinline__ unsigned role(unsigned bits) { return bits >> 30; }
@@ -409,9 +415,9 @@ inline int large_run(const LargeJob& job, LargeScratch& S, int sm_count, cudaStr
                                                     S.d_sorted_ekey);
         PairParams pp;
         pp.n = n; pp.n_ignored = job.n_ignored; pp.c2 = job.c2; pp.c2_lo = pp.c2_hi = job.c2;
-        pp.boundary_ulps = job.boundary_ulps; pp.xyz_frame = x; pp.box9 = box9;
+        pp.boundary_ulps = job.boundary_ulps; pp.xyz = x; pp.box = box9; pp.f = 0; pp.frame0 = job.frame0 + f;
         pp.atom_keys = job.atom_keys; pp.atom_cap = job.atom_cap; pp.counters = job.counters;
-        pp.boundary = job.boundary; pp.boundary_cap = job.boundary_cap; pp.frame_id = job.frame0 + f;
+        pp.boundary = job.boundary; pp.boundary_cap = job.boundary_cap;
         StampSink sink;
         sink.meta = job.meta; sink.atom_table = job.atom_table;
         sink.stamp = want_res ? S.d_stamp : nullptr;

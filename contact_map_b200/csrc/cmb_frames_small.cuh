@@ -180,6 +180,17 @@ struct SmallTraits {
     static __device__ __forceinline__ int e_jpos(hit_t e) { return (int)((e.x >> 13) & 0x1fffu); }
     static __device__ __forceinline__ int e_id(hit_t e) { return (int)(e.x >> 26); }
     static __device__ __forceinline__ unsigned e_mask(hit_t e) { return e.y; }
+    // task counter in shared memory; plain ATOMS (the compiler's warp-aggregated form costs 16
+    // issue slots for a single active lane)
+    static __device__ __forceinline__ int next_task(int* counter)
+    {
+        int old;
+        asm volatile("atom.shared.add.u32 %0, [%1], 1;"
+                     : "=r"(old)
+                     : "r"((unsigned)__cvta_generic_to_shared(counter))
+                     : "memory");
+        return old;
+    }
     // sorted[].w bits: atom index [0,13) | role [14,16) | exclusion key [16,32)
     static __device__ __forceinline__ unsigned bits(int atom, unsigned role, unsigned ekey)
     {
@@ -450,9 +461,9 @@ __global__ void __launch_bounds__(FS_THREADS, FS_MIN_CTAS) k_frames_small(const 
         const long long frame_id = p.frame0 + f;
         PairParams pp;
         pp.n = n; pp.n_ignored = p.n_ignored; pp.c2 = p.c2; pp.c2_lo = thresh_s[0]; pp.c2_hi = thresh_s[1];
-        pp.boundary_ulps = p.boundary_ulps; pp.xyz_frame = p.xyz + (size_t)f * (size_t)n * 3; pp.box9 = box9;
+        pp.boundary_ulps = p.boundary_ulps; pp.xyz = p.xyz; pp.box = p.box; pp.f = (int)f; pp.frame0 = p.frame0;
         pp.atom_keys = p.atom_keys; pp.atom_cap = p.atom_cap; pp.counters = p.counters;
-        pp.boundary = p.boundary; pp.boundary_cap = p.boundary_cap; pp.frame_id = frame_id;
+        pp.boundary = p.boundary; pp.boundary_cap = p.boundary_cap;
         PairCtx<SmallTraits> cx;
         cx.sorted = sorted; cx.cellptr = cell16; cx.cand = cand; cx.hitq = hitq;
         cx.shift = shift_s; cx.ekey = nullptr;
