@@ -347,13 +347,20 @@ def run_ours(args):
         elapsed_ms = float(t.item())
     value = world * F * args.steps / (elapsed_ms / 1e3)
 
-    # executed pair tests of one pass (separate, untimed launch with the counter switched on)
+    # candidate pairs of one pass (separate, untimed launches with the counter switched on):
+    # canonical = cutoff-sized cells, 27-cell half shell (SURVEY 8d's P_cand; task pairing off);
+    # screened = what the production configuration actually screens (task pairing on adds tests
+    # between cells two columns apart)
     engine.set_option("count_tests", 1)
-    atom_t.zero_()
-    res_t.zero_()
-    engine.accumulate(d_xyz, d_box, atom_t, res_t)
-    pair_tests = engine.get_stat("pair_tests")
+    counts = {}
+    for key, pairing in (("canonical", 0), ("screened", 1)):
+        engine.set_option("pair_tasks", pairing)
+        atom_t.zero_()
+        res_t.zero_()
+        engine.accumulate(d_xyz, d_box, atom_t, res_t)
+        counts[key] = engine.get_stat("pair_tests")
     engine.set_option("count_tests", 0)
+    pair_tests = counts["canonical"]
 
     # ---- end to end through the public API, host buffers -------------------------------
     e2e = None
@@ -412,20 +419,30 @@ def run_ours(args):
         traffic = None if per_frame is None else per_frame * F    # ncu capture, scaled to this launch
     sm_count = engine.get_stat("sm_count")
     sm_mhz = clocks.get("sm_mhz") or 1965.0
-    # FP32 view: executed pair tests x 23 separately rounded fp32 ops (orthorhombic) per test
+    # FP32 view: canonical candidate pairs x 23 lane-ops of the reference arithmetic
+    # (orthorhombic: 18 FP32 + 3 XU + exclusion/compare) per pair, against the FP32 pipe peak.  The
+    # kernel itself spends 10 issue slots per screened pair (3 FADD + 3 FFMA + 2 FADD + FMNMX + SHF)
+    # and runs the reference arithmetic only on the pairs the screening cannot decide.
     fp32_lane_ops = pair_tests * 23.0 / (kernel_ms / 1e3)
     fp32_peak = sm_count * 128 * sm_mhz * 1e6
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": traffic, "kernel": "k_frames_small", "kernel_ms": kernel_ms,
         "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-        "note": "HBM is the designated roofline (SURVEY 8d) but the kernel is FP32-issue bound: "
-                "see fp32_pipe",
-        "fp32_pipe": {"executed_pair_tests_per_launch": pair_tests,
-                      "lane_ops_per_test": 23, "achieved_lane_ops_per_s": fp32_lane_ops,
+        "note": "HBM is the designated roofline (SURVEY 8d) but the kernel is instruction-issue bound: "
+                "see fp32_pipe (SURVEY 8d's lower ceiling)",
+        "fp32_pipe": {"candidate_pairs_per_launch": pair_tests,
+                      "screened_pairs_per_launch": counts["screened"],
+                      "reference_lane_ops_per_pair": 23, "kernel_issue_slots_per_screened_pair": 10,
+                      "achieved_lane_ops_per_s": fp32_lane_ops,
                       "peak_lane_ops_per_s": fp32_peak, "frac": fp32_lane_ops / fp32_peak,
-                      "peak_definition": "%d SMs x 128 FP32 lanes x %.0f MHz (median SM clock under load), "
-                                         "non-FMA ops" % (sm_count, sm_mhz)},
+                      "definition": "frames/s x canonical candidate pairs (cutoff-sized cells, 27-cell half "
+                                    "shell) x 23 lane-ops of the reference arithmetic / FP32 pipe peak; the "
+                                    "kernel screens with FMA arithmetic and adjudicates only ambiguous pairs "
+                                    "with the reference arithmetic, so frac is work-equivalent throughput, "
+                                    "not pipe utilisation",
+                      "peak_definition": "%d SMs x 128 FP32 lanes x %.0f MHz (median SM clock under load)"
+                                         % (sm_count, sm_mhz)},
     }
 
     cpu_baseline = None
@@ -446,7 +463,8 @@ def run_ours(args):
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         "roofline": roofline, "cpu_baseline": cpu_baseline,
         "atom_pairs_screened_per_s": {"logical_nQ_x_nH": value * n * n,
-                                      "executed_tests": world * pair_tests * args.steps / (elapsed_ms / 1e3)},
+                                      "candidate_pairs": world * pair_tests * args.steps / (elapsed_ms / 1e3),
+                                      "screened_pairs": world * counts["screened"] * args.steps / (elapsed_ms / 1e3)},
         "result": {"distinct_atom_pairs": n_atom_pairs, "distinct_residue_pairs": n_res_pairs},
     }
     print(json.dumps(line))

@@ -69,6 +69,7 @@ struct cmb_ctx {
 
     // options / stats
     int count_tests = 0;
+    int pair_tasks = 1;
     int last_slot = 0;
     std::map<std::string, int64_t> stats;
 };
@@ -172,6 +173,7 @@ extern "C" int cmb_set_option(cmb_ctx* ctx, const char* name, int64_t value)
 {
     if (!ctx || !name) return CMB_ERR_ARG;
     if (!strcmp(name, "count_tests")) { ctx->count_tests = value != 0; return CMB_OK; }
+    if (!strcmp(name, "pair_tasks")) { ctx->pair_tasks = value != 0; return CMB_OK; }
     if (!strcmp(name, "max_cells")) {
         if (value < 8 || value > 16383) return fail(ctx, CMB_ERR_ARG, "max_cells out of range");
         ctx->fs_maxc = (int)value;
@@ -361,16 +363,6 @@ struct FrameJob {
     float4* boundary; long long boundary_cap; int boundary_ulps;
 };
 
-static float advance_float(float v, int steps)
-{
-    int32_t bits;
-    memcpy(&bits, &v, 4);
-    bits += steps;
-    float out;
-    memcpy(&out, &bits, 4);
-    return out;
-}
-
 static int launch_frames(cmb_ctx* ctx, const FrameJob& job, int slot, cudaStream_t stream)
 {
     if (!ctx->have_system) return fail(ctx, CMB_ERR_STATE, "cmb_set_system has not been called");
@@ -393,6 +385,7 @@ static int launch_frames(cmb_ctx* ctx, const FrameJob& job, int slot, cudaStream
         p.boundary_ulps = job.boundary_ulps;
         p.n_ignored = ctx->n_ignored; p.n_res_c = ctx->n_res_c;
         p.maxc = ctx->fs_maxc; p.bm_words = ctx->fs_bm_words; p.bm_in_smem = ctx->fs_bm_in_smem;
+        p.pair_tasks = ctx->pair_tasks;
         p.atom_table = job.atom_table; p.res_table = job.res_table;
         p.atom_keys = job.atom_keys; p.atom_cap = job.atom_cap;
         p.res_keys = job.res_keys; p.res_cap = job.res_cap;

@@ -71,6 +71,7 @@ struct FrameParams {
     int maxc;                    // cell capacity of the shared-memory arrays
     int bm_words;                // bitmap words
     int bm_in_smem;
+    int pair_tasks;              // merge sparsely populated x-adjacent interior cells into one task
     unsigned int* g_bitmap;      // [gridDim.x][bm_words] scratch when the bitmap is not in smem
     unsigned int* atom_table;    // [n][n] uint32 (entry [lo][hi]) or nullptr
     unsigned int* res_table;     // [n_res_c][n_res_c] uint32 or nullptr
@@ -422,7 +423,7 @@ __global__ void __launch_bounds__(FS_THREADS, FS_MIN_CTAS) k_frames_small(const 
                 run += v;
                 const bool inter = cell_interior(G, cxx, cy, cz);
                 if (v) {
-                    if (prev && inter && prev + v <= (unsigned)CT_PAIR_MAX_OWN) {
+                    if (prev && inter && prev + v <= (unsigned)CT_PAIR_MAX_OWN && p.pair_tasks) {
                         occ[ocur - 1] |= (unsigned short)SmallTraits::TASK_PAIR;
                         prev = 0u;
                     } else {
