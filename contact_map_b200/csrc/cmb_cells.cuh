@@ -138,7 +138,10 @@ __device__ __forceinline__ bool cell_interior(const GridS& G, int cx, int cy, in
 
 // two x-adjacent occupied interior cells are merged into one task when they are sparsely
 // populated (their candidate set, ~19 cells, then still fits the register-resident slots)
-constexpr int CT_PAIR_MAX_OWN = 13;
+#ifndef CT_PAIR_MAX_OWN_CFG
+#define CT_PAIR_MAX_OWN_CFG 18
+#endif
+constexpr int CT_PAIR_MAX_OWN = CT_PAIR_MAX_OWN_CFG;
 
 // =================================================================================
 // Pair phase shared by both paths.
