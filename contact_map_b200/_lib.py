@@ -27,7 +27,8 @@ EXPORTS = [
     "cmb_n_residues", "cmb_residue_map", "cmb_table_sizes", "cmb_path_kind", "cmb_accumulate",
     "cmb_accumulate_host", "cmb_accumulate_host_gather", "cmb_frame_contacts", "cmb_sort_keys", "cmb_export_nonzero",
     "cmb_boundary_pairs", "cmb_set_option", "cmb_get_stat", "cmb_gather_atoms", "cmb_min_dist",
-    "cmb_nearest", "cmb_synth_frames",
+    "cmb_nearest", "cmb_synth_frames", "cmb_set_table_mode", "cmb_hash_stats", "cmb_export_hashed",
+    "cmb_hash_rehash", "cmb_hash_overflow_buffer", "cmb_hash_add",
 ]
 
 
@@ -102,6 +103,18 @@ def lib():
     L.cmb_accumulate_host.argtypes = [vp, vp, vp, i64, i64, vp, vp]
     L.cmb_accumulate_host_gather.restype = i32
     L.cmb_accumulate_host_gather.argtypes = [vp, vp, i32, vp, vp, i64, i64, i32, vp, vp]
+    L.cmb_set_table_mode.restype = i32
+    L.cmb_set_table_mode.argtypes = [vp, i32, i32]
+    L.cmb_hash_stats.restype = i32
+    L.cmb_hash_stats.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i64)]
+    L.cmb_export_hashed.restype = i32
+    L.cmb_export_hashed.argtypes = [vp, vp, i32, i64, vp, vp, vp, vp]
+    L.cmb_hash_overflow_buffer.restype = i32
+    L.cmb_hash_overflow_buffer.argtypes = [vp, vp, i64]
+    L.cmb_hash_add.restype = i32
+    L.cmb_hash_add.argtypes = [vp, vp, i32, vp, vp, i64, i32, vp]
+    L.cmb_hash_rehash.restype = i32
+    L.cmb_hash_rehash.argtypes = [vp, vp, i32, vp, i32, vp]
     L.cmb_frame_contacts.restype = i32
     L.cmb_frame_contacts.argtypes = [vp, vp, vp, i64, i64, vp, i64, vp, i64, vp, vp, vp, vp]
     L.cmb_sort_keys.restype = i32

@@ -70,6 +70,10 @@ struct cmb_ctx {
     // options / stats
     int count_tests = 0;
     int pair_tasks = 1;
+    int atom_log2 = 0, res_log2 = 0;          // hashed count tables when > 0 (cmb_set_table_mode)
+    unsigned long long* d_hstats = nullptr;   // [4] new atom keys, new residue keys, parked hits, failed re-inserts
+    unsigned long long* d_ovf = nullptr;      // caller-owned overflow list (cmb_hash_overflow_buffer)
+    long long ovf_cap = 0;
     int last_slot = 0;
     std::map<std::string, int64_t> stats;
 };
@@ -166,6 +170,7 @@ extern "C" void cmb_ctx_destroy(cmb_ctx* ctx)
         large_scratch_free(ctx->large[s]);
     }
     cudaFree(ctx->d_tmp);
+    cudaFree(ctx->d_hstats);
     delete ctx;
 }
 
@@ -344,8 +349,9 @@ extern "C" int cmb_residue_map(const cmb_ctx* ctx, int32_t* out)
 extern "C" int cmb_table_sizes(const cmb_ctx* ctx, int64_t* atom_elems, int64_t* res_elems)
 {
     if (!ctx || !ctx->have_system) return CMB_ERR_STATE;
-    if (atom_elems) *atom_elems = (int64_t)ctx->n * ctx->n;
-    if (res_elems) *res_elems = (int64_t)ctx->n_res_c * ctx->n_res_c;
+    // dense: uint32 entries; hashed (cmb_set_table_mode): uint64 slots
+    if (atom_elems) *atom_elems = ctx->atom_log2 > 0 ? (1ll << ctx->atom_log2) : (int64_t)ctx->n * ctx->n;
+    if (res_elems) *res_elems = ctx->res_log2 > 0 ? (1ll << ctx->res_log2) : (int64_t)ctx->n_res_c * ctx->n_res_c;
     return CMB_OK;
 }
 
@@ -376,6 +382,8 @@ static int launch_frames(cmb_ctx* ctx, const FrameJob& job, int slot, cudaStream
     ctx->last_slot = slot;
 
     const float c2 = ctx->cutoff_f * ctx->cutoff_f;   // float multiply, as in MDTraj
+    if ((ctx->atom_log2 > 0 || ctx->res_log2 > 0) && ctx->path == 0)
+        return fail(ctx, CMB_ERR_STATE, "hashed count tables are only used by the global-memory cell path");
     if (ctx->path == 0) {
         FrameParams p;
         memset(&p, 0, sizeof(p));
@@ -430,6 +438,8 @@ static int launch_frames(cmb_ctx* ctx, const FrameJob& job, int slot, cudaStream
     lj.counters = counters; lj.boundary = job.boundary; lj.boundary_cap = job.boundary_cap;
     lj.count_tests = ctx->count_tests;
     lj.all_roles = ctx->all_roles ? 1 : 0;
+    lj.atom_log2 = ctx->atom_log2; lj.res_log2 = ctx->res_log2; lj.hstats = ctx->d_hstats;
+    lj.ovf_list = ctx->d_ovf; lj.ovf_cap = ctx->ovf_cap;
     std::string err;
     int launches = 0;
     int rc = large_run(lj, ctx->large[slot], ctx->sm_count, stream, err, launches);
@@ -606,6 +616,99 @@ extern "C" int cmb_accumulate_host_gather(cmb_ctx* ctx, const float* h_xyz_full,
     }
     CK(cudaStreamSynchronize(ctx->streams[0]));
     CK(cudaStreamSynchronize(ctx->streams[1]));
+    return CMB_OK;
+}
+
+
+// ---------------------------------------------------------------------------------
+// hashed count tables
+// ---------------------------------------------------------------------------------
+extern "C" int cmb_set_table_mode(cmb_ctx* ctx, int atom_log2, int res_log2)
+{
+    if (!ctx) return CMB_ERR_ARG;
+    if (atom_log2 < 0 || atom_log2 > 31 || res_log2 < 0 || res_log2 > 31 || (atom_log2 > 0 && atom_log2 < 5) ||
+        (res_log2 > 0 && res_log2 < 5))
+        return fail(ctx, CMB_ERR_ARG, "table sizes must be 0 (dense) or 2^5 .. 2^31 slots");
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->d_hstats) {
+        CK(cudaMalloc(&ctx->d_hstats, 4 * sizeof(unsigned long long)));
+        CK(cudaMemset(ctx->d_hstats, 0, 4 * sizeof(unsigned long long)));
+    }
+    ctx->atom_log2 = atom_log2;
+    ctx->res_log2 = res_log2;
+    return CMB_OK;
+}
+
+extern "C" int cmb_hash_overflow_buffer(cmb_ctx* ctx, uint64_t* d_list, int64_t cap)
+{
+    if (!ctx || cap < 0 || (cap > 0 && !d_list)) return CMB_ERR_ARG;
+    ctx->d_ovf = reinterpret_cast<unsigned long long*>(d_list);
+    ctx->ovf_cap = cap;
+    return CMB_OK;
+}
+
+extern "C" int cmb_hash_add(cmb_ctx* ctx, uint64_t* d_slots, int log2_slots, const uint64_t* d_key1,
+                            const uint64_t* d_count, int64_t n, int which, void* stream)
+{
+    if (!ctx || !d_slots || log2_slots < 5 || log2_slots > 31 || n < 0 || which < 0 || which > 1) return CMB_ERR_ARG;
+    if (!ctx->d_hstats) return fail(ctx, CMB_ERR_STATE, "cmb_set_table_mode has not been called");
+    if (n == 0) return CMB_OK;
+    CK(cudaSetDevice(ctx->device));
+    const int grid = (int)std::min<long long>((n + 255) / 256, (long long)ctx->sm_count * 16);
+    k_hash_add<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<unsigned long long*>(d_slots),
+                                                        (1u << log2_slots) - 1u,
+                                                        reinterpret_cast<const unsigned long long*>(d_key1),
+                                                        reinterpret_cast<const unsigned long long*>(d_count), n,
+                                                        ctx->d_hstats, which);
+    CK(cudaGetLastError());
+    ctx->stats["kernel_launches"] += 1;
+    return CMB_OK;
+}
+
+extern "C" int cmb_hash_stats(cmb_ctx* ctx, int64_t* new_atom_keys, int64_t* new_res_keys, int64_t* overflow)
+{
+    if (!ctx) return CMB_ERR_ARG;
+    if (!ctx->d_hstats) return fail(ctx, CMB_ERR_STATE, "cmb_set_table_mode has not been called");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    unsigned long long h[4];
+    CK(cudaMemcpy(h, ctx->d_hstats, sizeof(h), cudaMemcpyDeviceToHost));
+    CK(cudaMemset(ctx->d_hstats, 0, sizeof(h)));
+    if (new_atom_keys) *new_atom_keys = (int64_t)h[0];
+    if (new_res_keys) *new_res_keys = (int64_t)h[1];
+    if (overflow) *overflow = (int64_t)h[2];
+    if (h[3]) return fail(ctx, CMB_ERR_LIMIT, "%llu entries could not be re-inserted into a hashed table", h[3]);
+    return CMB_OK;
+}
+
+extern "C" int cmb_export_hashed(cmb_ctx* ctx, const uint64_t* d_slots, int log2_slots, int64_t cap,
+                                 int64_t* d_idx, uint32_t* d_cnt, uint64_t* d_n, void* stream)
+{
+    if (!ctx || !d_slots || !d_n || log2_slots < 5 || log2_slots > 31) return CMB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const long long n_slots = 1ll << log2_slots;
+    const int grid = (int)std::min<long long>((n_slots + 255) / 256, (long long)ctx->sm_count * 16);
+    k_export_hashed<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const unsigned long long*>(d_slots), n_slots, cap, reinterpret_cast<long long*>(d_idx), d_cnt,
+        reinterpret_cast<unsigned long long*>(d_n));
+    CK(cudaGetLastError());
+    ctx->stats["kernel_launches"] += 1;
+    return CMB_OK;
+}
+
+extern "C" int cmb_hash_rehash(cmb_ctx* ctx, const uint64_t* d_src, int src_log2, uint64_t* d_dst, int dst_log2,
+                               void* stream)
+{
+    if (!ctx || !d_src || !d_dst || src_log2 < 5 || dst_log2 < src_log2 || dst_log2 > 31) return CMB_ERR_ARG;
+    if (!ctx->d_hstats) return fail(ctx, CMB_ERR_STATE, "cmb_set_table_mode has not been called");
+    CK(cudaSetDevice(ctx->device));
+    const long long n_src = 1ll << src_log2;
+    const int grid = (int)std::min<long long>((n_src + 255) / 256, (long long)ctx->sm_count * 16);
+    k_rehash<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(d_src), n_src,
+                                                      reinterpret_cast<unsigned long long*>(d_dst),
+                                                      (1u << dst_log2) - 1u, ctx->d_hstats);
+    CK(cudaGetLastError());
+    ctx->stats["kernel_launches"] += 1;
     return CMB_OK;
 }
 

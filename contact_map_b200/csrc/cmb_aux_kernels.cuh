@@ -5,6 +5,92 @@
 namespace cmb {
 
 // ---------------------------------------------------------------------------------
+// hashed count tables (cmb_frames_large.cuh): sparse export and growth
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_export_hashed(const unsigned long long* __restrict__ slots,
+                                                       long long n_slots, long long cap,
+                                                       long long* __restrict__ out_idx,
+                                                       unsigned int* __restrict__ out_cnt,
+                                                       unsigned long long* __restrict__ out_n)
+{
+    const int lane = threadIdx.x & 31;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long warp_first = (long long)blockIdx.x * blockDim.x + threadIdx.x - lane;
+    for (long long v0 = warp_first; v0 < n_slots; v0 += stride) {
+        const long long v = v0 + lane;
+        const unsigned long long s = v < n_slots ? __ldg(&slots[v]) : 0ull;
+        const bool have = (s & 0xffffffull) != 0ull;            // a claimed slot with count 0 is no contact
+        const unsigned m = __ballot_sync(0xffffffffu, have);
+        if (m == 0u) continue;
+        unsigned long long base = 0;
+        const int leader = __ffs(m) - 1;
+        if (lane == leader) base = atomicAdd(out_n, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (have) {
+            const unsigned long long w = base + __popc(m & ((1u << lane) - 1u));
+            if ((long long)w < cap) {
+                out_idx[w] = (long long)((s >> 24) - 1ull);
+                out_cnt[w] = (unsigned int)(s & 0xffffffull);
+            }
+        }
+    }
+}
+
+// re-insert every entry of `src` into the (larger, zero-filled) table `dst`
+__global__ void __launch_bounds__(256) k_rehash(const unsigned long long* __restrict__ src, long long n_src,
+                                                unsigned long long* __restrict__ dst, unsigned dst_mask,
+                                                unsigned long long* __restrict__ stats)
+{
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < n_src;
+         v += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long s = __ldg(&src[v]);
+        if (s == 0ull) continue;
+        const unsigned long long key1 = s >> 24;
+        unsigned long long k = key1;
+        k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+        unsigned h = (unsigned)k & dst_mask;
+        bool placed = false;
+        for (int probe = 0; probe < (1 << 14) && !placed; probe++) {
+            const unsigned long long old = atomicCAS(&dst[h], 0ull, s);      // keys are distinct in src
+            if (old == 0ull) placed = true;
+            else h = (h + 1u) & dst_mask;
+        }
+        if (!placed) atomicAdd(&stats[3], 1ull);
+    }
+}
+
+// slots[key1] += count for a list of distinct keys (parked hits after a table was grown)
+__global__ void __launch_bounds__(256) k_hash_add(unsigned long long* __restrict__ slots, unsigned mask,
+                                                  const unsigned long long* __restrict__ key1,
+                                                  const unsigned long long* __restrict__ count, long long n,
+                                                  unsigned long long* __restrict__ stats, int which)
+{
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < n;
+         v += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long k1 = key1[v];
+        unsigned long long k = k1;
+        k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+        unsigned h = (unsigned)k & mask;
+        bool placed = false;
+        for (int probe = 0; probe < (1 << 14) && !placed; probe++) {
+            unsigned long long cur = *(volatile unsigned long long*)&slots[h];
+            if (cur == 0ull) {
+                const unsigned long long old = atomicCAS(&slots[h], 0ull, k1 << 24);
+                if (old == 0ull) atomicAdd(&stats[which], 1ull);
+                cur = old == 0ull ? (k1 << 24) : old;
+            }
+            if ((cur >> 24) == k1) {
+                atomicAdd(&slots[h], count[v]);
+                placed = true;
+            } else {
+                h = (h + 1u) & mask;
+            }
+        }
+        if (!placed) atomicAdd(&stats[3], 1ull);
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // sparse export of a uint32 count table (result container of contact_map.py:724-744)
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_export_nonzero(const unsigned int* __restrict__ table,

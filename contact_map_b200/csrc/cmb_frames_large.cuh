@@ -57,6 +57,9 @@ struct LargeJob {
     unsigned long long* res_keys; long long res_cap;
     unsigned long long* counters; float4* boundary; long long boundary_cap; int count_tests;
     int all_roles;
+    int atom_log2, res_log2;        // hashed tables when > 0 (table pointers are uint64 slot arrays)
+    unsigned long long* hstats;
+    unsigned long long* ovf_list; long long ovf_cap;
 };
 
 // ----- traits + hit sink of the global-memory path -------------------------------------
@@ -105,6 +108,62 @@ struct LargeTraits {
     }
 };
 
+// ----- hashed count tables (north_star: "dense or hashed count matrix") -------------------------
+// Open addressing with linear probing over uint64 slots, slot = (key + 1) << 24 | count; an
+// all-zero slot is empty, so a zero-filled buffer is an empty table.  key = flat index of the
+// dense layout (lo * n + hi < 2^40), counts < 2^24 (checked on the host).  The pair universe of a
+// trajectory is a few tens of partners per atom, so the table is a few tens of MB and stays in
+// L2, where the dense [n][n] table of a 100k-atom system (40 GB) turns every hit into DRAM
+// traffic.
+constexpr int HT_COUNT_BITS = 24;
+constexpr int HT_MAX_PROBES = 1 << 14;
+
+__device__ __forceinline__ unsigned ht_hash(unsigned long long k)
+{
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdull;
+    k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull;
+    k ^= k >> 33;
+    return (unsigned)k;
+}
+
+// slot of `key1` (= key + 1), claiming an empty one if the key is new; 0xffffffff: table full
+// (the caller then parks the hit in the overflow list).  stats[which] counts the new keys.
+__device__ __forceinline__ unsigned ht_find_or_insert(unsigned long long* slots, unsigned mask,
+                                                      unsigned long long key1, unsigned long long* stats,
+                                                      int which)
+{
+    unsigned h = ht_hash(key1) & mask;
+    for (int probe = 0; probe < HT_MAX_PROBES; probe++) {
+        const unsigned long long s = *(volatile unsigned long long*)&slots[h];
+        unsigned long long k = s >> HT_COUNT_BITS;
+        if (k == 0ull) {
+            const unsigned long long old = atomicCAS(&slots[h], 0ull, key1 << HT_COUNT_BITS);
+            if (old == 0ull) {
+                atomicAdd(&stats[which], 1ull);
+                return h;
+            }
+            k = old >> HT_COUNT_BITS;
+        }
+        if (k == key1) return h;
+        h = (h + 1u) & mask;
+    }
+    return 0xffffffffu;
+}
+
+// A hit that found no slot is parked in the overflow list (stats[2] = entries requested); the
+// host grows the table and adds the parked hits afterwards, so nothing is ever dropped.  Atom
+// entry: key1; residue entry: 1 << 63 | key1 << 24 | (frame sequence number & 0xffffff) -- the
+// host removes duplicates of one residue pair within one frame before adding.
+struct HashOverflow {
+    unsigned long long* list;
+    long long cap;
+};
+__device__ __forceinline__ void ht_park(const HashOverflow& o, unsigned long long* stats, unsigned long long entry)
+{
+    const unsigned long long w = atomicAdd(&stats[2], 1ull);
+    if ((long long)w < o.cap) o.list[w] = entry;
+}
+
 // Residue exclusion + accounting of one hit: RED into the dense atom table; per-frame residue
 // de-duplication through the frame-stamp table (frames run in stream order, so
 // atomicMax(stamp, seq) < seq is the first hit of that residue pair in the current frame).  The
@@ -117,6 +176,10 @@ struct StampSink {
     unsigned int* atom_table;
     unsigned int* stamp;            // nullptr: residues not requested
     unsigned int* res_table;
+    // hashed tables (mask != 0): the table pointers above are uint64 slot arrays
+    unsigned int atom_mask, res_mask;
+    unsigned long long* hstats;     // [0] new atom keys, [1] new residue keys, [2] parked hits
+    HashOverflow ovf;
     unsigned long long* res_keys;
     long long res_cap;
     unsigned long long* counters;
@@ -126,7 +189,7 @@ struct StampSink {
     long long frame_id;
     // pipeline state of this lane
     unsigned int pend_old;
-    unsigned int pend_lo, pend_hi;
+    unsigned int pend_lo, pend_hi, pend_slot;
     int pending;
     int ra, rb;                     // compact residues of the pair handed to prepare()
 
@@ -134,7 +197,10 @@ struct StampSink {
     {
         if (pending && pend_old < seq) {
             const size_t slot = (size_t)pend_lo * n_res_c + (size_t)pend_hi;
-            if (res_table != nullptr) atomicAdd(&res_table[slot], 1u);
+            if (res_table != nullptr) {
+                if (res_mask) atomicAdd(reinterpret_cast<unsigned long long*>(res_table) + pend_slot, 1ull);
+                else atomicAdd(&res_table[slot], 1u);
+            }
             if (res_keys != nullptr) {
                 const unsigned long long w = atomicAdd(&counters[1], 1ull);
                 if ((long long)w < res_cap)
@@ -155,15 +221,35 @@ struct StampSink {
     __device__ __forceinline__ void account(int ia, int ib)
     {
         const int a = min(ia, ib), b = max(ia, ib);
-        if (atom_table != nullptr) atomicAdd(&atom_table[(size_t)a * (size_t)n + (size_t)b], 1u);
+        if (atom_table != nullptr) {
+            const unsigned long long flat = (unsigned long long)a * (unsigned long long)n + (unsigned long long)b;
+            if (atom_mask) {
+                unsigned long long* slots = reinterpret_cast<unsigned long long*>(atom_table);
+                const unsigned h = ht_find_or_insert(slots, atom_mask, flat + 1ull, hstats, 0);
+                if (h != 0xffffffffu) atomicAdd(&slots[h], 1ull);
+                else ht_park(ovf, hstats, flat + 1ull);
+            } else {
+                atomicAdd(&atom_table[flat], 1u);
+            }
+        }
         if (stamp == nullptr) return;
         resolve();                                   // consume the previous call's atomicMax
         const unsigned rlo = (unsigned)min(ra, rb), rhi = (unsigned)max(ra, rb);
         const unsigned slot32 = rlo * n_res_c + rhi;     // R_c^2 < 2^32 (checked on the host)
         const unsigned peers = __match_any_sync(__activemask(), slot32);
         if ((__ffs(peers) - 1) == (int)(threadIdx.x & 31)) {
-            pend_old = atomicMax(&stamp[(size_t)slot32], seq);
-            pend_lo = rlo; pend_hi = rhi;
+            unsigned where = slot32;                 // index into the stamp array
+            if (res_mask) {
+                where = ht_find_or_insert(reinterpret_cast<unsigned long long*>(res_table), res_mask,
+                                          (unsigned long long)slot32 + 1ull, hstats, 1);
+                if (where == 0xffffffffu) {
+                    ht_park(ovf, hstats, (1ull << 63) | (((unsigned long long)slot32 + 1ull) << 24) |
+                                             (unsigned long long)(seq & 0xffffffu));
+                    return;
+                }
+            }
+            pend_old = atomicMax(&stamp[(size_t)where], seq);
+            pend_lo = rlo; pend_hi = rhi; pend_slot = where;
             pending = 1;
         }
     }
@@ -388,7 +474,12 @@ inline int large_run(const LargeJob& job, LargeScratch& S, int sm_count, cudaStr
         err = "more than 65535 used residues: residue table index exceeds 32 bits";
         return -4;
     }
-    const size_t need_stamp = (size_t)job.n_res_c * (size_t)job.n_res_c;
+    if (job.res_log2 > 0 && job.res_table == nullptr && job.res_keys != nullptr) {
+        err = "per-frame residue keys need a residue table (dense or hashed) for the de-duplication";
+        return -1;
+    }
+    const size_t need_stamp = job.res_log2 > 0 ? ((size_t)1 << job.res_log2)
+                                               : (size_t)job.n_res_c * (size_t)job.n_res_c;
     if (want_res && S.stamp_elems < need_stamp) {
         cudaFree(S.d_stamp);
         S.d_stamp = nullptr;
@@ -421,6 +512,10 @@ inline int large_run(const LargeJob& job, LargeScratch& S, int sm_count, cudaStr
         StampSink sink;
         sink.meta = job.meta; sink.atom_table = job.atom_table;
         sink.stamp = want_res ? S.d_stamp : nullptr;
+        sink.atom_mask = job.atom_log2 > 0 ? (1u << job.atom_log2) - 1u : 0u;
+        sink.res_mask = job.res_log2 > 0 ? (1u << job.res_log2) - 1u : 0u;
+        sink.hstats = job.hstats; sink.pend_slot = 0u;
+        sink.ovf.list = job.ovf_list; sink.ovf.cap = job.ovf_cap;
         sink.res_table = job.res_table; sink.res_keys = job.res_keys; sink.res_cap = job.res_cap;
         sink.counters = job.counters; sink.seq = S.seq; sink.n = (unsigned)n;
         sink.n_res_c = (unsigned)job.n_res_c; sink.frame_id = job.frame0 + f;

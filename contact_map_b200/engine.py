@@ -30,6 +30,37 @@ def _stream_ptr(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+class HashTable(object):
+    """Hashed count table of the global-memory cell path (``cmb_set_table_mode``): 2^log2 uint64
+    slots, slot = (flat index + 1) << 24 | count, zero = empty.  ``used`` tracks the number of
+    distinct keys (the engine keeps the load below 0.7 by rehashing into a larger table: small
+    tables stay L2-resident, which is the point of hashing);
+    ``merged`` holds the (index, count) arrays after a multi-rank reduce."""
+
+    def __init__(self, log2, device):
+        self.log2 = int(log2)
+        self.slots = torch.zeros(1 << self.log2, dtype=torch.int64, device=device)
+        self.used = 0
+        self.merged = None
+
+    def numel(self):
+        return self.slots.numel()
+
+    def zero_(self):
+        self.slots.zero_()
+        self.used = 0
+        self.merged = None
+        return self
+
+
+def _table_ptr(t):
+    return _ptr(t.slots) if isinstance(t, HashTable) else _ptr(t)
+
+
+def _table_log2(t):
+    return t.log2 if isinstance(t, HashTable) else 0
+
+
 class ContactEngine(object):
     """One engine per (process, device).  Not thread safe."""
 
@@ -96,14 +127,138 @@ class ContactEngine(object):
         self.residue_map = rmap
         self.path_kind = int(self._L.cmb_path_kind(self._ctx))
 
-    def new_tables(self):
-        """Zeroed device count tables (int32 views of the uint32 tables of the ABI)."""
-        a, r = ctypes.c_int64(0), ctypes.c_int64(0)
-        self._check(self._L.cmb_table_sizes(self._ctx, ctypes.byref(a), ctypes.byref(r)),
-                    "cmb_table_sizes")
-        atom = torch.zeros(int(a.value), dtype=torch.int32, device=self.device)
-        res = torch.zeros(int(r.value), dtype=torch.int32, device=self.device)
+    # dense tables above this size are replaced by hashed ones (global-memory cell path only).
+    # Measured on the 100k-atom system (40 GB dense table): dense 6.3k frames/s, hashed 5.4k --
+    # the hashed insert is a dependent L2 round trip where the dense path issues a RED -- so dense
+    # stays the default while it fits comfortably in the 180 GB of a B200.
+    DENSE_LIMIT_BYTES = 1 << 36
+
+    def new_tables(self, hashed=None):
+        """Zeroed device count tables: dense int32 views of the uint32 tables of the ABI, or
+        (``hashed=True``; default for systems whose dense atom table would exceed 64 GiB)
+        :class:`HashTable` objects."""
+        n, rc = int(self.n_used), int(self.n_res_c)
+        if hashed is None:
+            hashed = self.path_kind == 1 and 4 * n * n > self.DENSE_LIMIT_BYTES
+        if hashed:
+            if self.path_kind != 1:
+                raise EngineError("hashed count tables are only used by the global-memory cell path")
+            atom = HashTable(max(10, int(np.ceil(np.log2(32.0 * n)))), self.device)
+            if 4 * rc * rc > self.DENSE_LIMIT_BYTES // 4:
+                res = HashTable(max(10, int(np.ceil(np.log2(64.0 * rc)))), self.device)
+            else:
+                res = torch.zeros(rc * rc, dtype=torch.int32, device=self.device)
+            return atom, res
+        atom = torch.zeros(n * n, dtype=torch.int32, device=self.device)
+        res = torch.zeros(rc * rc, dtype=torch.int32, device=self.device)
         return atom, res
+
+    # ---- hashed tables: mode switch, frame schedule, growth ---------------------------
+    def _set_table_mode(self, atom_table, res_table):
+        mode = (_table_log2(atom_table), _table_log2(res_table))
+        if mode != getattr(self, "_table_mode", (0, 0)):
+            self._check(self._L.cmb_set_table_mode(self._ctx, mode[0], mode[1]), "cmb_set_table_mode")
+            self._table_mode = mode
+        if mode != (0, 0) and getattr(self, "_ovf", None) is None:
+            self._ovf = torch.zeros(self.OVERFLOW_ENTRIES, dtype=torch.int64, device=self.device)
+            self._check(self._L.cmb_hash_overflow_buffer(self._ctx, _ptr(self._ovf), self.OVERFLOW_ENTRIES),
+                        "cmb_hash_overflow_buffer")
+        return mode != (0, 0)
+
+    @staticmethod
+    def _hashed_schedule(n_frames, cap=256):
+        """Frame blocks 1, 1, 2, 4, ... (at most ``cap``): the tables are checked, and grown when
+        more than half full, after each block; the pair universe of a trajectory saturates after a
+        few frames, so a block never comes close to filling a table that was at most half full."""
+        out, start, size = [], 0, 1
+        while start < n_frames:
+            stop = min(n_frames, start + size)
+            out.append((start, stop))
+            start = stop
+            size = min(cap, max(1, 2 * size if len(out) > 1 else 1))
+        return out
+
+    def _hash_presize(self, xyz1, box1, atom_table, res_table):
+        """Fresh hashed tables are sized from the exact pair counts of the first frame (a counting
+        pass of the key kernel that writes nothing), so that the first block cannot overflow."""
+        if not (isinstance(atom_table, HashTable) and atom_table.used == 0):
+            return
+        self._set_table_mode(None, None)
+        counts = self._frame_contacts_once(xyz1, box1, 0, None, 0, None, 0, None, None,
+                                           count_only=(True, False))
+        # (a frame has at most as many residue pairs as atom pairs, usually far fewer: the residue
+        # table keeps its default size, 64 slots per residue, unless even that bound is smaller)
+        for t, first in ((atom_table, int(counts[0])),):
+            if isinstance(t, HashTable) and t.used == 0 and 3 * first > t.numel():
+                log2 = t.log2
+                while 3 * first > (1 << log2):
+                    log2 += 1
+                t.slots, t.log2 = torch.zeros(1 << log2, dtype=torch.int64, device=self.device), log2
+        self._set_table_mode(atom_table, res_table)
+
+    def _hash_presize_host(self, xyz1_np, box_np, atom_table, res_table):
+        xyz1 = torch.as_tensor(xyz1_np, device=self.device)
+        box1 = None if box_np is None else torch.as_tensor(box_np[:1], device=self.device)
+        self._hash_presize(xyz1, box1, atom_table, res_table)
+
+    OVERFLOW_ENTRIES = 1 << 22          # parked hits per block (32 MiB list)
+
+    def _grow(self, t, min_slots):
+        log2 = t.log2
+        while (1 << log2) < min_slots:
+            log2 += 1
+        if log2 == t.log2:
+            return
+        bigger = torch.zeros(1 << log2, dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self._L.cmb_hash_rehash(self._ctx, _ptr(t.slots), t.log2, _ptr(bigger), log2,
+                                                _stream_ptr(self.device)), "cmb_hash_rehash")
+        torch.cuda.current_stream(self.device).synchronize()
+        t.slots, t.log2 = bigger, log2
+
+    def _hash_maintain(self, tables):
+        """After a block of frames: bookkeeping of the distinct keys, growth (load <= 0.7), and the
+        hits that found their table full (parked in the overflow list by the kernel): the table
+        is grown and they are added, per-frame duplicates of a residue pair removed first."""
+        a, r, o = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
+        self._check(self._L.cmb_hash_stats(self._ctx, ctypes.byref(a), ctypes.byref(r), ctypes.byref(o)),
+                    "cmb_hash_stats")
+        parked = int(o.value)
+        if parked > self.OVERFLOW_ENTRIES:
+            raise EngineError("%d hits overflowed the hashed count tables and their overflow list "
+                              "(hits were lost); use larger tables" % parked)
+        adds = [None, None]
+        if parked:
+            entries = self._ovf[:parked]
+            is_res = entries < 0                                  # bit 63
+            atoms = entries[~is_res]
+            if atoms.numel():
+                adds[0] = torch.unique(atoms, return_counts=True)
+            res = entries[is_res]
+            if res.numel():
+                per_frame = torch.unique(res)                     # one entry per (pair, frame)
+                keys = (per_frame & 0x7fffffffffffffff) >> 24
+                adds[1] = torch.unique(keys, return_counts=True)
+        for which, (t, new) in enumerate(zip(tables, (a.value, r.value))):
+            if not isinstance(t, HashTable):
+                continue
+            t.used += int(new)
+            t.merged = None
+            extra = 0 if adds[which] is None else int(adds[which][0].numel())
+            if 10 * (t.used + extra) > 7 * t.numel():            # load > 0.7: grow to load <= 0.45
+                self._grow(t, int((t.used + extra) / 0.45) + 1)
+            if extra:
+                keys, counts = adds[which]
+                with torch.cuda.device(self.device):
+                    self._check(self._L.cmb_hash_add(self._ctx, _ptr(t.slots), t.log2, _ptr(keys.contiguous()),
+                                                     _ptr(counts.contiguous()), extra, which,
+                                                     _stream_ptr(self.device)), "cmb_hash_add")
+        if parked:
+            self._check(self._L.cmb_hash_stats(self._ctx, ctypes.byref(a), ctypes.byref(r), ctypes.byref(o)),
+                        "cmb_hash_stats")
+            for t, new in zip(tables, (a.value, r.value)):
+                if isinstance(t, HashTable):
+                    t.used += int(new)
 
     # ------------------------------------------------------------------
     def _dev_inputs(self, xyz, box):
@@ -123,6 +278,18 @@ class ContactEngine(object):
     def accumulate(self, xyz, box, atom_table, res_table):
         """Add the frames of a DEVICE trajectory into the tables (asynchronous)."""
         xyz, box = self._dev_inputs(xyz, box)
+        if self._set_table_mode(atom_table, res_table):
+            # hashed tables: block schedule with growth checks in between (synchronous)
+            self._hash_presize(xyz[:1], None if box is None else box[:1], atom_table, res_table)
+            for a, b in self._hashed_schedule(xyz.shape[0]):
+                with torch.cuda.device(self.device):
+                    self._set_table_mode(atom_table, res_table)      # growth changes the sizes
+                    self._check(self._L.cmb_accumulate(self._ctx, _ptr(xyz[a:b]),
+                                                       _ptr(None if box is None else box[a:b]), b - a,
+                                                       _table_ptr(atom_table), _table_ptr(res_table),
+                                                       _stream_ptr(self.device)), "cmb_accumulate")
+                self._hash_maintain((atom_table, res_table))
+            return
         with torch.cuda.device(self.device):
             self._check(self._L.cmb_accumulate(self._ctx, _ptr(xyz), _ptr(box), xyz.shape[0],
                                                _ptr(atom_table), _ptr(res_table),
@@ -142,6 +309,16 @@ class ContactEngine(object):
             if box_np.size != xyz_np.shape[0] * 9:
                 raise ValueError("box must have shape [n_frames, 3, 3]")
         torch.cuda.current_stream(self.device).synchronize()   # tables may still be zero-filling
+        if self._set_table_mode(atom_table, res_table):
+            self._hash_presize_host(xyz_np[:1], box_np, atom_table, res_table)
+            for a, b in self._hashed_schedule(xyz_np.shape[0]):
+                self._set_table_mode(atom_table, res_table)
+                self._check(self._L.cmb_accumulate_host(self._ctx, _ptr(xyz_np[a:b]),
+                                                        _ptr(None if box_np is None else box_np[a:b]),
+                                                        b - a, int(chunk_frames), _table_ptr(atom_table),
+                                                        _table_ptr(res_table)), "cmb_accumulate_host")
+                self._hash_maintain((atom_table, res_table))
+            return
         self._check(self._L.cmb_accumulate_host(self._ctx, _ptr(xyz_np), _ptr(box_np),
                                                 xyz_np.shape[0], int(chunk_frames),
                                                 _ptr(atom_table), _ptr(res_table)),
@@ -163,6 +340,16 @@ class ContactEngine(object):
                                    or box_np.size != xyz_np.shape[0] * 9):
             raise TypeError("box must be C-contiguous float32 [n_frames, 3, 3]")
         torch.cuda.current_stream(self.device).synchronize()
+        if self._set_table_mode(atom_table, res_table):
+            self._hash_presize_host(np.ascontiguousarray(xyz_np[:1][:, used]), box_np, atom_table, res_table)
+            for a, b in self._hashed_schedule(xyz_np.shape[0]):
+                self._set_table_mode(atom_table, res_table)
+                self._check(self._L.cmb_accumulate_host_gather(
+                    self._ctx, _ptr(xyz_np[a:b]), xyz_np.shape[1], _ptr(used),
+                    _ptr(None if box_np is None else box_np[a:b]), b - a, int(chunk_frames), int(n_threads),
+                    _table_ptr(atom_table), _table_ptr(res_table)), "cmb_accumulate_host_gather")
+                self._hash_maintain((atom_table, res_table))
+            return
         self._check(self._L.cmb_accumulate_host_gather(self._ctx, _ptr(xyz_np), xyz_np.shape[1], _ptr(used),
                                                        _ptr(box_np), xyz_np.shape[0], int(chunk_frames),
                                                        int(n_threads), _ptr(atom_table), _ptr(res_table)),
@@ -186,8 +373,11 @@ class ContactEngine(object):
         jobs = []
         with torch.cuda.device(self.device):
             for t in tables:
+                if isinstance(t, HashTable) and t.merged is not None:
+                    jobs.append(None)
+                    continue
                 numel = t.numel()
-                cap = hints.get(numel)
+                cap = t.used if isinstance(t, HashTable) else hints.get(numel)
                 if cap is None:
                     cap = int(torch.count_nonzero(t).item())
                 cap = max(16, min(numel, cap + cap // 4 + 1024))
@@ -195,6 +385,9 @@ class ContactEngine(object):
             stream.synchronize()
             out = []
             for slot, (t, job) in enumerate(zip(tables, jobs)):
+                if job is None:
+                    out.append(t.merged)
+                    continue
                 n = int(job["h_n"][0])
                 if n > job["cap"]:            # capacity guess too small: exact retry
                     job = self._export_launch(t, n, slot)
@@ -225,9 +418,14 @@ class ContactEngine(object):
                 pool.clear()
             pool[(table.numel(), slot)] = buf
         buf["d_n"].zero_()
-        self._check(self._L.cmb_export_nonzero(self._ctx, _ptr(table), table.numel(), buf["cap"],
-                                               _ptr(buf["d_idx"]), _ptr(buf["d_cnt"]), _ptr(buf["d_n"]),
-                                               _stream_ptr(self.device)), "cmb_export_nonzero")
+        if isinstance(table, HashTable):
+            self._check(self._L.cmb_export_hashed(self._ctx, _ptr(table.slots), table.log2, buf["cap"],
+                                                  _ptr(buf["d_idx"]), _ptr(buf["d_cnt"]), _ptr(buf["d_n"]),
+                                                  _stream_ptr(self.device)), "cmb_export_hashed")
+        else:
+            self._check(self._L.cmb_export_nonzero(self._ctx, _ptr(table), table.numel(), buf["cap"],
+                                                   _ptr(buf["d_idx"]), _ptr(buf["d_cnt"]), _ptr(buf["d_n"]),
+                                                   _stream_ptr(self.device)), "cmb_export_nonzero")
         buf["h_n"].copy_(buf["d_n"], non_blocking=True)
         buf["h_idx"].copy_(buf["d_idx"], non_blocking=True)
         buf["h_cnt"].copy_(buf["d_cnt"], non_blocking=True)
@@ -244,6 +442,9 @@ class ContactEngine(object):
         n_frames = xyz.shape[0]
         cap_a = int(cap_hint or max(1024, n_frames * 64)) if want_atoms else 0
         cap_r = int(cap_hint or max(1024, n_frames * 64)) if want_residues else 0
+        if isinstance(atom_table, HashTable) or isinstance(res_table, HashTable):
+            raise NotImplementedError("frame_contacts accumulates into dense tables only")
+        self._set_table_mode(None, None)
         if atom_table is not None or res_table is not None:
             # tables must only be touched once: size the key buffers with a dry run first
             counts = self._frame_contacts_once(xyz, box, frame0, None, 0, None, 0, None, None,
@@ -296,6 +497,7 @@ class ContactEngine(object):
         Returns a structured numpy array with fields frame, a, b (int32) and d2 (float32).
         """
         xyz, box = self._dev_inputs(xyz, box)
+        self._set_table_mode(None, None)
         dt = np.dtype([("frame", np.int32), ("a", np.int32), ("b", np.int32), ("d2", np.float32)])
         while True:
             rec = torch.zeros(cap * 4, dtype=torch.int32, device=self.device)

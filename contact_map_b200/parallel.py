@@ -40,6 +40,17 @@ def reduce_tables(tables, group=None):
     int32 view exact for uint32 counts."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return tables
+    hashed = [t for t in tables if hasattr(t, "slots")]
+    if hashed:
+        # hashed tables have rank-dependent layouts: gather the sparse exports and merge them
+        # (one all-gather per table; the merged (index, count) arrays become the table's export)
+        from .engine import get_engine
+        engine = get_engine(hashed[0].slots.device)
+        for t, (idx, cnt) in zip(hashed, engine.export_many(hashed)):
+            t.merged = merge_sparse(idx, cnt, t.slots.device, group)
+        tables = [t for t in tables if not hasattr(t, "slots")]
+        if not tables:
+            return hashed
     flat = torch.cat([t.reshape(-1) for t in tables]) if len(tables) > 1 else tables[0].reshape(-1)
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     if len(tables) > 1:
@@ -48,6 +59,28 @@ def reduce_tables(tables, group=None):
             t.copy_(flat[offset:offset + t.numel()].reshape(t.shape))
             offset += t.numel()
     return tables
+
+
+def merge_sparse(idx, cnt, device, group=None):
+    """Sum sparse (flat index, count) lists over all ranks: all-gather + sort + segment sum.
+    Returns (index int64[], count uint32[]) sorted by index, identical on every rank."""
+    w = dist.get_world_size(group)
+    li = torch.as_tensor(np.ascontiguousarray(idx, dtype=np.int64), device=device)
+    lc = torch.as_tensor(np.ascontiguousarray(cnt).astype(np.int64), device=device)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(w)]
+    dist.all_gather(sizes, torch.tensor([li.numel()], dtype=torch.int64, device=device), group=group)
+    sizes = [int(x.item()) for x in sizes]
+    cap = max(max(sizes), 1)
+    packed = torch.zeros((2, cap), dtype=torch.int64, device=device)
+    packed[0, :li.numel()] = li
+    packed[1, :lc.numel()] = lc
+    parts = [torch.empty((2, cap), dtype=torch.int64, device=device) for _ in range(w)]
+    dist.all_gather(parts, packed, group=group)
+    all_idx = torch.cat([p[0, :k] for p, k in zip(parts, sizes)])
+    all_cnt = torch.cat([p[1, :k] for p, k in zip(parts, sizes)])
+    uniq, inverse = torch.unique(all_idx, sorted=True, return_inverse=True)
+    total = torch.zeros(uniq.numel(), dtype=torch.int64, device=device).scatter_add_(0, inverse, all_cnt)
+    return uniq.cpu().numpy(), total.cpu().numpy().astype(np.uint32)
 
 
 def reduce_frame_count(n_frames, device, group=None):

@@ -104,6 +104,31 @@ int cmb_frame_contacts(cmb_ctx* ctx, const float* d_xyz, const float* d_box, int
                        uint64_t* d_res_keys, int64_t res_cap, uint64_t* d_counts,
                        uint32_t* d_atom_table, uint32_t* d_res_table, void* stream);
 
+/*
+ * Hashed count tables (north_star: "dense or hashed count matrix") for systems whose dense
+ * [n_used][n_used] table would not stay in L2 (a 100k-atom system: 40 GB): open addressing over
+ * uint64 slots, slot = (flat index + 1) << 24 | count, flat index = lo * n_used + hi as in the dense
+ * layout; a zero-filled buffer is an empty table.  After cmb_set_table_mode(ctx, a, r) with a, r > 0
+ * the d_atom_table / d_res_table arguments of cmb_accumulate*, cmb_frame_contacts are such slot
+ * arrays of 2^a / 2^r slots (0 = dense uint32 table).  Global-memory cell path only.  Counts are
+ * limited to 2^24 - 1 frames per table.  A hit that finds no free slot is PARKED in the caller's
+ * overflow list (cmb_hash_overflow_buffer; atom entry = flat index + 1, residue entry =
+ * 1 << 63 | (flat index + 1) << 24 | frame sequence number & 0xffffff, to be de-duplicated per
+ * frame); cmb_hash_stats returns and resets the number of new keys and of parked hits since the
+ * last call (it synchronises the device).  The caller grows the table (cmb_hash_rehash into a
+ * larger zero-filled buffer) and adds the parked hits with cmb_hash_add(keys + 1, counts); parked
+ * hits beyond the list capacity are lost, which the caller must treat as an error.
+ */
+int cmb_set_table_mode(cmb_ctx* ctx, int atom_log2, int res_log2);
+int cmb_hash_overflow_buffer(cmb_ctx* ctx, uint64_t* d_list, int64_t cap);
+int cmb_hash_stats(cmb_ctx* ctx, int64_t* new_atom_keys, int64_t* new_res_keys, int64_t* overflow);
+int cmb_hash_add(cmb_ctx* ctx, uint64_t* d_slots, int log2_slots, const uint64_t* d_key1,
+                 const uint64_t* d_count, int64_t n, int which, void* stream);
+int cmb_export_hashed(cmb_ctx* ctx, const uint64_t* d_slots, int log2_slots, int64_t cap,
+                      int64_t* d_idx, uint32_t* d_cnt, uint64_t* d_n, void* stream);
+int cmb_hash_rehash(cmb_ctx* ctx, const uint64_t* d_src, int src_log2, uint64_t* d_dst, int dst_log2,
+                    void* stream);
+
 /* In-place ascending radix sort of 64-bit keys (frame-major, then lo, then hi). */
 int cmb_sort_keys(cmb_ctx* ctx, uint64_t* d_keys, int64_t n, void* stream);
 

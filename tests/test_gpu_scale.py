@@ -69,6 +69,54 @@ def test_large_path_forced_on_small_systems(engine, box_kind):
     assert np.array_equal(results[0][0], results[1][0]) and np.array_equal(results[0][1], results[1][1])
 
 
+@pytest.mark.parametrize("box_kind", ["triclinic", "none"])
+def test_hashed_tables_match_dense(engine, box_kind):
+    """Hashed count tables (cmb_set_table_mode) of the global-memory cell path: same counts as
+    the oracle's dense tables, through growth (tiny initial tables are rehashed several times),
+    through the host entry point, and mixed with a dense residue table."""
+    from contact_map_b200.engine import HashTable
+    rng = np.random.default_rng(78)
+    system = synth.random_system(rng, 900, n_chains=2, box_kind=box_kind, extent=2.6)
+    res, chain, role = system_arrays(system)
+    n_frames = 7
+    xyz = system.frames(0, n_frames)
+    box = None if system.box is None else np.broadcast_to(system.box, (n_frames, 3, 3)).copy()
+    ref_atom, ref_res = clib.accumulate_dense(xyz, box, 0.45, res, chain, role, 2, system.topology.n_residues)
+    engine.set_option("force_path", 1)
+    try:
+        engine.set_system(res, chain, role, 0.45, 2)
+        rmap = engine.residue_map
+        want_res = ref_res[np.ix_(rmap, rmap)]
+        d_xyz = torch.as_tensor(xyz, device=engine.device)
+        d_box = None if box is None else torch.as_tensor(box, device=engine.device)
+        for res_hashed, host in ((True, False), (False, False), (True, True)):
+            atom_t = HashTable(5, engine.device)                 # 32 slots: forces repeated growth
+            res_t = HashTable(5, engine.device) if res_hashed else engine.new_tables(hashed=False)[1]
+            if host:
+                engine.accumulate_host(xyz, box, atom_t, res_t, chunk_frames=2)
+            else:
+                engine.accumulate(d_xyz, d_box, atom_t, res_t)
+            assert atom_t.log2 > 5 and atom_t.used == np.count_nonzero(ref_atom)
+            assert 10 * atom_t.used <= 7 * atom_t.numel()
+            (idx, cnt), (ridx, rcnt) = engine.export_many([atom_t, res_t])
+            assert np.all(np.diff(idx) > 0)
+            assert np.array_equal(dense_from_export(idx, cnt, 900), ref_atom)
+            assert np.array_equal(dense_from_export(ridx, rcnt, engine.n_res_c), want_res)
+        # the default for this size stays dense; hashed=True gives sensibly sized tables
+        a, r = engine.new_tables()
+        assert isinstance(a, torch.Tensor) and isinstance(r, torch.Tensor)
+        a, r = engine.new_tables(hashed=True)
+        assert isinstance(a, HashTable) and a.numel() >= 32 * 900
+    finally:
+        engine.set_option("force_path", -1)
+    # the fused path refuses hashed tables loudly
+    engine.set_system(res, chain, role, 0.45, 2)
+    assert engine.path_kind == 0
+    with pytest.raises(Exception):
+        engine.accumulate(d_xyz, d_box, HashTable(10, engine.device), engine.new_tables()[1])
+    engine._set_table_mode(None, None)
+
+
 def test_large_system_matches_oracle(engine):
     """n_used > 6144: S3-like solvated triclinic system (12 000 atoms), two frames."""
     system = synth.solvated_triclinic(n_atoms=12000, lattice=23)
@@ -85,14 +133,14 @@ def test_large_system_matches_oracle(engine):
         sel = frame == f
         assert np.array_equal(np.stack([lo[sel], hi[sel]], axis=1), want)
         assert len(want) > 50000
-    # tables == sum of the per-frame keys
-    atom_t, res_t = engine.new_tables()
-    engine.accumulate(xyz, box, atom_t, res_t)
-    assert int(atom_t.sum().item()) == len(akeys)
-    assert int(res_t.sum().item()) == len(rkeys)
-    idx, cnt = engine.export_nonzero(atom_t)
+    # tables == sum of the per-frame keys, dense and hashed
     flat, counts = np.unique(lo * n + hi, return_counts=True)
-    assert np.array_equal(idx, flat) and np.array_equal(cnt, counts.astype(np.uint32))
+    for hashed in (False, True):
+        atom_t, res_t = engine.new_tables(hashed=hashed)
+        engine.accumulate(xyz, box, atom_t, res_t)
+        (idx, cnt), (ridx, rcnt) = engine.export_many([atom_t, res_t])
+        assert int(cnt.sum()) == len(akeys) and int(rcnt.sum()) == len(rkeys)
+        assert np.array_equal(idx, flat) and np.array_equal(cnt, counts.astype(np.uint32))
 
 
 def test_boundary_report_matches_oracle(engine):

@@ -53,8 +53,11 @@ def _worker(rank, world, port, out_dir):
         total_frames = parallel.reduce_frame_count(mine, torch.device("cpu"))
         all_keys = parallel.gather_keys(np.sort(np.concatenate(keys)) if keys else np.empty(0, np.uint64),
                                         torch.device("cpu"))
+        # hashed tables are reduced through their sparse exports (parallel.merge_sparse)
+        flat = np.flatnonzero(atom.reshape(-1))
+        m_idx, m_cnt = parallel.merge_sparse(flat, atom.reshape(-1)[flat], torch.device("cpu"))
         np.savez(os.path.join(out_dir, "rank%d.npz" % rank), atom=t_atom.numpy(), res=t_res.numpy(),
-                 frames=total_frames, keys=all_keys.view(np.int64))
+                 frames=total_frames, keys=all_keys.view(np.int64), m_idx=m_idx, m_cnt=m_cnt)
     finally:
         dist.destroy_process_group()
 
@@ -83,4 +86,7 @@ def test_two_rank_reduce_equals_single(tmp_path):
         assert np.array_equal(got["res"].view(np.uint32).reshape(resc.shape), resc)
         assert int(got["frames"]) == 7
         assert np.array_equal(got["keys"].view(np.uint64), want_keys)
+        want_flat = np.flatnonzero(atom.reshape(-1))
+        assert np.array_equal(got["m_idx"], want_flat)
+        assert np.array_equal(got["m_cnt"], atom.reshape(-1)[want_flat])
     assert atom.sum() > 0

@@ -44,7 +44,7 @@ def main():
         torch.cuda.synchronize()
         print("%s: %d frames in %.3f ms -> %.0f frames/s" % (which, n_frames, e0.elapsed_time(e1),
                                                             n_frames / e0.elapsed_time(e1) * 1e3))
-    print("nonzero atom pairs:", int(torch.count_nonzero(atom_t)))
+    print("nonzero atom pairs:", len(engine.export_nonzero(atom_t)[0]))
 
 
 if __name__ == "__main__":
