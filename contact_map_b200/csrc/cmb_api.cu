@@ -688,7 +688,7 @@ extern "C" int cmb_export_hashed(cmb_ctx* ctx, const uint64_t* d_slots, int log2
     CK(cudaSetDevice(ctx->device));
     const long long n_slots = 1ll << log2_slots;
     const int grid = (int)std::min<long long>((n_slots + 255) / 256, (long long)ctx->sm_count * 16);
-    k_export_hashed<<<grid, 256, 0, (cudaStream_t)stream>>>(
+    k_export_hashed<false><<<grid, 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const unsigned long long*>(d_slots), n_slots, cap, reinterpret_cast<long long*>(d_idx), d_cnt,
         reinterpret_cast<unsigned long long*>(d_n));
     CK(cudaGetLastError());
@@ -785,11 +785,43 @@ extern "C" int cmb_export_nonzero(cmb_ctx* ctx, const uint32_t* d_table, int64_t
     const long long maxb = (long long)ctx->sm_count * 8;
     if (blocks > maxb) blocks = maxb;
     if (blocks < 1) blocks = 1;
-    k_export_nonzero<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+    k_export_nonzero<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         d_table, n_elems, cap, (long long*)d_idx, d_cnt, (unsigned long long*)d_n);
     CK(cudaGetLastError());
     ctx->stats["kernel_launches"] += 1;
     return CMB_OK;
+}
+
+// Sorted sparse export: d_packed[cap] receives (flat index << 24 | count) of the non-zero entries
+// in ascending index order, followed by 0xff..ff padding; d_n[0] = entries found (entries beyond
+// cap are dropped: retry with a larger buffer), d_n[1] != 0 if a count did not fit 24 bits.
+// log2_slots > 0: d_table is a hashed table of 2^log2_slots uint64 slots, else a dense uint32 table.
+extern "C" int cmb_export_sorted(cmb_ctx* ctx, const void* d_table, int64_t n_elems, int log2_slots, int64_t cap,
+                                 uint64_t* d_packed, uint64_t* d_n, void* stream)
+{
+    if (!ctx) return CMB_ERR_ARG;
+    if (!d_table || !d_packed || !d_n || n_elems < 0 || cap < 1) return fail(ctx, CMB_ERR_ARG, "bad export arguments");
+    if (((uintptr_t)d_table & 15) != 0) return fail(ctx, CMB_ERR_ARG, "table must be 16-byte aligned");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemsetAsync(d_packed, 0xff, (size_t)cap * 8, st));
+    CK(cudaMemsetAsync(d_n, 0, 16, st));
+    if (log2_slots > 0) {
+        const long long n_slots = 1ll << log2_slots;
+        const int grid = (int)std::min<long long>((n_slots + 255) / 256, (long long)ctx->sm_count * 16);
+        k_export_hashed<true><<<grid, 256, 0, st>>>(reinterpret_cast<const unsigned long long*>(d_table), n_slots, cap,
+                                                    reinterpret_cast<long long*>(d_packed), nullptr,
+                                                    reinterpret_cast<unsigned long long*>(d_n));
+    } else if (n_elems > 0) {
+        long long blocks = std::min<long long>((n_elems / 4 + 255) / 256, (long long)ctx->sm_count * 8);
+        if (blocks < 1) blocks = 1;
+        k_export_nonzero<true><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const unsigned int*>(d_table), n_elems, cap,
+                                                                 reinterpret_cast<long long*>(d_packed), nullptr,
+                                                                 reinterpret_cast<unsigned long long*>(d_n));
+    }
+    CK(cudaGetLastError());
+    ctx->stats["kernel_launches"] += 1;
+    return cmb_sort_keys(ctx, d_packed, cap, stream);
 }
 
 extern "C" int cmb_gather_atoms(cmb_ctx* ctx, const float* d_xyz_full, int64_t n_frames, int n_total,

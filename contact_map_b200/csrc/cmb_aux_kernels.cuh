@@ -7,6 +7,8 @@ namespace cmb {
 // ---------------------------------------------------------------------------------
 // hashed count tables (cmb_frames_large.cuh): sparse export and growth
 // ---------------------------------------------------------------------------------
+// PACKED: out_idx receives (flat index << 24 | count) and out_cnt is unused (cmb_export_sorted)
+template <bool PACKED>
 __global__ void __launch_bounds__(256) k_export_hashed(const unsigned long long* __restrict__ slots,
                                                        long long n_slots, long long cap,
                                                        long long* __restrict__ out_idx,
@@ -29,8 +31,12 @@ __global__ void __launch_bounds__(256) k_export_hashed(const unsigned long long*
         if (have) {
             const unsigned long long w = base + __popc(m & ((1u << lane) - 1u));
             if ((long long)w < cap) {
-                out_idx[w] = (long long)((s >> 24) - 1ull);
-                out_cnt[w] = (unsigned int)(s & 0xffffffull);
+                if (PACKED) {
+                    out_idx[w] = (long long)(s - (1ull << 24));
+                } else {
+                    out_idx[w] = (long long)((s >> 24) - 1ull);
+                    out_cnt[w] = (unsigned int)(s & 0xffffffull);
+                }
             }
         }
     }
@@ -93,6 +99,9 @@ __global__ void __launch_bounds__(256) k_hash_add(unsigned long long* __restrict
 // ---------------------------------------------------------------------------------
 // sparse export of a uint32 count table (result container of contact_map.py:724-744)
 // ---------------------------------------------------------------------------------
+// PACKED: out_idx receives (flat index << 24 | count), out_cnt is unused and out_n[1] is set when
+// a count does not fit 24 bits (cmb_export_sorted then reports CMB_ERR_LIMIT)
+template <bool PACKED>
 __global__ void __launch_bounds__(256) k_export_nonzero(const unsigned int* __restrict__ table,
                                                         long long n_elems, long long cap,
                                                         long long* __restrict__ out_idx,
@@ -129,8 +138,13 @@ __global__ void __launch_bounds__(256) k_export_nonzero(const unsigned int* __re
         for (int k = 0; k < 4; k++) {
             if (vals[k]) {
                 if ((long long)w < cap) {
-                    out_idx[w] = v * 4 + k;
-                    out_cnt[w] = vals[k];
+                    if (PACKED) {
+                        out_idx[w] = ((v * 4 + k) << 24) | (long long)(vals[k] & 0xffffffu);
+                        if (vals[k] >> 24) out_n[1] = 1ull;
+                    } else {
+                        out_idx[w] = v * 4 + k;
+                        out_cnt[w] = vals[k];
+                    }
                 }
                 w++;
             }
@@ -142,7 +156,15 @@ __global__ void __launch_bounds__(256) k_export_nonzero(const unsigned int* __re
             const unsigned val = table[e];
             if (val) {
                 const unsigned long long w = atomicAdd(out_n, 1ull);
-                if ((long long)w < cap) { out_idx[w] = e; out_cnt[w] = val; }
+                if ((long long)w < cap) {
+                    if (PACKED) {
+                        out_idx[w] = (e << 24) | (long long)(val & 0xffffffu);
+                        if (val >> 24) out_n[1] = 1ull;
+                    } else {
+                        out_idx[w] = e;
+                        out_cnt[w] = val;
+                    }
+                }
             }
         }
     }

@@ -362,10 +362,11 @@ class ContactEngine(object):
     def export_many(self, tables):
         """Sparse export of several count tables with ONE host synchronisation.
 
-        Every table is scanned by ``cmb_export_nonzero`` into capacity-sized device buffers; the
-        counters and the buffers are copied to pinned host memory asynchronously and the stream
-        is synchronised once.  Capacities come from the previous export of a table of the same
-        size (first use: ``count_nonzero``); an overflow triggers one exact retry.
+        Every table is scanned by ``cmb_export_sorted`` into a capacity-sized device buffer of
+        packed (flat index << 24 | count) words, radix-sorted on the device and copied to pinned
+        host memory asynchronously; the stream is synchronised once.  Capacities come from the
+        previous export of a table of the same size (first use: ``count_nonzero``); an overflow
+        triggers one exact retry; counts that do not fit 24 bits fall back to the unpacked export.
         Returns [(flat index int64[], count uint32[]), ...], each sorted by index.
         """
         hints = self.__dict__.setdefault("_export_hint", {})
@@ -388,16 +389,18 @@ class ContactEngine(object):
                 if job is None:
                     out.append(t.merged)
                     continue
-                n = int(job["h_n"][0])
+                n, wide = int(job["h_n"][0]), int(job["h_n"][1])
+                if wide:
+                    out.append(self._export_unpacked(t))
+                    continue
                 if n > job["cap"]:            # capacity guess too small: exact retry
                     job = self._export_launch(t, n, slot)
                     stream.synchronize()
                     n = int(job["h_n"][0])
-                hints[t.numel()] = n
-                idx_h = job["h_idx"][:n].numpy().copy()
-                cnt_h = job["h_cnt"][:n].numpy().view(np.uint32).copy()
-                order = np.argsort(idx_h, kind="stable")
-                out.append((idx_h[order], cnt_h[order]))
+                if not isinstance(t, HashTable):
+                    hints[t.numel()] = n
+                packed = job["h_packed"][:n].numpy()
+                out.append((packed >> 24, (packed & 0xffffff).astype(np.uint32)))
         return out
 
     def _export_launch(self, table, cap, slot):
@@ -407,29 +410,36 @@ class ContactEngine(object):
         if buf is None or buf["cap"] < cap:
             buf = {
                 "cap": cap,
-                "d_idx": torch.empty(cap, dtype=torch.int64, device=self.device),
-                "d_cnt": torch.empty(cap, dtype=torch.int32, device=self.device),
-                "d_n": torch.zeros(1, dtype=torch.int64, device=self.device),
-                "h_idx": torch.empty(cap, dtype=torch.int64, pin_memory=True),
-                "h_cnt": torch.empty(cap, dtype=torch.int32, pin_memory=True),
-                "h_n": torch.zeros(1, dtype=torch.int64, pin_memory=True),
+                "d_packed": torch.empty(cap, dtype=torch.int64, device=self.device),
+                "d_n": torch.zeros(2, dtype=torch.int64, device=self.device),
+                "h_packed": torch.empty(cap, dtype=torch.int64, pin_memory=True),
+                "h_n": torch.zeros(2, dtype=torch.int64, pin_memory=True),
             }
             if len(pool) > 8:
                 pool.clear()
             pool[(table.numel(), slot)] = buf
-        buf["d_n"].zero_()
-        if isinstance(table, HashTable):
-            self._check(self._L.cmb_export_hashed(self._ctx, _ptr(table.slots), table.log2, buf["cap"],
-                                                  _ptr(buf["d_idx"]), _ptr(buf["d_cnt"]), _ptr(buf["d_n"]),
-                                                  _stream_ptr(self.device)), "cmb_export_hashed")
-        else:
-            self._check(self._L.cmb_export_nonzero(self._ctx, _ptr(table), table.numel(), buf["cap"],
-                                                   _ptr(buf["d_idx"]), _ptr(buf["d_cnt"]), _ptr(buf["d_n"]),
-                                                   _stream_ptr(self.device)), "cmb_export_nonzero")
+        hashed = isinstance(table, HashTable)
+        self._check(self._L.cmb_export_sorted(self._ctx, _table_ptr(table), table.numel(),
+                                              table.log2 if hashed else 0, buf["cap"], _ptr(buf["d_packed"]),
+                                              _ptr(buf["d_n"]), _stream_ptr(self.device)), "cmb_export_sorted")
         buf["h_n"].copy_(buf["d_n"], non_blocking=True)
-        buf["h_idx"].copy_(buf["d_idx"], non_blocking=True)
-        buf["h_cnt"].copy_(buf["d_cnt"], non_blocking=True)
+        buf["h_packed"].copy_(buf["d_packed"], non_blocking=True)
         return buf
+
+    def _export_unpacked(self, table):
+        """Export through ``cmb_export_nonzero`` (counts of 2^24 and more), sorted on the host."""
+        n = int(torch.count_nonzero(table).item())
+        d_idx = torch.empty(max(n, 1), dtype=torch.int64, device=self.device)
+        d_cnt = torch.empty(max(n, 1), dtype=torch.int32, device=self.device)
+        d_n = torch.zeros(1, dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self._L.cmb_export_nonzero(self._ctx, _ptr(table), table.numel(), max(n, 1), _ptr(d_idx),
+                                                   _ptr(d_cnt), _ptr(d_n), _stream_ptr(self.device)),
+                        "cmb_export_nonzero")
+        idx = d_idx[:n].cpu().numpy()
+        cnt = d_cnt[:n].cpu().numpy().view(np.uint32)
+        order = np.argsort(idx, kind="stable")
+        return idx[order], cnt[order]
 
     def frame_contacts(self, xyz, box, frame0=0, atom_table=None, res_table=None,
                        want_atoms=True, want_residues=True, cap_hint=None):

@@ -142,6 +142,16 @@ int cmb_export_nonzero(cmb_ctx* ctx, const uint32_t* d_table, int64_t n_elems, i
                        int64_t* d_idx, uint32_t* d_cnt, uint64_t* d_n, void* stream);
 
 /*
+ * Sorted sparse export (the form the Python layer consumes): d_packed[cap] receives
+ * (flat index << 24 | count) of the non-zero entries in ascending index order, padded with
+ * 0xff..ff; d_n[0] = entries found (those beyond cap are dropped: retry with a larger buffer),
+ * d_n[1] != 0 if a count did not fit 24 bits (use cmb_export_nonzero then).  log2_slots > 0:
+ * d_table is a hashed table of 2^log2_slots slots, else a dense uint32 table of n_elems entries.
+ */
+int cmb_export_sorted(cmb_ctx* ctx, const void* d_table, int64_t n_elems, int log2_slots, int64_t cap,
+                      uint64_t* d_packed, uint64_t* d_n, void* stream);
+
+/*
  * north_star: "any pair within 1 ulp of the cutoff enumerated and reported".
  * Records {frame, lo, hi, d2} (int32,int32,int32,float32 = 16 bytes) of eligible
  * pairs whose d2 is within `ulps` float steps of cutoff^2.

@@ -119,3 +119,23 @@ def test_host_gather_path(engine, case_id, n_threads):
     assert np.array_equal(dense_from_export(idx, cnt, n), ref_atom)
     with pytest.raises(Exception):
         engine.accumulate_host_gather(full, used[::-1].copy(), box, atom_t, res_t)
+
+
+def test_export_sorted_and_wide_counts(engine):
+    """cmb_export_sorted (packed, device-sorted) and the unpacked fallback for counts >= 2^24."""
+    rng = np.random.default_rng(3)
+    table = np.zeros(5003, dtype=np.uint32)
+    where = np.sort(rng.choice(5003, size=700, replace=False))
+    table[where] = rng.integers(1, 1 << 20, size=700)
+    t = torch.as_tensor(table.view(np.int32), device=engine.device)
+    idx, cnt = engine.export_nonzero(t)
+    assert np.array_equal(idx, where) and np.array_equal(cnt, table[where])
+    table[where[5]] = (1 << 24) + 7                        # does not fit the packed form
+    table[5002] = 0xffffffff
+    t = torch.as_tensor(table.view(np.int32), device=engine.device)
+    idx, cnt = engine.export_nonzero(t)
+    nz = np.flatnonzero(table)
+    assert np.array_equal(idx, nz) and np.array_equal(cnt, table[nz])
+    empty = torch.zeros(64, dtype=torch.int32, device=engine.device)
+    idx, cnt = engine.export_nonzero(empty)
+    assert len(idx) == 0 and len(cnt) == 0
