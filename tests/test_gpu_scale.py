@@ -227,3 +227,71 @@ def test_binding_system_s2_matches_oracle(engine):
     # every contact joins the partner (query) with the receptor (haystack)
     lo, hi = idx // n, idx % n
     assert np.all((role[lo] | role[hi]) == 3) and np.all(role[lo] != role[hi])
+
+
+@pytest.mark.parametrize("box_kind,force_path,max_shift", [("ortho", 0, 2), ("triclinic", 0, 2), ("none", 0, 0),
+                                                           ("triclinic", 1, 2), ("ortho", 0, 400)])
+def test_pairs_at_the_cutoff_are_adjudicated_exactly(engine, box_kind, force_path, max_shift):
+    """The screening thresholds (frame_margins) must never decide a pair the reference arithmetic
+    would decide differently: 1 500 atom pairs are placed within a few float steps of the cutoff
+    (both sides), then moved by whole box vectors so that the raw coordinates are large and the
+    rounding of the reference chain matters.  Every pair is its own two single-atom residues in
+    two chains, so the oracle's contact set is exactly the set of pairs it judges inside.
+    max_shift = 400 puts the atoms thousands of nm from the origin: the error bound exceeds the
+    useful range and the kernel must fall back to adjudicating everything exactly."""
+    rng = np.random.default_rng(2024)
+    n_pairs, cutoff = 1500, 0.45
+    side = 12
+    if box_kind == "ortho":
+        box = np.diag([14.4, 15.0, 13.8]).astype(np.float32)
+    elif box_kind == "triclinic":
+        box = np.array([[14.4, 0, 0], [3.1, 15.0, 0], [-2.7, 4.2, 13.8]], dtype=np.float32)
+    else:
+        box = None
+    # pair centres on a coarse lattice (1.1 nm apart: different pairs never interact)
+    sites = np.stack(np.meshgrid(*[np.arange(side)] * 3, indexing="ij"), axis=-1).reshape(-1, 3)[:n_pairs]
+    centre = (sites * 1.1 + 0.6).astype(np.float64)
+    direction = rng.normal(size=(n_pairs, 3))
+    direction /= np.linalg.norm(direction, axis=1, keepdims=True)
+    c32 = np.float32(cutoff)
+    steps = rng.integers(-6, 7, size=n_pairs)                        # float steps of the DISTANCE
+    dist = np.float64(c32) * (1.0 + steps * 2.0 ** -24)
+    a = centre - 0.5 * dist[:, None] * direction
+    b = centre + 0.5 * dist[:, None] * direction
+    xyz = np.empty((3, 2 * n_pairs, 3), dtype=np.float32)
+    for f in range(3):
+        pa, pb = a.copy(), b.copy()
+        if box is not None:
+            # molecules "not made whole": each atom moved by its own lattice vector
+            for p in (pa, pb):
+                shift = rng.integers(-max_shift, max_shift + 1, size=(n_pairs, 3)).astype(np.float64)
+                p += shift @ box.astype(np.float64)
+        xyz[f, 0::2] = pa.astype(np.float32)
+        xyz[f, 1::2] = pb.astype(np.float32)
+    n = 2 * n_pairs
+    res = np.arange(n, dtype=np.int32)
+    chain = (np.arange(n) % 2).astype(np.int32)
+    role = np.full(n, 3, dtype=np.uint8)
+    boxes = None if box is None else np.broadcast_to(box, (3, 3, 3)).copy()
+    ref_atom, _ = clib.accumulate_dense(xyz, boxes, cutoff, res, chain, role, 0, n)
+    inside = int(ref_atom.sum())
+    assert 0.1 * 3 * n_pairs < inside < 0.9 * 3 * n_pairs            # both outcomes well represented
+    engine.set_option("force_path", force_path if force_path else -1)
+    try:
+        engine.set_system(res, chain, role, cutoff, 0)
+        assert engine.path_kind == force_path
+        atom_t, res_t = engine.new_tables(hashed=False)
+        d_xyz = torch.as_tensor(xyz, device=engine.device)
+        d_box = None if boxes is None else torch.as_tensor(boxes, device=engine.device)
+        engine.accumulate(d_xyz, d_box, atom_t, res_t)
+        idx, cnt = engine.export_nonzero(atom_t)
+        assert np.array_equal(dense_from_export(idx, cnt, n), ref_atom)
+        # and the boundary report sees them (north_star: pairs within N ulps are enumerated)
+        rec = engine.boundary_pairs(d_xyz[:1], None if d_box is None else d_box[:1], ulps=64)
+        wa, wb, wd = clib.boundary_pairs(xyz[0], box, cutoff, res, chain, role, 0, ulps=64)
+        assert len(wa) > (n_pairs // 2 if max_shift <= 2 else 0)
+        order = np.lexsort((wb, wa))
+        assert np.array_equal(rec["a"], wa[order]) and np.array_equal(rec["b"], wb[order])
+        assert np.array_equal(rec["d2"], wd[order])
+    finally:
+        engine.set_option("force_path", -1)
