@@ -18,6 +18,9 @@ from .min_dist import NearestAtoms, MinimumDistanceCounter                 # noq
 from .runner import (                                                      # noqa: F401
     ChunkedContactFrequency, DaskContactFrequency, DaskContactTrajectory,
 )
+from .concurrence import (                                                 # noqa: F401
+    Concurrence, AtomContactConcurrence, ResidueContactConcurrence,
+)
 from . import frequency_task                                               # noqa: F401
 from .trajectory import Trajectory, Topology, load, load_pdb               # noqa: F401
 

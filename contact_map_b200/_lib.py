@@ -28,7 +28,7 @@ EXPORTS = [
     "cmb_accumulate_host", "cmb_accumulate_host_gather", "cmb_frame_contacts", "cmb_sort_keys", "cmb_export_nonzero",
     "cmb_boundary_pairs", "cmb_set_option", "cmb_get_stat", "cmb_gather_atoms", "cmb_min_dist",
     "cmb_nearest", "cmb_synth_frames", "cmb_set_table_mode", "cmb_hash_stats", "cmb_export_hashed",
-    "cmb_hash_rehash", "cmb_hash_overflow_buffer", "cmb_hash_add", "cmb_export_sorted",
+    "cmb_hash_rehash", "cmb_hash_overflow_buffer", "cmb_hash_add", "cmb_export_sorted", "cmb_group_contacts",
 ]
 
 
@@ -115,6 +115,8 @@ def lib():
     L.cmb_hash_add.argtypes = [vp, vp, i32, vp, vp, i64, i32, vp]
     L.cmb_export_sorted.restype = i32
     L.cmb_export_sorted.argtypes = [vp, vp, i64, i32, i64, vp, vp, vp]
+    L.cmb_group_contacts.restype = i32
+    L.cmb_group_contacts.argtypes = [vp, vp, vp, i64, i32, vp, i32, vp, vp, i32, i32, flt, vp, vp]
     L.cmb_hash_rehash.restype = i32
     L.cmb_hash_rehash.argtypes = [vp, vp, i32, vp, i32, vp]
     L.cmb_frame_contacts.restype = i32

@@ -824,6 +824,31 @@ extern "C" int cmb_export_sorted(cmb_ctx* ctx, const void* d_table, int64_t n_el
     return cmb_sort_keys(ctx, d_packed, cap, stream);
 }
 
+extern "C" int cmb_group_contacts(cmb_ctx* ctx, const float* d_xyz, const float* d_box, int64_t n_frames, int n_atoms,
+                                  const int32_t* d_atoms, int n_sel, const int32_t* d_pairs,
+                                  const int64_t* d_group_ptr, int n_groups, int orthogonal, float cutoff,
+                                  uint8_t* d_out, void* stream)
+{
+    if (!ctx) return CMB_ERR_ARG;
+    if (!d_xyz || !d_atoms || !d_pairs || !d_group_ptr || !d_out || n_frames < 0 || n_atoms <= 0 || n_sel <= 0 ||
+        n_groups < 0)
+        return fail(ctx, CMB_ERR_ARG, "bad group-contact arguments");
+    if (n_frames == 0 || n_groups == 0) return CMB_OK;
+    if (n_frames > 0x7fffffffll) return fail(ctx, CMB_ERR_LIMIT, "too many frames for one call");
+    CK(cudaSetDevice(ctx->device));
+    const size_t smem = (size_t)n_sel * 12;
+    if (smem > (size_t)ctx->max_smem_optin)
+        return fail(ctx, CMB_ERR_LIMIT, "the contacts touch %d atoms; at most %d fit in shared memory", n_sel,
+                    ctx->max_smem_optin / 12);
+    CK(cudaFuncSetAttribute(k_group_contacts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_group_contacts<<<(unsigned)n_frames, CC_THREADS, smem, (cudaStream_t)stream>>>(
+        d_xyz, d_box, n_atoms, d_atoms, n_sel, reinterpret_cast<const int2*>(d_pairs),
+        reinterpret_cast<const long long*>(d_group_ptr), n_groups, orthogonal, cutoff, d_out);
+    CK(cudaGetLastError());
+    ctx->stats["kernel_launches"] += 1;
+    return CMB_OK;
+}
+
 extern "C" int cmb_gather_atoms(cmb_ctx* ctx, const float* d_xyz_full, int64_t n_frames, int n_total,
                                 const int32_t* d_used, int n_used, float* d_out, void* stream)
 {

@@ -401,4 +401,43 @@ __global__ void __launch_bounds__(NA_THREADS) k_nearest(
     if (i < n_atoms) { nearest[i] = bj; dist[i] = best; }
 }
 
+// ---------------------------------------------------------------------------------
+// contact concurrences (concurrence.py:100-162): for groups of atom pairs, is the minimum
+// compute_distances() distance of the group below the cutoff in each frame?  One CTA per frame:
+// the atoms the pairs touch are gathered into shared memory once, every thread walks whole
+// groups.  out[f][g] (frame-major, coalesced); the host transposes.
+// ---------------------------------------------------------------------------------
+constexpr int CC_THREADS = 256;
+
+__global__ void __launch_bounds__(CC_THREADS) k_group_contacts(
+    const float* __restrict__ xyz, const float* __restrict__ box, int n_atoms,
+    const int* __restrict__ atoms, int n_sel,          // atoms the pairs touch (gathered per frame)
+    const int2* __restrict__ pairs,                    // indices INTO `atoms`
+    const long long* __restrict__ group_ptr, int n_groups, int orthogonal, float cutoff_f,
+    unsigned char* __restrict__ out)
+{
+    extern __shared__ float cc_xyz[];                  // [n_sel][3]
+    const long long f = blockIdx.x;
+    const float* x = xyz + (size_t)f * (size_t)n_atoms * 3;
+    const DistBox D = make_distbox(box ? box + (size_t)f * 9 : nullptr, orthogonal);
+    for (int t = threadIdx.x; t < n_sel; t += CC_THREADS) {
+        const int a = __ldg(&atoms[t]);
+        cc_xyz[3 * t] = __ldg(&x[(size_t)a * 3]);
+        cc_xyz[3 * t + 1] = __ldg(&x[(size_t)a * 3 + 1]);
+        cc_xyz[3 * t + 2] = __ldg(&x[(size_t)a * 3 + 2]);
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < n_groups; g += CC_THREADS) {
+        float best = __int_as_float(0x7f800000);       // min() of an empty group: no contact
+        for (long long k = __ldg(&group_ptr[g]); k < __ldg(&group_ptr[g + 1]); k++) {
+            const int2 pr = __ldg(&pairs[k]);
+            // compute_distances(pair = (i, j)): r = p_j - p_i, float32 sqrt
+            const float d = __fsqrt_rn(dist2_pair(cc_xyz[3 * pr.x], cc_xyz[3 * pr.x + 1], cc_xyz[3 * pr.x + 2],
+                                                  cc_xyz[3 * pr.y], cc_xyz[3 * pr.y + 1], cc_xyz[3 * pr.y + 2], D));
+            best = fminf(best, d);
+        }
+        out[(size_t)f * (size_t)n_groups + g] = best < cutoff_f ? 1 : 0;
+    }
+}
+
 }  // namespace cmb

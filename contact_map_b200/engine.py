@@ -554,6 +554,33 @@ class ContactEngine(object):
                                              _stream_ptr(self.device)), "cmb_min_dist")
         return dmin, darg
 
+    def group_contacts(self, xyz, box, atom_pairs, group_ptr, cutoff, orthogonal):
+        """``[n_groups, n_frames]`` bool array: is the minimum ``compute_distances`` distance over
+        the atom pairs of each group below ``cutoff`` (float32, strict) in each frame?"""
+        if xyz.dtype != torch.float32 or not xyz.is_contiguous() or not xyz.is_cuda:
+            raise TypeError("xyz must be a contiguous float32 CUDA tensor")
+        pairs = np.ascontiguousarray(atom_pairs, dtype=np.int64).reshape(-1, 2)
+        group_ptr = np.ascontiguousarray(group_ptr, dtype=np.int64)
+        n_groups, n_frames, n_atoms = len(group_ptr) - 1, xyz.shape[0], xyz.shape[1]
+        if n_groups == 0 or n_frames == 0:
+            return np.zeros((n_groups, n_frames), dtype=bool)
+        if pairs.size and (pairs.min() < 0 or pairs.max() >= n_atoms):
+            raise ValueError("atom index out of range")
+        atoms, compact = np.unique(pairs, return_inverse=True)
+        if atoms.size == 0:
+            atoms = np.zeros(1, dtype=np.int64)
+        d_atoms = torch.as_tensor(atoms.astype(np.int32), device=self.device)
+        d_pairs = torch.as_tensor(compact.reshape(-1, 2).astype(np.int32), device=self.device)
+        d_ptr = torch.as_tensor(group_ptr, device=self.device)
+        out = torch.empty((n_frames, n_groups), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self._L.cmb_group_contacts(self._ctx, _ptr(xyz), _ptr(box), n_frames, n_atoms,
+                                                   _ptr(d_atoms), int(d_atoms.numel()), _ptr(d_pairs), _ptr(d_ptr),
+                                                   n_groups, int(bool(orthogonal)),
+                                                   ctypes.c_float(float(np.float32(cutoff))), _ptr(out),
+                                                   _stream_ptr(self.device)), "cmb_group_contacts")
+        return out.t().contiguous().cpu().numpy().astype(bool)
+
     def nearest(self, xyz_frame, box9, cutoff, orthogonal, excl_mode, atom_res=None,
                 excl_ptr=None, excl_idx=None):
         n_atoms = xyz_frame.shape[0]

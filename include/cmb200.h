@@ -166,6 +166,19 @@ int cmb_set_option(cmb_ctx* ctx, const char* name, int64_t value);
 int cmb_get_stat(cmb_ctx* ctx, const char* name, int64_t* value);
 
 /*
+ * AtomContactConcurrence / ResidueContactConcurrence (concurrence.py:100-162):
+ * d_out[f][g] = 1 iff min over the atom pairs of group g of the compute_distances() distance
+ * (float32, minimum image as in min_dist) is < cutoff (float32 compare, strict) in frame f.
+ * d_atoms[n_sel]: the atoms the pairs touch; d_pairs[P][2]: indices INTO d_atoms;
+ * d_group_ptr[n_groups + 1]: CSR offsets of the groups in d_pairs (an atom contact is a group of
+ * one pair, a residue contact the product of the two residues' selected atoms).
+ */
+int cmb_group_contacts(cmb_ctx* ctx, const float* d_xyz, const float* d_box, int64_t n_frames, int n_atoms,
+                       const int32_t* d_atoms, int n_sel, const int32_t* d_pairs,
+                       const int64_t* d_group_ptr, int n_groups, int orthogonal, float cutoff,
+                       uint8_t* d_out, void* stream);
+
+/*
  * _atom_slice (atom_indexer.py:5-22): out[f][i][:] = xyz[f][used[i]][:] on device.
  */
 int cmb_gather_atoms(cmb_ctx* ctx, const float* d_xyz_full, int64_t n_frames, int n_total,
