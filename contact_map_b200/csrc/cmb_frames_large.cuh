@@ -86,10 +86,10 @@ struct LargeTraits {
     static __device__ __forceinline__ int e_jpos(hit_t e) { return (int)(e.y & 0xfffffu); }
     static __device__ __forceinline__ int e_id(hit_t e) { return (int)(e.y >> 20); }
     static __device__ __forceinline__ unsigned e_mask(hit_t e) { return e.z; }
-    static __device__ __forceinline__ int next_task(int* counter)        // task counter in global memory
+    static __device__ __forceinline__ int next_tasks(int* counter, int count)        // task counter in global memory
     {
         int old;
-        asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(counter) : "memory");
+        asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(counter), "r"(count) : "memory");
         return old;
     }
     // sorted[].w bits: atom index [0,30) | role [30,32); exclusion keys in a separate array

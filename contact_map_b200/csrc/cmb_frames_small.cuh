@@ -183,12 +183,12 @@ struct SmallTraits {
     static __device__ __forceinline__ unsigned e_mask(hit_t e) { return e.y; }
     // task counter in shared memory; plain ATOMS (the compiler's warp-aggregated form costs 16
     // issue slots for a single active lane)
-    static __device__ __forceinline__ int next_task(int* counter)
+    static __device__ __forceinline__ int next_tasks(int* counter, int count)
     {
         int old;
-        asm volatile("atom.shared.add.u32 %0, [%1], 1;"
+        asm volatile("atom.shared.add.u32 %0, [%1], %2;"
                      : "=r"(old)
-                     : "r"((unsigned)__cvta_generic_to_shared(counter))
+                     : "r"((unsigned)__cvta_generic_to_shared(counter)), "r"(count)
                      : "memory");
         return old;
     }
