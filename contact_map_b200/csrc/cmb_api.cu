@@ -753,24 +753,29 @@ extern "C" int cmb_boundary_pairs(cmb_ctx* ctx, const float* d_xyz, const float*
 // ---------------------------------------------------------------------------------
 // sort / export / gather / synth
 // ---------------------------------------------------------------------------------
-extern "C" int cmb_sort_keys(cmb_ctx* ctx, uint64_t* d_keys, int64_t n, void* stream)
+// in-place radix sort of 64-bit keys on the bits [begin_bit, end_bit)
+static int sort_key_bits(cmb_ctx* ctx, uint64_t* d_keys, int64_t n, int begin_bit, int end_bit, cudaStream_t stream)
 {
-    if (!ctx) return CMB_ERR_ARG;
     if (n <= 1) return CMB_OK;
     if (n > 0x7fffffffll) return fail(ctx, CMB_ERR_LIMIT, "too many keys for one sort");
     CK(cudaSetDevice(ctx->device));
     size_t tmp = 0;
     unsigned long long* keys = (unsigned long long*)d_keys;
-    CK(cub::DeviceRadixSort::SortKeys(nullptr, tmp, keys, keys, (int)n, 0, 64, (cudaStream_t)stream));
+    CK(cub::DeviceRadixSort::SortKeys(nullptr, tmp, keys, keys, (int)n, begin_bit, end_bit, stream));
     const size_t alt = ((size_t)n * 8 + 255) & ~(size_t)255;
     int rc = ensure_bytes(ctx, &ctx->d_tmp, &ctx->tmp_bytes, alt + tmp);
     if (rc) return rc;
     unsigned long long* out = (unsigned long long*)ctx->d_tmp;
-    CK(cub::DeviceRadixSort::SortKeys((char*)ctx->d_tmp + alt, tmp, keys, out, (int)n, 0, 64,
-                                      (cudaStream_t)stream));
-    CK(cudaMemcpyAsync(keys, out, (size_t)n * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    CK(cub::DeviceRadixSort::SortKeys((char*)ctx->d_tmp + alt, tmp, keys, out, (int)n, begin_bit, end_bit, stream));
+    CK(cudaMemcpyAsync(keys, out, (size_t)n * 8, cudaMemcpyDeviceToDevice, stream));
     ctx->stats["kernel_launches"] += 1;
     return CMB_OK;
+}
+
+extern "C" int cmb_sort_keys(cmb_ctx* ctx, uint64_t* d_keys, int64_t n, void* stream)
+{
+    if (!ctx) return CMB_ERR_ARG;
+    return sort_key_bits(ctx, d_keys, n, 0, 64, (cudaStream_t)stream);
 }
 
 extern "C" int cmb_export_nonzero(cmb_ctx* ctx, const uint32_t* d_table, int64_t n_elems, int64_t cap,
@@ -821,7 +826,12 @@ extern "C" int cmb_export_sorted(cmb_ctx* ctx, const void* d_table, int64_t n_el
     }
     CK(cudaGetLastError());
     ctx->stats["kernel_launches"] += 1;
-    return cmb_sort_keys(ctx, d_packed, cap, stream);
+    // the indices are distinct: sort on the index bits only.  2^bits > largest index + 1, so the
+    // all-ones padding sorts behind every entry.
+    const unsigned long long span = log2_slots > 0 ? (1ull << 40) : (unsigned long long)std::max<int64_t>(n_elems, 1);
+    int bits = 1;
+    while (bits < 40 && (1ull << bits) <= span) bits++;
+    return sort_key_bits(ctx, d_packed, cap, 24, 24 + bits, st);
 }
 
 extern "C" int cmb_group_contacts(cmb_ctx* ctx, const float* d_xyz, const float* d_box, int64_t n_frames, int n_atoms,
