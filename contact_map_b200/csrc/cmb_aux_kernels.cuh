@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(256) k_rehash(const unsigned long long* __rest
         const unsigned long long key1 = s >> 24;
         unsigned long long k = key1;
         k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
-        unsigned h = (unsigned)k & dst_mask;
+        unsigned h = ((unsigned)k & dst_mask) & ~3u;         // bucketed probe sequence (ht_find_or_insert)
         bool placed = false;
         for (int probe = 0; probe < (1 << 14) && !placed; probe++) {
             const unsigned long long old = atomicCAS(&dst[h], 0ull, s);      // keys are distinct in src
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(256) k_hash_add(unsigned long long* __restrict
         const unsigned long long k1 = key1[v];
         unsigned long long k = k1;
         k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
-        unsigned h = (unsigned)k & mask;
+        unsigned h = ((unsigned)k & mask) & ~3u;
         bool placed = false;
         for (int probe = 0; probe < (1 << 14) && !placed; probe++) {
             unsigned long long cur = *(volatile unsigned long long*)&slots[h];

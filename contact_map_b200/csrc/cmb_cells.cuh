@@ -168,7 +168,6 @@ constexpr int CT_PAIR_MAX_OWN = CT_PAIR_MAX_OWN_CFG;
 // =================================================================================
 constexpr int CT_KSLOT = 4;                 // register-resident candidates per lane
 constexpr int CT_CAND = 32 * CT_KSLOT;      // candidates per chunk
-constexpr int CT_TASK_BATCH = 4;            // task-list entries per fetch of a warp
 constexpr int CT_QCAP = 64;                 // per-warp ring of screened (candidate, own-atom mask) entries
 constexpr int CT_NOSHIFT = 13;              // shift id of "no lattice shift"
 constexpr float CT_FAR = 1.0e18f;           // coordinate of an empty candidate slot
@@ -623,16 +622,16 @@ __device__ __forceinline__ void ct_pair_phase(const PairParams& p, const GridS& 
     Ring ring;
     ring.head = ring.tail = 0u;
     for (;;) {
-        // CT_TASK_BATCH consecutive list entries per fetch: the fetch (ATOMS + SHFL + bounds) and
+        // TASK_BATCH consecutive list entries per fetch: the fetch (atomic + SHFL + bounds) and
         // the entries the pair merge left empty cost one trip per batch instead of one each
         int k = 0;
-        if (lane == 0) k = Traits::next_tasks(task_counter, CT_TASK_BATCH);
+        if (lane == 0) k = Traits::next_tasks(task_counter, Traits::TASK_BATCH);
         k = __shfl_sync(0xffffffffu, k, 0);
         if (k >= n_occ) break;
         unsigned mine = Traits::TASK_EMPTY;
-        if (lane < CT_TASK_BATCH && k + lane < n_occ) mine = (unsigned)occ[k + lane];
+        if (lane < Traits::TASK_BATCH && k + lane < n_occ) mine = (unsigned)occ[k + lane];
 #pragma unroll 1
-        for (int t = 0; t < CT_TASK_BATCH; t++) {
+        for (int t = 0; t < Traits::TASK_BATCH; t++) {
             const unsigned task = __shfl_sync(0xffffffffu, mine, t);
             if (task == Traits::TASK_EMPTY) continue;
             ct_cell_task<Traits, Sink, MODE, FLAGS>(p, G, cx, sink, task, n_tests, ring);

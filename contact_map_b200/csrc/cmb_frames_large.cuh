@@ -70,6 +70,7 @@ struct LargeTraits {
     // task word: cell [0,28) | interior | pair
     static constexpr unsigned TASK_CMASK = 0x0fffffffu, TASK_INTERIOR = 0x10000000u, TASK_PAIR = 0x20000000u,
                               TASK_EMPTY = 0xffffffffu;
+    static constexpr int TASK_BATCH = 1;          // the whole GPU shares one frame's task list
     static __device__ __forceinline__ cand_t cand(int pos, int wrap)
     {
         return (unsigned)pos | ((unsigned)wrap << 20);
@@ -128,24 +129,38 @@ __device__ __forceinline__ unsigned ht_hash(unsigned long long k)
 
 // slot of `key1` (= key + 1), claiming an empty one if the key is new; 0xffffffff: table full
 // (the caller then parks the hit in the overflow list).  stats[which] counts the new keys.
+// Probing is bucketed: the probe sequence starts at a 32-byte aligned group of four slots and one
+// probe reads the whole group (one L2 sector, two 16-byte loads), so a lookup is one round trip
+// for > 95 % of the hits at load <= 0.7 instead of one round trip per slot.
+__device__ __forceinline__ ulonglong2 ht_load2(const unsigned long long* p)
+{
+    ulonglong2 v;
+    asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ unsigned ht_find_or_insert(unsigned long long* slots, unsigned mask,
                                                       unsigned long long key1, unsigned long long* stats,
                                                       int which)
 {
-    unsigned h = ht_hash(key1) & mask;
-    for (int probe = 0; probe < HT_MAX_PROBES; probe++) {
-        const unsigned long long s = *(volatile unsigned long long*)&slots[h];
-        unsigned long long k = s >> HT_COUNT_BITS;
-        if (k == 0ull) {
-            const unsigned long long old = atomicCAS(&slots[h], 0ull, key1 << HT_COUNT_BITS);
-            if (old == 0ull) {
-                atomicAdd(&stats[which], 1ull);
-                return h;
+    unsigned h0 = (ht_hash(key1) & mask) & ~3u;
+    for (int probe = 0; probe < HT_MAX_PROBES / 4; probe++) {
+        const ulonglong2 lo = ht_load2(&slots[h0]), hi = ht_load2(&slots[h0 + 2]);
+        const unsigned long long s[4] = {lo.x, lo.y, hi.x, hi.y};
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if ((s[j] >> HT_COUNT_BITS) == key1) return h0 + j;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if ((s[j] >> HT_COUNT_BITS) == 0ull) {
+                const unsigned long long old = atomicCAS(&slots[h0 + j], 0ull, key1 << HT_COUNT_BITS);
+                if (old == 0ull) {
+                    atomicAdd(&stats[which], 1ull);
+                    return h0 + j;
+                }
+                if ((old >> HT_COUNT_BITS) == key1) return h0 + j;
             }
-            k = old >> HT_COUNT_BITS;
         }
-        if (k == key1) return h;
-        h = (h + 1u) & mask;
+        h0 = (h0 + 4u) & mask;
     }
     return 0xffffffffu;
 }
@@ -220,6 +235,10 @@ struct StampSink {
     // called by the lanes of one drain whose pair is a hit
     __device__ __forceinline__ void account(int ia, int ib)
     {
+#ifdef CMB_EXPERIMENT_NO_SINK
+        if (ia == -12345) atomicAdd(&atom_table[0], (unsigned)ib);    // keep the call alive, touch nothing
+        return;
+#endif
         const int a = min(ia, ib), b = max(ia, ib);
         if (atom_table != nullptr) {
             const unsigned long long flat = (unsigned long long)a * (unsigned long long)n + (unsigned long long)b;

@@ -162,6 +162,7 @@ struct SmallTraits {
     // task word: cell [0,14) | interior | pair
     static constexpr unsigned TASK_CMASK = 0x3fffu, TASK_INTERIOR = 0x4000u, TASK_PAIR = 0x8000u,
                               TASK_EMPTY = 0xffffu;
+    static constexpr int TASK_BATCH = 4;          // ~550 list entries per frame for 16 warps
     static __device__ __forceinline__ cand_t cand(int pos, int wrap)
     {
         return (cand_t)((unsigned)pos | ((unsigned)wrap << 13));

@@ -33,7 +33,7 @@ def _stream_ptr(device):
 class HashTable(object):
     """Hashed count table of the global-memory cell path (``cmb_set_table_mode``): 2^log2 uint64
     slots, slot = (flat index + 1) << 24 | count, zero = empty.  ``used`` tracks the number of
-    distinct keys (the engine keeps the load below 0.7 by rehashing into a larger table: small
+    distinct keys (the engine keeps the load below 0.85 by rehashing into a larger table: small
     tables stay L2-resident, which is the point of hashing);
     ``merged`` holds the (index, count) arrays after a multi-rank reduce."""
 
@@ -144,8 +144,8 @@ class ContactEngine(object):
             if self.path_kind != 1:
                 raise EngineError("hashed count tables are only used by the global-memory cell path")
             atom = HashTable(max(10, int(np.ceil(np.log2(32.0 * n)))), self.device)
-            if 4 * rc * rc > self.DENSE_LIMIT_BYTES // 4:
-                res = HashTable(max(10, int(np.ceil(np.log2(64.0 * rc)))), self.device)
+            if 4 * rc * rc > (1 << 28):
+                res = HashTable(max(10, int(np.ceil(np.log2(48.0 * rc)))), self.device)
             else:
                 res = torch.zeros(rc * rc, dtype=torch.int32, device=self.device)
             return atom, res
@@ -189,9 +189,9 @@ class ContactEngine(object):
         # (a frame has at most as many residue pairs as atom pairs, usually far fewer: the residue
         # table keeps its default size, 64 slots per residue, unless even that bound is smaller)
         for t, first in ((atom_table, int(counts[0])),):
-            if isinstance(t, HashTable) and t.used == 0 and 3 * first > t.numel():
+            if isinstance(t, HashTable) and t.used == 0 and 2 * first > t.numel():
                 log2 = t.log2
-                while 3 * first > (1 << log2):
+                while 2 * first > (1 << log2):
                     log2 += 1
                 t.slots, t.log2 = torch.zeros(1 << log2, dtype=torch.int64, device=self.device), log2
         self._set_table_mode(atom_table, res_table)
@@ -245,8 +245,10 @@ class ContactEngine(object):
             t.used += int(new)
             t.merged = None
             extra = 0 if adds[which] is None else int(adds[which][0].numel())
-            if 10 * (t.used + extra) > 7 * t.numel():            # load > 0.7: grow to load <= 0.45
-                self._grow(t, int((t.used + extra) / 0.45) + 1)
+            # load > 0.85: grow to load <= 0.6.  Bucketed probing tolerates high loads, and a SMALL
+            # table is the point: the hot set (tables + stamps) has to stay inside the 126 MB L2
+            if 100 * (t.used + extra) > 85 * t.numel():
+                self._grow(t, int((t.used + extra) / 0.6) + 1)
             if extra:
                 keys, counts = adds[which]
                 with torch.cuda.device(self.device):

@@ -35,7 +35,7 @@ def main():
                                 torch.as_tensor(system.box.reshape(9), device=dev), system.seed,
                                 system.amplitude, True, 0, n_frames)
     d_box = torch.as_tensor(system.box, device=dev).reshape(1, 3, 3).expand(n_frames, 3, 3).contiguous()
-    atom_t, res_t = engine.new_tables()
+    atom_t, res_t = engine.new_tables(hashed=True if os.environ.get("CMB_PROFILE_HASHED") else None)
     for _ in range(launches):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -23,6 +23,7 @@ def run(name, mk):
         del a, r
 rc = engine.n_res_c
 run("dense/dense", lambda: engine.new_tables(hashed=False))
-run("dense/hashed-res", lambda: (engine.new_tables(hashed=False)[0], HashTable(22, dev)))
-run("hashed/hashed", lambda: (HashTable(23, dev), HashTable(22, dev)))
+run("dense/hashed-res", lambda: (engine.new_tables(hashed=False)[0], HashTable(21, dev)))
+run("hashed/hashed", lambda: engine.new_tables(hashed=True))
+run("hashed/none", lambda: (engine.new_tables(hashed=True)[0], None))
 run("dense/none", lambda: (engine.new_tables(hashed=False)[0], None))
