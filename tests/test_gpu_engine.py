@@ -139,3 +139,46 @@ def test_export_sorted_and_wide_counts(engine):
     empty = torch.zeros(64, dtype=torch.int32, device=engine.device)
     idx, cnt = engine.export_nonzero(empty)
     assert len(idx) == 0 and len(cnt) == 0
+
+
+@pytest.mark.parametrize("box_kind", ["none", "ortho", "triclinic"])
+def test_crowded_cells(engine, box_kind):
+    """Cells holding far more than 32 atoms: own atoms are screened in sub-batches of 32, the
+    candidate set spans several 128-slot chunks, and the ring fills faster than it drains (the
+    slot-by-slot push path).  350 atoms inside a 0.9 nm blob, optionally in a periodic box."""
+    rng = np.random.default_rng(99)
+    n, n_frames, cutoff = 350, 3, 0.45
+    blob = rng.uniform(0.0, 0.9, size=(n, 3))
+    if box_kind == "none":
+        box = None
+    elif box_kind == "ortho":
+        box = np.diag([2.9, 3.3, 2.5]).astype(np.float32)
+    else:
+        box = np.array([[2.9, 0, 0], [0.7, 3.3, 0], [-0.5, 0.9, 2.5]], dtype=np.float32)
+    xyz = np.empty((n_frames, n, 3), dtype=np.float32)
+    for f in range(n_frames):
+        p = blob + rng.normal(scale=0.02, size=(n, 3)) + np.array([2.7, 0.1, 1.2])    # straddles box faces
+        if box is not None:
+            p = p + rng.integers(-1, 2, size=(n, 3)).astype(np.float64) @ box.astype(np.float64)
+        xyz[f] = p.astype(np.float32)
+    res = (np.arange(n) // 5).astype(np.int32)
+    chain = (res // 20).astype(np.int32)
+    role = np.full(n, 3, dtype=np.uint8)
+    boxes = None if box is None else np.broadcast_to(box, (n_frames, 3, 3)).copy()
+    n_res = int(res.max()) + 1
+    ref_atom, ref_res = clib.accumulate_dense(xyz, boxes, cutoff, res, chain, role, 1, n_res)
+    assert ref_atom.sum() > 20000
+    for force in (0, 1):
+        engine.set_option("force_path", force if force else -1)
+        try:
+            engine.set_system(res, chain, role, cutoff, 1)
+            atom_t, res_t = engine.new_tables(hashed=False)
+            engine.accumulate(torch.as_tensor(xyz, device=engine.device),
+                              None if boxes is None else torch.as_tensor(boxes, device=engine.device),
+                              atom_t, res_t)
+            (idx, cnt), (ridx, rcnt) = engine.export_many([atom_t, res_t])
+            assert np.array_equal(dense_from_export(idx, cnt, n), ref_atom)
+            rmap = engine.residue_map
+            assert np.array_equal(dense_from_export(ridx, rcnt, engine.n_res_c), ref_res[np.ix_(rmap, rmap)])
+        finally:
+            engine.set_option("force_path", -1)
