@@ -104,6 +104,10 @@ class ContactEngine(object):
     # ------------------------------------------------------------------
     def set_option(self, name, value):
         self._check(self._L.cmb_set_option(self._ctx, name.encode(), int(value)), "cmb_set_option")
+        if name == "force_path":
+            self._forced_path = int(value)
+        if name in ("force_path", "max_cells"):
+            self._system_key = None           # these take effect at the next cmb_set_system
 
     def get_stat(self, name):
         out = ctypes.c_int64(0)
@@ -117,6 +121,12 @@ class ContactEngine(object):
         n = atom_res.shape[0]
         if atom_chain.shape[0] != n or role.shape[0] != n:
             raise ValueError("system arrays must have the same length")
+        # the same system again (one analysis object per trajectory chunk): nothing to upload
+        key = (n, float(cutoff), int(n_ignored), hash(atom_res.tobytes()), hash(atom_chain.tobytes()),
+               hash(role.tobytes()), self.get_stat("max_cells"), int(getattr(self, "_forced_path", -1)))
+        if key == getattr(self, "_system_key", None):
+            return
+        self._system_key = None
         self._check(self._L.cmb_set_system(self._ctx, n, _ptr(atom_res), _ptr(atom_chain),
                                            _ptr(role), float(cutoff), int(n_ignored)),
                     "cmb_set_system")
@@ -126,6 +136,7 @@ class ContactEngine(object):
         self._check(self._L.cmb_residue_map(self._ctx, _ptr(rmap)), "cmb_residue_map")
         self.residue_map = rmap
         self.path_kind = int(self._L.cmb_path_kind(self._ctx))
+        self._system_key = key
 
     # dense tables above this size are replaced by hashed ones (global-memory cell path only).
     # Measured on the 100k-atom system (40 GB dense table): dense 6.3k frames/s, hashed 5.4k --
