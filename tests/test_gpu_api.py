@@ -229,3 +229,27 @@ def test_device_resident_input_and_slicing(engine):
     assert dev._atom_contacts == host._atom_contacts
     assert dev._residue_contacts == host._residue_contacts
     assert host._atom_contacts == goldens.counter(case["atom_pairs"], case["atom_counts"])
+
+
+def test_public_api_on_hashed_tables(engine, monkeypatch):
+    """Systems whose dense count table would be too large run on hashed tables transparently:
+    force that regime (global-memory cell path + a tiny dense limit) and compare the public
+    ContactFrequency / chunked runner results with the default (dense, fused) ones."""
+    from contact_map_b200.engine import ContactEngine, HashTable
+    case = goldens.load("syn_tric_sub")
+    traj = goldens.trajectory(case)
+    kw = goldens.call_kwargs(case)
+    want = cm.ContactFrequency(traj, **kw)
+    engine.set_option("force_path", 1)
+    monkeypatch.setattr(ContactEngine, "DENSE_LIMIT_BYTES", 1024)
+    try:
+        got = cm.ContactFrequency(traj, **kw)
+        assert isinstance(got._device_tables[0], HashTable)
+        assert got._atom_contacts == want._atom_contacts == goldens.counter(case["atom_pairs"], case["atom_counts"])
+        assert got._residue_contacts == want._residue_contacts
+        chunked = cm.ChunkedContactFrequency(traj, n_blocks=3, **kw)
+        assert chunked._atom_contacts == want._atom_contacts
+        assert chunked._residue_contacts == want._residue_contacts
+        assert chunked.n_frames == len(traj)
+    finally:
+        engine.set_option("force_path", -1)
