@@ -201,7 +201,8 @@ template <typename Traits>
 struct PairCtx {
     const float4* sorted;                       // [n] {wx, wy, wz, bits}: atom index, role (+ exclusion
                                                 // key in the fused kernel), layout known to Traits
-    const float* ekey;                          // [n] exclusion key per sorted position (global path)
+    const float2* kr;                           // [n] {exclusion key, compact residue (int bits)} per sorted
+                                                // position (global-memory path; nullptr in the fused kernel)
     const typename Traits::pos_t* cellptr;      // [ncell + 1]
     typename Traits::cand_t* cand;              // this warp's candidate list [CT_CAND]
     typename Traits::hit_t* hitq;               // this warp's ring [CT_QCAP]
@@ -309,7 +310,7 @@ __device__ __forceinline__ void ct_account(const PairParams& p, const PairCtx<Tr
                                 __fadd_rn(wj.z, sh.z));
     const unsigned bi = __float_as_uint(wi.w), bj = __float_as_uint(wj.w);
     const int ia = Traits::atom(bi), ib = Traits::atom(bj);
-    sink.prepare(ia, ib);                      // (the residue exclusion was part of the screen)
+    sink.prepare(cx, ipos, jpos, ia, ib);      // residues of the pair (the exclusion was part of the screen)
     bool elig = active;
     if (FLAGS & CT_ROLES) {
         const unsigned ri = Traits::role(bi), rj = Traits::role(bj);

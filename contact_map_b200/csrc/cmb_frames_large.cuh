@@ -23,6 +23,7 @@ namespace cmb {
 
 constexpr int LG_MAXC = 1 << 21;
 constexpr int LG_PAIR_THREADS = 256;
+constexpr int LG_RCACHE = 128;          // per-warp cache of stamped residue pairs (entries)
 
 struct LargeScratch {
     int cap_atoms = 0;
@@ -34,7 +35,7 @@ struct LargeScratch {
     float4* d_wrapped = nullptr;   // [n] {wrapped x, y, z, cell id}
     int* d_atomrank = nullptr;     // [n]
     float4* d_sorted = nullptr;    // [n]
-    float* d_sorted_ekey = nullptr;  // [n]
+    float2* d_sorted_kr = nullptr;   // [n] {exclusion key, compact residue}
     unsigned int* d_stamp = nullptr;
     size_t stamp_elems = 0;
     unsigned int seq = 0;
@@ -43,7 +44,7 @@ struct LargeScratch {
 inline void large_scratch_free(LargeScratch& S)
 {
     cudaFree(S.d_grid); cudaFree(S.d_cellcnt); cudaFree(S.d_cellptr); cudaFree(S.d_occ);
-    cudaFree(S.d_misc); cudaFree(S.d_wrapped); cudaFree(S.d_atomrank); cudaFree(S.d_sorted); cudaFree(S.d_sorted_ekey);
+    cudaFree(S.d_misc); cudaFree(S.d_wrapped); cudaFree(S.d_atomrank); cudaFree(S.d_sorted); cudaFree(S.d_sorted_kr);
     cudaFree(S.d_stamp);
     S = LargeScratch();
 }
@@ -98,7 +99,7 @@ struct LargeTraits {
     static __device__ __forceinline__ unsigned role(unsigned bits) { return bits >> 30; }
     static __device__ __forceinline__ float ekey_f(const PairCtx<LargeTraits>& cx, int pos, unsigned)
     {
-        return __ldg(cx.ekey + pos);
+        return __ldg(&cx.kr[pos]).x;
     }
     static __device__ __forceinline__ void decode(int c, const GridS& G, int& cx, int& cy, int& cz)
     {
@@ -195,6 +196,7 @@ struct StampSink {
     unsigned int atom_mask, res_mask;
     unsigned long long* hstats;     // [0] new atom keys, [1] new residue keys, [2] parked hits
     HashOverflow ovf;
+    unsigned int* rcache;           // this warp's residue pairs already stamped in this frame (shared memory)
     unsigned long long* res_keys;
     long long res_cap;
     unsigned long long* counters;
@@ -226,10 +228,12 @@ struct StampSink {
         pending = 0;
     }
 
-    __device__ __forceinline__ void prepare(int ia, int ib)
+    // residues from the per-position array: the positions of a task are neighbours in memory
+    // (L1 hits), where meta[atom] would be two random L2 sectors per pair
+    __device__ __forceinline__ void prepare(const PairCtx<LargeTraits>& cx, int ipos, int jpos, int, int)
     {
-        ra = __ldg(&meta[ia]).y & 0x3fffffff;
-        rb = __ldg(&meta[ib]).y & 0x3fffffff;
+        ra = __float_as_int(__ldg(&cx.kr[ipos]).y);
+        rb = __float_as_int(__ldg(&cx.kr[jpos]).y);
     }
 
     // called by the lanes of one drain whose pair is a hit
@@ -257,6 +261,13 @@ struct StampSink {
         const unsigned slot32 = rlo * n_res_c + rhi;     // R_c^2 < 2^32 (checked on the host)
         const unsigned peers = __match_any_sync(__activemask(), slot32);
         if ((__ffs(peers) - 1) == (int)(threadIdx.x & 31)) {
+            // the atom pairs of one residue pair come from the same few tasks: a small per-warp
+            // cache of the pairs this warp has stamped in this frame (= this launch) filters most
+            // repeats before they become atomics on the stamp table.  A tag is only ever written
+            // by a lane that goes on to stamp the pair, so a matching tag is always safe to skip.
+            unsigned int* tag = &rcache[slot32 & (LG_RCACHE - 1)];
+            if (*(volatile unsigned int*)tag == slot32) return;
+            *tag = slot32;
             unsigned where = slot32;                 // index into the stamp array
             if (res_mask) {
                 where = ht_find_or_insert(reinterpret_cast<unsigned long long*>(res_table), res_mask,
@@ -405,7 +416,7 @@ __global__ void __launch_bounds__(256) kl_scatter(int n, const int* __restrict__
                                                   const float4* __restrict__ wrapped,
                                                   const int* __restrict__ atomrank,
                                                   const int2* __restrict__ meta,
-                                                  float4* __restrict__ sorted, float* __restrict__ sorted_ekey)
+                                                  float4* __restrict__ sorted, float2* __restrict__ sorted_kr)
 {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 w = wrapped[i];
@@ -413,7 +424,8 @@ __global__ void __launch_bounds__(256) kl_scatter(int n, const int* __restrict__
         const int2 mw = __ldg(&meta[i]);
         const unsigned bits = (unsigned)i | ((unsigned)mw.y & (3u << 30));
         sorted[pos] = make_float4(w.x, w.y, w.z, __uint_as_float(bits));
-        sorted_ekey[pos] = (float)mw.x;          // keys are < 2^24 (checked on the host): exact
+        // keys are < 2^24 (checked on the host): exact as floats
+        sorted_kr[pos] = make_float2((float)mw.x, __int_as_float(mw.y & 0x3fffffff));
     }
 }
 
@@ -422,7 +434,7 @@ __global__ void __launch_bounds__(LG_PAIR_THREADS, 4) kl_pairs(PairParams pp, St
                                                                const float* __restrict__ box9, float cutoff,
                                                                const GridS* __restrict__ grid,
                                                                const float4* __restrict__ sorted,
-                                                               const float* __restrict__ sorted_ekey,
+                                                               const float2* __restrict__ sorted_kr,
                                                                const int* __restrict__ cellptr,
                                                                const int* __restrict__ occ, int* misc)
 {
@@ -430,10 +442,12 @@ __global__ void __launch_bounds__(LG_PAIR_THREADS, 4) kl_pairs(PairParams pp, St
     __shared__ uint4 hitq_all[(LG_PAIR_THREADS / 32) * CT_QCAP];
     __shared__ float4 shift_s[27];
     __shared__ float thresh_s[2];
+    __shared__ unsigned int rcache_all[(LG_PAIR_THREADS / 32) * LG_RCACHE];
     __shared__ GridS G;
     const int warp = threadIdx.x >> 5;
     if (threadIdx.x == 64) G = *grid;
     __syncthreads();
+    for (int t = threadIdx.x; t < (LG_PAIR_THREADS / 32) * LG_RCACHE; t += LG_PAIR_THREADS) rcache_all[t] = 0xffffffffu;
     if (threadIdx.x < 27) shift_s[threadIdx.x] = lattice_shift(box9, threadIdx.x);
     if (threadIdx.x == 32) {
         float lo, hi;
@@ -444,12 +458,13 @@ __global__ void __launch_bounds__(LG_PAIR_THREADS, 4) kl_pairs(PairParams pp, St
     __syncthreads();
     pp.c2_lo = thresh_s[0]; pp.c2_hi = thresh_s[1];
     PairCtx<LargeTraits> cx;
-    cx.sorted = sorted; cx.ekey = sorted_ekey; cx.cellptr = cellptr;
+    cx.sorted = sorted; cx.kr = sorted_kr; cx.cellptr = cellptr;
     cx.cand = cand_all + warp * CT_CAND; cx.hitq = hitq_all + warp * CT_QCAP;
     cx.shift = shift_s;
     unsigned long long n_tests = 0;
     StampSink sink = sink_in;
     sink.pending = 0; sink.pend_old = 0u; sink.pend_lo = sink.pend_hi = 0u;
+    sink.rcache = rcache_all + warp * LG_RCACHE;
     ct_pair_phase_dyn<LargeTraits, StampSink, FLAGS, int>(pp, G, cx, sink, occ, misc[0], &misc[1], n_tests);
     sink.resolve();
     if (FLAGS & CT_COUNT) {
@@ -473,9 +488,9 @@ inline int large_run(const LargeJob& job, LargeScratch& S, int sm_count, cudaStr
 {
     const int n = job.n;
     if (S.cap_atoms < n) {
-        cudaFree(S.d_wrapped); cudaFree(S.d_atomrank); cudaFree(S.d_sorted); cudaFree(S.d_sorted_ekey);
-        S.d_atomrank = nullptr; S.d_sorted = nullptr; S.d_wrapped = nullptr; S.d_sorted_ekey = nullptr;
-        LG_CK(cudaMalloc(&S.d_sorted_ekey, sizeof(float) * (size_t)n));
+        cudaFree(S.d_wrapped); cudaFree(S.d_atomrank); cudaFree(S.d_sorted); cudaFree(S.d_sorted_kr);
+        S.d_atomrank = nullptr; S.d_sorted = nullptr; S.d_wrapped = nullptr; S.d_sorted_kr = nullptr;
+        LG_CK(cudaMalloc(&S.d_sorted_kr, sizeof(float2) * (size_t)n));
         LG_CK(cudaMalloc(&S.d_wrapped, sizeof(float4) * (size_t)n));
         LG_CK(cudaMalloc(&S.d_atomrank, sizeof(int) * (size_t)n));
         LG_CK(cudaMalloc(&S.d_sorted, sizeof(float4) * (size_t)n));
@@ -522,7 +537,7 @@ inline int large_run(const LargeJob& job, LargeScratch& S, int sm_count, cudaStr
         kl_bin<<<atom_blocks, 256, 0, stream>>>(x, n, S.d_grid, S.d_cellcnt, S.d_wrapped, S.d_atomrank, S.d_misc);
         kl_scan<<<1, 1024, 0, stream>>>(S.d_grid, n, S.d_cellcnt, S.d_cellptr, S.d_occ, S.d_misc);
         kl_scatter<<<atom_blocks, 256, 0, stream>>>(n, S.d_cellptr, S.d_wrapped, S.d_atomrank, job.meta, S.d_sorted,
-                                                    S.d_sorted_ekey);
+                                                    S.d_sorted_kr);
         PairParams pp;
         pp.n = n; pp.n_ignored = job.n_ignored; pp.c2 = job.c2; pp.c2_lo = pp.c2_hi = job.c2;
         pp.boundary_ulps = job.boundary_ulps; pp.xyz = x; pp.box = box9; pp.f = 0; pp.frame0 = job.frame0 + f;
@@ -543,19 +558,19 @@ inline int large_run(const LargeJob& job, LargeScratch& S, int sm_count, cudaStr
         const bool emit = job.atom_keys != nullptr;
         if (job.boundary_ulps > 0)
             kl_pairs<CT_BOUNDARY | CT_ROLES><<<pg, LG_PAIR_THREADS, 0, stream>>>(
-                pp, sink, box9, job.cutoff, S.d_grid, S.d_sorted, S.d_sorted_ekey, S.d_cellptr, S.d_occ, S.d_misc);
+                pp, sink, box9, job.cutoff, S.d_grid, S.d_sorted, S.d_sorted_kr, S.d_cellptr, S.d_occ, S.d_misc);
         else if (job.count_tests && !emit)
             kl_pairs<CT_COUNT | CT_ROLES><<<pg, LG_PAIR_THREADS, 0, stream>>>(
-                pp, sink, box9, job.cutoff, S.d_grid, S.d_sorted, S.d_sorted_ekey, S.d_cellptr, S.d_occ, S.d_misc);
+                pp, sink, box9, job.cutoff, S.d_grid, S.d_sorted, S.d_sorted_kr, S.d_cellptr, S.d_occ, S.d_misc);
         else if (emit)
             kl_pairs<CT_EMIT | CT_ROLES><<<pg, LG_PAIR_THREADS, 0, stream>>>(
-                pp, sink, box9, job.cutoff, S.d_grid, S.d_sorted, S.d_sorted_ekey, S.d_cellptr, S.d_occ, S.d_misc);
+                pp, sink, box9, job.cutoff, S.d_grid, S.d_sorted, S.d_sorted_kr, S.d_cellptr, S.d_occ, S.d_misc);
         else if (job.all_roles)
             kl_pairs<0><<<pg, LG_PAIR_THREADS, 0, stream>>>(
-                pp, sink, box9, job.cutoff, S.d_grid, S.d_sorted, S.d_sorted_ekey, S.d_cellptr, S.d_occ, S.d_misc);
+                pp, sink, box9, job.cutoff, S.d_grid, S.d_sorted, S.d_sorted_kr, S.d_cellptr, S.d_occ, S.d_misc);
         else
             kl_pairs<CT_ROLES><<<pg, LG_PAIR_THREADS, 0, stream>>>(
-                pp, sink, box9, job.cutoff, S.d_grid, S.d_sorted, S.d_sorted_ekey, S.d_cellptr, S.d_occ, S.d_misc);
+                pp, sink, box9, job.cutoff, S.d_grid, S.d_sorted, S.d_sorted_kr, S.d_cellptr, S.d_occ, S.d_misc);
         launches += 5;
     }
     LG_CK(cudaGetLastError());

@@ -222,7 +222,7 @@ struct BitmapSink {
     unsigned n;
     unsigned n_res_c;
     unsigned ra, rb;          // compact residues of the pair handed to prepare()
-    __device__ __forceinline__ void prepare(int ia, int ib)
+    __device__ __forceinline__ void prepare(const PairCtx<SmallTraits>&, int, int, int ia, int ib)
     {
         ra = (__ldg(&meta32[ia]) >> FS_EKEY_BITS) & FS_RES_MASK;
         rb = (__ldg(&meta32[ib]) >> FS_EKEY_BITS) & FS_RES_MASK;
@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(FS_THREADS, FS_MIN_CTAS) k_frames_small(const 
         pp.boundary = p.boundary; pp.boundary_cap = p.boundary_cap;
         PairCtx<SmallTraits> cx;
         cx.sorted = sorted; cx.cellptr = cell16; cx.cand = cand; cx.hitq = hitq;
-        cx.shift = shift_s; cx.ekey = nullptr;
+        cx.shift = shift_s; cx.kr = nullptr;
         BitmapSink sink{p.meta32, p.atom_table, bitmap, (unsigned)n, (unsigned)p.n_res_c, 0u, 0u};
         ct_pair_phase_dyn<SmallTraits, BitmapSink, FLAGS, unsigned short>(pp, G, cx, sink, occ, *n_occ_s,
                                                                           task_counter, n_tests);
