@@ -790,7 +790,7 @@ extern "C" int cmb_export_nonzero(cmb_ctx* ctx, const uint32_t* d_table, int64_t
     const long long maxb = (long long)ctx->sm_count * 8;
     if (blocks > maxb) blocks = maxb;
     if (blocks < 1) blocks = 1;
-    k_export_nonzero<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+    k_export_nonzero<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         d_table, n_elems, cap, (long long*)d_idx, d_cnt, (unsigned long long*)d_n);
     CK(cudaGetLastError());
     ctx->stats["kernel_launches"] += 1;
@@ -809,29 +809,42 @@ extern "C" int cmb_export_sorted(cmb_ctx* ctx, const void* d_table, int64_t n_el
     if (((uintptr_t)d_table & 15) != 0) return fail(ctx, CMB_ERR_ARG, "table must be 16-byte aligned");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
+    if (log2_slots <= 0) {
+        // dense table: ordered two-pass export, no sort
+        CK(cudaMemsetAsync(d_n, 0, 16, st));
+        const long long nvec = n_elems >> 2;
+        long long blocks = std::min<long long>((nvec + 32 * 8 * 8 - 1) / (32 * 8 * 8), (long long)ctx->sm_count * 8);
+        if (blocks < 1) blocks = 1;
+        const long long n_warps = blocks * (EO_THREADS / 32);
+        long long span = (nvec + n_warps - 1) / n_warps;
+        span = (span + 31) / 32 * 32;                      // whole warp iterations
+        if (span < 32) span = 32;
+        int rc = ensure_bytes(ctx, &ctx->d_tmp, &ctx->tmp_bytes, (size_t)n_warps * sizeof(int));
+        if (rc) return rc;
+        int* counts = reinterpret_cast<int*>(ctx->d_tmp);
+        k_export_count<<<(unsigned)blocks, EO_THREADS, 0, st>>>(reinterpret_cast<const unsigned int*>(d_table), n_elems,
+                                                                span, counts);
+        k_export_write<<<(unsigned)blocks, EO_THREADS, 0, st>>>(reinterpret_cast<const unsigned int*>(d_table), n_elems,
+                                                                span, counts, cap,
+                                                                reinterpret_cast<unsigned long long*>(d_packed),
+                                                                reinterpret_cast<unsigned long long*>(d_n));
+        CK(cudaGetLastError());
+        ctx->stats["kernel_launches"] += 2;
+        return CMB_OK;
+    }
     CK(cudaMemsetAsync(d_packed, 0xff, (size_t)cap * 8, st));
     CK(cudaMemsetAsync(d_n, 0, 16, st));
-    if (log2_slots > 0) {
+    {
         const long long n_slots = 1ll << log2_slots;
         const int grid = (int)std::min<long long>((n_slots + 255) / 256, (long long)ctx->sm_count * 16);
         k_export_hashed<true><<<grid, 256, 0, st>>>(reinterpret_cast<const unsigned long long*>(d_table), n_slots, cap,
                                                     reinterpret_cast<long long*>(d_packed), nullptr,
                                                     reinterpret_cast<unsigned long long*>(d_n));
-    } else if (n_elems > 0) {
-        long long blocks = std::min<long long>((n_elems / 4 + 255) / 256, (long long)ctx->sm_count * 8);
-        if (blocks < 1) blocks = 1;
-        k_export_nonzero<true><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const unsigned int*>(d_table), n_elems, cap,
-                                                                 reinterpret_cast<long long*>(d_packed), nullptr,
-                                                                 reinterpret_cast<unsigned long long*>(d_n));
     }
     CK(cudaGetLastError());
     ctx->stats["kernel_launches"] += 1;
-    // the indices are distinct: sort on the index bits only.  2^bits > largest index + 1, so the
-    // all-ones padding sorts behind every entry.
-    const unsigned long long span = log2_slots > 0 ? (1ull << 40) : (unsigned long long)std::max<int64_t>(n_elems, 1);
-    int bits = 1;
-    while (bits < 40 && (1ull << bits) <= span) bits++;
-    return sort_key_bits(ctx, d_packed, cap, 24, 24 + bits, st);
+    // the indices are distinct: sort on the index bits only (the all-ones padding sorts last)
+    return sort_key_bits(ctx, d_packed, cap, 24, 64, st);
 }
 
 extern "C" int cmb_group_contacts(cmb_ctx* ctx, const float* d_xyz, const float* d_box, int64_t n_frames, int n_atoms,

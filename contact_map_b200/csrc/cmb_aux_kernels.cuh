@@ -99,9 +99,6 @@ __global__ void __launch_bounds__(256) k_hash_add(unsigned long long* __restrict
 // ---------------------------------------------------------------------------------
 // sparse export of a uint32 count table (result container of contact_map.py:724-744)
 // ---------------------------------------------------------------------------------
-// PACKED: out_idx receives (flat index << 24 | count), out_cnt is unused and out_n[1] is set when
-// a count does not fit 24 bits (cmb_export_sorted then reports CMB_ERR_LIMIT)
-template <bool PACKED>
 __global__ void __launch_bounds__(256) k_export_nonzero(const unsigned int* __restrict__ table,
                                                         long long n_elems, long long cap,
                                                         long long* __restrict__ out_idx,
@@ -138,13 +135,8 @@ __global__ void __launch_bounds__(256) k_export_nonzero(const unsigned int* __re
         for (int k = 0; k < 4; k++) {
             if (vals[k]) {
                 if ((long long)w < cap) {
-                    if (PACKED) {
-                        out_idx[w] = ((v * 4 + k) << 24) | (long long)(vals[k] & 0xffffffu);
-                        if (vals[k] >> 24) out_n[1] = 1ull;
-                    } else {
-                        out_idx[w] = v * 4 + k;
-                        out_cnt[w] = vals[k];
-                    }
+                    out_idx[w] = v * 4 + k;
+                    out_cnt[w] = vals[k];
                 }
                 w++;
             }
@@ -156,18 +148,104 @@ __global__ void __launch_bounds__(256) k_export_nonzero(const unsigned int* __re
             const unsigned val = table[e];
             if (val) {
                 const unsigned long long w = atomicAdd(out_n, 1ull);
-                if ((long long)w < cap) {
-                    if (PACKED) {
-                        out_idx[w] = (e << 24) | (long long)(val & 0xffffffu);
-                        if (val >> 24) out_n[1] = 1ull;
-                    } else {
-                        out_idx[w] = e;
-                        out_cnt[w] = val;
-                    }
-                }
+                if ((long long)w < cap) { out_idx[w] = e; out_cnt[w] = val; }
             }
         }
     }
+}
+
+// ---------------------------------------------------------------------------------
+// ordered sparse export of a dense table in two passes (no atomics, no sort): every warp owns a
+// contiguous span of the table; pass 1 counts its non-zero entries, pass 2 turns the counts into
+// offsets (each block sums the counts of the warps before it) and writes the packed
+// (flat index << 24 | count) words in index order.
+// ---------------------------------------------------------------------------------
+constexpr int EO_THREADS = 256;
+
+__device__ __forceinline__ int eo_count4(const uint4& q) { return (q.x != 0) + (q.y != 0) + (q.z != 0) + (q.w != 0); }
+
+__global__ void __launch_bounds__(EO_THREADS) k_export_count(const unsigned int* __restrict__ table, long long n_elems,
+                                                             long long span_vec, int* __restrict__ counts)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = (long long)blockIdx.x * (EO_THREADS / 32) + (threadIdx.x >> 5);
+    const long long nvec = n_elems >> 2;
+    const uint4* __restrict__ t4 = reinterpret_cast<const uint4*>(table);
+    const long long v0 = warp * span_vec, v1 = min(nvec, v0 + span_vec);
+    int mine = 0;
+    for (long long v = v0 + lane; v < v1; v += 32) mine += eo_count4(__ldg(&t4[v]));
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
+    if (lane == 0) counts[warp] = mine;
+}
+
+__global__ void __launch_bounds__(EO_THREADS) k_export_write(const unsigned int* __restrict__ table, long long n_elems,
+                                                             long long span_vec, const int* __restrict__ counts,
+                                                             long long cap, unsigned long long* __restrict__ out,
+                                                             unsigned long long* __restrict__ out_n)
+{
+    __shared__ long long red[EO_THREADS / 32];
+    __shared__ long long block_base;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long first_warp = (long long)blockIdx.x * (EO_THREADS / 32);
+    const long long n_warps = (long long)gridDim.x * (EO_THREADS / 32);
+    // offset of this block's first warp: sum of the counts of all earlier warps
+    long long part = 0;
+    for (long long w = threadIdx.x; w < first_warp; w += EO_THREADS) part += counts[w];
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+    if (lane == 0) red[wib] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long b = 0;
+        for (int k = 0; k < EO_THREADS / 32; k++) b += red[k];
+        block_base = b;
+    }
+    __syncthreads();
+    long long base = block_base;
+    for (int k = 0; k < wib; k++) base += counts[first_warp + k];
+
+    const long long warp = first_warp + wib;
+    const long long nvec = n_elems >> 2;
+    const uint4* __restrict__ t4 = reinterpret_cast<const uint4*>(table);
+    const long long v0 = warp * span_vec, v1 = min(nvec, v0 + span_vec);
+    bool wide = false;
+    for (long long vb = v0; vb < v1; vb += 32) {            // uniform trip count per warp
+        const long long v = vb + lane;
+        uint4 q = make_uint4(0u, 0u, 0u, 0u);
+        if (v < v1) q = __ldg(&t4[v]);
+        const unsigned vals[4] = {q.x, q.y, q.z, q.w};
+        const int mine = eo_count4(q);
+        int incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += u;
+        }
+        long long w = base + (incl - mine);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (vals[k]) {
+                if (w < cap) out[w] = ((unsigned long long)(v * 4 + k) << 24) | (unsigned long long)(vals[k] & 0xffffffu);
+                wide = wide || (vals[k] >> 24);
+                w++;
+            }
+        }
+        base += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (warp == n_warps - 1 && lane == 0) {
+        // tail (n_elems % 4) and the total
+        for (long long e = nvec * 4; e < n_elems; e++) {
+            const unsigned val = table[e];
+            if (val) {
+                if (base < cap) out[base] = ((unsigned long long)e << 24) | (unsigned long long)(val & 0xffffffu);
+                wide = wide || (val >> 24);
+                base++;
+            }
+        }
+        out_n[0] = (unsigned long long)base;
+    }
+    if (wide) out_n[1] = 1ull;
 }
 
 // ---------------------------------------------------------------------------------

@@ -143,8 +143,10 @@ int cmb_export_nonzero(cmb_ctx* ctx, const uint32_t* d_table, int64_t n_elems, i
 
 /*
  * Sorted sparse export (the form the Python layer consumes): d_packed[cap] receives
- * (flat index << 24 | count) of the non-zero entries in ascending index order, padded with
- * 0xff..ff; d_n[0] = entries found (those beyond cap are dropped: retry with a larger buffer),
+ * (flat index << 24 | count) of the non-zero entries in ascending index order (dense tables: an
+ * ordered two-pass scan, no sort; hashed tables: unordered scan + radix sort on the index bits,
+ * unused tail of d_packed = 0xff..ff); d_n[0] = entries found (those beyond cap are dropped: retry
+ * with a larger buffer),
  * d_n[1] != 0 if a count did not fit 24 bits (use cmb_export_nonzero then).  log2_slots > 0:
  * d_table is a hashed table of 2^log2_slots slots, else a dense uint32 table of n_elems entries.
  */
