@@ -14,9 +14,9 @@
 //      has consumed the buffer, so it overlaps the pair phase;
 //   2. atoms are binned into >= cutoff-wide cells of the (orthorhombic / triclinic /
 //      open) cell grid: u16 shared-memory histogram, block scan, scatter into a
-//      cell-sorted float4 array {wrapped x, y, z, atom index | role << 30};
-//   3. one warp per occupied cell: the candidate atoms of the half shell
-//      (neighbour cells with id >= own) are held in registers (3 per lane), the
+//      cell-sorted float4 array {wrapped x, y, z, atom index | role | exclusion key};
+//   3. one warp per task (an occupied cell, or two sparse x-adjacent cells): the candidate atoms of the half shell
+//      (neighbour cells with id >= own) are held in registers (up to 4 per lane), the
 //      cell's own atoms are broadcast from shared memory, every candidate pair is
 //      SCREENED with an FMA distance on the wrapped coordinates, and the few pairs the
 //      per-frame error bound cannot decide are adjudicated with MDTraj's exact float32
@@ -41,9 +41,9 @@ constexpr int FS_MAX_ATOMS = FS_THREADS * FS_APT;   // 6144
 constexpr int FS_HEADER_BYTES = 2048;
 constexpr int FS_CAND = CT_CAND;
 constexpr int FS_QCAP = CT_QCAP;
-// header layout (bytes): mbarrier 0, task counter 8, occupied cells 12, thresholds 16/20,
-// ring counters 32, per-warp max|coordinate| 96, reduction scratch 256, grid 1024, shifts 1536
-constexpr int FS_H_QCNT = 32, FS_H_AMAX = 96, FS_H_RED = 256, FS_H_GRID = 1024, FS_H_SHIFT = 1536;
+// header layout (bytes): mbarrier 0, task counter 8, task count 12, thresholds 16/20,
+// per-warp max|coordinate| 96, reduction scratch 256, grid 1024, shifts 1536
+constexpr int FS_H_AMAX = 96, FS_H_RED = 256, FS_H_GRID = 1024, FS_H_SHIFT = 1536;
 
 // packed per-atom meta word: ekey [0,16) | compact residue [16,29) | role [30,32)
 constexpr unsigned FS_EKEY_BITS = 16;
