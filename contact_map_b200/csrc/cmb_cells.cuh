@@ -232,47 +232,50 @@ __device__ __forceinline__ void ring_push(const PairCtx<Traits>& cx, Ring& ring,
 }
 
 // Per-frame thresholds.  A = max |raw coordinate| of the frame, box9 = unit cell rows or nullptr.
-// Bound on |d2_exact - d2_screen| for pairs whose distance is near the cutoff (DESIGN.md 4.1):
+// Bound on |d2_exact - d2_screen| for pairs whose distance is near the cutoff (DESIGN.md 4.0):
 // per-component error of the exact chain <= 8u * (largest intermediate magnitude), of the
 // screening chain <= 10u * (sum of |box entries|) (wrapped position, shift, subtraction);
 // both chains resolve the same periodic image when the stencil cells are distinct, the box is
 // lower triangular and the image counts stay far below 2^23.  The rounding of either
-// accumulation order of the squares is covered by the 24u c^2 term.
-__device__ inline void frame_margins(const float* box9, int distinct, double A, float c2, double cutoff,
+// accumulation order of the squares is covered by the 24u c^2 term.  Evaluated in fp32 (one
+// thread, on the critical path of the frame): every quantity is non-negative and only an upper
+// bound is needed, so the fp32 rounding of this evaluation itself is absorbed by the 1.01 factor
+// on the final margin, which is then applied with directed rounding.
+__device__ inline void frame_margins(const float* box9, int distinct, float A, float c2, float cutoff,
                                      int extra_ulps, float& c2_lo, float& c2_hi)
 {
-    const double u = 5.9604644775390625e-8;   // 2^-24
+    const float u = 5.9604644775390625e-8f;   // 2^-24
     bool ok = true;
-    double e;
+    float e;
     if (box9 == nullptr) {
-        e = 4.0 * u * A;
+        e = 4.0f * u * A;
     } else {
-        const double ax = box9[0], ay = box9[1], az = box9[2], bx = fabs((double)box9[3]), by = box9[4],
-                     bz = box9[5], cx = fabs((double)box9[6]), cy = fabs((double)box9[7]), cz = box9[8];
-        ok = distinct && ay == 0.0 && az == 0.0 && bz == 0.0 && ax > 0.0 && by > 0.0 && cz > 0.0;
-        const double sc = 2.0 * A / cz + 2.0;
-        const double sb = (2.0 * A + sc * cy) / by + 2.0;
-        const double sa = (2.0 * A + sc * cx + sb * bx) / ax + 2.0;
-        ok = ok && sa < 1.0e5 && sb < 1.0e5 && sc < 1.0e5;
-        const double mx = 2.0 * A + sc * cx + sb * bx + sa * ax;
-        const double my = 2.0 * A + sc * cy + sb * by;
-        const double mz = 2.0 * A + sc * cz;
-        const double mmax = fmax(mx, fmax(my, mz));
-        const double S = ax + bx + by + cx + cy + cz;
-        e = 8.0 * u * mmax + 10.0 * u * S + 1.0e-15 * mmax;
+        const float ax = box9[0], ay = box9[1], az = box9[2], bx = fabsf(box9[3]), by = box9[4],
+                    bz = box9[5], cx = fabsf(box9[6]), cy = fabsf(box9[7]), cz = box9[8];
+        ok = distinct && ay == 0.f && az == 0.f && bz == 0.f && ax > 0.f && by > 0.f && cz > 0.f;
+        const float sc = 2.0f * A / cz + 2.0f;
+        const float sb = (2.0f * A + sc * cy) / by + 2.0f;
+        const float sa = (2.0f * A + sc * cx + sb * bx) / ax + 2.0f;
+        ok = ok && sa < 1.0e5f && sb < 1.0e5f && sc < 1.0e5f;
+        const float mx = 2.0f * A + sc * cx + sb * bx + sa * ax;
+        const float my = 2.0f * A + sc * cy + sb * by;
+        const float mz = 2.0f * A + sc * cz;
+        const float mmax = fmaxf(mx, fmaxf(my, mz));
+        const float S = ax + bx + by + cx + cy + cz;
+        e = 8.0f * u * mmax + 10.0f * u * S + 1.0e-15f * mmax;
     }
-    const double c = cutoff * 1.01;
-    const double bound = 1.7320508075688772 * e * (2.0 * c + 2.0 * e) + 24.0 * u * c * c;
-    const double M = 2.0 * bound;
-    ok = ok && (M < 0.25 * (double)c2);
+    const float c = cutoff * 1.01f;
+    const float bound = 1.7320508f * e * (2.0f * c + 2.0f * e) + 24.0f * u * c * c;
+    const float M = 2.0f * 1.01f * bound;
+    ok = ok && (M < 0.25f * c2);        // also false for NaN
     if (!ok) {
         // adjudicate everything exactly; still below CT_FAR^2, so that empty slots never pass
         c2_lo = -1.0e30f;
         c2_hi = 1.0e30f;
         return;
     }
-    c2_lo = __double2float_rd((double)c2 - M);
-    c2_hi = __double2float_ru((double)c2 + M);
+    c2_lo = __fsub_rd(c2, M);
+    c2_hi = __fadd_ru(c2, M);
     if (extra_ulps > 0) {
         c2_lo = fminf(c2_lo, __int_as_float(__float_as_int(c2) - extra_ulps - 1));
         c2_hi = fmaxf(c2_hi, __int_as_float(__float_as_int(c2) + extra_ulps + 1));

@@ -451,8 +451,7 @@ __global__ void __launch_bounds__(LG_PAIR_THREADS, 4) kl_pairs(PairParams pp, St
     if (threadIdx.x < 27) shift_s[threadIdx.x] = lattice_shift(box9, threadIdx.x);
     if (threadIdx.x == 32) {
         float lo, hi;
-        frame_margins(box9, G.distinct, (double)__int_as_float(misc[2]), pp.c2, (double)cutoff, pp.boundary_ulps,
-                      lo, hi);
+        frame_margins(box9, G.distinct, __int_as_float(misc[2]), pp.c2, cutoff, pp.boundary_ulps, lo, hi);
         thresh_s[0] = lo; thresh_s[1] = hi;
     }
     __syncthreads();

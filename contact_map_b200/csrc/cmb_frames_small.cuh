@@ -41,7 +41,7 @@ constexpr int FS_MAX_ATOMS = FS_THREADS * FS_APT;   // 6144
 constexpr int FS_HEADER_BYTES = 2048;
 constexpr int FS_CAND = CT_CAND;
 constexpr int FS_QCAP = CT_QCAP;
-// header layout (bytes): mbarrier 0, task counter 8, task count 12, thresholds 16/20,
+// header layout (bytes): mbarrier 0, task counter 8, task count 12, thresholds 16/20, grid cache 24..68,
 // per-warp max|coordinate| 96, reduction scratch 256, grid 1024, shifts 1536
 constexpr int FS_H_AMAX = 96, FS_H_RED = 256, FS_H_GRID = 1024, FS_H_SHIFT = 1536;
 
@@ -219,6 +219,8 @@ struct BitmapSink {
     const unsigned int* meta32;
     unsigned int* atom_table;
     unsigned int* bitmap;
+    unsigned int* res_inline;  // residue table when a new bit is counted at once (nullptr: the
+                               // end-of-frame sweep counts / emits the set bits)
     unsigned n;
     unsigned n_res_c;
     unsigned ra, rb;          // compact residues of the pair handed to prepare()
@@ -234,7 +236,11 @@ struct BitmapSink {
         const unsigned bit = min(ra, rb) * n_res_c + max(ra, rb);
         const unsigned msk = 1u << (bit & 31);
         unsigned int* wp = &bitmap[bit >> 5];
-        if (!(*(volatile unsigned int*)wp & msk)) atomicOr(wp, msk);
+        if (!(*(volatile unsigned int*)wp & msk)) {
+            const unsigned old = atomicOr(wp, msk);
+            // first hit of this residue pair in this frame (per-frame set semantics)
+            if (res_inline != nullptr && !(old & msk)) atomicAdd(&res_inline[bit], 1u);
+        }
     }
 };
 
@@ -255,6 +261,8 @@ __global__ void __launch_bounds__(FS_THREADS, FS_MIN_CTAS) k_frames_small(const 
     int* task_counter = reinterpret_cast<int*>(smem + 8);
     int* n_occ_s = reinterpret_cast<int*>(smem + 12);
     float* thresh_s = reinterpret_cast<float*>(smem + 16);                 // {c2_lo, c2_hi} of the frame
+    unsigned int* box_valid_s = reinterpret_cast<unsigned int*>(smem + 24);   // grid cache: box it was built for
+    unsigned int* box_saved_s = reinterpret_cast<unsigned int*>(smem + 32);   // [9]
     float* amax_s = reinterpret_cast<float*>(smem + FS_H_AMAX);
     float* red = reinterpret_cast<float*>(smem + FS_H_RED);                // 6 * 32 floats
     unsigned int* scan_s = reinterpret_cast<unsigned int*>(smem + FS_H_RED);   // overlays `red`
@@ -274,6 +282,7 @@ __global__ void __launch_bounds__(FS_THREADS, FS_MIN_CTAS) k_frames_small(const 
     if (tid == 0) {
         mbar_init(mbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        *box_valid_s = 0u;
     }
     for (int w = tid; w < p.bm_words; w += FS_THREADS) bitmap[w] = 0u;
     __syncthreads();
@@ -336,7 +345,16 @@ __global__ void __launch_bounds__(FS_THREADS, FS_MIN_CTAS) k_frames_small(const 
             }
         }
         if (tid == 0) {
-            make_grid(*Gs, box9, (double)p.cutoff, p.maxc, lo, hi);
+            // the grid only depends on the box: constant-volume trajectories build it once
+            bool same = box9 != nullptr && *box_valid_s != 0;
+            if (same)
+                for (int k = 0; k < 9; k++) same = same && (__float_as_uint(box9[k]) == box_saved_s[k]);
+            if (!same) {
+                make_grid(*Gs, box9, (double)p.cutoff, p.maxc, lo, hi);
+                *box_valid_s = box9 != nullptr;
+                if (box9 != nullptr)
+                    for (int k = 0; k < 9; k++) box_saved_s[k] = __float_as_uint(box9[k]);
+            }
             *task_counter = 0;
         }
         __syncthreads();
@@ -372,7 +390,7 @@ __global__ void __launch_bounds__(FS_THREADS, FS_MIN_CTAS) k_frames_small(const 
             float A = 0.f;
             for (int w = 0; w < FS_WARPS; w++) A = fmaxf(A, amax_s[w]);
             float c2_lo, c2_hi;
-            frame_margins(box9, G.distinct, (double)A, p.c2, (double)p.cutoff, p.boundary_ulps, c2_lo, c2_hi);
+            frame_margins(box9, G.distinct, A, p.c2, p.cutoff, p.boundary_ulps, c2_lo, c2_hi);
             thresh_s[0] = c2_lo; thresh_s[1] = c2_hi;
         }
         if (tid >= 64 && tid < 64 + 27) shift_s[tid - 64] = lattice_shift(box9, tid - 64);
@@ -469,12 +487,19 @@ __global__ void __launch_bounds__(FS_THREADS, FS_MIN_CTAS) k_frames_small(const 
         PairCtx<SmallTraits> cx;
         cx.sorted = sorted; cx.cellptr = cell16; cx.cand = cand; cx.hitq = hitq;
         cx.shift = shift_s; cx.kr = nullptr;
-        BitmapSink sink{p.meta32, p.atom_table, bitmap, (unsigned)n, (unsigned)p.n_res_c, 0u, 0u};
+        // without residue keys the residue table is updated at the first hit of a pair and the
+        // end-of-frame pass only clears the bitmap
+        const bool res_at_once = p.res_table != nullptr && !((FLAGS & FS_EMIT) && p.res_keys != nullptr);
+        BitmapSink sink{p.meta32, p.atom_table, bitmap, res_at_once ? p.res_table : nullptr, (unsigned)n,
+                        (unsigned)p.n_res_c, 0u, 0u};
         ct_pair_phase_dyn<SmallTraits, BitmapSink, FLAGS, unsigned short>(pp, G, cx, sink, occ, *n_occ_s,
                                                                           task_counter, n_tests);
         __syncthreads();
 
-        // ---- pass E: flush the per-frame residue bitmap ------------------------------
+        // ---- pass E: clear / flush the per-frame residue bitmap -----------------------
+        if (res_at_once) {
+            for (int w = tid; w < p.bm_words; w += FS_THREADS) bitmap[w] = 0u;
+        } else
         for (int w = tid; w < p.bm_words; w += FS_THREADS) {
             unsigned v = bitmap[w];
             if (v) {
