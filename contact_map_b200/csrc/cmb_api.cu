@@ -70,6 +70,7 @@ struct cmb_ctx {
     // options / stats
     int count_tests = 0;
     int pair_tasks = 1;
+    int stage_pageable = 1;                   // pageable host input goes through threaded pinned staging
     int atom_log2 = 0, res_log2 = 0;          // hashed count tables when > 0 (cmb_set_table_mode)
     unsigned long long* d_hstats = nullptr;   // [4] new atom keys, new residue keys, parked hits, failed re-inserts
     unsigned long long* d_ovf = nullptr;      // caller-owned overflow list (cmb_hash_overflow_buffer)
@@ -179,6 +180,7 @@ extern "C" int cmb_set_option(cmb_ctx* ctx, const char* name, int64_t value)
     if (!ctx || !name) return CMB_ERR_ARG;
     if (!strcmp(name, "count_tests")) { ctx->count_tests = value != 0; return CMB_OK; }
     if (!strcmp(name, "pair_tasks")) { ctx->pair_tasks = value != 0; return CMB_OK; }
+    if (!strcmp(name, "stage_pageable")) { ctx->stage_pageable = value != 0; return CMB_OK; }
     if (!strcmp(name, "max_cells")) {
         if (value < 8 || value > 16383) return fail(ctx, CMB_ERR_ARG, "max_cells out of range");
         ctx->fs_maxc = (int)value;
@@ -499,6 +501,10 @@ static int ensure_staging(cmb_ctx* ctx, int64_t chunk_frames, bool with_box)
     return CMB_OK;
 }
 
+static int accumulate_staged(cmb_ctx* ctx, const float* h_xyz_full, int n_total, const int32_t* h_used,
+                             const float* h_box, int64_t n_frames, int64_t chunk_frames, int n_threads,
+                             uint32_t* d_atom_table, uint32_t* d_res_table);
+
 extern "C" int cmb_accumulate_host(cmb_ctx* ctx, const float* h_xyz, const float* h_box, int64_t n_frames,
                                    int64_t chunk_frames, uint32_t* d_atom_table, uint32_t* d_res_table)
 {
@@ -507,6 +513,17 @@ extern "C" int cmb_accumulate_host(cmb_ctx* ctx, const float* h_xyz, const float
     if (n_frames <= 0) return CMB_OK;
     if (!h_xyz) return fail(ctx, CMB_ERR_ARG, "xyz is NULL");
     CK(cudaSetDevice(ctx->device));
+    if (ctx->stage_pageable) {
+        // pageable memory (an ordinary numpy array, a memory-mapped file): cudaMemcpyAsync would
+        // stage it synchronously chunk by chunk; host threads copying into the pinned staging
+        // buffers while earlier chunks are transferred and processed keep the pipeline full
+        cudaPointerAttributes attr;
+        const cudaError_t e = cudaPointerGetAttributes(&attr, h_xyz);
+        if (e != cudaSuccess) cudaGetLastError();
+        if (e != cudaSuccess || attr.type == cudaMemoryTypeUnregistered)
+            return accumulate_staged(ctx, h_xyz, ctx->n, nullptr, h_box, n_frames, chunk_frames, 0, d_atom_table,
+                                     d_res_table);
+    }
     const size_t frame_bytes = (size_t)ctx->n * 12;
     chunk_frames = pick_chunk(ctx, n_frames, chunk_frames);
     int rc0 = ensure_staging(ctx, chunk_frames, h_box != nullptr);
@@ -539,6 +556,11 @@ static void gather_chunk(const float* full, int n_total, const int32_t* used, in
                          int64_t nf, float* out, int n_threads)
 {
     auto work = [=](int64_t a, int64_t b) {
+        if (used == nullptr) {                   // all atoms: one contiguous block
+            memcpy(out + (size_t)a * (size_t)n_used * 3, full + (size_t)(f0 + a) * (size_t)n_total * 3,
+                   (size_t)(b - a) * (size_t)n_used * 12);
+            return;
+        }
         for (int64_t f = a; f < b; f++) {
             const float* src = full + (size_t)(f0 + f) * (size_t)n_total * 3;
             float* dst = out + (size_t)f * (size_t)n_used * 3;
@@ -573,6 +595,16 @@ extern "C" int cmb_accumulate_host_gather(cmb_ctx* ctx, const float* h_xyz_full,
     for (int i = 0; i < ctx->n; i++)
         if (h_used[i] < 0 || h_used[i] >= n_total || (i > 0 && h_used[i] <= h_used[i - 1]))
             return fail(ctx, CMB_ERR_ARG, "used atom indices must be ascending and inside [0, n_total)");
+    return accumulate_staged(ctx, h_xyz_full, n_total, h_used, h_box, n_frames, chunk_frames, n_threads, d_atom_table,
+                             d_res_table);
+}
+
+// host threads pack chunk k + 1 into pinned staging while chunk k is copied and processed
+// (h_used == nullptr: all n_total == n atoms, a plain copy)
+static int accumulate_staged(cmb_ctx* ctx, const float* h_xyz_full, int n_total, const int32_t* h_used,
+                             const float* h_box, int64_t n_frames, int64_t chunk_frames, int n_threads,
+                             uint32_t* d_atom_table, uint32_t* d_res_table)
+{
     CK(cudaSetDevice(ctx->device));
     if (n_threads <= 0) {
         n_threads = (int)std::thread::hardware_concurrency();

@@ -73,8 +73,11 @@ int cmb_accumulate(cmb_ctx* ctx, const float* d_xyz, const float* d_box, int64_t
                    uint32_t* d_atom_table, uint32_t* d_res_table, void* stream);
 
 /*
- * Same, with HOST coordinates (pinned memory recommended): frames are staged
- * through two device buffers, host->device copies overlapping the kernels.
+ * Same, with HOST coordinates: frames are staged through two device buffers, host->device
+ * copies overlapping the kernels.  Pinned memory is copied directly; pageable memory (an
+ * ordinary array, a memory-mapped file) is first packed by host threads into pinned staging
+ * buffers, chunk k + 1 while chunk k is transferred and processed (2.3x faster than letting the
+ * driver stage it; cmb_set_option "stage_pageable" 0 switches that off).
  * chunk_frames <= 0 picks a chunk of about 32 MiB.  Synchronous.
  */
 int cmb_accumulate_host(cmb_ctx* ctx, const float* h_xyz, const float* h_box, int64_t n_frames,

@@ -70,11 +70,18 @@ def test_host_path_and_frame_keys(engine, case_id):
     n, _, cutoff, n_ign, n_frames = case[0], case[1], case[2], case[3], case[4]
     system, xyz, box, (atom_res, atom_chain, role), (ref_atom, ref_res) = _run_case(engine, case, 100 + case_id)
     engine.set_system(atom_res, atom_chain, role, cutoff, n_ign)
-    # host-buffer entry point, tiny chunks to exercise the double buffering
-    atom_t, res_t = engine.new_tables()
-    engine.accumulate_host(xyz, box, atom_t, res_t, chunk_frames=2)
-    idx, cnt = engine.export_nonzero(atom_t)
-    assert np.array_equal(dense_from_export(idx, cnt, n), ref_atom)
+    # host-buffer entry point, tiny chunks to exercise the double buffering: pageable memory
+    # (host threads stage it into pinned buffers), pinned memory (direct async copies), and
+    # pageable memory with the staging switched off
+    pinned = torch.empty(xyz.shape, dtype=torch.float32, pin_memory=True)
+    pinned.copy_(torch.as_tensor(xyz))
+    for host_xyz, staged in ((xyz, 1), (pinned.numpy(), 1), (xyz, 0)):
+        engine.set_option("stage_pageable", staged)
+        atom_t, res_t = engine.new_tables()
+        engine.accumulate_host(host_xyz, box, atom_t, res_t, chunk_frames=2)
+        idx, cnt = engine.export_nonzero(atom_t)
+        assert np.array_equal(dense_from_export(idx, cnt, n), ref_atom)
+    engine.set_option("stage_pageable", 1)
     # per-frame keys
     d_xyz = torch.as_tensor(xyz, device=engine.device)
     d_box = None if box is None else torch.as_tensor(box, device=engine.device)
