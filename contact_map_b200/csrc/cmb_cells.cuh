@@ -216,6 +216,21 @@ __device__ __forceinline__ float d2_screen(float xi, float yi, float zi, float x
     return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
 }
 
+// lane id / lanes-below mask straight from the special registers: one S2R when the compiler
+// re-materialises them, instead of S2R tid + mask + shift + subtract
+__device__ __forceinline__ int ct_lane()
+{
+    unsigned v;
+    asm("mov.u32 %0, %%laneid;" : "=r"(v));
+    return (int)v;
+}
+__device__ __forceinline__ unsigned ct_ltmask()
+{
+    unsigned v;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(v));
+    return v;
+}
+
 // Per-warp ring of screened entries: head / tail live in (warp-uniform) registers, pushes are
 // warp-aggregated with one ballot (no atomics, no shared counter).
 struct Ring {
@@ -307,7 +322,7 @@ template <typename Traits, typename Sink, int MODE, int FLAGS>
 __device__ __forceinline__ void ct_account(const PairParams& p, const PairCtx<Traits>& cx, Sink& sink, int ipos,
                                            int jpos, int id, bool active)
 {
-    const int lane = threadIdx.x & 31;
+    const int lane = ct_lane();
     const float4 wi = cx.sorted[ipos], wj = cx.sorted[jpos], sh = cx.shift[id];
     const float d2a = d2_screen(wi.x, wi.y, wi.z, __fadd_rn(wj.x, sh.x), __fadd_rn(wj.y, sh.y),
                                 __fadd_rn(wj.z, sh.z));
@@ -368,7 +383,7 @@ template <typename Traits, typename Sink, int MODE, int FLAGS>
 __device__ __forceinline__ void ct_drain(const PairParams& p, const PairCtx<Traits>& cx, Sink& sink, Ring& ring,
                                          unsigned ltmask)
 {
-    const int lane = threadIdx.x & 31;
+    const int lane = ct_lane();
     const unsigned left = ring.tail - ring.head;
     const bool active = (unsigned)lane < left;
     __syncwarp();
@@ -435,9 +450,9 @@ template <typename Traits, typename Sink, int MODE, int FLAGS>
 __device__ __forceinline__ void ct_cell_task(const PairParams& p, const GridS& G, const PairCtx<Traits>& cx,
                                              Sink& sink, unsigned task, unsigned long long& n_tests, Ring& ring)
 {
-    const int lane = threadIdx.x & 31;
+    const int lane = ct_lane();
     const unsigned FULL = 0xffffffffu;
-    const unsigned ltmask = (1u << lane) - 1u;
+    const unsigned ltmask = ct_ltmask();
     const int c = (int)(task & Traits::TASK_CMASK);
     const int L = (task & Traits::TASK_PAIR) ? 2 : 1;
     const int cstart = (int)cx.cellptr[c], cend = (int)cx.cellptr[c + L];
@@ -622,7 +637,7 @@ __device__ __forceinline__ void ct_pair_phase(const PairParams& p, const GridS& 
                                               Sink& sink, const OccT* occ, int n_occ, int* task_counter,
                                               unsigned long long& n_tests)
 {
-    const int lane = threadIdx.x & 31;
+    const int lane = ct_lane();
     Ring ring;
     ring.head = ring.tail = 0u;
     for (;;) {
@@ -641,7 +656,7 @@ __device__ __forceinline__ void ct_pair_phase(const PairParams& p, const GridS& 
             ct_cell_task<Traits, Sink, MODE, FLAGS>(p, G, cx, sink, task, n_tests, ring);
         }
     }
-    const unsigned ltmask = (1u << lane) - 1u;
+    const unsigned ltmask = ct_ltmask();
     while (ring.tail != ring.head) ct_drain<Traits, Sink, MODE, FLAGS>(p, cx, sink, ring, ltmask);
 }
 
