@@ -82,6 +82,7 @@ class ContactEngine(object):
         self.n_used = 0
         self.n_res_c = 0
         self.residue_map = None
+        self._system_key = None
         self._keepalive = []
 
     # ------------------------------------------------------------------
@@ -463,8 +464,10 @@ class ContactEngine(object):
         """
         xyz, box = self._dev_inputs(xyz, box)
         n_frames = xyz.shape[0]
-        cap_a = int(cap_hint or max(1024, n_frames * 64)) if want_atoms else 0
-        cap_r = int(cap_hint or max(1024, n_frames * 64)) if want_residues else 0
+        # capacities: keys per frame seen in the previous call for this system (+25 %), else 64
+        hint = self.__dict__.setdefault("_keys_hint", {}).get(self._system_key, (64.0, 64.0))
+        cap_a = int(cap_hint or max(1024, n_frames * hint[0] * 1.25 + 1024)) if want_atoms else 0
+        cap_r = int(cap_hint or max(1024, n_frames * hint[1] * 1.25 + 1024)) if want_residues else 0
         if isinstance(atom_table, HashTable) or isinstance(res_table, HashTable):
             raise NotImplementedError("frame_contacts accumulates into dense tables only")
         self._set_table_mode(None, None)
@@ -484,6 +487,9 @@ class ContactEngine(object):
             if atom_table is not None or res_table is not None:
                 raise EngineError("key buffers overflowed after sizing pass")
             cap_a, cap_r = (max(cap_a, na) if want_atoms else 0), (max(cap_r, nr) if want_residues else 0)
+        if self._system_key is not None and n_frames > 0:
+            self._keys_hint[self._system_key] = (max(1.0, na / n_frames) if want_atoms else hint[0],
+                                                 max(1.0, nr / n_frames) if want_residues else hint[1])
         out = []
         for keys, n_keys in ((ak, na), (rk, nr)):
             if keys is None:
