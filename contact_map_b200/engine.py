@@ -123,8 +123,8 @@ class ContactEngine(object):
         if atom_chain.shape[0] != n or role.shape[0] != n:
             raise ValueError("system arrays must have the same length")
         # the same system again (one analysis object per trajectory chunk): nothing to upload
-        key = (n, float(cutoff), int(n_ignored), hash(atom_res.tobytes()), hash(atom_chain.tobytes()),
-               hash(role.tobytes()), self.get_stat("max_cells"), int(getattr(self, "_forced_path", -1)))
+        key = (n, float(cutoff), int(n_ignored), atom_res.tobytes(), atom_chain.tobytes(), role.tobytes(),
+               self.get_stat("max_cells"), int(getattr(self, "_forced_path", -1)))
         if key == getattr(self, "_system_key", None):
             return
         self._system_key = None
