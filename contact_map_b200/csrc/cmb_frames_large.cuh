@@ -22,7 +22,10 @@
 namespace cmb {
 
 constexpr int LG_MAXC = 1 << 21;
-constexpr int LG_PAIR_THREADS = 256;
+#ifndef LG_PAIR_THREADS_CFG
+#define LG_PAIR_THREADS_CFG 256
+#endif
+constexpr int LG_PAIR_THREADS = LG_PAIR_THREADS_CFG;
 constexpr int LG_RCACHE = 128;          // per-warp cache of stamped residue pairs (entries)
 
 struct LargeScratch {
@@ -429,8 +432,11 @@ __global__ void __launch_bounds__(256) kl_scatter(int n, const int* __restrict__
     }
 }
 
+#ifndef LG_MIN_CTAS
+#define LG_MIN_CTAS 2
+#endif
 template <int FLAGS>
-__global__ void __launch_bounds__(LG_PAIR_THREADS, 4) kl_pairs(PairParams pp, StampSink sink_in,
+__global__ void __launch_bounds__(LG_PAIR_THREADS, LG_MIN_CTAS) kl_pairs(PairParams pp, StampSink sink_in,
                                                                const float* __restrict__ box9, float cutoff,
                                                                const GridS* __restrict__ grid,
                                                                const float4* __restrict__ sorted,
@@ -553,7 +559,7 @@ inline int large_run(const LargeJob& job, LargeScratch& S, int sm_count, cudaStr
         sink.counters = job.counters; sink.seq = S.seq; sink.n = (unsigned)n;
         sink.n_res_c = (unsigned)job.n_res_c; sink.frame_id = job.frame0 + f;
         sink.pending = 0; sink.pend_old = 0u; sink.pend_lo = sink.pend_hi = 0u; sink.ra = sink.rb = 0;
-        const int pg = sm_count * 4;
+        const int pg = sm_count * LG_MIN_CTAS;
         const bool emit = job.atom_keys != nullptr;
         if (job.boundary_ulps > 0)
             kl_pairs<CT_BOUNDARY | CT_ROLES><<<pg, LG_PAIR_THREADS, 0, stream>>>(
