@@ -302,6 +302,10 @@ __global__ void __launch_bounds__(FS_THREADS, FS_MIN_CTAS) k_frames_small(const 
     };
     if (tid == 0 && f < p.n_frames) issue_load(f);
 
+    // without residue keys the residue table is updated at the first hit of a pair and the
+    // bitmap is only cleared between frames (together with the histogram, before the grid barrier)
+    const bool res_at_once = p.res_table != nullptr && !((FLAGS & FS_EMIT) && p.res_keys != nullptr);
+    bool first_frame = true;
     for (; f < p.n_frames; f += stride) {
         const float* box9 = p.box ? p.box + (size_t)f * 9 : nullptr;
         const unsigned long long addr = (unsigned long long)(p.xyz + (size_t)f * (size_t)n * 3);
@@ -344,6 +348,12 @@ __global__ void __launch_bounds__(FS_THREADS, FS_MIN_CTAS) k_frames_small(const 
                 hi[0] = red[96]; hi[1] = red[128]; hi[2] = red[160];
             }
         }
+        // the cell arrays and the residue bitmap of the previous frame are dead: clear them here, so
+        // that the barrier below is the only one before the histogram
+        for (int w = tid; w < (p.maxc + 3) / 2; w += FS_THREADS) cell32[w] = 0u;
+        if (res_at_once && !first_frame)
+            for (int w = tid; w < p.bm_words; w += FS_THREADS) bitmap[w] = 0u;
+        first_frame = false;
         if (tid == 0) {
             // the grid only depends on the box: constant-volume trajectories build it once
             bool same = box9 != nullptr && *box_valid_s != 0;
@@ -362,8 +372,6 @@ __global__ void __launch_bounds__(FS_THREADS, FS_MIN_CTAS) k_frames_small(const 
 
         // ---- pass A: histogram (u16 counters packed in u32 words); on periodic grids the raw
         //      buffer is overwritten with the wrapped positions ----------------------------
-        for (int w = tid; w < (G.ncell + 3) / 2; w += FS_THREADS) cell32[w] = 0u;
-        __syncthreads();
         unsigned my_cr[FS_APT];              // cell | rank << 16 of this thread's atoms
         float amax = 0.f;
 #pragma unroll
@@ -487,19 +495,15 @@ __global__ void __launch_bounds__(FS_THREADS, FS_MIN_CTAS) k_frames_small(const 
         PairCtx<SmallTraits> cx;
         cx.sorted = sorted; cx.cellptr = cell16; cx.cand = cand; cx.hitq = hitq;
         cx.shift = shift_s; cx.kr = nullptr;
-        // without residue keys the residue table is updated at the first hit of a pair and the
-        // end-of-frame pass only clears the bitmap
-        const bool res_at_once = p.res_table != nullptr && !((FLAGS & FS_EMIT) && p.res_keys != nullptr);
         BitmapSink sink{p.meta32, p.atom_table, bitmap, res_at_once ? p.res_table : nullptr, (unsigned)n,
                         (unsigned)p.n_res_c, 0u, 0u};
         ct_pair_phase_dyn<SmallTraits, BitmapSink, FLAGS, unsigned short>(pp, G, cx, sink, occ, *n_occ_s,
                                                                           task_counter, n_tests);
         __syncthreads();
 
-        // ---- pass E: clear / flush the per-frame residue bitmap -----------------------
-        if (res_at_once) {
-            for (int w = tid; w < p.bm_words; w += FS_THREADS) bitmap[w] = 0u;
-        } else
+        // ---- pass E: sweep the per-frame residue bitmap (only when its bits were not counted at
+        //      once: residue keys requested, or no residue table) ---------------------------
+        if (!res_at_once)
         for (int w = tid; w < p.bm_words; w += FS_THREADS) {
             unsigned v = bitmap[w];
             if (v) {
@@ -529,7 +533,7 @@ __global__ void __launch_bounds__(FS_THREADS, FS_MIN_CTAS) k_frames_small(const 
                 }
             }
         }
-        __syncthreads();
+        if (!res_at_once) __syncthreads();
     }
     if (FLAGS & FS_COUNT) {
 #pragma unroll
