@@ -206,6 +206,16 @@ def test_full_size_properties_s1(engine):
         want = clib.contacts_frame(h[f], system.box, 0.45, res, chain, role, 2, cells=True)
         sel = frame == f
         assert np.array_equal(np.stack([klo[sel], khi[sel]], axis=1), want)
+    # (7) both count tables of a 96-frame block (frames 5000..5095) against the oracle's dense tables
+    blk = slice(5000, 5096)
+    ref_atom, ref_res = clib.accumulate_dense(xyz[blk].cpu().numpy(), box[blk].cpu().numpy(), 0.45, res, chain,
+                                              role, 2, system.topology.n_residues)
+    blk_a, blk_r = engine.new_tables()
+    engine.accumulate(xyz[blk], box[blk], blk_a, blk_r)
+    (idx, cnt), (ridx, rcnt) = engine.export_many([blk_a, blk_r])
+    assert np.array_equal(dense_from_export(idx, cnt, n), ref_atom)
+    rmap = engine.residue_map
+    assert np.array_equal(dense_from_export(ridx, rcnt, engine.n_res_c), ref_res[np.ix_(rmap, rmap)])
 
 
 def test_binding_system_s2_matches_oracle(engine):
