@@ -161,9 +161,11 @@ class ContactEngine(object):
             else:
                 res = torch.zeros(rc * rc, dtype=torch.int32, device=self.device)
             return atom, res
-        atom = torch.zeros(n * n, dtype=torch.int32, device=self.device)
-        res = torch.zeros(rc * rc, dtype=torch.int32, device=self.device)
-        return atom, res
+        # one allocation, two views (16-byte aligned): the multi-rank reduce is then a single
+        # all-reduce of the allocation, with no packing copies (parallel.reduce_tables)
+        n_atom = (n * n + 3) // 4 * 4
+        flat = torch.zeros(n_atom + rc * rc, dtype=torch.int32, device=self.device)
+        return flat[:n * n], flat[n_atom:n_atom + rc * rc]
 
     # ---- hashed tables: mode switch, frame schedule, growth ---------------------------
     def _set_table_mode(self, atom_table, res_table):

@@ -51,6 +51,17 @@ def reduce_tables(tables, group=None):
         tables = [t for t in tables if not hasattr(t, "slots")]
         if not tables:
             return hashed
+    if len(tables) > 1 and all(t.is_contiguous() and t.dtype == tables[0].dtype and
+                               t.untyped_storage().data_ptr() == tables[0].untyped_storage().data_ptr()
+                               for t in tables):
+        # views of one allocation (engine.new_tables): reduce the span they cover in place
+        lo = min(t.storage_offset() for t in tables)
+        hi = max(t.storage_offset() + t.numel() for t in tables)
+        if hi - lo <= 2 * sum(t.numel() for t in tables):
+            span = torch.empty(0, dtype=tables[0].dtype, device=tables[0].device)
+            span.set_(tables[0].untyped_storage(), lo, (hi - lo,))
+            dist.all_reduce(span, op=dist.ReduceOp.SUM, group=group)
+            return tables
     flat = torch.cat([t.reshape(-1) for t in tables]) if len(tables) > 1 else tables[0].reshape(-1)
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     if len(tables) > 1:
