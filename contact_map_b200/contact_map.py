@@ -97,25 +97,19 @@ class ContactObject(object):
 
     def __init__(self, topology, query, haystack, cutoff, n_neighbors_ignored):
         self._topology = topology
-        if query is None:
-            query = topology.select("not water and symbol != 'H'")
-        if haystack is None:
-            haystack = topology.select("not water and symbol != 'H'")
+        if query is None or haystack is None:
+            default = topology.select("not water and symbol != 'H'")
+            query = default if query is None else query
+            haystack = default if haystack is None else haystack
         self._cutoff = cutoff
-        # same containers as the reference (sets of plain ints), built through numpy
-        q_arr = np.unique(np.asarray(list(query) if not isinstance(query, np.ndarray) else query,
-                                     dtype=np.int64))
-        h_arr = np.unique(np.asarray(list(haystack) if not isinstance(haystack, np.ndarray) else haystack,
-                                     dtype=np.int64))
-        self._query = set(q_arr.tolist())
-        self._haystack = set(h_arr.tolist())
-        atom_res, _ = topology_arrays(topology)
-        self._query_res_idx = set(np.unique(atom_res[q_arr]).tolist())
-        self._haystack_res_idx = set(np.unique(atom_res[h_arr]).tolist())
-        all_arr = np.union1d(q_arr, h_arr)
-        self._all_atoms = tuple(all_arr.tolist())
-        self._all_residues = set(np.unique(atom_res[all_arr]).tolist())
-        self._use_atom_slice = self._set_atom_slice(self._all_atoms)
+        # sorted unique index arrays drive the GPU path; the reference's containers (sets of plain
+        # ints, a sorted tuple) are built from them on first access (see the properties below)
+        self._q_arr = _sorted_unique(query)
+        self._h_arr = self._q_arr if haystack is query else _sorted_unique(haystack)
+        self._all_arr = self._q_arr if self._q_arr is self._h_arr or np.array_equal(self._q_arr, self._h_arr) \
+            else np.union1d(self._q_arr, self._h_arr)
+        self._lazy = {}
+        self._use_atom_slice = self._set_atom_slice(self._all_arr)
         if getattr(self, "_indexer", None) is None:
             self._indexer = None          # built on first access (two dicts over all atoms)
         self._n_neighbors_ignored = n_neighbors_ignored
@@ -131,6 +125,41 @@ class ContactObject(object):
     @indexer.setter
     def indexer(self, value):
         self._indexer = value
+
+    # -- the reference's containers (contact_map.py:132-139), built lazily from the arrays ------
+    def _lazy_get(self, name, build):
+        value = self._lazy.get(name)
+        if value is None:
+            value = self._lazy[name] = build()
+        return value
+
+    def _residues_of(self, atoms):
+        atom_res, _ = topology_arrays(self._topology)
+        return set(np.unique(atom_res[atoms]).tolist())
+
+    @property
+    def _query(self):
+        return self._lazy_get("query", lambda: set(self._q_arr.tolist()))
+
+    @property
+    def _haystack(self):
+        return self._lazy_get("haystack", lambda: set(self._h_arr.tolist()))
+
+    @property
+    def _query_res_idx(self):
+        return self._lazy_get("query_res", lambda: self._residues_of(self._q_arr))
+
+    @property
+    def _haystack_res_idx(self):
+        return self._lazy_get("haystack_res", lambda: self._residues_of(self._h_arr))
+
+    @property
+    def _all_atoms(self):
+        return self._lazy_get("all_atoms", lambda: tuple(self._all_arr.tolist()))
+
+    @property
+    def _all_residues(self):
+        return self._lazy_get("all_residues", lambda: self._residues_of(self._all_arr))
 
     def _set_atom_slice(self, all_atoms):
         if self._class_use_atom_slice is None:
@@ -350,6 +379,14 @@ class ContactObject(object):
                 for pair, value in self.atom_contacts.most_common_idx() if frozenset(pair) in wanted]
 
 
+def _sorted_unique(indices):
+    """Sorted unique int64 array of an iterable of atom indices (already-sorted input is kept)."""
+    arr = np.asarray(indices if isinstance(indices, np.ndarray) else list(indices), dtype=np.int64).reshape(-1)
+    if arr.shape[0] > 1 and not bool(np.all(arr[1:] > arr[:-1])):
+        arr = np.unique(arr)
+    return arr
+
+
 def _split_trajectory(trajectory):
     """(xyz, unit-cell vectors or None) of an mdtraj-like trajectory object."""
     xyz = trajectory.xyz
@@ -361,10 +398,10 @@ def _split_trajectory(trajectory):
 def _engine_system(contact_object, engine):
     """Upload the per-used-atom arrays of ``contact_object`` (cmb_set_system)."""
     atom_res, atom_chain = topology_arrays(contact_object.topology)
-    used = np.asarray(contact_object._all_atoms, dtype=np.int64)
+    used = contact_object._all_arr
     role = np.zeros(used.shape[0], dtype=np.uint8)
-    role[np.isin(used, np.fromiter(contact_object._query, dtype=np.int64))] |= 1
-    role[np.isin(used, np.fromiter(contact_object._haystack, dtype=np.int64))] |= 2
+    role[np.searchsorted(used, contact_object._q_arr)] |= 1        # both are subsets of the sorted `used`
+    role[np.searchsorted(used, contact_object._h_arr)] |= 2
     if contact_object.n_neighbors_ignored is None or contact_object.cutoff is None:
         raise ValueError("cutoff and n_neighbors_ignored must be set to compute contacts")
     if contact_object.n_neighbors_ignored < 0:
@@ -408,10 +445,12 @@ def _tables_to_pairs(engine, atom_table, res_table, used):
     """Sparse export of the device tables -> (atom PairTable, residue PairTable) in REAL indices."""
     n = engine.n_used
     (idx, cnt), (ridx, rcnt) = engine.export_many([atom_table, res_table])
-    atoms = PairTable(used[idx // n], used[idx % n], cnt.astype(np.int64))
+    lo, hi = np.divmod(idx, n)
+    atoms = PairTable(used[lo], used[hi], cnt.astype(np.int64))
     rc = engine.n_res_c
     rmap = engine.residue_map.astype(np.int64)
-    residues = PairTable(rmap[ridx // rc], rmap[ridx % rc], rcnt.astype(np.int64))
+    rlo, rhi = np.divmod(ridx, rc)
+    residues = PairTable(rmap[rlo], rmap[rhi], rcnt.astype(np.int64))
     return atoms, residues
 
 

@@ -18,7 +18,7 @@ h_box.copy_(torch.as_tensor(system.box).reshape(1, 3, 3).expand(F, 3, 3))
 torch.cuda.synchronize()
 traj = cm.Trajectory(h_xyz.numpy(), top, h_box.numpy())
 everyone = np.arange(n)
-for chunk in (0, 2000, 500, 250, 125):
+for chunk in (0, 600, 300, 150, 75):
     orig = engine.accumulate_host
     engine.accumulate_host = lambda x, b, a, r, chunk_frames=0, _o=orig, _c=chunk: _o(x, b, a, r, chunk_frames=_c)
     for rep in range(5):
