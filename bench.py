@@ -219,7 +219,7 @@ def run_reference(args):
     system = synth.kras_like()
     cores = len(os.sched_getaffinity(0))
     workers = max(1, cores)
-    frames = args.cpu_frames or max(workers * 4, 32)
+    frames = args.cpu_frames or max(workers * 16, 64)
     rates = []
     for _ in range(args.warmup):
         cpu_reference_rate(system, max(workers, 8), workers)
@@ -447,7 +447,7 @@ def run_ours(args):
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        frames_cpu = args.cpu_frames or 64
+        frames_cpu = args.cpu_frames or 512
         rate, dt, _, _ = cpu_reference_rate(system, frames_cpu, 1)
         cpu_baseline = {"value": rate, "unit": "frames/s", "cores": 1, "kind": "port",
                         "sample": "first %d frames of S1 (%.1f s): reference Python set/Counter loop restated "

@@ -70,5 +70,42 @@ def main():
                                                   ", ".join("%s %.0f" % (n, v) for v, n in stalls if v)))
 
 
+    # the same numbers by code region of the pair phase (line ranges of the CURRENT sources: the
+    # function a line belongs to is found from the nearest preceding definition)
+    regions = source_regions()
+    by_region = defaultdict(lambda: [0.0, 0.0])
+    for (fname, line), a in agg.items():
+        name = "%s: %s" % (fname, regions.get(fname, lambda _l: "-")(line))
+        by_region[name][0] += a["inst"]
+        by_region[name][1] += a["samples"]
+    print("\n%-58s %8s %8s" % ("function (file: name)", "inst%", "samp%"))
+    for name, (inst, samp) in sorted(by_region.items(), key=lambda kv: -kv[1][0])[:24]:
+        print("%-58s %7.2f%% %7.2f%%" % (name, 100 * inst / tot_inst, 100 * samp / max(tot_samp, 1)))
+
+
+def source_regions():
+    """{file name: line -> name of the enclosing __device__/__global__ function} for csrc/."""
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "contact_map_b200", "csrc")
+    out = {}
+    for fname in os.listdir(root):
+        starts = []
+        for no, text in enumerate(open(os.path.join(root, fname), errors="replace"), 1):
+            text = re.sub(r"__launch_bounds__\([^)]*\)", "", text)
+            m = re.match(r"\s*(?:static\s+)?(?:__device__|__global__|__host__).*?\b(\w+)\s*\(", text) or \
+                re.match(r"\s*(?:__launch_bounds__\S*\s+)?(\w+)\(const .*Params", text)
+            if m and m.group(1) not in ("if", "for", "while", "__launch_bounds__"):
+                starts.append((no, m.group(1)))
+
+        def find(line, _s=starts):
+            name = "-"
+            for no, n in _s:
+                if no > line:
+                    break
+                name = n
+            return name
+        out[fname] = find
+    return out
+
+
 if __name__ == "__main__":
     main()
