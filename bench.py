@@ -7,8 +7,8 @@
 Workload (config.workload): "S1" = BASELINE.json configs[1], synthetic KRAS-sized protein,
 2700 heavy atoms, 10 000 frames, orthorhombic PBC, query = haystack = all atoms, cutoff
 0.45 nm, n_neighbors_ignored = 2.  A "step" is one full ContactFrequency pass over the 10 000
-frames: zero the count tables, bin + screen + accumulate every frame, (N > 1: one NCCL
-all-reduce of the tables), sparse export of both tables.  Multi-GPU runs shard by frame with
+frames: zero the count tables, bin + screen + accumulate every frame, (N > 1: one
+NCCL reduce of the tables to rank 0), sparse export of both tables.  Multi-GPU runs shard by frame with
 fixed per-GPU work (weak scaling): every rank owns 10 000 different frames.
 
 `value` is measured with CUDA events, inputs resident in HBM (generated on device by the
@@ -61,7 +61,7 @@ def workload_config(args, world):
         "n_atoms": 2700,
         "cutoff_nm": CUTOFF,
         "n_neighbors_ignored": N_IGNORED,
-        "sharding": "frames (rank r owns frames [r*F, (r+1)*F)), one NCCL all-reduce of the count tables"
+        "sharding": "frames (rank r owns frames [r*F, (r+1)*F)), one NCCL reduce of the count tables to rank 0"
                     if world > 1 else "single GPU",
         "l2": "inputs larger than L2: %.0f MB of coordinates per pass vs 126 MB L2" % (args.frames * 2700 * 12 / 1e6),
     }
@@ -320,12 +320,14 @@ def run_ours(args):
         if record:
             e1.record()
             kern_events.append((e0, e1))
-        parallel.reduce_tables([atom_t, res_t])
-        return engine.export_many([atom_t, res_t])
+        # the reference's reduce hands the result to the client only (frequency_task.py:125-141):
+        # one NCCL reduce to rank 0, which alone exports it
+        parallel.reduce_tables([atom_t, res_t], dst=0)
+        return engine.export_many([atom_t, res_t]) if rank == 0 else None
 
     for _ in range(max(args.warmup, 3)):      # timing rule: at least 3 warm-up steps
         out = step(False)
-    n_atom_pairs, n_res_pairs = len(out[0][0]), len(out[1][0])
+    n_atom_pairs, n_res_pairs = (len(out[0][0]), len(out[1][0])) if rank == 0 else (0, 0)
 
     launches0 = engine.get_stat("kernel_launches")
     sampler = ClockSampler(local_rank)
@@ -376,7 +378,7 @@ def run_ours(args):
 
         def e2e_step():
             m = cm.ChunkedContactFrequency(traj, query=everyone, haystack=everyone, cutoff=CUTOFF,
-                                           n_neighbors_ignored=N_IGNORED, presharded=True)
+                                           n_neighbors_ignored=N_IGNORED, presharded=True, result_rank=0)
             return m
 
         for _ in range(2):
@@ -397,7 +399,7 @@ def run_ours(args):
                "d2h_bytes_per_step": int((na + nr) * 12 + 16),
                "ms_per_step": 1e3 * dt / args.steps,
                "api": "ChunkedContactFrequency(trajectory with pinned host xyz, presharded=True) -> "
-                      "cmb_accumulate_host (chunked H2D overlapped with kernels) -> all-reduce -> sparse export -> D2H"}
+                      "cmb_accumulate_host (chunked H2D overlapped with kernels) -> NCCL reduce to rank 0 -> sparse export -> D2H"}
 
     if rank != 0:
         if world > 1:

@@ -32,14 +32,23 @@ def rank_slices(n_frames, n_blocks=None, rank=None, world_size=None):
     return [s for k, s in enumerate(slices) if k % world_size == rank]
 
 
-def reduce_tables(tables, group=None):
-    """Sum count tables over all ranks, in place, with a single all-reduce.
+def reduce_tables(tables, group=None, dst=None):
+    """Sum count tables over all ranks, in place, with a single collective.
 
-    ``tables`` is a list of int32 tensors (views of the uint32 tables).  They are packed into
-    one flat buffer so exactly one collective is issued; two's-complement addition makes the
-    int32 view exact for uint32 counts."""
+    ``tables`` is a list of int32 tensors (views of the uint32 tables).  They are reduced as one
+    flat buffer so exactly one collective is issued; two's-complement addition makes the int32
+    view exact for uint32 counts.  ``dst=None``: all-reduce, every rank ends up with the sum.
+    ``dst=r``: reduce to rank ``r`` only -- what the reference's ``reduce_all_results`` does (the
+    client alone receives the result, frequency_task.py:125-141) at about half the traffic; the
+    tables of the other ranks are unspecified afterwards."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return tables
+
+    def collective(flat):
+        if dst is None:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        else:
+            dist.reduce(flat, dst=dst, op=dist.ReduceOp.SUM, group=group)
     hashed = [t for t in tables if hasattr(t, "slots")]
     if hashed:
         # hashed tables have rank-dependent layouts: gather the sparse exports and merge them
@@ -60,10 +69,10 @@ def reduce_tables(tables, group=None):
         if hi - lo <= 2 * sum(t.numel() for t in tables):
             span = torch.empty(0, dtype=tables[0].dtype, device=tables[0].device)
             span.set_(tables[0].untyped_storage(), lo, (hi - lo,))
-            dist.all_reduce(span, op=dist.ReduceOp.SUM, group=group)
+            collective(span)
             return tables
     flat = torch.cat([t.reshape(-1) for t in tables]) if len(tables) > 1 else tables[0].reshape(-1)
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    collective(flat)
     if len(tables) > 1:
         offset = 0
         for t in tables:

@@ -14,6 +14,7 @@ from . import parallel
 from . import trajectory as _trajectory
 from .contact_map import (ContactFrequency, ContactObject, _engine_system, _split_trajectory,
                           _tables_to_pairs, _used_coordinates)
+from .contact_count import PairTable
 from .contact_trajectory import ContactTrajectory, FrameCSR, _build_contacts
 
 
@@ -34,12 +35,15 @@ class ChunkedContactFrequency(ContactFrequency):
     """
 
     def __init__(self, trajectory, query=None, haystack=None, cutoff=0.45, n_neighbors_ignored=2,
-                 n_blocks=None, presharded=False):
+                 n_blocks=None, presharded=False, result_rank=None):
         """``presharded=True``: ``trajectory`` already holds only THIS rank's frames (each rank
         loaded / generated its own shard); every local frame is processed and ``n_frames``
-        becomes the sum over the ranks."""
+        becomes the sum over the ranks.  ``result_rank=r``: the partial tables are reduced to
+        rank ``r`` only, as the reference's client-side ``reduce_all_results`` does (half the
+        traffic of the default all-reduce); the other ranks end up with empty contact maps."""
         self._n_blocks = n_blocks
         self._presharded = presharded
+        self._result_rank = result_rank
         super(ChunkedContactFrequency, self).__init__(trajectory, query, haystack, cutoff,
                                                       n_neighbors_ignored)
 
@@ -64,7 +68,10 @@ class ChunkedContactFrequency(ContactFrequency):
                 engine.accumulate(bx, bb, atom_table, res_table)
             else:
                 engine.accumulate_host(bx, bb, atom_table, res_table)
-        parallel.reduce_tables([atom_table, res_table])
+        parallel.reduce_tables([atom_table, res_table], dst=self._result_rank)
+        if self._result_rank is not None and parallel.world()[0] != self._result_rank:
+            self._device_tables = None
+            return PairTable.empty(), PairTable.empty()
         self._device_tables = (atom_table, res_table, used)
         return _tables_to_pairs(engine, atom_table, res_table, used)
 

@@ -49,6 +49,10 @@ def _worker(rank, world, port, out_dir):
                             | pairs[:, 1].astype(np.uint64))
         t_atom = torch.from_numpy(atom.view(np.int32).reshape(-1).copy())
         t_res = torch.from_numpy(resc.view(np.int32).reshape(-1).copy())
+        # reduce to rank 0 only (the reference's client-side reduce), on two views of one allocation
+        both = torch.cat([t_atom, t_res])
+        r_atom, r_res = both[:t_atom.numel()], both[t_atom.numel():]
+        parallel.reduce_tables([r_atom, r_res], dst=0)
         parallel.reduce_tables([t_atom, t_res])
         total_frames = parallel.reduce_frame_count(mine, torch.device("cpu"))
         all_keys = parallel.gather_keys(np.sort(np.concatenate(keys)) if keys else np.empty(0, np.uint64),
@@ -57,7 +61,8 @@ def _worker(rank, world, port, out_dir):
         flat = np.flatnonzero(atom.reshape(-1))
         m_idx, m_cnt = parallel.merge_sparse(flat, atom.reshape(-1)[flat], torch.device("cpu"))
         np.savez(os.path.join(out_dir, "rank%d.npz" % rank), atom=t_atom.numpy(), res=t_res.numpy(),
-                 frames=total_frames, keys=all_keys.view(np.int64), m_idx=m_idx, m_cnt=m_cnt)
+                 frames=total_frames, keys=all_keys.view(np.int64), m_idx=m_idx, m_cnt=m_cnt,
+                 root_atom=r_atom.numpy(), root_res=r_res.numpy())
     finally:
         dist.destroy_process_group()
 
@@ -85,6 +90,9 @@ def test_two_rank_reduce_equals_single(tmp_path):
         assert np.array_equal(got["atom"].view(np.uint32).reshape(80, 80), atom)
         assert np.array_equal(got["res"].view(np.uint32).reshape(resc.shape), resc)
         assert int(got["frames"]) == 7
+        if rank == 0:
+            assert np.array_equal(got["root_atom"].view(np.uint32).reshape(80, 80), atom)
+            assert np.array_equal(got["root_res"].view(np.uint32).reshape(resc.shape), resc)
         assert np.array_equal(got["keys"].view(np.uint64), want_keys)
         want_flat = np.flatnonzero(atom.reshape(-1))
         assert np.array_equal(got["m_idx"], want_flat)

@@ -25,5 +25,15 @@ for hashed in (False, True):
             and sharded.n_frames == len(traj))
     print("rank %d hashed=%s tables=%s equal=%s" % (rank, hashed, type(sharded._device_tables[0]).__name__, same))
     ok = ok and same
+# reduce to rank 0 only: rank 0 holds the serial result, the other ranks an empty map
+engine.set_option("force_path", -1)
+ContactEngine.DENSE_LIMIT_BYTES = 1 << 36
+rooted = cm.ChunkedContactFrequency(traj, cutoff=0.45, n_neighbors_ignored=2, n_blocks=5, result_rank=0)
+if rank == 0:
+    same = rooted._atom_contacts == serial._atom_contacts and rooted._residue_contacts == serial._residue_contacts
+else:
+    same = len(rooted._atom_contacts) == 0 and len(rooted._residue_contacts) == 0
+print("rank %d result_rank=0 equal=%s" % (rank, same))
+ok = ok and same
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
