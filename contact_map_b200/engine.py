@@ -385,6 +385,9 @@ class ContactEngine(object):
         triggers one exact retry; counts that do not fit 24 bits fall back to the unpacked export.
         Returns [(flat index int64[], count uint32[]), ...], each sorted by index.
         """
+        fused = self._export_span(tables)
+        if fused is not None:
+            return fused
         hints = self.__dict__.setdefault("_export_hint", {})
         stream = torch.cuda.current_stream(self.device)
         jobs = []
@@ -418,6 +421,27 @@ class ContactEngine(object):
                 packed = job["h_packed"][:n].numpy()
                 out.append((packed >> 24, (packed & 0xffffff).astype(np.uint32)))
         return out
+
+    def _export_span(self, tables):
+        """Dense tables that are views of ONE allocation (``new_tables``) are exported with a single
+        scan of that allocation and split on the host at the view boundaries."""
+        if len(tables) < 2 or any(isinstance(t, HashTable) or not t.is_contiguous() for t in tables):
+            return None
+        base = tables[0].untyped_storage().data_ptr()
+        if any(t.untyped_storage().data_ptr() != base or t.dtype != tables[0].dtype for t in tables):
+            return None
+        offsets = [t.storage_offset() for t in tables]
+        ends = [o + t.numel() for o, t in zip(offsets, tables)]
+        if offsets != sorted(offsets) or any(e > o2 for e, o2 in zip(ends[:-1], offsets[1:])):
+            return None
+        lo, hi = offsets[0], ends[-1]
+        if hi - lo > 2 * sum(t.numel() for t in tables) or lo % 4:
+            return None
+        span = torch.empty(0, dtype=tables[0].dtype, device=tables[0].device)
+        span.set_(tables[0].untyped_storage(), lo, (hi - lo,))
+        (idx, cnt), = self.export_many([span])
+        cuts = np.searchsorted(idx, np.asarray(offsets + [hi], dtype=np.int64) - lo)
+        return [(idx[a:b] - (o - lo), cnt[a:b]) for a, b, o in zip(cuts[:-1], cuts[1:], offsets)]
 
     def _export_launch(self, table, cap, slot):
         # staging buffers are keyed by (table size, position in the call) and reused across calls
