@@ -26,10 +26,13 @@ constexpr int LG_MAXC = 1 << 21;
 #define LG_PAIR_THREADS_CFG 256
 #endif
 constexpr int LG_PAIR_THREADS = LG_PAIR_THREADS_CFG;
+constexpr int LG_BIN_THREADS = 256;      // single-CTA set-up / scan kernels: small enough to share an SM with kl_pairs
 constexpr int LG_RCACHE = 128;          // per-warp cache of stamped residue pairs (entries)
 
-struct LargeScratch {
-    int cap_atoms = 0;
+// Per-frame binning buffers.  Two sets: the binning kernels of frame f + 1 run on a second stream
+// while the pair kernel of frame f is still busy (it is latency-bound on the count tables and
+// leaves most issue slots idle), see large_run.
+struct LargeBins {
     GridS* d_grid = nullptr;
     int* d_cellcnt = nullptr;      // [LG_MAXC + 1]
     int* d_cellptr = nullptr;      // [LG_MAXC + 1]
@@ -39,6 +42,16 @@ struct LargeScratch {
     int* d_atomrank = nullptr;     // [n]
     float4* d_sorted = nullptr;    // [n]
     float2* d_sorted_kr = nullptr;   // [n] {exclusion key, compact residue}
+    cudaEvent_t binned = nullptr;    // binning kernels of the set's current frame have finished
+    cudaEvent_t paired = nullptr;    // pair kernel of the set's current frame has finished
+    bool paired_recorded = false;
+};
+
+struct LargeScratch {
+    int cap_atoms = 0;
+    LargeBins bins[2];
+    cudaStream_t aux = nullptr;      // stream of the binning kernels
+    cudaEvent_t entry = nullptr;     // everything the caller queued before large_run
     unsigned int* d_stamp = nullptr;
     size_t stamp_elems = 0;
     unsigned int seq = 0;
@@ -46,8 +59,15 @@ struct LargeScratch {
 
 inline void large_scratch_free(LargeScratch& S)
 {
-    cudaFree(S.d_grid); cudaFree(S.d_cellcnt); cudaFree(S.d_cellptr); cudaFree(S.d_occ);
-    cudaFree(S.d_misc); cudaFree(S.d_wrapped); cudaFree(S.d_atomrank); cudaFree(S.d_sorted); cudaFree(S.d_sorted_kr);
+    for (LargeBins& B : S.bins) {
+        cudaFree(B.d_grid); cudaFree(B.d_cellcnt); cudaFree(B.d_cellptr); cudaFree(B.d_occ);
+        cudaFree(B.d_misc); cudaFree(B.d_wrapped); cudaFree(B.d_atomrank); cudaFree(B.d_sorted);
+        cudaFree(B.d_sorted_kr);
+        if (B.binned) cudaEventDestroy(B.binned);
+        if (B.paired) cudaEventDestroy(B.paired);
+    }
+    if (S.aux) cudaStreamDestroy(S.aux);
+    if (S.entry) cudaEventDestroy(S.entry);
     cudaFree(S.d_stamp);
     S = LargeScratch();
 }
@@ -288,7 +308,7 @@ struct StampSink {
     }
 };
 
-__global__ void __launch_bounds__(1024) kl_prepare(const float* __restrict__ x, int n,
+__global__ void __launch_bounds__(LG_BIN_THREADS) kl_prepare(const float* __restrict__ x, int n,
                                                    const float* __restrict__ box9, float cutoff,
                                                    GridS* __restrict__ grid, int* __restrict__ cellcnt,
                                                    int* __restrict__ misc)
@@ -299,7 +319,7 @@ __global__ void __launch_bounds__(1024) kl_prepare(const float* __restrict__ x, 
     float lo[3] = {0.f, 0.f, 0.f}, hi[3] = {0.f, 0.f, 0.f};
     if (box9 == nullptr) {
         float l0 = 3.0e38f, l1 = 3.0e38f, l2 = 3.0e38f, h0 = -3.0e38f, h1 = -3.0e38f, h2 = -3.0e38f;
-        for (int i = tid; i < n; i += 1024) {
+        for (int i = tid; i < n; i += LG_BIN_THREADS) {
             const float px = x[3 * (size_t)i], py = x[3 * (size_t)i + 1], pz = x[3 * (size_t)i + 2];
             l0 = fminf(l0, px); h0 = fmaxf(h0, px);
             l1 = fminf(l1, py); h1 = fmaxf(h1, py);
@@ -320,7 +340,7 @@ __global__ void __launch_bounds__(1024) kl_prepare(const float* __restrict__ x, 
         }
         __syncthreads();
         if (tid == 0) {
-            for (int w = 1; w < 32; w++) {
+            for (int w = 1; w < LG_BIN_THREADS / 32; w++) {
                 red[0] = fminf(red[0], red[w]); red[32] = fminf(red[32], red[32 + w]);
                 red[64] = fminf(red[64], red[64 + w]); red[96] = fmaxf(red[96], red[96 + w]);
                 red[128] = fmaxf(red[128], red[128 + w]); red[160] = fmaxf(red[160], red[160 + w]);
@@ -338,7 +358,7 @@ __global__ void __launch_bounds__(1024) kl_prepare(const float* __restrict__ x, 
     }
     __syncthreads();
     const int ncell = Gs.ncell;
-    for (int c = tid; c <= ncell; c += 1024) cellcnt[c] = 0;
+    for (int c = tid; c <= ncell; c += LG_BIN_THREADS) cellcnt[c] = 0;
 }
 
 __global__ void __launch_bounds__(256) kl_bin(const float* __restrict__ x, int n,
@@ -361,14 +381,14 @@ __global__ void __launch_bounds__(256) kl_bin(const float* __restrict__ x, int n
     if ((threadIdx.x & 31) == 0 && amax > 0.f) atomicMax(&misc[2], __float_as_int(amax));
 }
 
-__global__ void __launch_bounds__(1024) kl_scan(const GridS* __restrict__ grid, int n,
+__global__ void __launch_bounds__(LG_BIN_THREADS) kl_scan(const GridS* __restrict__ grid, int n,
                                                 const int* __restrict__ cellcnt, int* __restrict__ cellptr,
                                                 int* __restrict__ occ, int* __restrict__ misc)
 {
     __shared__ int s_sum[32], s_occ[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ncell = grid->ncell;
-    const int cpt = (ncell + 1023) / 1024;
+    const int cpt = (ncell + LG_BIN_THREADS - 1) / LG_BIN_THREADS;
     const int c0 = min(tid * cpt, ncell), c1 = min(c0 + cpt, ncell);
     int sum = 0, nocc = 0;
     for (int c = c0; c < c1; c++) {
@@ -386,7 +406,7 @@ __global__ void __launch_bounds__(1024) kl_scan(const GridS* __restrict__ grid, 
     if (lane == 31) { s_sum[warp] = isum; s_occ[warp] = iocc; }
     __syncthreads();
     if (warp == 0) {
-        int a = s_sum[lane], b = s_occ[lane];
+        int a = lane < LG_BIN_THREADS / 32 ? s_sum[lane] : 0, b = lane < LG_BIN_THREADS / 32 ? s_occ[lane] : 0;
         int ia = a, ib = b;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -396,7 +416,7 @@ __global__ void __launch_bounds__(1024) kl_scan(const GridS* __restrict__ grid, 
         }
         s_sum[lane] = ia - a;
         s_occ[lane] = ib - b;
-        if (lane == 31) misc[0] = ib;
+        if (lane == 31) misc[0] = ib;      // lanes beyond the warp count add nothing
     }
     __syncthreads();
     int run = isum - sum + s_sum[warp];
@@ -493,20 +513,28 @@ inline int large_run(const LargeJob& job, LargeScratch& S, int sm_count, cudaStr
 {
     const int n = job.n;
     if (S.cap_atoms < n) {
-        cudaFree(S.d_wrapped); cudaFree(S.d_atomrank); cudaFree(S.d_sorted); cudaFree(S.d_sorted_kr);
-        S.d_atomrank = nullptr; S.d_sorted = nullptr; S.d_wrapped = nullptr; S.d_sorted_kr = nullptr;
-        LG_CK(cudaMalloc(&S.d_sorted_kr, sizeof(float2) * (size_t)n));
-        LG_CK(cudaMalloc(&S.d_wrapped, sizeof(float4) * (size_t)n));
-        LG_CK(cudaMalloc(&S.d_atomrank, sizeof(int) * (size_t)n));
-        LG_CK(cudaMalloc(&S.d_sorted, sizeof(float4) * (size_t)n));
+        for (LargeBins& B : S.bins) {
+            cudaFree(B.d_wrapped); cudaFree(B.d_atomrank); cudaFree(B.d_sorted); cudaFree(B.d_sorted_kr);
+            B.d_atomrank = nullptr; B.d_sorted = nullptr; B.d_wrapped = nullptr; B.d_sorted_kr = nullptr;
+            LG_CK(cudaMalloc(&B.d_sorted_kr, sizeof(float2) * (size_t)n));
+            LG_CK(cudaMalloc(&B.d_wrapped, sizeof(float4) * (size_t)n));
+            LG_CK(cudaMalloc(&B.d_atomrank, sizeof(int) * (size_t)n));
+            LG_CK(cudaMalloc(&B.d_sorted, sizeof(float4) * (size_t)n));
+        }
         S.cap_atoms = n;
     }
-    if (!S.d_grid) {
-        LG_CK(cudaMalloc(&S.d_grid, sizeof(GridS)));
-        LG_CK(cudaMalloc(&S.d_cellcnt, sizeof(int) * (size_t)(LG_MAXC + 1)));
-        LG_CK(cudaMalloc(&S.d_cellptr, sizeof(int) * (size_t)(LG_MAXC + 1)));
-        LG_CK(cudaMalloc(&S.d_occ, sizeof(int) * (size_t)LG_MAXC));
-        LG_CK(cudaMalloc(&S.d_misc, sizeof(int) * 4));
+    if (!S.aux) {
+        for (LargeBins& B : S.bins) {
+            LG_CK(cudaMalloc(&B.d_grid, sizeof(GridS)));
+            LG_CK(cudaMalloc(&B.d_cellcnt, sizeof(int) * (size_t)(LG_MAXC + 1)));
+            LG_CK(cudaMalloc(&B.d_cellptr, sizeof(int) * (size_t)(LG_MAXC + 1)));
+            LG_CK(cudaMalloc(&B.d_occ, sizeof(int) * (size_t)LG_MAXC));
+            LG_CK(cudaMalloc(&B.d_misc, sizeof(int) * 4));
+            LG_CK(cudaEventCreateWithFlags(&B.binned, cudaEventDisableTiming));
+            LG_CK(cudaEventCreateWithFlags(&B.paired, cudaEventDisableTiming));
+        }
+        LG_CK(cudaEventCreateWithFlags(&S.entry, cudaEventDisableTiming));
+        LG_CK(cudaStreamCreateWithFlags(&S.aux, cudaStreamNonBlocking));
     }
     const bool want_res = (job.res_table != nullptr) || (job.res_keys != nullptr);
     if (want_res && (unsigned long long)job.n_res_c * (unsigned long long)job.n_res_c >= (1ull << 32)) {
@@ -528,6 +556,11 @@ inline int large_run(const LargeJob& job, LargeScratch& S, int sm_count, cudaStr
         S.seq = 0;
     }
     const int atom_blocks = std::min((n + 255) / 256, sm_count * 8);
+    // Two-stage pipeline over the frames: bins[f & 1] is filled on the aux stream while kl_pairs
+    // of the previous frame (other set) runs on the caller's stream.  kl_pairs launches stay in
+    // stream order, which is what the frame-stamp de-duplication needs.
+    LG_CK(cudaEventRecord(S.entry, stream));              // the frames may still be in flight (H2D)
+    LG_CK(cudaStreamWaitEvent(S.aux, S.entry, 0));
     for (long long f = 0; f < job.n_frames; f++) {
         const float* x = job.xyz + (size_t)f * (size_t)n * 3;
         const float* box9 = job.box ? job.box + (size_t)f * 9 : nullptr;
@@ -538,11 +571,15 @@ inline int large_run(const LargeJob& job, LargeScratch& S, int sm_count, cudaStr
             }
             S.seq++;
         }
-        kl_prepare<<<1, 1024, 0, stream>>>(x, n, box9, job.cutoff, S.d_grid, S.d_cellcnt, S.d_misc);
-        kl_bin<<<atom_blocks, 256, 0, stream>>>(x, n, S.d_grid, S.d_cellcnt, S.d_wrapped, S.d_atomrank, S.d_misc);
-        kl_scan<<<1, 1024, 0, stream>>>(S.d_grid, n, S.d_cellcnt, S.d_cellptr, S.d_occ, S.d_misc);
-        kl_scatter<<<atom_blocks, 256, 0, stream>>>(n, S.d_cellptr, S.d_wrapped, S.d_atomrank, job.meta, S.d_sorted,
-                                                    S.d_sorted_kr);
+        LargeBins& B = S.bins[f & 1];
+        if (B.paired_recorded) LG_CK(cudaStreamWaitEvent(S.aux, B.paired, 0));   // the set is free again
+        kl_prepare<<<1, LG_BIN_THREADS, 0, S.aux>>>(x, n, box9, job.cutoff, B.d_grid, B.d_cellcnt, B.d_misc);
+        kl_bin<<<atom_blocks, 256, 0, S.aux>>>(x, n, B.d_grid, B.d_cellcnt, B.d_wrapped, B.d_atomrank, B.d_misc);
+        kl_scan<<<1, LG_BIN_THREADS, 0, S.aux>>>(B.d_grid, n, B.d_cellcnt, B.d_cellptr, B.d_occ, B.d_misc);
+        kl_scatter<<<atom_blocks, 256, 0, S.aux>>>(n, B.d_cellptr, B.d_wrapped, B.d_atomrank, job.meta, B.d_sorted,
+                                                   B.d_sorted_kr);
+        LG_CK(cudaEventRecord(B.binned, S.aux));
+        LG_CK(cudaStreamWaitEvent(stream, B.binned, 0));
         PairParams pp;
         pp.n = n; pp.n_ignored = job.n_ignored; pp.c2 = job.c2; pp.c2_lo = pp.c2_hi = job.c2;
         pp.boundary_ulps = job.boundary_ulps; pp.xyz = x; pp.box = box9; pp.f = 0; pp.frame0 = job.frame0 + f;
@@ -563,19 +600,21 @@ inline int large_run(const LargeJob& job, LargeScratch& S, int sm_count, cudaStr
         const bool emit = job.atom_keys != nullptr;
         if (job.boundary_ulps > 0)
             kl_pairs<CT_BOUNDARY | CT_ROLES><<<pg, LG_PAIR_THREADS, 0, stream>>>(
-                pp, sink, box9, job.cutoff, S.d_grid, S.d_sorted, S.d_sorted_kr, S.d_cellptr, S.d_occ, S.d_misc);
+                pp, sink, box9, job.cutoff, B.d_grid, B.d_sorted, B.d_sorted_kr, B.d_cellptr, B.d_occ, B.d_misc);
         else if (job.count_tests && !emit)
             kl_pairs<CT_COUNT | CT_ROLES><<<pg, LG_PAIR_THREADS, 0, stream>>>(
-                pp, sink, box9, job.cutoff, S.d_grid, S.d_sorted, S.d_sorted_kr, S.d_cellptr, S.d_occ, S.d_misc);
+                pp, sink, box9, job.cutoff, B.d_grid, B.d_sorted, B.d_sorted_kr, B.d_cellptr, B.d_occ, B.d_misc);
         else if (emit)
             kl_pairs<CT_EMIT | CT_ROLES><<<pg, LG_PAIR_THREADS, 0, stream>>>(
-                pp, sink, box9, job.cutoff, S.d_grid, S.d_sorted, S.d_sorted_kr, S.d_cellptr, S.d_occ, S.d_misc);
+                pp, sink, box9, job.cutoff, B.d_grid, B.d_sorted, B.d_sorted_kr, B.d_cellptr, B.d_occ, B.d_misc);
         else if (job.all_roles)
             kl_pairs<0><<<pg, LG_PAIR_THREADS, 0, stream>>>(
-                pp, sink, box9, job.cutoff, S.d_grid, S.d_sorted, S.d_sorted_kr, S.d_cellptr, S.d_occ, S.d_misc);
+                pp, sink, box9, job.cutoff, B.d_grid, B.d_sorted, B.d_sorted_kr, B.d_cellptr, B.d_occ, B.d_misc);
         else
             kl_pairs<CT_ROLES><<<pg, LG_PAIR_THREADS, 0, stream>>>(
-                pp, sink, box9, job.cutoff, S.d_grid, S.d_sorted, S.d_sorted_kr, S.d_cellptr, S.d_occ, S.d_misc);
+                pp, sink, box9, job.cutoff, B.d_grid, B.d_sorted, B.d_sorted_kr, B.d_cellptr, B.d_occ, B.d_misc);
+        LG_CK(cudaEventRecord(B.paired, stream));
+        B.paired_recorded = true;
         launches += 5;
     }
     LG_CK(cudaGetLastError());
