@@ -211,6 +211,8 @@ struct PairCtx {
     typename Traits::cand_t* cand;              // this warp's candidate list [CT_CAND]
     typename Traits::hit_t* hitq;               // this warp's ring [CT_QCAP]
     const float4* shift;                        // [27] lattice shift of each wrap combination
+    const unsigned* cellrole;                   // 2 role bits per cell (OR over its atoms), 16 cells per word,
+                                                // or nullptr (Traits::CELL_ROLES)
 };
 
 // screening distance, as recomputed when a screened pair is accounted
@@ -459,6 +461,25 @@ __device__ __forceinline__ void ct_cell_task(const PairParams& p, const GridS& G
     const unsigned ltmask = ct_ltmask();
     const int c = (int)(task & Traits::TASK_CMASK);
     const int L = (task & Traits::TASK_PAIR) ? 2 : 1;
+    if ((FLAGS & CT_ROLES) && Traits::CELL_ROLES && (task & Traits::TASK_INTERIOR)) {
+        // Query / haystack subsets (a ligand against a receptor): most tasks cannot produce a
+        // query-haystack pair at all.  One lane per cell of the task's five runs reads the cell's
+        // role bits; the task is dropped before any candidate is loaded unless the own cells hold
+        // a query atom and the runs a haystack atom, or the other way round.
+        const int nx = G.nx, nxy = G.nx * G.ny, w = 2 + L;
+        const int t = lane - (1 + L);
+        const int r = (t >= 0) + (t >= w) + (t >= 2 * w) + (t >= 3 * w);
+        int cell = c + lane;                                    // run 0: own cells and the next one
+        cell = r == 1 ? c + nx - 1 + t : cell;
+        cell = r == 2 ? c + nxy - nx - 1 + (t - w) : cell;
+        cell = r == 3 ? c + nxy - 1 + (t - 2 * w) : cell;
+        cell = r == 4 ? c + nxy + nx - 1 + (t - 3 * w) : cell;
+        unsigned bits = 0u;
+        if (t < 4 * w) bits = (cx.cellrole[cell >> 4] >> ((cell & 15) * 2)) & 3u;
+        const unsigned all = __reduce_or_sync(FULL, bits);
+        const unsigned own = __reduce_or_sync(FULL, lane < L ? bits : 0u);
+        if (!(((own & 1u) && (all & 2u)) || ((own & 2u) && (all & 1u)))) return;
+    }
     const int cstart = (int)cx.cellptr[c], cend = (int)cx.cellptr[c + L];
 
     for (int base = 0;; base += CT_CAND) {

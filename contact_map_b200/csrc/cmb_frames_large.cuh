@@ -95,6 +95,7 @@ struct LargeTraits {
     static constexpr unsigned TASK_CMASK = 0x0fffffffu, TASK_INTERIOR = 0x10000000u, TASK_PAIR = 0x20000000u,
                               TASK_EMPTY = 0xffffffffu;
     static constexpr int TASK_BATCH = 1;          // the whole GPU shares one frame's task list
+    static constexpr bool CELL_ROLES = false;
     static __device__ __forceinline__ cand_t cand(int pos, int wrap)
     {
         return (unsigned)pos | ((unsigned)wrap << 20);
@@ -484,7 +485,7 @@ __global__ void __launch_bounds__(LG_PAIR_THREADS, LG_MIN_CTAS) kl_pairs(PairPar
     pp.c2_lo = thresh_s[0]; pp.c2_hi = thresh_s[1];
     PairCtx<LargeTraits> cx;
     cx.sorted = sorted; cx.kr = sorted_kr; cx.cellptr = cellptr;
-    cx.cand = cand_all + warp * CT_CAND; cx.hitq = hitq_all + warp * CT_QCAP;
+    cx.cand = cand_all + warp * CT_CAND; cx.hitq = hitq_all + warp * CT_QCAP; cx.cellrole = nullptr;
     cx.shift = shift_s;
     unsigned long long n_tests = 0;
     StampSink sink = sink_in;

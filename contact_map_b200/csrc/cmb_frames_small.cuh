@@ -127,7 +127,7 @@ __device__ __forceinline__ void fence_proxy_async()
 
 // ----- shared-memory layout ------------------------------------------------------
 struct FsLayout {
-    int raw_off, sorted_off, cell_off, occ_off, bm_off, cand_off, hitq_off, total;
+    int raw_off, sorted_off, cell_off, occ_off, role_off, bm_off, cand_off, hitq_off, total;
 };
 
 __host__ __device__ inline int fs_align(int x, int a) { return (x + a - 1) / a * a; }
@@ -144,6 +144,8 @@ __host__ __device__ inline FsLayout fs_layout(int n, int maxc, int bm_words_smem
     off += fs_align(2 * (maxc + 2), 128);
     L.occ_off = off;
     off += fs_align(2 * (maxc < n ? maxc : n) + 2, 128);
+    L.role_off = off;
+    off += fs_align(4 * ((maxc + 15) / 16), 128);      // 2 role bits per cell
     L.bm_off = off;
     off += fs_align(4 * bm_words_smem, 128);
     L.cand_off = off;
@@ -163,6 +165,7 @@ struct SmallTraits {
     static constexpr unsigned TASK_CMASK = 0x3fffu, TASK_INTERIOR = 0x4000u, TASK_PAIR = 0x8000u,
                               TASK_EMPTY = 0xffffu;
     static constexpr int TASK_BATCH = 4;          // ~550 list entries per frame for 16 warps
+    static constexpr bool CELL_ROLES = true;      // per-cell role bits let role-restricted runs drop tasks early
     static __device__ __forceinline__ cand_t cand(int pos, int wrap)
     {
         return (cand_t)((unsigned)pos | ((unsigned)wrap << 13));
@@ -274,6 +277,7 @@ __global__ void __launch_bounds__(FS_THREADS, FS_MIN_CTAS) k_frames_small(const 
     unsigned int* cell32 = reinterpret_cast<unsigned int*>(smem + L.cell_off);
     unsigned short* cell16 = reinterpret_cast<unsigned short*>(smem + L.cell_off);
     unsigned short* occ = reinterpret_cast<unsigned short*>(smem + L.occ_off);
+    unsigned int* cellrole = reinterpret_cast<unsigned int*>(smem + L.role_off);
     unsigned int* bitmap = p.bm_in_smem ? reinterpret_cast<unsigned int*>(smem + L.bm_off)
                                         : p.g_bitmap + (size_t)blockIdx.x * (size_t)p.bm_words;
     unsigned short* cand = reinterpret_cast<unsigned short*>(smem + L.cand_off) + warp * FS_CAND;
@@ -351,6 +355,8 @@ __global__ void __launch_bounds__(FS_THREADS, FS_MIN_CTAS) k_frames_small(const 
         // the cell arrays and the residue bitmap of the previous frame are dead: clear them here, so
         // that the barrier below is the only one before the histogram
         for (int w = tid; w < (p.maxc + 3) / 2; w += FS_THREADS) cell32[w] = 0u;
+        if (FLAGS & FS_ROLES)
+            for (int w = tid; w < (p.maxc + 15) / 16; w += FS_THREADS) cellrole[w] = 0u;
         if (res_at_once && !first_frame)
             for (int w = tid; w < p.bm_words; w += FS_THREADS) bitmap[w] = 0u;
         first_frame = false;
@@ -476,6 +482,10 @@ __global__ void __launch_bounds__(FS_THREADS, FS_MIN_CTAS) k_frames_small(const 
                 const unsigned mw = __ldg(&p.meta32[i]);
                 sorted[pos] = make_float4(xr[3 * i], xr[3 * i + 1], xr[3 * i + 2],
                                           __uint_as_float(SmallTraits::bits(i, mw >> 30, mw & FS_EKEY_MASK)));
+                if (FLAGS & FS_ROLES) {
+                    const unsigned c = my_cr[k] & 0xffffu;
+                    atomicOr(&cellrole[c >> 4], (mw >> 30) << ((c & 15u) * 2u));
+                }
             }
         }
         __syncthreads();
@@ -493,7 +503,7 @@ __global__ void __launch_bounds__(FS_THREADS, FS_MIN_CTAS) k_frames_small(const 
         pp.atom_keys = p.atom_keys; pp.atom_cap = p.atom_cap; pp.counters = p.counters;
         pp.boundary = p.boundary; pp.boundary_cap = p.boundary_cap;
         PairCtx<SmallTraits> cx;
-        cx.sorted = sorted; cx.cellptr = cell16; cx.cand = cand; cx.hitq = hitq;
+        cx.sorted = sorted; cx.cellptr = cell16; cx.cand = cand; cx.hitq = hitq; cx.cellrole = cellrole;
         cx.shift = shift_s; cx.kr = nullptr;
         BitmapSink sink{p.meta32, p.atom_table, bitmap, res_at_once ? p.res_table : nullptr, (unsigned)n,
                         (unsigned)p.n_res_c, 0u, 0u};
