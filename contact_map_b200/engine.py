@@ -513,6 +513,7 @@ class ContactEngine(object):
             if atom_table is not None or res_table is not None:
                 raise EngineError("key buffers overflowed after sizing pass")
             cap_a, cap_r = (max(cap_a, na) if want_atoms else 0), (max(cap_r, nr) if want_residues else 0)
+        repeated = self._system_key is not None and self._system_key in self._keys_hint
         if self._system_key is not None and n_frames > 0:
             self._keys_hint[self._system_key] = (max(1.0, na / n_frames) if want_atoms else hint[0],
                                                  max(1.0, nr / n_frames) if want_residues else hint[1])
@@ -526,7 +527,15 @@ class ContactEngine(object):
                 with torch.cuda.device(self.device):
                     self._check(self._L.cmb_sort_keys(self._ctx, _ptr(keys), n_keys,
                                                       _stream_ptr(self.device)), "cmb_sort_keys")
-            out.append(keys.cpu().numpy().view(np.uint64))
+            # Repeated calls (a trajectory processed chunk by chunk) copy into pinned memory from
+            # torch's caching host allocator: the copy then runs at PCIe speed and the block is
+            # recycled once the returned array, which keeps it alive, is dropped.  The first call
+            # for a system stays pageable: pinning 100 MB costs more than one slow copy.
+            host = torch.empty(n_keys, dtype=torch.int64, pin_memory=repeated)
+            host.copy_(keys, non_blocking=True)
+            out.append(host)
+        torch.cuda.current_stream(self.device).synchronize()
+        out = [None if h is None else h.numpy().view(np.uint64) for h in out]
         return out[0], out[1]
 
     def _frame_contacts_once(self, xyz, box, frame0, ak, cap_a, rk, cap_r, atom_table, res_table,

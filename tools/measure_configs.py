@@ -85,17 +85,21 @@ def main():
         res, chain = top.atom_residue_chain()
         engine.set_system(res, chain, roles(system), 0.45, 2)
         chunk = 20000
-        n_keys = 0
-        t_total = 0.0
-        for f0 in range(0, F, chunk):
-            xyz, box = device_frames(engine, system, f0, chunk)
-            ms, (ak, rk) = timed(lambda: engine.frame_contacts(xyz, box, frame0=0), repeat=1)
-            t_total += ms
-            n_keys += len(ak)
+        passes = []
+        for rep in range(2):          # pass 0 also pays for the pinned key buffers, pass 1 is steady state
+            n_keys = 0
+            t_total = 0.0
+            for f0 in range(0, F, chunk):
+                xyz, box = device_frames(engine, system, f0, chunk)
+                ms, (ak, rk) = timed(lambda: engine.frame_contacts(xyz, box, frame0=0), repeat=1)
+                t_total += ms
+                n_keys += len(ak)
+                del ak, rk
+            passes.append(t_total)
         name = "S2_ligand" if ligand else "S2_partner"
         b_alg = F * (12 * system.n_atoms + 36) + 8 * n_keys
         out[name + "_contact_trajectory"] = {
-            "frames": F, "n_atoms": system.n_atoms, "atom_keys": n_keys, "ms": t_total,
+            "frames": F, "n_atoms": system.n_atoms, "atom_keys": n_keys, "ms": t_total, "first_pass_ms": passes[0],
             "frames_per_s": F / t_total * 1e3, "includes": "key emission kernels, radix sort, D2H of the keys",
             "hbm_algorithmic_gbs": b_alg / t_total / 1e6, "hbm_frac": b_alg / t_total / 1e6 / PEAK_HBM}
         # public API: ContactTrajectory + ContactDifference(first half, second half)
