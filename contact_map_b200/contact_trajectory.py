@@ -23,7 +23,6 @@ try:
 except ImportError:  # pragma: no cover
     torch = None
 
-_MASK20 = np.uint64(0xFFFFF)
 
 
 class FrameCSR(object):
@@ -37,11 +36,15 @@ class FrameCSR(object):
 
     @classmethod
     def from_keys(cls, n_frames, keys, index_map):
-        keys = np.asarray(keys, dtype=np.uint64)
-        frame = (keys >> np.uint64(40)).astype(np.int64)
-        lo = index_map[((keys >> np.uint64(20)) & _MASK20).astype(np.int64)]
-        hi = index_map[(keys & _MASK20).astype(np.int64)]
-        return cls(n_frames, frame, np.minimum(lo, hi), np.maximum(lo, hi))
+        k = np.asarray(keys, dtype=np.uint64).view(np.int64)       # frame ids < 2^24: never negative
+        index_map = np.asarray(index_map, dtype=np.int64)
+        frame = k >> 40
+        lo = index_map[(k >> 20) & 0xFFFFF]
+        hi = index_map[k & 0xFFFFF]
+        # keys hold lo < hi in compact numbering; an increasing map (sorted used atoms) keeps that
+        if index_map.shape[0] > 1 and not bool(np.all(index_map[1:] > index_map[:-1])):
+            lo, hi = np.minimum(lo, hi), np.maximum(lo, hi)
+        return cls(n_frames, frame, lo, hi)
 
     def frame_table(self, f):
         a, b = self.ptr[f], self.ptr[f + 1]
@@ -82,10 +85,12 @@ def _build_contacts(contact_object, trajectory, chunk_bytes=64 << 20):
             cb = None if box is None else torch.as_tensor(box[f0:f1]).to(engine.device)
         ak, rk = engine.frame_contacts(cx, cb, frame0=0)
         # keys carry chunk-local frame ids; shift to trajectory frame numbers
-        atom_keys.append(ak + (np.uint64(f0) << np.uint64(40)))
-        res_keys.append(rk + (np.uint64(f0) << np.uint64(40)))
-    atom_keys = np.concatenate(atom_keys) if atom_keys else np.empty(0, np.uint64)
-    res_keys = np.concatenate(res_keys) if res_keys else np.empty(0, np.uint64)
+        atom_keys.append(ak if f0 == 0 else ak + (np.uint64(f0) << np.uint64(40)))
+        res_keys.append(rk if f0 == 0 else rk + (np.uint64(f0) << np.uint64(40)))
+    atom_keys = (atom_keys[0] if len(atom_keys) == 1 else np.concatenate(atom_keys)) if atom_keys \
+        else np.empty(0, np.uint64)
+    res_keys = (res_keys[0] if len(res_keys) == 1 else np.concatenate(res_keys)) if res_keys \
+        else np.empty(0, np.uint64)
     atoms = FrameCSR.from_keys(n_frames, atom_keys, used)
     residues = FrameCSR.from_keys(n_frames, res_keys, engine.residue_map.astype(np.int64))
     return atoms, residues
