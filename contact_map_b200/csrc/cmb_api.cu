@@ -71,6 +71,7 @@ struct cmb_ctx {
     int count_tests = 0;
     int pair_tasks = 1;
     int stage_pageable = 1;                   // pageable host input goes through threaded pinned staging
+    int large_batch = 1;                      // global-memory cell path: 0 one frame at a time, 1 auto, 2 batched whenever possible
     int atom_log2 = 0, res_log2 = 0;          // hashed count tables when > 0 (cmb_set_table_mode)
     unsigned long long* d_hstats = nullptr;   // [4] new atom keys, new residue keys, parked hits, failed re-inserts
     unsigned long long* d_ovf = nullptr;      // caller-owned overflow list (cmb_hash_overflow_buffer)
@@ -181,6 +182,11 @@ extern "C" int cmb_set_option(cmb_ctx* ctx, const char* name, int64_t value)
     if (!strcmp(name, "count_tests")) { ctx->count_tests = value != 0; return CMB_OK; }
     if (!strcmp(name, "pair_tasks")) { ctx->pair_tasks = value != 0; return CMB_OK; }
     if (!strcmp(name, "stage_pageable")) { ctx->stage_pageable = value != 0; return CMB_OK; }
+    if (!strcmp(name, "large_batch")) {
+        if (value < 0 || value > 2) return fail(ctx, CMB_ERR_ARG, "large_batch must be 0, 1 or 2");
+        ctx->large_batch = (int)value;
+        return CMB_OK;
+    }
     if (!strcmp(name, "max_cells")) {
         if (value < 8 || value > 16383) return fail(ctx, CMB_ERR_ARG, "max_cells out of range");
         ctx->fs_maxc = (int)value;
@@ -442,6 +448,7 @@ static int launch_frames(cmb_ctx* ctx, const FrameJob& job, int slot, cudaStream
     lj.all_roles = ctx->all_roles ? 1 : 0;
     lj.atom_log2 = ctx->atom_log2; lj.res_log2 = ctx->res_log2; lj.hstats = ctx->d_hstats;
     lj.ovf_list = ctx->d_ovf; lj.ovf_cap = ctx->ovf_cap;
+    lj.batch_mode = ctx->large_batch;
     std::string err;
     int launches = 0;
     int rc = large_run(lj, ctx->large[slot], ctx->sm_count, stream, err, launches);

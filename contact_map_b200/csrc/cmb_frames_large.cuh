@@ -52,6 +52,12 @@ struct LargeScratch {
     LargeBins bins[2];
     cudaStream_t aux = nullptr;      // stream of the binning kernels
     cudaEvent_t entry = nullptr;     // everything the caller queued before large_run
+    // batched mode (large_run_batched): one slice per frame of a batch
+    LargeBins batch;
+    long long batch_frames = 0;
+    int batch_atoms = 0;
+    size_t batch_bm_words = 0;
+    unsigned int* d_bitmaps = nullptr;   // [batch_frames][R_c^2 / 32] per-frame residue-pair bitmaps
     unsigned int* d_stamp = nullptr;
     size_t stamp_elems = 0;
     unsigned int seq = 0;
@@ -68,6 +74,13 @@ inline void large_scratch_free(LargeScratch& S)
     }
     if (S.aux) cudaStreamDestroy(S.aux);
     if (S.entry) cudaEventDestroy(S.entry);
+    {
+        LargeBins& B = S.batch;
+        cudaFree(B.d_grid); cudaFree(B.d_cellcnt); cudaFree(B.d_cellptr); cudaFree(B.d_occ);
+        cudaFree(B.d_misc); cudaFree(B.d_wrapped); cudaFree(B.d_atomrank); cudaFree(B.d_sorted);
+        cudaFree(B.d_sorted_kr);
+    }
+    cudaFree(S.d_bitmaps);
     cudaFree(S.d_stamp);
     S = LargeScratch();
 }
@@ -84,6 +97,7 @@ struct LargeJob {
     int atom_log2, res_log2;        // hashed tables when > 0 (table pointers are uint64 slot arrays)
     unsigned long long* hstats;
     unsigned long long* ovf_list; long long ovf_cap;
+    int batch_mode;                 // 0: one frame at a time, 1: batched when it pays (default), 2: batched whenever possible
 };
 
 // ----- traits + hit sink of the global-memory path -------------------------------------
@@ -234,6 +248,8 @@ struct StampSink {
     int pending;
     int ra, rb;                     // compact residues of the pair handed to prepare()
 
+    __device__ __forceinline__ void set_frame(int) {}
+
     __device__ __forceinline__ void resolve()
     {
         if (pending && pend_old < seq) {
@@ -309,13 +325,85 @@ struct StampSink {
     }
 };
 
-__global__ void __launch_bounds__(LG_BIN_THREADS) kl_prepare(const float* __restrict__ x, int n,
-                                                   const float* __restrict__ box9, float cutoff,
-                                                   GridS* __restrict__ grid, int* __restrict__ cellcnt,
-                                                   int* __restrict__ misc)
+// The frames one launch works on: frame `fb = blockIdx.y` of the batch uses slice fb of every
+// array (one frame at a time, batch of 1: the whole GPU on slice 0).
+struct LargeBatch {
+    const float* xyz;     // [frames][n][3], first frame of the batch
+    const float* box;     // [frames][9] or nullptr
+    int n;
+    int maxc;             // cell capacity of one slice
+    GridS* grid;          // [frames]
+    int* cellcnt;         // [frames][maxc + 1]
+    int* cellptr;         // [frames][maxc + 1]
+    int* occ;             // [frames][maxc]
+    int* misc;            // [frames][4]: n_occ, task counter, max |coordinate| (float bits)
+    float4* wrapped;      // [frames][n]
+    int* atomrank;        // [frames][n]
+    float4* sorted;       // [frames][n]
+    float2* sorted_kr;    // [frames][n]
+};
+
+// Sink of the BATCHED mode (mid-sized systems: many frames per launch, a few CTAs each).  Frames
+// of a batch run concurrently, so the per-frame residue de-duplication cannot rely on stream
+// order: every frame of the batch has its own residue-pair bitmap in global memory (R_c^2 bits,
+// L2-resident for the systems this mode is used for) and the lane whose atomicOr sets a new bit
+// counts / emits the residue pair -- the scheme of the fused kernel, in global memory.
+struct BatchSink {
+    unsigned int* atom_table;
+    unsigned int* res_table;
+    unsigned int* bitmap;           // [frames][bm_words], nullptr: residues not requested
+    long long bm_words;
+    unsigned long long* res_keys;
+    long long res_cap;
+    unsigned long long* counters;
+    unsigned int n;
+    unsigned int n_res_c;
+    long long frame_id;             // id of frame 0 of the batch, then of this CTA's frame
+    unsigned int* rcache;           // unused (interface of kl_pairs)
+    int ra, rb;
+
+    __device__ __forceinline__ void set_frame(int fb)
+    {
+        if (bitmap != nullptr) bitmap += (size_t)fb * (size_t)bm_words;
+        frame_id += fb;
+    }
+    __device__ __forceinline__ void resolve() {}
+    __device__ __forceinline__ void prepare(const PairCtx<LargeTraits>& cx, int ipos, int jpos, int, int)
+    {
+        ra = __float_as_int(__ldg(&cx.kr[ipos]).y);
+        rb = __float_as_int(__ldg(&cx.kr[jpos]).y);
+    }
+    __device__ __forceinline__ void account(int ia, int ib)
+    {
+        const int a = min(ia, ib), b = max(ia, ib);
+        if (atom_table != nullptr)
+            atomicAdd(&atom_table[(unsigned long long)a * (unsigned long long)n + (unsigned long long)b], 1u);
+        if (bitmap == nullptr) return;
+        const unsigned rlo = (unsigned)min(ra, rb), rhi = (unsigned)max(ra, rb);
+        const unsigned slot = rlo * n_res_c + rhi;              // R_c^2 < 2^32 (checked on the host)
+        const unsigned bit = 1u << (slot & 31u);
+        unsigned int* word = &bitmap[slot >> 5];
+        if (*(volatile unsigned int*)word & bit) return;        // most repeats stop here
+        if (atomicOr(word, bit) & bit) return;
+        if (res_table != nullptr) atomicAdd(&res_table[slot], 1u);
+        if (res_keys != nullptr) {
+            const unsigned long long w = atomicAdd(&counters[1], 1ull);
+            if ((long long)w < res_cap)
+                res_keys[w] = ((unsigned long long)frame_id << 40) | ((unsigned long long)rlo << 20) |
+                              (unsigned long long)rhi;
+        }
+    }
+};
+
+__global__ void __launch_bounds__(LG_BIN_THREADS) kl_prepare(LargeBatch lb, float cutoff)
 {
     __shared__ float red[6 * 32];
     __shared__ GridS Gs;
+    const int fb = blockIdx.y, n = lb.n;
+    const float* __restrict__ x = lb.xyz + (size_t)fb * (size_t)n * 3;
+    const float* __restrict__ box9 = lb.box ? lb.box + (size_t)fb * 9 : nullptr;
+    int* __restrict__ cellcnt = lb.cellcnt + (size_t)fb * (size_t)(lb.maxc + 1);
+    int* __restrict__ misc = lb.misc + (size_t)fb * 4;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float lo[3] = {0.f, 0.f, 0.f}, hi[3] = {0.f, 0.f, 0.f};
     if (box9 == nullptr) {
@@ -351,8 +439,8 @@ __global__ void __launch_bounds__(LG_BIN_THREADS) kl_prepare(const float* __rest
         }
     }
     if (tid == 0) {
-        make_grid(Gs, box9, (double)cutoff, LG_MAXC, lo, hi);
-        *grid = Gs;
+        make_grid(Gs, box9, (double)cutoff, lb.maxc, lo, hi);
+        lb.grid[fb] = Gs;
         misc[0] = 0;
         misc[1] = 0;
         misc[2] = 0;
@@ -362,12 +450,14 @@ __global__ void __launch_bounds__(LG_BIN_THREADS) kl_prepare(const float* __rest
     for (int c = tid; c <= ncell; c += LG_BIN_THREADS) cellcnt[c] = 0;
 }
 
-__global__ void __launch_bounds__(256) kl_bin(const float* __restrict__ x, int n,
-                                              const GridS* __restrict__ grid, int* __restrict__ cellcnt,
-                                              float4* __restrict__ wrapped, int* __restrict__ atomrank,
-                                              int* __restrict__ misc)
+__global__ void __launch_bounds__(256) kl_bin(LargeBatch lb)
 {
-    const GridS G = *grid;
+    const int fb = blockIdx.y, n = lb.n;
+    const float* __restrict__ x = lb.xyz + (size_t)fb * (size_t)n * 3;
+    int* __restrict__ cellcnt = lb.cellcnt + (size_t)fb * (size_t)(lb.maxc + 1);
+    float4* __restrict__ wrapped = lb.wrapped + (size_t)fb * (size_t)n;
+    int* __restrict__ atomrank = lb.atomrank + (size_t)fb * (size_t)n;
+    const GridS G = lb.grid[fb];
     float amax = 0.f;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float px = __ldg(&x[3 * (size_t)i]), py = __ldg(&x[3 * (size_t)i + 1]), pz = __ldg(&x[3 * (size_t)i + 2]);
@@ -379,14 +469,18 @@ __global__ void __launch_bounds__(256) kl_bin(const float* __restrict__ x, int n
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, d));
     // non-negative floats order like their bit patterns
-    if ((threadIdx.x & 31) == 0 && amax > 0.f) atomicMax(&misc[2], __float_as_int(amax));
+    if ((threadIdx.x & 31) == 0 && amax > 0.f) atomicMax(&lb.misc[(size_t)fb * 4 + 2], __float_as_int(amax));
 }
 
-__global__ void __launch_bounds__(LG_BIN_THREADS) kl_scan(const GridS* __restrict__ grid, int n,
-                                                const int* __restrict__ cellcnt, int* __restrict__ cellptr,
-                                                int* __restrict__ occ, int* __restrict__ misc)
+__global__ void __launch_bounds__(LG_BIN_THREADS) kl_scan(LargeBatch lb)
 {
     __shared__ int s_sum[32], s_occ[32];
+    const int fb = blockIdx.y, n = lb.n;
+    const GridS* __restrict__ grid = lb.grid + fb;
+    const int* __restrict__ cellcnt = lb.cellcnt + (size_t)fb * (size_t)(lb.maxc + 1);
+    int* __restrict__ cellptr = lb.cellptr + (size_t)fb * (size_t)(lb.maxc + 1);
+    int* __restrict__ occ = lb.occ + (size_t)fb * (size_t)lb.maxc;
+    int* __restrict__ misc = lb.misc + (size_t)fb * 4;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ncell = grid->ncell;
     const int cpt = (ncell + LG_BIN_THREADS - 1) / LG_BIN_THREADS;
@@ -436,12 +530,14 @@ __global__ void __launch_bounds__(LG_BIN_THREADS) kl_scan(const GridS* __restric
     if (tid == 0) cellptr[ncell] = n;
 }
 
-__global__ void __launch_bounds__(256) kl_scatter(int n, const int* __restrict__ cellptr,
-                                                  const float4* __restrict__ wrapped,
-                                                  const int* __restrict__ atomrank,
-                                                  const int2* __restrict__ meta,
-                                                  float4* __restrict__ sorted, float2* __restrict__ sorted_kr)
+__global__ void __launch_bounds__(256) kl_scatter(LargeBatch lb, const int2* __restrict__ meta)
 {
+    const int fb = blockIdx.y, n = lb.n;
+    const int* __restrict__ cellptr = lb.cellptr + (size_t)fb * (size_t)(lb.maxc + 1);
+    const float4* __restrict__ wrapped = lb.wrapped + (size_t)fb * (size_t)n;
+    const int* __restrict__ atomrank = lb.atomrank + (size_t)fb * (size_t)n;
+    float4* __restrict__ sorted = lb.sorted + (size_t)fb * (size_t)n;
+    float2* __restrict__ sorted_kr = lb.sorted_kr + (size_t)fb * (size_t)n;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 w = wrapped[i];
         const int pos = cellptr[__float_as_int(w.w)] + atomrank[i];
@@ -456,14 +552,11 @@ __global__ void __launch_bounds__(256) kl_scatter(int n, const int* __restrict__
 #ifndef LG_MIN_CTAS
 #define LG_MIN_CTAS 2
 #endif
-template <int FLAGS>
-__global__ void __launch_bounds__(LG_PAIR_THREADS, LG_MIN_CTAS) kl_pairs(PairParams pp, StampSink sink_in,
-                                                               const float* __restrict__ box9, float cutoff,
-                                                               const GridS* __restrict__ grid,
-                                                               const float4* __restrict__ sorted,
-                                                               const float2* __restrict__ sorted_kr,
-                                                               const int* __restrict__ cellptr,
-                                                               const int* __restrict__ occ, int* misc)
+// gridDim.x CTAs per frame, frame blockIdx.y of the batch; pp.xyz / pp.box point at the batch's
+// first frame and pp.frame0 is its id
+template <int FLAGS, typename Sink>
+__global__ void __launch_bounds__(LG_PAIR_THREADS, LG_MIN_CTAS) kl_pairs(PairParams pp, Sink sink_in, LargeBatch lb,
+                                                                         float cutoff)
 {
     __shared__ unsigned int cand_all[(LG_PAIR_THREADS / 32) * CT_CAND];
     __shared__ uint4 hitq_all[(LG_PAIR_THREADS / 32) * CT_QCAP];
@@ -471,8 +564,11 @@ __global__ void __launch_bounds__(LG_PAIR_THREADS, LG_MIN_CTAS) kl_pairs(PairPar
     __shared__ float thresh_s[2];
     __shared__ unsigned int rcache_all[(LG_PAIR_THREADS / 32) * LG_RCACHE];
     __shared__ GridS G;
+    const int fb = blockIdx.y;
+    const float* __restrict__ box9 = lb.box ? lb.box + (size_t)fb * 9 : nullptr;
+    int* misc = lb.misc + (size_t)fb * 4;
     const int warp = threadIdx.x >> 5;
-    if (threadIdx.x == 64) G = *grid;
+    if (threadIdx.x == 64) G = lb.grid[fb];
     __syncthreads();
     for (int t = threadIdx.x; t < (LG_PAIR_THREADS / 32) * LG_RCACHE; t += LG_PAIR_THREADS) rcache_all[t] = 0xffffffffu;
     if (threadIdx.x < 27) shift_s[threadIdx.x] = lattice_shift(box9, threadIdx.x);
@@ -483,15 +579,19 @@ __global__ void __launch_bounds__(LG_PAIR_THREADS, LG_MIN_CTAS) kl_pairs(PairPar
     }
     __syncthreads();
     pp.c2_lo = thresh_s[0]; pp.c2_hi = thresh_s[1];
+    pp.f = fb;
     PairCtx<LargeTraits> cx;
-    cx.sorted = sorted; cx.kr = sorted_kr; cx.cellptr = cellptr;
+    cx.sorted = lb.sorted + (size_t)fb * (size_t)lb.n;
+    cx.kr = lb.sorted_kr + (size_t)fb * (size_t)lb.n;
+    cx.cellptr = lb.cellptr + (size_t)fb * (size_t)(lb.maxc + 1);
     cx.cand = cand_all + warp * CT_CAND; cx.hitq = hitq_all + warp * CT_QCAP; cx.cellrole = nullptr;
     cx.shift = shift_s;
     unsigned long long n_tests = 0;
-    StampSink sink = sink_in;
-    sink.pending = 0; sink.pend_old = 0u; sink.pend_lo = sink.pend_hi = 0u;
+    Sink sink = sink_in;
+    sink.set_frame(fb);
     sink.rcache = rcache_all + warp * LG_RCACHE;
-    ct_pair_phase_dyn<LargeTraits, StampSink, FLAGS, int>(pp, G, cx, sink, occ, misc[0], &misc[1], n_tests);
+    ct_pair_phase_dyn<LargeTraits, Sink, FLAGS, int>(pp, G, cx, sink, lb.occ + (size_t)fb * (size_t)lb.maxc, misc[0],
+                                                     &misc[1], n_tests);
     sink.resolve();
     if (FLAGS & CT_COUNT) {
 #pragma unroll
@@ -509,10 +609,124 @@ __global__ void __launch_bounds__(LG_PAIR_THREADS, LG_MIN_CTAS) kl_pairs(PairPar
         }                                                                            \
     } while (0)
 
+// launch the pair kernel variant the job asks for
+template <typename Sink>
+inline void launch_pairs(const LargeJob& job, const PairParams& pp, const Sink& sink, const LargeBatch& lb,
+                         dim3 grid, cudaStream_t stream)
+{
+    const bool emit = job.atom_keys != nullptr;
+    if (job.boundary_ulps > 0)
+        kl_pairs<CT_BOUNDARY | CT_ROLES, Sink><<<grid, LG_PAIR_THREADS, 0, stream>>>(pp, sink, lb, job.cutoff);
+    else if (job.count_tests && !emit)
+        kl_pairs<CT_COUNT | CT_ROLES, Sink><<<grid, LG_PAIR_THREADS, 0, stream>>>(pp, sink, lb, job.cutoff);
+    else if (emit)
+        kl_pairs<CT_EMIT | CT_ROLES, Sink><<<grid, LG_PAIR_THREADS, 0, stream>>>(pp, sink, lb, job.cutoff);
+    else if (job.all_roles)
+        kl_pairs<0, Sink><<<grid, LG_PAIR_THREADS, 0, stream>>>(pp, sink, lb, job.cutoff);
+    else
+        kl_pairs<CT_ROLES, Sink><<<grid, LG_PAIR_THREADS, 0, stream>>>(pp, sink, lb, job.cutoff);
+}
+
+inline PairParams large_pair_params(const LargeJob& job, const float* x, const float* box9, long long frame0)
+{
+    PairParams pp;
+    pp.n = job.n; pp.n_ignored = job.n_ignored; pp.c2 = job.c2; pp.c2_lo = pp.c2_hi = job.c2;
+    pp.boundary_ulps = job.boundary_ulps; pp.xyz = x; pp.box = box9; pp.f = 0; pp.frame0 = frame0;
+    pp.atom_keys = job.atom_keys; pp.atom_cap = job.atom_cap; pp.counters = job.counters;
+    pp.boundary = job.boundary; pp.boundary_cap = job.boundary_cap;
+    return pp;
+}
+
+// BATCHED mode: mid-sized systems (a frame is far too little work for the whole GPU, and five
+// launches per frame would dominate).  `frames` frames per launch, `ctas` CTAs of the pair kernel
+// each; per-frame residue bitmaps instead of the stream-ordered frame stamps.  Returns 1 when
+// the mode does not apply (hashed tables, bitmaps too large, a single frame).
+constexpr int LG_BATCH_MAXC = 1 << 16;                  // cell capacity of one batch slice
+constexpr size_t LG_BATCH_BYTES = (size_t)768 << 20;    // scratch budget of the batched mode
+constexpr int LG_BATCH_MAX_ATOMS = 1 << 16;             // above this the one-frame-at-a-time mode is used
+
+inline int large_run_batched(const LargeJob& job, LargeScratch& S, int sm_count, cudaStream_t stream,
+                             std::string& err, int& launches)
+{
+    const int n = job.n;
+    const bool want_res = (job.res_table != nullptr) || (job.res_keys != nullptr);
+    if (job.batch_mode == 0 || job.atom_log2 > 0 || job.res_log2 > 0 || job.n_frames < 2) return 1;
+    if (job.batch_mode == 1 && n > LG_BATCH_MAX_ATOMS) return 1;     // big frames fill the GPU on their own
+    const size_t bm_words = want_res ? ((size_t)job.n_res_c * (size_t)job.n_res_c + 31) / 32 : 0;
+    const size_t per_frame = (size_t)n * 44 + (size_t)LG_BATCH_MAXC * 12 + 64 + sizeof(GridS) + bm_words * 4;
+    const int total_ctas = sm_count * LG_MIN_CTAS;
+    // a CTA (8 warps) per ~2000 atoms keeps the task queues of a frame busy without idling warps
+    const int ctas = std::max(1, std::min(total_ctas, (n + 2047) / 2048));
+    long long frames = std::min<long long>(job.n_frames, std::max(1, total_ctas / ctas));
+    frames = std::min<long long>(frames, (long long)(LG_BATCH_BYTES / per_frame));
+    if (frames < 2) return 1;
+    LargeBins& B = S.batch;
+    if (S.batch_frames < frames || S.batch_atoms < n || S.batch_bm_words < bm_words) {
+        cudaFree(B.d_grid); cudaFree(B.d_cellcnt); cudaFree(B.d_cellptr); cudaFree(B.d_occ); cudaFree(B.d_misc);
+        cudaFree(B.d_wrapped); cudaFree(B.d_atomrank); cudaFree(B.d_sorted); cudaFree(B.d_sorted_kr);
+        cudaFree(S.d_bitmaps);
+        B = LargeBins();
+        S.d_bitmaps = nullptr;
+        S.batch_frames = 0;
+        const size_t F = (size_t)frames;
+        LG_CK(cudaMalloc(&B.d_grid, sizeof(GridS) * F));
+        LG_CK(cudaMalloc(&B.d_cellcnt, sizeof(int) * F * (size_t)(LG_BATCH_MAXC + 1)));
+        LG_CK(cudaMalloc(&B.d_cellptr, sizeof(int) * F * (size_t)(LG_BATCH_MAXC + 1)));
+        LG_CK(cudaMalloc(&B.d_occ, sizeof(int) * F * (size_t)LG_BATCH_MAXC));
+        LG_CK(cudaMalloc(&B.d_misc, sizeof(int) * F * 4));
+        LG_CK(cudaMalloc(&B.d_wrapped, sizeof(float4) * F * (size_t)n));
+        LG_CK(cudaMalloc(&B.d_atomrank, sizeof(int) * F * (size_t)n));
+        LG_CK(cudaMalloc(&B.d_sorted, sizeof(float4) * F * (size_t)n));
+        LG_CK(cudaMalloc(&B.d_sorted_kr, sizeof(float2) * F * (size_t)n));
+        if (bm_words) LG_CK(cudaMalloc(&S.d_bitmaps, sizeof(unsigned int) * F * bm_words));
+        S.batch_frames = frames; S.batch_atoms = n; S.batch_bm_words = bm_words;
+    }
+    const int atom_blocks = std::min((n + 255) / 256, sm_count * 8);
+    for (long long f0 = 0; f0 < job.n_frames; f0 += frames) {
+        const unsigned nf = (unsigned)std::min<long long>(frames, job.n_frames - f0);
+        LargeBatch lb;
+        lb.xyz = job.xyz + (size_t)f0 * (size_t)n * 3;
+        lb.box = job.box ? job.box + (size_t)f0 * 9 : nullptr;
+        lb.n = n; lb.maxc = LG_BATCH_MAXC;
+        lb.grid = B.d_grid; lb.cellcnt = B.d_cellcnt; lb.cellptr = B.d_cellptr; lb.occ = B.d_occ; lb.misc = B.d_misc;
+        lb.wrapped = B.d_wrapped; lb.atomrank = B.d_atomrank; lb.sorted = B.d_sorted; lb.sorted_kr = B.d_sorted_kr;
+        if (bm_words) LG_CK(cudaMemsetAsync(S.d_bitmaps, 0, sizeof(unsigned int) * (size_t)nf * bm_words, stream));
+        kl_prepare<<<dim3(1, nf), LG_BIN_THREADS, 0, stream>>>(lb, job.cutoff);
+        kl_bin<<<dim3(atom_blocks, nf), 256, 0, stream>>>(lb);
+        kl_scan<<<dim3(1, nf), LG_BIN_THREADS, 0, stream>>>(lb);
+        kl_scatter<<<dim3(atom_blocks, nf), 256, 0, stream>>>(lb, job.meta);
+        const PairParams pp = large_pair_params(job, lb.xyz, lb.box, job.frame0 + f0);
+        BatchSink sink;
+        sink.atom_table = job.atom_table; sink.res_table = job.res_table;
+        sink.bitmap = want_res ? S.d_bitmaps : nullptr; sink.bm_words = (long long)bm_words;
+        sink.res_keys = job.res_keys; sink.res_cap = job.res_cap; sink.counters = job.counters;
+        sink.n = (unsigned)n; sink.n_res_c = (unsigned)job.n_res_c; sink.frame_id = job.frame0 + f0;
+        sink.rcache = nullptr; sink.ra = sink.rb = 0;
+        launch_pairs(job, pp, sink, lb, dim3(ctas, nf), stream);
+        launches += 5;
+    }
+    LG_CK(cudaGetLastError());
+    return 0;
+}
+
 inline int large_run(const LargeJob& job, LargeScratch& S, int sm_count, cudaStream_t stream,
                      std::string& err, int& launches)
 {
     const int n = job.n;
+    const bool want_res = (job.res_table != nullptr) || (job.res_keys != nullptr);
+    if (want_res && (unsigned long long)job.n_res_c * (unsigned long long)job.n_res_c >= (1ull << 32)) {
+        err = "more than 65535 used residues: residue table index exceeds 32 bits";
+        return -4;
+    }
+    if (job.res_log2 > 0 && job.res_table == nullptr && job.res_keys != nullptr) {
+        err = "per-frame residue keys need a residue table (dense or hashed) for the de-duplication";
+        return -1;
+    }
+    {
+        const int rc = large_run_batched(job, S, sm_count, stream, err, launches);
+        if (rc <= 0) return rc;
+    }
+    // ONE FRAME AT A TIME: the whole GPU on a frame, residue de-duplication by frame stamps
     if (S.cap_atoms < n) {
         for (LargeBins& B : S.bins) {
             cudaFree(B.d_wrapped); cudaFree(B.d_atomrank); cudaFree(B.d_sorted); cudaFree(B.d_sorted_kr);
@@ -537,15 +751,6 @@ inline int large_run(const LargeJob& job, LargeScratch& S, int sm_count, cudaStr
         LG_CK(cudaEventCreateWithFlags(&S.entry, cudaEventDisableTiming));
         LG_CK(cudaStreamCreateWithFlags(&S.aux, cudaStreamNonBlocking));
     }
-    const bool want_res = (job.res_table != nullptr) || (job.res_keys != nullptr);
-    if (want_res && (unsigned long long)job.n_res_c * (unsigned long long)job.n_res_c >= (1ull << 32)) {
-        err = "more than 65535 used residues: residue table index exceeds 32 bits";
-        return -4;
-    }
-    if (job.res_log2 > 0 && job.res_table == nullptr && job.res_keys != nullptr) {
-        err = "per-frame residue keys need a residue table (dense or hashed) for the de-duplication";
-        return -1;
-    }
     const size_t need_stamp = job.res_log2 > 0 ? ((size_t)1 << job.res_log2)
                                                : (size_t)job.n_res_c * (size_t)job.n_res_c;
     if (want_res && S.stamp_elems < need_stamp) {
@@ -563,8 +768,6 @@ inline int large_run(const LargeJob& job, LargeScratch& S, int sm_count, cudaStr
     LG_CK(cudaEventRecord(S.entry, stream));              // the frames may still be in flight (H2D)
     LG_CK(cudaStreamWaitEvent(S.aux, S.entry, 0));
     for (long long f = 0; f < job.n_frames; f++) {
-        const float* x = job.xyz + (size_t)f * (size_t)n * 3;
-        const float* box9 = job.box ? job.box + (size_t)f * 9 : nullptr;
         if (want_res) {
             if (S.seq == 0xffffffffu) {
                 LG_CK(cudaMemsetAsync(S.d_stamp, 0, sizeof(unsigned int) * S.stamp_elems, stream));
@@ -573,19 +776,20 @@ inline int large_run(const LargeJob& job, LargeScratch& S, int sm_count, cudaStr
             S.seq++;
         }
         LargeBins& B = S.bins[f & 1];
+        LargeBatch lb;
+        lb.xyz = job.xyz + (size_t)f * (size_t)n * 3;
+        lb.box = job.box ? job.box + (size_t)f * 9 : nullptr;
+        lb.n = n; lb.maxc = LG_MAXC;
+        lb.grid = B.d_grid; lb.cellcnt = B.d_cellcnt; lb.cellptr = B.d_cellptr; lb.occ = B.d_occ; lb.misc = B.d_misc;
+        lb.wrapped = B.d_wrapped; lb.atomrank = B.d_atomrank; lb.sorted = B.d_sorted; lb.sorted_kr = B.d_sorted_kr;
         if (B.paired_recorded) LG_CK(cudaStreamWaitEvent(S.aux, B.paired, 0));   // the set is free again
-        kl_prepare<<<1, LG_BIN_THREADS, 0, S.aux>>>(x, n, box9, job.cutoff, B.d_grid, B.d_cellcnt, B.d_misc);
-        kl_bin<<<atom_blocks, 256, 0, S.aux>>>(x, n, B.d_grid, B.d_cellcnt, B.d_wrapped, B.d_atomrank, B.d_misc);
-        kl_scan<<<1, LG_BIN_THREADS, 0, S.aux>>>(B.d_grid, n, B.d_cellcnt, B.d_cellptr, B.d_occ, B.d_misc);
-        kl_scatter<<<atom_blocks, 256, 0, S.aux>>>(n, B.d_cellptr, B.d_wrapped, B.d_atomrank, job.meta, B.d_sorted,
-                                                   B.d_sorted_kr);
+        kl_prepare<<<1, LG_BIN_THREADS, 0, S.aux>>>(lb, job.cutoff);
+        kl_bin<<<atom_blocks, 256, 0, S.aux>>>(lb);
+        kl_scan<<<1, LG_BIN_THREADS, 0, S.aux>>>(lb);
+        kl_scatter<<<atom_blocks, 256, 0, S.aux>>>(lb, job.meta);
         LG_CK(cudaEventRecord(B.binned, S.aux));
         LG_CK(cudaStreamWaitEvent(stream, B.binned, 0));
-        PairParams pp;
-        pp.n = n; pp.n_ignored = job.n_ignored; pp.c2 = job.c2; pp.c2_lo = pp.c2_hi = job.c2;
-        pp.boundary_ulps = job.boundary_ulps; pp.xyz = x; pp.box = box9; pp.f = 0; pp.frame0 = job.frame0 + f;
-        pp.atom_keys = job.atom_keys; pp.atom_cap = job.atom_cap; pp.counters = job.counters;
-        pp.boundary = job.boundary; pp.boundary_cap = job.boundary_cap;
+        const PairParams pp = large_pair_params(job, lb.xyz, lb.box, job.frame0 + f);
         StampSink sink;
         sink.meta = job.meta; sink.atom_table = job.atom_table;
         sink.stamp = want_res ? S.d_stamp : nullptr;
@@ -597,23 +801,7 @@ inline int large_run(const LargeJob& job, LargeScratch& S, int sm_count, cudaStr
         sink.counters = job.counters; sink.seq = S.seq; sink.n = (unsigned)n;
         sink.n_res_c = (unsigned)job.n_res_c; sink.frame_id = job.frame0 + f;
         sink.pending = 0; sink.pend_old = 0u; sink.pend_lo = sink.pend_hi = 0u; sink.ra = sink.rb = 0;
-        const int pg = sm_count * LG_MIN_CTAS;
-        const bool emit = job.atom_keys != nullptr;
-        if (job.boundary_ulps > 0)
-            kl_pairs<CT_BOUNDARY | CT_ROLES><<<pg, LG_PAIR_THREADS, 0, stream>>>(
-                pp, sink, box9, job.cutoff, B.d_grid, B.d_sorted, B.d_sorted_kr, B.d_cellptr, B.d_occ, B.d_misc);
-        else if (job.count_tests && !emit)
-            kl_pairs<CT_COUNT | CT_ROLES><<<pg, LG_PAIR_THREADS, 0, stream>>>(
-                pp, sink, box9, job.cutoff, B.d_grid, B.d_sorted, B.d_sorted_kr, B.d_cellptr, B.d_occ, B.d_misc);
-        else if (emit)
-            kl_pairs<CT_EMIT | CT_ROLES><<<pg, LG_PAIR_THREADS, 0, stream>>>(
-                pp, sink, box9, job.cutoff, B.d_grid, B.d_sorted, B.d_sorted_kr, B.d_cellptr, B.d_occ, B.d_misc);
-        else if (job.all_roles)
-            kl_pairs<0><<<pg, LG_PAIR_THREADS, 0, stream>>>(
-                pp, sink, box9, job.cutoff, B.d_grid, B.d_sorted, B.d_sorted_kr, B.d_cellptr, B.d_occ, B.d_misc);
-        else
-            kl_pairs<CT_ROLES><<<pg, LG_PAIR_THREADS, 0, stream>>>(
-                pp, sink, box9, job.cutoff, B.d_grid, B.d_sorted, B.d_sorted_kr, B.d_cellptr, B.d_occ, B.d_misc);
+        launch_pairs(job, pp, sink, lb, dim3(sm_count * LG_MIN_CTAS, 1), stream);
         LG_CK(cudaEventRecord(B.paired, stream));
         B.paired_recorded = true;
         launches += 5;

@@ -166,7 +166,11 @@ int cmb_boundary_pairs(cmb_ctx* ctx, const float* d_xyz, const float* d_box, int
                        void* stream);
 
 /* Executed candidate-pair tests of the last accumulate / frame_contacts call when
- * enabled with cmb_set_option(ctx, "count_tests", 1) (bench metric; synchronises). */
+ * enabled with cmb_set_option(ctx, "count_tests", 1) (bench metric; synchronises).
+ * Other options: "force_path" (-1 auto, 0 fused kernel, 1 global-memory cell path), "max_cells",
+ * "pair_tasks", "stage_pageable", "large_batch" (global-memory cell path: 0 = one frame at a time
+ * with frame stamps, 1 = many frames per launch with per-frame residue bitmaps when the system
+ * is small enough for that to pay (default), 2 = batched whenever the bitmaps fit). */
 int cmb_set_option(cmb_ctx* ctx, const char* name, int64_t value);
 int cmb_get_stat(cmb_ctx* ctx, const char* name, int64_t* value);
 

@@ -50,8 +50,10 @@ def test_large_path_forced_on_small_systems(engine, box_kind):
     d_xyz = torch.as_tensor(xyz, device=engine.device)
     d_box = None if box is None else torch.as_tensor(box, device=engine.device)
     results = []
-    for force in (1, 0):
+    # global-memory path one frame at a time (frame stamps), batched (per-frame bitmaps), fused kernel
+    for force, batch in ((1, 0), (1, 2), (0, 1)):
         engine.set_option("force_path", force)
+        engine.set_option("large_batch", batch)
         engine.set_system(res, chain, role, 0.45, 2)
         assert engine.path_kind == force
         atom_t, res_t = engine.new_tables()
@@ -66,7 +68,9 @@ def test_large_path_forced_on_small_systems(engine, box_kind):
         results.append((akeys, rkeys))
         assert len(akeys) == int(ref_atom.sum()) and len(rkeys) == int(ref_res.sum())
     engine.set_option("force_path", -1)
-    assert np.array_equal(results[0][0], results[1][0]) and np.array_equal(results[0][1], results[1][1])
+    engine.set_option("large_batch", 1)
+    for other in results[1:]:
+        assert np.array_equal(results[0][0], other[0]) and np.array_equal(results[0][1], other[1])
 
 
 @pytest.mark.parametrize("box_kind", ["triclinic", "none"])
