@@ -642,8 +642,8 @@ inline PairParams large_pair_params(const LargeJob& job, const float* x, const f
 // each; per-frame residue bitmaps instead of the stream-ordered frame stamps.  Returns 1 when
 // the mode does not apply (hashed tables, bitmaps too large, a single frame).
 constexpr int LG_BATCH_MAXC = 1 << 16;                  // cell capacity of one batch slice
-constexpr size_t LG_BATCH_BYTES = (size_t)768 << 20;    // scratch budget of the batched mode
-constexpr int LG_BATCH_MAX_ATOMS = 1 << 16;             // above this the one-frame-at-a-time mode is used
+constexpr size_t LG_BATCH_BYTES = (size_t)1024 << 20;   // scratch budget of the batched mode
+constexpr int LG_BATCH_MAX_ATOMS = 1 << 18;             // mode 1: above this the one-frame-at-a-time mode is used
 
 inline int large_run_batched(const LargeJob& job, LargeScratch& S, int sm_count, cudaStream_t stream,
                              std::string& err, int& launches)

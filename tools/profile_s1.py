@@ -28,6 +28,8 @@ def main():
     role = np.zeros(n, dtype=np.uint8)
     role[np.arange(n) if system.query is None else system.query] |= 1
     role[np.arange(n) if system.haystack is None else system.haystack] |= 2
+    if os.environ.get("CMB_LARGE_BATCH"):
+        engine.set_option("large_batch", int(os.environ["CMB_LARGE_BATCH"]))
     engine.set_system(atom_res, atom_chain, role, 0.45, 2)
     dev = engine.device
     d_xyz = engine.synth_frames(torch.as_tensor(system.base, device=dev),

@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from contact_map_b200 import synth
 from contact_map_b200.engine import get_engine
 engine = get_engine(0); dev = engine.device
-for n_res in (100, 200, 270, 280, 300, 400, 500, 614, 700, 1000):
+for n_res in [int(a) for a in sys.argv[1:]] or (100, 200, 270, 280, 300, 400, 500, 614, 700, 1000, 2000, 5000):
     edge = 7.0 * (n_res / 270.0) ** (1.0 / 3.0)
     system = synth.kras_like(n_res=n_res, box=(edge, edge * 1.07, edge * 1.14))
     top = system.topology; n = top.n_atoms
