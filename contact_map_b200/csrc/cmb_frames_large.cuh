@@ -53,11 +53,13 @@ struct LargeScratch {
     cudaStream_t aux = nullptr;      // stream of the binning kernels
     cudaEvent_t entry = nullptr;     // everything the caller queued before large_run
     // batched mode (large_run_batched): one slice per frame of a batch
-    LargeBins batch;
+    LargeBins batch[2];              // two sets: binning of batch k + 1 overlaps the pair kernel of batch k
     long long batch_frames = 0;
     int batch_atoms = 0;
     size_t batch_bm_words = 0;
     unsigned int* d_bitmaps = nullptr;   // [batch_frames][R_c^2 / 32] per-frame residue-pair bitmaps
+    cudaStream_t aux_batch = nullptr;
+    cudaEvent_t entry_batch = nullptr;
     unsigned int* d_stamp = nullptr;
     size_t stamp_elems = 0;
     unsigned int seq = 0;
@@ -74,13 +76,16 @@ inline void large_scratch_free(LargeScratch& S)
     }
     if (S.aux) cudaStreamDestroy(S.aux);
     if (S.entry) cudaEventDestroy(S.entry);
-    {
-        LargeBins& B = S.batch;
+    for (LargeBins& B : S.batch) {
         cudaFree(B.d_grid); cudaFree(B.d_cellcnt); cudaFree(B.d_cellptr); cudaFree(B.d_occ);
         cudaFree(B.d_misc); cudaFree(B.d_wrapped); cudaFree(B.d_atomrank); cudaFree(B.d_sorted);
         cudaFree(B.d_sorted_kr);
+        if (B.binned) cudaEventDestroy(B.binned);
+        if (B.paired) cudaEventDestroy(B.paired);
     }
     cudaFree(S.d_bitmaps);
+    if (S.aux_batch) cudaStreamDestroy(S.aux_batch);
+    if (S.entry_batch) cudaEventDestroy(S.entry_batch);
     cudaFree(S.d_stamp);
     S = LargeScratch();
 }
@@ -641,6 +646,9 @@ inline PairParams large_pair_params(const LargeJob& job, const float* x, const f
 // launches per frame would dominate).  `frames` frames per launch, `ctas` CTAs of the pair kernel
 // each; per-frame residue bitmaps instead of the stream-ordered frame stamps.  Returns 1 when
 // the mode does not apply (hashed tables, bitmaps too large, a single frame).
+#ifndef LG_BATCH_ATOMS_PER_CTA
+#define LG_BATCH_ATOMS_PER_CTA 8192
+#endif
 constexpr int LG_BATCH_MAXC = 1 << 16;                  // cell capacity of one batch slice
 constexpr size_t LG_BATCH_BYTES = (size_t)1024 << 20;   // scratch budget of the batched mode
 constexpr int LG_BATCH_MAX_ATOMS = 1 << 18;             // mode 1: above this the one-frame-at-a-time mode is used
@@ -653,48 +661,69 @@ inline int large_run_batched(const LargeJob& job, LargeScratch& S, int sm_count,
     if (job.batch_mode == 0 || job.atom_log2 > 0 || job.res_log2 > 0 || job.n_frames < 2) return 1;
     if (job.batch_mode == 1 && n > LG_BATCH_MAX_ATOMS) return 1;     // big frames fill the GPU on their own
     const size_t bm_words = want_res ? ((size_t)job.n_res_c * (size_t)job.n_res_c + 31) / 32 : 0;
-    const size_t per_frame = (size_t)n * 44 + (size_t)LG_BATCH_MAXC * 12 + 64 + sizeof(GridS) + bm_words * 4;
+    const size_t per_frame = 2 * ((size_t)n * 44 + (size_t)LG_BATCH_MAXC * 12 + 64 + sizeof(GridS)) + bm_words * 4;
     const int total_ctas = sm_count * LG_MIN_CTAS;
-    // a CTA (8 warps) per ~2000 atoms keeps the task queues of a frame busy without idling warps
-    const int ctas = std::max(1, std::min(total_ctas, (n + 2047) / 2048));
-    long long frames = std::min<long long>(job.n_frames, std::max(1, total_ctas / ctas));
+    // as many frames per launch as the scratch budget allows, at least one CTA (8 warps) per
+    // LG_BATCH_ATOMS_PER_CTA atoms of a frame (measured: fewer, longer-lived CTAs per frame win),
+    // and the CTAs the frame count leaves free are spread over the frames
+    const int ctas_min = std::max(1, std::min(total_ctas, (n + LG_BATCH_ATOMS_PER_CTA - 1) / LG_BATCH_ATOMS_PER_CTA));
+    long long frames = std::min<long long>(job.n_frames, std::max(1, total_ctas / ctas_min));
     frames = std::min<long long>(frames, (long long)(LG_BATCH_BYTES / per_frame));
     if (frames < 2) return 1;
-    LargeBins& B = S.batch;
+    const int ctas = std::max<int>(ctas_min, (int)(total_ctas / frames));
     if (S.batch_frames < frames || S.batch_atoms < n || S.batch_bm_words < bm_words) {
-        cudaFree(B.d_grid); cudaFree(B.d_cellcnt); cudaFree(B.d_cellptr); cudaFree(B.d_occ); cudaFree(B.d_misc);
-        cudaFree(B.d_wrapped); cudaFree(B.d_atomrank); cudaFree(B.d_sorted); cudaFree(B.d_sorted_kr);
         cudaFree(S.d_bitmaps);
-        B = LargeBins();
         S.d_bitmaps = nullptr;
         S.batch_frames = 0;
         const size_t F = (size_t)frames;
-        LG_CK(cudaMalloc(&B.d_grid, sizeof(GridS) * F));
-        LG_CK(cudaMalloc(&B.d_cellcnt, sizeof(int) * F * (size_t)(LG_BATCH_MAXC + 1)));
-        LG_CK(cudaMalloc(&B.d_cellptr, sizeof(int) * F * (size_t)(LG_BATCH_MAXC + 1)));
-        LG_CK(cudaMalloc(&B.d_occ, sizeof(int) * F * (size_t)LG_BATCH_MAXC));
-        LG_CK(cudaMalloc(&B.d_misc, sizeof(int) * F * 4));
-        LG_CK(cudaMalloc(&B.d_wrapped, sizeof(float4) * F * (size_t)n));
-        LG_CK(cudaMalloc(&B.d_atomrank, sizeof(int) * F * (size_t)n));
-        LG_CK(cudaMalloc(&B.d_sorted, sizeof(float4) * F * (size_t)n));
-        LG_CK(cudaMalloc(&B.d_sorted_kr, sizeof(float2) * F * (size_t)n));
+        for (LargeBins& B : S.batch) {
+            cudaFree(B.d_grid); cudaFree(B.d_cellcnt); cudaFree(B.d_cellptr); cudaFree(B.d_occ); cudaFree(B.d_misc);
+            cudaFree(B.d_wrapped); cudaFree(B.d_atomrank); cudaFree(B.d_sorted); cudaFree(B.d_sorted_kr);
+            B.d_grid = nullptr; B.d_cellcnt = B.d_cellptr = B.d_occ = B.d_misc = B.d_atomrank = nullptr;
+            B.d_wrapped = B.d_sorted = nullptr; B.d_sorted_kr = nullptr;
+            LG_CK(cudaMalloc(&B.d_grid, sizeof(GridS) * F));
+            LG_CK(cudaMalloc(&B.d_cellcnt, sizeof(int) * F * (size_t)(LG_BATCH_MAXC + 1)));
+            LG_CK(cudaMalloc(&B.d_cellptr, sizeof(int) * F * (size_t)(LG_BATCH_MAXC + 1)));
+            LG_CK(cudaMalloc(&B.d_occ, sizeof(int) * F * (size_t)LG_BATCH_MAXC));
+            LG_CK(cudaMalloc(&B.d_misc, sizeof(int) * F * 4));
+            LG_CK(cudaMalloc(&B.d_wrapped, sizeof(float4) * F * (size_t)n));
+            LG_CK(cudaMalloc(&B.d_atomrank, sizeof(int) * F * (size_t)n));
+            LG_CK(cudaMalloc(&B.d_sorted, sizeof(float4) * F * (size_t)n));
+            LG_CK(cudaMalloc(&B.d_sorted_kr, sizeof(float2) * F * (size_t)n));
+            if (!B.binned) LG_CK(cudaEventCreateWithFlags(&B.binned, cudaEventDisableTiming));
+            if (!B.paired) LG_CK(cudaEventCreateWithFlags(&B.paired, cudaEventDisableTiming));
+            B.paired_recorded = false;
+        }
         if (bm_words) LG_CK(cudaMalloc(&S.d_bitmaps, sizeof(unsigned int) * F * bm_words));
         S.batch_frames = frames; S.batch_atoms = n; S.batch_bm_words = bm_words;
     }
+    if (!S.aux_batch) {
+        LG_CK(cudaEventCreateWithFlags(&S.entry_batch, cudaEventDisableTiming));
+        LG_CK(cudaStreamCreateWithFlags(&S.aux_batch, cudaStreamNonBlocking));
+    }
     const int atom_blocks = std::min((n + 255) / 256, sm_count * 8);
-    for (long long f0 = 0; f0 < job.n_frames; f0 += frames) {
+    // binning of batch k + 1 (aux stream, other buffer set) under the pair kernel of batch k; the
+    // bitmaps are only touched on the caller's stream
+    LG_CK(cudaEventRecord(S.entry_batch, stream));         // the frames may still be in flight (H2D)
+    LG_CK(cudaStreamWaitEvent(S.aux_batch, S.entry_batch, 0));
+    int kb = 0;
+    for (long long f0 = 0; f0 < job.n_frames; f0 += frames, kb++) {
         const unsigned nf = (unsigned)std::min<long long>(frames, job.n_frames - f0);
+        LargeBins& B = S.batch[kb & 1];
         LargeBatch lb;
         lb.xyz = job.xyz + (size_t)f0 * (size_t)n * 3;
         lb.box = job.box ? job.box + (size_t)f0 * 9 : nullptr;
         lb.n = n; lb.maxc = LG_BATCH_MAXC;
         lb.grid = B.d_grid; lb.cellcnt = B.d_cellcnt; lb.cellptr = B.d_cellptr; lb.occ = B.d_occ; lb.misc = B.d_misc;
         lb.wrapped = B.d_wrapped; lb.atomrank = B.d_atomrank; lb.sorted = B.d_sorted; lb.sorted_kr = B.d_sorted_kr;
+        if (B.paired_recorded) LG_CK(cudaStreamWaitEvent(S.aux_batch, B.paired, 0));   // the set is free again
+        kl_prepare<<<dim3(1, nf), LG_BIN_THREADS, 0, S.aux_batch>>>(lb, job.cutoff);
+        kl_bin<<<dim3(atom_blocks, nf), 256, 0, S.aux_batch>>>(lb);
+        kl_scan<<<dim3(1, nf), LG_BIN_THREADS, 0, S.aux_batch>>>(lb);
+        kl_scatter<<<dim3(atom_blocks, nf), 256, 0, S.aux_batch>>>(lb, job.meta);
+        LG_CK(cudaEventRecord(B.binned, S.aux_batch));
         if (bm_words) LG_CK(cudaMemsetAsync(S.d_bitmaps, 0, sizeof(unsigned int) * (size_t)nf * bm_words, stream));
-        kl_prepare<<<dim3(1, nf), LG_BIN_THREADS, 0, stream>>>(lb, job.cutoff);
-        kl_bin<<<dim3(atom_blocks, nf), 256, 0, stream>>>(lb);
-        kl_scan<<<dim3(1, nf), LG_BIN_THREADS, 0, stream>>>(lb);
-        kl_scatter<<<dim3(atom_blocks, nf), 256, 0, stream>>>(lb, job.meta);
+        LG_CK(cudaStreamWaitEvent(stream, B.binned, 0));
         const PairParams pp = large_pair_params(job, lb.xyz, lb.box, job.frame0 + f0);
         BatchSink sink;
         sink.atom_table = job.atom_table; sink.res_table = job.res_table;
@@ -703,6 +732,8 @@ inline int large_run_batched(const LargeJob& job, LargeScratch& S, int sm_count,
         sink.n = (unsigned)n; sink.n_res_c = (unsigned)job.n_res_c; sink.frame_id = job.frame0 + f0;
         sink.rcache = nullptr; sink.ra = sink.rb = 0;
         launch_pairs(job, pp, sink, lb, dim3(ctas, nf), stream);
+        LG_CK(cudaEventRecord(B.paired, stream));
+        B.paired_recorded = true;
         launches += 5;
     }
     LG_CK(cudaGetLastError());
