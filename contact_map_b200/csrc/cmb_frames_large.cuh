@@ -26,6 +26,9 @@ constexpr int LG_MAXC = 1 << 21;
 #define LG_PAIR_THREADS_CFG 256
 #endif
 constexpr int LG_PAIR_THREADS = LG_PAIR_THREADS_CFG;
+#ifndef LG_MIN_CTAS
+#define LG_MIN_CTAS 2
+#endif
 constexpr int LG_BIN_THREADS = 256;      // single-CTA set-up / scan kernels: small enough to share an SM with kl_pairs
 constexpr int LG_RCACHE = 128;          // per-warp cache of stamped residue pairs (entries)
 
@@ -231,6 +234,7 @@ __device__ __forceinline__ void ht_park(const HashOverflow& o, unsigned long lon
 // drain that hit the same residue pair are merged first (__match_any_sync), which removes most of
 // the atomics for 3-atom solvent residues.
 struct StampSink {
+    static constexpr int MIN_CTAS = LG_MIN_CTAS;    // resident CTAs per SM of kl_pairs with this sink
     const int2* meta;               // [n] {ekey, res_c | role << 30}
     unsigned int* atom_table;
     unsigned int* stamp;            // nullptr: residues not requested
@@ -354,6 +358,9 @@ struct LargeBatch {
 // L2-resident for the systems this mode is used for) and the lane whose atomicOr sets a new bit
 // counts / emits the residue pair -- the scheme of the fused kernel, in global memory.
 struct BatchSink {
+    // resident CTAs per SM of kl_pairs with this sink: the batched schedule is latency-bound and not
+    // limited by table thrashing, more warps pay (measured 2 / 3 / 4 / 5 / 6: best at 4)
+    static constexpr int MIN_CTAS = 4;
     unsigned int* atom_table;
     unsigned int* res_table;
     unsigned int* bitmap;           // [frames][bm_words], nullptr: residues not requested
@@ -554,13 +561,10 @@ __global__ void __launch_bounds__(256) kl_scatter(LargeBatch lb, const int2* __r
     }
 }
 
-#ifndef LG_MIN_CTAS
-#define LG_MIN_CTAS 2
-#endif
 // gridDim.x CTAs per frame, frame blockIdx.y of the batch; pp.xyz / pp.box point at the batch's
 // first frame and pp.frame0 is its id
 template <int FLAGS, typename Sink>
-__global__ void __launch_bounds__(LG_PAIR_THREADS, LG_MIN_CTAS) kl_pairs(PairParams pp, Sink sink_in, LargeBatch lb,
+__global__ void __launch_bounds__(LG_PAIR_THREADS, Sink::MIN_CTAS) kl_pairs(PairParams pp, Sink sink_in, LargeBatch lb,
                                                                          float cutoff)
 {
     __shared__ unsigned int cand_all[(LG_PAIR_THREADS / 32) * CT_CAND];
@@ -662,7 +666,7 @@ inline int large_run_batched(const LargeJob& job, LargeScratch& S, int sm_count,
     if (job.batch_mode == 1 && n > LG_BATCH_MAX_ATOMS) return 1;     // big frames fill the GPU on their own
     const size_t bm_words = want_res ? ((size_t)job.n_res_c * (size_t)job.n_res_c + 31) / 32 : 0;
     const size_t per_frame = 2 * ((size_t)n * 44 + (size_t)LG_BATCH_MAXC * 12 + 64 + sizeof(GridS)) + bm_words * 4;
-    const int total_ctas = sm_count * LG_MIN_CTAS;
+    const int total_ctas = sm_count * BatchSink::MIN_CTAS;
     // as many frames per launch as the scratch budget allows, at least one CTA (8 warps) per
     // LG_BATCH_ATOMS_PER_CTA atoms of a frame (measured: fewer, longer-lived CTAs per frame win),
     // and the CTAs the frame count leaves free are spread over the frames
