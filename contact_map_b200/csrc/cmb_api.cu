@@ -44,6 +44,7 @@ struct cmb_ctx {
     int fs_bm_in_smem = 1;
     int fs_smem = 0;
     int fs_ctas_per_sm = 1;
+    int fs_threads = 512;             // 512 (two CTAs per SM) or 1024 (one CTA per SM)
 
     // scratch, two slots so that two in-flight launches never share it
     unsigned int* d_bitmap[2] = {nullptr, nullptr};
@@ -218,6 +219,23 @@ extern "C" int cmb_get_stat(cmb_ctx* ctx, const char* name, int64_t* value)
 // ---------------------------------------------------------------------------------
 // system set-up
 // ---------------------------------------------------------------------------------
+template <int THREADS>
+static int fs_prepare(cmb_ctx* ctx, int smem_total, int* ctas_per_sm)
+{
+    CK(cudaFuncSetAttribute(k_frames_small<0, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total));
+    CK(cudaFuncSetAttribute(k_frames_small<FS_ROLES, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total));
+    CK(cudaFuncSetAttribute(k_frames_small<FS_EMIT, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total));
+    CK(cudaFuncSetAttribute(k_frames_small<FS_EMIT | FS_ROLES, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            smem_total));
+    CK(cudaFuncSetAttribute(k_frames_small<FS_BOUNDARY | FS_ROLES, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            smem_total));
+    CK(cudaFuncSetAttribute(k_frames_small<FS_COUNT | FS_ROLES, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            smem_total));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, k_frames_small<0, THREADS>, THREADS,
+                                                     (size_t)smem_total));
+    return CMB_OK;
+}
+
 static int configure_small_path(cmb_ctx* ctx)
 {
     const int n = ctx->n;
@@ -225,27 +243,39 @@ static int configure_small_path(cmb_ctx* ctx)
     ctx->fs_bm_words = (int)((bits + 31) / 32);
     // residue bitmap in shared memory when it leaves room for two CTAs per SM
     int maxc = ctx->fs_maxc;
-    FsLayout with_bm = fs_layout(n, maxc, ctx->fs_bm_words);
     const int budget_two = (ctx->max_smem_optin + 1024) / 2 - 1024;
+    // 512 threads and two CTAs per SM when two copies of the arrays fit, else one CTA of 1024 threads
+    // (same number of warps per SM; its per-warp candidate lists and rings need 12 KB more)
+    int warps = 16;
+    {
+        const FsLayout two = fs_layout(n, maxc, ctx->fs_bm_words, 16);
+        const FsLayout two_nobm = fs_layout(n, maxc, ctx->fs_bm_words * 4 > 48 * 1024 ? 0 : ctx->fs_bm_words, 16);
+        if (two.total > budget_two && two_nobm.total > budget_two &&
+            fs_layout(n, maxc, 0, 32).total <= ctx->max_smem_optin)
+            warps = 32;
+    }
+    FsLayout with_bm = fs_layout(n, maxc, ctx->fs_bm_words, warps);
     ctx->fs_bm_in_smem = 1;
-    if (with_bm.total > ctx->max_smem_optin || (ctx->fs_bm_words * 4 > 48 * 1024 && with_bm.total > budget_two))
+    if (with_bm.total > ctx->max_smem_optin ||
+        (warps == 16 && ctx->fs_bm_words * 4 > 48 * 1024 && with_bm.total > budget_two))
         ctx->fs_bm_in_smem = 0;
-    FsLayout L = fs_layout(n, maxc, ctx->fs_bm_in_smem ? ctx->fs_bm_words : 0);
+    FsLayout L = fs_layout(n, maxc, ctx->fs_bm_in_smem ? ctx->fs_bm_words : 0, warps);
     while (L.total > ctx->max_smem_optin && maxc > 64) {
         maxc /= 2;
-        L = fs_layout(n, maxc, ctx->fs_bm_in_smem ? ctx->fs_bm_words : 0);
+        L = fs_layout(n, maxc, ctx->fs_bm_in_smem ? ctx->fs_bm_words : 0, warps);
     }
     if (L.total > ctx->max_smem_optin) return fail(ctx, CMB_ERR_LIMIT, "system does not fit the fused kernel");
     ctx->fs_maxc = maxc;
     ctx->fs_smem = L.total;
-    CK(cudaFuncSetAttribute(k_frames_small<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-    CK(cudaFuncSetAttribute(k_frames_small<FS_ROLES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-    CK(cudaFuncSetAttribute(k_frames_small<FS_EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-    CK(cudaFuncSetAttribute(k_frames_small<FS_EMIT | FS_ROLES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-    CK(cudaFuncSetAttribute(k_frames_small<FS_BOUNDARY | FS_ROLES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-    CK(cudaFuncSetAttribute(k_frames_small<FS_COUNT | FS_ROLES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    ctx->fs_threads = warps * 32;
     int nb = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_frames_small<0>, FS_THREADS, (size_t)L.total));
+    if (warps == 16) {
+        int rc = fs_prepare<512>(ctx, L.total, &nb);
+        if (rc != CMB_OK) return rc;
+    } else {
+        int rc = fs_prepare<1024>(ctx, L.total, &nb);
+        if (rc != CMB_OK) return rc;
+    }
     if (nb < 1) return fail(ctx, CMB_ERR_LIMIT, "fused kernel cannot be resident (smem %d)", L.total);
     ctx->fs_ctas_per_sm = nb;
     return CMB_OK;
@@ -377,6 +407,27 @@ struct FrameJob {
     float4* boundary; long long boundary_cap; int boundary_ulps;
 };
 
+// the fused-kernel variant a job asks for
+template <int THREADS>
+static void fs_launch(const cmb_ctx* ctx, const FrameJob& job, const FrameParams& p, unsigned g, size_t sm,
+                      cudaStream_t stream)
+{
+    const bool emit = job.atom_keys != nullptr || job.res_keys != nullptr;
+    if (job.boundary_ulps > 0)
+        k_frames_small<FS_BOUNDARY | FS_ROLES, THREADS><<<g, THREADS, sm, stream>>>(p);
+    else if (ctx->count_tests && !emit)
+        k_frames_small<FS_COUNT | FS_ROLES, THREADS><<<g, THREADS, sm, stream>>>(p);
+    else if (emit && ctx->all_roles)
+        k_frames_small<FS_EMIT, THREADS><<<g, THREADS, sm, stream>>>(p);
+    else if (emit)
+        k_frames_small<FS_EMIT | FS_ROLES, THREADS><<<g, THREADS, sm, stream>>>(p);
+    else if (ctx->all_roles)
+        k_frames_small<0, THREADS><<<g, THREADS, sm, stream>>>(p);
+    else
+        k_frames_small<FS_ROLES, THREADS><<<g, THREADS, sm, stream>>>(p);
+}
+
+
 static int launch_frames(cmb_ctx* ctx, const FrameJob& job, int slot, cudaStream_t stream)
 {
     if (!ctx->have_system) return fail(ctx, CMB_ERR_STATE, "cmb_set_system has not been called");
@@ -415,21 +466,10 @@ static int launch_frames(cmb_ctx* ctx, const FrameJob& job, int slot, cudaStream
             if (rc) return rc;
             p.g_bitmap = ctx->d_bitmap[slot];
         }
-        const bool emit = job.atom_keys != nullptr || job.res_keys != nullptr;
         const unsigned g = (unsigned)grid;
         const size_t sm = (size_t)ctx->fs_smem;
-        if (job.boundary_ulps > 0)
-            k_frames_small<FS_BOUNDARY | FS_ROLES><<<g, FS_THREADS, sm, stream>>>(p);
-        else if (ctx->count_tests && !emit)
-            k_frames_small<FS_COUNT | FS_ROLES><<<g, FS_THREADS, sm, stream>>>(p);
-        else if (emit && ctx->all_roles)
-            k_frames_small<FS_EMIT><<<g, FS_THREADS, sm, stream>>>(p);
-        else if (emit)
-            k_frames_small<FS_EMIT | FS_ROLES><<<g, FS_THREADS, sm, stream>>>(p);
-        else if (ctx->all_roles)
-            k_frames_small<0><<<g, FS_THREADS, sm, stream>>>(p);
-        else
-            k_frames_small<FS_ROLES><<<g, FS_THREADS, sm, stream>>>(p);
+        if (ctx->fs_threads == 1024) fs_launch<1024>(ctx, job, p, g, sm, stream);
+        else fs_launch<512>(ctx, job, p, g, sm, stream);
         CK(cudaGetLastError());
         ctx->stats["kernel_launches"] += 1;
         return CMB_OK;

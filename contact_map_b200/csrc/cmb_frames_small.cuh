@@ -132,7 +132,7 @@ struct FsLayout {
 
 __host__ __device__ inline int fs_align(int x, int a) { return (x + a - 1) / a * a; }
 
-__host__ __device__ inline FsLayout fs_layout(int n, int maxc, int bm_words_smem)
+__host__ __device__ inline FsLayout fs_layout(int n, int maxc, int bm_words_smem, int warps = FS_WARPS)
 {
     FsLayout L;
     int off = FS_HEADER_BYTES;
@@ -149,9 +149,9 @@ __host__ __device__ inline FsLayout fs_layout(int n, int maxc, int bm_words_smem
     L.bm_off = off;
     off += fs_align(4 * bm_words_smem, 128);
     L.cand_off = off;
-    off += FS_WARPS * FS_CAND * 2;
+    off += warps * FS_CAND * 2;
     L.hitq_off = off;
-    off += FS_WARPS * FS_QCAP * 8;
+    off += warps * FS_QCAP * 8;
     L.total = off;
     return L;
 }
@@ -251,14 +251,18 @@ struct BitmapSink {
 #define FS_MIN_CTAS 2
 #endif
 
-template <int FLAGS>
-__global__ void __launch_bounds__(FS_THREADS, FS_MIN_CTAS) k_frames_small(const FrameParams p)
+// THREADS = 512: two CTAs per SM when the system's arrays leave room for that (<= ~2 800 atoms);
+// THREADS = 1024: one CTA per SM with the same number of warps for the systems that do not
+template <int FLAGS, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS > 512 ? 1 : FS_MIN_CTAS) k_frames_small(const FrameParams p)
 {
+    // shadow the namespace-level defaults with this instantiation's values
+    constexpr int FS_THREADS = THREADS, FS_WARPS = THREADS / 32, FS_APT = FS_MAX_ATOMS / THREADS;
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int n = p.n;
-    const FsLayout L = fs_layout(n, p.maxc, p.bm_in_smem ? p.bm_words : 0);
+    const FsLayout L = fs_layout(n, p.maxc, p.bm_in_smem ? p.bm_words : 0, FS_WARPS);
 
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem);
     int* task_counter = reinterpret_cast<int*>(smem + 8);

@@ -21,6 +21,10 @@ CASES = [
     (1500, "ortho", 0.45, 2, 3, 1.0, 1.0),
     (10, "ortho", 0.45, 2, 5, 1.0, 1.0),
     (3, "none", 0.45, 0, 2, 1.0, 1.0),
+    # too large for two CTAs per SM: the 1024-thread instantiation of the fused kernel
+    (3500, "triclinic", 0.45, 2, 2, 1.0, 1.0),
+    (4100, "none", 0.50, 1, 2, 0.6, 0.8),
+    (6144, "ortho", 0.45, 2, 2, 1.0, 1.0),
 ]
 
 
