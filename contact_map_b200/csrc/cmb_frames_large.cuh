@@ -60,7 +60,7 @@ struct LargeScratch {
     long long batch_frames = 0;
     int batch_atoms = 0;
     size_t batch_bm_words = 0;
-    unsigned int* d_bitmaps = nullptr;   // [batch_frames][R_c^2 / 32] per-frame residue-pair bitmaps
+    unsigned int* d_bitmaps[2] = {nullptr, nullptr};   // per set: [batch_frames][R_c^2 / 32] per-frame residue-pair bitmaps
     cudaStream_t aux_batch = nullptr;
     cudaEvent_t entry_batch = nullptr;
     unsigned int* d_stamp = nullptr;
@@ -86,7 +86,7 @@ inline void large_scratch_free(LargeScratch& S)
         if (B.binned) cudaEventDestroy(B.binned);
         if (B.paired) cudaEventDestroy(B.paired);
     }
-    cudaFree(S.d_bitmaps);
+    cudaFree(S.d_bitmaps[0]); cudaFree(S.d_bitmaps[1]);
     if (S.aux_batch) cudaStreamDestroy(S.aux_batch);
     if (S.entry_batch) cudaEventDestroy(S.entry_batch);
     cudaFree(S.d_stamp);
@@ -654,7 +654,7 @@ inline PairParams large_pair_params(const LargeJob& job, const float* x, const f
 #define LG_BATCH_ATOMS_PER_CTA 8192
 #endif
 constexpr int LG_BATCH_MAXC = 1 << 16;                  // cell capacity of one batch slice
-constexpr size_t LG_BATCH_BYTES = (size_t)1024 << 20;   // scratch budget of the batched mode
+constexpr size_t LG_BATCH_BYTES = (size_t)2048 << 20;   // scratch budget of the batched mode
 constexpr int LG_BATCH_MAX_ATOMS = 1 << 18;             // mode 1: above this the one-frame-at-a-time mode is used
 
 inline int large_run_batched(const LargeJob& job, LargeScratch& S, int sm_count, cudaStream_t stream,
@@ -665,7 +665,7 @@ inline int large_run_batched(const LargeJob& job, LargeScratch& S, int sm_count,
     if (job.batch_mode == 0 || job.atom_log2 > 0 || job.res_log2 > 0 || job.n_frames < 2) return 1;
     if (job.batch_mode == 1 && n > LG_BATCH_MAX_ATOMS) return 1;     // big frames fill the GPU on their own
     const size_t bm_words = want_res ? ((size_t)job.n_res_c * (size_t)job.n_res_c + 31) / 32 : 0;
-    const size_t per_frame = 2 * ((size_t)n * 44 + (size_t)LG_BATCH_MAXC * 12 + 64 + sizeof(GridS)) + bm_words * 4;
+    const size_t per_frame = 2 * ((size_t)n * 44 + (size_t)LG_BATCH_MAXC * 12 + 64 + sizeof(GridS) + bm_words * 4);
     const int total_ctas = sm_count * BatchSink::MIN_CTAS;
     // as many frames per launch as the scratch budget allows, at least one CTA (8 warps) per
     // LG_BATCH_ATOMS_PER_CTA atoms of a frame (measured: fewer, longer-lived CTAs per frame win),
@@ -676,8 +676,8 @@ inline int large_run_batched(const LargeJob& job, LargeScratch& S, int sm_count,
     if (frames < 2) return 1;
     const int ctas = std::max<int>(ctas_min, (int)(total_ctas / frames));
     if (S.batch_frames < frames || S.batch_atoms < n || S.batch_bm_words < bm_words) {
-        cudaFree(S.d_bitmaps);
-        S.d_bitmaps = nullptr;
+        cudaFree(S.d_bitmaps[0]); cudaFree(S.d_bitmaps[1]);
+        S.d_bitmaps[0] = S.d_bitmaps[1] = nullptr;
         S.batch_frames = 0;
         const size_t F = (size_t)frames;
         for (LargeBins& B : S.batch) {
@@ -698,7 +698,7 @@ inline int large_run_batched(const LargeJob& job, LargeScratch& S, int sm_count,
             if (!B.paired) LG_CK(cudaEventCreateWithFlags(&B.paired, cudaEventDisableTiming));
             B.paired_recorded = false;
         }
-        if (bm_words) LG_CK(cudaMalloc(&S.d_bitmaps, sizeof(unsigned int) * F * bm_words));
+        for (int k = 0; k < 2 && bm_words; k++) LG_CK(cudaMalloc(&S.d_bitmaps[k], sizeof(unsigned int) * F * bm_words));
         S.batch_frames = frames; S.batch_atoms = n; S.batch_bm_words = bm_words;
     }
     if (!S.aux_batch) {
@@ -706,8 +706,8 @@ inline int large_run_batched(const LargeJob& job, LargeScratch& S, int sm_count,
         LG_CK(cudaStreamCreateWithFlags(&S.aux_batch, cudaStreamNonBlocking));
     }
     const int atom_blocks = std::min((n + 255) / 256, sm_count * 8);
-    // binning of batch k + 1 (aux stream, other buffer set) under the pair kernel of batch k; the
-    // bitmaps are only touched on the caller's stream
+    // binning of batch k + 1 and the clearing of its bitmaps (aux stream, other buffer set) run
+    // under the pair kernel of batch k
     LG_CK(cudaEventRecord(S.entry_batch, stream));         // the frames may still be in flight (H2D)
     LG_CK(cudaStreamWaitEvent(S.aux_batch, S.entry_batch, 0));
     int kb = 0;
@@ -721,17 +721,18 @@ inline int large_run_batched(const LargeJob& job, LargeScratch& S, int sm_count,
         lb.grid = B.d_grid; lb.cellcnt = B.d_cellcnt; lb.cellptr = B.d_cellptr; lb.occ = B.d_occ; lb.misc = B.d_misc;
         lb.wrapped = B.d_wrapped; lb.atomrank = B.d_atomrank; lb.sorted = B.d_sorted; lb.sorted_kr = B.d_sorted_kr;
         if (B.paired_recorded) LG_CK(cudaStreamWaitEvent(S.aux_batch, B.paired, 0));   // the set is free again
+        unsigned int* bitmaps = S.d_bitmaps[kb & 1];
+        if (bm_words) LG_CK(cudaMemsetAsync(bitmaps, 0, sizeof(unsigned int) * (size_t)nf * bm_words, S.aux_batch));
         kl_prepare<<<dim3(1, nf), LG_BIN_THREADS, 0, S.aux_batch>>>(lb, job.cutoff);
         kl_bin<<<dim3(atom_blocks, nf), 256, 0, S.aux_batch>>>(lb);
         kl_scan<<<dim3(1, nf), LG_BIN_THREADS, 0, S.aux_batch>>>(lb);
         kl_scatter<<<dim3(atom_blocks, nf), 256, 0, S.aux_batch>>>(lb, job.meta);
         LG_CK(cudaEventRecord(B.binned, S.aux_batch));
-        if (bm_words) LG_CK(cudaMemsetAsync(S.d_bitmaps, 0, sizeof(unsigned int) * (size_t)nf * bm_words, stream));
         LG_CK(cudaStreamWaitEvent(stream, B.binned, 0));
         const PairParams pp = large_pair_params(job, lb.xyz, lb.box, job.frame0 + f0);
         BatchSink sink;
         sink.atom_table = job.atom_table; sink.res_table = job.res_table;
-        sink.bitmap = want_res ? S.d_bitmaps : nullptr; sink.bm_words = (long long)bm_words;
+        sink.bitmap = want_res ? bitmaps : nullptr; sink.bm_words = (long long)bm_words;
         sink.res_keys = job.res_keys; sink.res_cap = job.res_cap; sink.counters = job.counters;
         sink.n = (unsigned)n; sink.n_res_c = (unsigned)job.n_res_c; sink.frame_id = job.frame0 + f0;
         sink.rcache = nullptr; sink.ra = sink.rb = 0;
