@@ -48,6 +48,8 @@ def test_random_configuration_matches_oracle(engine, seed):
     ref_atom, ref_res = clib.accumulate_dense(xyz, box, cutoff, res, chain, role, n_ign,
                                               system.topology.n_residues)
     engine.set_option("force_path", force)
+    # global-memory cell path: alternate between its two schedules (one frame at a time / batched)
+    engine.set_option("large_batch", 0 if (seed // 4) % 2 else 2)
     try:
         engine.set_system(res, chain, role, cutoff, n_ign)
         atom_t, res_t = engine.new_tables()
@@ -65,3 +67,4 @@ def test_random_configuration_matches_oracle(engine, seed):
         assert len(akeys) == int(ref_atom.sum()) and len(rkeys) == int(ref_res.sum())
     finally:
         engine.set_option("force_path", -1)
+        engine.set_option("large_batch", 1)
