@@ -117,6 +117,35 @@ def test_objects_without_gpu():
     assert rt == m2
 
 
+def test_query_haystack_containers_follow_the_reference():
+    """query / haystack arrive in any order, with duplicates, as lists, sets, ranges or arrays; the
+    containers the reference exposes (contact_map.py:132-139,409-422) come out the same whichever."""
+    case = goldens.load("pdb_c0075_n0")
+    top = goldens.trajectory(case).topology
+    import warnings
+    for query, haystack in (([7, 2, 2, 5], {9, 0, 4}), (np.array([5, 7, 2]), range(0, 10, 4)),
+                            ((q for q in (2, 5, 7)), [4, 0, 9, 9])):
+        if isinstance(haystack, range):
+            haystack = [0, 4, 9]                                  # same set as the other spellings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            m = cm.ContactFrequency.from_contacts({}, {}, n_frames=1, topology=top, query=query,
+                                                  haystack=haystack, cutoff=0.075, n_neighbors_ignored=0)
+        assert m._query == {2, 5, 7} and m._haystack == {0, 4, 9}
+        assert sorted(m.query) == [2, 5, 7] and sorted(m.haystack) == [0, 4, 9]
+        assert m._all_atoms == (0, 2, 4, 5, 7, 9) and m.all_atoms == [0, 2, 4, 5, 7, 9]
+        assert all(type(a) is int for a in m._all_atoms)
+        assert m.query_range == (2, 8) and m.haystack_range == (0, 10)
+        assert m._query_res_idx == {1, 2, 3} and m._haystack_res_idx == {0, 2, 4}
+        assert m._all_residues == {0, 1, 2, 3, 4}
+        assert m.use_atom_slice is True
+    # defaults: both None share one selection
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        d = cm.ContactFrequency.from_contacts({}, {}, n_frames=1, topology=top, cutoff=0.075, n_neighbors_ignored=0)
+    assert d._query == d._haystack == set(range(10)) and d.use_atom_slice is False
+
+
 def test_product_fails_loudly_without_gpu():
     import torch
     if torch.cuda.is_available():
