@@ -150,14 +150,16 @@ constexpr int CT_PAIR_MAX_OWN = CT_PAIR_MAX_OWN_CFG;
 // =================================================================================
 // Pair phase shared by both paths.
 //
-// Screening and adjudication are split (DESIGN.md 4.1):
+// Screening and adjudication are split (DESIGN.md 4.0):
 //   * the frame's atoms are cell-sorted into `sorted[pos] = {wx, wy, wz, bits}`: the position
 //     WRAPPED into the primary cell image (fp64 in the binning pass, rounded to fp32) and
-//     `bits = atom index | role << 30`;
-//   * one warp per occupied cell; every candidate pair of the half-shell stencil costs 3 FADD +
-//     3 FFMA + 1 SHF: t = dx*dx + dy*dy + dz*dz - c2_hi on the wrapped coordinates (+ the lattice
-//     shift of the candidate's stencil cell), whose sign bit is funnel-shifted into a per-lane
-//     bit mask (one bit per own atom of the cell, one mask per register-resident candidate);
+//     `bits` = atom index, role and (fused kernel) exclusion key, layout known to Traits;
+//   * one warp per task (an occupied cell, or two sparse x-adjacent cells); every candidate pair
+//     of the half-shell stencil costs 10 issue slots: t = dx*dx + dy*dy + dz*dz - c2_hi on the
+//     wrapped coordinates (+ the lattice shift of the candidate's stencil cell) as 3 FADD +
+//     3 FFMA, the residue exclusion q = n_ignored + 0.5 - |ekey_i - ekey_j| as 2 FADD, and the
+//     sign of max(t, q) funnel-shifted into a per-lane bit mask (one bit per own atom of the
+//     task, one mask per register-resident candidate);
 //   * after the own-atom loop the non-zero masks are pushed to a per-warp shared-memory ring
 //     and accounted 32 pairs at a time with all lanes busy: d2a <= c2_lo is a certain contact,
 //     anything else that passed the screen is AMBIGUOUS and is decided by MDTraj's exact
