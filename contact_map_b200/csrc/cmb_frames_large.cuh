@@ -1,19 +1,22 @@
 // cmb_frames_large.cuh -- global-memory cell path for systems that do not fit the
-// fused shared-memory kernel (n_used > 6144, e.g. the 100k-atom solvated system).
+// fused shared-memory kernel (n_used > 6144, up to the 100k-atom solvated system and beyond).
 //
 // Same pair-phase code as the fused kernel (cmb_cells.cuh::ct_pair_phase, LargeTraits); the
 // cell arrays and the cell-sorted float4 copy of the frame live in HBM/L2 instead of
-// shared memory, and the whole GPU works on ONE frame at a time:
+// shared memory, one kernel per stage, frame `blockIdx.y` of a batch in slice blockIdx.y of
+// every scratch array (LargeBatch):
 //   kl_prepare  grid of the frame (+ bounding box for open boundaries), zero counters
 //   kl_bin      cell id + rank + wrapped position per atom (L2 atomics on the cell histogram),
 //               max |coordinate| of the frame
-//   kl_scan     exclusive scan over cells + occupied-cell list (single CTA)
+//   kl_scan     exclusive scan over cells + occupied-cell list (one CTA per frame)
 //   kl_scatter  cell-sorted float4 {wrapped x, y, z, atom index | role << 30}
-//   kl_pairs    persistent CTAs, one warp per occupied cell (global task counter)
-// Per-frame residue de-duplication (contact_map.py:601-607,740) uses a frame-stamp
-// table instead of a bitmap: frames are processed in stream order, so
-// atomicMax(stamp[slot], seq) < seq identifies the first hit of a residue pair in
-// the current frame.
+//   kl_pairs    persistent CTAs, one warp per task (one task counter per frame)
+// Two schedules (large_run): BATCHED -- many frames per launch, per-frame residue-pair bitmaps
+// in global memory (BatchSink), binning of the next batch on an auxiliary stream; and ONE FRAME
+// AT A TIME -- the whole GPU on a frame, per-frame residue de-duplication
+// (contact_map.py:601-607,740) by a frame-stamp table: frames are processed in stream order, so
+// atomicMax(stamp[slot], seq) < seq identifies the first hit of a residue pair in the current
+// frame (StampSink; also the schedule of the hashed count tables).
 #pragma once
 #include <string>
 

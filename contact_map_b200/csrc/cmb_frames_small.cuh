@@ -7,7 +7,8 @@
 //   Counter.update / Counter += of ContactFrequency        contact_map.py:739-740
 //   per-frame pair sets of _build_contacts                 contact_trajectory.py:32-44
 //
-// Persistent CTAs (grid = SMs x resident CTAs), frames dealt round-robin:
+// Persistent CTAs (grid = SMs x resident CTAs: two of 512 threads, or one of 1024 threads when
+// the system's arrays do not leave room for two), frames dealt round-robin:
 //   1. the frame's fp32 xyz (12*n bytes, contiguous in HBM) is pulled into shared
 //      memory with ONE 1-D TMA bulk copy (cp.async.bulk -> UBLKCP) signalled on an
 //      mbarrier; the copy of the NEXT frame is issued as soon as the scatter pass
