@@ -17,12 +17,18 @@ bit-reproducible generator).  `e2e` goes through the public API
 copies, kernels, reduce, export and the device->host read of the sparse result are all inside
 the timed region.
 """
+import os
+import sys
+
+if "--impl" in sys.argv and "reference" in sys.argv:
+    # the reference arm runs one oracle process per core: the OpenMP team size has to be fixed
+    # BEFORE anything loads libgomp (numpy / torch / the oracle library read it at load time)
+    os.environ["OMP_NUM_THREADS"] = "1"
+
 import argparse
 import json
-import os
 import statistics
 import subprocess
-import sys
 import threading
 import time
 import warnings
@@ -199,13 +205,27 @@ def cpu_reference_rate(system, n_frames, n_workers):
         dt = time.perf_counter() - t0
     else:
         import multiprocessing as mp
-        os.environ["OMP_NUM_THREADS"] = "1"
-        with mp.get_context("fork").Pool(n_workers) as pool:
-            pool.map(abs, range(n_workers))      # spin the workers up outside the timed region
+        with mp.get_context("fork").Pool(n_workers, initializer=_worker_init) as pool:
+            # spin the workers up outside the timed region and record the OpenMP team size each
+            # of them really runs the oracle with
+            observed = pool.map(_worker_threads, range(n_workers))
+            cpu_reference_rate.worker_threads = max(observed)
             t0 = time.perf_counter()
             atoms, residues = refpath.chunked_contact_frequency(*args, n_workers=n_workers, pool=pool)
             dt = time.perf_counter() - t0
     return n_frames / dt, dt, len(atoms), len(residues)
+
+
+def _worker_init():
+    """One OpenMP thread per worker process (one worker per core): omp_set_num_threads through
+    the oracle library, which works whatever OMP_NUM_THREADS said when libgomp was loaded."""
+    from oracle import clib
+    clib.set_threads(1)
+
+
+def _worker_threads(_):
+    from oracle import clib
+    return clib.max_threads()
 
 
 def run_reference(args):
@@ -216,6 +236,7 @@ def run_reference(args):
         return 0
     from contact_map_b200 import synth
     from oracle import clib
+    clib.lib()                       # build / load once in the parent, before the workers fork
     system = synth.kras_like()
     cores = len(os.sched_getaffinity(0))
     workers = max(1, cores)
@@ -240,11 +261,13 @@ def run_reference(args):
             "sample": "%d frames of S1 per step; reference Python set/Counter algorithm restated "
                       "(oracle/refpath.py) over the C restatement of MDTraj's neighbour list, run as the "
                       "Dask-equivalent runner: default_slices -> %d worker processes -> Counter reduce "
-                      "(oracle C lib OpenMP threads per worker: 1)" % (frames, workers),
+                      "(oracle C lib OpenMP threads per worker, observed inside the workers: %d)"
+                      % (frames, workers, getattr(cpu_reference_rate, "worker_threads", 0)),
         },
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "oracle_threads_available": clib.max_threads(),
+        "oracle_threads_per_worker": getattr(cpu_reference_rate, "worker_threads", None),
+        "oracle_threads_parent": clib.max_threads(),
     }
     print(json.dumps(line))
     return 0
@@ -421,11 +444,11 @@ def run_ours(args):
         traffic = None if per_frame is None else per_frame * F    # ncu capture, scaled to this launch
     sm_count = engine.get_stat("sm_count")
     sm_mhz = clocks.get("sm_mhz") or 1965.0
-    # FP32 view: canonical candidate pairs x 23 lane-ops of the reference arithmetic
-    # (orthorhombic: 18 FP32 + 3 XU + exclusion/compare) per pair, against the FP32 pipe peak.  The
+    # FP32 view: canonical candidate pairs x 21 lane-ops of the reference arithmetic
+    # (orthorhombic: 18 FP32 + 3 XU per pair; triclinic would be 24 + 3), against the FP32 pipe peak.  The
     # kernel itself spends 10 issue slots per screened pair (3 FADD + 3 FFMA + 2 FADD + FMNMX + SHF)
     # and runs the reference arithmetic only on the pairs the screening cannot decide.
-    fp32_lane_ops = pair_tests * 23.0 / (kernel_ms / 1e3)
+    fp32_lane_ops = pair_tests * 21.0 / (kernel_ms / 1e3)
     fp32_peak = sm_count * 128 * sm_mhz * 1e6
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -435,11 +458,11 @@ def run_ours(args):
                 "see fp32_pipe (SURVEY 8d's lower ceiling)",
         "fp32_pipe": {"candidate_pairs_per_launch": pair_tests,
                       "screened_pairs_per_launch": counts["screened"],
-                      "reference_lane_ops_per_pair": 23, "kernel_issue_slots_per_screened_pair": 10,
+                      "reference_lane_ops_per_pair": 21, "kernel_issue_slots_per_screened_pair": 10,
                       "achieved_lane_ops_per_s": fp32_lane_ops,
                       "peak_lane_ops_per_s": fp32_peak, "frac": fp32_lane_ops / fp32_peak,
                       "definition": "frames/s x canonical candidate pairs (cutoff-sized cells, 27-cell half "
-                                    "shell) x 23 lane-ops of the reference arithmetic / FP32 pipe peak; the "
+                                    "shell) x 21 lane-ops (18 FP32 + 3 XU, SURVEY 8d) of the reference arithmetic / FP32 pipe peak; the "
                                     "kernel screens with FMA arithmetic and adjudicates only ambiguous pairs "
                                     "with the reference arithmetic, so frac is work-equivalent throughput, "
                                     "not pipe utilisation",

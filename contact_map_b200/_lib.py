@@ -29,6 +29,7 @@ EXPORTS = [
     "cmb_boundary_pairs", "cmb_set_option", "cmb_get_stat", "cmb_gather_atoms", "cmb_min_dist",
     "cmb_nearest", "cmb_synth_frames", "cmb_set_table_mode", "cmb_hash_stats", "cmb_export_hashed",
     "cmb_hash_rehash", "cmb_hash_overflow_buffer", "cmb_hash_add", "cmb_export_sorted", "cmb_group_contacts",
+    "cmb_min_dist_pairs",
 ]
 
 
@@ -135,6 +136,8 @@ def lib():
     L.cmb_gather_atoms.argtypes = [vp, vp, i64, i32, vp, i32, vp, vp]
     L.cmb_min_dist.restype = i32
     L.cmb_min_dist.argtypes = [vp, vp, vp, i64, i32, vp, i32, vp, i32, i32, vp, vp, vp]
+    L.cmb_min_dist_pairs.restype = i32
+    L.cmb_min_dist_pairs.argtypes = [vp, vp, vp, i64, i32, vp, i64, i32, vp, vp, vp]
     L.cmb_nearest.restype = i32
     L.cmb_nearest.argtypes = [vp, vp, vp, i32, dbl, i32, i32, vp, vp, vp, vp, vp, vp]
     L.cmb_synth_frames.restype = i32

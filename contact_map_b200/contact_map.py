@@ -14,6 +14,7 @@ There is no CPU implementation in this package: without a CUDA device the constr
 raise ``engine.EngineError``.
 """
 import collections
+import io
 import json
 import pickle
 import warnings
@@ -344,6 +345,64 @@ class ContactObject(object):
         return (getattr(self, "_atom_counter", None) is not None
                 or getattr(self, "_atom_table", None) is not None)
 
+    # -- dict / JSON round trip: the reference's format (contact_map.py:202-333), so that files
+    #    written by either package load in the other --------------------------------------------
+    def to_dict(self):
+        return {
+            "topology": self._serialize_topology(self.topology),
+            "cutoff": self._cutoff,
+            "query": [int(v) for v in self._query],
+            "haystack": [int(v) for v in self._haystack],
+            "query_res_idx": [int(v) for v in self._query_res_idx],
+            "haystack_res_idx": [int(v) for v in self._haystack_res_idx],
+            "all_atoms": tuple(int(v) for v in self._all_atoms),
+            "all_residues": tuple(int(v) for v in self._all_residues),
+            "n_neighbors_ignored": self._n_neighbors_ignored,
+            "atom_contacts": self._serialize_contact_counter(self._atom_contacts),
+            "residue_contacts": self._serialize_contact_counter(self._residue_contacts),
+            "use_atom_slice": self._use_atom_slice,
+        }
+
+    @classmethod
+    def from_dict(cls, dct, topology=None):
+        """Rebuild from ``to_dict`` output of this package OR of the reference.  ``topology``
+        overrides the serialised one (kept for callers of the earlier two-argument form)."""
+        if topology is None:
+            topology = cls._deserialize_topology(dct["topology"])
+        obj = cls.__new__(cls)
+        obj.indexer = None
+        ContactObject.__init__(obj, topology, [int(v) for v in dct["query"]],
+                               [int(v) for v in dct["haystack"]], dct["cutoff"],
+                               dct["n_neighbors_ignored"])
+        if dct.get("use_atom_slice") is not None:
+            obj._use_atom_slice = dct["use_atom_slice"]
+        obj._set_counts(cls._deserialize_contact_counter(dct["atom_contacts"]),
+                        cls._deserialize_contact_counter(dct["residue_contacts"]))
+        if "n_frames" in dct:
+            obj._n_frames = dct["n_frames"]
+        return obj
+
+    def to_json(self):
+        return json.dumps(self.to_dict())
+
+    @classmethod
+    def from_json(cls, json_string, topology=None):
+        return cls.from_dict(json.loads(json_string), topology)
+
+    @staticmethod
+    def _serialize_topology(topology):
+        """JSON of (atom table, bonds) -- reference contact_map.py:278-283."""
+        table, bonds = topology.to_dataframe()
+        return json.dumps((table.to_json(), np.asarray(bonds).tolist()))
+
+    @staticmethod
+    def _deserialize_topology(topology_json):
+        """Reference contact_map.py:269-276, into this package's array-backed Topology."""
+        import pandas as pd
+        from .trajectory import Topology
+        table, bonds = json.loads(topology_json)
+        return Topology.from_dataframe(pd.read_json(io.StringIO(table)), np.array(bonds))
+
     @staticmethod
     def _serialize_contact_counter(counter):
         return json.dumps({json.dumps(sorted(int(v) for v in key)): value
@@ -441,6 +500,11 @@ def _used_coordinates(xyz, box, used, n_total, engine, keep_full_host=False):
     return xyz, box, False
 
 
+def _table_kind(table):
+    """'hashed' or 'dense': which count-table layout a build used (diagnostics / tests)."""
+    return "hashed" if hasattr(table, "slots") else "dense"
+
+
 def _tables_to_pairs(engine, atom_table, res_table, used):
     """Sparse export of the device tables -> (atom PairTable, residue PairTable) in REAL indices."""
     n = engine.n_used
@@ -507,13 +571,10 @@ class ContactFrequency(ContactObject):
                 engine.accumulate_host_gather(xyz, used, box, atom_table, res_table)
             else:
                 engine.accumulate_host(xyz, box, atom_table, res_table)
-        self._device_tables = (atom_table, res_table, used)
+        # the sparse export is the result: the device tables (29 MB at 2.7k atoms, 40 GB at 100k)
+        # are dropped here, only their kind is remembered
+        self._table_kind = _table_kind(atom_table)
         return _tables_to_pairs(engine, atom_table, res_table, used)
-
-    def __getstate__(self):
-        state = super(ContactFrequency, self).__getstate__()
-        state.pop("_device_tables", None)
-        return state
 
     def __hash__(self):
         return hash((super(ContactFrequency, self).__hash__(),
@@ -536,7 +597,6 @@ class ContactFrequency(ContactObject):
         residues = self._table_of("residue").combine(other._table_of("residue"), sign)
         self._set_counts(atoms, residues)
         self._n_frames += sign * other._n_frames
-        self.__dict__.pop("_device_tables", None)
 
     def add_contact_frequency(self, other):
         """Add the counts of ``other`` (the reduce operator, reference :751-763)."""
@@ -559,31 +619,11 @@ class ContactFrequency(ContactObject):
                             self.query_residue_range, self.haystack_residue_range,
                             self.topology.n_residues)
 
-    # -- JSON round trip (reference :202-333), host-side ------------------------------------
     def to_dict(self):
-        return {
-            "cutoff": self._cutoff,
-            "query": sorted(int(v) for v in self._query),
-            "haystack": sorted(int(v) for v in self._haystack),
-            "n_neighbors_ignored": self._n_neighbors_ignored,
-            "atom_contacts": self._serialize_contact_counter(self._atom_contacts),
-            "residue_contacts": self._serialize_contact_counter(self._residue_contacts),
-            "n_frames": self.n_frames,
-        }
-
-    def to_json(self):
-        return json.dumps(self.to_dict())
-
-    @classmethod
-    def from_dict(cls, dct, topology):
-        return cls.from_contacts(cls._deserialize_contact_counter(dct["atom_contacts"]),
-                                 cls._deserialize_contact_counter(dct["residue_contacts"]),
-                                 dct["n_frames"], topology, dct["query"], dct["haystack"],
-                                 dct["cutoff"], dct["n_neighbors_ignored"])
-
-    @classmethod
-    def from_json(cls, json_string, topology):
-        return cls.from_dict(json.loads(json_string), topology)
+        """Reference contact_map.py:712-715: the ContactObject keys plus ``n_frames``."""
+        dct = super(ContactFrequency, self).to_dict()
+        dct["n_frames"] = self.n_frames
+        return dct
 
 
 CONTACT_MAP_ERROR = (
@@ -706,6 +746,24 @@ class ContactDifference(ContactObject):
     @classmethod
     def from_contacts(cls, *args, **kwargs):
         raise NotImplementedError
+
+    def to_dict(self):
+        """Reference contact_map.py:838-851."""
+        return {"positive": self.positive.to_json(), "negative": self.negative.to_json(),
+                "positive_cls": self.positive.__class__.__name__,
+                "negative_cls": self.negative.__class__.__name__}
+
+    @classmethod
+    def from_dict(cls, dct):
+        """Reference contact_map.py:853-880."""
+        supported = {"ContactFrequency": ContactFrequency}
+
+        def rebuild(which):
+            name = dct[which + "_cls"]
+            if name not in supported:
+                raise RuntimeError("Can't rebuild class " + name)
+            return supported[name].from_json(dct[which])
+        return cls(rebuild("positive"), rebuild("negative"))
 
     @staticmethod
     def _filtered_difference(pos_count, neg_count, selection, object_f, max_size):

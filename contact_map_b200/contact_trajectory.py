@@ -25,6 +25,11 @@ except ImportError:  # pragma: no cover
 
 
 
+# layout of the 64-bit per-frame keys (cmb_frame_contacts): frame << 40 | lo << 20 | hi
+KEY_MAX_FRAMES = 1 << 24
+KEY_MAX_INDEX = 1 << 20
+
+
 class FrameCSR(object):
     """Per-frame unordered pairs: ``ptr[f]:ptr[f+1]`` indexes ``i``/``j`` (i < j, real indices)."""
 
@@ -36,11 +41,16 @@ class FrameCSR(object):
 
     @classmethod
     def from_keys(cls, n_frames, keys, index_map):
-        k = np.asarray(keys, dtype=np.uint64).view(np.int64)       # frame ids < 2^24: never negative
+        k = np.asarray(keys, dtype=np.uint64)                      # unsigned shifts: frame ids use bits 40..63
         index_map = np.asarray(index_map, dtype=np.int64)
-        frame = k >> 40
-        lo = index_map[(k >> 20) & 0xFFFFF]
-        hi = index_map[k & 0xFFFFF]
+        if int(n_frames) > KEY_MAX_FRAMES:
+            raise ValueError("per-frame keys hold 24-bit frame ids: at most %d frames per key stream"
+                             % KEY_MAX_FRAMES)
+        if index_map.shape[0] > KEY_MAX_INDEX:
+            raise ValueError("per-frame keys hold 20-bit indices: at most %d used atoms / residues" % KEY_MAX_INDEX)
+        frame = (k >> np.uint64(40)).astype(np.int64)
+        lo = index_map[((k >> np.uint64(20)) & np.uint64(0xFFFFF)).astype(np.int64)]
+        hi = index_map[(k & np.uint64(0xFFFFF)).astype(np.int64)]
         # keys hold lo < hi in compact numbering; an increasing map (sorted used atoms) keeps that
         if index_map.shape[0] > 1 and not bool(np.all(index_map[1:] > index_map[:-1])):
             lo, hi = np.minimum(lo, hi), np.maximum(lo, hi)
@@ -74,6 +84,9 @@ def _build_contacts(contact_object, trajectory, chunk_bytes=64 << 20):
     xyz, box = _split_trajectory(trajectory)
     xyz, box, on_device = _used_coordinates(xyz, box, used, contact_object.topology.n_atoms, engine)
     n_frames = xyz.shape[0]
+    if n_frames > KEY_MAX_FRAMES:
+        raise ValueError("ContactTrajectory handles at most %d frames per call (24-bit frame ids in "
+                         "the per-frame keys); split the trajectory and join the parts" % KEY_MAX_FRAMES)
     chunk = max(1, min(n_frames, chunk_bytes // max(1, used.shape[0] * 12), (1 << 24) - 1))
     atom_keys, res_keys = [], []
     for f0 in range(0, n_frames, chunk):
@@ -201,6 +214,27 @@ class ContactTrajectory(ContactObject, abc.Sequence):
         for other in others:
             maps.extend(list(other._contact_maps))
         return cls.from_contact_maps(maps)
+
+    def to_dict(self):
+        """Reference contact_trajectory.py:152-155."""
+        return {"contact_maps": [cmap.to_dict() for cmap in self._contact_maps]}
+
+    @classmethod
+    def from_dict(cls, dct):
+        """Reference contact_trajectory.py:157-162."""
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", PendingDeprecationWarning)
+            return cls.from_contact_maps([ContactFrequency.from_dict(cmap) for cmap in dct["contact_maps"]])
+
+    def to_json(self):
+        import json
+        return json.dumps(self.to_dict())
+
+    @classmethod
+    def from_json(cls, json_string):
+        import json
+        return cls.from_dict(json.loads(json_string))
 
     def contact_frequency(self):
         """ContactFrequency summed over all frames (reference :132-150); one reduce-by-key

@@ -1020,6 +1020,39 @@ extern "C" int cmb_min_dist(cmb_ctx* ctx, const float* d_xyz, const float* d_box
     return CMB_OK;
 }
 
+extern "C" int cmb_min_dist_pairs(cmb_ctx* ctx, const float* d_xyz, const float* d_box, int64_t n_frames,
+                                  int n_atoms, const int32_t* d_pairs, int64_t n_pairs, int orthogonal,
+                                  float* d_min, int64_t* d_arg, void* stream)
+{
+    if (!ctx) return CMB_ERR_ARG;
+    if (!d_xyz || !d_pairs || !d_min || !d_arg || n_pairs <= 0 || n_atoms <= 0)
+        return fail(ctx, CMB_ERR_ARG, "bad min_dist_pairs arguments");
+    if (n_frames <= 0) return CMB_OK;
+    CK(cudaSetDevice(ctx->device));
+    const long long n_chunks_ll = (n_pairs + MD_PCHUNK - 1) / MD_PCHUNK;
+    if (n_chunks_ll > 0x7fffffffll) return fail(ctx, CMB_ERR_LIMIT, "too many atom pairs");
+    const int n_chunks = (int)n_chunks_ll;
+    const int64_t fmax = 32768;   // gridDim.y limit is 65535
+    for (int64_t f0 = 0; f0 < n_frames; f0 += fmax) {
+        const int64_t nf = std::min<int64_t>(fmax, n_frames - f0);
+        const size_t need = (size_t)nf * n_chunks * (sizeof(float) + sizeof(long long)) + 256;
+        int rc = ensure_bytes(ctx, &ctx->d_tmp, &ctx->tmp_bytes, need);
+        if (rc) return rc;
+        long long* part_idx = (long long*)ctx->d_tmp;
+        float* part_d = (float*)((char*)ctx->d_tmp + (size_t)nf * n_chunks * sizeof(long long));
+        dim3 grid((unsigned)n_chunks, (unsigned)nf);
+        k_min_dist_pairs_partial<<<grid, MD_THREADS, 0, (cudaStream_t)stream>>>(
+            d_xyz + (size_t)f0 * n_atoms * 3, d_box ? d_box + (size_t)f0 * 9 : nullptr, n_atoms,
+            reinterpret_cast<const int2*>(d_pairs), n_pairs, orthogonal, part_d, part_idx);
+        CK(cudaGetLastError());
+        k_min_dist_final<<<(unsigned)((nf + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+            part_d, part_idx, n_chunks, nf, d_min + f0, (long long*)d_arg + f0);
+        CK(cudaGetLastError());
+        ctx->stats["kernel_launches"] += 2;
+    }
+    return CMB_OK;
+}
+
 extern "C" int cmb_nearest(cmb_ctx* ctx, const float* d_xyz_frame, const float* d_box9, int n_atoms,
                            double cutoff, int orthogonal, int excl_mode, const int32_t* d_atom_res,
                            const int64_t* d_excl_ptr, const int32_t* d_excl_idx, int32_t* d_nearest,

@@ -401,6 +401,51 @@ __global__ void __launch_bounds__(MD_THREADS) k_min_dist_partial(
     }
 }
 
+// MinimumDistanceCounter._compute_from_atom_pairs (min_dist.py:142-168) for an ARBITRARY pair
+// list: grid = (n_chunks, n_frames), chunk c owns pairs [c * MD_PCHUNK, (c + 1) * MD_PCHUNK);
+// partial[(f * n_chunks + chunk)] = best of that chunk, index = position in the pair list
+// (numpy argmin: first index among equal float32 distances).
+constexpr int MD_PCHUNK = MD_THREADS * 16;
+
+__global__ void __launch_bounds__(MD_THREADS) k_min_dist_pairs_partial(
+    const float* __restrict__ xyz, const float* __restrict__ box, int n_atoms,
+    const int2* __restrict__ pairs, long long n_pairs, int orthogonal,
+    float* __restrict__ part_d, long long* __restrict__ part_idx)
+{
+    __shared__ float red_d[MD_THREADS / 32];
+    __shared__ long long red_i[MD_THREADS / 32];
+    const long long f = blockIdx.y;
+    const float* x = xyz + (size_t)f * (size_t)n_atoms * 3;
+    const DistBox D = make_distbox(box ? box + (size_t)f * 9 : nullptr, orthogonal);
+    float best = __int_as_float(0x7f800000);
+    long long bidx = 0x7fffffffffffffffll;
+    const long long p0 = (long long)blockIdx.x * MD_PCHUNK;
+    const long long p1 = min(n_pairs, p0 + (long long)MD_PCHUNK);
+    for (long long p = p0 + threadIdx.x; p < p1; p += MD_THREADS) {
+        const int2 pr = __ldg(&pairs[p]);
+        const float* a = x + (size_t)pr.x * 3;
+        const float* b = x + (size_t)pr.y * 3;
+        // compute_distances(pair = (i, j)): r = p_j - p_i
+        const float d = __fsqrt_rn(dist2_pair(__ldg(a), __ldg(a + 1), __ldg(a + 2), __ldg(b), __ldg(b + 1),
+                                              __ldg(b + 2), D));
+        if (md_better(d, p, best, bidx)) { best = d; bidx = p; }
+    }
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const float od = __shfl_xor_sync(0xffffffffu, best, s);
+        const long long oi = __shfl_xor_sync(0xffffffffu, bidx, s);
+        if (md_better(od, oi, best, bidx)) { best = od; bidx = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { red_d[threadIdx.x >> 5] = best; red_i[threadIdx.x >> 5] = bidx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < MD_THREADS / 32; w++)
+            if (md_better(red_d[w], red_i[w], best, bidx)) { best = red_d[w]; bidx = red_i[w]; }
+        part_d[(size_t)f * gridDim.x + blockIdx.x] = best;
+        part_idx[(size_t)f * gridDim.x + blockIdx.x] = bidx;
+    }
+}
+
 __global__ void __launch_bounds__(128) k_min_dist_final(const float* __restrict__ part_d,
                                                         const long long* __restrict__ part_idx,
                                                         int n_chunks, long long n_frames,

@@ -608,6 +608,21 @@ class ContactEngine(object):
                                              _stream_ptr(self.device)), "cmb_min_dist")
         return dmin, darg
 
+    def min_dist_pairs(self, xyz, box, atom_pairs, orthogonal):
+        """Per-frame minimum distance and first arg-min position over an arbitrary pair list."""
+        if xyz.dtype != torch.float32 or not xyz.is_contiguous() or not xyz.is_cuda:
+            raise TypeError("xyz must be a contiguous float32 CUDA tensor")
+        pairs = torch.as_tensor(np.ascontiguousarray(atom_pairs, dtype=np.int32).reshape(-1, 2), device=self.device)
+        n_frames, n_atoms = xyz.shape[0], xyz.shape[1]
+        dmin = torch.empty(n_frames, dtype=torch.float32, device=self.device)
+        darg = torch.empty(n_frames, dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self._L.cmb_min_dist_pairs(self._ctx, _ptr(xyz), _ptr(box), n_frames, n_atoms,
+                                                   _ptr(pairs), pairs.shape[0], int(bool(orthogonal)),
+                                                   _ptr(dmin), _ptr(darg), _stream_ptr(self.device)),
+                        "cmb_min_dist_pairs")
+        return dmin, darg
+
     def group_contacts(self, xyz, box, atom_pairs, group_ptr, cutoff, orthogonal):
         """``[n_groups, n_frames]`` bool array: is the minimum ``compute_distances`` distance over
         the atom pairs of each group below ``cutoff`` (float32, strict) in each frame?"""

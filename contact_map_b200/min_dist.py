@@ -90,7 +90,9 @@ class NearestAtoms(object):
         frame_box = None if box is None else box[frame_number:frame_number + 1] \
             if frame_number != -1 else box[-1:]
         d_xyz, d_box = _to_device(xyz[frame_number], frame_box, engine)
-        orthogonal = _is_orthogonal(frame_box)
+        # md.compute_distances(trajectory, ...)[frame_number] (min_dist.py:63-64): MDTraj decides
+        # orthorhombic vs triclinic arithmetic from ALL frames of the trajectory it is given
+        orthogonal = _is_orthogonal(box)
         if _raw_excluded is None:
             atom_res, _ = topology_arrays(trajectory.topology)
             mode, kwargs = 1, {"atom_res": atom_res}
@@ -151,6 +153,26 @@ class MinimumDistanceCounter(object):
             raise ValueError("atom_pairs must be between 0 and %d" % n_atoms)
         d_xyz, d_box = _to_device(xyz, box, engine)
         dmin, darg = engine.min_dist(d_xyz, d_box, query, haystack, _is_orthogonal(box))
+        return dmin.cpu().numpy(), darg.cpu().numpy()
+
+    @staticmethod
+    def _compute_from_atom_pairs(trajectory, atom_pairs):
+        """The reference's seam for alternative constructors (min_dist.py:142-168): minimum
+        distance and first arg-min index per frame over an arbitrary list of atom pairs, i.e.
+        ``D.min(axis=1), D.argmin(axis=1)`` of ``D = md.compute_distances(trajectory,
+        atom_pairs)`` -- returned as (minimum_distances, min_pairs) like the reference."""
+        from .engine import get_engine
+        engine = get_engine()
+        xyz, box = _split_trajectory(trajectory)
+        n_atoms = xyz.shape[1]
+        pairs = np.asarray(list(atom_pairs) if not isinstance(atom_pairs, np.ndarray) else atom_pairs,
+                           dtype=np.int64).reshape(-1, 2)
+        if pairs.shape[0] == 0:
+            raise ValueError("atom_pairs must not be empty")
+        if pairs.min() < 0 or pairs.max() >= n_atoms:
+            raise ValueError("atom_pairs must be between 0 and %d" % n_atoms)
+        d_xyz, d_box = _to_device(xyz, box, engine)
+        dmin, darg = engine.min_dist_pairs(d_xyz, d_box, pairs, _is_orthogonal(box))
         return dmin.cpu().numpy(), darg.cpu().numpy()
 
     def _remap(self, pair_number):

@@ -13,9 +13,9 @@ import numpy as np
 from . import parallel
 from . import trajectory as _trajectory
 from .contact_map import (ContactFrequency, ContactObject, _engine_system, _split_trajectory,
-                          _tables_to_pairs, _used_coordinates)
+                          _table_kind, _tables_to_pairs, _used_coordinates)
 from .contact_count import PairTable
-from .contact_trajectory import ContactTrajectory, FrameCSR, _build_contacts
+from .contact_trajectory import KEY_MAX_FRAMES, KEY_MAX_INDEX, ContactTrajectory, FrameCSR, _build_contacts
 
 
 def _n_workers(client):
@@ -70,9 +70,9 @@ class ChunkedContactFrequency(ContactFrequency):
                 engine.accumulate_host(bx, bb, atom_table, res_table)
         parallel.reduce_tables([atom_table, res_table], dst=self._result_rank)
         if self._result_rank is not None and parallel.world()[0] != self._result_rank:
-            self._device_tables = None
+            self._table_kind = _table_kind(atom_table)
             return PairTable.empty(), PairTable.empty()
-        self._device_tables = (atom_table, res_table, used)
+        self._table_kind = _table_kind(atom_table)
         return _tables_to_pairs(engine, atom_table, res_table, used)
 
 
@@ -125,19 +125,28 @@ class DaskContactTrajectory(ContactTrajectory):
         if world_size == 1 and self._n_blocks in (None, 1):
             return _build_contacts(self, trajectory)
         engine = get_engine()
+        if n_frames > KEY_MAX_FRAMES:
+            raise ValueError("DaskContactTrajectory handles at most %d frames (24-bit frame ids in the "
+                             "per-frame keys)" % KEY_MAX_FRAMES)
+        # keys travel between the ranks in COMPACT numbering (rank among the used atoms / used
+        # residues, < 2^20 by the C limit) and are mapped to real indices after the gather, so a
+        # topology with more than 2^20 atoms and a small query still packs correctly
+        used = np.asarray(self._all_arr, dtype=np.int64)
+        atom_res, _ = _trajectory.topology_arrays(self.topology)
+        used_res = np.unique(atom_res[used]).astype(np.int64)
+        if used.shape[0] > KEY_MAX_INDEX or used_res.shape[0] > KEY_MAX_INDEX:
+            raise ValueError("per-frame keys hold 20-bit indices: at most %d used atoms" % KEY_MAX_INDEX)
         atom_keys, res_keys = [], []
-        used = None
         for block in parallel.rank_slices(n_frames, self._n_blocks):
             atoms, residues = _build_contacts(self, trajectory[block])
-            used = np.asarray(self._all_atoms, dtype=np.int64)
             shift = np.uint64(block.start) << np.uint64(40)
-            for csr, sink in ((atoms, atom_keys), (residues, res_keys)):
+            for csr, sink, compact in ((atoms, atom_keys, used), (residues, res_keys, used_res)):
                 frame = np.repeat(np.arange(csr.n_frames, dtype=np.uint64), np.diff(csr.ptr))
-                sink.append(((frame << np.uint64(40)) + shift)
-                            | (csr.i.astype(np.uint64) << np.uint64(20)) | csr.j.astype(np.uint64))
+                lo = np.searchsorted(compact, csr.i).astype(np.uint64)
+                hi = np.searchsorted(compact, csr.j).astype(np.uint64)
+                sink.append(((frame << np.uint64(40)) + shift) | (lo << np.uint64(20)) | hi)
         cat = lambda parts: np.sort(np.concatenate(parts)) if parts else np.empty(0, np.uint64)  # noqa: E731
         atom_keys = parallel.gather_keys(cat(atom_keys), engine.device)
         res_keys = parallel.gather_keys(cat(res_keys), engine.device)
-        identity = np.arange(1 << 20, dtype=np.int64)
-        return (FrameCSR.from_keys(n_frames, atom_keys, identity),
-                FrameCSR.from_keys(n_frames, res_keys, identity))
+        return (FrameCSR.from_keys(n_frames, atom_keys, used),
+                FrameCSR.from_keys(n_frames, res_keys, used_res))

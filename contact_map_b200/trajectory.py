@@ -237,6 +237,52 @@ class Topology(object):
                         [self.residue_names[r] for r in kept_res], self.residue_resseq[kept_res],
                         self.atom_serials[idx])
 
+    # -- data frame round trip (the columns of mdtraj.Topology.to_dataframe) ---------------
+    def to_dataframe(self):
+        """(atoms DataFrame, bonds array): what the reference serialises in ``to_dict``
+        (contact_map.py:278-283).  This container holds no bonds: the array is empty."""
+        import pandas as pd
+        res = self.atom_residue
+        atoms = pd.DataFrame({
+            "serial": self.atom_serials,
+            "name": list(self.atom_names),
+            "element": list(self.atom_elements),
+            "resSeq": self.residue_resseq[res],
+            "resName": [self.residue_names[r] for r in res],
+            "chainID": self.residue_chain[res],
+            "segmentID": [""] * self.n_atoms,
+        })
+        return atoms, np.zeros((0, 4))
+
+    @classmethod
+    def from_dataframe(cls, atoms, bonds=None):
+        """Inverse of :meth:`to_dataframe`; a new residue starts where (chainID, resSeq, resName,
+        segmentID) changes, as in MDTraj.  Bonds are not kept."""
+        n = len(atoms)
+        chain = np.asarray(atoms["chainID"])
+        resseq = np.asarray(atoms["resSeq"])
+        resname = [str(v) for v in atoms["resName"]]
+        seg = [("" if v is None else str(v)) for v in atoms["segmentID"]] if "segmentID" in atoms.columns \
+            else [""] * n
+        atom_res = np.zeros(n, dtype=np.int32)
+        res_chain, res_names, res_seq = [], [], []
+        chain_ids = {}
+        prev = None
+        for i in range(n):
+            key = (chain[i], resseq[i], resname[i], seg[i])
+            if key != prev:
+                res_chain.append(chain_ids.setdefault(chain[i], len(chain_ids)))
+                res_names.append(resname[i])
+                res_seq.append(int(resseq[i]))
+                prev = key
+            atom_res[i] = len(res_chain) - 1
+        serial = np.asarray(atoms["serial"])
+        serials = None if serial.dtype == object or np.any(np.isnan(serial.astype(np.float64))) \
+            else serial.astype(np.int64)
+        return cls(atom_res, np.asarray(res_chain, dtype=np.int32), [str(v) for v in atoms["name"]],
+                   [("" if v is None else str(v)) for v in atoms["element"]], res_names,
+                   np.asarray(res_seq, dtype=np.int64), serials)
+
     def _signature(self):
         return (self.atom_residue.tobytes(), self.residue_chain.tobytes(), tuple(self.atom_names),
                 tuple(self.atom_elements), tuple(self.residue_names), self.residue_resseq.tobytes())

@@ -205,6 +205,16 @@ int cmb_min_dist(cmb_ctx* ctx, const float* d_xyz, const float* d_box, int64_t n
                  int orthogonal, float* d_min, int64_t* d_arg, void* stream);
 
 /*
+ * MinimumDistanceCounter._compute_from_atom_pairs(trajectory, atom_pairs) (min_dist.py:142-168)
+ * for an ARBITRARY pair list d_pairs[n_pairs][2] (int32 atom indices, device): per frame
+ * D.min(axis=1) and D.argmin(axis=1) of D = md.compute_distances(trajectory, atom_pairs)
+ * (min_dist.py:165-167) without materialising D; ties -> lowest position in the list.
+ */
+int cmb_min_dist_pairs(cmb_ctx* ctx, const float* d_xyz, const float* d_box, int64_t n_frames,
+                       int n_atoms, const int32_t* d_pairs, int64_t n_pairs, int orthogonal,
+                       float* d_min, int64_t* d_arg, void* stream);
+
+/*
  * NearestAtoms._calculate_nearest (min_dist.py:47-70) for one frame: for every atom
  * the nearest allowed neighbour within the cutoff (neighbour-list arithmetic for the
  * cutoff test, compute_distances arithmetic for the value; ties -> lower index).

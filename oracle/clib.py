@@ -27,9 +27,11 @@ def build(force=False):
     last = None
     for cc in compilers:
         for omp in (["-fopenmp"], []):
-            cmd = [cc] + _BASE_FLAGS + omp + ["-o", _SO, _SRC, "-lm"]
+            tmp = _SO + ".tmp%d" % os.getpid()        # atomic: concurrent builders never see a partial file
+            cmd = [cc] + _BASE_FLAGS + omp + ["-o", tmp, _SRC, "-lm"]
             try:
                 subprocess.run(cmd, check=True, capture_output=True, text=True)
+                os.replace(tmp, _SO)
                 return _SO
             except (OSError, subprocess.CalledProcessError) as exc:   # try the next recipe
                 last = exc
@@ -49,6 +51,8 @@ def lib():
     c_u32 = ctypes.POINTER(ctypes.c_uint32)
     L.orc_version.restype = ctypes.c_int
     L.orc_max_threads.restype = ctypes.c_int
+    L.orc_set_threads.restype = None
+    L.orc_set_threads.argtypes = [ctypes.c_int]
     L.orc_nl_d2.restype = ctypes.c_float
     L.orc_nl_d2.argtypes = [c_f, c_f, c_f]
     L.orc_neighborlist_csr.restype = ctypes.c_int64
@@ -209,3 +213,8 @@ def min_dist(xyz, query, haystack, box, orthogonal):
 
 def max_threads():
     return int(lib().orc_max_threads())
+
+
+def set_threads(n):
+    """Team size of the oracle's OpenMP loops from now on (this process)."""
+    lib().orc_set_threads(int(n))

@@ -235,7 +235,7 @@ def test_public_api_on_hashed_tables(engine, monkeypatch):
     """Systems whose dense count table would be too large run on hashed tables transparently:
     force that regime (global-memory cell path + a tiny dense limit) and compare the public
     ContactFrequency / chunked runner results with the default (dense, fused) ones."""
-    from contact_map_b200.engine import ContactEngine, HashTable
+    from contact_map_b200.engine import ContactEngine
     case = goldens.load("syn_tric_sub")
     traj = goldens.trajectory(case)
     kw = goldens.call_kwargs(case)
@@ -244,7 +244,7 @@ def test_public_api_on_hashed_tables(engine, monkeypatch):
     monkeypatch.setattr(ContactEngine, "DENSE_LIMIT_BYTES", 1024)
     try:
         got = cm.ContactFrequency(traj, **kw)
-        assert isinstance(got._device_tables[0], HashTable)
+        assert got._table_kind == "hashed"
         assert got._atom_contacts == want._atom_contacts == goldens.counter(case["atom_pairs"], case["atom_counts"])
         assert got._residue_contacts == want._residue_contacts
         chunked = cm.ChunkedContactFrequency(traj, n_blocks=3, **kw)

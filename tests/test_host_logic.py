@@ -113,8 +113,43 @@ def test_objects_without_gpu():
     import pickle
     again = pickle.loads(pickle.dumps(m2))
     assert again == m2
-    rt = cm.ContactFrequency.from_json(m2.to_json(), traj.topology)
+    rt = cm.ContactFrequency.from_json(m2.to_json(), traj.topology)      # earlier two-argument form
     assert rt == m2
+    assert cm.ContactFrequency.from_json(m2.to_json()) == m2              # the reference's signature
+
+
+def test_json_files_written_by_the_reference_load_here():
+    """tests/golden/ref_json.json holds the reference's own to_json / to_dict output (generated by
+    make_golden_json.py, which also checks that the reference loads THIS package's JSON): same key
+    set, same counters, one-argument from_json / from_dict (contact_map.py:202-333,838-880;
+    contact_trajectory.py:152-162)."""
+    import json
+    with open(os.path.join(goldens.GOLDEN_DIR, "ref_json.json")) as f:
+        gold = json.load(f)
+    want_atoms = collections.Counter({frozenset(k): v for k, v in gold["expected"]["atom_contacts"]})
+    want_res = collections.Counter({frozenset(k): v for k, v in gold["expected"]["residue_contacts"]})
+    freq = cm.ContactFrequency.from_json(gold["frequency_json"])
+    assert freq._atom_contacts == want_atoms and freq._residue_contacts == want_res
+    assert freq.n_frames == gold["expected"]["n_frames"] and freq.cutoff == 0.075
+    assert freq.topology.n_atoms == 10 and freq.topology.n_residues == 5
+    again = json.loads(freq.to_json())
+    ref_dct = json.loads(gold["frequency_json"])
+    assert set(again) == set(ref_dct)
+    for key in ("cutoff", "n_neighbors_ignored", "n_frames", "use_atom_slice"):
+        assert again[key] == ref_dct[key]
+    for key in ("query", "haystack", "query_res_idx", "haystack_res_idx", "all_atoms", "all_residues"):
+        assert sorted(again[key]) == sorted(ref_dct[key])
+    norm = lambda text: {tuple(sorted(json.loads(k))): v for k, v in json.loads(text).items()}   # noqa: E731
+    assert norm(again["atom_contacts"]) == norm(ref_dct["atom_contacts"])
+    assert norm(again["residue_contacts"]) == norm(ref_dct["residue_contacts"])
+    ctraj = cm.ContactTrajectory.from_dict(gold["trajectory_dict"])
+    assert len(ctraj) == 5
+    assert ctraj.contact_frequency()._atom_contacts == want_atoms
+    assert cm.ContactTrajectory.from_json(ctraj.to_json()) == ctraj
+    diff = cm.ContactDifference.from_dict(gold["difference_dict"])
+    want_diff = {frozenset(k): v for k, v in gold["expected"]["difference_atom"]}
+    assert dict(diff.atom_contacts.counter) == want_diff
+    assert set(diff.to_dict()) == set(gold["difference_dict"])
 
 
 def test_query_haystack_containers_follow_the_reference():

@@ -23,7 +23,7 @@ for hashed in (False, True):
     sharded = cm.ChunkedContactFrequency(traj, cutoff=0.45, n_neighbors_ignored=2, n_blocks=5)
     same = (sharded._atom_contacts == serial._atom_contacts and sharded._residue_contacts == serial._residue_contacts
             and sharded.n_frames == len(traj))
-    print("rank %d hashed=%s tables=%s equal=%s" % (rank, hashed, type(sharded._device_tables[0]).__name__, same))
+    print("rank %d hashed=%s tables=%s equal=%s" % (rank, hashed, sharded._table_kind, same))
     ok = ok and same
 # reduce to rank 0 only: rank 0 holds the serial result, the other ranks an empty map
 engine.set_option("force_path", -1)
