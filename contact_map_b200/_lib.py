@@ -15,7 +15,7 @@ _ROOT = os.path.dirname(_HERE)
 SO_PATH = os.environ.get("CMB200_SO") or os.path.join(_HERE, "libcmb200.so")
 _SOURCES = [os.path.join(_HERE, "csrc", f) for f in (
     "cmb_api.cu", "cmb_math.cuh", "cmb_cells.cuh", "cmb_frames_small.cuh",
-    "cmb_frames_large.cuh", "cmb_aux_kernels.cuh")] + [os.path.join(_ROOT, "include", "cmb200.h")]
+    "cmb_frames_large.cuh", "cmb_aux_kernels.cuh", "cmb_verlet.cuh")] + [os.path.join(_ROOT, "include", "cmb200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

@@ -16,6 +16,7 @@
 #include "cmb_aux_kernels.cuh"
 #include "cmb_frames_large.cuh"
 #include "cmb_frames_small.cuh"
+#include "cmb_verlet.cuh"
 
 using namespace cmb;
 
@@ -54,6 +55,16 @@ struct cmb_ctx {
 
     // large path scratch
     LargeScratch large[2];
+
+    // frame-batch pair-list path (cmb_verlet.cuh), one scratch set per stream slot
+    VlScratch vl[2];
+    int* d_res_anchor = nullptr;              // [n_res_c] first used atom of each compact residue
+    int verlet = 1;                           // 0 off, 1 when the batch is long enough, 2 always
+    int verlet_audit = 0;                     // run the exact arithmetic on every listed pair and count disagreements
+    int verlet_max_rlist_pct = 175;           // lists with r_list above this percentage of the cutoff are not built
+    unsigned long long* d_vl_audit = nullptr; // [2] audited pairs, disagreements
+    int last_used_verlet = 0;
+    int last_vl_slot = 0;
 
     // host pipeline
     float* d_stage_xyz[2] = {nullptr, nullptr};
@@ -172,6 +183,9 @@ extern "C" void cmb_ctx_destroy(cmb_ctx* ctx)
         if (ctx->streams[s]) cudaStreamDestroy(ctx->streams[s]);
         large_scratch_free(ctx->large[s]);
     }
+    for (int s = 0; s < 2; s++) vl_free(ctx->vl[s]);
+    cudaFree(ctx->d_res_anchor);
+    cudaFree(ctx->d_vl_audit);
     cudaFree(ctx->d_tmp);
     cudaFree(ctx->d_hstats);
     delete ctx;
@@ -194,6 +208,17 @@ extern "C" int cmb_set_option(cmb_ctx* ctx, const char* name, int64_t value)
         return CMB_OK;
     }
     if (!strcmp(name, "force_path")) { ctx->stats["force_path"] = value; return CMB_OK; }
+    if (!strcmp(name, "verlet")) {
+        if (value < 0 || value > 2) return fail(ctx, CMB_ERR_ARG, "verlet must be 0 (off), 1 (auto) or 2 (always)");
+        ctx->verlet = (int)value;
+        return CMB_OK;
+    }
+    if (!strcmp(name, "verlet_audit")) { ctx->verlet_audit = value != 0; return CMB_OK; }
+    if (!strcmp(name, "verlet_max_rlist_pct")) {
+        if (value < 101 || value > 400) return fail(ctx, CMB_ERR_ARG, "verlet_max_rlist_pct out of range");
+        ctx->verlet_max_rlist_pct = (int)value;
+        return CMB_OK;
+    }
     return fail(ctx, CMB_ERR_ARG, "unknown option %s", name);
 }
 
@@ -213,6 +238,32 @@ extern "C" int cmb_get_stat(cmb_ctx* ctx, const char* name, int64_t* value)
     if (!strcmp(name, "smem_bytes")) { *value = ctx->fs_smem; return CMB_OK; }
     if (!strcmp(name, "max_cells")) { *value = ctx->fs_maxc; return CMB_OK; }
     if (!strcmp(name, "kernel_launches")) { *value = ctx->stats["kernel_launches"]; return CMB_OK; }
+    if (!strcmp(name, "vl_used")) { *value = ctx->last_used_verlet; return CMB_OK; }
+    if (!strncmp(name, "vl_", 3)) {
+        // pair-list path diagnostics of the last launch (synchronises)
+        const VlScratch& V = ctx->vl[ctx->last_vl_slot];
+        if (!V.L.hdr) { *value = 0; return CMB_OK; }
+        CK(cudaSetDevice(ctx->device));
+        CK(cudaDeviceSynchronize());
+        VlHeader h;
+        CK(cudaMemcpy(&h, V.L.hdr, sizeof(h), cudaMemcpyDeviceToHost));
+        if (!strcmp(name, "vl_valid")) { *value = h.valid; return CMB_OK; }
+        if (!strcmp(name, "vl_fail")) { *value = h.fail_code; return CMB_OK; }
+        if (!strcmp(name, "vl_tripped")) { *value = h.n_tripped; return CMB_OK; }
+        if (!strcmp(name, "vl_entries")) { *value = h.n_entries; return CMB_OK; }
+        if (!strcmp(name, "vl_tiles")) { *value = h.n_tiles; return CMB_OK; }
+        if (!strcmp(name, "vl_rows")) { *value = h.n_rows; return CMB_OK; }
+        if (!strcmp(name, "vl_slots")) { *value = h.n_slots; return CMB_OK; }
+        if (!strcmp(name, "vl_segs")) { *value = h.n_segs; return CMB_OK; }
+        if (!strcmp(name, "vl_bundles")) { *value = h.n_bundles; return CMB_OK; }
+        if (!strcmp(name, "vl_rlist_um")) { *value = (int64_t)(h.rlist * 1.0e6f); return CMB_OK; }
+        if (!strcmp(name, "vl_audited") || !strcmp(name, "vl_disagree")) {
+            unsigned long long a[2] = {0, 0};
+            if (ctx->d_vl_audit) CK(cudaMemcpy(a, ctx->d_vl_audit, sizeof(a), cudaMemcpyDeviceToHost));
+            *value = (int64_t)a[!strcmp(name, "vl_disagree") ? 1 : 0];
+            return CMB_OK;
+        }
+    }
     return fail(ctx, CMB_ERR_ARG, "unknown stat %s", name);
 }
 
@@ -357,6 +408,15 @@ extern "C" int cmb_set_system(cmb_ctx* ctx, int n_used, const int32_t* atom_res,
     }
     CK(cudaMemcpy(ctx->d_meta, meta.data(), sizeof(int2) * (size_t)n_used, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_meta32, meta32.data(), sizeof(unsigned int) * (size_t)n_used, cudaMemcpyHostToDevice));
+    {
+        // first used atom of every compact residue (tile assignment of the pair-list path)
+        std::vector<int> anchor(uniq.size(), -1);
+        for (int i = n_used - 1; i >= 0; i--) anchor[rc_of_atom[i]] = i;
+        if (ctx->d_res_anchor) CK(cudaFree(ctx->d_res_anchor));
+        ctx->d_res_anchor = nullptr;
+        CK(cudaMalloc(&ctx->d_res_anchor, sizeof(int) * anchor.size()));
+        CK(cudaMemcpy(ctx->d_res_anchor, anchor.data(), sizeof(int) * anchor.size(), cudaMemcpyHostToDevice));
+    }
 
     ctx->n = n_used;
     ctx->cutoff_f = (float)cutoff;
@@ -443,9 +503,48 @@ static int launch_frames(cmb_ctx* ctx, const FrameJob& job, int slot, cudaStream
     const float c2 = ctx->cutoff_f * ctx->cutoff_f;   // float multiply, as in MDTraj
     if ((ctx->atom_log2 > 0 || ctx->res_log2 > 0) && ctx->path == 0)
         return fail(ctx, CMB_ERR_STATE, "hashed count tables are only used by the global-memory cell path");
+
+    // ---- frame-batch pair-list path (cmb_verlet.cuh): plain accumulation into dense tables over a
+    //      batch long enough to pay for the list; the frames it cannot take (guard tripped, list
+    //      unusable) come back on a device-side list and run through the cell kernels below --------
+    const int* frame_list = nullptr;
+    const int* frame_count = nullptr;
+    ctx->last_used_verlet = 0;
+    {
+        const bool plain = !job.atom_keys && !job.res_keys && job.boundary_ulps == 0 && !ctx->count_tests &&
+                           (job.atom_table || job.res_table) && ctx->atom_log2 == 0 && ctx->res_log2 == 0;
+        const long long min_frames = ctx->path == 0 ? 256 : 32;
+        if (plain && ctx->verlet != 0 && (ctx->verlet == 2 || job.n_frames >= min_frames) && job.n_frames >= 2 &&
+            job.n_frames < (1ll << 30)) {
+            VlScratch& V = ctx->vl[slot];
+            std::string err;
+            int launches = 0;
+            int rc = vl_ensure(V, ctx->n, ctx->n_res_c, job.n_frames, err);
+            if (rc != 0) return fail(ctx, rc, "%s", err.c_str());
+            if (ctx->verlet_audit && !ctx->d_vl_audit) {
+                CK(cudaMalloc(&ctx->d_vl_audit, 2 * sizeof(unsigned long long)));
+                CK(cudaMemset(ctx->d_vl_audit, 0, 2 * sizeof(unsigned long long)));
+            }
+            VlJob vj;
+            vj.xyz = job.xyz; vj.box = job.box; vj.n_frames = job.n_frames; vj.n = ctx->n; vj.n_res_c = ctx->n_res_c;
+            vj.meta = ctx->d_meta; vj.res_anchor = ctx->d_res_anchor; vj.cutoff = ctx->cutoff_f; vj.c2 = c2;
+            vj.n_ignored = ctx->n_ignored; vj.atom_table = job.atom_table; vj.res_table = job.res_table;
+            vj.audit = ctx->verlet_audit; vj.d_audit = ctx->d_vl_audit;
+            vj.max_rlist_factor = 0.01f * (float)ctx->verlet_max_rlist_pct;
+            rc = vl_build(vj, V, stream, err, launches);
+            if (rc == 0) rc = vl_run_frames(vj, V, ctx->sm_count, stream, err, launches);
+            ctx->stats["kernel_launches"] += launches;
+            if (rc != 0) return fail(ctx, rc, "%s", err.c_str());
+            ctx->last_used_verlet = 1;
+            ctx->last_vl_slot = slot;
+            frame_list = V.L.tripped;
+            frame_count = &V.L.hdr->n_tripped;
+        }
+    }
     if (ctx->path == 0) {
         FrameParams p;
         memset(&p, 0, sizeof(p));
+        p.frame_list = frame_list; p.frame_count = frame_count;
         p.xyz = job.xyz; p.box = job.box; p.n_frames = job.n_frames; p.frame0 = job.frame0;
         p.n = ctx->n; p.meta32 = ctx->d_meta32;
         p.cutoff = ctx->cutoff_f; p.c2 = c2;
@@ -475,6 +574,28 @@ static int launch_frames(cmb_ctx* ctx, const FrameJob& job, int slot, cudaStream
         return CMB_OK;
     }
     // global-memory cell path
+    std::vector<std::pair<long long, long long>> runs;      // [first, last) frame ranges to process
+    if (frame_list != nullptr) {
+        // fall back of the pair-list path: the list of tripped frames is read back (one stream
+        // synchronisation per call; a call is tens of milliseconds on this path) and processed
+        // as runs of consecutive frames
+        VlScratch& V = ctx->vl[slot];
+        CK(cudaMemcpyAsync(V.h_info, frame_count, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        const int n_trip = V.h_info[0];
+        if (n_trip == 0) return CMB_OK;
+        std::vector<int> trip((size_t)n_trip);
+        CK(cudaMemcpy(trip.data(), frame_list, sizeof(int) * (size_t)n_trip, cudaMemcpyDeviceToHost));
+        std::sort(trip.begin(), trip.end());
+        for (size_t k = 0; k < trip.size();) {
+            size_t e = k + 1;
+            while (e < trip.size() && trip[e] == trip[e - 1] + 1) e++;
+            runs.push_back({trip[k], (long long)trip[e - 1] + 1});
+            k = e;
+        }
+    } else {
+        runs.push_back({0, job.n_frames});
+    }
     LargeJob lj;
     lj.xyz = job.xyz; lj.box = job.box; lj.n_frames = job.n_frames; lj.frame0 = job.frame0;
     lj.n = ctx->n; lj.meta = ctx->d_meta; lj.cutoff = ctx->cutoff_f; lj.c2 = c2;
@@ -489,11 +610,18 @@ static int launch_frames(cmb_ctx* ctx, const FrameJob& job, int slot, cudaStream
     lj.atom_log2 = ctx->atom_log2; lj.res_log2 = ctx->res_log2; lj.hstats = ctx->d_hstats;
     lj.ovf_list = ctx->d_ovf; lj.ovf_cap = ctx->ovf_cap;
     lj.batch_mode = ctx->large_batch;
-    std::string err;
-    int launches = 0;
-    int rc = large_run(lj, ctx->large[slot], ctx->sm_count, stream, err, launches);
-    ctx->stats["kernel_launches"] += launches;
-    if (rc != CMB_OK) return fail(ctx, rc, "%s", err.c_str());
+    for (const auto& run : runs) {
+        LargeJob part = lj;
+        part.xyz = lj.xyz + (size_t)run.first * (size_t)ctx->n * 3;
+        part.box = lj.box ? lj.box + (size_t)run.first * 9 : nullptr;
+        part.n_frames = run.second - run.first;
+        part.frame0 = lj.frame0 + run.first;
+        std::string err;
+        int launches = 0;
+        int rc = large_run(part, ctx->large[slot], ctx->sm_count, stream, err, launches);
+        ctx->stats["kernel_launches"] += launches;
+        if (rc != CMB_OK) return fail(ctx, rc, "%s", err.c_str());
+    }
     return CMB_OK;
 }
 

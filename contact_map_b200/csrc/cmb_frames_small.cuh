@@ -83,6 +83,10 @@ struct FrameParams {
     unsigned long long* counters;    // [0] atom keys, [1] residue keys, [2] boundary records, [3] pair tests
     float4* boundary;            // records {frame, lo, hi, d2} (ints bit-cast) or nullptr
     long long boundary_cap;
+    // fall back of the pair-list path (cmb_verlet.cuh): only the frames frame_list[0 .. *frame_count)
+    // are processed (both device side: no host round trip); nullptr: all n_frames frames
+    const int* frame_list;
+    const int* frame_count;
 };
 
 // ----- mbarrier / TMA bulk helpers (sm_90+ PTX; SASS: SYNCS / UBLKCP) -------------
@@ -299,7 +303,11 @@ __global__ void __launch_bounds__(THREADS, THREADS > 512 ? 1 : FS_MIN_CTAS) k_fr
     unsigned long long n_tests = 0;
     uint32_t parity = 0;
     const long long stride = gridDim.x;
-    long long f = blockIdx.x;
+    // the frames this CTA works on: li-th entries of the frame list (identity without a list)
+    const long long n_list = p.frame_list != nullptr ? (long long)*p.frame_count : p.n_frames;
+    long long li = blockIdx.x;
+    auto frame_of = [&](long long k) { return p.frame_list != nullptr ? (long long)p.frame_list[k] : k; };
+    long long f = li < n_list ? frame_of(li) : 0;
 
     auto issue_load = [&](long long frame) {
         const unsigned long long addr = (unsigned long long)(p.xyz + (size_t)frame * (size_t)n * 3);
@@ -309,13 +317,14 @@ __global__ void __launch_bounds__(THREADS, THREADS > 512 ? 1 : FS_MIN_CTAS) k_fr
         mbar_expect_tx(mbar, bytes);
         tma_bulk_g2s(raw, reinterpret_cast<const void*>(a0), bytes, mbar);
     };
-    if (tid == 0 && f < p.n_frames) issue_load(f);
+    if (tid == 0 && li < n_list) issue_load(f);
 
     // without residue keys the residue table is updated at the first hit of a pair and the
     // bitmap is only cleared between frames (together with the histogram, before the grid barrier)
     const bool res_at_once = p.res_table != nullptr && !((FLAGS & FS_EMIT) && p.res_keys != nullptr);
     bool first_frame = true;
-    for (; f < p.n_frames; f += stride) {
+    for (; li < n_list; li += stride) {
+        f = frame_of(li);
         const float* box9 = p.box ? p.box + (size_t)f * 9 : nullptr;
         const unsigned long long addr = (unsigned long long)(p.xyz + (size_t)f * (size_t)n * 3);
         float* xr = reinterpret_cast<float*>(raw + (addr & 15ull));
@@ -495,9 +504,9 @@ __global__ void __launch_bounds__(THREADS, THREADS > 512 ? 1 : FS_MIN_CTAS) k_fr
         }
         __syncthreads();
         // raw buffer is free: prefetch this CTA's next frame under the pair phase
-        if (tid == 0 && f + stride < p.n_frames) {
+        if (tid == 0 && li + stride < n_list) {
             fence_proxy_async();
-            issue_load(f + stride);
+            issue_load(frame_of(li + stride));
         }
 
         // ---- pass D: pair phase, one warp per occupied cell ---------------------------

@@ -1,0 +1,1345 @@
+// cmb_verlet.cuh -- frame-batch pair-list path ("Verlet batch"): the candidate pair list of a
+// batch of frames is built ONCE, every frame of the batch then only walks that list.
+//
+// Replaces, per frame (reference file:line under /root/reference/contact_map/), the same lines as
+// the cell kernels (cmb_frames_small.cuh / cmb_frames_large.cuh):
+//   md.compute_neighborlist(used_traj, cutoff, frame)      contact_map.py:575
+//   the Python set algebra of ContactObject._contact_map   contact_map.py:582-607
+//   Counter.update / Counter += of ContactFrequency        contact_map.py:739-740
+//
+// Why: the cell kernels screen ~8 candidate pairs per contact and spend 2/3 of their issue slots
+// on per-task set-up, ring traffic and per-hit atomics.  Frames of one trajectory
+// are strongly correlated, so the classical MD answer applies: a skin-padded pair list.
+//
+//   builder (once per batch, all on the device, no host round trip):
+//     1. REFERENCE positions: the mean of VL_SAMPLES frames spread over the batch (every sample
+//        unwrapped to the periodic image next to the first one), wrapped into the primary cell;
+//        skin = 1.3 x the largest displacement of any sampled atom from that mean (+ 0.002 nm).
+//     2. cell grid with cells >= r_list = 1.002 c + 2 skin; every eligible pair (roles, residue
+//        exclusion: contact_map.py:41-60,442-461 -- both are frame independent, so they are
+//        applied HERE and never again) whose reference minimum-image distance is <= r_list is
+//        recorded once, with the lattice shift of its image.
+//     3. the records are sorted by (tile, residue pair): the atom pairs of one residue pair form
+//        a SEGMENT.  Segments are sorted by length and dealt 32 at a time to "bundles"
+//        (lane = segment); a bundle is stored as ROWS of 4 steps x 32 lanes.  A tile is a block of
+//        cells whose segments, atoms ("slots", periodic images of an atom are separate slots
+//        that carry their lattice shift) and counters fit one CTA's shared memory: small systems
+//        are one tile, the 100k-atom system a few hundred.
+//   frame kernel (persistent CTAs, work item = tile x range of frames):
+//     a. every thread loads its slots' RAW coordinates (prefetched one frame ahead), moves them
+//        to the periodic image next to the slot's reference position (fp64, one rounding) and
+//        checks the GUARD |x - ref| <= skin; a frame that violates it (or whose unit cell differs
+//        from the batch's, or whose coordinates exceed the magnitude the error bound was derived
+//        for) is appended to the fall-back list and skipped;
+//     b. warps pull rows (two at a time, the next two already in flight from L2); a lane walks
+//        the atom pairs of ITS residue pair: two LDS.128 (one when the first atom repeats),
+//        3 FADD + 3 FFMA, two compares; d2 <= c2_lo is a certain contact, c2_lo < d2 < c2_hi is
+//        AMBIGUOUS and decided by MDTraj's exact non-fused arithmetic on the raw coordinates
+//        (cmb_math.cuh::nl_d2), exactly as in the cell kernels (same per-batch error bound,
+//        frame_margins); contacts increment a per-entry byte counter in shared memory (the
+//        thread owns the entry: no atomics) and set the lane's "residue pair seen" bit -- the
+//        per-frame set semantics of contact_map.py:601-607,740 without a bitmap;
+//     c. after the last frame of the item the counters are flushed with one RED per non-zero
+//        entry (a batch of 64 frames issues ~30x fewer atomics than one per hit).
+//   fall back: the frames on the fall-back list are processed by the cell kernels (which accept
+//   a device-side frame list), so the result never depends on the list being usable.
+//
+// Exactness.  A pair the reference arithmetic calls a contact in frame f has a true minimum-image
+// distance < 1.002 c (DESIGN.md 4.0 "domain").  Both atoms are within `skin` of their reference
+// positions (guard), so the same image of the pair is within 1.002 c + 2 skin = r_list at the
+// reference positions and the pair is on the list (the builder tests with a relative slack of
+// 1e-5 and bins in fp64).  For listed pairs the screening distance differs from the exact one by
+// at most the frame_margins bound, evaluated for the largest coordinate magnitude the guard
+// admits.  Unit cells need >= 3 list cells per periodic dimension (then the image of a pair
+// inside r_list is unique) and the lower-triangular form MDTraj produces; otherwise the builder
+// marks the list invalid and every frame falls back.
+#pragma once
+#include <cub/cub.cuh>
+
+#include <string>
+
+#include "cmb_cells.cuh"
+
+namespace cmb {
+
+constexpr int VL_THREADS = 1024;
+constexpr int VL_SPT = 4;                                // slots per thread
+constexpr int VL_MAX_SLOTS = VL_THREADS * VL_SPT - 1;    // + 1 "far" slot for padding entries
+constexpr int VL_ROW = 128;                              // entries per row: 32 lanes x 4 steps
+constexpr int VL_MAX_ROWS = 768;                         // per tile
+constexpr int VL_MAX_ENTRIES = VL_MAX_ROWS * VL_ROW;     // 98 304 byte counters
+constexpr int VL_MAX_SEGS = 24576;                       // residue pairs per tile
+constexpr int VL_FETCH_ROWS = 2;                         // rows a warp takes per trip to the work counter
+constexpr int VL_MAX_TILES = 4096;
+constexpr int VL_MAXC = 1 << 17;                         // cells of the list grid
+constexpr int VL_SAMPLES = 16;
+constexpr int VL_ITEM_FRAMES = 255;                      // byte counters: flush at least this often
+constexpr int VL_SINGLE_TILE_ATOMS = 3800;
+constexpr int VL_LEN_BITS = 20;                          // segment length field of the bundle sort key
+constexpr unsigned long long VL_PAD = ~0ull;
+
+struct VlHeader {
+    int valid;                 // 0: the list cannot be used, every frame falls back
+    int n_tiles, tdim, ntx, nty, ntz;
+    int n_entries;             // list pairs found (may exceed the capacity -> invalid)
+    int n_segs, n_slots, n_bundles, n_rows;
+    int rbits, abits;          // bits of a compact residue id / of a used-atom index in the sort keys
+    unsigned d_max_bits, a_max_bits;       // sample maxima (non-negative float bits)
+    unsigned bb_lo[3], bb_hi[3];           // bounding box of the reference positions (ordered uints)
+    float skin2, rlist, a_assumed, c2_lo, c2_hi;
+    int periodic;
+    unsigned box_bits[9];      // the batch's unit cell (compared bit for bit per frame)
+    double hinv[9], h[9];
+    float4 shift[27];
+    GridS grid;
+    int n_tripped;             // frames on the fall-back list
+    int next_item;             // work queue of the frame kernel
+    int fail_code;             // why valid == 0 (diagnostics)
+};
+
+struct VlTile {
+    int slot0, n_slots;        // into slot_word / slot_ref
+    int seg0, n_segs;          // into seg_pair (length-sorted order)
+    int row0, n_rows;          // into entries (rows of VL_ROW words) and row_bundle
+};
+
+// everything the builder writes and the frame kernel reads (device pointers)
+struct VlList {
+    VlHeader* hdr;
+    VlTile* tiles;             // [VL_MAX_TILES]
+    unsigned* slot_word;       // [slot_cap] atom | shift id << 24
+    float4* slot_ref;          // [slot_cap] reference position of the slot's atom (primary cell)
+    unsigned short* row_bundle;  // [row_cap] bundle (tile relative) of each row: its lanes are segments 32 b + lane
+    unsigned* entries;         // [row_cap * VL_ROW] 16 slot_i | 16 slot_j << 16 (byte offsets into the position array)
+    uint2* seg_pair;           // [entry_cap] {compact residue lo, hi} in length-sorted order
+    int* tripped;              // [frame_cap] frames of the current call that fall back
+    int* frame_flag;           // [frame_cap] 1: the frame is on the fall-back list (multi-tile lists: set by vl_guard)
+    long long entry_cap, slot_cap, row_cap;
+};
+
+// builder scratch
+struct VlScratch {
+    int cap_atoms = 0;
+    long long entry_cap = 0;
+    long long frame_cap = 0;
+    VlList L{};
+    float4* ref_raw = nullptr;      // [n] mean of the unwrapped samples
+    float4* ref_w = nullptr;        // [n] wrapped reference {x, y, z, cell}
+    int* atomrank = nullptr;        // [n]
+    int* cellcnt = nullptr;         // [VL_MAXC + 1]
+    int* cellptr = nullptr;         // [VL_MAXC + 1]
+    float4* sref = nullptr;         // [n] cell-sorted reference {x, y, z, atom}
+    int2* smeta = nullptr;          // [n] cell-sorted {ekey, res_c | role << 30}
+    int* scell = nullptr;           // [n] cell of each sorted position
+    int* tile_of_res = nullptr;     // [n_res_c]
+    unsigned long long* rec_key[2] = {nullptr, nullptr};   // [entry_cap]
+    unsigned long long* rec_val[2] = {nullptr, nullptr};
+    unsigned long long* seg_key = nullptr;                 // [entry_cap] unique keys
+    int* seg_len = nullptr;                                // [entry_cap]
+    int* seg_start = nullptr;                              // [entry_cap + 1]
+    int* n_runs = nullptr;                                 // [2]
+    unsigned long long* skey[2] = {nullptr, nullptr};      // [entry_cap] tile << VL_LEN_BITS | ~len
+    int* sval[2] = {nullptr, nullptr};                     // [entry_cap] segment id
+    unsigned long long* slot_key[2] = {nullptr, nullptr};  // [2 * entry_cap + n]
+    unsigned long long* slot_uniq = nullptr;               // [2 * entry_cap + n]
+    int* tile_seg0 = nullptr;       // [VL_MAX_TILES + 1] first segment (sorted order) of each tile
+    int* tile_bundle0 = nullptr;    // [VL_MAX_TILES + 1]
+    int* tile_slot0 = nullptr;      // [VL_MAX_TILES + 1]
+    int* bundle_row0 = nullptr;     // [bundle_cap + 1]
+    long long bundle_cap = 0;
+    void* cub_tmp = nullptr;
+    size_t cub_bytes = 0;
+    int* h_info = nullptr;          // pinned: n_tripped read back by the large path
+};
+
+inline void vl_free(VlScratch& S)
+{
+    cudaFree(S.L.hdr); cudaFree(S.L.tiles); cudaFree(S.L.slot_word); cudaFree(S.L.slot_ref);
+    cudaFree(S.L.row_bundle); cudaFree(S.L.entries); cudaFree(S.L.seg_pair); cudaFree(S.L.tripped);
+    cudaFree(S.L.frame_flag);
+    cudaFree(S.ref_raw); cudaFree(S.ref_w); cudaFree(S.atomrank); cudaFree(S.cellcnt); cudaFree(S.cellptr);
+    cudaFree(S.sref); cudaFree(S.smeta); cudaFree(S.scell); cudaFree(S.tile_of_res);
+    for (int k = 0; k < 2; k++) {
+        cudaFree(S.rec_key[k]); cudaFree(S.rec_val[k]); cudaFree(S.skey[k]); cudaFree(S.sval[k]);
+        cudaFree(S.slot_key[k]);
+    }
+    cudaFree(S.seg_key); cudaFree(S.seg_len); cudaFree(S.seg_start); cudaFree(S.n_runs); cudaFree(S.slot_uniq);
+    cudaFree(S.tile_seg0); cudaFree(S.tile_bundle0); cudaFree(S.tile_slot0); cudaFree(S.bundle_row0);
+    cudaFree(S.cub_tmp);
+    if (S.h_info) cudaFreeHost(S.h_info);
+    S = VlScratch();
+}
+
+// ----- small helpers --------------------------------------------------------------------
+__device__ __forceinline__ unsigned vl_ordered(float v)      // monotone float -> uint map
+{
+    const unsigned b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float vl_unordered(unsigned o)
+{
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+// position of `p` moved to the periodic image next to `r` (fp64, rounded once to fp32)
+__device__ __forceinline__ void vl_unwrap(const double* hinv, const double* h, int periodic, float px, float py,
+                                          float pz, float rx, float ry, float rz, float& ox, float& oy, float& oz)
+{
+    if (!periodic) { ox = px; oy = py; oz = pz; return; }
+    const double dx = (double)px - (double)rx, dy = (double)py - (double)ry, dz = (double)pz - (double)rz;
+    const double n0 = rint(dx * hinv[0] + dy * hinv[3] + dz * hinv[6]);
+    const double n1 = rint(dx * hinv[1] + dy * hinv[4] + dz * hinv[7]);
+    const double n2 = rint(dx * hinv[2] + dy * hinv[5] + dz * hinv[8]);
+    ox = (float)((double)px - (n0 * h[0] + n1 * h[3] + n2 * h[6]));
+    oy = (float)((double)py - (n0 * h[1] + n1 * h[4] + n2 * h[7]));
+    oz = (float)((double)pz - (n0 * h[2] + n1 * h[5] + n2 * h[8]));
+}
+
+__device__ __forceinline__ void vl_box_inverse(const float* box9, double* h, double* m)
+{
+    for (int k = 0; k < 9; k++) h[k] = (double)box9[k];
+    const double det = h[0] * (h[4] * h[8] - h[5] * h[7]) - h[1] * (h[3] * h[8] - h[5] * h[6]) +
+                       h[2] * (h[3] * h[7] - h[4] * h[6]);
+    const double id = 1.0 / det;
+    m[0] = (h[4] * h[8] - h[5] * h[7]) * id; m[1] = (h[2] * h[7] - h[1] * h[8]) * id;
+    m[2] = (h[1] * h[5] - h[2] * h[4]) * id; m[3] = (h[5] * h[6] - h[3] * h[8]) * id;
+    m[4] = (h[0] * h[8] - h[2] * h[6]) * id; m[5] = (h[2] * h[3] - h[0] * h[5]) * id;
+    m[6] = (h[3] * h[7] - h[4] * h[6]) * id; m[7] = (h[1] * h[6] - h[0] * h[7]) * id;
+    m[8] = (h[0] * h[4] - h[1] * h[3]) * id;
+}
+
+// shared-memory atomics as single instructions (the compiler's warp-aggregated forms cost a dozen
+// issue slots when one lane is active)
+__device__ __forceinline__ int vl_atoms_add(int* addr, int v)
+{
+    int old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;"
+                 : "=r"(old) : "r"((unsigned)__cvta_generic_to_shared(addr)), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ void vl_reds_or(unsigned* addr, unsigned v)
+{
+    asm volatile("red.shared.or.b32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(addr)), "r"(v) : "memory");
+}
+
+// ----- builder kernels --------------------------------------------------------------------
+__global__ void vl_init(VlHeader* hdr, const float* box, int periodic, int rbits, int abits)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    VlHeader& H = *hdr;
+    H.valid = 1; H.fail_code = 0;
+    H.n_tiles = H.n_entries = H.n_segs = H.n_slots = H.n_bundles = H.n_rows = 0;
+    H.rbits = rbits; H.abits = abits;
+    H.d_max_bits = 0u; H.a_max_bits = 0u;
+    for (int k = 0; k < 3; k++) { H.bb_lo[k] = 0xffffffffu; H.bb_hi[k] = 0u; }
+    H.periodic = periodic;
+    H.n_tripped = 0; H.next_item = 0;
+    for (int k = 0; k < 9; k++) { H.hinv[k] = 0.0; H.h[k] = 0.0; H.box_bits[k] = 0u; }
+    if (periodic) {
+        for (int k = 0; k < 9; k++) H.box_bits[k] = __float_as_uint(box[k]);
+        vl_box_inverse(box, H.h, H.hinv);
+    }
+}
+
+// Reference positions: mean over the sample frames (each unwrapped next to the first sample),
+// largest displacement of a sample from the mean, largest |raw coordinate|, bounding box.
+// 16 lanes per atom (lane = sample), 8 atoms per block.
+__global__ void __launch_bounds__(128) vl_sample(VlHeader* hdr, const float* __restrict__ xyz,
+                                                 const float* __restrict__ box, long long n_frames, int n,
+                                                 float4* __restrict__ ref_raw)
+{
+    __shared__ double hs[18];
+    __shared__ int box_ok;
+    const int n_samp = (int)(n_frames < VL_SAMPLES ? n_frames : VL_SAMPLES);
+    if (threadIdx.x < 18) hs[threadIdx.x] = threadIdx.x < 9 ? hdr->hinv[threadIdx.x] : hdr->h[threadIdx.x - 9];
+    if (threadIdx.x == 0) {
+        // the sampled frames must share the batch's unit cell (all frames are checked again by the
+        // frame kernel / the guard pass)
+        int ok = 1;
+        if (box != nullptr)
+            for (int k = 0; k < n_samp; k++) {
+                const long long f = n_samp > 1 ? (long long)k * (n_frames - 1) / (n_samp - 1) : 0;
+                for (int q = 0; q < 9; q++) ok = ok && (__float_as_uint(box[f * 9 + q]) == hdr->box_bits[q]);
+            }
+        box_ok = ok;
+    }
+    __syncthreads();
+    if (!box_ok) {
+        if (threadIdx.x == 0 && blockIdx.x == 0) { hdr->valid = 0; hdr->fail_code = 1; }
+        return;
+    }
+    const int k = threadIdx.x & 15;                       // sample of this lane
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 4);    // atom of this half warp
+    const int periodic = box != nullptr;
+    const bool live = i < n && k < n_samp;
+    float px = 0.f, py = 0.f, pz = 0.f;
+    if (live) {
+        const long long f = n_samp > 1 ? (long long)k * (n_frames - 1) / (n_samp - 1) : 0;
+        const float* p = xyz + ((size_t)f * (size_t)n + (size_t)i) * 3;
+        px = __ldg(p); py = __ldg(p + 1); pz = __ldg(p + 2);
+    }
+    // anchor: the first sample of the atom
+    const float ax = __shfl_sync(0xffffffffu, px, 0, 16), ay = __shfl_sync(0xffffffffu, py, 0, 16),
+                az = __shfl_sync(0xffffffffu, pz, 0, 16);
+    float ux = 0.f, uy = 0.f, uz = 0.f;
+    if (live) vl_unwrap(hs, hs + 9, periodic, px, py, pz, ax, ay, az, ux, uy, uz);
+    float sx = ux, sy = uy, sz = uz;
+#pragma unroll
+    for (int d = 8; d >= 1; d >>= 1) {
+        sx += __shfl_xor_sync(0xffffffffu, sx, d, 16);
+        sy += __shfl_xor_sync(0xffffffffu, sy, d, 16);
+        sz += __shfl_xor_sync(0xffffffffu, sz, d, 16);
+    }
+    const float inv = 1.0f / (float)n_samp;
+    const float mx = sx * inv, my = sy * inv, mz = sz * inv;
+    float dmax = 0.f, amax = 0.f;
+    if (live) {
+        const float ex = ux - mx, ey = uy - my, ez = uz - mz;
+        dmax = sqrtf(ex * ex + ey * ey + ez * ez);
+        amax = fmaxf(fabsf(px), fmaxf(fabsf(py), fabsf(pz)));
+        // NaN / Inf coordinates: the bits of +Inf exceed every finite value, vl_setup rejects them
+        if (!(dmax >= 0.f)) dmax = __int_as_float(0x7f800000);
+        if (!(amax >= 0.f)) amax = __int_as_float(0x7f800000);
+    }
+    if (i < n && k == 0) {
+        ref_raw[i] = make_float4(mx, my, mz, 0.f);
+        if (!periodic) {
+            atomicMin(&hdr->bb_lo[0], vl_ordered(mx)); atomicMax(&hdr->bb_hi[0], vl_ordered(mx));
+            atomicMin(&hdr->bb_lo[1], vl_ordered(my)); atomicMax(&hdr->bb_hi[1], vl_ordered(my));
+            atomicMin(&hdr->bb_lo[2], vl_ordered(mz)); atomicMax(&hdr->bb_hi[2], vl_ordered(mz));
+        }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, d));
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, d));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(&hdr->d_max_bits, __float_as_uint(dmax));
+        atomicMax(&hdr->a_max_bits, __float_as_uint(amax));
+    }
+}
+
+// skin, list radius, error bound, list grid, tiling (one thread)
+__global__ void vl_setup(VlHeader* hdr, const float* box, int n, float cutoff, float c2, float max_rlist_factor,
+                         int* cellcnt_unused)
+{
+    (void)cellcnt_unused;
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    VlHeader& H = *hdr;
+    if (!H.valid) return;
+    const float dmax = __uint_as_float(H.d_max_bits), amax = __uint_as_float(H.a_max_bits);
+    if (!(dmax < 1.0e6f) || !(amax < 1.0e6f)) { H.valid = 0; H.fail_code = 2; return; }
+    const float skin = 1.3f * dmax + 0.002f;
+    const float rlist = cutoff * 1.002f + 2.0f * skin + 1.0e-6f;
+    if (rlist > max_rlist_factor * cutoff) { H.valid = 0; H.fail_code = 3; return; }   // the list would not pay
+    // the guard compares in fp32 against a slightly smaller radius than the list was built for
+    H.skin2 = skin * skin * 0.9999f;
+    H.rlist = rlist;
+    H.a_assumed = 1.25f * amax + 0.5f;
+    float lo[3] = {0.f, 0.f, 0.f}, hi[3] = {0.f, 0.f, 0.f};
+    if (!H.periodic)
+        for (int k = 0; k < 3; k++) { lo[k] = vl_unordered(H.bb_lo[k]); hi[k] = vl_unordered(H.bb_hi[k]); }
+    make_grid(H.grid, H.periodic ? box : nullptr, (double)rlist, VL_MAXC, lo, hi);
+    if (H.periodic && !H.grid.distinct) { H.valid = 0; H.fail_code = 4; return; }     // < 3 list cells per dimension
+    // screening thresholds for every frame the guard admits
+    frame_margins(H.periodic ? box : nullptr, 1, H.a_assumed + skin, c2, cutoff, 0, H.c2_lo, H.c2_hi);
+    if (!(H.c2_lo > 0.f)) { H.valid = 0; H.fail_code = 5; return; }                   // no usable error bound
+    for (int id = 0; id < 27; id++) H.shift[id] = lattice_shift(H.periodic ? box : nullptr, id);
+    // tiles: blocks of tdim^3 cells; one tile for systems that fit a CTA
+    const GridS& G = H.grid;
+    int t;
+    if (n <= VL_SINGLE_TILE_ATOMS) {
+        t = max(G.nx, max(G.ny, G.nz));
+    } else {
+        const float apc = (float)n / (float)G.ncell;
+        t = 6;
+        while (t > 1 && (float)((t + 2) * (t + 2) * (t + 2)) * apc * 1.15f > (float)VL_MAX_SLOTS) t--;
+    }
+    H.tdim = t;
+    H.ntx = (G.nx + t - 1) / t; H.nty = (G.ny + t - 1) / t; H.ntz = (G.nz + t - 1) / t;
+    const long long nt = (long long)H.ntx * H.nty * H.ntz;
+    if (nt > VL_MAX_TILES) { H.valid = 0; H.fail_code = 6; return; }
+    H.n_tiles = (int)nt;
+}
+
+__global__ void __launch_bounds__(256) vl_zero_cells(const VlHeader* hdr, int* cellcnt)
+{
+    if (!hdr->valid) return;
+    const int ncell = hdr->grid.ncell;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c <= ncell; c += gridDim.x * blockDim.x) cellcnt[c] = 0;
+}
+
+__global__ void __launch_bounds__(256) vl_bin(const VlHeader* hdr, int n, const float4* __restrict__ ref_raw,
+                                              float4* __restrict__ ref_w, int* __restrict__ atomrank,
+                                              int* __restrict__ cellcnt)
+{
+    if (!hdr->valid) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const GridS& G = hdr->grid;
+    const float4 r = ref_raw[i];
+    float x = r.x, y = r.y, z = r.z;
+    const int c = cell_wrap(G, x, y, z);
+    if (!G.periodic) { x = r.x; y = r.y; z = r.z; }
+    ref_w[i] = make_float4(x, y, z, __int_as_float(c));
+    atomrank[i] = atomicAdd(&cellcnt[c], 1);
+}
+
+// exclusive scan over the cells (one CTA)
+__global__ void __launch_bounds__(1024) vl_scan_cells(const VlHeader* hdr, const int* __restrict__ cellcnt,
+                                                      int* __restrict__ cellptr, int n)
+{
+    if (!hdr->valid) return;
+    __shared__ int wsum[32];
+    __shared__ int carry;
+    const int ncell = hdr->grid.ncell;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < ncell; base += 1024) {
+        const int c = base + threadIdx.x;
+        const int v = c < ncell ? cellcnt[c] : 0;
+        int incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += u;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int w = wsum[lane];
+            int iw = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, iw, d);
+                if (lane >= d) iw += u;
+            }
+            wsum[lane] = iw - w;
+        }
+        __syncthreads();
+        const int excl = carry + wsum[warp] + incl - v;
+        if (c < ncell) cellptr[c] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) cellptr[ncell] = n;
+}
+
+__global__ void __launch_bounds__(256) vl_scatter(const VlHeader* hdr, int n, const float4* __restrict__ ref_w,
+                                                  const int* __restrict__ atomrank, const int* __restrict__ cellptr,
+                                                  const int2* __restrict__ meta, float4* __restrict__ sref,
+                                                  int2* __restrict__ smeta, int* __restrict__ scell)
+{
+    if (!hdr->valid) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 w = ref_w[i];
+    const int c = __float_as_int(w.w);
+    const int pos = cellptr[c] + atomrank[i];
+    sref[pos] = make_float4(w.x, w.y, w.z, __int_as_float(i));
+    smeta[pos] = __ldg(&meta[i]);
+    scell[pos] = c;
+}
+
+__device__ __forceinline__ int vl_tile_of_cell(const VlHeader& H, int c)
+{
+    const GridS& G = H.grid;
+    const int cyz = c / G.nx, cx = c - cyz * G.nx, cz = cyz / G.ny, cy = cyz - cz * G.ny;
+    return ((cz / H.tdim) * H.nty + cy / H.tdim) * H.ntx + cx / H.tdim;
+}
+
+// tile of a residue = tile of the cell of its anchor (first used) atom: every atom pair of a
+// residue pair is then assigned to the same tile (the tile of the lower residue)
+__global__ void __launch_bounds__(256) vl_res_tiles(const VlHeader* hdr, int n_res_c, const int* __restrict__ res_anchor,
+                                                    const float4* __restrict__ ref_w, int* __restrict__ tile_of_res)
+{
+    if (!hdr->valid) return;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_res_c) return;
+    tile_of_res[r] = vl_tile_of_cell(*hdr, __float_as_int(ref_w[res_anchor[r]].w));
+}
+
+// Candidate pairs of the sorted position p (one WARP per position): q > p in the 27 neighbour
+// cells, reference minimum-image distance <= r_list, roles and residue exclusion.  The warp
+// counts its pairs, reserves room with one atomic and writes the records on a second sweep.
+// record: key = tile << 2 rbits | res_lo << rbits | res_hi,  value = atom_p | atom_q << 20 | shift id << 40
+__global__ void __launch_bounds__(256) vl_pairs(VlHeader* hdr, int n, int n_ignored, const float4* __restrict__ sref,
+                                                const int2* __restrict__ smeta, const int* __restrict__ scell,
+                                                const int* __restrict__ cellptr, const int* __restrict__ tile_of_res,
+                                                unsigned long long* __restrict__ rec_key,
+                                                unsigned long long* __restrict__ rec_val, long long entry_cap)
+{
+    if (!hdr->valid) return;
+    const int p = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+    if (p >= n) return;
+    const int lane = threadIdx.x & 31;
+    const unsigned ltmask = (1u << lane) - 1u;
+    const VlHeader& H = *hdr;
+    const GridS& G = H.grid;
+    const float4 pi = sref[p];
+    const int2 mi = smeta[p];
+    const int c = scell[p];
+    const int cyz = c / G.nx, cx = c - cyz * G.nx, cz = cyz / G.ny, cy = cyz - cz * G.ny;
+    const float r2 = H.rlist * H.rlist * 1.00001f;
+    const unsigned role_i = (unsigned)mi.y >> 30;
+    const int res_i = mi.y & 0x3fffffff;
+    const int rbits = H.rbits;
+    // lane l < 27 owns stencil cell l
+    int my_lo = 0, my_hi = 0, my_id = CT_NOSHIFT;
+    if (lane < 27) {
+        const int dz = lane / 9 - 1, dy = (lane / 3) % 3 - 1, dx = lane % 3 - 1;
+        int x = cx + dx, y = cy + dy, z = cz + dz, wx = 0, wy = 0, wz = 0;
+        bool ok = true;
+        if (x < 0) { x += G.nx; wx = -1; ok = G.periodic; } else if (x >= G.nx) { x -= G.nx; wx = 1; ok = G.periodic; }
+        if (y < 0) { y += G.ny; wy = -1; ok = ok && G.periodic; } else if (y >= G.ny) { y -= G.ny; wy = 1; ok = ok && G.periodic; }
+        if (z < 0) { z += G.nz; wz = -1; ok = ok && G.periodic; } else if (z >= G.nz) { z -= G.nz; wz = 1; ok = ok && G.periodic; }
+        if (ok) {
+            const int D = (z * G.ny + y) * G.nx + x;
+            my_lo = max(cellptr[D], p + 1);
+            my_hi = cellptr[D + 1];
+            my_id = (wx + 1) + 3 * (wy + 1) + 9 * (wz + 1);
+        }
+    }
+    long long base = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        int found = 0;
+        for (int l = 0; l < 27; l++) {
+            const int lo = __shfl_sync(0xffffffffu, my_lo, l), hi = __shfl_sync(0xffffffffu, my_hi, l);
+            if (lo >= hi) continue;
+            const int id = __shfl_sync(0xffffffffu, my_id, l);
+            const float4 sh = H.shift[id];
+            for (int q0 = lo; q0 < hi; q0 += 32) {
+                const int q = q0 + lane;
+                bool take = false;
+                float4 pj = make_float4(0.f, 0.f, 0.f, 0.f);
+                int2 mj = make_int2(0, 0);
+                if (q < hi) {
+                    pj = sref[q];
+                    const float ex = (pj.x + sh.x) - pi.x, ey = (pj.y + sh.y) - pi.y, ez = (pj.z + sh.z) - pi.z;
+                    if (ex * ex + ey * ey + ez * ez <= r2) {
+                        mj = smeta[q];
+                        const int dk = mi.x - mj.x;
+                        const unsigned role_j = (unsigned)mj.y >> 30;
+                        take = (dk < 0 ? -dk : dk) > n_ignored &&              // residue exclusion (also same residue)
+                               ((((role_i & (role_j >> 1)) | (role_j & (role_i >> 1))) & 1u) != 0u);
+                    }
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, take);
+                if (pass == 1 && take) {
+                    const long long out = base + found + __popc(m & ltmask);
+                    if (out < entry_cap) {
+                        const int res_j = mj.y & 0x3fffffff;
+                        const int rlo = min(res_i, res_j), rhi = max(res_i, res_j);
+                        const unsigned long long tile = (unsigned long long)tile_of_res[rlo];
+                        rec_key[out] = (tile << (2 * rbits)) | ((unsigned long long)rlo << rbits) | (unsigned long long)rhi;
+                        rec_val[out] = (unsigned long long)__float_as_int(pi.w) |
+                                       ((unsigned long long)__float_as_int(pj.w) << 20) | ((unsigned long long)id << 40);
+                    }
+                }
+                found += __popc(m);
+            }
+        }
+        if (pass == 0) {
+            if (found == 0) return;
+            int b = 0;
+            if (lane == 0) b = atomicAdd(&hdr->n_entries, found);
+            base = (long long)__shfl_sync(0xffffffffu, b, 0);
+        }
+    }
+}
+
+__global__ void vl_after_pairs(VlHeader* hdr, long long entry_cap)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0 || !hdr->valid) return;
+    if ((long long)hdr->n_entries > entry_cap) { hdr->valid = 0; hdr->fail_code = 7; }
+    if (hdr->n_entries <= 0) { hdr->valid = 0; hdr->fail_code = 8; }     // no pairs (or overflow): the fall back handles it
+}
+
+// segment bookkeeping after the run-length encode of the sorted record keys
+__global__ void vl_after_rle(VlHeader* hdr, const unsigned long long* __restrict__ seg_key, const int* __restrict__ n_runs)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0 || !hdr->valid) return;
+    int runs = n_runs[0];
+    if (runs > 0 && seg_key[runs - 1] == VL_PAD) runs--;         // the padding forms one trailing run
+    hdr->n_segs = runs;
+}
+
+// bundle sort key of every segment: tile, then length descending
+__global__ void __launch_bounds__(256) vl_seg_sortkeys(const VlHeader* hdr, const unsigned long long* __restrict__ seg_key,
+                                                       const int* __restrict__ seg_len, unsigned long long* __restrict__ skey,
+                                                       int* __restrict__ sval, long long cap)
+{
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= cap) return;
+    const bool live = hdr->valid && s < hdr->n_segs;
+    const unsigned lmax = (1u << VL_LEN_BITS) - 1u;
+    skey[s] = live ? (((seg_key[s] >> (2 * hdr->rbits)) << VL_LEN_BITS) |
+                      (unsigned long long)(lmax - min((unsigned)seg_len[s], lmax)))
+                   : VL_PAD;
+    sval[s] = (int)s;
+}
+
+// lower bound of `key` in the sorted array a[0, n)
+__device__ __forceinline__ int vl_lower_bound(const unsigned long long* __restrict__ a, int n, unsigned long long key)
+{
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (a[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// last index t in [0, n) with a[t] <= v (a ascending, a[0] <= v)
+__device__ __forceinline__ int vl_last_le(const int* __restrict__ a, int n, int v)
+{
+    int lo = 0, hi = n;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (a[mid] <= v) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ int vl_block_excl_scan(int v, int* wsum, int& total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += u;
+    }
+    __syncthreads();
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const int w = wsum[lane];
+        int iw = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, iw, d);
+            if (lane >= d) iw += u;
+        }
+        wsum[lane] = iw - w;
+        if (lane == 31) wsum[32] = iw;
+    }
+    __syncthreads();
+    total = wsum[32];
+    return wsum[warp] + incl - v;
+}
+
+// Layout of tiles / bundles / rows (one CTA of 1024 threads).
+__global__ void __launch_bounds__(1024) vl_layout(VlHeader* hdr, VlTile* __restrict__ tiles,
+                                                  const unsigned long long* __restrict__ skey_sorted,
+                                                  const int* __restrict__ sval_sorted, const int* __restrict__ seg_len,
+                                                  int* __restrict__ tile_seg0, int* __restrict__ tile_bundle0,
+                                                  int* __restrict__ bundle_row0, long long bundle_cap, long long row_cap)
+{
+    if (!hdr->valid) return;
+    __shared__ int wsum[33];
+    __shared__ int carry_a;
+    const int n_tiles = hdr->n_tiles, n_segs = hdr->n_segs;
+    for (int t = threadIdx.x; t <= n_tiles; t += 1024)
+        tile_seg0[t] = t == n_tiles ? n_segs : vl_lower_bound(skey_sorted, n_segs, (unsigned long long)t << VL_LEN_BITS);
+    __syncthreads();
+    // bundles per tile -> tile_bundle0
+    if (threadIdx.x == 0) carry_a = 0;
+    __syncthreads();
+    for (int base = 0; base < n_tiles; base += 1024) {
+        const int t = base + threadIdx.x;
+        const int nb = t < n_tiles ? (tile_seg0[t + 1] - tile_seg0[t] + 31) / 32 : 0;
+        int total;
+        const int excl = vl_block_excl_scan(nb, wsum, total);
+        if (t < n_tiles) tile_bundle0[t] = carry_a + excl;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_a += total;
+        __syncthreads();
+    }
+    const int n_bundles = carry_a;
+    if (threadIdx.x == 0) { tile_bundle0[n_tiles] = n_bundles; hdr->n_bundles = n_bundles; }
+    if ((long long)n_bundles > bundle_cap) {
+        if (threadIdx.x == 0) { hdr->valid = 0; hdr->fail_code = 9; }
+        return;
+    }
+    __syncthreads();
+    // rows per bundle (global running offsets; tile-relative ones are derived below)
+    if (threadIdx.x == 0) carry_a = 0;
+    __syncthreads();
+    for (int base = 0; base < n_bundles; base += 1024) {
+        const int g = base + threadIdx.x;
+        int rows = 0;
+        if (g < n_bundles) {
+            const int t = vl_last_le(tile_bundle0, n_tiles, g);
+            const int first = tile_seg0[t] + 32 * (g - tile_bundle0[t]);
+            // segments are sorted by length (descending, lengths clipped to VL_LEN_BITS in the key):
+            // the first one is the longest unless it was clipped, then look at all 32
+            int maxlen = seg_len[sval_sorted[first]];
+            if (maxlen >= (1 << VL_LEN_BITS) - 1) {
+                const int last = min(first + 32, tile_seg0[t + 1]);
+                for (int s = first; s < last; s++) maxlen = max(maxlen, seg_len[sval_sorted[s]]);
+            }
+            rows = (maxlen + 3) / 4;
+        }
+        int total_r;
+        const int er = vl_block_excl_scan(rows, wsum, total_r);
+        if (g < n_bundles) bundle_row0[g] = carry_a + er;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_a += total_r;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        bundle_row0[n_bundles] = carry_a;
+        hdr->n_rows = carry_a;
+        if ((long long)carry_a > row_cap) { hdr->valid = 0; hdr->fail_code = 10; }
+    }
+    __syncthreads();
+    if (!hdr->valid) return;
+    for (int t = threadIdx.x; t < n_tiles; t += 1024) {
+        VlTile T;
+        const int b0 = tile_bundle0[t], b1 = tile_bundle0[t + 1];
+        T.seg0 = tile_seg0[t]; T.n_segs = tile_seg0[t + 1] - tile_seg0[t];
+        T.row0 = bundle_row0[b0]; T.n_rows = bundle_row0[b1] - bundle_row0[b0];
+        T.slot0 = 0; T.n_slots = 0;
+        tiles[t] = T;
+        if (T.n_rows > VL_MAX_ROWS || T.n_segs > VL_MAX_SEGS || b1 - b0 > 0xffff) { hdr->valid = 0; hdr->fail_code = 11; }
+    }
+}
+
+// the two slots every list entry refers to: key = tile << (abits + 5) | atom << 5 | shift id
+// (single-tile lists: every used atom becomes a slot as well -- keys [2 cap, 2 cap + n) -- so that
+// the guard inside the frame kernel sees ALL atoms: an atom without list pairs that wanders off
+// its reference position could otherwise come into contact unnoticed)
+__global__ void __launch_bounds__(256) vl_slot_keys(const VlHeader* hdr, const unsigned long long* __restrict__ rec_key,
+                                                    const unsigned long long* __restrict__ rec_val,
+                                                    unsigned long long* __restrict__ slot_key, long long cap, int n)
+{
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n)
+        slot_key[2 * cap + e] = (hdr->valid && hdr->n_tiles == 1)
+                                    ? (((unsigned long long)e << 5) | (unsigned long long)CT_NOSHIFT) : VL_PAD;
+    if (e >= cap) return;
+    unsigned long long k0 = VL_PAD, k1 = VL_PAD;
+    if (hdr->valid && e < hdr->n_entries) {
+        const unsigned long long tile = (rec_key[e] >> (2 * hdr->rbits)) << (hdr->abits + 5), v = rec_val[e];
+        k0 = tile | ((v & 0xfffffull) << 5) | (unsigned long long)CT_NOSHIFT;
+        k1 = tile | (((v >> 20) & 0xfffffull) << 5) | ((v >> 40) & 31ull);
+    }
+    slot_key[2 * e] = k0;
+    slot_key[2 * e + 1] = k1;
+}
+
+__global__ void __launch_bounds__(256) vl_slot_ranges(VlHeader* hdr, VlTile* __restrict__ tiles,
+                                                      const unsigned long long* __restrict__ slot_uniq,
+                                                      const int* __restrict__ n_uniq_ptr, int* __restrict__ tile_slot0,
+                                                      long long slot_cap)
+{
+    if (!hdr->valid) return;
+    int n_uniq = n_uniq_ptr[1];
+    if (n_uniq > 0 && slot_uniq[n_uniq - 1] == VL_PAD) n_uniq--;
+    const int n_tiles = hdr->n_tiles, tb = hdr->abits + 5;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) {
+        hdr->n_slots = n_uniq;
+        if ((long long)n_uniq > slot_cap) { hdr->valid = 0; hdr->fail_code = 12; }
+    }
+    if (t > n_tiles) return;
+    const int s0 = t == n_tiles ? n_uniq : vl_lower_bound(slot_uniq, n_uniq, (unsigned long long)t << tb);
+    tile_slot0[t] = s0;
+    if (t < n_tiles) {
+        const int s1 = t + 1 == n_tiles ? n_uniq : vl_lower_bound(slot_uniq, n_uniq, (unsigned long long)(t + 1) << tb);
+        tiles[t].slot0 = s0;
+        tiles[t].n_slots = s1 - s0;
+        if (s1 - s0 > VL_MAX_SLOTS) { hdr->valid = 0; hdr->fail_code = 13; }
+    }
+}
+
+__global__ void __launch_bounds__(256) vl_slot_fill(const VlHeader* hdr, const unsigned long long* __restrict__ slot_uniq,
+                                                    const float4* __restrict__ ref_w, unsigned* __restrict__ slot_word,
+                                                    float4* __restrict__ slot_ref, long long slot_cap)
+{
+    if (!hdr->valid) return;
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= hdr->n_slots || s >= slot_cap) return;
+    const unsigned long long k = slot_uniq[s];
+    const unsigned atom = (unsigned)((k >> 5) & ((1ull << hdr->abits) - 1ull)), id = (unsigned)(k & 31ull);
+    slot_word[s] = atom | (id << 24);
+    const float4 r = ref_w[atom];
+    slot_ref[s] = make_float4(r.x, r.y, r.z, 0.f);
+}
+
+// residue pair of every segment (length-sorted order)
+__global__ void __launch_bounds__(256) vl_seg_fill(const VlHeader* hdr, const int* __restrict__ sval_sorted,
+                                                   const unsigned long long* __restrict__ seg_key,
+                                                   uint2* __restrict__ seg_pair, long long cap)
+{
+    if (!hdr->valid) return;
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= hdr->n_segs || s >= cap) return;
+    const unsigned long long k = seg_key[sval_sorted[s]];
+    const int rbits = hdr->rbits;
+    const unsigned long long rmask = (1ull << rbits) - 1ull;
+    seg_pair[s] = make_uint2((unsigned)((k >> rbits) & rmask), (unsigned)(k & rmask));
+}
+
+// Entry words: one block of 128 threads per ROW (thread = lane * 4 + step).
+__global__ void __launch_bounds__(VL_ROW) vl_fill(const VlHeader* hdr, const VlTile* __restrict__ tiles,
+                                                  const int* __restrict__ tile_bundle0, const int* __restrict__ bundle_row0,
+                                                  const int* __restrict__ sval_sorted, const int* __restrict__ seg_len,
+                                                  const int* __restrict__ seg_start,
+                                                  const unsigned long long* __restrict__ rec_val,
+                                                  const unsigned long long* __restrict__ slot_uniq,
+                                                  const int* __restrict__ tile_slot0, unsigned short* __restrict__ row_bundle,
+                                                  unsigned* __restrict__ entries)
+{
+    if (!hdr->valid) return;
+    const int R = blockIdx.x;
+    if (R >= hdr->n_rows) return;
+    __shared__ int sh[4];          // bundle, tile, first row of the bundle
+    if (threadIdx.x == 0) {
+        const int g = vl_last_le(bundle_row0, hdr->n_bundles, R);
+        const int t = vl_last_le(tile_bundle0, hdr->n_tiles, g);
+        sh[0] = g; sh[1] = t; sh[2] = bundle_row0[g];
+        row_bundle[R] = (unsigned short)(g - tile_bundle0[t]);
+    }
+    __syncthreads();
+    const int g = sh[0], t = sh[1];
+    const VlTile T = tiles[t];
+    const int lane = threadIdx.x >> 2, step = (R - sh[2]) * 4 + (threadIdx.x & 3);
+    const int seg_rel = 32 * (g - tile_bundle0[t]) + lane;
+    const unsigned far_off = (unsigned)T.n_slots * 16u;                       // pads never pass the screen
+    unsigned word = far_off << 16;
+    if (seg_rel < T.n_segs) {
+        const int s = sval_sorted[T.seg0 + seg_rel];
+        if (step < seg_len[s]) {
+            const int tb = hdr->abits + 5;
+            const unsigned long long tkey = (unsigned long long)t << tb;
+            const unsigned long long* uniq = slot_uniq + tile_slot0[t];
+            const unsigned long long v = rec_val[seg_start[s] + step];
+            const unsigned long long k0 = tkey | ((v & 0xfffffull) << 5) | (unsigned long long)CT_NOSHIFT;
+            const unsigned long long k1 = tkey | (((v >> 20) & 0xfffffull) << 5) | ((v >> 40) & 31ull);
+            const unsigned si = (unsigned)vl_lower_bound(uniq, T.n_slots, k0);
+            const unsigned sj = (unsigned)vl_lower_bound(uniq, T.n_slots, k1);
+            word = (si * 16u) | ((sj * 16u) << 16);
+        }
+    }
+    entries[(size_t)R * VL_ROW + threadIdx.x] = word;
+}
+
+// ----- frame kernel --------------------------------------------------------------------------
+struct VlFrameParams {
+    const float* xyz;            // [n_frames][n][3]
+    const float* box;            // [n_frames][9] or nullptr
+    long long n_frames;
+    int n;
+    int n_res_c;
+    float c2;
+    int item_frames;             // frames per work item (<= VL_ITEM_FRAMES)
+    unsigned int* atom_table;    // dense [n][n] or nullptr
+    unsigned int* res_table;     // dense [n_res_c][n_res_c] or nullptr
+    unsigned long long* audit;   // [2] pairs audited, disagreements (VL_AUDIT) or nullptr
+};
+
+constexpr int VL_AUDIT = 1;      // template flag: run the exact arithmetic on EVERY listed pair and
+                                 // count decisions that differ from the screen's
+
+// dynamic shared memory of the frame kernel (bytes); the position array sits at offset 0 so that
+// the entry words are ready-made shared-memory addresses
+constexpr int VL_SM_POS = 0;                                           // float4 [VL_MAX_SLOTS + 1]
+constexpr int VL_SM_CNT = VL_SM_POS + (VL_MAX_SLOTS + 1) * 16;         // u32 [VL_MAX_ENTRIES / 4]
+constexpr int VL_SM_RES = VL_SM_CNT + VL_MAX_ENTRIES;                  // u8 [VL_MAX_SEGS]
+constexpr int VL_SM_FLAG = VL_SM_RES + VL_MAX_SEGS;                    // u32 [VL_MAX_SEGS / 32]
+constexpr int VL_SM_ROWB = VL_SM_FLAG + VL_MAX_SEGS / 8;               // u16 [VL_MAX_ROWS]
+constexpr int VL_SM_HDR = VL_SM_ROWB + VL_MAX_ROWS * 2;                // double[18], float4[27], misc
+constexpr int VL_SM_TOTAL = VL_SM_HDR + 18 * 8 + 27 * 16 + 64;
+
+__device__ __forceinline__ float4 vl_lds128(unsigned byte_off)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(byte_off));
+    return v;
+}
+
+template <int FLAGS>
+__global__ void __launch_bounds__(VL_THREADS, 1) vl_frames(const VlFrameParams p, const VlList L)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    float4* pos = reinterpret_cast<float4*>(smem + VL_SM_POS);
+    unsigned* cnt32 = reinterpret_cast<unsigned*>(smem + VL_SM_CNT);
+    unsigned char* rescnt = smem + VL_SM_RES;
+    unsigned* segflag = reinterpret_cast<unsigned*>(smem + VL_SM_FLAG);
+    unsigned short* rowb = reinterpret_cast<unsigned short*>(smem + VL_SM_ROWB);
+    double* hs = reinterpret_cast<double*>(smem + VL_SM_HDR);                  // hinv[9], h[9]
+    float4* shift_s = reinterpret_cast<float4*>(smem + VL_SM_HDR + 18 * 8);
+    int* misc = reinterpret_cast<int*>(smem + VL_SM_HDR + 18 * 8 + 27 * 16);   // [0] item, [1] row counter
+    const VlHeader& H = *L.hdr;
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (!H.valid) return;                       // every frame is on the fall-back list (vl_all_tripped)
+    const unsigned pos_base = (unsigned)__cvta_generic_to_shared(pos);
+    if (tid < 18) hs[tid] = tid < 9 ? H.hinv[tid] : H.h[tid - 9];
+    if (tid >= 32 && tid < 32 + 27) shift_s[tid - 32] = H.shift[tid - 32];
+    const int periodic = H.periodic;
+    const float skin2 = H.skin2, a_assumed = H.a_assumed, c2_lo = H.c2_lo, c2_hi = H.c2_hi;
+    const int n_tiles = H.n_tiles;
+    const bool multi_tile = n_tiles > 1;
+    const long long n_chunks = (p.n_frames + p.item_frames - 1) / p.item_frames;
+    const long long n_items = n_chunks * n_tiles;
+    const NlBox B = make_nlbox(p.box);          // the batch's unit cell (frames with another one trip)
+    unsigned long long audited = 0, disagreements = 0;
+    __syncthreads();
+
+    for (;;) {
+        if (tid == 0) misc[0] = atomicAdd(&L.hdr->next_item, 1);
+        __syncthreads();
+        const long long item = misc[0];
+        __syncthreads();
+        if (item >= n_items) break;
+        const int t = (int)(item % n_tiles);
+        const long long chunk = item / n_tiles;
+        const long long fa = chunk * p.item_frames, fb = min(p.n_frames, fa + p.item_frames);
+        const VlTile T = L.tiles[t];
+        if (T.n_rows == 0) continue;
+        // ---- tile set-up: counters, row -> bundle table, this thread's slots ----------------
+        for (int w = tid; w < T.n_rows * (VL_ROW / 4); w += VL_THREADS) cnt32[w] = 0u;
+        for (int w = tid; w < (T.n_segs + 3) / 4; w += VL_THREADS) reinterpret_cast<unsigned*>(rescnt)[w] = 0u;
+        for (int w = tid; w < (T.n_segs + 31) / 32; w += VL_THREADS) segflag[w] = 0u;
+        for (int w = tid; w < T.n_rows; w += VL_THREADS) rowb[w] = L.row_bundle[T.row0 + w];
+        if (tid == 0) pos[T.n_slots] = make_float4(3.0e18f, 0.f, 0.f, 0.f);      // the "far" slot of padding entries
+        // per slot only the word (atom | shift id << 24) and the prefetched raw coordinates stay in
+        // registers across the pair phase; the reference position is re-read (L2) every frame
+        unsigned s_word[VL_SPT];
+        float raw_x[VL_SPT], raw_y[VL_SPT], raw_z[VL_SPT];
+        const float4* slot_ref = L.slot_ref + T.slot0;
+#pragma unroll
+        for (int k = 0; k < VL_SPT; k++) {
+            const int s = tid + k * VL_THREADS;
+            s_word[k] = 0xffffffffu;
+            raw_x[k] = raw_y[k] = raw_z[k] = 0.f;
+            if (s < T.n_slots) {
+                s_word[k] = L.slot_word[T.slot0 + s];
+                const float* q = p.xyz + ((size_t)fa * (size_t)p.n + (size_t)(s_word[k] & 0xffffffu)) * 3;
+                raw_x[k] = __ldg(q); raw_y[k] = __ldg(q + 1); raw_z[k] = __ldg(q + 2);
+            }
+        }
+        const uint4* rows4 = reinterpret_cast<const uint4*>(L.entries + (size_t)T.row0 * VL_ROW);
+        const int n_rows = T.n_rows;
+        for (long long f = fa; f < fb; f++) {
+            // ---- residue pairs seen in the previous frame (set semantics per frame) ------------
+            for (int w = tid; w < (T.n_segs + 31) / 32; w += VL_THREADS) {
+                unsigned m = segflag[w];
+                if (m) {
+                    segflag[w] = 0u;
+                    while (m) {
+                        const int b = __ffs(m) - 1;
+                        m &= m - 1;
+                        rescnt[w * 32 + b]++;
+                    }
+                }
+            }
+            if (tid == 0) misc[1] = 0;
+            // ---- this frame's slots: unwrap next to the reference, guard -----------------------
+            // (a frame is re-done by the fall back as a WHOLE: lists with several tiles take the
+            // decision from the guard pass vl_guard, which looks at every atom of the frame; a
+            // single tile holds every atom as a slot and decides here)
+            int trip = 0;
+            if (multi_tile) trip = L.frame_flag[f];
+            else if (p.box != nullptr && tid < 9)
+                trip = __float_as_uint(__ldg(&p.box[f * 9 + tid])) != H.box_bits[tid];
+#pragma unroll
+            for (int k = 0; k < VL_SPT; k++) {
+                if (s_word[k] != 0xffffffffu) {
+                    const int atom = (int)(s_word[k] & 0xffffffu);
+                    const float4 ref = __ldg(&slot_ref[tid + k * VL_THREADS]);
+                    const float4 sh = shift_s[s_word[k] >> 24];
+                    float x, y, z;
+                    vl_unwrap(hs, hs + 9, periodic, raw_x[k], raw_y[k], raw_z[k], ref.x, ref.y, ref.z, x, y, z);
+                    if (!multi_tile) {
+                        const float ex = x - ref.x, ey = y - ref.y, ez = z - ref.z;
+                        const float a = fmaxf(fabsf(raw_x[k]), fmaxf(fabsf(raw_y[k]), fabsf(raw_z[k])));
+                        // (negated comparisons: NaN coordinates trip)
+                        trip |= !(ex * ex + ey * ey + ez * ez <= skin2) || !(a <= a_assumed);
+                    }
+                    pos[tid + k * VL_THREADS] = make_float4(__fadd_rn(x, sh.x), __fadd_rn(y, sh.y), __fadd_rn(z, sh.z),
+                                                            __int_as_float(atom));
+                    if (f + 1 < fb) {           // prefetch the next frame under the pair phase
+                        const float* q = p.xyz + ((size_t)(f + 1) * (size_t)p.n + (size_t)atom) * 3;
+                        raw_x[k] = __ldg(q); raw_y[k] = __ldg(q + 1); raw_z[k] = __ldg(q + 2);
+                    }
+                }
+            }
+            trip = __syncthreads_or(trip);
+            if (trip) {
+                if (tid == 0 && !multi_tile) {
+                    const int w = atomicAdd(&L.hdr->n_tripped, 1);
+                    L.tripped[w] = (int)f;
+                }
+                __syncthreads();
+                continue;
+            }
+            // ---- pair phase: warps pull rows, VL_FETCH_ROWS at a time; the entry words of the next
+            //      trip are requested from L2 before the current ones are worked on ------------------
+            const float* frame = p.xyz + (size_t)f * (size_t)p.n * 3;
+            int r = 0;
+            if (lane == 0) r = vl_atoms_add(&misc[1], VL_FETCH_ROWS);
+            r = __shfl_sync(0xffffffffu, r, 0);
+            uint4 cur[VL_FETCH_ROWS];
+#pragma unroll
+            for (int k = 0; k < VL_FETCH_ROWS; k++)
+                cur[k] = r + k < n_rows ? __ldg(&rows4[(size_t)(r + k) * 32 + lane]) : make_uint4(0u, 0u, 0u, 0u);
+            unsigned prev_i = 0xffffffffu;           // first atom of the previous entry: its position is still in `a`
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            while (r < n_rows) {
+                int rn = 0;
+                if (lane == 0) rn = vl_atoms_add(&misc[1], VL_FETCH_ROWS);
+                rn = __shfl_sync(0xffffffffu, rn, 0);
+                uint4 nxt[VL_FETCH_ROWS];
+#pragma unroll
+                for (int k = 0; k < VL_FETCH_ROWS; k++)
+                    nxt[k] = rn + k < n_rows ? __ldg(&rows4[(size_t)(rn + k) * 32 + lane]) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                for (int k = 0; k < VL_FETCH_ROWS; k++) {
+                    if (r + k >= n_rows) break;
+                    const unsigned ew[4] = {cur[k].x, cur[k].y, cur[k].z, cur[k].w};
+                    unsigned c = 0u;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const unsigned oi = ew[q] & 0xffffu, oj = ew[q] >> 16;
+                        if (oi != prev_i) { a = vl_lds128(pos_base + oi); prev_i = oi; }
+                        const float4 b = vl_lds128(pos_base + oj);
+                        const float dx = __fsub_rn(b.x, a.x), dy = __fsub_rn(b.y, a.y), dz = __fsub_rn(b.z, a.z);
+                        const float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+                        bool hit = d2 <= c2_lo;
+                        const bool listed = oj != (unsigned)T.n_slots * 16u;     // not a padding entry
+                        if ((d2 < c2_hi && !hit) || ((FLAGS & VL_AUDIT) && listed)) {
+                            // ambiguous: MDTraj's arithmetic on the raw coordinates, direction slot i -> slot j
+                            // (the lower -> higher position of the list's cell order; DESIGN.md "direction")
+                            const float* pa = frame + 3 * (size_t)__float_as_int(a.w);
+                            const float* pb = frame + 3 * (size_t)__float_as_int(b.w);
+                            const float d2x = nl_d2_dyn(__ldg(pa), __ldg(pa + 1), __ldg(pa + 2), __ldg(pb),
+                                                        __ldg(pb + 1), __ldg(pb + 2), B);
+                            const bool exact = d2x <= p.c2;
+                            if (FLAGS & VL_AUDIT) {
+                                audited++;
+                                // the screen's decision must agree wherever it takes one
+                                if ((hit && !exact) || (!(d2 < c2_hi) && exact)) disagreements++;
+                            }
+                            hit = exact;
+                        }
+                        c += hit ? (1u << (8 * q)) : 0u;
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, c != 0u);
+                    if (c) cnt32[(r + k) * 32 + lane] += c;
+                    // the lanes of a row are the segments 32 b + lane of its bundle b: one flag word per
+                    // bundle (other rows of the bundle may be setting it at the same time)
+                    if (lane == 0 && m) {
+                        unsigned* fw = &segflag[rowb[r + k]];
+                        if ((*(volatile unsigned*)fw & m) != m) vl_reds_or(fw, m);
+                    }
+                }
+                r = rn;
+#pragma unroll
+                for (int k = 0; k < VL_FETCH_ROWS; k++) cur[k] = nxt[k];
+            }
+            __syncthreads();
+        }
+        // ---- end of the item: last frame's residue pairs, then flush the counters -------------
+        for (int w = tid; w < (T.n_segs + 31) / 32; w += VL_THREADS) {
+            unsigned m = segflag[w];
+            while (m) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                rescnt[w * 32 + b]++;
+            }
+        }
+        __syncthreads();
+        if (p.atom_table != nullptr) {
+            const unsigned* ent = L.entries + (size_t)T.row0 * VL_ROW;
+            for (int w = tid; w < T.n_rows * (VL_ROW / 4); w += VL_THREADS) {
+                const unsigned c = cnt32[w];
+                if (c == 0u) continue;
+                const uint4 e4 = *reinterpret_cast<const uint4*>(ent + (size_t)w * 4);
+                const unsigned ew[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const unsigned cq = (c >> (8 * q)) & 0xffu;
+                    if (cq) {
+                        const unsigned ia = L.slot_word[T.slot0 + ((ew[q] & 0xffffu) >> 4)] & 0xffffffu;
+                        const unsigned ib = L.slot_word[T.slot0 + (ew[q] >> 20)] & 0xffffffu;
+                        const unsigned lo = min(ia, ib), hi = max(ia, ib);
+                        atomicAdd(&p.atom_table[(size_t)lo * (size_t)p.n + (size_t)hi], cq);
+                    }
+                }
+            }
+        }
+        if (p.res_table != nullptr) {
+            for (int s = tid; s < T.n_segs; s += VL_THREADS) {
+                const unsigned c = rescnt[s];
+                if (c) {
+                    const uint2 rp = L.seg_pair[T.seg0 + s];
+                    atomicAdd(&p.res_table[(size_t)rp.x * (size_t)p.n_res_c + (size_t)rp.y], c);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if ((FLAGS & VL_AUDIT) && p.audit != nullptr) {
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            audited += __shfl_xor_sync(0xffffffffu, audited, d);
+            disagreements += __shfl_xor_sync(0xffffffffu, disagreements, d);
+        }
+        if (lane == 0) {
+            if (audited) atomicAdd(&p.audit[0], audited);
+            if (disagreements) atomicAdd(&p.audit[1], disagreements);
+        }
+    }
+}
+
+// Guard pass for lists with more than one tile: a frame is re-done by the fall back as a WHOLE,
+// so the trip decision is taken once per frame, over all atoms, before the frame kernel runs;
+// tripped frames get their flag set and every tile skips them.  (Single-tile lists check inside
+// the frame kernel: the tile sees every atom.)  grid = (atom blocks, frames).
+__global__ void __launch_bounds__(256) vl_guard(VlHeader* hdr, const float* __restrict__ xyz,
+                                                const float* __restrict__ box, long long f0, int n,
+                                                const float4* __restrict__ ref_w, int* __restrict__ frame_flag,
+                                                int* __restrict__ tripped)
+{
+    __shared__ double hs[18];
+    if (!hdr->valid || hdr->n_tiles <= 1) return;
+    if (threadIdx.x < 18) hs[threadIdx.x] = threadIdx.x < 9 ? hdr->hinv[threadIdx.x] : hdr->h[threadIdx.x - 9];
+    __syncthreads();
+    const long long f = f0 + blockIdx.y;
+    const int periodic = hdr->periodic;
+    const float skin2 = hdr->skin2, a_assumed = hdr->a_assumed;
+    int trip = 0;
+    if (box != nullptr && blockIdx.x == 0 && threadIdx.x < 9)
+        trip = __float_as_uint(__ldg(&box[f * 9 + threadIdx.x])) != hdr->box_bits[threadIdx.x];
+    const float* frame = xyz + (size_t)f * (size_t)n * 3;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float px = __ldg(&frame[3 * (size_t)i]), py = __ldg(&frame[3 * (size_t)i + 1]),
+                    pz = __ldg(&frame[3 * (size_t)i + 2]);
+        const float4 r = __ldg(&ref_w[i]);
+        float x, y, z;
+        vl_unwrap(hs, hs + 9, periodic, px, py, pz, r.x, r.y, r.z, x, y, z);
+        const float ex = x - r.x, ey = y - r.y, ez = z - r.z;
+        const float a = fmaxf(fabsf(px), fmaxf(fabsf(py), fabsf(pz)));
+        trip |= !(ex * ex + ey * ey + ez * ez <= skin2) || !(a <= a_assumed);
+    }
+    trip = __syncthreads_or(trip);
+    if (trip && threadIdx.x == 0 && atomicExch(&frame_flag[f], 1) == 0) {
+        const int w = atomicAdd(&hdr->n_tripped, 1);
+        tripped[w] = (int)f;
+    }
+}
+
+// an invalid list puts every frame on the fall-back list
+__global__ void __launch_bounds__(256) vl_all_tripped(VlHeader* hdr, int* __restrict__ tripped, long long n_frames)
+{
+    if (hdr->valid) return;
+    for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < n_frames;
+         f += (long long)gridDim.x * blockDim.x)
+        tripped[f] = (int)f;
+    if (blockIdx.x == 0 && threadIdx.x == 0) hdr->n_tripped = (int)n_frames;
+}
+
+// ----- host driver ----------------------------------------------------------------------------
+struct VlJob {
+    const float* xyz; const float* box; long long n_frames;
+    int n; int n_res_c;
+    const int2* meta;            // [n] {ekey, res_c | role << 30}
+    const int* res_anchor;       // [n_res_c] first used atom of each compact residue
+    float cutoff; float c2; int n_ignored;
+    unsigned int* atom_table; unsigned int* res_table;
+    int audit; unsigned long long* d_audit;
+    float max_rlist_factor;      // lists with r_list > factor * cutoff are not built (all frames fall back)
+};
+
+#define VL_CK(call)                                                                  \
+    do {                                                                             \
+        cudaError_t e_ = (call);                                                     \
+        if (e_ != cudaSuccess) {                                                     \
+            err = std::string(#call) + " failed: " + cudaGetErrorString(e_);         \
+            return -2;                                                               \
+        }                                                                            \
+    } while (0)
+
+inline int vl_bits(long long v)       // bits needed for values in [0, v)
+{
+    int b = 1;
+    while ((1ll << b) < v) b++;
+    return b;
+}
+
+inline int vl_ensure(VlScratch& S, int n, int n_res_c, long long n_frames, std::string& err)
+{
+    if (S.cap_atoms < n || S.frame_cap < n_frames) {
+        vl_free(S);
+        const long long E = std::max<long long>((long long)n * 80, 1 << 15);
+        const long long frames = std::max<long long>(n_frames, 1024);
+        if (2 * E + n > 0x7fffffffll) { err = "system too large for the pair-list path"; return -4; }
+        S.entry_cap = E;
+        S.L.entry_cap = E;
+        S.L.slot_cap = (long long)n * 12 + 8192;
+        S.L.row_cap = E / 32 + 1024;
+        S.bundle_cap = E / 32 + VL_MAX_TILES;
+        VL_CK(cudaMalloc(&S.L.hdr, sizeof(VlHeader)));
+        VL_CK(cudaMalloc(&S.L.tiles, sizeof(VlTile) * VL_MAX_TILES));
+        VL_CK(cudaMalloc(&S.L.slot_word, sizeof(unsigned) * (size_t)S.L.slot_cap));
+        VL_CK(cudaMalloc(&S.L.slot_ref, sizeof(float4) * (size_t)S.L.slot_cap));
+        VL_CK(cudaMalloc(&S.L.row_bundle, sizeof(unsigned short) * (size_t)S.L.row_cap));
+        VL_CK(cudaMalloc(&S.L.entries, sizeof(unsigned) * (size_t)S.L.row_cap * VL_ROW));
+        VL_CK(cudaMalloc(&S.L.seg_pair, sizeof(uint2) * (size_t)E));
+        VL_CK(cudaMalloc(&S.L.tripped, sizeof(int) * (size_t)frames));
+        VL_CK(cudaMalloc(&S.L.frame_flag, sizeof(int) * (size_t)frames));
+        VL_CK(cudaMalloc(&S.ref_raw, sizeof(float4) * (size_t)n));
+        VL_CK(cudaMalloc(&S.ref_w, sizeof(float4) * (size_t)n));
+        VL_CK(cudaMalloc(&S.atomrank, sizeof(int) * (size_t)n));
+        VL_CK(cudaMalloc(&S.cellcnt, sizeof(int) * (size_t)(VL_MAXC + 1)));
+        VL_CK(cudaMalloc(&S.cellptr, sizeof(int) * (size_t)(VL_MAXC + 1)));
+        VL_CK(cudaMalloc(&S.sref, sizeof(float4) * (size_t)n));
+        VL_CK(cudaMalloc(&S.smeta, sizeof(int2) * (size_t)n));
+        VL_CK(cudaMalloc(&S.scell, sizeof(int) * (size_t)n));
+        VL_CK(cudaMalloc(&S.tile_of_res, sizeof(int) * (size_t)std::max(n_res_c, n)));
+        for (int k = 0; k < 2; k++) {
+            VL_CK(cudaMalloc(&S.rec_key[k], 8 * (size_t)E));
+            VL_CK(cudaMalloc(&S.rec_val[k], 8 * (size_t)E));
+            VL_CK(cudaMalloc(&S.skey[k], 8 * (size_t)E));
+            VL_CK(cudaMalloc(&S.sval[k], 4 * (size_t)E));
+            VL_CK(cudaMalloc(&S.slot_key[k], 8 * (size_t)(2 * E + n)));
+        }
+        VL_CK(cudaMalloc(&S.seg_key, 8 * (size_t)E));
+        VL_CK(cudaMalloc(&S.seg_len, 4 * (size_t)E));
+        VL_CK(cudaMalloc(&S.seg_start, 4 * (size_t)(E + 1)));
+        VL_CK(cudaMalloc(&S.n_runs, 4 * 2));
+        VL_CK(cudaMalloc(&S.slot_uniq, 8 * (size_t)(2 * E + n)));
+        VL_CK(cudaMalloc(&S.tile_seg0, 4 * (VL_MAX_TILES + 1)));
+        VL_CK(cudaMalloc(&S.tile_bundle0, 4 * (VL_MAX_TILES + 1)));
+        VL_CK(cudaMalloc(&S.tile_slot0, 4 * (VL_MAX_TILES + 1)));
+        VL_CK(cudaMalloc(&S.bundle_row0, 4 * (size_t)(S.bundle_cap + 1)));
+        VL_CK(cudaMallocHost(&S.h_info, 4 * 4));
+        size_t need = 0, t = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, t, S.rec_key[0], S.rec_key[1], S.rec_val[0], S.rec_val[1], (int)E, 0, 64);
+        need = std::max(need, t);
+        cub::DeviceRadixSort::SortPairs(nullptr, t, S.skey[0], S.skey[1], S.sval[0], S.sval[1], (int)E, 0, 64);
+        need = std::max(need, t);
+        cub::DeviceRadixSort::SortKeys(nullptr, t, S.slot_key[0], S.slot_key[1], (int)(2 * E + n), 0, 64);
+        need = std::max(need, t);
+        cub::DeviceRunLengthEncode::Encode(nullptr, t, S.rec_key[1], S.seg_key, S.seg_len, S.n_runs, (int)E);
+        need = std::max(need, t);
+        cub::DeviceSelect::Unique(nullptr, t, S.slot_key[1], S.slot_uniq, S.n_runs + 1, (int)(2 * E + n));
+        need = std::max(need, t);
+        cub::DeviceScan::ExclusiveSum(nullptr, t, S.seg_len, S.seg_start, (int)E);
+        need = std::max(need, t);
+        VL_CK(cudaMalloc(&S.cub_tmp, need + 256));
+        S.cub_bytes = need + 256;
+        S.cap_atoms = n;
+        S.frame_cap = frames;
+    }
+    return 0;
+}
+
+// Build the list of a batch (asynchronous, everything stays on the device).
+inline int vl_build(const VlJob& job, VlScratch& S, cudaStream_t st, std::string& err, int& launches)
+{
+    const int n = job.n;
+    const long long E = S.entry_cap;
+    const int periodic = job.box != nullptr;
+    const bool single = n <= VL_SINGLE_TILE_ATOMS;
+    // sort keys only carry the bits their fields need (fewer radix passes); the all-ones padding
+    // still sorts last: no live key has all of its compared bits set
+    const int rbits = vl_bits(job.n_res_c + 1), abits = vl_bits(n + 1), tbits = single ? 0 : 12;
+    vl_init<<<1, 1, 0, st>>>(S.L.hdr, job.box, periodic, rbits, abits);
+    vl_sample<<<(n + 7) / 8, 128, 0, st>>>(S.L.hdr, job.xyz, job.box, job.n_frames, n, S.ref_raw);
+    vl_setup<<<1, 1, 0, st>>>(S.L.hdr, job.box, n, job.cutoff, job.c2, job.max_rlist_factor, nullptr);
+    vl_zero_cells<<<64, 256, 0, st>>>(S.L.hdr, S.cellcnt);
+    vl_bin<<<(n + 255) / 256, 256, 0, st>>>(S.L.hdr, n, S.ref_raw, S.ref_w, S.atomrank, S.cellcnt);
+    vl_scan_cells<<<1, 1024, 0, st>>>(S.L.hdr, S.cellcnt, S.cellptr, n);
+    vl_scatter<<<(n + 255) / 256, 256, 0, st>>>(S.L.hdr, n, S.ref_w, S.atomrank, S.cellptr, job.meta, S.sref, S.smeta,
+                                                S.scell);
+    vl_res_tiles<<<(job.n_res_c + 255) / 256, 256, 0, st>>>(S.L.hdr, job.n_res_c, job.res_anchor, S.ref_w, S.tile_of_res);
+    VL_CK(cudaMemsetAsync(S.rec_key[0], 0xff, 8 * (size_t)E, st));
+    vl_pairs<<<(n + 7) / 8, 256, 0, st>>>(S.L.hdr, n, job.n_ignored, S.sref, S.smeta, S.scell, S.cellptr, S.tile_of_res,
+                                          S.rec_key[0], S.rec_val[0], E);
+    vl_after_pairs<<<1, 1, 0, st>>>(S.L.hdr, E);
+    size_t tb = S.cub_bytes;
+    VL_CK(cub::DeviceRadixSort::SortPairs(S.cub_tmp, tb, S.rec_key[0], S.rec_key[1], S.rec_val[0], S.rec_val[1], (int)E, 0,
+                                          2 * rbits + tbits, st));
+    VL_CK(cudaMemsetAsync(S.seg_len, 0, 4 * (size_t)E, st));
+    VL_CK(cudaMemsetAsync(S.n_runs, 0, 8, st));
+    tb = S.cub_bytes;
+    VL_CK(cub::DeviceRunLengthEncode::Encode(S.cub_tmp, tb, S.rec_key[1], S.seg_key, S.seg_len, S.n_runs, (int)E, st));
+    vl_after_rle<<<1, 1, 0, st>>>(S.L.hdr, S.seg_key, S.n_runs);
+    tb = S.cub_bytes;
+    VL_CK(cub::DeviceScan::ExclusiveSum(S.cub_tmp, tb, S.seg_len, S.seg_start, (int)E, st));
+    vl_seg_sortkeys<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(S.L.hdr, S.seg_key, S.seg_len, S.skey[0], S.sval[0], E);
+    tb = S.cub_bytes;
+    VL_CK(cub::DeviceRadixSort::SortPairs(S.cub_tmp, tb, S.skey[0], S.skey[1], S.sval[0], S.sval[1], (int)E, 0,
+                                          VL_LEN_BITS + tbits, st));
+    vl_layout<<<1, 1024, 0, st>>>(S.L.hdr, S.L.tiles, S.skey[1], S.sval[1], S.seg_len, S.tile_seg0, S.tile_bundle0,
+                                  S.bundle_row0, S.bundle_cap, S.L.row_cap);
+    const long long n_keys = 2 * E + n;
+    vl_slot_keys<<<(unsigned)((std::max<long long>(E, n) + 255) / 256), 256, 0, st>>>(S.L.hdr, S.rec_key[1], S.rec_val[1],
+                                                                                      S.slot_key[0], E, n);
+    tb = S.cub_bytes;
+    VL_CK(cub::DeviceRadixSort::SortKeys(S.cub_tmp, tb, S.slot_key[0], S.slot_key[1], (int)n_keys, 0, abits + 5 + tbits, st));
+    tb = S.cub_bytes;
+    VL_CK(cub::DeviceSelect::Unique(S.cub_tmp, tb, S.slot_key[1], S.slot_uniq, S.n_runs + 1, (int)n_keys, st));
+    vl_slot_ranges<<<(VL_MAX_TILES + 1 + 255) / 256, 256, 0, st>>>(S.L.hdr, S.L.tiles, S.slot_uniq, S.n_runs, S.tile_slot0,
+                                                                   S.L.slot_cap);
+    vl_slot_fill<<<(unsigned)((S.L.slot_cap + 255) / 256), 256, 0, st>>>(S.L.hdr, S.slot_uniq, S.ref_w, S.L.slot_word,
+                                                                         S.L.slot_ref, S.L.slot_cap);
+    vl_seg_fill<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(S.L.hdr, S.sval[1], S.seg_key, S.L.seg_pair, E);
+    vl_fill<<<(unsigned)S.L.row_cap, VL_ROW, 0, st>>>(S.L.hdr, S.L.tiles, S.tile_bundle0, S.bundle_row0, S.sval[1],
+                                                      S.seg_len, S.seg_start, S.rec_val[1], S.slot_uniq, S.tile_slot0,
+                                                      S.L.row_bundle, S.L.entries);
+    VL_CK(cudaGetLastError());
+    launches += 24;
+    return 0;
+}
+
+// Walk the list over the frames of the job; frames that cannot use it end up on S.L.tripped
+// (count in hdr->n_tripped) for the caller's fall back.
+inline int vl_run_frames(const VlJob& job, VlScratch& S, int sm_count, cudaStream_t st, std::string& err, int& launches)
+{
+    static bool attr_set[2] = {false, false};
+    if (!attr_set[0]) {
+        VL_CK(cudaFuncSetAttribute(vl_frames<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, VL_SM_TOTAL));
+        attr_set[0] = true;
+    }
+    if (job.audit && !attr_set[1]) {
+        VL_CK(cudaFuncSetAttribute(vl_frames<VL_AUDIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, VL_SM_TOTAL));
+        attr_set[1] = true;
+    }
+    vl_all_tripped<<<64, 256, 0, st>>>(S.L.hdr, S.L.tripped, job.n_frames);
+    if (job.n > VL_SINGLE_TILE_ATOMS) {
+        VL_CK(cudaMemsetAsync(S.L.frame_flag, 0, sizeof(int) * (size_t)job.n_frames, st));
+        const int blocks = std::max(1, std::min((job.n + 255) / 256, 64));
+        for (long long f0 = 0; f0 < job.n_frames; f0 += 32768) {
+            const unsigned nf = (unsigned)std::min<long long>(32768, job.n_frames - f0);
+            vl_guard<<<dim3(blocks, nf), 256, 0, st>>>(S.L.hdr, job.xyz, job.box, f0, job.n, S.ref_w, S.L.frame_flag,
+                                                       S.L.tripped);
+            launches++;
+        }
+    }
+    VlFrameParams p;
+    p.xyz = job.xyz; p.box = job.box; p.n_frames = job.n_frames; p.n = job.n; p.n_res_c = job.n_res_c; p.c2 = job.c2;
+    // a whole number of rounds of work items over the SMs (rounded UP: never one item more than
+    // that), long enough to amortise the tile set-up / flush
+    const long long tiles_guess = job.n <= VL_SINGLE_TILE_ATOMS ? 1 : std::max<long long>(1, job.n / 700);
+    const long long rounds = tiles_guess > 1 ? 2 : 4;
+    long long item = (job.n_frames * tiles_guess + rounds * sm_count - 1) / (rounds * sm_count);
+    item = std::max<long long>(4, std::min<long long>(item, VL_ITEM_FRAMES));
+    p.item_frames = (int)std::min<long long>(item, std::max<long long>(job.n_frames, 1));
+    p.atom_table = job.atom_table; p.res_table = job.res_table; p.audit = job.d_audit;
+    if (job.audit) vl_frames<VL_AUDIT><<<sm_count, VL_THREADS, VL_SM_TOTAL, st>>>(p, S.L);
+    else vl_frames<0><<<sm_count, VL_THREADS, VL_SM_TOTAL, st>>>(p, S.L);
+    VL_CK(cudaGetLastError());
+    launches += 2;
+    return 0;
+}
+
+}  // namespace cmb
