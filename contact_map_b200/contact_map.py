@@ -507,8 +507,13 @@ def _table_kind(table):
 
 def _tables_to_pairs(engine, atom_table, res_table, used):
     """Sparse export of the device tables -> (atom PairTable, residue PairTable) in REAL indices."""
+    return _exports_to_pairs(engine, engine.export_many([atom_table, res_table]), used)
+
+
+def _exports_to_pairs(engine, exports, used):
+    """(flat index, count) exports of the atom and residue tables -> PairTables in REAL indices."""
     n = engine.n_used
-    (idx, cnt), (ridx, rcnt) = engine.export_many([atom_table, res_table])
+    (idx, cnt), (ridx, rcnt) = exports
     lo, hi = np.divmod(idx, n)
     atoms = PairTable(used[lo], used[hi], cnt.astype(np.int64))
     rc = engine.n_res_c

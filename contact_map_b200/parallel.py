@@ -81,6 +81,35 @@ def reduce_tables(tables, group=None, dst=None):
     return tables
 
 
+# dense tables above this many bytes are not all-reduced: their sparse exports are merged instead
+# (the 100 000-atom system has a 40 GB atom table holding ~3 M non-zero entries)
+SPARSE_REDUCE_BYTES = 1 << 30
+
+
+def reduce_export(engine, tables, dst=None, group=None):
+    """Sum the count tables over all ranks AND export them: the multi-GPU replacement of the
+    reference's ``reduce_all_results`` (frequency_task.py:125-141).  Returns
+    ``[(flat index int64[], count uint32[]), ...]`` sorted by index on the ranks that receive the
+    result (every rank for ``dst=None``), ``None`` on the others.
+
+    Small dense tables: ONE in-place collective over the tables (NCCL over NVLink), then the
+    sparse export on the result rank.  Large dense tables and hashed tables: every rank exports
+    its own non-zero entries (a few tens of MB) and the sparse lists are all-gathered and merged
+    by key -- moving 40 GB per rank through the switch to add up 3 M numbers would cost more than
+    the frames themselves."""
+    rank, world_size = world()
+    if world_size == 1:
+        return engine.export_many(tables)
+    dense_bytes = sum(t.numel() * 4 for t in tables if not hasattr(t, "slots"))
+    if any(hasattr(t, "slots") for t in tables) or dense_bytes > SPARSE_REDUCE_BYTES:
+        local = engine.export_many(tables)
+        device = tables[0].slots.device if hasattr(tables[0], "slots") else tables[0].device
+        merged = [merge_sparse(idx, cnt, device, group) for idx, cnt in local]
+        return merged if dst is None or rank == dst else None
+    reduce_tables(tables, group=group, dst=dst)
+    return engine.export_many(tables) if dst is None or rank == dst else None
+
+
 def merge_sparse(idx, cnt, device, group=None):
     """Sum sparse (flat index, count) lists over all ranks: all-gather + sort + segment sum.
     Returns (index int64[], count uint32[]) sorted by index, identical on every rank."""
