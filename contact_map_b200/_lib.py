@@ -122,6 +122,10 @@ def lib():
     L.cmb_hash_rehash.argtypes = [vp, vp, i32, vp, i32, vp]
     L.cmb_frame_contacts.restype = i32
     L.cmb_frame_contacts.argtypes = [vp, vp, vp, i64, i64, vp, i64, vp, i64, vp, vp, vp, vp]
+    L.cmb_frame_contacts_host.restype = i32
+    L.cmb_frame_contacts_host.argtypes = [vp, vp, i32, vp, vp, i64, i64, i64, i32, vp, i64, vp, i64, vp]
+    L.cmb_keys_to_csr.restype = i32
+    L.cmb_keys_to_csr.argtypes = [vp, vp, i64, i64, i64, vp, vp, vp, vp, vp]
     L.cmb_sort_keys.restype = i32
     L.cmb_sort_keys.argtypes = [vp, vp, i64, vp]
     L.cmb_export_nonzero.restype = i32

@@ -40,6 +40,14 @@ class FrameCSR(object):
         self.j = np.asarray(j, dtype=np.int64)
 
     @classmethod
+    def from_arrays(cls, n_frames, ptr, i, j):
+        """Ready-made CSR arrays (``cmb_keys_to_csr``): nothing is recomputed on the host."""
+        self = cls.__new__(cls)
+        self.n_frames = int(n_frames)
+        self.ptr, self.i, self.j = ptr, i, j
+        return self
+
+    @classmethod
     def from_keys(cls, n_frames, keys, index_map):
         k = np.asarray(keys, dtype=np.uint64)                      # unsigned shifts: frame ids use bits 40..63
         index_map = np.asarray(index_map, dtype=np.int64)
@@ -69,44 +77,37 @@ class FrameCSR(object):
         if b == a:
             return PairTable.empty()
         base = int(self.j[a:b].max()) + 1
-        uniq, counts = np.unique(self.i[a:b] * base + self.j[a:b], return_counts=True)
+        uniq, counts = np.unique(self.i[a:b].astype(np.int64) * base + self.j[a:b], return_counts=True)
         return PairTable(uniq // base, uniq % base, counts.astype(np.int64))
 
 
-def _build_contacts(contact_object, trajectory, chunk_bytes=64 << 20):
+def _build_contacts(contact_object, trajectory):
     """GPU replacement of the reference's ``_build_contacts`` (contact_trajectory.py:7-44).
 
-    Returns (atom FrameCSR, residue FrameCSR) in REAL atom / residue indices.
+    Returns (atom FrameCSR, residue FrameCSR) in REAL atom / residue indices.  Host trajectories
+    stream through the engine's pinned double-buffered pipeline (``cmb_frame_contacts_host``; the
+    used atoms of a trajectory that still holds all atoms are gathered on the way), the keys are
+    sorted and turned into CSR arrays on the device, and only those arrays come back.
     """
     from .engine import get_engine
     engine = get_engine()
     used = _engine_system(contact_object, engine)
     xyz, box = _split_trajectory(trajectory)
-    xyz, box, on_device = _used_coordinates(xyz, box, used, contact_object.topology.n_atoms, engine)
+    xyz, box, on_device = _used_coordinates(xyz, box, used, contact_object.topology.n_atoms, engine,
+                                            keep_full_host=True)
     n_frames = xyz.shape[0]
-    if n_frames > KEY_MAX_FRAMES:
-        raise ValueError("ContactTrajectory handles at most %d frames per call (24-bit frame ids in "
+    if n_frames >= KEY_MAX_FRAMES:
+        raise ValueError("ContactTrajectory handles fewer than %d frames per call (24-bit frame ids in "
                          "the per-frame keys); split the trajectory and join the parts" % KEY_MAX_FRAMES)
-    chunk = max(1, min(n_frames, chunk_bytes // max(1, used.shape[0] * 12), (1 << 24) - 1))
-    atom_keys, res_keys = [], []
-    for f0 in range(0, n_frames, chunk):
-        f1 = min(n_frames, f0 + chunk)
-        if on_device:
-            cx, cb = xyz[f0:f1], (None if box is None else box[f0:f1])
-        else:
-            cx = torch.as_tensor(xyz[f0:f1]).to(engine.device, non_blocking=True)
-            cb = None if box is None else torch.as_tensor(box[f0:f1]).to(engine.device)
-        ak, rk = engine.frame_contacts(cx, cb, frame0=0)
-        # keys carry chunk-local frame ids; shift to trajectory frame numbers
-        atom_keys.append(ak if f0 == 0 else ak + (np.uint64(f0) << np.uint64(40)))
-        res_keys.append(rk if f0 == 0 else rk + (np.uint64(f0) << np.uint64(40)))
-    atom_keys = (atom_keys[0] if len(atom_keys) == 1 else np.concatenate(atom_keys)) if atom_keys \
-        else np.empty(0, np.uint64)
-    res_keys = (res_keys[0] if len(res_keys) == 1 else np.concatenate(res_keys)) if res_keys \
-        else np.empty(0, np.uint64)
-    atoms = FrameCSR.from_keys(n_frames, atom_keys, used)
-    residues = FrameCSR.from_keys(n_frames, res_keys, engine.residue_map.astype(np.int64))
-    return atoms, residues
+    if used.shape[0] > KEY_MAX_INDEX:
+        raise ValueError("per-frame keys hold 20-bit indices: at most %d used atoms" % KEY_MAX_INDEX)
+    res_map = engine.residue_map
+    if n_frames == 0:
+        empty = (np.zeros(1, np.int64), np.empty(0, np.int32), np.empty(0, np.int32))
+        return FrameCSR.from_arrays(0, *empty), FrameCSR.from_arrays(0, *empty)
+    gather = (not on_device) and xyz.shape[1] != used.shape[0]
+    atoms, residues = engine.frame_csr(xyz, box, used, res_map, used=used if gather else None)
+    return FrameCSR.from_arrays(n_frames, *atoms), FrameCSR.from_arrays(n_frames, *residues)
 
 
 class _LazyFrames(abc.Sequence):

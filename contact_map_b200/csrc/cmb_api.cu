@@ -65,6 +65,7 @@ struct cmb_ctx {
     unsigned long long* d_vl_audit = nullptr; // [2] audited pairs, disagreements
     int last_used_verlet = 0;
     int last_vl_slot = 0;
+    int vl_conservative = 0;                  // the optimistic tile size overflowed a tile of this system once
 
     // host pipeline
     float* d_stage_xyz[2] = {nullptr, nullptr};
@@ -83,6 +84,7 @@ struct cmb_ctx {
     int count_tests = 0;
     int pair_tasks = 1;
     int stage_pageable = 1;                   // pageable host input goes through threaded pinned staging
+    long long stage_chunk_frames = 0;         // frames per staging chunk of the host paths (0: automatic)
     int large_batch = 1;                      // global-memory cell path: 0 one frame at a time, 1 auto, 2 batched whenever possible
     int atom_log2 = 0, res_log2 = 0;          // hashed count tables when > 0 (cmb_set_table_mode)
     unsigned long long* d_hstats = nullptr;   // [4] new atom keys, new residue keys, parked hits, failed re-inserts
@@ -197,6 +199,11 @@ extern "C" int cmb_set_option(cmb_ctx* ctx, const char* name, int64_t value)
     if (!strcmp(name, "count_tests")) { ctx->count_tests = value != 0; return CMB_OK; }
     if (!strcmp(name, "pair_tasks")) { ctx->pair_tasks = value != 0; return CMB_OK; }
     if (!strcmp(name, "stage_pageable")) { ctx->stage_pageable = value != 0; return CMB_OK; }
+    if (!strcmp(name, "stage_chunk_frames")) {
+        if (value < 0) return fail(ctx, CMB_ERR_ARG, "stage_chunk_frames must be >= 0");
+        ctx->stage_chunk_frames = value;
+        return CMB_OK;
+    }
     if (!strcmp(name, "large_batch")) {
         if (value < 0 || value > 2) return fail(ctx, CMB_ERR_ARG, "large_batch must be 0, 1 or 2");
         ctx->large_batch = (int)value;
@@ -214,6 +221,7 @@ extern "C" int cmb_set_option(cmb_ctx* ctx, const char* name, int64_t value)
         return CMB_OK;
     }
     if (!strcmp(name, "verlet_audit")) { ctx->verlet_audit = value != 0; return CMB_OK; }
+    if (!strcmp(name, "verlet_conservative_tiles")) { ctx->vl_conservative = value != 0; return CMB_OK; }
     if (!strcmp(name, "verlet_max_rlist_pct")) {
         if (value < 101 || value > 400) return fail(ctx, CMB_ERR_ARG, "verlet_max_rlist_pct out of range");
         ctx->verlet_max_rlist_pct = (int)value;
@@ -239,6 +247,9 @@ extern "C" int cmb_get_stat(cmb_ctx* ctx, const char* name, int64_t* value)
     if (!strcmp(name, "max_cells")) { *value = ctx->fs_maxc; return CMB_OK; }
     if (!strcmp(name, "kernel_launches")) { *value = ctx->stats["kernel_launches"]; return CMB_OK; }
     if (!strcmp(name, "vl_used")) { *value = ctx->last_used_verlet; return CMB_OK; }
+    if (!strcmp(name, "vl_rebuilds")) { *value = ctx->stats["vl_rebuilds"]; return CMB_OK; }
+    if (!strcmp(name, "vl_rebuild_code")) { *value = ctx->stats["vl_rebuild_code"]; return CMB_OK; }
+    if (!strcmp(name, "vl_conservative")) { *value = ctx->vl_conservative; return CMB_OK; }
     if (!strncmp(name, "vl_", 3)) {
         // pair-list path diagnostics of the last launch (synchronises)
         const VlScratch& V = ctx->vl[ctx->last_vl_slot];
@@ -252,6 +263,7 @@ extern "C" int cmb_get_stat(cmb_ctx* ctx, const char* name, int64_t* value)
         if (!strcmp(name, "vl_tripped")) { *value = h.n_tripped; return CMB_OK; }
         if (!strcmp(name, "vl_entries")) { *value = h.n_entries; return CMB_OK; }
         if (!strcmp(name, "vl_tiles")) { *value = h.n_tiles; return CMB_OK; }
+        if (!strcmp(name, "vl_tdim")) { *value = h.tdim; return CMB_OK; }
         if (!strcmp(name, "vl_rows")) { *value = h.n_rows; return CMB_OK; }
         if (!strcmp(name, "vl_slots")) { *value = h.n_slots; return CMB_OK; }
         if (!strcmp(name, "vl_segs")) { *value = h.n_segs; return CMB_OK; }
@@ -419,6 +431,7 @@ extern "C" int cmb_set_system(cmb_ctx* ctx, int n_used, const int32_t* atom_res,
     }
 
     ctx->n = n_used;
+    ctx->vl_conservative = 0;
     ctx->cutoff_f = (float)cutoff;
     ctx->n_ignored = n_ignored;
     ctx->have_system = false;
@@ -531,8 +544,23 @@ static int launch_frames(cmb_ctx* ctx, const FrameJob& job, int slot, cudaStream
             vj.n_ignored = ctx->n_ignored; vj.atom_table = job.atom_table; vj.res_table = job.res_table;
             vj.audit = ctx->verlet_audit; vj.d_audit = ctx->d_vl_audit;
             vj.max_rlist_factor = 0.01f * (float)ctx->verlet_max_rlist_pct;
-            rc = vl_build(vj, V, stream, err, launches);
-            if (rc == 0) rc = vl_run_frames(vj, V, ctx->sm_count, stream, err, launches);
+            for (int attempt = 0; attempt < 2; attempt++) {
+                vj.conservative_tiles = ctx->vl_conservative;
+                rc = vl_build(vj, V, stream, err, launches);
+                if (rc == 0) rc = vl_run_frames(vj, V, ctx->sm_count, stream, err, launches);
+                if (rc != 0 || ctx->path == 0 || ctx->vl_conservative) break;
+                // lists of several tiles: the outcome is read back (the fall back below needs the
+                // tripped frames on the host anyway).  A tile that overflowed the frame kernel's
+                // shared memory with the optimistic tile size (nothing was counted then: every
+                // frame is on the fall-back list) gets the list rebuilt with the pessimistic one.
+                CK(cudaMemcpyAsync(V.h_info + 1, &V.L.hdr->valid, sizeof(int), cudaMemcpyDeviceToHost, stream));
+                CK(cudaMemcpyAsync(V.h_info + 2, &V.L.hdr->fail_code, sizeof(int), cudaMemcpyDeviceToHost, stream));
+                CK(cudaStreamSynchronize(stream));
+                if (V.h_info[1] != 0 || V.h_info[2] < 9 || V.h_info[2] > 13) break;
+                ctx->vl_conservative = 1;
+                ctx->stats["vl_rebuilds"] += 1;
+                ctx->stats["vl_rebuild_code"] = V.h_info[2];
+            }
             ctx->stats["kernel_launches"] += launches;
             if (rc != 0) return fail(ctx, rc, "%s", err.c_str());
             ctx->last_used_verlet = 1;
@@ -640,6 +668,7 @@ extern "C" int cmb_accumulate(cmb_ctx* ctx, const float* d_xyz, const float* d_b
 static int64_t pick_chunk(const cmb_ctx* ctx, int64_t n_frames, int64_t chunk_frames)
 {
     const size_t frame_bytes = (size_t)ctx->n * 12;
+    if (chunk_frames <= 0 && ctx->stage_chunk_frames > 0) chunk_frames = ctx->stage_chunk_frames;
     if (chunk_frames <= 0) {
         chunk_frames = (int64_t)((32ull << 20) / frame_bytes);
         // at least four chunks so copies and kernels overlap, but keep every SM busy
@@ -676,56 +705,6 @@ static int ensure_staging(cmb_ctx* ctx, int64_t chunk_frames, bool with_box)
     return CMB_OK;
 }
 
-static int accumulate_staged(cmb_ctx* ctx, const float* h_xyz_full, int n_total, const int32_t* h_used,
-                             const float* h_box, int64_t n_frames, int64_t chunk_frames, int n_threads,
-                             uint32_t* d_atom_table, uint32_t* d_res_table);
-
-extern "C" int cmb_accumulate_host(cmb_ctx* ctx, const float* h_xyz, const float* h_box, int64_t n_frames,
-                                   int64_t chunk_frames, uint32_t* d_atom_table, uint32_t* d_res_table)
-{
-    if (!ctx) return CMB_ERR_ARG;
-    if (!ctx->have_system) return fail(ctx, CMB_ERR_STATE, "cmb_set_system has not been called");
-    if (n_frames <= 0) return CMB_OK;
-    if (!h_xyz) return fail(ctx, CMB_ERR_ARG, "xyz is NULL");
-    CK(cudaSetDevice(ctx->device));
-    if (ctx->stage_pageable) {
-        // pageable memory (an ordinary numpy array, a memory-mapped file): cudaMemcpyAsync would
-        // stage it synchronously chunk by chunk; host threads copying into the pinned staging
-        // buffers while earlier chunks are transferred and processed keep the pipeline full
-        cudaPointerAttributes attr;
-        const cudaError_t e = cudaPointerGetAttributes(&attr, h_xyz);
-        if (e != cudaSuccess) cudaGetLastError();
-        if (e != cudaSuccess || attr.type == cudaMemoryTypeUnregistered)
-            return accumulate_staged(ctx, h_xyz, ctx->n, nullptr, h_box, n_frames, chunk_frames, 0, d_atom_table,
-                                     d_res_table);
-    }
-    const size_t frame_bytes = (size_t)ctx->n * 12;
-    chunk_frames = pick_chunk(ctx, n_frames, chunk_frames);
-    int rc0 = ensure_staging(ctx, chunk_frames, h_box != nullptr);
-    if (rc0 != CMB_OK) return rc0;
-    int c = 0;
-    for (int64_t f0 = 0; f0 < n_frames; f0 += chunk_frames, c++) {
-        const int s = c & 1;
-        const int64_t nf = std::min<int64_t>(chunk_frames, n_frames - f0);
-        // stream order on streams[s] serialises reuse of staging buffer s
-        CK(cudaMemcpyAsync(ctx->d_stage_xyz[s], h_xyz + (size_t)f0 * ctx->n * 3, (size_t)nf * frame_bytes,
-                           cudaMemcpyHostToDevice, ctx->streams[s]));
-        if (h_box)
-            CK(cudaMemcpyAsync(ctx->d_stage_box[s], h_box + (size_t)f0 * 9, (size_t)nf * 36,
-                               cudaMemcpyHostToDevice, ctx->streams[s]));
-        FrameJob job;
-        memset(&job, 0, sizeof(job));
-        job.xyz = ctx->d_stage_xyz[s]; job.box = h_box ? ctx->d_stage_box[s] : nullptr;
-        job.n_frames = nf; job.frame0 = f0;
-        job.atom_table = d_atom_table; job.res_table = d_res_table;
-        int rc = launch_frames(ctx, job, s, ctx->streams[s]);
-        if (rc != CMB_OK) return rc;
-    }
-    CK(cudaStreamSynchronize(ctx->streams[0]));
-    CK(cudaStreamSynchronize(ctx->streams[1]));
-    return CMB_OK;
-}
-
 // pack out[f][i][:] = full[f][used[i]][:] for frames [f0, f0 + nf), split over host threads
 static void gather_chunk(const float* full, int n_total, const int32_t* used, int n_used, int64_t f0,
                          int64_t nf, float* out, int n_threads)
@@ -758,29 +737,28 @@ static void gather_chunk(const float* full, int n_total, const int32_t* used, in
     for (auto& th : pool) th.join();
 }
 
-extern "C" int cmb_accumulate_host_gather(cmb_ctx* ctx, const float* h_xyz_full, int n_total,
-                                          const int32_t* h_used, const float* h_box, int64_t n_frames,
-                                          int64_t chunk_frames, int n_threads, uint32_t* d_atom_table,
-                                          uint32_t* d_res_table)
+static bool host_pointer_is_pinned(const void* p)
 {
-    if (!ctx) return CMB_ERR_ARG;
-    if (!ctx->have_system) return fail(ctx, CMB_ERR_STATE, "cmb_set_system has not been called");
-    if (n_frames <= 0) return CMB_OK;
-    if (!h_xyz_full || !h_used || n_total < ctx->n) return fail(ctx, CMB_ERR_ARG, "bad gather arguments");
-    for (int i = 0; i < ctx->n; i++)
-        if (h_used[i] < 0 || h_used[i] >= n_total || (i > 0 && h_used[i] <= h_used[i - 1]))
-            return fail(ctx, CMB_ERR_ARG, "used atom indices must be ascending and inside [0, n_total)");
-    return accumulate_staged(ctx, h_xyz_full, n_total, h_used, h_box, n_frames, chunk_frames, n_threads, d_atom_table,
-                             d_res_table);
+    cudaPointerAttributes attr;
+    const cudaError_t e = cudaPointerGetAttributes(&attr, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return attr.type != cudaMemoryTypeUnregistered;
 }
 
-// host threads pack chunk k + 1 into pinned staging while chunk k is copied and processed
-// (h_used == nullptr: all n_total == n atoms, a plain copy)
-static int accumulate_staged(cmb_ctx* ctx, const float* h_xyz_full, int n_total, const int32_t* h_used,
-                             const float* h_box, int64_t n_frames, int64_t chunk_frames, int n_threads,
-                             uint32_t* d_atom_table, uint32_t* d_res_table)
+// Stream a HOST trajectory through the frame kernels, chunk by chunk over two streams: the copy of
+// chunk k + 1 overlaps the kernels of chunk k.  `proto` says what the kernels produce (count tables
+// and / or per-frame keys appended to caller-owned device buffers through proto.ext_counters).
+//   direct: the frames are read by cudaMemcpyAsync straight from the caller's (pinned) buffer;
+//   staged: host threads pack chunk k + 1 into the context's pinned staging buffers -- gathering
+//           the used atoms if h_used != nullptr -- while chunk k is copied and processed (pageable
+//           memory, memory-mapped files, trajectories that still hold all atoms).
+static int stream_host_frames(cmb_ctx* ctx, const float* h_xyz_full, int n_total, const int32_t* h_used,
+                              const float* h_box, int64_t n_frames, int64_t chunk_frames, int n_threads,
+                              const FrameJob& proto)
 {
     CK(cudaSetDevice(ctx->device));
+    const bool direct = h_used == nullptr && n_total == ctx->n &&
+                        (!ctx->stage_pageable || host_pointer_is_pinned(h_xyz_full));
     if (n_threads <= 0) {
         n_threads = (int)std::thread::hardware_concurrency();
         if (n_threads > 16) n_threads = 16;
@@ -790,34 +768,38 @@ static int accumulate_staged(cmb_ctx* ctx, const float* h_xyz_full, int n_total,
     chunk_frames = pick_chunk(ctx, n_frames, chunk_frames);
     int rc0 = ensure_staging(ctx, chunk_frames, h_box != nullptr);
     if (rc0 != CMB_OK) return rc0;
-    const size_t need_pinned = (size_t)chunk_frames * frame_bytes;
-    if (ctx->pinned_bytes < need_pinned) {
-        for (int s = 0; s < 2; s++) {
-            if (ctx->h_pinned[s]) CK(cudaFreeHost(ctx->h_pinned[s]));
-            ctx->h_pinned[s] = nullptr;
-            CK(cudaMallocHost(&ctx->h_pinned[s], need_pinned));
+    if (!direct) {
+        const size_t need_pinned = (size_t)chunk_frames * frame_bytes;
+        if (ctx->pinned_bytes < need_pinned) {
+            for (int s = 0; s < 2; s++) {
+                if (ctx->h_pinned[s]) CK(cudaFreeHost(ctx->h_pinned[s]));
+                ctx->h_pinned[s] = nullptr;
+                CK(cudaMallocHost(&ctx->h_pinned[s], need_pinned));
+            }
+            ctx->pinned_bytes = need_pinned;
         }
-        ctx->pinned_bytes = need_pinned;
+        for (int s = 0; s < 2; s++)
+            if (!ctx->copy_done[s]) CK(cudaEventCreateWithFlags(&ctx->copy_done[s], cudaEventDisableTiming));
     }
-    for (int s = 0; s < 2; s++)
-        if (!ctx->copy_done[s]) CK(cudaEventCreateWithFlags(&ctx->copy_done[s], cudaEventDisableTiming));
     int c = 0;
     for (int64_t f0 = 0; f0 < n_frames; f0 += chunk_frames, c++) {
         const int s = c & 1;
         const int64_t nf = std::min<int64_t>(chunk_frames, n_frames - f0);
-        if (c >= 2) CK(cudaEventSynchronize(ctx->copy_done[s]));   // pinned buffer s is free again
-        gather_chunk(h_xyz_full, n_total, h_used, ctx->n, f0, nf, ctx->h_pinned[s], n_threads);
-        CK(cudaMemcpyAsync(ctx->d_stage_xyz[s], ctx->h_pinned[s], (size_t)nf * frame_bytes,
-                           cudaMemcpyHostToDevice, ctx->streams[s]));
-        CK(cudaEventRecord(ctx->copy_done[s], ctx->streams[s]));
+        const float* src = h_xyz_full + (size_t)f0 * (size_t)ctx->n * 3;
+        if (!direct) {
+            if (c >= 2) CK(cudaEventSynchronize(ctx->copy_done[s]));   // pinned buffer s is free again
+            gather_chunk(h_xyz_full, n_total, h_used, ctx->n, f0, nf, ctx->h_pinned[s], n_threads);
+            src = ctx->h_pinned[s];
+        }
+        // stream order on streams[s] serialises reuse of staging buffer s
+        CK(cudaMemcpyAsync(ctx->d_stage_xyz[s], src, (size_t)nf * frame_bytes, cudaMemcpyHostToDevice, ctx->streams[s]));
+        if (!direct) CK(cudaEventRecord(ctx->copy_done[s], ctx->streams[s]));
         if (h_box)
             CK(cudaMemcpyAsync(ctx->d_stage_box[s], h_box + (size_t)f0 * 9, (size_t)nf * 36,
                                cudaMemcpyHostToDevice, ctx->streams[s]));
-        FrameJob job;
-        memset(&job, 0, sizeof(job));
+        FrameJob job = proto;
         job.xyz = ctx->d_stage_xyz[s]; job.box = h_box ? ctx->d_stage_box[s] : nullptr;
-        job.n_frames = nf; job.frame0 = f0;
-        job.atom_table = d_atom_table; job.res_table = d_res_table;
+        job.n_frames = nf; job.frame0 = proto.frame0 + f0;
         int rc = launch_frames(ctx, job, s, ctx->streams[s]);
         if (rc != CMB_OK) return rc;
     }
@@ -826,6 +808,74 @@ static int accumulate_staged(cmb_ctx* ctx, const float* h_xyz_full, int n_total,
     return CMB_OK;
 }
 
+static int check_used(cmb_ctx* ctx, const int32_t* h_used, int n_total)
+{
+    for (int i = 0; i < ctx->n; i++)
+        if (h_used[i] < 0 || h_used[i] >= n_total || (i > 0 && h_used[i] <= h_used[i - 1]))
+            return fail(ctx, CMB_ERR_ARG, "used atom indices must be ascending and inside [0, n_total)");
+    return CMB_OK;
+}
+
+extern "C" int cmb_accumulate_host(cmb_ctx* ctx, const float* h_xyz, const float* h_box, int64_t n_frames,
+                                   int64_t chunk_frames, uint32_t* d_atom_table, uint32_t* d_res_table)
+{
+    if (!ctx) return CMB_ERR_ARG;
+    if (!ctx->have_system) return fail(ctx, CMB_ERR_STATE, "cmb_set_system has not been called");
+    if (n_frames <= 0) return CMB_OK;
+    if (!h_xyz) return fail(ctx, CMB_ERR_ARG, "xyz is NULL");
+    FrameJob proto;
+    memset(&proto, 0, sizeof(proto));
+    proto.atom_table = d_atom_table; proto.res_table = d_res_table;
+    return stream_host_frames(ctx, h_xyz, ctx->n, nullptr, h_box, n_frames, chunk_frames, 0, proto);
+}
+
+extern "C" int cmb_accumulate_host_gather(cmb_ctx* ctx, const float* h_xyz_full, int n_total,
+                                          const int32_t* h_used, const float* h_box, int64_t n_frames,
+                                          int64_t chunk_frames, int n_threads, uint32_t* d_atom_table,
+                                          uint32_t* d_res_table)
+{
+    if (!ctx) return CMB_ERR_ARG;
+    if (!ctx->have_system) return fail(ctx, CMB_ERR_STATE, "cmb_set_system has not been called");
+    if (n_frames <= 0) return CMB_OK;
+    if (!h_xyz_full || !h_used || n_total < ctx->n) return fail(ctx, CMB_ERR_ARG, "bad gather arguments");
+    int rc = check_used(ctx, h_used, n_total);
+    if (rc != CMB_OK) return rc;
+    FrameJob proto;
+    memset(&proto, 0, sizeof(proto));
+    proto.atom_table = d_atom_table; proto.res_table = d_res_table;
+    return stream_host_frames(ctx, h_xyz_full, n_total, h_used, h_box, n_frames, chunk_frames, n_threads, proto);
+}
+
+// Per-frame contact keys of a HOST trajectory (the host-side twin of cmb_frame_contacts): the
+// frames stream through the key kernels exactly as in cmb_accumulate_host[_gather]; every chunk
+// APPENDS its keys -- which carry trajectory frame numbers frame0 + f -- to the caller's device
+// buffers through the shared counters d_counts, so no chunk waits for the host.  The caller
+// sorts the buffers afterwards (cmb_sort_keys) and turns them into CSR arrays (cmb_keys_to_csr).
+extern "C" int cmb_frame_contacts_host(cmb_ctx* ctx, const float* h_xyz_full, int n_total, const int32_t* h_used,
+                                       const float* h_box, int64_t n_frames, int64_t frame0, int64_t chunk_frames,
+                                       int n_threads, uint64_t* d_atom_keys, int64_t atom_cap,
+                                       uint64_t* d_res_keys, int64_t res_cap, uint64_t* d_counts)
+{
+    if (!ctx) return CMB_ERR_ARG;
+    if (!ctx->have_system) return fail(ctx, CMB_ERR_STATE, "cmb_set_system has not been called");
+    if (!d_counts) return fail(ctx, CMB_ERR_ARG, "d_counts is NULL");
+    if (n_frames <= 0) return CMB_OK;
+    if (!h_xyz_full || n_total < ctx->n || (h_used == nullptr && n_total != ctx->n))
+        return fail(ctx, CMB_ERR_ARG, "bad trajectory arguments");
+    if (h_used) {
+        int rc = check_used(ctx, h_used, n_total);
+        if (rc != CMB_OK) return rc;
+    }
+    if (frame0 < 0 || frame0 + n_frames >= (1ll << 24))
+        return fail(ctx, CMB_ERR_LIMIT, "frame ids in emitted keys are limited to 2^24 per call");
+    FrameJob proto;
+    memset(&proto, 0, sizeof(proto));
+    proto.frame0 = frame0;
+    proto.atom_keys = (unsigned long long*)d_atom_keys; proto.atom_cap = d_atom_keys ? atom_cap : 0;
+    proto.res_keys = (unsigned long long*)d_res_keys; proto.res_cap = d_res_keys ? res_cap : 0;
+    proto.ext_counters = (unsigned long long*)d_counts;
+    return stream_host_frames(ctx, h_xyz_full, n_total, h_used, h_box, n_frames, chunk_frames, n_threads, proto);
+}
 
 // ---------------------------------------------------------------------------------
 // hashed count tables
@@ -935,6 +985,23 @@ extern "C" int cmb_frame_contacts(cmb_ctx* ctx, const float* d_xyz, const float*
     job.ext_counters = (unsigned long long*)d_counts;
     ctx->slot ^= 1;
     return launch_frames(ctx, job, ctx->slot, (cudaStream_t)stream);
+}
+
+extern "C" int cmb_keys_to_csr(cmb_ctx* ctx, const uint64_t* d_sorted_keys, int64_t n_keys, int64_t n_frames,
+                               int64_t frame0, const int32_t* d_index_map, int64_t* d_ptr, int32_t* d_i,
+                               int32_t* d_j, void* stream)
+{
+    if (!ctx) return CMB_ERR_ARG;
+    if (n_keys < 0 || n_frames < 1 || !d_ptr || (n_keys > 0 && (!d_sorted_keys || !d_i || !d_j)))
+        return fail(ctx, CMB_ERR_ARG, "bad CSR arguments");
+    CK(cudaSetDevice(ctx->device));
+    const long long blocks = std::max<long long>(1, (n_keys + 255) / 256);
+    k_keys_to_csr<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const unsigned long long*>(d_sorted_keys), n_keys, n_frames, frame0, d_index_map,
+        reinterpret_cast<long long*>(d_ptr), d_i, d_j);
+    CK(cudaGetLastError());
+    ctx->stats["kernel_launches"] += 1;
+    return CMB_OK;
 }
 
 extern "C" int cmb_boundary_pairs(cmb_ctx* ctx, const float* d_xyz, const float* d_box, int64_t n_frames,

@@ -97,6 +97,39 @@ __global__ void __launch_bounds__(256) k_hash_add(unsigned long long* __restrict
 }
 
 // ---------------------------------------------------------------------------------
+// sorted per-frame keys -> CSR arrays (the container of contact_trajectory.py:7-44 as arrays):
+// ptr[f] = first key of frame f (ptr[n_frames] = n_keys), i / j = the pair in REAL indices
+// (index_map[compact index], or the compact index itself).  One thread per key; the thread of
+// the first key of a frame also fills the ptr entries of the empty frames before it.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_keys_to_csr(const unsigned long long* __restrict__ keys, long long n_keys,
+                                                     long long n_frames, long long frame0,
+                                                     const int* __restrict__ index_map, long long* __restrict__ ptr,
+                                                     int* __restrict__ out_i, int* __restrict__ out_j)
+{
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k == 0 && n_keys == 0)
+        for (long long f = 0; f <= n_frames; f++) ptr[f] = 0;
+    if (k >= n_keys) return;
+    const unsigned long long key = keys[k];
+    long long f = (long long)(key >> 40) - frame0;
+    f = f < 0 ? 0 : (f >= n_frames ? n_frames - 1 : f);          // (keys of other frames cannot occur)
+    long long fprev = -1;
+    if (k > 0) {
+        fprev = (long long)(keys[k - 1] >> 40) - frame0;
+        fprev = fprev < 0 ? 0 : (fprev >= n_frames ? n_frames - 1 : fprev);
+    }
+    for (long long g = fprev + 1; g <= f; g++) ptr[g] = k;
+    if (k == n_keys - 1)
+        for (long long g = f + 1; g <= n_frames; g++) ptr[g] = n_keys;
+    const int lo = (int)((key >> 20) & 0xfffffull), hi = (int)(key & 0xfffffull);
+    int a = lo, b = hi;
+    if (index_map != nullptr) { a = __ldg(&index_map[lo]); b = __ldg(&index_map[hi]); }
+    out_i[k] = a < b ? a : b;
+    out_j[k] = a < b ? b : a;
+}
+
+// ---------------------------------------------------------------------------------
 // sparse export of a uint32 count table (result container of contact_map.py:724-744)
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_export_nonzero(const unsigned int* __restrict__ table,

@@ -74,6 +74,7 @@ constexpr int VL_MAX_TILES = 4096;
 constexpr int VL_MAXC = 1 << 17;                         // cells of the list grid
 constexpr int VL_SAMPLES = 16;
 constexpr int VL_ITEM_FRAMES = 255;                      // byte counters: flush at least this often
+constexpr int VL_MIN_ITEM_FRAMES = 12;                   // shorter items would not amortise set-up and flush
 constexpr int VL_SINGLE_TILE_ATOMS = 3800;
 constexpr int VL_LEN_BITS = 20;                          // segment length field of the bundle sort key
 constexpr unsigned long long VL_PAD = ~0ull;
@@ -322,9 +323,8 @@ __global__ void __launch_bounds__(128) vl_sample(VlHeader* hdr, const float* __r
 
 // skin, list radius, error bound, list grid, tiling (one thread)
 __global__ void vl_setup(VlHeader* hdr, const float* box, int n, float cutoff, float c2, float max_rlist_factor,
-                         int* cellcnt_unused)
+                         int conservative_tiles)
 {
-    (void)cellcnt_unused;
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     VlHeader& H = *hdr;
     if (!H.valid) return;
@@ -352,9 +352,19 @@ __global__ void vl_setup(VlHeader* hdr, const float* box, int n, float cutoff, f
     if (n <= VL_SINGLE_TILE_ATOMS) {
         t = max(G.nx, max(G.ny, G.nz));
     } else {
+        // slots of a tile: its own atoms plus the partners of its pairs in the shell of cells around
+        // it.  A pair belongs to the tile of its lower residue, so about half the shell shows up
+        // (measured on the 100k-atom system: average tile = estimate x 1.0, fullest tile up to x 1.5).
+        // Should a tile of an unusual system still overflow (fail codes 10-13), the host rebuilds
+        // the list with the whole shell counted.
         const float apc = (float)n / (float)G.ncell;
         t = 6;
-        while (t > 1 && (float)((t + 2) * (t + 2) * (t + 2)) * apc * 1.15f > (float)VL_MAX_SLOTS) t--;
+        for (; t > 1; t--) {
+            const float core = (float)(t * t * t), halo = (float)((t + 2) * (t + 2) * (t + 2));
+            const float est = (conservative_tiles ? halo * 1.15f : 0.5f * (core + halo) * 1.5f) * apc;
+            // (rows: ~ 0.19 per slot of such a tile: 128 entries per row at ~ 70 % fill)
+            if (est <= (float)VL_MAX_SLOTS && (conservative_tiles || est * 0.19f <= (float)VL_MAX_ROWS)) break;
+        }
     }
     H.tdim = t;
     H.ntx = (G.nx + t - 1) / t; H.nty = (G.ny + t - 1) / t; H.ntz = (G.nz + t - 1) / t;
@@ -837,7 +847,7 @@ struct VlFrameParams {
     int n;
     int n_res_c;
     float c2;
-    int item_frames;             // frames per work item (<= VL_ITEM_FRAMES)
+    int rounds;                  // work items per SM the frame kernel aims at (it sizes the items itself)
     unsigned int* atom_table;    // dense [n][n] or nullptr
     unsigned int* res_table;     // dense [n_res_c][n_res_c] or nullptr
     unsigned long long* audit;   // [2] pairs audited, disagreements (VL_AUDIT) or nullptr
@@ -848,13 +858,16 @@ constexpr int VL_AUDIT = 1;      // template flag: run the exact arithmetic on E
 
 // dynamic shared memory of the frame kernel (bytes); the position array sits at offset 0 so that
 // the entry words are ready-made shared-memory addresses
+constexpr int VL_QCAP = 1024;                                          // ambiguous pairs parked per tile and frame
 constexpr int VL_SM_POS = 0;                                           // float4 [VL_MAX_SLOTS + 1]
 constexpr int VL_SM_CNT = VL_SM_POS + (VL_MAX_SLOTS + 1) * 16;         // u32 [VL_MAX_ENTRIES / 4]
 constexpr int VL_SM_RES = VL_SM_CNT + VL_MAX_ENTRIES;                  // u8 [VL_MAX_SEGS]
-constexpr int VL_SM_FLAG = VL_SM_RES + VL_MAX_SEGS;                    // u32 [VL_MAX_SEGS / 32]
-constexpr int VL_SM_ROWB = VL_SM_FLAG + VL_MAX_SEGS / 8;               // u16 [VL_MAX_ROWS]
-constexpr int VL_SM_HDR = VL_SM_ROWB + VL_MAX_ROWS * 2;                // double[18], float4[27], misc
+constexpr int VL_SM_FLAG = VL_SM_RES + VL_MAX_SEGS;                    // u32 [2][VL_MAX_SEGS / 32] (frame parity)
+constexpr int VL_SM_ROWB = VL_SM_FLAG + 2 * (VL_MAX_SEGS / 8);         // u16 [VL_MAX_ROWS]
+constexpr int VL_SM_QUEUE = VL_SM_ROWB + VL_MAX_ROWS * 2;              // uint2 [VL_QCAP]
+constexpr int VL_SM_HDR = VL_SM_QUEUE + VL_QCAP * 8;                   // double[18], float4[27], misc
 constexpr int VL_SM_TOTAL = VL_SM_HDR + 18 * 8 + 27 * 16 + 64;
+static_assert(VL_SM_TOTAL <= 232448, "frame kernel exceeds the 227 KB of shared memory a CTA can have");
 
 __device__ __forceinline__ float4 vl_lds128(unsigned byte_off)
 {
@@ -864,6 +877,32 @@ __device__ __forceinline__ float4 vl_lds128(unsigned byte_off)
     return v;
 }
 
+__device__ __forceinline__ int vl_lds32i(unsigned byte_off)
+{
+    int v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(byte_off));
+    return v;
+}
+
+// Exact decision of one parked (ambiguous) list entry and its accounting.  e.x = entry word (slot
+// byte offsets), e.y = row << 7 | lane << 2 | step of the entry inside its tile.  MDTraj's
+// arithmetic on the RAW coordinates of the frame, direction slot i -> slot j (the lower -> higher
+// position of the list's cell order; DESIGN.md "direction").  The counters of an entry belong to
+// the lane that walks it, which may be at work on the same word: shared-memory atomics here.
+__device__ __forceinline__ void vl_exact_account(uint2 e, const float* __restrict__ frame, const NlBox& B, float c2,
+                                                 unsigned pos_base, unsigned* cnt32, unsigned* segflag,
+                                                 const unsigned short* rowb)
+{
+    const float* pa = frame + 3 * (size_t)vl_lds32i(pos_base + (e.x & 0xffffu) + 12u);
+    const float* pb = frame + 3 * (size_t)vl_lds32i(pos_base + (e.x >> 16) + 12u);
+    const float d2x = nl_d2_dyn(__ldg(pa), __ldg(pa + 1), __ldg(pa + 2), __ldg(pb), __ldg(pb + 1), __ldg(pb + 2), B);
+    if (d2x <= c2) {
+        const unsigned row = e.y >> 7, ln = (e.y >> 2) & 31u, q = e.y & 3u;
+        atomicAdd(&cnt32[row * 32u + ln], 1u << (8u * q));
+        vl_reds_or(&segflag[rowb[row]], 1u << ln);
+    }
+}
+
 template <int FLAGS>
 __global__ void __launch_bounds__(VL_THREADS, 1) vl_frames(const VlFrameParams p, const VlList L)
 {
@@ -871,11 +910,13 @@ __global__ void __launch_bounds__(VL_THREADS, 1) vl_frames(const VlFrameParams p
     float4* pos = reinterpret_cast<float4*>(smem + VL_SM_POS);
     unsigned* cnt32 = reinterpret_cast<unsigned*>(smem + VL_SM_CNT);
     unsigned char* rescnt = smem + VL_SM_RES;
-    unsigned* segflag = reinterpret_cast<unsigned*>(smem + VL_SM_FLAG);
+    unsigned* segflag2 = reinterpret_cast<unsigned*>(smem + VL_SM_FLAG);       // [2][VL_MAX_SEGS / 32]
     unsigned short* rowb = reinterpret_cast<unsigned short*>(smem + VL_SM_ROWB);
+    uint2* queue = reinterpret_cast<uint2*>(smem + VL_SM_QUEUE);
     double* hs = reinterpret_cast<double*>(smem + VL_SM_HDR);                  // hinv[9], h[9]
     float4* shift_s = reinterpret_cast<float4*>(smem + VL_SM_HDR + 18 * 8);
-    int* misc = reinterpret_cast<int*>(smem + VL_SM_HDR + 18 * 8 + 27 * 16);   // [0] item, [1] row counter
+    // [0] item, [1] row counter, [2 + parity] parked pairs of the frame with that parity
+    int* misc = reinterpret_cast<int*>(smem + VL_SM_HDR + 18 * 8 + 27 * 16);
     const VlHeader& H = *L.hdr;
     const int tid = threadIdx.x, lane = tid & 31;
     if (!H.valid) return;                       // every frame is on the fall-back list (vl_all_tripped)
@@ -886,7 +927,13 @@ __global__ void __launch_bounds__(VL_THREADS, 1) vl_frames(const VlFrameParams p
     const float skin2 = H.skin2, a_assumed = H.a_assumed, c2_lo = H.c2_lo, c2_hi = H.c2_hi;
     const int n_tiles = H.n_tiles;
     const bool multi_tile = n_tiles > 1;
-    const long long n_chunks = (p.n_frames + p.item_frames - 1) / p.item_frames;
+    // work item = tile x range of frames: about p.rounds items per SM, of equal length, long enough
+    // to amortise the tile set-up / flush and short enough for the byte counters
+    long long n_chunks = max(((long long)p.rounds * gridDim.x + n_tiles - 1) / n_tiles,
+                             (p.n_frames + VL_ITEM_FRAMES - 1) / VL_ITEM_FRAMES);
+    n_chunks = max(1ll, min(n_chunks, (p.n_frames + VL_MIN_ITEM_FRAMES - 1) / VL_MIN_ITEM_FRAMES));
+    const long long item_frames = (p.n_frames + n_chunks - 1) / n_chunks;
+    n_chunks = (p.n_frames + item_frames - 1) / item_frames;
     const long long n_items = n_chunks * n_tiles;
     const NlBox B = make_nlbox(p.box);          // the batch's unit cell (frames with another one trip)
     unsigned long long audited = 0, disagreements = 0;
@@ -900,13 +947,14 @@ __global__ void __launch_bounds__(VL_THREADS, 1) vl_frames(const VlFrameParams p
         if (item >= n_items) break;
         const int t = (int)(item % n_tiles);
         const long long chunk = item / n_tiles;
-        const long long fa = chunk * p.item_frames, fb = min(p.n_frames, fa + p.item_frames);
+        const long long fa = chunk * item_frames, fb = min(p.n_frames, fa + item_frames);
         const VlTile T = L.tiles[t];
         if (T.n_rows == 0) continue;
+        const int flag_words = (T.n_segs + 31) / 32;
         // ---- tile set-up: counters, row -> bundle table, this thread's slots ----------------
         for (int w = tid; w < T.n_rows * (VL_ROW / 4); w += VL_THREADS) cnt32[w] = 0u;
         for (int w = tid; w < (T.n_segs + 3) / 4; w += VL_THREADS) reinterpret_cast<unsigned*>(rescnt)[w] = 0u;
-        for (int w = tid; w < (T.n_segs + 31) / 32; w += VL_THREADS) segflag[w] = 0u;
+        for (int w = tid; w < flag_words; w += VL_THREADS) { segflag2[w] = 0u; segflag2[VL_MAX_SEGS / 32 + w] = 0u; }
         for (int w = tid; w < T.n_rows; w += VL_THREADS) rowb[w] = L.row_bundle[T.row0 + w];
         if (tid == 0) pos[T.n_slots] = make_float4(3.0e18f, 0.f, 0.f, 0.f);      // the "far" slot of padding entries
         // per slot only the word (atom | shift id << 24) and the prefetched raw coordinates stay in
@@ -927,21 +975,37 @@ __global__ void __launch_bounds__(VL_THREADS, 1) vl_frames(const VlFrameParams p
         }
         const uint4* rows4 = reinterpret_cast<const uint4*>(L.entries + (size_t)T.row0 * VL_ROW);
         const int n_rows = T.n_rows;
-        for (long long f = fa; f < fb; f++) {
-            // ---- residue pairs seen in the previous frame (set semantics per frame) ------------
-            for (int w = tid; w < (T.n_segs + 31) / 32; w += VL_THREADS) {
-                unsigned m = segflag[w];
-                if (m) {
-                    segflag[w] = 0u;
+        // Per frame f: [phase 1] the pairs frame f-1 could not decide by screening (parked in
+        // `queue`) are decided exactly, one per thread, while every thread brings its slots of frame
+        // f into `pos`; barrier; [phase 2] the residue pairs seen in frame f-1 are folded into their
+        // counters, the rows of frame f are walked; barrier.  The "seen" flags and the queue
+        // counter alternate between two copies with the parity of the frame.
+        for (long long f = fa; f <= fb; f++) {
+            const int par = (int)((f - fa) & 1);
+            unsigned* flag_cur = segflag2 + par * (VL_MAX_SEGS / 32);
+            unsigned* flag_prev = segflag2 + (par ^ 1) * (VL_MAX_SEGS / 32);
+            // ---- phase 1a: parked pairs of the previous frame -----------------------------------
+            const int parked = f > fa ? min(misc[2 + (par ^ 1)], VL_QCAP) : 0;
+            if (parked > 0) {
+                const float* prev = p.xyz + (size_t)(f - 1) * (size_t)p.n * 3;
+                for (int w = tid; w < parked; w += VL_THREADS)
+                    vl_exact_account(queue[w], prev, B, p.c2, pos_base, cnt32, flag_prev, rowb);
+            }
+            if (f == fb) {
+                // after the last frame: fold its flags once the parked pairs are in
+                __syncthreads();
+                for (int w = tid; w < flag_words; w += VL_THREADS) {
+                    unsigned m = flag_prev[w];
                     while (m) {
                         const int b = __ffs(m) - 1;
                         m &= m - 1;
                         rescnt[w * 32 + b]++;
                     }
                 }
+                break;
             }
-            if (tid == 0) misc[1] = 0;
-            // ---- this frame's slots: unwrap next to the reference, guard -----------------------
+            if (tid == 0) { misc[1] = 0; misc[2 + par] = 0; }
+            // ---- phase 1b: this frame's slots: unwrap next to the reference, guard ---------------
             // (a frame is re-done by the fall back as a WHOLE: lists with several tiles take the
             // decision from the guard pass vl_guard, which looks at every atom of the frame; a
             // single tile holds every atom as a slot and decides here)
@@ -949,6 +1013,8 @@ __global__ void __launch_bounds__(VL_THREADS, 1) vl_frames(const VlFrameParams p
             if (multi_tile) trip = L.frame_flag[f];
             else if (p.box != nullptr && tid < 9)
                 trip = __float_as_uint(__ldg(&p.box[f * 9 + tid])) != H.box_bits[tid];
+            // (the parked pairs above read the atom index in pos[].w while other threads rewrite
+            // their slots: a slot's index never changes, and the 16 bytes are written by one store)
 #pragma unroll
             for (int k = 0; k < VL_SPT; k++) {
                 if (s_word[k] != 0xffffffffu) {
@@ -972,6 +1038,18 @@ __global__ void __launch_bounds__(VL_THREADS, 1) vl_frames(const VlFrameParams p
                 }
             }
             trip = __syncthreads_or(trip);
+            // ---- phase 2a: residue pairs seen in the previous frame (set semantics per frame) ----
+            for (int w = tid; w < flag_words; w += VL_THREADS) {
+                unsigned m = flag_prev[w];
+                if (m) {
+                    flag_prev[w] = 0u;
+                    while (m) {
+                        const int b = __ffs(m) - 1;
+                        m &= m - 1;
+                        rescnt[w * 32 + b]++;
+                    }
+                }
+            }
             if (trip) {
                 if (tid == 0 && !multi_tile) {
                     const int w = atomicAdd(&L.hdr->n_tripped, 1);
@@ -980,7 +1058,7 @@ __global__ void __launch_bounds__(VL_THREADS, 1) vl_frames(const VlFrameParams p
                 __syncthreads();
                 continue;
             }
-            // ---- pair phase: warps pull rows, VL_FETCH_ROWS at a time; the entry words of the next
+            // ---- phase 2b: warps pull rows, VL_FETCH_ROWS at a time; the entry words of the next
             //      trip are requested from L2 before the current ones are worked on ------------------
             const float* frame = p.xyz + (size_t)f * (size_t)p.n * 3;
             int r = 0;
@@ -1000,6 +1078,7 @@ __global__ void __launch_bounds__(VL_THREADS, 1) vl_frames(const VlFrameParams p
 #pragma unroll
                 for (int k = 0; k < VL_FETCH_ROWS; k++)
                     nxt[k] = rn + k < n_rows ? __ldg(&rows4[(size_t)(rn + k) * 32 + lane]) : make_uint4(0u, 0u, 0u, 0u);
+                unsigned amb = 0u;                   // bit 4 k + q: entry q of row r + k is ambiguous
 #pragma unroll
                 for (int k = 0; k < VL_FETCH_ROWS; k++) {
                     if (r + k >= n_rows) break;
@@ -1012,32 +1091,45 @@ __global__ void __launch_bounds__(VL_THREADS, 1) vl_frames(const VlFrameParams p
                         const float4 b = vl_lds128(pos_base + oj);
                         const float dx = __fsub_rn(b.x, a.x), dy = __fsub_rn(b.y, a.y), dz = __fsub_rn(b.z, a.z);
                         const float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
-                        bool hit = d2 <= c2_lo;
-                        const bool listed = oj != (unsigned)T.n_slots * 16u;     // not a padding entry
-                        if ((d2 < c2_hi && !hit) || ((FLAGS & VL_AUDIT) && listed)) {
-                            // ambiguous: MDTraj's arithmetic on the raw coordinates, direction slot i -> slot j
-                            // (the lower -> higher position of the list's cell order; DESIGN.md "direction")
+                        // d2 <= c2_lo: certain contact; c2_lo < d2 < c2_hi: AMBIGUOUS, parked and decided
+                        // by MDTraj's arithmetic in phase 1a of the next frame
+                        const bool hit = d2 <= c2_lo;
+                        amb |= (d2 < c2_hi && !hit) ? (1u << (4 * k + q)) : 0u;
+                        c += hit ? (1u << (8 * q)) : 0u;
+                        if ((FLAGS & VL_AUDIT) && oj != (unsigned)T.n_slots * 16u) {
+                            // audit: the exact arithmetic on EVERY listed pair; the screen's decision
+                            // must agree wherever it takes one
                             const float* pa = frame + 3 * (size_t)__float_as_int(a.w);
                             const float* pb = frame + 3 * (size_t)__float_as_int(b.w);
-                            const float d2x = nl_d2_dyn(__ldg(pa), __ldg(pa + 1), __ldg(pa + 2), __ldg(pb),
-                                                        __ldg(pb + 1), __ldg(pb + 2), B);
-                            const bool exact = d2x <= p.c2;
-                            if (FLAGS & VL_AUDIT) {
-                                audited++;
-                                // the screen's decision must agree wherever it takes one
-                                if ((hit && !exact) || (!(d2 < c2_hi) && exact)) disagreements++;
-                            }
-                            hit = exact;
+                            const bool exact = nl_d2_dyn(__ldg(pa), __ldg(pa + 1), __ldg(pa + 2), __ldg(pb),
+                                                         __ldg(pb + 1), __ldg(pb + 2), B) <= p.c2;
+                            audited++;
+                            if ((hit && !exact) || (!(d2 < c2_hi) && exact)) disagreements++;
                         }
-                        c += hit ? (1u << (8 * q)) : 0u;
                     }
                     const unsigned m = __ballot_sync(0xffffffffu, c != 0u);
                     if (c) cnt32[(r + k) * 32 + lane] += c;
                     // the lanes of a row are the segments 32 b + lane of its bundle b: one flag word per
                     // bundle (other rows of the bundle may be setting it at the same time)
                     if (lane == 0 && m) {
-                        unsigned* fw = &segflag[rowb[r + k]];
+                        unsigned* fw = &flag_cur[rowb[r + k]];
                         if ((*(volatile unsigned*)fw & m) != m) vl_reds_or(fw, m);
+                    }
+                }
+                if (amb) {
+                    // park (rare, divergent); a full queue decides on the spot
+#pragma unroll
+                    for (int k = 0; k < VL_FETCH_ROWS; k++) {
+                        const unsigned ew[4] = {cur[k].x, cur[k].y, cur[k].z, cur[k].w};
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            if (amb & (1u << (4 * k + q))) {
+                                const uint2 e = make_uint2(ew[q], ((unsigned)(r + k) << 7) | ((unsigned)lane << 2) | (unsigned)q);
+                                const int w = vl_atoms_add(&misc[2 + par], 1);
+                                if (w < VL_QCAP) queue[w] = e;
+                                else vl_exact_account(e, frame, B, p.c2, pos_base, cnt32, flag_cur, rowb);
+                            }
+                        }
                     }
                 }
                 r = rn;
@@ -1046,16 +1138,8 @@ __global__ void __launch_bounds__(VL_THREADS, 1) vl_frames(const VlFrameParams p
             }
             __syncthreads();
         }
-        // ---- end of the item: last frame's residue pairs, then flush the counters -------------
-        for (int w = tid; w < (T.n_segs + 31) / 32; w += VL_THREADS) {
-            unsigned m = segflag[w];
-            while (m) {
-                const int b = __ffs(m) - 1;
-                m &= m - 1;
-                rescnt[w * 32 + b]++;
-            }
-        }
         __syncthreads();
+        // ---- end of the item: flush the counters ------------------------------------------------
         if (p.atom_table != nullptr) {
             const unsigned* ent = L.entries + (size_t)T.row0 * VL_ROW;
             for (int w = tid; w < T.n_rows * (VL_ROW / 4); w += VL_THREADS) {
@@ -1156,6 +1240,7 @@ struct VlJob {
     unsigned int* atom_table; unsigned int* res_table;
     int audit; unsigned long long* d_audit;
     float max_rlist_factor;      // lists with r_list > factor * cutoff are not built (all frames fall back)
+    int conservative_tiles;      // 1: tile size from the pessimistic slot estimate (vl_setup)
 };
 
 #define VL_CK(call)                                                                  \
@@ -1254,7 +1339,7 @@ inline int vl_build(const VlJob& job, VlScratch& S, cudaStream_t st, std::string
     const int rbits = vl_bits(job.n_res_c + 1), abits = vl_bits(n + 1), tbits = single ? 0 : 12;
     vl_init<<<1, 1, 0, st>>>(S.L.hdr, job.box, periodic, rbits, abits);
     vl_sample<<<(n + 7) / 8, 128, 0, st>>>(S.L.hdr, job.xyz, job.box, job.n_frames, n, S.ref_raw);
-    vl_setup<<<1, 1, 0, st>>>(S.L.hdr, job.box, n, job.cutoff, job.c2, job.max_rlist_factor, nullptr);
+    vl_setup<<<1, 1, 0, st>>>(S.L.hdr, job.box, n, job.cutoff, job.c2, job.max_rlist_factor, job.conservative_tiles);
     vl_zero_cells<<<64, 256, 0, st>>>(S.L.hdr, S.cellcnt);
     vl_bin<<<(n + 255) / 256, 256, 0, st>>>(S.L.hdr, n, S.ref_raw, S.ref_w, S.atomrank, S.cellcnt);
     vl_scan_cells<<<1, 1024, 0, st>>>(S.L.hdr, S.cellcnt, S.cellptr, n);
@@ -1327,13 +1412,7 @@ inline int vl_run_frames(const VlJob& job, VlScratch& S, int sm_count, cudaStrea
     }
     VlFrameParams p;
     p.xyz = job.xyz; p.box = job.box; p.n_frames = job.n_frames; p.n = job.n; p.n_res_c = job.n_res_c; p.c2 = job.c2;
-    // a whole number of rounds of work items over the SMs (rounded UP: never one item more than
-    // that), long enough to amortise the tile set-up / flush
-    const long long tiles_guess = job.n <= VL_SINGLE_TILE_ATOMS ? 1 : std::max<long long>(1, job.n / 700);
-    const long long rounds = tiles_guess > 1 ? 2 : 4;
-    long long item = (job.n_frames * tiles_guess + rounds * sm_count - 1) / (rounds * sm_count);
-    item = std::max<long long>(4, std::min<long long>(item, VL_ITEM_FRAMES));
-    p.item_frames = (int)std::min<long long>(item, std::max<long long>(job.n_frames, 1));
+    p.rounds = job.n <= VL_SINGLE_TILE_ATOMS ? 4 : 6;
     p.atom_table = job.atom_table; p.res_table = job.res_table; p.audit = job.d_audit;
     if (job.audit) vl_frames<VL_AUDIT><<<sm_count, VL_THREADS, VL_SM_TOTAL, st>>>(p, S.L);
     else vl_frames<0><<<sm_count, VL_THREADS, VL_SM_TOTAL, st>>>(p, S.L);

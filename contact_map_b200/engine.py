@@ -538,6 +538,98 @@ class ContactEngine(object):
         out = [None if h is None else h.numpy().view(np.uint64) for h in out]
         return out[0], out[1]
 
+    def frame_csr(self, xyz, box, atom_map, res_map, used=None, frame0=0):
+        """Per-frame contacts of a whole trajectory as CSR arrays, everything but the final copy on
+        the device: key emission -> radix sort -> ``cmb_keys_to_csr`` -> pinned host buffers.
+
+        ``xyz``: CUDA tensor ``[F, n_used, 3]``, or a HOST array ``[F, n_total, 3]`` streamed through
+        ``cmb_frame_contacts_host`` (``used``: ascending indices of the used atoms when the array
+        still holds all atoms).  ``atom_map`` / ``res_map``: compact -> real index.
+        Returns ``((ptr, i, j), (ptr, i, j))`` for atoms and residues: ``ptr`` int64 ``[F + 1]``,
+        ``i < j`` int32 real indices, rows sorted by (i, j) within a frame.
+        """
+        on_device = isinstance(xyz, torch.Tensor) and xyz.is_cuda
+        if on_device:
+            xyz, box = self._dev_inputs(xyz, box)
+        else:
+            xyz = xyz.numpy() if isinstance(xyz, torch.Tensor) else xyz
+            box = box.numpy() if isinstance(box, torch.Tensor) else box
+            if xyz.dtype != np.float32 or not xyz.flags["C_CONTIGUOUS"] or xyz.ndim != 3:
+                raise TypeError("xyz must be C-contiguous float32 [n_frames, n_atoms, 3]")
+            if used is None and xyz.shape[1] != self.n_used:
+                raise ValueError("xyz must hold the %d used atoms (or pass `used`)" % self.n_used)
+            if used is not None:
+                used = np.ascontiguousarray(used, dtype=np.int32)
+                if used.shape[0] != self.n_used:
+                    raise ValueError("len(used) must equal the number of used atoms of the system")
+            if box is not None and (box.dtype != np.float32 or not box.flags["C_CONTIGUOUS"]
+                                    or box.size != xyz.shape[0] * 9):
+                raise TypeError("box must be C-contiguous float32 [n_frames, 3, 3]")
+        n_frames = int(xyz.shape[0])
+        self._set_table_mode(None, None)
+        dev = self.device
+        hints = self.__dict__.setdefault("_keys_hint", {})
+        hint = hints.get(self._system_key)
+        if hint is None:
+            # keys per frame from a counting pass over a short prefix (nothing is written)
+            k = min(n_frames, 64)
+            if on_device:
+                px, pb = xyz[:k], (None if box is None else box[:k])
+            else:
+                px = np.ascontiguousarray(xyz[:k] if used is None else xyz[:k][:, used])
+                px = torch.as_tensor(px, device=dev)
+                pb = None if box is None else torch.as_tensor(np.ascontiguousarray(box[:k]), device=dev)
+            counts = self._frame_contacts_once(px, pb, 0, None, 0, None, 0, None, None, count_only=(True, True))
+            hint = (max(1.0, float(counts[0]) / k), max(1.0, float(counts[1]) / k))
+        cap_a = int(n_frames * hint[0] * 1.25 + 4096)
+        cap_r = int(n_frames * hint[1] * 1.25 + 4096)
+        stream = torch.cuda.current_stream(dev)
+        while True:
+            ak = torch.empty(cap_a, dtype=torch.int64, device=dev)
+            rk = torch.empty(cap_r, dtype=torch.int64, device=dev)
+            counts = torch.zeros(4, dtype=torch.int64, device=dev)
+            with torch.cuda.device(dev):
+                if on_device:
+                    self._check(self._L.cmb_frame_contacts(self._ctx, _ptr(xyz), _ptr(box), n_frames, int(frame0),
+                                                           _ptr(ak), cap_a, _ptr(rk), cap_r, _ptr(counts), None,
+                                                           None, _stream_ptr(dev)), "cmb_frame_contacts")
+                else:
+                    stream.synchronize()                     # counters zeroed before the engine's streams start
+                    self._check(self._L.cmb_frame_contacts_host(
+                        self._ctx, _ptr(xyz), int(xyz.shape[1]), _ptr(used), _ptr(box), n_frames, int(frame0), 0, 0,
+                        _ptr(ak), cap_a, _ptr(rk), cap_r, _ptr(counts)), "cmb_frame_contacts_host")
+            na, nr = (int(v) for v in counts[:2].cpu().numpy())
+            if na <= cap_a and nr <= cap_r:
+                break
+            cap_a, cap_r = max(cap_a, na + na // 8), max(cap_r, nr + nr // 8)
+        if self._system_key is not None and n_frames > 0:
+            hints[self._system_key] = (max(1.0, na / n_frames), max(1.0, nr / n_frames))
+        maps = self.__dict__.setdefault("_csr_maps", {})
+        key = (self._system_key, id(atom_map), id(res_map))
+        if key not in maps:
+            maps.clear()
+            maps[key] = (torch.as_tensor(np.ascontiguousarray(atom_map, dtype=np.int32), device=dev),
+                         torch.as_tensor(np.ascontiguousarray(res_map, dtype=np.int32), device=dev),
+                         atom_map, res_map)          # (the arrays are kept alive so that their ids stay theirs)
+        d_maps = maps[key]
+        out = []
+        with torch.cuda.device(dev):
+            for keys, n, d_map in ((ak, na, d_maps[0]), (rk, nr, d_maps[1])):
+                if n > 1:
+                    self._check(self._L.cmb_sort_keys(self._ctx, _ptr(keys), n, _stream_ptr(dev)), "cmb_sort_keys")
+                d_ptr = torch.empty(n_frames + 1, dtype=torch.int64, device=dev)
+                d_ij = torch.empty((2, max(n, 1)), dtype=torch.int32, device=dev)
+                self._check(self._L.cmb_keys_to_csr(self._ctx, _ptr(keys), n, max(n_frames, 1), int(frame0), _ptr(d_map),
+                                                    _ptr(d_ptr), _ptr(d_ij[0]), _ptr(d_ij[1]), _stream_ptr(dev)),
+                            "cmb_keys_to_csr")
+                h_ptr = torch.empty(n_frames + 1, dtype=torch.int64, pin_memory=True)
+                h_ij = torch.empty((2, max(n, 1)), dtype=torch.int32, pin_memory=True)
+                h_ptr.copy_(d_ptr, non_blocking=True)
+                h_ij.copy_(d_ij, non_blocking=True)
+                out.append((h_ptr, h_ij, n))
+        stream.synchronize()
+        return tuple((h_ptr.numpy(), h_ij[0, :n].numpy(), h_ij[1, :n].numpy()) for h_ptr, h_ij, n in out)
+
     def _frame_contacts_once(self, xyz, box, frame0, ak, cap_a, rk, cap_r, atom_table, res_table,
                              count_only=None):
         counts = torch.zeros(4, dtype=torch.int64, device=self.device)

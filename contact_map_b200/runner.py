@@ -52,7 +52,10 @@ class ChunkedContactFrequency(ContactFrequency):
         engine = get_engine()
         used = _engine_system(self, engine)
         xyz, box = _split_trajectory(trajectory)
-        xyz, box, on_device = _used_coordinates(xyz, box, used, self.topology.n_atoms, engine)
+        # (host arrays keep all their atoms: the used ones are gathered block by block into pinned
+        # staging, so a memory-mapped trajectory is only ever read where this rank's blocks lie)
+        xyz, box, on_device = _used_coordinates(xyz, box, used, self.topology.n_atoms, engine,
+                                                keep_full_host=True)
         atom_table, res_table = engine.new_tables()
         if self._presharded:
             self.block_slices = [slice(0, xyz.shape[0])]
@@ -66,6 +69,8 @@ class ChunkedContactFrequency(ContactFrequency):
                 continue
             if on_device:
                 engine.accumulate(bx, bb, atom_table, res_table)
+            elif bx.shape[1] != used.shape[0]:
+                engine.accumulate_host_gather(bx, used, bb, atom_table, res_table)
             else:
                 engine.accumulate_host(bx, bb, atom_table, res_table)
         self._table_kind = _table_kind(atom_table)
@@ -80,7 +85,8 @@ class DaskContactFrequency(ChunkedContactFrequency):
 
     ``client`` is only asked for its worker count (``len(client.ncores())``) to reproduce the
     reference partition; it may be ``None`` or an int.  ``filename`` is loaded with
-    ``trajectory.load`` (``.pdb`` / ``.npz``); a trajectory object is accepted as well.
+    ``trajectory.load`` (``.pdb`` / ``.npz``, or a memory-mapped ``.npy`` of which every rank then
+    reads only its own frame blocks); a trajectory object is accepted as well.
     """
 
     def __init__(self, client, filename, query=None, haystack=None, cutoff=0.45,

@@ -458,20 +458,89 @@ def load_pdb(filename):
     return Trajectory(xyz, topology, vectors)
 
 
+def _topology_from_npz(data):
+    return Topology(data["atom_residue"], data["residue_chain"],
+                    atom_names=[str(s) for s in data["atom_names"]] if "atom_names" in data else None,
+                    atom_elements=[str(s) for s in data["atom_elements"]] if "atom_elements" in data else None,
+                    residue_names=[str(s) for s in data["residue_names"]] if "residue_names" in data else None,
+                    residue_resseq=data["residue_resseq"] if "residue_resseq" in data else None)
+
+
+def save_npy(filename, trajectory):
+    """Write ``trajectory`` in the chunk-readable layout :func:`load` memory-maps:
+
+    * ``<filename>`` (``.npy``): the coordinates, float32 ``[n_frames, n_atoms, 3]`` in nm, plain
+      NumPy format -- any writer of ``.npy`` files (``numpy.lib.format.open_memmap``) can produce it
+      frame block by frame block without ever holding the trajectory in memory;
+    * ``<filename minus .npy>.top.npz``: topology arrays and, if present, the unit-cell vectors
+      ``[n_frames, 3, 3]`` (36 bytes per frame).
+
+    Returns the side-car file name."""
+    filename = str(filename)
+    if not filename.lower().endswith(".npy"):
+        raise ValueError("save_npy writes a .npy coordinate file")
+    out = np.lib.format.open_memmap(filename, mode="w+", dtype=np.float32, shape=tuple(trajectory.xyz.shape))
+    step = max(1, (64 << 20) // max(1, trajectory.xyz.shape[1] * 12))
+    for f0 in range(0, trajectory.xyz.shape[0], step):          # block copy: works for memory-mapped sources too
+        out[f0:f0 + step] = trajectory.xyz[f0:f0 + step]
+    out.flush()
+    del out
+    top = trajectory.topology
+    arrays = {"atom_residue": top.atom_residue, "residue_chain": top.residue_chain,
+              "atom_names": np.asarray(top.atom_names, dtype="U8"),
+              "atom_elements": np.asarray(top.atom_elements, dtype="U4"),
+              "residue_names": np.asarray(top.residue_names, dtype="U8"),
+              "residue_resseq": np.asarray(top.residue_resseq, dtype=np.int64)}
+    if trajectory.unitcell_vectors is not None:
+        arrays["unitcell_vectors"] = trajectory.unitcell_vectors
+    sidecar = filename[:-4] + ".top.npz"
+    np.savez(sidecar, **arrays)
+    return sidecar
+
+
+def load_npy(filename, top=None):
+    """Memory-mapped trajectory: ``xyz`` is a read-only view of the file, so slicing frames
+    (``load(...)[subslice]``, the reference's ``load_trajectory_task``, frequency_task.py:70-88)
+    touches no data, and the engine's staged host path (``cmb_accumulate_host`` /
+    ``cmb_accumulate_host_gather``: host threads pack chunk k+1 into pinned staging while chunk k is
+    copied and processed) pages in exactly the frames a rank works on.  A trajectory larger than
+    host memory therefore streams through the GPU without ever being materialised.
+
+    ``top`` (MDTraj's keyword): a :class:`Topology`, a trajectory object, or a ``.npz`` / ``.pdb``
+    file; default: the side-car ``<name>.top.npz`` written by :func:`save_npy`."""
+    filename = str(filename)
+    xyz = np.load(filename, mmap_mode="r", allow_pickle=False)
+    if xyz.dtype != np.float32 or xyz.ndim != 3 or xyz.shape[2] != 3 or not xyz.flags["C_CONTIGUOUS"]:
+        raise IOError("%r must hold C-ordered float32 coordinates [n_frames, n_atoms, 3]" % (filename,))
+    cell = None
+    if top is None:
+        top = filename[:-4] + ".top.npz"
+    if isinstance(top, str):
+        if top.lower().endswith(".npz"):
+            data = np.load(top, allow_pickle=False)
+            cell = data["unitcell_vectors"] if "unitcell_vectors" in data else None
+            top = _topology_from_npz(data)
+        else:
+            top = load(top).topology
+    elif hasattr(top, "topology"):
+        top = top.topology
+    return Trajectory(xyz, top, cell)
+
+
 def load(filename, **kwargs):
-    """Loader used by the chunked runner: ``.pdb`` text or ``.npz`` (xyz, unitcell_vectors,
-    atom_residue, residue_chain[, atom_elements, residue_names])."""
+    """Loader used by the chunked runner: ``.pdb`` text, ``.npz`` (xyz, unitcell_vectors,
+    atom_residue, residue_chain[, atom_elements, residue_names]) or a memory-mapped ``.npy``
+    coordinate file with its topology side-car (:func:`load_npy`, :func:`save_npy`)."""
     name = str(filename).lower()
     if name.endswith(".pdb"):
         return load_pdb(filename)
+    if name.endswith(".npy"):
+        return load_npy(filename, top=kwargs.get("top"))
     if name.endswith(".npz"):
         data = np.load(filename, allow_pickle=False)
-        top = Topology(data["atom_residue"], data["residue_chain"],
-                       atom_elements=[str(s) for s in data["atom_elements"]] if "atom_elements" in data else None,
-                       residue_names=[str(s) for s in data["residue_names"]] if "residue_names" in data else None)
         cell = data["unitcell_vectors"] if "unitcell_vectors" in data else None
-        return Trajectory(data["xyz"], top, cell)
-    raise IOError("unsupported trajectory file %r (only .pdb and .npz)" % (filename,))
+        return Trajectory(data["xyz"], _topology_from_npz(data), cell)
+    raise IOError("unsupported trajectory file %r (only .pdb, .npz and .npy)" % (filename,))
 
 
 def topology_arrays(topology):

@@ -108,6 +108,31 @@ int cmb_frame_contacts(cmb_ctx* ctx, const float* d_xyz, const float* d_box, int
                        uint32_t* d_atom_table, uint32_t* d_res_table, void* stream);
 
 /*
+ * The same for a HOST trajectory (the data the reference hands to _build_contacts,
+ * contact_trajectory.py:7-44, lives in host memory: trajectory.xyz): the frames stream through
+ * the key kernels chunk by chunk over two streams like cmb_accumulate_host[_gather] (pinned
+ * buffers are copied directly, pageable / memory-mapped ones and trajectories that still hold
+ * all n_total atoms are packed into pinned staging by host threads; h_used = NULL: the
+ * trajectory holds exactly the used atoms).  Every chunk APPENDS its keys -- they carry the
+ * trajectory frame numbers frame0 + f -- to the caller's DEVICE buffers through the shared
+ * counters d_counts (zeroed by the caller), so the result is unordered: sort it with
+ * cmb_sort_keys, then cmb_keys_to_csr.  Synchronous.
+ */
+int cmb_frame_contacts_host(cmb_ctx* ctx, const float* h_xyz_full, int n_total, const int32_t* h_used,
+                            const float* h_box, int64_t n_frames, int64_t frame0, int64_t chunk_frames,
+                            int n_threads, uint64_t* d_atom_keys, int64_t atom_cap,
+                            uint64_t* d_res_keys, int64_t res_cap, uint64_t* d_counts);
+
+/*
+ * Sorted keys -> the per-frame containers of ContactTrajectory (contact_trajectory.py:70-89) as
+ * CSR arrays: d_ptr[n_frames + 1] (keys of frame f are [ptr[f], ptr[f+1])), d_i / d_j[n_keys] the
+ * pairs, i < j, mapped through d_index_map (compact -> real index; NULL: identity).
+ */
+int cmb_keys_to_csr(cmb_ctx* ctx, const uint64_t* d_sorted_keys, int64_t n_keys, int64_t n_frames,
+                    int64_t frame0, const int32_t* d_index_map, int64_t* d_ptr, int32_t* d_i,
+                    int32_t* d_j, void* stream);
+
+/*
  * Hashed count tables (north_star: "dense or hashed count matrix") for systems whose dense
  * [n_used][n_used] table would not stay in L2 (a 100k-atom system: 40 GB): open addressing over
  * uint64 slots, slot = (flat index + 1) << 24 | count, flat index = lo * n_used + hi as in the dense

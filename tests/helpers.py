@@ -15,6 +15,12 @@ def system_arrays(system, query=None, haystack=None):
     return atom_res.astype(np.int32), atom_chain.astype(np.int32), role
 
 
+def system_arrays_of_topology(top):
+    """Per-atom arrays of a bare topology, every atom query and haystack."""
+    atom_res, atom_chain = top.atom_residue_chain()
+    return atom_res.astype(np.int32), atom_chain.astype(np.int32), np.full(top.n_atoms, 3, dtype=np.uint8)
+
+
 def dense_from_export(idx, cnt, n):
     out = np.zeros(n * n, dtype=np.uint32)
     out[idx] = cnt

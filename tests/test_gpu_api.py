@@ -253,3 +253,37 @@ def test_public_api_on_hashed_tables(engine, monkeypatch):
         assert chunked.n_frames == len(traj)
     finally:
         engine.set_option("force_path", -1)
+
+
+def test_chunked_reader_streams_a_mapped_file(engine, tmp_path):
+    """f2 (reference frequency_task.py:70-88, dask_runner.py:109,179): a memory-mapped trajectory
+    file several times larger than the engine's staging buffers goes through the runner block by
+    block -- plain copy (all atoms used) and fused gather (query/haystack subsets) -- and equals the
+    in-memory run; the map/reduce tasks see only their own slices."""
+    from contact_map_b200 import synth, trajectory
+    system = synth.kras_like()
+    n_frames = 1500                                        # 48.6 MB of coordinates
+    xyz = system.frames(0, n_frames)
+    box = np.broadcast_to(system.box, (n_frames, 3, 3)).copy()
+    mem = cm.Trajectory(xyz, system.topology, box)
+    name = str(tmp_path / "big.npy")
+    trajectory.save_npy(name, mem)
+    lazy = cm.load(name)
+    assert not lazy.xyz.flags["OWNDATA"]
+    engine.set_option("stage_chunk_frames", 100)           # staging buffers of 100 frames (3.2 MB)
+    try:
+        for kw in ({}, {"query": list(range(0, 300)), "haystack": list(range(200, 2700, 2))}):
+            serial = cm.ContactFrequency(mem, **kw)
+            from_file = cm.DaskContactFrequency(client=4, filename=name, **kw)
+            assert from_file._atom_contacts == serial._atom_contacts
+            assert from_file._residue_contacts == serial._residue_contacts
+            assert from_file.n_frames == n_frames
+            direct = cm.ContactFrequency(lazy, **kw)       # the plain class on the mapped file
+            assert direct == serial
+        ft = cm.frequency_task
+        parts = [ft.map_task(ft.load_trajectory_task(s, name), {"cutoff": 0.45, "n_neighbors_ignored": 2})
+                 for s in ft.default_slices(n_frames, 2)]
+        assert ft.reduce_all_results(parts) == cm.ContactFrequency(mem)
+    finally:
+        engine.set_option("stage_chunk_frames", 0)
+    assert len(serial._atom_contacts) > 100

@@ -243,6 +243,84 @@ def test_binding_system_s2_matches_oracle(engine):
     assert np.all((role[lo] | role[hi]) == 3) and np.all(role[lo] != role[hi])
 
 
+@pytest.mark.parametrize("ligand", [True, False])
+def test_s2_contact_trajectory_per_frame_keys_match_oracle(engine, ligand):
+    """BASELINE configs[2] at benchmark SHAPE (30-atom ligand / 600-atom partner chain against the
+    2 700-atom receptor) through the public API from HOST memory: the per-frame atom and residue
+    sets of ContactTrajectory equal the oracle's for every frame of a 40-frame block, and
+    ContactDifference of two halves equals the difference of the oracle's count tables."""
+    import contact_map_b200 as cm
+    system = synth.binding_system(ligand=ligand)
+    top = system.topology
+    res, chain, role = system_arrays(system, system.query, system.haystack)
+    F = 40
+    xyz = system.frames(0, F)
+    box = np.broadcast_to(system.box, (F, 3, 3)).copy()
+    traj = cm.Trajectory(xyz, top, box)
+    kw = dict(query=system.query, haystack=system.haystack, cutoff=0.45, n_neighbors_ignored=2)
+    ct = cm.ContactTrajectory(traj, **kw)
+    atoms_csr, res_csr = ct._csr
+    n_hits = 0
+    for f in range(F):
+        pairs = clib.contacts_frame(xyz[f], box[f], 0.45, res, chain, role, 2)
+        want = {(int(a), int(b)) for a, b in pairs}
+        a, b = atoms_csr.ptr[f], atoms_csr.ptr[f + 1]
+        got = set(zip(atoms_csr.i[a:b].tolist(), atoms_csr.j[a:b].tolist()))
+        assert got == want, f
+        want_res = {(min(int(res[a_]), int(res[b_])), max(int(res[a_]), int(res[b_]))) for a_, b_ in pairs}
+        a, b = res_csr.ptr[f], res_csr.ptr[f + 1]
+        assert set(zip(res_csr.i[a:b].tolist(), res_csr.j[a:b].tolist())) == want_res, f
+        n_hits += len(want)
+        # every contact joins the query with the haystack
+        assert all((role[i] | role[j]) == 3 and role[i] != role[j] for i, j in want)
+    assert n_hits > (200 if ligand else 100)
+    # a frame object built from the CSR arrays holds the same set
+    assert set(map(tuple, map(sorted, ct[3]._atom_contacts.keys()))) == \
+        {(int(a), int(b)) for a, b in clib.contacts_frame(xyz[3], box[3], 0.45, res, chain, role, 2)}
+    # ContactDifference(first half, second half) == difference of the oracle tables
+    half = F // 2
+    diff = cm.ContactFrequency(traj[:half], **kw) - cm.ContactFrequency(traj[half:], **kw)
+    ref_a0, _ = clib.accumulate_dense(xyz[:half], box[:half], 0.45, res, chain, role, 2, top.n_residues)
+    ref_a1, _ = clib.accumulate_dense(xyz[half:], box[half:], 0.45, res, chain, role, 2, top.n_residues)
+    want_diff = ref_a0.astype(np.float64) / half - ref_a1.astype(np.float64) / half
+    got = diff.atom_contacts.counter
+    ii, jj = np.nonzero(np.triu(ref_a0 + ref_a1))
+    assert len(got) == len(ii)
+    for i, j in zip(ii.tolist(), jj.tolist()):
+        assert got[frozenset((i, j))] == want_diff[i, j]
+
+
+def test_s2_long_trajectory_properties(engine):
+    """S2 ligand at its full length (100 000 frames from host memory, the configuration north_star
+    names): size-independent properties -- the per-frame keys summed over frames equal the
+    ContactFrequency tables of the same trajectory, frame pointers are monotone and complete, and a
+    sampled set of frames equals the oracle."""
+    import contact_map_b200 as cm
+    system = synth.binding_system(ligand=True)
+    top = system.topology
+    res, chain, role = system_arrays(system, system.query, system.haystack)
+    F = 100000
+    d_xyz, d_box = _dev(engine, system, 0, F)
+    xyz, box = d_xyz.cpu().numpy(), d_box.cpu().numpy()
+    del d_xyz, d_box
+    traj = cm.Trajectory(xyz, top, box)
+    kw = dict(query=system.query, haystack=system.haystack, cutoff=0.45, n_neighbors_ignored=2)
+    ct = cm.ContactTrajectory(traj, **kw)
+    assert len(ct) == F
+    atoms_csr, res_csr = ct._csr
+    for csr in (atoms_csr, res_csr):
+        assert csr.ptr[0] == 0 and csr.ptr[-1] == csr.i.shape[0] and np.all(np.diff(csr.ptr) >= 0)
+        assert np.all(csr.i < csr.j)
+    freq = cm.ContactFrequency(traj, **kw)
+    total = ct.contact_frequency()
+    assert total._atom_contacts == freq._atom_contacts
+    assert total._residue_contacts == freq._residue_contacts
+    for f in (0, 1, F // 2, F - 1):
+        pairs = clib.contacts_frame(xyz[f], box[f], 0.45, res, chain, role, 2)
+        a, b = atoms_csr.ptr[f], atoms_csr.ptr[f + 1]
+        assert set(zip(atoms_csr.i[a:b].tolist(), atoms_csr.j[a:b].tolist())) == {(int(p), int(q)) for p, q in pairs}
+
+
 @pytest.mark.parametrize("box_kind,force_path,max_shift", [("ortho", 0, 2), ("triclinic", 0, 2), ("none", 0, 0),
                                                            ("triclinic", 1, 2), ("ortho", 0, 400)])
 def test_pairs_at_the_cutoff_are_adjudicated_exactly(engine, box_kind, force_path, max_shift):

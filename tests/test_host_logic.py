@@ -249,3 +249,37 @@ def test_trajectory_container(tmp_path):
     assert t.n_atoms == 3 and t.topology.n_residues == 2
     assert t.xyz[0, 2].tolist() == [np.float32(0.225), np.float32(0.275), 0.0]
     assert np.array_equal(t.unitcell_vectors[0], np.diag([2.5, 2.5, 2.5]).astype(np.float32))
+
+
+def test_memory_mapped_npy_reader_is_lazy(tmp_path):
+    """Chunked reader (reference load_trajectory_task, frequency_task.py:70-88): a .npy coordinate
+    file is memory-mapped, slicing frames copies nothing, and every task sees exactly its frames."""
+    from contact_map_b200 import frequency_task, trajectory
+    case = goldens.load("syn_tric_all")
+    traj = goldens.trajectory(case)
+    name = str(tmp_path / "traj.npy")
+    sidecar = trajectory.save_npy(name, traj)
+    assert sidecar.endswith("traj.top.npz")
+    lazy = cm.load(name)
+    assert isinstance(lazy.xyz.base, np.memmap) or isinstance(lazy.xyz, np.memmap)
+    assert not lazy.xyz.flags["OWNDATA"] and not lazy.xyz.flags["WRITEABLE"]
+    assert lazy.topology == traj.topology
+    assert np.array_equal(lazy.unitcell_vectors, traj.unitcell_vectors)
+    assert np.array_equal(lazy.xyz, traj.xyz)
+    # slices of the mapped file stay views of it (nothing is materialised)
+    total = 0
+    for sl in frequency_task.default_slices(len(traj), 3):
+        part = frequency_task.load_trajectory_task(sl, name)
+        assert np.shares_memory(part.xyz, lazy.xyz) or not part.xyz.flags["OWNDATA"]
+        assert np.array_equal(part.xyz, traj.xyz[sl])
+        assert np.array_equal(part.unitcell_vectors, traj.unitcell_vectors[sl])
+        total += len(part)
+    assert total == len(traj)
+    # MDTraj's `top=` keyword: topology from another file / object; no side-car needed then
+    bare = str(tmp_path / "bare.npy")
+    np.save(bare, traj.xyz)
+    assert cm.load(bare, top=traj).topology == traj.topology
+    assert cm.load(bare, top=sidecar).n_atoms == traj.n_atoms
+    with pytest.raises(IOError):
+        np.save(str(tmp_path / "bad.npy"), traj.xyz.astype(np.float64))
+        cm.load(str(tmp_path / "bad.npy"), top=traj)

@@ -98,3 +98,65 @@ def test_two_rank_reduce_equals_single(tmp_path):
         assert np.array_equal(got["m_idx"], want_flat)
         assert np.array_equal(got["m_cnt"], atom.reshape(-1)[want_flat])
     assert atom.sum() > 0
+
+
+def _file_worker(rank, world, port, out_dir, file_name):
+    """Each rank maps the trajectory FILE and touches only the frames of its own blocks."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from contact_map_b200 import frequency_task, parallel
+        from oracle import clib
+        from tests.helpers import system_arrays_of_topology
+        probe = frequency_task.load_trajectory_task(slice(0, 0), file_name)      # topology only, no frames read
+        res, chain, role = system_arrays_of_topology(probe.topology)
+        n, n_res = probe.topology.n_atoms, probe.topology.n_residues
+        n_frames = len(frequency_task.load_trajectory_task(slice(None), file_name))
+        atom = np.zeros((n, n), dtype=np.uint32)
+        resc = np.zeros((n_res, n_res), dtype=np.uint32)
+        touched = []
+        for s in parallel.rank_slices(n_frames, n_blocks=5):
+            part = frequency_task.load_trajectory_task(s, file_name)
+            assert not part.xyz.flags["OWNDATA"]                      # still a view of the mapped file
+            a, r = clib.accumulate_dense(np.ascontiguousarray(part.xyz), np.ascontiguousarray(part.unitcell_vectors),
+                                         0.45, res, chain, role, 2, n_res)
+            atom += a
+            resc += r
+            touched.extend(range(s.start, s.stop))
+        t_atom = torch.from_numpy(atom.view(np.int32).reshape(-1).copy())
+        t_res = torch.from_numpy(resc.view(np.int32).reshape(-1).copy())
+        parallel.reduce_tables([t_atom, t_res])
+        total = parallel.reduce_frame_count(len(touched), torch.device("cpu"))
+        np.savez(os.path.join(out_dir, "file_rank%d.npz" % rank), atom=t_atom.numpy(), res=t_res.numpy(),
+                 frames=total, touched=np.asarray(touched, dtype=np.int64))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_ranks_read_disjoint_slices_of_a_mapped_file(tmp_path):
+    """f2: the chunked reader sharded over two ranks -- every frame of the file is read by exactly
+    one rank and the reduced tables equal the in-memory single-process run."""
+    from contact_map_b200 import synth, trajectory
+    from oracle import clib
+    from tests.helpers import system_arrays
+    rng = np.random.default_rng(5)
+    system = synth.random_system(rng, 90, n_chains=2, box_kind="triclinic", extent=1.6)
+    n_frames = 23
+    xyz = system.frames(0, n_frames)
+    box = np.broadcast_to(system.box, (n_frames, 3, 3)).copy()
+    file_name = str(tmp_path / "sharded.npy")
+    trajectory.save_npy(file_name, trajectory.Trajectory(xyz, system.topology, box))
+    port = _free_port()
+    mp.spawn(_file_worker, args=(2, port, str(tmp_path), file_name), nprocs=2, join=True)
+    res, chain, role = system_arrays(system)
+    atom, resc = clib.accumulate_dense(xyz, box, 0.45, res, chain, role, 2, system.topology.n_residues)
+    seen = []
+    for rank in range(2):
+        got = np.load(os.path.join(str(tmp_path), "file_rank%d.npz" % rank))
+        assert np.array_equal(got["atom"].view(np.uint32).reshape(atom.shape), atom)
+        assert np.array_equal(got["res"].view(np.uint32).reshape(resc.shape), resc)
+        assert int(got["frames"]) == n_frames
+        seen.extend(got["touched"].tolist())
+    assert sorted(seen) == list(range(n_frames))
+    assert atom.sum() > 0

@@ -1,10 +1,13 @@
-"""Host/device time breakdown of one bench step (S1, inputs resident in HBM)."""
+"""Host/device time breakdown of one bench step (inputs resident in HBM).
+    python tools/step_breakdown.py [s1|s3] [frames]"""
 import os, sys, time
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from contact_map_b200 import synth
 from contact_map_b200.engine import get_engine
-system = synth.kras_like(); top = system.topology; n = top.n_atoms; F = 10000
+which = sys.argv[1] if len(sys.argv) > 1 else 's1'
+system = synth.kras_like() if which == 's1' else synth.solvated_triclinic(n_atoms=100000)
+top = system.topology; n = top.n_atoms; F = int(sys.argv[2]) if len(sys.argv) > 2 else (10000 if which == 's1' else 1024)
 engine = get_engine(0); dev = engine.device
 atom_res, atom_chain = top.atom_residue_chain()
 engine.set_system(atom_res, atom_chain, np.full(n, 3, np.uint8), 0.45, 2)

@@ -12,6 +12,8 @@ system = synth.kras_like() if which == "s1" else synth.solvated_triclinic(n_atom
 frames = [int(a) for a in sys.argv[2:]] or [256, 1024, 4096, 10000, 40000]
 res, chain = system.topology.atom_residue_chain()
 engine.set_system(res, chain, np.full(system.n_atoms, 3, np.uint8), 0.45, 2)
+if os.environ.get("VL_CONSERVATIVE"):
+    engine.set_option("verlet_conservative_tiles", 1)
 base = torch.as_tensor(system.base, device=dev); grp = torch.as_tensor(system.groups.astype(np.int32), device=dev)
 box9 = torch.as_tensor(system.box.reshape(9), device=dev)
 a, r = engine.new_tables()
@@ -31,5 +33,7 @@ for F in frames:
             best = min(best, e0.elapsed_time(e1))
         out["ms_mode%d" % mode] = best
     out["tripped"] = engine.get_stat("vl_tripped"); out["entries"] = engine.get_stat("vl_entries")
+    for k in ("vl_tiles", "vl_tdim", "vl_rows", "vl_slots", "vl_fail", "vl_rebuilds", "vl_rebuild_code", "vl_conservative"):
+        out[k[3:]] = engine.get_stat(k)
     print(json.dumps(out), flush=True)
     del xyz, box
