@@ -29,7 +29,7 @@ EXPORTS = [
     "cmb_boundary_pairs", "cmb_set_option", "cmb_get_stat", "cmb_gather_atoms", "cmb_min_dist",
     "cmb_nearest", "cmb_synth_frames", "cmb_set_table_mode", "cmb_hash_stats", "cmb_export_hashed",
     "cmb_hash_rehash", "cmb_hash_overflow_buffer", "cmb_hash_add", "cmb_export_sorted", "cmb_group_contacts",
-    "cmb_min_dist_pairs",
+    "cmb_min_dist_pairs", "cmb_frame_contacts_host", "cmb_keys_to_csr",
 ]
 
 

@@ -114,7 +114,11 @@ class _LazyFrames(abc.Sequence):
     """Sequence of 1-frame ContactFrequency objects built on first access."""
 
     def __init__(self, owner, atoms, residues):
-        self._owner = owner
+        # (the parameters are copied, not the owner: a reference back to the ContactTrajectory would
+        # be a cycle, and the CSR arrays -- pinned host memory -- would wait for the cycle collector)
+        self._params = dict(topology=owner.topology, query=owner.query, haystack=owner.haystack,
+                            cutoff=owner.cutoff, n_neighbors_ignored=owner.n_neighbors_ignored,
+                            indexer=owner.indexer)
         self._atoms = atoms
         self._residues = residues
         self._cache = {}
@@ -124,11 +128,8 @@ class _LazyFrames(abc.Sequence):
 
     def _make(self, f):
         if f not in self._cache:
-            o = self._owner
             self._cache[f] = ContactFrequency.from_contacts(
-                self._atoms.frame_table(f), self._residues.frame_table(f), n_frames=1,
-                topology=o.topology, query=o.query, haystack=o.haystack, cutoff=o.cutoff,
-                n_neighbors_ignored=o.n_neighbors_ignored, indexer=o.indexer)
+                self._atoms.frame_table(f), self._residues.frame_table(f), n_frames=1, **self._params)
         return self._cache[f]
 
     def __getitem__(self, num):

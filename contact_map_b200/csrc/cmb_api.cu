@@ -20,6 +20,17 @@
 
 using namespace cmb;
 
+struct FrameJob {
+    const float* xyz; const float* box; long long n_frames; long long frame0;
+    unsigned int* atom_table; unsigned int* res_table;
+    unsigned long long* atom_keys; long long atom_cap;
+    unsigned long long* res_keys; long long res_cap;
+    unsigned long long* ext_counters;      // caller-provided device counters or nullptr
+    float4* boundary; long long boundary_cap; int boundary_ulps;
+    int shared_list;                       // 1: a chunk of a streamed trajectory: walk the context's shared pair
+                                           // list (built from the first chunk, rebuilt when too many frames trip)
+};
+
 struct cmb_ctx {
     int device = 0;
     int sm_count = 0;
@@ -66,6 +77,15 @@ struct cmb_ctx {
     int last_used_verlet = 0;
     int last_vl_slot = 0;
     int vl_conservative = 0;                  // the optimistic tile size overflowed a tile of this system once
+    VlRun vl_run[2];                          // per stream slot: state of one walk over a list
+    int vl_shared = -1;                       // scratch holding the list the chunks of a streamed trajectory share
+    int vl_shared_stale = 0;                  // too many frames of a chunk tripped: the next chunk rebuilds the list
+    cudaEvent_t vl_built[2] = {nullptr, nullptr};            // list of scratch X complete
+    cudaEvent_t vl_walked[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // last walk of list X on stream slot s
+    bool vl_walked_set[2][2] = {{false, false}, {false, false}};
+    cudaEvent_t vl_info_ready[2] = {nullptr, nullptr};       // read-back of slot s's walk has landed
+    // the large path's fall back of a streamed chunk is finished when its stream slot comes round again
+    struct Pending { bool active = false; bool info = false; FrameJob job; cudaStream_t stream = nullptr; int list = 0; } pending[2];
 
     // host pipeline
     float* d_stage_xyz[2] = {nullptr, nullptr};
@@ -185,7 +205,14 @@ extern "C" void cmb_ctx_destroy(cmb_ctx* ctx)
         if (ctx->streams[s]) cudaStreamDestroy(ctx->streams[s]);
         large_scratch_free(ctx->large[s]);
     }
-    for (int s = 0; s < 2; s++) vl_free(ctx->vl[s]);
+    for (int s = 0; s < 2; s++) {
+        vl_free(ctx->vl[s]);
+        vl_run_free(ctx->vl_run[s]);
+        if (ctx->vl_built[s]) cudaEventDestroy(ctx->vl_built[s]);
+        if (ctx->vl_info_ready[s]) cudaEventDestroy(ctx->vl_info_ready[s]);
+        for (int t = 0; t < 2; t++)
+            if (ctx->vl_walked[s][t]) cudaEventDestroy(ctx->vl_walked[s][t]);
+    }
     cudaFree(ctx->d_res_anchor);
     cudaFree(ctx->d_vl_audit);
     cudaFree(ctx->d_tmp);
@@ -260,7 +287,12 @@ extern "C" int cmb_get_stat(cmb_ctx* ctx, const char* name, int64_t* value)
         CK(cudaMemcpy(&h, V.L.hdr, sizeof(h), cudaMemcpyDeviceToHost));
         if (!strcmp(name, "vl_valid")) { *value = h.valid; return CMB_OK; }
         if (!strcmp(name, "vl_fail")) { *value = h.fail_code; return CMB_OK; }
-        if (!strcmp(name, "vl_tripped")) { *value = h.n_tripped; return CMB_OK; }
+        if (!strcmp(name, "vl_tripped")) {
+            int t = 0;
+            if (ctx->vl_run[ctx->last_slot].state) CK(cudaMemcpy(&t, ctx->vl_run[ctx->last_slot].state, sizeof(int), cudaMemcpyDeviceToHost));
+            *value = t;
+            return CMB_OK;
+        }
         if (!strcmp(name, "vl_entries")) { *value = h.n_entries; return CMB_OK; }
         if (!strcmp(name, "vl_tiles")) { *value = h.n_tiles; return CMB_OK; }
         if (!strcmp(name, "vl_tdim")) { *value = h.tdim; return CMB_OK; }
@@ -432,6 +464,7 @@ extern "C" int cmb_set_system(cmb_ctx* ctx, int n_used, const int32_t* atom_res,
 
     ctx->n = n_used;
     ctx->vl_conservative = 0;
+    ctx->vl_shared = -1;
     ctx->cutoff_f = (float)cutoff;
     ctx->n_ignored = n_ignored;
     ctx->have_system = false;
@@ -471,15 +504,6 @@ extern "C" int cmb_path_kind(const cmb_ctx* ctx) { return ctx && ctx->have_syste
 // ---------------------------------------------------------------------------------
 // frame kernels
 // ---------------------------------------------------------------------------------
-struct FrameJob {
-    const float* xyz; const float* box; long long n_frames; long long frame0;
-    unsigned int* atom_table; unsigned int* res_table;
-    unsigned long long* atom_keys; long long atom_cap;
-    unsigned long long* res_keys; long long res_cap;
-    unsigned long long* ext_counters;      // caller-provided device counters or nullptr
-    float4* boundary; long long boundary_cap; int boundary_ulps;
-};
-
 // the fused-kernel variant a job asks for
 template <int THREADS>
 static void fs_launch(const cmb_ctx* ctx, const FrameJob& job, const FrameParams& p, unsigned g, size_t sm,
@@ -501,7 +525,39 @@ static void fs_launch(const cmb_ctx* ctx, const FrameJob& job, const FrameParams
 }
 
 
-static int launch_frames(cmb_ctx* ctx, const FrameJob& job, int slot, cudaStream_t stream)
+static int large_cells(cmb_ctx* ctx, const FrameJob& job, int slot, cudaStream_t stream,
+                       const std::vector<std::pair<long long, long long>>& runs);
+
+// The frames of a walked pair list that the list could not take (guard tripped, list unusable),
+// global-memory cell path: the count was requested from the device when the walk was enqueued;
+// wait for it, fetch the frame numbers and run the cell kernels on them as runs of consecutive
+// frames.  Small systems never come here: the fused kernel reads the device-side list itself.
+static int finish_pending(cmb_ctx* ctx, int slot)
+{
+    cmb_ctx::Pending& P = ctx->pending[slot];
+    if (!P.active) return CMB_OK;
+    P.active = false;
+    VlRun& R = ctx->vl_run[slot];
+    CK(cudaEventSynchronize(ctx->vl_info_ready[slot]));
+    const int n_trip = R.h_info[0];
+    if (P.job.shared_list && n_trip * 8 > P.job.n_frames) ctx->vl_shared_stale = 1;
+    if (n_trip == 0) return CMB_OK;
+    std::vector<int> trip((size_t)n_trip);
+    CK(cudaMemcpy(trip.data(), R.tripped, sizeof(int) * (size_t)n_trip, cudaMemcpyDeviceToHost));
+    std::sort(trip.begin(), trip.end());
+    std::vector<std::pair<long long, long long>> runs;      // [first, last) frame ranges to process
+    for (size_t k = 0; k < trip.size();) {
+        size_t e = k + 1;
+        while (e < trip.size() && trip[e] == trip[e - 1] + 1) e++;
+        runs.push_back({trip[k], (long long)trip[e - 1] + 1});
+        k = e;
+    }
+    return large_cells(ctx, P.job, slot, P.stream, runs);
+}
+
+// defer_fallback: the caller (a streamed host trajectory) calls finish_pending(slot) itself before
+// it reuses the slot's coordinates; otherwise the fall back is finished before returning.
+static int launch_frames(cmb_ctx* ctx, const FrameJob& job, int slot, cudaStream_t stream, bool defer_fallback = false)
 {
     if (!ctx->have_system) return fail(ctx, CMB_ERR_STATE, "cmb_set_system has not been called");
     if (job.n_frames <= 0) return CMB_OK;
@@ -509,6 +565,8 @@ static int launch_frames(cmb_ctx* ctx, const FrameJob& job, int slot, cudaStream
     if (job.frame0 + job.n_frames >= (1ll << 24) && (job.atom_keys || job.res_keys))
         return fail(ctx, CMB_ERR_LIMIT, "frame ids in emitted keys are limited to 2^24 per call");
     CK(cudaSetDevice(ctx->device));
+    int rc = finish_pending(ctx, slot);                    // (a no-op unless a deferred fall back is still open)
+    if (rc != CMB_OK) return rc;
     unsigned long long* counters = job.ext_counters ? job.ext_counters : ctx->d_counters[slot];
     if (!job.ext_counters) CK(cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned long long), stream));
     ctx->last_slot = slot;
@@ -527,12 +585,32 @@ static int launch_frames(cmb_ctx* ctx, const FrameJob& job, int slot, cudaStream
         const bool plain = !job.atom_keys && !job.res_keys && job.boundary_ulps == 0 && !ctx->count_tests &&
                            (job.atom_table || job.res_table) && ctx->atom_log2 == 0 && ctx->res_log2 == 0;
         const long long min_frames = ctx->path == 0 ? 256 : 32;
-        if (plain && ctx->verlet != 0 && (ctx->verlet == 2 || job.n_frames >= min_frames) && job.n_frames >= 2 &&
-            job.n_frames < (1ll << 30)) {
-            VlScratch& V = ctx->vl[slot];
+        const bool have_shared = job.shared_list && ctx->vl_shared >= 0;
+        if (plain && ctx->verlet != 0 && (ctx->verlet == 2 || job.n_frames >= min_frames || have_shared) &&
+            job.n_frames >= 2 && job.n_frames < (1ll << 30)) {
             std::string err;
             int launches = 0;
-            int rc = vl_ensure(V, ctx->n, ctx->n_res_c, job.n_frames, err);
+            VlRun& R = ctx->vl_run[slot];
+            rc = vl_run_ensure(R, job.n_frames, err);
+            if (rc != 0) return fail(ctx, rc, "%s", err.c_str());
+            for (int x = 0; x < 2; x++) {
+                if (!ctx->vl_built[x]) CK(cudaEventCreateWithFlags(&ctx->vl_built[x], cudaEventDisableTiming));
+                if (!ctx->vl_info_ready[x]) CK(cudaEventCreateWithFlags(&ctx->vl_info_ready[x], cudaEventDisableTiming));
+                for (int t = 0; t < 2; t++)
+                    if (!ctx->vl_walked[x][t]) CK(cudaEventCreateWithFlags(&ctx->vl_walked[x][t], cudaEventDisableTiming));
+            }
+            // which scratch holds the list this batch walks, and does it have to be built?
+            //   ordinary call: the slot's own scratch, built from this batch;
+            //   chunk of a streamed trajectory: the shared list if there is a fresh one, else a new
+            //   one in the scratch no chunk in flight is walking.
+            int lx = slot;
+            bool build = true;
+            if (job.shared_list) {
+                if (have_shared && !ctx->vl_shared_stale) { lx = ctx->vl_shared; build = false; }
+                else if (ctx->vl_shared >= 0) lx = ctx->vl_shared ^ 1;
+            }
+            VlScratch& V = ctx->vl[lx];
+            rc = vl_ensure(V, ctx->n, ctx->n_res_c, err);
             if (rc != 0) return fail(ctx, rc, "%s", err.c_str());
             if (ctx->verlet_audit && !ctx->d_vl_audit) {
                 CK(cudaMalloc(&ctx->d_vl_audit, 2 * sizeof(unsigned long long)));
@@ -544,29 +622,40 @@ static int launch_frames(cmb_ctx* ctx, const FrameJob& job, int slot, cudaStream
             vj.n_ignored = ctx->n_ignored; vj.atom_table = job.atom_table; vj.res_table = job.res_table;
             vj.audit = ctx->verlet_audit; vj.d_audit = ctx->d_vl_audit;
             vj.max_rlist_factor = 0.01f * (float)ctx->verlet_max_rlist_pct;
-            for (int attempt = 0; attempt < 2; attempt++) {
-                vj.conservative_tiles = ctx->vl_conservative;
-                rc = vl_build(vj, V, stream, err, launches);
-                if (rc == 0) rc = vl_run_frames(vj, V, ctx->sm_count, stream, err, launches);
-                if (rc != 0 || ctx->path == 0 || ctx->vl_conservative) break;
-                // lists of several tiles: the outcome is read back (the fall back below needs the
-                // tripped frames on the host anyway).  A tile that overflowed the frame kernel's
-                // shared memory with the optimistic tile size (nothing was counted then: every
-                // frame is on the fall-back list) gets the list rebuilt with the pessimistic one.
-                CK(cudaMemcpyAsync(V.h_info + 1, &V.L.hdr->valid, sizeof(int), cudaMemcpyDeviceToHost, stream));
-                CK(cudaMemcpyAsync(V.h_info + 2, &V.L.hdr->fail_code, sizeof(int), cudaMemcpyDeviceToHost, stream));
-                CK(cudaStreamSynchronize(stream));
-                if (V.h_info[1] != 0 || V.h_info[2] < 9 || V.h_info[2] > 13) break;
-                ctx->vl_conservative = 1;
-                ctx->stats["vl_rebuilds"] += 1;
-                ctx->stats["vl_rebuild_code"] = V.h_info[2];
+            if (build) {
+                // earlier walks of the list this scratch held must be over before it is overwritten
+                for (int t = 0; t < 2; t++)
+                    if (ctx->vl_walked_set[lx][t]) CK(cudaStreamWaitEvent(stream, ctx->vl_walked[lx][t], 0));
+                for (int attempt = 0; attempt < 2; attempt++) {
+                    vj.conservative_tiles = ctx->vl_conservative;
+                    rc = vl_build(vj, V, stream, err, launches);
+                    if (rc != 0 || ctx->path == 0 || ctx->vl_conservative) break;
+                    // lists of several tiles: a tile that overflowed the frame kernel's shared memory
+                    // with the optimistic tile size gets the list rebuilt with the pessimistic one
+                    CK(cudaMemcpyAsync(R.h_info + 1, &V.L.hdr->valid, sizeof(int), cudaMemcpyDeviceToHost, stream));
+                    CK(cudaMemcpyAsync(R.h_info + 2, &V.L.hdr->fail_code, sizeof(int), cudaMemcpyDeviceToHost, stream));
+                    CK(cudaStreamSynchronize(stream));
+                    if (R.h_info[1] != 0 || R.h_info[2] < 9 || R.h_info[2] > 13) break;
+                    ctx->vl_conservative = 1;
+                    ctx->stats["vl_rebuilds"] += 1;
+                    ctx->stats["vl_rebuild_code"] = R.h_info[2];
+                }
+                if (rc != 0) return fail(ctx, rc, "%s", err.c_str());
+                CK(cudaEventRecord(ctx->vl_built[lx], stream));
+                ctx->stats["vl_builds"] += 1;
+                if (job.shared_list) { ctx->vl_shared = lx; ctx->vl_shared_stale = 0; }
+            } else {
+                CK(cudaStreamWaitEvent(stream, ctx->vl_built[lx], 0));
             }
+            rc = vl_run_frames(vj, V.L, R, ctx->sm_count, stream, err, launches);
             ctx->stats["kernel_launches"] += launches;
             if (rc != 0) return fail(ctx, rc, "%s", err.c_str());
+            CK(cudaEventRecord(ctx->vl_walked[lx][slot], stream));
+            ctx->vl_walked_set[lx][slot] = true;
             ctx->last_used_verlet = 1;
-            ctx->last_vl_slot = slot;
-            frame_list = V.L.tripped;
-            frame_count = &V.L.hdr->n_tripped;
+            ctx->last_vl_slot = lx;
+            frame_list = R.tripped;
+            frame_count = R.state;
         }
     }
     if (ctx->path == 0) {
@@ -589,7 +678,7 @@ static int launch_frames(cmb_ctx* ctx, const FrameJob& job, int slot, cudaStream
         if (grid > job.n_frames) grid = job.n_frames;
         if (!p.bm_in_smem) {
             size_t need = (size_t)grid * (size_t)p.bm_words * 4;
-            int rc = ensure_bytes(ctx, (void**)&ctx->d_bitmap[slot], &ctx->bitmap_bytes[slot], need);
+            rc = ensure_bytes(ctx, (void**)&ctx->d_bitmap[slot], &ctx->bitmap_bytes[slot], need);
             if (rc) return rc;
             p.g_bitmap = ctx->d_bitmap[slot];
         }
@@ -599,31 +688,39 @@ static int launch_frames(cmb_ctx* ctx, const FrameJob& job, int slot, cudaStream
         else fs_launch<512>(ctx, job, p, g, sm, stream);
         CK(cudaGetLastError());
         ctx->stats["kernel_launches"] += 1;
+        if (frame_list != nullptr && job.shared_list) {
+            // streamed trajectory: the tripped count of this chunk steers the rebuild of the shared
+            // list; it is looked at when the slot comes round again (never waited for)
+            cmb_ctx::Pending& P = ctx->pending[slot];
+            if (P.info && cudaEventQuery(ctx->vl_info_ready[slot]) == cudaSuccess &&
+                ctx->vl_run[slot].h_info[0] * 8 > ctx->vl_run[slot].h_info[3])
+                ctx->vl_shared_stale = 1;
+            ctx->vl_run[slot].h_info[3] = (int)job.n_frames;
+            CK(cudaMemcpyAsync(ctx->vl_run[slot].h_info, frame_count, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            CK(cudaEventRecord(ctx->vl_info_ready[slot], stream));
+            P.info = true;
+        }
         return CMB_OK;
     }
     // global-memory cell path
-    std::vector<std::pair<long long, long long>> runs;      // [first, last) frame ranges to process
     if (frame_list != nullptr) {
-        // fall back of the pair-list path: the list of tripped frames is read back (one stream
-        // synchronisation per call; a call is tens of milliseconds on this path) and processed
-        // as runs of consecutive frames
-        VlScratch& V = ctx->vl[slot];
-        CK(cudaMemcpyAsync(V.h_info, frame_count, sizeof(int), cudaMemcpyDeviceToHost, stream));
-        CK(cudaStreamSynchronize(stream));
-        const int n_trip = V.h_info[0];
-        if (n_trip == 0) return CMB_OK;
-        std::vector<int> trip((size_t)n_trip);
-        CK(cudaMemcpy(trip.data(), frame_list, sizeof(int) * (size_t)n_trip, cudaMemcpyDeviceToHost));
-        std::sort(trip.begin(), trip.end());
-        for (size_t k = 0; k < trip.size();) {
-            size_t e = k + 1;
-            while (e < trip.size() && trip[e] == trip[e - 1] + 1) e++;
-            runs.push_back({trip[k], (long long)trip[e - 1] + 1});
-            k = e;
-        }
-    } else {
-        runs.push_back({0, job.n_frames});
+        cmb_ctx::Pending& P = ctx->pending[slot];
+        CK(cudaMemcpyAsync(ctx->vl_run[slot].h_info, frame_count, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CK(cudaEventRecord(ctx->vl_info_ready[slot], stream));
+        P.active = true; P.job = job; P.stream = stream;
+        return defer_fallback ? CMB_OK : finish_pending(ctx, slot);
     }
+    std::vector<std::pair<long long, long long>> runs;
+    runs.push_back({0, job.n_frames});
+    return large_cells(ctx, job, slot, stream, runs);
+}
+
+// global-memory cell kernels over runs of consecutive frames of a job
+static int large_cells(cmb_ctx* ctx, const FrameJob& job, int slot, cudaStream_t stream,
+                       const std::vector<std::pair<long long, long long>>& runs)
+{
+    const float c2 = ctx->cutoff_f * ctx->cutoff_f;
+    unsigned long long* counters = job.ext_counters ? job.ext_counters : ctx->d_counters[slot];
     LargeJob lj;
     lj.xyz = job.xyz; lj.box = job.box; lj.n_frames = job.n_frames; lj.frame0 = job.frame0;
     lj.n = ctx->n; lj.meta = ctx->d_meta; lj.cutoff = ctx->cutoff_f; lj.c2 = c2;
@@ -768,6 +865,11 @@ static int stream_host_frames(cmb_ctx* ctx, const float* h_xyz_full, int n_total
     chunk_frames = pick_chunk(ctx, n_frames, chunk_frames);
     int rc0 = ensure_staging(ctx, chunk_frames, h_box != nullptr);
     if (rc0 != CMB_OK) return rc0;
+    // the chunks share ONE pair list, built from the first chunk (cmb_verlet.cuh: the guard decides
+    // frame by frame whether the list still covers a frame, whichever batch it was built from)
+    ctx->vl_shared = -1;
+    ctx->vl_shared_stale = 0;
+    for (int s = 0; s < 2; s++) ctx->pending[s].info = false;
     if (!direct) {
         const size_t need_pinned = (size_t)chunk_frames * frame_bytes;
         if (ctx->pinned_bytes < need_pinned) {
@@ -786,6 +888,10 @@ static int stream_host_frames(cmb_ctx* ctx, const float* h_xyz_full, int n_total
         const int s = c & 1;
         const int64_t nf = std::min<int64_t>(chunk_frames, n_frames - f0);
         const float* src = h_xyz_full + (size_t)f0 * (size_t)ctx->n * 3;
+        {   // the frames chunk c - 2 left to the cell kernels still sit in staging buffer s
+            int rc = finish_pending(ctx, s);
+            if (rc != CMB_OK) return rc;
+        }
         if (!direct) {
             if (c >= 2) CK(cudaEventSynchronize(ctx->copy_done[s]));   // pinned buffer s is free again
             gather_chunk(h_xyz_full, n_total, h_used, ctx->n, f0, nf, ctx->h_pinned[s], n_threads);
@@ -800,7 +906,12 @@ static int stream_host_frames(cmb_ctx* ctx, const float* h_xyz_full, int n_total
         FrameJob job = proto;
         job.xyz = ctx->d_stage_xyz[s]; job.box = h_box ? ctx->d_stage_box[s] : nullptr;
         job.n_frames = nf; job.frame0 = proto.frame0 + f0;
-        int rc = launch_frames(ctx, job, s, ctx->streams[s]);
+        job.shared_list = 1;
+        int rc = launch_frames(ctx, job, s, ctx->streams[s], true);
+        if (rc != CMB_OK) return rc;
+    }
+    for (int s = 0; s < 2; s++) {
+        int rc = finish_pending(ctx, s);
         if (rc != CMB_OK) return rc;
     }
     CK(cudaStreamSynchronize(ctx->streams[0]));

@@ -93,8 +93,6 @@ struct VlHeader {
     double hinv[9], h[9];
     float4 shift[27];
     GridS grid;
-    int n_tripped;             // frames on the fall-back list
-    int next_item;             // work queue of the frame kernel
     int fail_code;             // why valid == 0 (diagnostics)
 };
 
@@ -113,16 +111,24 @@ struct VlList {
     unsigned short* row_bundle;  // [row_cap] bundle (tile relative) of each row: its lanes are segments 32 b + lane
     unsigned* entries;         // [row_cap * VL_ROW] 16 slot_i | 16 slot_j << 16 (byte offsets into the position array)
     uint2* seg_pair;           // [entry_cap] {compact residue lo, hi} in length-sorted order
-    int* tripped;              // [frame_cap] frames of the current call that fall back
-    int* frame_flag;           // [frame_cap] 1: the frame is on the fall-back list (multi-tile lists: set by vl_guard)
+    const float4* ref_w;       // [n] wrapped reference position of every atom (guard pass)
     long long entry_cap, slot_cap, row_cap;
+};
+
+// State of ONE walk over a list (a list outlives the batch it was built from: the chunks of a
+// host trajectory all walk the list built from the first one, on two streams).
+struct VlRun {
+    int* state = nullptr;      // device [2]: frames on the fall-back list, work queue of the frame kernel
+    int* tripped = nullptr;    // [frame_cap] frames of the current call that fall back
+    int* frame_flag = nullptr; // [frame_cap] 1: the frame is on the fall-back list (multi-tile lists: set by vl_guard)
+    long long frame_cap = 0;
+    int* h_info = nullptr;     // pinned [4]: read-backs of the large path (tripped count, list validity, fail code)
 };
 
 // builder scratch
 struct VlScratch {
     int cap_atoms = 0;
     long long entry_cap = 0;
-    long long frame_cap = 0;
     VlList L{};
     float4* ref_raw = nullptr;      // [n] mean of the unwrapped samples
     float4* ref_w = nullptr;        // [n] wrapped reference {x, y, z, cell}
@@ -150,14 +156,12 @@ struct VlScratch {
     long long bundle_cap = 0;
     void* cub_tmp = nullptr;
     size_t cub_bytes = 0;
-    int* h_info = nullptr;          // pinned: n_tripped read back by the large path
 };
 
 inline void vl_free(VlScratch& S)
 {
     cudaFree(S.L.hdr); cudaFree(S.L.tiles); cudaFree(S.L.slot_word); cudaFree(S.L.slot_ref);
-    cudaFree(S.L.row_bundle); cudaFree(S.L.entries); cudaFree(S.L.seg_pair); cudaFree(S.L.tripped);
-    cudaFree(S.L.frame_flag);
+    cudaFree(S.L.row_bundle); cudaFree(S.L.entries); cudaFree(S.L.seg_pair);
     cudaFree(S.ref_raw); cudaFree(S.ref_w); cudaFree(S.atomrank); cudaFree(S.cellcnt); cudaFree(S.cellptr);
     cudaFree(S.sref); cudaFree(S.smeta); cudaFree(S.scell); cudaFree(S.tile_of_res);
     for (int k = 0; k < 2; k++) {
@@ -167,8 +171,14 @@ inline void vl_free(VlScratch& S)
     cudaFree(S.seg_key); cudaFree(S.seg_len); cudaFree(S.seg_start); cudaFree(S.n_runs); cudaFree(S.slot_uniq);
     cudaFree(S.tile_seg0); cudaFree(S.tile_bundle0); cudaFree(S.tile_slot0); cudaFree(S.bundle_row0);
     cudaFree(S.cub_tmp);
-    if (S.h_info) cudaFreeHost(S.h_info);
     S = VlScratch();
+}
+
+inline void vl_run_free(VlRun& R)
+{
+    cudaFree(R.state); cudaFree(R.tripped); cudaFree(R.frame_flag);
+    if (R.h_info) cudaFreeHost(R.h_info);
+    R = VlRun();
 }
 
 // ----- small helpers --------------------------------------------------------------------
@@ -234,7 +244,6 @@ __global__ void vl_init(VlHeader* hdr, const float* box, int periodic, int rbits
     H.d_max_bits = 0u; H.a_max_bits = 0u;
     for (int k = 0; k < 3; k++) { H.bb_lo[k] = 0xffffffffu; H.bb_hi[k] = 0u; }
     H.periodic = periodic;
-    H.n_tripped = 0; H.next_item = 0;
     for (int k = 0; k < 9; k++) { H.hinv[k] = 0.0; H.h[k] = 0.0; H.box_bits[k] = 0u; }
     if (periodic) {
         for (int k = 0; k < 9; k++) H.box_bits[k] = __float_as_uint(box[k]);
@@ -904,7 +913,7 @@ __device__ __forceinline__ void vl_exact_account(uint2 e, const float* __restric
 }
 
 template <int FLAGS>
-__global__ void __launch_bounds__(VL_THREADS, 1) vl_frames(const VlFrameParams p, const VlList L)
+__global__ void __launch_bounds__(VL_THREADS, 1) vl_frames(const VlFrameParams p, const VlList L, const VlRun R)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     float4* pos = reinterpret_cast<float4*>(smem + VL_SM_POS);
@@ -940,7 +949,7 @@ __global__ void __launch_bounds__(VL_THREADS, 1) vl_frames(const VlFrameParams p
     __syncthreads();
 
     for (;;) {
-        if (tid == 0) misc[0] = atomicAdd(&L.hdr->next_item, 1);
+        if (tid == 0) misc[0] = atomicAdd(&R.state[1], 1);
         __syncthreads();
         const long long item = misc[0];
         __syncthreads();
@@ -1010,7 +1019,7 @@ __global__ void __launch_bounds__(VL_THREADS, 1) vl_frames(const VlFrameParams p
             // decision from the guard pass vl_guard, which looks at every atom of the frame; a
             // single tile holds every atom as a slot and decides here)
             int trip = 0;
-            if (multi_tile) trip = L.frame_flag[f];
+            if (multi_tile) trip = R.frame_flag[f];
             else if (p.box != nullptr && tid < 9)
                 trip = __float_as_uint(__ldg(&p.box[f * 9 + tid])) != H.box_bits[tid];
             // (the parked pairs above read the atom index in pos[].w while other threads rewrite
@@ -1052,8 +1061,8 @@ __global__ void __launch_bounds__(VL_THREADS, 1) vl_frames(const VlFrameParams p
             }
             if (trip) {
                 if (tid == 0 && !multi_tile) {
-                    const int w = atomicAdd(&L.hdr->n_tripped, 1);
-                    L.tripped[w] = (int)f;
+                    const int w = atomicAdd(&R.state[0], 1);
+                    R.tripped[w] = (int)f;
                 }
                 __syncthreads();
                 continue;
@@ -1187,10 +1196,10 @@ __global__ void __launch_bounds__(VL_THREADS, 1) vl_frames(const VlFrameParams p
 // so the trip decision is taken once per frame, over all atoms, before the frame kernel runs;
 // tripped frames get their flag set and every tile skips them.  (Single-tile lists check inside
 // the frame kernel: the tile sees every atom.)  grid = (atom blocks, frames).
-__global__ void __launch_bounds__(256) vl_guard(VlHeader* hdr, const float* __restrict__ xyz,
+__global__ void __launch_bounds__(256) vl_guard(const VlHeader* hdr, const float* __restrict__ xyz,
                                                 const float* __restrict__ box, long long f0, int n,
                                                 const float4* __restrict__ ref_w, int* __restrict__ frame_flag,
-                                                int* __restrict__ tripped)
+                                                int* __restrict__ tripped, int* __restrict__ state)
 {
     __shared__ double hs[18];
     if (!hdr->valid || hdr->n_tiles <= 1) return;
@@ -1215,19 +1224,24 @@ __global__ void __launch_bounds__(256) vl_guard(VlHeader* hdr, const float* __re
     }
     trip = __syncthreads_or(trip);
     if (trip && threadIdx.x == 0 && atomicExch(&frame_flag[f], 1) == 0) {
-        const int w = atomicAdd(&hdr->n_tripped, 1);
+        const int w = atomicAdd(&state[0], 1);
         tripped[w] = (int)f;
     }
 }
 
 // an invalid list puts every frame on the fall-back list
-__global__ void __launch_bounds__(256) vl_all_tripped(VlHeader* hdr, int* __restrict__ tripped, long long n_frames)
+__global__ void __launch_bounds__(256) vl_all_tripped(const VlHeader* hdr, int* __restrict__ tripped,
+                                                      int* __restrict__ state, long long n_frames)
 {
-    if (hdr->valid) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) state[1] = 0;          // work queue of the frame kernel
+    if (hdr->valid) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) state[0] = 0;
+        return;
+    }
     for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < n_frames;
          f += (long long)gridDim.x * blockDim.x)
         tripped[f] = (int)f;
-    if (blockIdx.x == 0 && threadIdx.x == 0) hdr->n_tripped = (int)n_frames;
+    if (blockIdx.x == 0 && threadIdx.x == 0) state[0] = (int)n_frames;
 }
 
 // ----- host driver ----------------------------------------------------------------------------
@@ -1259,12 +1273,25 @@ inline int vl_bits(long long v)       // bits needed for values in [0, v)
     return b;
 }
 
-inline int vl_ensure(VlScratch& S, int n, int n_res_c, long long n_frames, std::string& err)
+inline int vl_run_ensure(VlRun& R, long long n_frames, std::string& err)
 {
-    if (S.cap_atoms < n || S.frame_cap < n_frames) {
+    if (R.frame_cap < n_frames || R.state == nullptr) {
+        vl_run_free(R);
+        const long long frames = std::max<long long>(n_frames, 1024);
+        VL_CK(cudaMalloc(&R.state, sizeof(int) * 2));
+        VL_CK(cudaMalloc(&R.tripped, sizeof(int) * (size_t)frames));
+        VL_CK(cudaMalloc(&R.frame_flag, sizeof(int) * (size_t)frames));
+        VL_CK(cudaMallocHost(&R.h_info, 4 * 4));
+        R.frame_cap = frames;
+    }
+    return 0;
+}
+
+inline int vl_ensure(VlScratch& S, int n, int n_res_c, std::string& err)
+{
+    if (S.cap_atoms < n) {
         vl_free(S);
         const long long E = std::max<long long>((long long)n * 80, 1 << 15);
-        const long long frames = std::max<long long>(n_frames, 1024);
         if (2 * E + n > 0x7fffffffll) { err = "system too large for the pair-list path"; return -4; }
         S.entry_cap = E;
         S.L.entry_cap = E;
@@ -1278,10 +1305,9 @@ inline int vl_ensure(VlScratch& S, int n, int n_res_c, long long n_frames, std::
         VL_CK(cudaMalloc(&S.L.row_bundle, sizeof(unsigned short) * (size_t)S.L.row_cap));
         VL_CK(cudaMalloc(&S.L.entries, sizeof(unsigned) * (size_t)S.L.row_cap * VL_ROW));
         VL_CK(cudaMalloc(&S.L.seg_pair, sizeof(uint2) * (size_t)E));
-        VL_CK(cudaMalloc(&S.L.tripped, sizeof(int) * (size_t)frames));
-        VL_CK(cudaMalloc(&S.L.frame_flag, sizeof(int) * (size_t)frames));
         VL_CK(cudaMalloc(&S.ref_raw, sizeof(float4) * (size_t)n));
         VL_CK(cudaMalloc(&S.ref_w, sizeof(float4) * (size_t)n));
+        S.L.ref_w = S.ref_w;
         VL_CK(cudaMalloc(&S.atomrank, sizeof(int) * (size_t)n));
         VL_CK(cudaMalloc(&S.cellcnt, sizeof(int) * (size_t)(VL_MAXC + 1)));
         VL_CK(cudaMalloc(&S.cellptr, sizeof(int) * (size_t)(VL_MAXC + 1)));
@@ -1305,7 +1331,6 @@ inline int vl_ensure(VlScratch& S, int n, int n_res_c, long long n_frames, std::
         VL_CK(cudaMalloc(&S.tile_bundle0, 4 * (VL_MAX_TILES + 1)));
         VL_CK(cudaMalloc(&S.tile_slot0, 4 * (VL_MAX_TILES + 1)));
         VL_CK(cudaMalloc(&S.bundle_row0, 4 * (size_t)(S.bundle_cap + 1)));
-        VL_CK(cudaMallocHost(&S.h_info, 4 * 4));
         size_t need = 0, t = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, t, S.rec_key[0], S.rec_key[1], S.rec_val[0], S.rec_val[1], (int)E, 0, 64);
         need = std::max(need, t);
@@ -1322,7 +1347,6 @@ inline int vl_ensure(VlScratch& S, int n, int n_res_c, long long n_frames, std::
         VL_CK(cudaMalloc(&S.cub_tmp, need + 256));
         S.cub_bytes = need + 256;
         S.cap_atoms = n;
-        S.frame_cap = frames;
     }
     return 0;
 }
@@ -1386,9 +1410,11 @@ inline int vl_build(const VlJob& job, VlScratch& S, cudaStream_t st, std::string
     return 0;
 }
 
-// Walk the list over the frames of the job; frames that cannot use it end up on S.L.tripped
-// (count in hdr->n_tripped) for the caller's fall back.
-inline int vl_run_frames(const VlJob& job, VlScratch& S, int sm_count, cudaStream_t st, std::string& err, int& launches)
+// Walk a list over the frames of the job; frames that cannot use it end up on R.tripped (count in
+// R.state[0]) for the caller's fall back.  The list may have been built from another batch of the
+// same trajectory: the guard decides frame by frame.
+inline int vl_run_frames(const VlJob& job, const VlList& L, const VlRun& R, int sm_count, cudaStream_t st,
+                         std::string& err, int& launches)
 {
     static bool attr_set[2] = {false, false};
     if (!attr_set[0]) {
@@ -1399,14 +1425,14 @@ inline int vl_run_frames(const VlJob& job, VlScratch& S, int sm_count, cudaStrea
         VL_CK(cudaFuncSetAttribute(vl_frames<VL_AUDIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, VL_SM_TOTAL));
         attr_set[1] = true;
     }
-    vl_all_tripped<<<64, 256, 0, st>>>(S.L.hdr, S.L.tripped, job.n_frames);
+    vl_all_tripped<<<64, 256, 0, st>>>(L.hdr, R.tripped, R.state, job.n_frames);
     if (job.n > VL_SINGLE_TILE_ATOMS) {
-        VL_CK(cudaMemsetAsync(S.L.frame_flag, 0, sizeof(int) * (size_t)job.n_frames, st));
+        VL_CK(cudaMemsetAsync(R.frame_flag, 0, sizeof(int) * (size_t)job.n_frames, st));
         const int blocks = std::max(1, std::min((job.n + 255) / 256, 64));
         for (long long f0 = 0; f0 < job.n_frames; f0 += 32768) {
             const unsigned nf = (unsigned)std::min<long long>(32768, job.n_frames - f0);
-            vl_guard<<<dim3(blocks, nf), 256, 0, st>>>(S.L.hdr, job.xyz, job.box, f0, job.n, S.ref_w, S.L.frame_flag,
-                                                       S.L.tripped);
+            vl_guard<<<dim3(blocks, nf), 256, 0, st>>>(L.hdr, job.xyz, job.box, f0, job.n, L.ref_w, R.frame_flag,
+                                                       R.tripped, R.state);
             launches++;
         }
     }
@@ -1414,8 +1440,8 @@ inline int vl_run_frames(const VlJob& job, VlScratch& S, int sm_count, cudaStrea
     p.xyz = job.xyz; p.box = job.box; p.n_frames = job.n_frames; p.n = job.n; p.n_res_c = job.n_res_c; p.c2 = job.c2;
     p.rounds = job.n <= VL_SINGLE_TILE_ATOMS ? 4 : 6;
     p.atom_table = job.atom_table; p.res_table = job.res_table; p.audit = job.d_audit;
-    if (job.audit) vl_frames<VL_AUDIT><<<sm_count, VL_THREADS, VL_SM_TOTAL, st>>>(p, S.L);
-    else vl_frames<0><<<sm_count, VL_THREADS, VL_SM_TOTAL, st>>>(p, S.L);
+    if (job.audit) vl_frames<VL_AUDIT><<<sm_count, VL_THREADS, VL_SM_TOTAL, st>>>(p, L, R);
+    else vl_frames<0><<<sm_count, VL_THREADS, VL_SM_TOTAL, st>>>(p, L, R);
     VL_CK(cudaGetLastError());
     launches += 2;
     return 0;

@@ -6,6 +6,7 @@ PyTorch is used only for device memory, streams and (in ``parallel.py``)
 CUDA device raises RuntimeError.
 """
 import ctypes
+import time
 
 import numpy as np
 import torch
@@ -568,8 +569,13 @@ class ContactEngine(object):
         n_frames = int(xyz.shape[0])
         self._set_table_mode(None, None)
         dev = self.device
+        marks = [("start", time.perf_counter())]
         hints = self.__dict__.setdefault("_keys_hint", {})
         hint = hints.get(self._system_key)
+        # Repeated calls for a system copy the result into pinned memory from torch's caching host
+        # allocator (PCIe speed; the block is recycled once the returned arrays are dropped).  The
+        # first call stays pageable: pinning 80 MB costs several times more than one slower copy.
+        repeated = hint is not None
         if hint is None:
             # keys per frame from a counting pass over a short prefix (nothing is written)
             k = min(n_frames, 64)
@@ -599,6 +605,7 @@ class ContactEngine(object):
                         self._ctx, _ptr(xyz), int(xyz.shape[1]), _ptr(used), _ptr(box), n_frames, int(frame0), 0, 0,
                         _ptr(ak), cap_a, _ptr(rk), cap_r, _ptr(counts)), "cmb_frame_contacts_host")
             na, nr = (int(v) for v in counts[:2].cpu().numpy())
+            marks.append(("emit", time.perf_counter()))
             if na <= cap_a and nr <= cap_r:
                 break
             cap_a, cap_r = max(cap_a, na + na // 8), max(cap_r, nr + nr // 8)
@@ -622,12 +629,15 @@ class ContactEngine(object):
                 self._check(self._L.cmb_keys_to_csr(self._ctx, _ptr(keys), n, max(n_frames, 1), int(frame0), _ptr(d_map),
                                                     _ptr(d_ptr), _ptr(d_ij[0]), _ptr(d_ij[1]), _stream_ptr(dev)),
                             "cmb_keys_to_csr")
-                h_ptr = torch.empty(n_frames + 1, dtype=torch.int64, pin_memory=True)
-                h_ij = torch.empty((2, max(n, 1)), dtype=torch.int32, pin_memory=True)
+                h_ptr = torch.empty(n_frames + 1, dtype=torch.int64, pin_memory=repeated)
+                h_ij = torch.empty((2, max(n, 1)), dtype=torch.int32, pin_memory=repeated)
                 h_ptr.copy_(d_ptr, non_blocking=True)
                 h_ij.copy_(d_ij, non_blocking=True)
                 out.append((h_ptr, h_ij, n))
+        marks.append(("launch_sort_csr_copy", time.perf_counter()))
         stream.synchronize()
+        marks.append(("sync", time.perf_counter()))
+        self.last_timing = {b[0]: b[1] - a[1] for a, b in zip(marks, marks[1:])}
         return tuple((h_ptr.numpy(), h_ij[0, :n].numpy(), h_ij[1, :n].numpy()) for h_ptr, h_ij, n in out)
 
     def _frame_contacts_once(self, xyz, box, frame0, ak, cap_a, rk, cap_r, atom_table, res_table,

@@ -18,7 +18,7 @@ h_box.copy_(torch.as_tensor(system.box).reshape(1, 3, 3).expand(F, 3, 3))
 torch.cuda.synchronize()
 traj = cm.Trajectory(h_xyz.numpy(), top, h_box.numpy())
 everyone = np.arange(n)
-for chunk in (0, 600, 300, 150, 75):
+for chunk in (0, 10000, 5000, 2500, 1250, 625, 300):
     orig = engine.accumulate_host
     engine.accumulate_host = lambda x, b, a, r, chunk_frames=0, _o=orig, _c=chunk: _o(x, b, a, r, chunk_frames=_c)
     for rep in range(5):
@@ -34,3 +34,14 @@ for rep in range(3):
     atom_t.zero_(); res_t.zero_(); torch.cuda.synchronize()
     t0 = time.perf_counter(); engine.accumulate_host(h_xyz.numpy(), h_box.numpy(), atom_t, res_t); dt = time.perf_counter() - t0
 print("cmb_accumulate_host alone: %.2f ms" % (dt * 1e3))
+for mode in (0, 1):
+    engine.set_option("verlet", mode)
+    for rep in range(3):
+        atom_t.zero_(); res_t.zero_(); torch.cuda.synchronize()
+        t0 = time.perf_counter(); engine.accumulate_host(h_xyz.numpy(), h_box.numpy(), atom_t, res_t); dt = time.perf_counter() - t0
+    print("cmb_accumulate_host alone, verlet=%d: %.2f ms" % (mode, dt * 1e3))
+# copy only
+d = torch.empty((F, n, 3), dtype=torch.float32, device=dev)
+for rep in range(3):
+    torch.cuda.synchronize(); t0 = time.perf_counter(); d.copy_(h_xyz, non_blocking=True); torch.cuda.synchronize(); dt = time.perf_counter() - t0
+print("plain H2D of the trajectory: %.2f ms (%.1f GB/s)" % (dt * 1e3, F * n * 12 / dt / 1e9))
