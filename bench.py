@@ -53,7 +53,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="s1", choices=["s1", "s3"],
                     help="s1: BASELINE.json configs[1] (the headline); s3: configs[3], 100 000-atom triclinic system")
-    ap.add_argument("--frames", type=int, default=0, help="frames per GPU (default 10000 for s1, 1024 for s3)")
+    ap.add_argument("--frames", type=int, default=0, help="frames per GPU (default 10000 for s1, 4096 for s3)")
     ap.add_argument("--cpu-frames", type=int, default=0, help="frames of the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -61,7 +61,7 @@ def parse_args():
     ap.add_argument("--no-pair-list", action="store_true", help="cell kernels only (no frame-batch pair list)")
     args = ap.parse_args()
     if args.frames <= 0:
-        args.frames = N_FRAMES if args.workload == "s1" else 1024
+        args.frames = N_FRAMES if args.workload == "s1" else 4096
     return args
 
 

@@ -767,7 +767,7 @@ static int64_t pick_chunk(const cmb_ctx* ctx, int64_t n_frames, int64_t chunk_fr
     const size_t frame_bytes = (size_t)ctx->n * 12;
     if (chunk_frames <= 0 && ctx->stage_chunk_frames > 0) chunk_frames = ctx->stage_chunk_frames;
     if (chunk_frames <= 0) {
-        chunk_frames = (int64_t)((32ull << 20) / frame_bytes);
+        chunk_frames = (int64_t)((80ull << 20) / frame_bytes);
         // at least four chunks so copies and kernels overlap, but keep every SM busy
         const int64_t quarter = (n_frames + 3) / 4;
         if (chunk_frames > quarter) chunk_frames = quarter;
@@ -1202,15 +1202,17 @@ extern "C" int cmb_export_sorted(cmb_ctx* ctx, const void* d_table, int64_t n_el
         if (blocks < 1) blocks = 1;
         const long long n_warps = blocks * (EO_THREADS / 32);
         long long span = (nvec + n_warps - 1) / n_warps;
-        span = (span + 31) / 32 * 32;                      // whole warp iterations
-        if (span < 32) span = 32;
-        int rc = ensure_bytes(ctx, &ctx->d_tmp, &ctx->tmp_bytes, (size_t)n_warps * sizeof(int));
+        span = (span + 1023) / 1024 * 1024;                // whole flag words (32 warp iterations of 32 vectors)
+        if (span < 1024) span = 1024;
+        const size_t flag_words = (size_t)n_warps * (size_t)(span / 1024);
+        int rc = ensure_bytes(ctx, &ctx->d_tmp, &ctx->tmp_bytes, (size_t)n_warps * sizeof(int) + flag_words * sizeof(unsigned));
         if (rc) return rc;
         int* counts = reinterpret_cast<int*>(ctx->d_tmp);
+        unsigned int* flags = reinterpret_cast<unsigned int*>(counts + n_warps);
         k_export_count<<<(unsigned)blocks, EO_THREADS, 0, st>>>(reinterpret_cast<const unsigned int*>(d_table), n_elems,
-                                                                span, counts);
+                                                                span, counts, flags);
         k_export_write<<<(unsigned)blocks, EO_THREADS, 0, st>>>(reinterpret_cast<const unsigned int*>(d_table), n_elems,
-                                                                span, counts, cap,
+                                                                span, counts, flags, cap,
                                                                 reinterpret_cast<unsigned long long*>(d_packed),
                                                                 reinterpret_cast<unsigned long long*>(d_n));
         CK(cudaGetLastError());

@@ -197,16 +197,40 @@ constexpr int EO_THREADS = 256;
 
 __device__ __forceinline__ int eo_count4(const uint4& q) { return (q.x != 0) + (q.y != 0) + (q.z != 0) + (q.w != 0); }
 
+// `flags`: one bit per warp iteration (32 vectors = 512 bytes of table), one word per 32
+// iterations of a warp's span (span_vec is a multiple of 1024 vectors): the write pass only
+// revisits the iterations that hold something -- a 40 GB table with 3 M entries is read ONCE.
 __global__ void __launch_bounds__(EO_THREADS) k_export_count(const unsigned int* __restrict__ table, long long n_elems,
-                                                             long long span_vec, int* __restrict__ counts)
+                                                             long long span_vec, int* __restrict__ counts,
+                                                             unsigned int* __restrict__ flags)
 {
     const int lane = threadIdx.x & 31;
     const long long warp = (long long)blockIdx.x * (EO_THREADS / 32) + (threadIdx.x >> 5);
     const long long nvec = n_elems >> 2;
     const uint4* __restrict__ t4 = reinterpret_cast<const uint4*>(table);
     const long long v0 = warp * span_vec, v1 = min(nvec, v0 + span_vec);
+    const long long words_per_warp = span_vec / 1024;
     int mine = 0;
-    for (long long v = v0 + lane; v < v1; v += 32) mine += eo_count4(__ldg(&t4[v]));
+    for (long long g = 0; g < words_per_warp; g++) {
+        const long long gb = v0 + g * 1024;
+        if (gb >= v1) { if (lane == 0) flags[warp * words_per_warp + g] = 0u; continue; }
+        unsigned word = 0u;
+#pragma unroll 1
+        for (int i0 = 0; i0 < 32; i0 += 8) {
+            int c[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {               // eight independent 16-byte loads in flight per thread
+                const long long v = gb + (long long)(i0 + k) * 32 + lane;
+                c[k] = v < v1 ? eo_count4(__ldg(&t4[v])) : 0;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                mine += c[k];
+                if (__any_sync(0xffffffffu, c[k] != 0)) word |= 1u << (i0 + k);
+            }
+        }
+        if (lane == 0) flags[warp * words_per_warp + g] = word;
+    }
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
     if (lane == 0) counts[warp] = mine;
@@ -214,6 +238,7 @@ __global__ void __launch_bounds__(EO_THREADS) k_export_count(const unsigned int*
 
 __global__ void __launch_bounds__(EO_THREADS) k_export_write(const unsigned int* __restrict__ table, long long n_elems,
                                                              long long span_vec, const int* __restrict__ counts,
+                                                             const unsigned int* __restrict__ flags,
                                                              long long cap, unsigned long long* __restrict__ out,
                                                              unsigned long long* __restrict__ out_n)
 {
@@ -242,29 +267,37 @@ __global__ void __launch_bounds__(EO_THREADS) k_export_write(const unsigned int*
     const long long nvec = n_elems >> 2;
     const uint4* __restrict__ t4 = reinterpret_cast<const uint4*>(table);
     const long long v0 = warp * span_vec, v1 = min(nvec, v0 + span_vec);
+    const long long words_per_warp = span_vec / 1024;
     bool wide = false;
-    for (long long vb = v0; vb < v1; vb += 32) {            // uniform trip count per warp
-        const long long v = vb + lane;
-        uint4 q = make_uint4(0u, 0u, 0u, 0u);
-        if (v < v1) q = __ldg(&t4[v]);
-        const unsigned vals[4] = {q.x, q.y, q.z, q.w};
-        const int mine = eo_count4(q);
-        int incl = mine;
+    if (counts[warp] != 0) {
+        for (long long g = 0; g < words_per_warp; g++) {
+            unsigned word = __ldg(&flags[warp * words_per_warp + g]);      // uniform over the warp
+            while (word) {
+                const int it = __ffs(word) - 1;
+                word &= word - 1;
+                const long long v = v0 + g * 1024 + (long long)it * 32 + lane;
+                uint4 q = make_uint4(0u, 0u, 0u, 0u);
+                if (v < v1) q = __ldg(&t4[v]);
+                const unsigned vals[4] = {q.x, q.y, q.z, q.w};
+                const int mine = eo_count4(q);
+                int incl = mine;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int u = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += u;
-        }
-        long long w = base + (incl - mine);
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int u = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += u;
+                }
+                long long w = base + (incl - mine);
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            if (vals[k]) {
-                if (w < cap) out[w] = ((unsigned long long)(v * 4 + k) << 24) | (unsigned long long)(vals[k] & 0xffffffu);
-                wide = wide || (vals[k] >> 24);
-                w++;
+                for (int k = 0; k < 4; k++) {
+                    if (vals[k]) {
+                        if (w < cap) out[w] = ((unsigned long long)(v * 4 + k) << 24) | (unsigned long long)(vals[k] & 0xffffffu);
+                        wide = wide || (vals[k] >> 24);
+                        w++;
+                    }
+                }
+                base += __shfl_sync(0xffffffffu, incl, 31);
             }
         }
-        base += __shfl_sync(0xffffffffu, incl, 31);
     }
     if (warp == n_warps - 1 && lane == 0) {
         // tail (n_elems % 4) and the total
