@@ -17,6 +17,7 @@
 #include "cmb_frames_large.cuh"
 #include "cmb_frames_small.cuh"
 #include "cmb_verlet.cuh"
+#include "cmb_prune.cuh"
 
 using namespace cmb;
 
@@ -105,6 +106,8 @@ struct cmb_ctx {
     int pair_tasks = 1;
     int stage_pageable = 1;                   // pageable host input goes through threaded pinned staging
     long long stage_chunk_frames = 0;         // frames per staging chunk of the host paths (0: automatic)
+    int prune = 1;                            // NearestAtoms / MinimumDistanceCounter: cell-pruned search (cmb_prune.cuh)
+    PgScratch pg;
     int large_batch = 1;                      // global-memory cell path: 0 one frame at a time, 1 auto, 2 batched whenever possible
     int atom_log2 = 0, res_log2 = 0;          // hashed count tables when > 0 (cmb_set_table_mode)
     unsigned long long* d_hstats = nullptr;   // [4] new atom keys, new residue keys, parked hits, failed re-inserts
@@ -213,6 +216,7 @@ extern "C" void cmb_ctx_destroy(cmb_ctx* ctx)
         for (int t = 0; t < 2; t++)
             if (ctx->vl_walked[s][t]) cudaEventDestroy(ctx->vl_walked[s][t]);
     }
+    pg_free(ctx->pg);
     cudaFree(ctx->d_res_anchor);
     cudaFree(ctx->d_vl_audit);
     cudaFree(ctx->d_tmp);
@@ -248,6 +252,7 @@ extern "C" int cmb_set_option(cmb_ctx* ctx, const char* name, int64_t value)
         return CMB_OK;
     }
     if (!strcmp(name, "verlet_audit")) { ctx->verlet_audit = value != 0; return CMB_OK; }
+    if (!strcmp(name, "prune")) { ctx->prune = value != 0; return CMB_OK; }
     if (!strcmp(name, "verlet_conservative_tiles")) { ctx->vl_conservative = value != 0; return CMB_OK; }
     if (!strcmp(name, "verlet_max_rlist_pct")) {
         if (value < 101 || value > 400) return fail(ctx, CMB_ERR_ARG, "verlet_max_rlist_pct out of range");
@@ -274,6 +279,8 @@ extern "C" int cmb_get_stat(cmb_ctx* ctx, const char* name, int64_t* value)
     if (!strcmp(name, "max_cells")) { *value = ctx->fs_maxc; return CMB_OK; }
     if (!strcmp(name, "kernel_launches")) { *value = ctx->stats["kernel_launches"]; return CMB_OK; }
     if (!strcmp(name, "vl_used")) { *value = ctx->last_used_verlet; return CMB_OK; }
+    if (!strcmp(name, "pruned_frames")) { *value = ctx->stats["pruned_frames"]; return CMB_OK; }
+    if (!strcmp(name, "brute_frames")) { *value = ctx->stats["brute_frames"]; return CMB_OK; }
     if (!strcmp(name, "vl_rebuilds")) { *value = ctx->stats["vl_rebuilds"]; return CMB_OK; }
     if (!strcmp(name, "vl_rebuild_code")) { *value = ctx->stats["vl_rebuild_code"]; return CMB_OK; }
     if (!strcmp(name, "vl_conservative")) { *value = ctx->vl_conservative; return CMB_OK; }
@@ -1297,6 +1304,30 @@ extern "C" int cmb_synth_frames(cmb_ctx* ctx, const float* d_base, const int32_t
 // ---------------------------------------------------------------------------------
 // min-distance analyses
 // ---------------------------------------------------------------------------------
+// brute force over the whole product for frames [f0, f0 + nf) (at most 32768 frames)
+static int min_dist_brute(cmb_ctx* ctx, const float* d_xyz, const float* d_box, int64_t f0, int64_t nf, int n_atoms,
+                          const int32_t* d_query, int n_q, const int32_t* d_haystack, int n_h, int orthogonal,
+                          float* d_min, int64_t* d_arg, cudaStream_t st)
+{
+    const int n_chunks = (n_h + MD_HCHUNK - 1) / MD_HCHUNK;
+    const size_t need = (size_t)nf * n_chunks * (sizeof(float) + sizeof(long long)) + 256;
+    int rc = ensure_bytes(ctx, &ctx->d_tmp, &ctx->tmp_bytes, need);
+    if (rc) return rc;
+    long long* part_idx = (long long*)ctx->d_tmp;
+    float* part_d = (float*)((char*)ctx->d_tmp + (size_t)nf * n_chunks * sizeof(long long));
+    dim3 grid((unsigned)n_chunks, (unsigned)nf);
+    k_min_dist_partial<<<grid, MD_THREADS, 0, st>>>(
+        d_xyz + (size_t)f0 * n_atoms * 3, d_box ? d_box + (size_t)f0 * 9 : nullptr, n_atoms, d_query, n_q,
+        d_haystack, n_h, orthogonal, part_d, part_idx);
+    CK(cudaGetLastError());
+    k_min_dist_final<<<(unsigned)((nf + 127) / 128), 128, 0, st>>>(part_d, part_idx, n_chunks, nf, d_min + f0,
+                                                                   (long long*)d_arg + f0);
+    CK(cudaGetLastError());
+    ctx->stats["kernel_launches"] += 2;
+    ctx->stats["brute_frames"] += nf;
+    return CMB_OK;
+}
+
 extern "C" int cmb_min_dist(cmb_ctx* ctx, const float* d_xyz, const float* d_box, int64_t n_frames,
                             int n_atoms, const int32_t* d_query, int n_q, const int32_t* d_haystack, int n_h,
                             int orthogonal, float* d_min, int64_t* d_arg, void* stream)
@@ -1306,24 +1337,61 @@ extern "C" int cmb_min_dist(cmb_ctx* ctx, const float* d_xyz, const float* d_box
         return fail(ctx, CMB_ERR_ARG, "bad min_dist arguments");
     if (n_frames <= 0) return CMB_OK;
     CK(cudaSetDevice(ctx->device));
-    const int n_chunks = (n_h + MD_HCHUNK - 1) / MD_HCHUNK;
-    const int64_t fmax = 32768;   // gridDim.y limit is 65535
-    for (int64_t f0 = 0; f0 < n_frames; f0 += fmax) {
-        const int64_t nf = std::min<int64_t>(fmax, n_frames - f0);
-        const size_t need = (size_t)nf * n_chunks * (sizeof(float) + sizeof(long long)) + 256;
-        int rc = ensure_bytes(ctx, &ctx->d_tmp, &ctx->tmp_bytes, need);
+    cudaStream_t st = (cudaStream_t)stream;
+    // Cell-pruned search (cmb_prune.cuh) when the product is large enough to pay for the binning:
+    // the haystack atoms of a batch of frames are binned, every query atom searches its 27-cell
+    // stencil, and the frames whose stencil minimum is not inside the guaranteed radius are re-done
+    // by the brute-force kernel (synchronises once per batch to learn which).
+    const bool pruned = ctx->prune && (long long)n_q * (long long)n_h >= (1ll << 18) && n_h >= 512;
+    if (!pruned) {
+        for (int64_t f0 = 0; f0 < n_frames; f0 += 32768) {
+            int rc = min_dist_brute(ctx, d_xyz, d_box, f0, std::min<int64_t>(32768, n_frames - f0), n_atoms, d_query,
+                                    n_q, d_haystack, n_h, orthogonal, d_min, d_arg, st);
+            if (rc != CMB_OK) return rc;
+        }
+        return CMB_OK;
+    }
+    const int64_t batch = pg_batch_frames(n_h);
+    const int qblocks = (n_q + PG_THREADS - 1) / PG_THREADS;
+    PgScratch& S = ctx->pg;
+    for (int64_t f0 = 0; f0 < n_frames; f0 += batch) {
+        const int64_t nf = std::min<int64_t>(batch, n_frames - f0);
+        std::string err;
+        int launches = 0;
+        int rc = pg_ensure(S, nf, n_h, err);
+        if (rc != 0) return fail(ctx, CMB_ERR_CUDA, "%s", err.c_str());
+        const float* x = d_xyz + (size_t)f0 * n_atoms * 3;
+        const float* b = d_box ? d_box + (size_t)f0 * 9 : nullptr;
+        rc = pg_bin_frames(S, x, b, nf, n_atoms, d_haystack, n_h, d_query, n_q, 0.f, st, err, launches);
+        if (rc != 0) return fail(ctx, CMB_ERR_CUDA, "%s", err.c_str());
+        const size_t need = (size_t)nf * qblocks * (sizeof(float) + sizeof(long long)) + 256;
+        rc = ensure_bytes(ctx, &ctx->d_tmp, &ctx->tmp_bytes, need);
         if (rc) return rc;
         long long* part_idx = (long long*)ctx->d_tmp;
-        float* part_d = (float*)((char*)ctx->d_tmp + (size_t)nf * n_chunks * sizeof(long long));
-        dim3 grid((unsigned)n_chunks, (unsigned)nf);
-        k_min_dist_partial<<<grid, MD_THREADS, 0, (cudaStream_t)stream>>>(
-            d_xyz + (size_t)f0 * n_atoms * 3, d_box ? d_box + (size_t)f0 * 9 : nullptr, n_atoms, d_query, n_q,
-            d_haystack, n_h, orthogonal, part_d, part_idx);
+        float* part_d = (float*)((char*)ctx->d_tmp + (size_t)nf * qblocks * sizeof(long long));
+        k_min_dist_cells<<<dim3((unsigned)qblocks, (unsigned)nf), PG_THREADS, 0, st>>>(
+            S.frames, x, b, n_atoms, d_query, n_q, n_h, S.cap_sel, orthogonal, S.cellptr, S.sorted, part_d, part_idx);
+        k_min_dist_final<<<(unsigned)((nf + 127) / 128), 128, 0, st>>>(part_d, part_idx, qblocks, nf, d_min + f0,
+                                                                       (long long*)d_arg + f0);
+        CK(cudaMemsetAsync(S.flags + S.cap_frames, 0, sizeof(int), st));
+        pg_flag<<<(unsigned)((nf + 127) / 128), 128, 0, st>>>(S.frames, d_min + f0, nf, S.flags, S.flags + S.cap_frames);
         CK(cudaGetLastError());
-        k_min_dist_final<<<(unsigned)((nf + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-            part_d, part_idx, n_chunks, nf, d_min + f0, (long long*)d_arg + f0);
-        CK(cudaGetLastError());
-        ctx->stats["kernel_launches"] += 2;
+        CK(cudaMemcpyAsync(S.h_flags + S.cap_frames, S.flags + S.cap_frames, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        ctx->stats["kernel_launches"] += launches + 3;
+        const int n_flagged = S.h_flags[S.cap_frames];
+        ctx->stats["pruned_frames"] += nf - n_flagged;
+        if (n_flagged == 0) continue;
+        CK(cudaMemcpy(S.h_flags, S.flags, sizeof(int) * (size_t)nf, cudaMemcpyDeviceToHost));
+        for (int64_t k = 0; k < nf;) {
+            if (!S.h_flags[k]) { k++; continue; }
+            int64_t e = k + 1;
+            while (e < nf && S.h_flags[e]) e++;
+            rc = min_dist_brute(ctx, d_xyz, d_box, f0 + k, e - k, n_atoms, d_query, n_q, d_haystack, n_h, orthogonal,
+                                d_min, d_arg, st);
+            if (rc != CMB_OK) return rc;
+            k = e;
+        }
     }
     return CMB_OK;
 }
@@ -1374,6 +1442,31 @@ extern "C" int cmb_nearest(cmb_ctx* ctx, const float* d_xyz_frame, const float* 
     CK(cudaSetDevice(ctx->device));
     const float cf = (float)cutoff;
     const float c2 = cf * cf;
+    if (ctx->prune && n_atoms >= 4096 && cf > 0.f) {
+        // cell-pruned search (cmb_prune.cuh): cells of the contact kernels' width, 27-cell stencil;
+        // grids with fewer than 3 cells along a periodic dimension keep the brute-force kernel
+        PgScratch& S = ctx->pg;
+        std::string err;
+        int launches = 0;
+        cudaStream_t st = (cudaStream_t)stream;
+        int rc = pg_ensure(S, 1, n_atoms, err);
+        if (rc != 0) return fail(ctx, CMB_ERR_CUDA, "%s", err.c_str());
+        rc = pg_bin_frames(S, d_xyz_frame, d_box9, 1, n_atoms, nullptr, n_atoms, nullptr, 0, cf, st, err, launches);
+        if (rc != 0) return fail(ctx, CMB_ERR_CUDA, "%s", err.c_str());
+        CK(cudaMemcpyAsync(S.h_flags, &S.frames[0].usable, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        ctx->stats["kernel_launches"] += launches;
+        if (S.h_flags[0]) {
+            k_nearest_cells<<<(unsigned)((n_atoms + PG_THREADS / 32 - 1) / (PG_THREADS / 32)), PG_THREADS, 0, st>>>(
+                S.frames, d_xyz_frame, d_box9, n_atoms, c2, orthogonal, excl_mode, d_atom_res,
+                (const long long*)d_excl_ptr, d_excl_idx, S.cellptr, S.sorted, d_nearest, d_dist);
+            CK(cudaGetLastError());
+            ctx->stats["kernel_launches"] += 1;
+            ctx->stats["pruned_frames"] += 1;
+            return CMB_OK;
+        }
+    }
+    ctx->stats["brute_frames"] += 1;
     k_nearest<<<(unsigned)((n_atoms + NA_THREADS - 1) / NA_THREADS), NA_THREADS, 0, (cudaStream_t)stream>>>(
         d_xyz_frame, d_box9, n_atoms, c2, orthogonal, excl_mode, d_atom_res, (const long long*)d_excl_ptr,
         d_excl_idx, d_nearest, d_dist);
