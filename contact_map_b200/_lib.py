@@ -29,7 +29,7 @@ EXPORTS = [
     "cmb_boundary_pairs", "cmb_set_option", "cmb_get_stat", "cmb_gather_atoms", "cmb_min_dist",
     "cmb_nearest", "cmb_synth_frames", "cmb_set_table_mode", "cmb_hash_stats", "cmb_export_hashed",
     "cmb_hash_rehash", "cmb_hash_overflow_buffer", "cmb_hash_add", "cmb_export_sorted", "cmb_group_contacts",
-    "cmb_min_dist_pairs", "cmb_frame_contacts_host", "cmb_keys_to_csr",
+    "cmb_min_dist_pairs", "cmb_frame_contacts_host", "cmb_keys_to_csr", "cmb_screen_audit",
 ]
 
 
@@ -126,6 +126,8 @@ def lib():
     L.cmb_frame_contacts_host.argtypes = [vp, vp, i32, vp, vp, i64, i64, i64, i32, vp, i64, vp, i64, vp]
     L.cmb_keys_to_csr.restype = i32
     L.cmb_keys_to_csr.argtypes = [vp, vp, i64, i64, i64, vp, vp, vp, vp, vp]
+    L.cmb_screen_audit.restype = i32
+    L.cmb_screen_audit.argtypes = [vp, vp, vp, i64, vp, vp]
     L.cmb_sort_keys.restype = i32
     L.cmb_sort_keys.argtypes = [vp, vp, i64, vp]
     L.cmb_export_nonzero.restype = i32

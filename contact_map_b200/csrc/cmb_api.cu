@@ -476,7 +476,7 @@ extern "C" int cmb_set_system(cmb_ctx* ctx, int n_used, const int32_t* atom_res,
     ctx->n_ignored = n_ignored;
     ctx->have_system = false;
     int64_t force = ctx->stats.count("force_path") ? ctx->stats["force_path"] : -1;
-    // the fused kernel packs ekey (17 bits) and the compact residue id (13 bits) into one word
+    // the fused kernel packs ekey (FS_EKEY_BITS = 16 bits), the compact residue id (13 bits) and the role (2 bits) into one word
     ctx->path = (n_used <= FS_MAX_ATOMS && ekey_max <= (long long)FS_EKEY_MASK &&
                  (long long)ctx->n_res_c <= (long long)FS_RES_MASK) ? 0 : 1;
     if (force == 1) ctx->path = 1;
@@ -517,7 +517,7 @@ static void fs_launch(const cmb_ctx* ctx, const FrameJob& job, const FrameParams
                       cudaStream_t stream)
 {
     const bool emit = job.atom_keys != nullptr || job.res_keys != nullptr;
-    if (job.boundary_ulps > 0)
+    if (job.boundary_ulps != 0)
         k_frames_small<FS_BOUNDARY | FS_ROLES, THREADS><<<g, THREADS, sm, stream>>>(p);
     else if (ctx->count_tests && !emit)
         k_frames_small<FS_COUNT | FS_ROLES, THREADS><<<g, THREADS, sm, stream>>>(p);
@@ -1138,6 +1138,28 @@ extern "C" int cmb_boundary_pairs(cmb_ctx* ctx, const float* d_xyz, const float*
     int rc = launch_frames(ctx, job, ctx->slot, (cudaStream_t)stream);
     if (rc != CMB_OK) return rc;
     CK(cudaMemcpyAsync(d_n, ctx->d_counters[ctx->slot] + 2, sizeof(unsigned long long),
+                       cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return CMB_OK;
+}
+
+// Audit of the screening shortcut of the cell kernels: every candidate pair of the
+// stencil that is not residue-excluded is decided by the reference arithmetic (nl_d2) AND by the
+// production thresholds of its frame; d_out[0] = pairs audited, d_out[1] = pairs on which the screen
+// alone (d2 <= c2_lo: contact, d2 >= c2_hi: no contact) would have decided differently -- must be 0.
+extern "C" int cmb_screen_audit(cmb_ctx* ctx, const float* d_xyz, const float* d_box, int64_t n_frames,
+                                uint64_t* d_out, void* stream)
+{
+    if (!ctx) return CMB_ERR_ARG;
+    if (!d_out) return fail(ctx, CMB_ERR_ARG, "d_out is NULL");
+    CK(cudaSetDevice(ctx->device));
+    ctx->slot ^= 1;
+    FrameJob job;
+    memset(&job, 0, sizeof(job));
+    job.xyz = d_xyz; job.box = d_box; job.n_frames = n_frames;
+    job.boundary_ulps = -1;
+    int rc = launch_frames(ctx, job, ctx->slot, (cudaStream_t)stream);
+    if (rc != CMB_OK) return rc;
+    CK(cudaMemcpyAsync(d_out, ctx->d_counters[ctx->slot] + 2, 2 * sizeof(unsigned long long),
                        cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return CMB_OK;
 }

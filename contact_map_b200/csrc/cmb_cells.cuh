@@ -190,7 +190,10 @@ struct PairParams {
     int n_ignored;
     float c2;                        // cutoff_f * cutoff_f
     float c2_lo, c2_hi;              // certain-contact / screening thresholds of this frame
-    int boundary_ulps;
+    int boundary_ulps;               // CT_BOUNDARY: > 0 report pairs within that many float steps of the cutoff;
+                                     // < 0 AUDIT: every candidate that is not residue-excluded is decided by the
+                                     // reference arithmetic and compared with what the screen would have decided
+    float audit_lo, audit_hi;        // audit: the thresholds the production kernels use for this frame
     // the frame: addressed through its index so that only one register stays live in the hot loop
     const float* xyz;                // RAW coordinates [frames][n][3] (global memory)
     const float* box;                // unit cell rows [frames][9] (global memory) or nullptr
@@ -353,7 +356,7 @@ __device__ __forceinline__ void ct_account(const PairParams& p, const PairCtx<Tr
         const float d2 = nl_d2<MODE>(__ldg(pa), __ldg(pa + 1), __ldg(pa + 2), __ldg(pb), __ldg(pb + 1),
                                      __ldg(pb + 2), B);
         hit = d2 <= p.c2;
-        if (FLAGS & CT_BOUNDARY) {
+        if ((FLAGS & CT_BOUNDARY) && p.boundary_ulps > 0) {
             int diff = __float_as_int(d2) - __float_as_int(p.c2);
             diff = diff < 0 ? -diff : diff;
             if (diff <= p.boundary_ulps) {
@@ -362,6 +365,16 @@ __device__ __forceinline__ void ct_account(const PairParams& p, const PairCtx<Tr
                     p.boundary[w] = make_float4(__int_as_float((int)(p.frame0 + p.f)), __int_as_float(min(ia, ib)),
                                                 __int_as_float(max(ia, ib)), d2);
             }
+        }
+    }
+    if ((FLAGS & CT_BOUNDARY) && p.boundary_ulps < 0) {
+        // audit (counters[2] = pairs audited, counters[3] = disagreements): the production screen
+        // calls d2a <= lo a contact without looking and drops d2a >= hi without looking
+        const bool bad = elig && ((d2a <= p.audit_lo && !hit) || (d2a >= p.audit_hi && hit));
+        const unsigned am = __ballot_sync(0xffffffffu, elig), bm = __ballot_sync(0xffffffffu, bad);
+        if (lane == 0) {
+            if (am) atomicAdd(&p.counters[2], (unsigned long long)__popc(am));
+            if (bm) atomicAdd(&p.counters[3], (unsigned long long)__popc(bm));
         }
     }
     if (FLAGS & CT_EMIT) {

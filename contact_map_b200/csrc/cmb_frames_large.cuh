@@ -573,7 +573,7 @@ __global__ void __launch_bounds__(LG_PAIR_THREADS, Sink::MIN_CTAS) kl_pairs(Pair
     __shared__ unsigned int cand_all[(LG_PAIR_THREADS / 32) * CT_CAND];
     __shared__ uint4 hitq_all[(LG_PAIR_THREADS / 32) * CT_QCAP];
     __shared__ float4 shift_s[27];
-    __shared__ float thresh_s[2];
+    __shared__ float thresh_s[4];
     __shared__ unsigned int rcache_all[(LG_PAIR_THREADS / 32) * LG_RCACHE];
     __shared__ GridS G;
     const int fb = blockIdx.y;
@@ -587,10 +587,13 @@ __global__ void __launch_bounds__(LG_PAIR_THREADS, Sink::MIN_CTAS) kl_pairs(Pair
     if (threadIdx.x == 32) {
         float lo, hi;
         frame_margins(box9, G.distinct, __int_as_float(misc[2]), pp.c2, cutoff, pp.boundary_ulps, lo, hi);
+        thresh_s[2] = lo; thresh_s[3] = hi;
+        if ((FLAGS & CT_BOUNDARY) && pp.boundary_ulps < 0) { lo = -1.0e30f; hi = 1.0e30f; }   // audit
         thresh_s[0] = lo; thresh_s[1] = hi;
     }
     __syncthreads();
     pp.c2_lo = thresh_s[0]; pp.c2_hi = thresh_s[1];
+    pp.audit_lo = thresh_s[2]; pp.audit_hi = thresh_s[3];
     pp.f = fb;
     PairCtx<LargeTraits> cx;
     cx.sorted = lb.sorted + (size_t)fb * (size_t)lb.n;
@@ -627,7 +630,7 @@ inline void launch_pairs(const LargeJob& job, const PairParams& pp, const Sink& 
                          dim3 grid, cudaStream_t stream)
 {
     const bool emit = job.atom_keys != nullptr;
-    if (job.boundary_ulps > 0)
+    if (job.boundary_ulps != 0)
         kl_pairs<CT_BOUNDARY | CT_ROLES, Sink><<<grid, LG_PAIR_THREADS, 0, stream>>>(pp, sink, lb, job.cutoff);
     else if (job.count_tests && !emit)
         kl_pairs<CT_COUNT | CT_ROLES, Sink><<<grid, LG_PAIR_THREADS, 0, stream>>>(pp, sink, lb, job.cutoff);

@@ -419,6 +419,7 @@ __global__ void __launch_bounds__(THREADS, THREADS > 512 ? 1 : FS_MIN_CTAS) k_fr
             for (int w = 0; w < FS_WARPS; w++) A = fmaxf(A, amax_s[w]);
             float c2_lo, c2_hi;
             frame_margins(box9, G.distinct, A, p.c2, p.cutoff, p.boundary_ulps, c2_lo, c2_hi);
+            if ((FLAGS & FS_BOUNDARY) && p.boundary_ulps < 0) { c2_lo = -1.0e30f; c2_hi = 1.0e30f; }   // audit
             thresh_s[0] = c2_lo; thresh_s[1] = c2_hi;
         }
         if (tid >= 64 && tid < 64 + 27) shift_s[tid - 64] = lattice_shift(box9, tid - 64);
@@ -514,6 +515,13 @@ __global__ void __launch_bounds__(THREADS, THREADS > 512 ? 1 : FS_MIN_CTAS) k_fr
         PairParams pp;
         pp.n = n; pp.n_ignored = p.n_ignored; pp.c2 = p.c2; pp.c2_lo = thresh_s[0]; pp.c2_hi = thresh_s[1];
         pp.boundary_ulps = p.boundary_ulps; pp.xyz = p.xyz; pp.box = p.box; pp.f = (int)f; pp.frame0 = p.frame0;
+        pp.audit_lo = pp.audit_hi = p.c2;
+        if ((FLAGS & FS_BOUNDARY) && p.boundary_ulps < 0) {
+            // audit: the thresholds the production variants would use for this frame
+            float A = 0.f;
+            for (int w = 0; w < FS_WARPS; w++) A = fmaxf(A, amax_s[w]);
+            frame_margins(box9, G.distinct, A, p.c2, p.cutoff, 0, pp.audit_lo, pp.audit_hi);
+        }
         pp.atom_keys = p.atom_keys; pp.atom_cap = p.atom_cap; pp.counters = p.counters;
         pp.boundary = p.boundary; pp.boundary_cap = p.boundary_cap;
         PairCtx<SmallTraits> cx;

@@ -680,6 +680,19 @@ class ContactEngine(object):
         out = rec.cpu().numpy()[:n * 4].view(dt)
         return np.sort(out, order=["frame", "a", "b"])
 
+    def screen_audit(self, xyz, box):
+        """(pairs audited, disagreements) of the cell kernels' screening shortcut on a DEVICE
+        trajectory: every stencil candidate that is not residue-excluded is decided by the reference
+        arithmetic and by the production thresholds; the second number must be 0."""
+        xyz, box = self._dev_inputs(xyz, box)
+        self._set_table_mode(None, None)
+        out = torch.zeros(2, dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self._L.cmb_screen_audit(self._ctx, _ptr(xyz), _ptr(box), xyz.shape[0], _ptr(out),
+                                                 _stream_ptr(self.device)), "cmb_screen_audit")
+        audited, bad = out.cpu().numpy().tolist()
+        return int(audited), int(bad)
+
     def gather_atoms(self, xyz_full, used):
         """Device ``_atom_slice``: [F, n_total, 3] -> [F, len(used), 3]."""
         if xyz_full.dtype != torch.float32 or not xyz_full.is_contiguous() or not xyz_full.is_cuda:

@@ -190,6 +190,18 @@ int cmb_boundary_pairs(cmb_ctx* ctx, const float* d_xyz, const float* d_box, int
                        int64_t frame0, int ulps, void* d_records, int64_t cap, uint64_t* d_n,
                        void* stream);
 
+/*
+ * Audit of the cell kernels' screening shortcut: the kernels call a pair a contact without running
+ * MDTraj's arithmetic when its screening distance is below a per-frame threshold c2_lo, and drop it
+ * when it is above c2_hi (md.compute_neighborlist, contact_map.py:575, is then never evaluated for
+ * that pair).  This entry runs the reference arithmetic on EVERY stencil candidate that is not
+ * residue-excluded and compares: d_out[0] (device uint64) = pairs audited, d_out[1] = pairs the
+ * screen alone would have decided differently -- which must be 0.  Same frame arguments as
+ * cmb_accumulate.  The pair-list path has its own audit (cmb_set_option "verlet_audit").
+ */
+int cmb_screen_audit(cmb_ctx* ctx, const float* d_xyz, const float* d_box, int64_t n_frames,
+                     uint64_t* d_out, void* stream);
+
 /* Executed candidate-pair tests of the last accumulate / frame_contacts call when
  * enabled with cmb_set_option(ctx, "count_tests", 1) (bench metric; synchronises).
  * Other options: "force_path" (-1 auto, 0 fused kernel, 1 global-memory cell path), "max_cells",

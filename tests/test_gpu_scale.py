@@ -387,3 +387,60 @@ def test_pairs_at_the_cutoff_are_adjudicated_exactly(engine, box_kind, force_pat
         assert np.array_equal(rec["d2"], wd[order])
     finally:
         engine.set_option("force_path", -1)
+
+
+@pytest.mark.parametrize("case", ["s1", "triclinic_large_path", "varying_cells", "far_from_origin", "open", "at_the_cutoff"])
+def test_screen_audit_finds_no_disagreement(engine, case):
+    """the screening margins (frame_margins) are AUDITED, not only argued --
+    the audit variant of the cell kernels runs the reference arithmetic on every stencil candidate
+    that is not residue-excluded and counts the pairs on which the production thresholds alone
+    (d2 <= c2_lo: contact, d2 >= c2_hi: no contact) would have decided differently: zero, on S1
+    (> 10^9 pairs), the triclinic global-memory cell path, cells that change every frame,
+    coordinates hundreds of nm from the origin (unwrapped trajectories, up to the 900 nm domain
+    limit), no unit cell, and pairs placed within a few float steps of the cutoff."""
+    rng = np.random.default_rng(77)
+    dev = engine.device
+    min_pairs = 1
+    try:
+        if case == "s1":
+            system = synth.kras_like()
+            res, chain, role = system_arrays(system)
+            engine.set_system(res, chain, role, 0.45, 2)
+            xyz, box = _dev(engine, system, 0, 8000)
+            min_pairs = 10 ** 9
+        elif case == "triclinic_large_path":
+            system = synth.solvated_triclinic(n_atoms=12000, lattice=23)
+            res, chain, role = system_arrays(system)
+            engine.set_option("force_path", 1)
+            engine.set_system(res, chain, role, 0.45, 2)
+            xyz, box = _dev(engine, system, 0, 48)
+            min_pairs = 10 ** 7
+        else:
+            kind = {"varying_cells": "triclinic", "far_from_origin": "ortho", "open": "open", "at_the_cutoff": "triclinic"}[case]
+            system = synth.random_system(rng, 2500, n_chains=3, box_kind=kind, extent=3.2)
+            res, chain, role = system_arrays(system)
+            engine.set_system(res, chain, role, 0.45, 1)
+            F = 200
+            h_xyz = system.frames(0, F)
+            h_box = None if system.box is None else np.broadcast_to(system.box, (F, 3, 3)).copy()
+            if case == "varying_cells":
+                h_box = (h_box * (1.0 + 0.002 * np.arange(F, dtype=np.float32))[:, None, None]).astype(np.float32)
+            if case == "far_from_origin":
+                # whole-cell shifts of up to +-200 cells per residue group: |coordinates| up to ~850 nm
+                shift = rng.integers(-200, 201, size=(F, 1, 3)).astype(np.float32) * np.diag(system.box)[None, None, :]
+                h_xyz = (h_xyz + shift).astype(np.float32)
+                assert np.abs(h_xyz).max() > 500 and np.abs(h_xyz).max() < 900
+            if case == "at_the_cutoff":
+                # move every odd atom onto a sphere of radius cutoff (+- a few float steps) around its predecessor
+                d = rng.normal(size=(F, 1250, 3))
+                d /= np.linalg.norm(d, axis=2, keepdims=True)
+                r = np.float32(0.45) * (1.0 + rng.integers(-6, 7, size=(F, 1250, 1)) * 6e-8)
+                h_xyz[:, 1::2] = (h_xyz[:, 0::2].astype(np.float64) + d * r).astype(np.float32)
+            xyz = torch.as_tensor(h_xyz, device=dev)
+            box = None if h_box is None else torch.as_tensor(h_box, device=dev)
+            min_pairs = 10 ** 6
+        audited, bad = engine.screen_audit(xyz, box)
+    finally:
+        engine.set_option("force_path", -1)
+    assert bad == 0
+    assert audited >= min_pairs
