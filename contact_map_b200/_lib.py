@@ -29,7 +29,9 @@ EXPORTS = [
     "cmb_boundary_pairs", "cmb_set_option", "cmb_get_stat", "cmb_gather_atoms", "cmb_min_dist",
     "cmb_nearest", "cmb_synth_frames", "cmb_set_table_mode", "cmb_hash_stats", "cmb_export_hashed",
     "cmb_hash_rehash", "cmb_hash_overflow_buffer", "cmb_hash_add", "cmb_export_sorted", "cmb_group_contacts",
-    "cmb_min_dist_pairs", "cmb_frame_contacts_host", "cmb_keys_to_csr", "cmb_screen_audit",
+    "cmb_min_dist_pairs", "cmb_frame_contacts_host", "cmb_keys_to_csr", "cmb_screen_audit", "cmb_device_alloc", "cmb_device_free", "cmb_device_zero",
+    "cmb_copy_to_host", "cmb_copy_to_device", "cmb_nccl_unique_id", "cmb_nccl_comm_create", "cmb_nccl_comm_destroy",
+    "cmb_reduce",
 ]
 
 
@@ -128,6 +130,24 @@ def lib():
     L.cmb_keys_to_csr.argtypes = [vp, vp, i64, i64, i64, vp, vp, vp, vp, vp]
     L.cmb_screen_audit.restype = i32
     L.cmb_screen_audit.argtypes = [vp, vp, vp, i64, vp, vp]
+    L.cmb_device_alloc.restype = i32
+    L.cmb_device_alloc.argtypes = [vp, u64, ctypes.POINTER(vp)]
+    L.cmb_device_free.restype = i32
+    L.cmb_device_free.argtypes = [vp, vp]
+    L.cmb_device_zero.restype = i32
+    L.cmb_device_zero.argtypes = [vp, vp, u64, vp]
+    L.cmb_copy_to_host.restype = i32
+    L.cmb_copy_to_host.argtypes = [vp, vp, vp, u64, vp]
+    L.cmb_copy_to_device.restype = i32
+    L.cmb_copy_to_device.argtypes = [vp, vp, vp, u64, vp]
+    L.cmb_nccl_unique_id.restype = i32
+    L.cmb_nccl_unique_id.argtypes = [vp, vp]
+    L.cmb_nccl_comm_create.restype = i32
+    L.cmb_nccl_comm_create.argtypes = [vp, i32, vp, i32, ctypes.POINTER(vp)]
+    L.cmb_nccl_comm_destroy.restype = i32
+    L.cmb_nccl_comm_destroy.argtypes = [vp, vp]
+    L.cmb_reduce.restype = i32
+    L.cmb_reduce.argtypes = [vp, vp, vp, i64, i32, vp]
     L.cmb_sort_keys.restype = i32
     L.cmb_sort_keys.argtypes = [vp, vp, i64, vp]
     L.cmb_export_nonzero.restype = i32

@@ -2,6 +2,7 @@
 // reference interfaces each entry point replaces).
 #include <cub/device/device_radix_sort.cuh>
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cstdarg>
@@ -1494,5 +1495,145 @@ extern "C" int cmb_nearest(cmb_ctx* ctx, const float* d_xyz_frame, const float* 
         d_excl_idx, d_nearest, d_dist);
     CK(cudaGetLastError());
     ctx->stats["kernel_launches"] += 1;
+    return CMB_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// device memory and the multi-GPU reduce for hosts that are not Python
+// (the Python layer uses torch tensors / torch.distributed for the same things)
+// ---------------------------------------------------------------------------------
+extern "C" int cmb_device_alloc(cmb_ctx* ctx, uint64_t n_bytes, void** d_ptr)
+{
+    if (!ctx || !d_ptr) return CMB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    *d_ptr = nullptr;
+    CK(cudaMalloc(d_ptr, n_bytes ? (size_t)n_bytes : 16));
+    CK(cudaMemset(*d_ptr, 0, (size_t)n_bytes));
+    return CMB_OK;
+}
+
+extern "C" int cmb_device_free(cmb_ctx* ctx, void* d_ptr)
+{
+    if (!ctx) return CMB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaFree(d_ptr));
+    return CMB_OK;
+}
+
+extern "C" int cmb_device_zero(cmb_ctx* ctx, void* d_ptr, uint64_t n_bytes, void* stream)
+{
+    if (!ctx || !d_ptr) return CMB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemsetAsync(d_ptr, 0, (size_t)n_bytes, (cudaStream_t)stream));
+    return CMB_OK;
+}
+
+extern "C" int cmb_copy_to_host(cmb_ctx* ctx, void* h_dst, const void* d_src, uint64_t n_bytes, void* stream)
+{
+    if (!ctx || (n_bytes && (!h_dst || !d_src))) return CMB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(h_dst, d_src, (size_t)n_bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return CMB_OK;
+}
+
+extern "C" int cmb_copy_to_device(cmb_ctx* ctx, void* d_dst, const void* h_src, uint64_t n_bytes, void* stream)
+{
+    if (!ctx || (n_bytes && (!d_dst || !h_src))) return CMB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(d_dst, h_src, (size_t)n_bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return CMB_OK;
+}
+
+// NCCL is bound at run time (dlopen): the library loads and every single-GPU entry point works on
+// machines without NCCL; the prototypes below are NCCL's public, stable C API (nccl.h).
+namespace {
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, cmb_nccl_id, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Reduce)(const void*, void*, size_t, int, int, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+
+int nccl_load(cmb_ctx* ctx)
+{
+    if (g_nccl.handle) return CMB_OK;
+    const char* names[] = {getenv("CMB200_NCCL"), "libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* name : names) {
+        if (!name || !*name) continue;
+        h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) return fail(ctx, CMB_ERR_STATE, "NCCL not found (libnccl.so.2; set CMB200_NCCL to its path): %s", dlerror());
+    NcclApi a;
+    a.handle = h;
+    a.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
+    a.CommInitRank = (int (*)(void**, int, cmb_nccl_id, int))dlsym(h, "ncclCommInitRank");
+    a.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+    a.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
+    a.Reduce = (int (*)(const void*, void*, size_t, int, int, int, void*, cudaStream_t))dlsym(h, "ncclReduce");
+    a.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+    if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllReduce || !a.Reduce || !a.GetErrorString)
+        return fail(ctx, CMB_ERR_STATE, "the NCCL library lacks an expected symbol");
+    g_nccl = a;
+    return CMB_OK;
+}
+#define NCCL_CK(call)                                                                              \
+    do {                                                                                           \
+        const int r_ = (call);                                                                     \
+        if (r_ != 0) return fail(ctx, CMB_ERR_CUDA, "%s failed: %s", #call, g_nccl.GetErrorString(r_)); \
+    } while (0)
+}  // namespace
+
+extern "C" int cmb_nccl_unique_id(cmb_ctx* ctx, cmb_nccl_id* out)
+{
+    if (!ctx || !out) return CMB_ERR_ARG;
+    int rc = nccl_load(ctx);
+    if (rc != CMB_OK) return rc;
+    NCCL_CK(g_nccl.GetUniqueId(out));
+    return CMB_OK;
+}
+
+extern "C" int cmb_nccl_comm_create(cmb_ctx* ctx, int n_ranks, const cmb_nccl_id* id, int rank, void** comm)
+{
+    if (!ctx || !id || !comm || n_ranks < 1 || rank < 0 || rank >= n_ranks) return CMB_ERR_ARG;
+    int rc = nccl_load(ctx);
+    if (rc != CMB_OK) return rc;
+    CK(cudaSetDevice(ctx->device));
+    NCCL_CK(g_nccl.CommInitRank(comm, n_ranks, *id, rank));
+    return CMB_OK;
+}
+
+extern "C" int cmb_nccl_comm_destroy(cmb_ctx* ctx, void* comm)
+{
+    if (!ctx || !comm) return CMB_ERR_ARG;
+    int rc = nccl_load(ctx);
+    if (rc != CMB_OK) return rc;
+    NCCL_CK(g_nccl.CommDestroy(comm));
+    return CMB_OK;
+}
+
+// reduce_all_results (frequency_task.py:125-141) across GPUs: the ranks' dense uint32 count tables
+// -- identical layout on every rank -- are summed in place with ONE collective.  root < 0: every
+// rank receives the sum (all-reduce); root >= 0: only that rank does (what the reference's
+// client-side reduce delivers, at about half the traffic).  `comm` is an ncclComm_t (from
+// cmb_nccl_comm_create, or any communicator of the same NCCL library the host already owns).
+extern "C" int cmb_reduce(cmb_ctx* ctx, void* comm, uint32_t* d_table, int64_t n_elems, int root, void* stream)
+{
+    if (!ctx || !comm || !d_table || n_elems < 0) return CMB_ERR_ARG;
+    int rc = nccl_load(ctx);
+    if (rc != CMB_OK) return rc;
+    CK(cudaSetDevice(ctx->device));
+    const int nccl_uint32 = 3, nccl_sum = 0;
+    if (root < 0)
+        NCCL_CK(g_nccl.AllReduce(d_table, d_table, (size_t)n_elems, nccl_uint32, nccl_sum, comm, (cudaStream_t)stream));
+    else
+        NCCL_CK(g_nccl.Reduce(d_table, d_table, (size_t)n_elems, nccl_uint32, nccl_sum, root, comm, (cudaStream_t)stream));
     return CMB_OK;
 }

@@ -274,6 +274,35 @@ int cmb_synth_frames(cmb_ctx* ctx, const float* d_base, const int32_t* d_atom_gr
                      const float* d_box9, uint64_t seed, float amplitude, int image_shifts,
                      int64_t frame0, int64_t n_frames, float* d_out, void* stream);
 
+/*
+ * Device memory for hosts that bring no CUDA allocator of their own (the Python layer uses torch
+ * tensors instead): zero-filled allocation, free, asynchronous zero fill, synchronous copies.
+ * A zero-filled buffer of cmb_table_sizes() elements is an empty count table.
+ */
+int cmb_device_alloc(cmb_ctx* ctx, uint64_t n_bytes, void** d_ptr);
+int cmb_device_free(cmb_ctx* ctx, void* d_ptr);
+int cmb_device_zero(cmb_ctx* ctx, void* d_ptr, uint64_t n_bytes, void* stream);
+int cmb_copy_to_host(cmb_ctx* ctx, void* h_dst, const void* d_src, uint64_t n_bytes, void* stream);
+int cmb_copy_to_device(cmb_ctx* ctx, void* d_dst, const void* h_src, uint64_t n_bytes, void* stream);
+
+/*
+ * reduce_all_results (frequency_task.py:125-141; orchestrated by dask_run, dask_runner.py:11-37)
+ * across the GPUs of a job, one process per GPU: the ranks' dense uint32 count tables -- the layout
+ * is identical on every rank -- are summed in place with ONE NCCL collective over NVLink/NVSwitch.
+ * root < 0: all-reduce (every rank ends up with the sum); root >= 0: reduce to that rank only,
+ * which is what the reference's client-side reduce delivers.  `comm` is an ncclComm_t.  NCCL is
+ * bound at run time (dlopen "libnccl.so.2", or the path in $CMB200_NCCL), so the library loads
+ * without it; cmb_nccl_unique_id / cmb_nccl_comm_create / cmb_nccl_comm_destroy wrap
+ * ncclGetUniqueId / ncclCommInitRank / ncclCommDestroy for hosts without NCCL bindings (rank 0
+ * creates the id and hands its 128 bytes to the other ranks by whatever means the host has).
+ * Hashed tables have rank-dependent layouts: export them and merge the sparse lists instead.
+ */
+typedef struct { char internal[128]; } cmb_nccl_id;
+int cmb_nccl_unique_id(cmb_ctx* ctx, cmb_nccl_id* out);
+int cmb_nccl_comm_create(cmb_ctx* ctx, int n_ranks, const cmb_nccl_id* id, int rank, void** comm);
+int cmb_nccl_comm_destroy(cmb_ctx* ctx, void* comm);
+int cmb_reduce(cmb_ctx* ctx, void* comm, uint32_t* d_table, int64_t n_elems, int root, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
