@@ -423,6 +423,42 @@ class ContactEngine(object):
                 out.append((packed >> 24, (packed & 0xffffff).astype(np.uint32)))
         return out
 
+    def export_packed_device(self, tables):
+        """Sparse export that STAYS on the device: for every dense table a sorted int64 tensor of
+        packed (flat index << 24 | count) words (``cmb_export_sorted``), or ``None`` for a table
+        whose counts do not fit 24 bits / a hashed table (callers then use :meth:`export_many`).
+        One host synchronisation (the entry counts)."""
+        hints = self.__dict__.setdefault("_export_hint", {})
+        stream = torch.cuda.current_stream(self.device)
+        jobs = []
+        with torch.cuda.device(self.device):
+            for slot, t in enumerate(tables):
+                if isinstance(t, HashTable):
+                    jobs.append(None)
+                    continue
+                cap = hints.get(t.numel())
+                if cap is None:
+                    cap = int(torch.count_nonzero(t).item())
+                cap = max(16, min(t.numel(), cap + cap // 4 + 1024))
+                jobs.append(self._export_launch(t, cap, slot, to_host=False))
+            stream.synchronize()
+            out = []
+            for slot, (t, job) in enumerate(zip(tables, jobs)):
+                if job is None:
+                    out.append(None)
+                    continue
+                n, wide = int(job["h_n"][0]), int(job["h_n"][1])
+                if n > job["cap"] and not wide:
+                    job = self._export_launch(t, n, slot, to_host=False)
+                    stream.synchronize()
+                    n, wide = int(job["h_n"][0]), int(job["h_n"][1])
+                if wide:
+                    out.append(None)
+                    continue
+                hints[t.numel()] = n
+                out.append(job["d_packed"][:n])
+        return out
+
     def _export_span(self, tables):
         """Dense tables that are views of ONE allocation (``new_tables``) are exported with a single
         scan of that allocation and split on the host at the view boundaries."""
@@ -444,7 +480,7 @@ class ContactEngine(object):
         cuts = np.searchsorted(idx, np.asarray(offsets + [hi], dtype=np.int64) - lo)
         return [(idx[a:b] - (o - lo), cnt[a:b]) for a, b, o in zip(cuts[:-1], cuts[1:], offsets)]
 
-    def _export_launch(self, table, cap, slot):
+    def _export_launch(self, table, cap, slot, to_host=True):
         # staging buffers are keyed by (table size, position in the call) and reused across calls
         pool = self.__dict__.setdefault("_export_pool", {})
         buf = pool.get((table.numel(), slot))
@@ -464,7 +500,8 @@ class ContactEngine(object):
                                               table.log2 if hashed else 0, buf["cap"], _ptr(buf["d_packed"]),
                                               _ptr(buf["d_n"]), _stream_ptr(self.device)), "cmb_export_sorted")
         buf["h_n"].copy_(buf["d_n"], non_blocking=True)
-        buf["h_packed"].copy_(buf["d_packed"], non_blocking=True)
+        if to_host:
+            buf["h_packed"].copy_(buf["d_packed"], non_blocking=True)
         return buf
 
     def _export_unpacked(self, table):

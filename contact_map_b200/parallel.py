@@ -102,12 +102,45 @@ def reduce_export(engine, tables, dst=None, group=None):
         return engine.export_many(tables)
     dense_bytes = sum(t.numel() * 4 for t in tables if not hasattr(t, "slots"))
     if any(hasattr(t, "slots") for t in tables) or dense_bytes > SPARSE_REDUCE_BYTES:
-        local = engine.export_many(tables)
-        device = tables[0].slots.device if hasattr(tables[0], "slots") else tables[0].device
-        merged = [merge_sparse(idx, cnt, device, group) for idx, cnt in local]
-        return merged if dst is None or rank == dst else None
+        receives = dst is None or rank == dst
+        packed = engine.export_packed_device(tables)
+        merged = []
+        for t, p in zip(tables, packed):
+            if p is None:
+                # hashed tables / counts beyond 24 bits: through the host lists
+                (idx, cnt), = engine.export_many([t])
+                device = t.slots.device if hasattr(t, "slots") else t.device
+                m = merge_sparse(idx, cnt, device, group)
+                merged.append(m if receives else None)
+            else:
+                merged.append(merge_packed(p, receives, group))
+        return merged if receives else None
     reduce_tables(tables, group=group, dst=dst)
     return engine.export_many(tables) if dst is None or rank == dst else None
+
+
+def merge_packed(packed, receives=True, group=None):
+    """Sum the ranks' sparse exports WITHOUT leaving the device: ``packed`` is this rank's sorted
+    int64 tensor of (flat index << 24 | count) words (``engine.export_packed_device``); the lists
+    are all-gathered (NCCL over NVLink: a few tens of MB per rank), sorted by index and summed per
+    index; only the ranks that receive the result copy it to the host.
+    Returns (index int64[], count uint32[]) sorted by index, or ``None``."""
+    w = dist.get_world_size(group)
+    device = packed.device
+    sizes = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(w)]
+    dist.all_gather(sizes, torch.tensor([packed.numel()], dtype=torch.int64, device=device), group=group)
+    sizes = [int(x.item()) for x in sizes]
+    cap = max(max(sizes), 1)
+    mine = torch.zeros(cap, dtype=torch.int64, device=device)
+    mine[:packed.numel()] = packed
+    parts = [torch.empty(cap, dtype=torch.int64, device=device) for _ in range(w)]
+    dist.all_gather(parts, mine, group=group)
+    if not receives:
+        return None
+    everything = torch.cat([p[:k] for p, k in zip(parts, sizes)])
+    uniq, inverse = torch.unique(everything >> 24, sorted=True, return_inverse=True)
+    total = torch.zeros(uniq.numel(), dtype=torch.int64, device=device).scatter_add_(0, inverse, everything & 0xffffff)
+    return uniq.cpu().numpy(), total.cpu().numpy().astype(np.uint32)
 
 
 def merge_sparse(idx, cnt, device, group=None):

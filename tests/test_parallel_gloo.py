@@ -60,8 +60,12 @@ def _worker(rank, world, port, out_dir):
         # hashed tables are reduced through their sparse exports (parallel.merge_sparse)
         flat = np.flatnonzero(atom.reshape(-1))
         m_idx, m_cnt = parallel.merge_sparse(flat, atom.reshape(-1)[flat], torch.device("cpu"))
+        # ... and, for large dense tables, through packed device-side lists (parallel.merge_packed)
+        packed = torch.from_numpy(((flat.astype(np.int64) << 24) | atom.reshape(-1)[flat].astype(np.int64)))
+        p_idx, p_cnt = parallel.merge_packed(packed)
+        assert parallel.merge_packed(packed, receives=False) is None
         np.savez(os.path.join(out_dir, "rank%d.npz" % rank), atom=t_atom.numpy(), res=t_res.numpy(),
-                 frames=total_frames, keys=all_keys.view(np.int64), m_idx=m_idx, m_cnt=m_cnt,
+                 frames=total_frames, keys=all_keys.view(np.int64), m_idx=m_idx, m_cnt=m_cnt, p_idx=p_idx, p_cnt=p_cnt,
                  root_atom=r_atom.numpy(), root_res=r_res.numpy())
     finally:
         dist.destroy_process_group()
@@ -97,6 +101,8 @@ def test_two_rank_reduce_equals_single(tmp_path):
         want_flat = np.flatnonzero(atom.reshape(-1))
         assert np.array_equal(got["m_idx"], want_flat)
         assert np.array_equal(got["m_cnt"], atom.reshape(-1)[want_flat])
+        assert np.array_equal(got["p_idx"], want_flat)
+        assert np.array_equal(got["p_cnt"], atom.reshape(-1)[want_flat])
     assert atom.sum() > 0
 
 
