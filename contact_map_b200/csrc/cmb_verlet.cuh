@@ -68,22 +68,22 @@ constexpr int VL_MAX_SLOTS = VL_THREADS * VL_SPT - 1;    // + 1 "far" slot for p
 constexpr int VL_ROW = 128;                              // entries per row: 32 lanes x 4 steps
 constexpr int VL_MAX_ROWS = 768;                         // per tile
 constexpr int VL_MAX_ENTRIES = VL_MAX_ROWS * VL_ROW;     // 98 304 byte counters
-constexpr int VL_MAX_SEGS = 24576;                       // residue pairs per tile
-constexpr int VL_FETCH_ROWS = 2;                         // rows a warp takes per trip to the work counter
+constexpr int VL_MAX_SEGS = 16384;                       // residue pairs per tile
+constexpr int VL_SEG_BITS = 14;                          // bits of a tile-relative segment id
 constexpr int VL_MAX_TILES = 4096;
 constexpr int VL_MAXC = 1 << 17;                         // cells of the list grid
 constexpr int VL_SAMPLES = 16;
 constexpr int VL_ITEM_FRAMES = 255;                      // byte counters: flush at least this often
 constexpr int VL_MIN_ITEM_FRAMES = 12;                   // shorter items would not amortise set-up and flush
 constexpr int VL_SINGLE_TILE_ATOMS = 3800;
-constexpr int VL_LEN_BITS = 20;                          // segment length field of the bundle sort key
+constexpr int VL_LEN_BITS = 20;                          // list length field of the bundle sort key
 constexpr unsigned long long VL_PAD = ~0ull;
 
 struct VlHeader {
     int valid;                 // 0: the list cannot be used, every frame falls back
     int n_tiles, tdim, ntx, nty, ntz;
     int n_entries;             // list pairs found (may exceed the capacity -> invalid)
-    int n_segs, n_slots, n_bundles, n_rows;
+    int n_segs, n_lists, n_slots, n_bundles, n_rows;
     int rbits, abits;          // bits of a compact residue id / of a used-atom index in the sort keys
     unsigned d_max_bits, a_max_bits;       // sample maxima (non-negative float bits)
     unsigned bb_lo[3], bb_hi[3];           // bounding box of the reference positions (ordered uints)
@@ -98,8 +98,9 @@ struct VlHeader {
 
 struct VlTile {
     int slot0, n_slots;        // into slot_word / slot_ref
-    int seg0, n_segs;          // into seg_pair (length-sorted order)
-    int row0, n_rows;          // into entries (rows of VL_ROW words) and row_bundle
+    int seg0, n_segs;          // into seg_pair: the residue pairs of the tile
+    int list0, n_lists;        // owner lists of the tile (length-sorted order; builder only)
+    int row0, n_rows;          // into entries (rows of VL_ROW words) and row_owner
 };
 
 // everything the builder writes and the frame kernel reads (device pointers)
@@ -108,9 +109,11 @@ struct VlList {
     VlTile* tiles;             // [VL_MAX_TILES]
     unsigned* slot_word;       // [slot_cap] atom | shift id << 24
     float4* slot_ref;          // [slot_cap] reference position of the slot's atom (primary cell)
-    unsigned short* row_bundle;  // [row_cap] bundle (tile relative) of each row: its lanes are segments 32 b + lane
-    unsigned* entries;         // [row_cap * VL_ROW] 16 slot_i | 16 slot_j << 16 (byte offsets into the position array)
-    uint2* seg_pair;           // [entry_cap] {compact residue lo, hi} in length-sorted order
+    unsigned short* row_owner; // [row_cap * 32] slot (byte offset into the position array) of the atom that owns
+                               // lane l of the row: the lane walks (a part of) that atom's partner list
+    unsigned* entries;         // [row_cap * VL_ROW] partner slot byte offset (bits 4-15) | direction (bit 0) |
+                               // tile-relative segment (residue pair) << 16
+    uint2* seg_pair;           // [entry_cap] {compact residue lo, hi} of every segment
     const float4* ref_w;       // [n] wrapped reference position of every atom (guard pass)
     long long entry_cap, slot_cap, row_cap;
 };
@@ -144,12 +147,18 @@ struct VlScratch {
     unsigned long long* seg_key = nullptr;                 // [entry_cap] unique keys
     int* seg_len = nullptr;                                // [entry_cap]
     int* seg_start = nullptr;                              // [entry_cap + 1]
-    int* n_runs = nullptr;                                 // [2]
+    int* n_runs = nullptr;                                 // [3] segments, unique slots, owner lists
+    unsigned long long* own_key = nullptr;                 // [entry_cap] records re-sorted by (tile, owner atom)
+    unsigned long long* own_val = nullptr;
+    unsigned long long* list_key = nullptr;                // [entry_cap] unique (tile, owner atom)
+    int* list_len = nullptr;                               // [entry_cap]
+    int* list_start = nullptr;                             // [entry_cap + 1]
     unsigned long long* skey[2] = {nullptr, nullptr};      // [entry_cap] tile << VL_LEN_BITS | ~len
-    int* sval[2] = {nullptr, nullptr};                     // [entry_cap] segment id
+    int* sval[2] = {nullptr, nullptr};                     // [entry_cap] owner list id
     unsigned long long* slot_key[2] = {nullptr, nullptr};  // [2 * entry_cap + n]
     unsigned long long* slot_uniq = nullptr;               // [2 * entry_cap + n]
-    int* tile_seg0 = nullptr;       // [VL_MAX_TILES + 1] first segment (sorted order) of each tile
+    int* tile_seg0 = nullptr;       // [VL_MAX_TILES + 1] first segment of each tile
+    int* tile_list0 = nullptr;      // [VL_MAX_TILES + 1] first owner list (length-sorted order) of each tile
     int* tile_bundle0 = nullptr;    // [VL_MAX_TILES + 1]
     int* tile_slot0 = nullptr;      // [VL_MAX_TILES + 1]
     int* bundle_row0 = nullptr;     // [bundle_cap + 1]
@@ -161,7 +170,9 @@ struct VlScratch {
 inline void vl_free(VlScratch& S)
 {
     cudaFree(S.L.hdr); cudaFree(S.L.tiles); cudaFree(S.L.slot_word); cudaFree(S.L.slot_ref);
-    cudaFree(S.L.row_bundle); cudaFree(S.L.entries); cudaFree(S.L.seg_pair);
+    cudaFree(S.L.row_owner); cudaFree(S.L.entries); cudaFree(S.L.seg_pair);
+    cudaFree(S.own_key); cudaFree(S.own_val); cudaFree(S.list_key); cudaFree(S.list_len); cudaFree(S.list_start);
+    cudaFree(S.tile_list0);
     cudaFree(S.ref_raw); cudaFree(S.ref_w); cudaFree(S.atomrank); cudaFree(S.cellcnt); cudaFree(S.cellptr);
     cudaFree(S.sref); cudaFree(S.smeta); cudaFree(S.scell); cudaFree(S.tile_of_res);
     for (int k = 0; k < 2; k++) {
@@ -239,7 +250,7 @@ __global__ void vl_init(VlHeader* hdr, const float* box, int periodic, int rbits
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     VlHeader& H = *hdr;
     H.valid = 1; H.fail_code = 0;
-    H.n_tiles = H.n_entries = H.n_segs = H.n_slots = H.n_bundles = H.n_rows = 0;
+    H.n_tiles = H.n_entries = H.n_segs = H.n_lists = H.n_slots = H.n_bundles = H.n_rows = 0;
     H.rbits = rbits; H.abits = abits;
     H.d_max_bits = 0u; H.a_max_bits = 0u;
     for (int k = 0; k < 3; k++) { H.bb_lo[k] = 0xffffffffu; H.bb_hi[k] = 0u; }
@@ -484,7 +495,13 @@ __global__ void __launch_bounds__(256) vl_res_tiles(const VlHeader* hdr, int n_r
 // Candidate pairs of the sorted position p (one WARP per position): q > p in the 27 neighbour
 // cells, reference minimum-image distance <= r_list, roles and residue exclusion.  The warp
 // counts its pairs, reserves room with one atomic and writes the records on a second sweep.
-// record: key = tile << 2 rbits | res_lo << rbits | res_hi,  value = atom_p | atom_q << 20 | shift id << 40
+// record: key = tile << 2 rbits | res_lo << rbits | res_hi,
+//         value = owner atom | partner atom << 20 | shift id of the partner << 40 | direction << 45
+// The OWNER of a pair is its atom in the lower residue (the residue whose tile the pair belongs
+// to): in the frame kernel a lane walks the partners of one owner.  The partner carries the lattice
+// shift of its image relative to the owner (the negated shift when p and q swap roles: shift ids
+// are 13 + (wx, wy, wz) . (1, 3, 9), so -shift is 26 - id and lattice_shift(26 - id) = -lattice_shift(id)
+// bit for bit).  direction = 1: the exact arithmetic runs partner -> owner (always p -> q).
 __global__ void __launch_bounds__(256) vl_pairs(VlHeader* hdr, int n, int n_ignored, const float4* __restrict__ sref,
                                                 const int2* __restrict__ smeta, const int* __restrict__ scell,
                                                 const int* __restrict__ cellptr, const int* __restrict__ tile_of_res,
@@ -554,8 +571,10 @@ __global__ void __launch_bounds__(256) vl_pairs(VlHeader* hdr, int n, int n_igno
                         const int rlo = min(res_i, res_j), rhi = max(res_i, res_j);
                         const unsigned long long tile = (unsigned long long)tile_of_res[rlo];
                         rec_key[out] = (tile << (2 * rbits)) | ((unsigned long long)rlo << rbits) | (unsigned long long)rhi;
-                        rec_val[out] = (unsigned long long)__float_as_int(pi.w) |
-                                       ((unsigned long long)__float_as_int(pj.w) << 20) | ((unsigned long long)id << 40);
+                        const unsigned long long ap = (unsigned long long)__float_as_int(pi.w),
+                                                 aq = (unsigned long long)__float_as_int(pj.w);
+                        rec_val[out] = res_i < res_j ? (ap | (aq << 20) | ((unsigned long long)id << 40))
+                                                     : (aq | (ap << 20) | ((unsigned long long)(26 - id) << 40) | (1ull << 45));
                     }
                 }
                 found += __popc(m);
@@ -577,26 +596,29 @@ __global__ void vl_after_pairs(VlHeader* hdr, long long entry_cap)
     if (hdr->n_entries <= 0) { hdr->valid = 0; hdr->fail_code = 8; }     // no pairs (or overflow): the fall back handles it
 }
 
-// segment bookkeeping after the run-length encode of the sorted record keys
-__global__ void vl_after_rle(VlHeader* hdr, const unsigned long long* __restrict__ seg_key, const int* __restrict__ n_runs)
+// bookkeeping after a run-length encode of sorted keys: which = 0 segments (residue pairs of the
+// records sorted by tile and residue pair), 1 owner lists (records sorted by tile and owner atom)
+__global__ void vl_after_rle(VlHeader* hdr, const unsigned long long* __restrict__ run_key, const int* __restrict__ n_runs,
+                             int which)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0 || !hdr->valid) return;
     int runs = n_runs[0];
-    if (runs > 0 && seg_key[runs - 1] == VL_PAD) runs--;         // the padding forms one trailing run
-    hdr->n_segs = runs;
+    if (runs > 0 && run_key[runs - 1] == VL_PAD) runs--;         // the padding forms one trailing run
+    if (which == 0) hdr->n_segs = runs; else hdr->n_lists = runs;
 }
 
-// bundle sort key of every segment: tile, then length descending
-__global__ void __launch_bounds__(256) vl_seg_sortkeys(const VlHeader* hdr, const unsigned long long* __restrict__ seg_key,
-                                                       const int* __restrict__ seg_len, unsigned long long* __restrict__ skey,
-                                                       int* __restrict__ sval, long long cap)
+// bundle sort key of every owner list: tile, then length descending
+__global__ void __launch_bounds__(256) vl_list_sortkeys(const VlHeader* hdr, const unsigned long long* __restrict__ list_key,
+                                                        const int* __restrict__ list_len,
+                                                        unsigned long long* __restrict__ skey, int* __restrict__ sval,
+                                                        long long cap)
 {
     const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= cap) return;
-    const bool live = hdr->valid && s < hdr->n_segs;
+    const bool live = hdr->valid && s < hdr->n_lists;
     const unsigned lmax = (1u << VL_LEN_BITS) - 1u;
-    skey[s] = live ? (((seg_key[s] >> (2 * hdr->rbits)) << VL_LEN_BITS) |
-                      (unsigned long long)(lmax - min((unsigned)seg_len[s], lmax)))
+    skey[s] = live ? (((list_key[s] >> hdr->abits) << VL_LEN_BITS) |
+                      (unsigned long long)(lmax - min((unsigned)list_len[s], lmax)))
                    : VL_PAD;
     sval[s] = (int)s;
 }
@@ -651,7 +673,49 @@ __device__ __forceinline__ int vl_block_excl_scan(int v, int* wsum, int& total)
     return wsum[warp] + incl - v;
 }
 
-// Layout of tiles / bundles / rows (one CTA of 1024 threads).
+// Segments (residue pairs) of every tile: the unique record keys are sorted by tile.
+__global__ void __launch_bounds__(256) vl_tile_segs(VlHeader* hdr, VlTile* __restrict__ tiles,
+                                                    const unsigned long long* __restrict__ seg_key,
+                                                    int* __restrict__ tile_seg0)
+{
+    if (!hdr->valid) return;
+    const int n_tiles = hdr->n_tiles, n_segs = hdr->n_segs, sh = 2 * hdr->rbits;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > n_tiles) return;
+    const int s0 = t == n_tiles ? n_segs : vl_lower_bound(seg_key, n_segs, (unsigned long long)t << sh);
+    tile_seg0[t] = s0;
+    if (t < n_tiles) {
+        const int s1 = t + 1 == n_tiles ? n_segs : vl_lower_bound(seg_key, n_segs, (unsigned long long)(t + 1) << sh);
+        tiles[t].seg0 = s0;
+        tiles[t].n_segs = s1 - s0;
+        if (s1 - s0 > VL_MAX_SEGS) { hdr->valid = 0; hdr->fail_code = 11; }
+    }
+}
+
+// Second sort key of every record (in the order of the first sort: tile, residue pair): tile and
+// owner atom.  The radix sort is stable, so the partners of one owner stay ordered by residue pair.
+// value: partner atom | shift id << 20 | direction << 25 | tile-relative segment << 26
+__global__ void __launch_bounds__(256) vl_owner_keys(const VlHeader* hdr, const unsigned long long* __restrict__ rec_key,
+                                                     const unsigned long long* __restrict__ rec_val,
+                                                     const int* __restrict__ seg_start, const int* __restrict__ tile_seg0,
+                                                     unsigned long long* __restrict__ own_key,
+                                                     unsigned long long* __restrict__ own_val, long long cap)
+{
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= cap) return;
+    unsigned long long k = VL_PAD, v = 0ull;
+    if (hdr->valid && e < hdr->n_entries) {
+        const unsigned long long tile = rec_key[e] >> (2 * hdr->rbits), r = rec_val[e];
+        const int seg = vl_last_le(seg_start, hdr->n_segs, (int)e) - tile_seg0[tile];
+        k = (tile << hdr->abits) | (r & 0xfffffull);
+        v = ((r >> 20) & 0xfffffull) | (((r >> 40) & 63ull) << 20) | ((unsigned long long)seg << 26);
+    }
+    own_key[e] = k;
+    own_val[e] = v;
+}
+
+// Layout of tiles / bundles / rows (one CTA of 1024 threads).  A bundle = 32 owner lists of
+// similar length (lane = list), stored as rows of 4 steps x 32 lanes.
 __global__ void __launch_bounds__(1024) vl_layout(VlHeader* hdr, VlTile* __restrict__ tiles,
                                                   const unsigned long long* __restrict__ skey_sorted,
                                                   const int* __restrict__ sval_sorted, const int* __restrict__ seg_len,
@@ -661,7 +725,7 @@ __global__ void __launch_bounds__(1024) vl_layout(VlHeader* hdr, VlTile* __restr
     if (!hdr->valid) return;
     __shared__ int wsum[33];
     __shared__ int carry_a;
-    const int n_tiles = hdr->n_tiles, n_segs = hdr->n_segs;
+    const int n_tiles = hdr->n_tiles, n_segs = hdr->n_lists;     // ("seg" below: an owner list)
     for (int t = threadIdx.x; t <= n_tiles; t += 1024)
         tile_seg0[t] = t == n_tiles ? n_segs : vl_lower_bound(skey_sorted, n_segs, (unsigned long long)t << VL_LEN_BITS);
     __syncthreads();
@@ -718,13 +782,12 @@ __global__ void __launch_bounds__(1024) vl_layout(VlHeader* hdr, VlTile* __restr
     __syncthreads();
     if (!hdr->valid) return;
     for (int t = threadIdx.x; t < n_tiles; t += 1024) {
-        VlTile T;
         const int b0 = tile_bundle0[t], b1 = tile_bundle0[t + 1];
-        T.seg0 = tile_seg0[t]; T.n_segs = tile_seg0[t + 1] - tile_seg0[t];
-        T.row0 = bundle_row0[b0]; T.n_rows = bundle_row0[b1] - bundle_row0[b0];
-        T.slot0 = 0; T.n_slots = 0;
-        tiles[t] = T;
-        if (T.n_rows > VL_MAX_ROWS || T.n_segs > VL_MAX_SEGS || b1 - b0 > 0xffff) { hdr->valid = 0; hdr->fail_code = 11; }
+        const int rows = bundle_row0[b1] - bundle_row0[b0];
+        tiles[t].list0 = tile_seg0[t]; tiles[t].n_lists = tile_seg0[t + 1] - tile_seg0[t];
+        tiles[t].row0 = bundle_row0[b0]; tiles[t].n_rows = rows;
+        tiles[t].slot0 = 0; tiles[t].n_slots = 0;
+        if (rows > VL_MAX_ROWS) { hdr->valid = 0; hdr->fail_code = 11; }
     }
 }
 
@@ -790,28 +853,29 @@ __global__ void __launch_bounds__(256) vl_slot_fill(const VlHeader* hdr, const u
     slot_ref[s] = make_float4(r.x, r.y, r.z, 0.f);
 }
 
-// residue pair of every segment (length-sorted order)
-__global__ void __launch_bounds__(256) vl_seg_fill(const VlHeader* hdr, const int* __restrict__ sval_sorted,
-                                                   const unsigned long long* __restrict__ seg_key,
+// residue pair of every segment
+__global__ void __launch_bounds__(256) vl_seg_fill(const VlHeader* hdr, const unsigned long long* __restrict__ seg_key,
                                                    uint2* __restrict__ seg_pair, long long cap)
 {
     if (!hdr->valid) return;
     const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= hdr->n_segs || s >= cap) return;
-    const unsigned long long k = seg_key[sval_sorted[s]];
+    const unsigned long long k = seg_key[s];
     const int rbits = hdr->rbits;
     const unsigned long long rmask = (1ull << rbits) - 1ull;
     seg_pair[s] = make_uint2((unsigned)((k >> rbits) & rmask), (unsigned)(k & rmask));
 }
 
-// Entry words: one block of 128 threads per ROW (thread = lane * 4 + step).
+// Entry words and owner slots: one block of 128 threads per ROW (thread = lane * 4 + step).
+// Lane l of the rows of bundle g walks the owner list 32 g + l of its tile (length-sorted order).
 __global__ void __launch_bounds__(VL_ROW) vl_fill(const VlHeader* hdr, const VlTile* __restrict__ tiles,
                                                   const int* __restrict__ tile_bundle0, const int* __restrict__ bundle_row0,
-                                                  const int* __restrict__ sval_sorted, const int* __restrict__ seg_len,
-                                                  const int* __restrict__ seg_start,
-                                                  const unsigned long long* __restrict__ rec_val,
+                                                  const int* __restrict__ sval_sorted, const int* __restrict__ list_len,
+                                                  const int* __restrict__ list_start,
+                                                  const unsigned long long* __restrict__ list_key,
+                                                  const unsigned long long* __restrict__ own_val,
                                                   const unsigned long long* __restrict__ slot_uniq,
-                                                  const int* __restrict__ tile_slot0, unsigned short* __restrict__ row_bundle,
+                                                  const int* __restrict__ tile_slot0, unsigned short* __restrict__ row_owner,
                                                   unsigned* __restrict__ entries)
 {
     if (!hdr->valid) return;
@@ -822,30 +886,30 @@ __global__ void __launch_bounds__(VL_ROW) vl_fill(const VlHeader* hdr, const VlT
         const int g = vl_last_le(bundle_row0, hdr->n_bundles, R);
         const int t = vl_last_le(tile_bundle0, hdr->n_tiles, g);
         sh[0] = g; sh[1] = t; sh[2] = bundle_row0[g];
-        row_bundle[R] = (unsigned short)(g - tile_bundle0[t]);
     }
     __syncthreads();
     const int g = sh[0], t = sh[1];
     const VlTile T = tiles[t];
     const int lane = threadIdx.x >> 2, step = (R - sh[2]) * 4 + (threadIdx.x & 3);
-    const int seg_rel = 32 * (g - tile_bundle0[t]) + lane;
+    const int list_rel = 32 * (g - tile_bundle0[t]) + lane;
     const unsigned far_off = (unsigned)T.n_slots * 16u;                       // pads never pass the screen
-    unsigned word = far_off << 16;
-    if (seg_rel < T.n_segs) {
-        const int s = sval_sorted[T.seg0 + seg_rel];
-        if (step < seg_len[s]) {
-            const int tb = hdr->abits + 5;
-            const unsigned long long tkey = (unsigned long long)t << tb;
-            const unsigned long long* uniq = slot_uniq + tile_slot0[t];
-            const unsigned long long v = rec_val[seg_start[s] + step];
-            const unsigned long long k0 = tkey | ((v & 0xfffffull) << 5) | (unsigned long long)CT_NOSHIFT;
-            const unsigned long long k1 = tkey | (((v >> 20) & 0xfffffull) << 5) | ((v >> 40) & 31ull);
-            const unsigned si = (unsigned)vl_lower_bound(uniq, T.n_slots, k0);
+    const int tb = hdr->abits + 5;
+    const unsigned long long tkey = (unsigned long long)t << tb;
+    const unsigned long long* uniq = slot_uniq + tile_slot0[t];
+    unsigned word = far_off, owner = 0u;         // (a lane without a list: any finite slot against the far one)
+    if (list_rel < T.n_lists) {
+        const int l = sval_sorted[T.list0 + list_rel];
+        const unsigned long long atom = list_key[l] & ((1ull << hdr->abits) - 1ull);
+        owner = (unsigned)vl_lower_bound(uniq, T.n_slots, tkey | (atom << 5) | (unsigned long long)CT_NOSHIFT) * 16u;
+        if (step < list_len[l]) {
+            const unsigned long long v = own_val[list_start[l] + step];
+            const unsigned long long k1 = tkey | ((v & 0xfffffull) << 5) | ((v >> 20) & 31ull);
             const unsigned sj = (unsigned)vl_lower_bound(uniq, T.n_slots, k1);
-            word = (si * 16u) | ((sj * 16u) << 16);
+            word = (sj * 16u) | (unsigned)((v >> 25) & 1ull) | ((unsigned)(v >> 26) << 16);
         }
     }
     entries[(size_t)R * VL_ROW + threadIdx.x] = word;
+    if ((threadIdx.x & 3) == 0) row_owner[(size_t)R * 32 + lane] = (unsigned short)owner;
 }
 
 // ----- frame kernel --------------------------------------------------------------------------
@@ -866,49 +930,38 @@ constexpr int VL_AUDIT = 1;      // template flag: run the exact arithmetic on E
                                  // count decisions that differ from the screen's
 
 // dynamic shared memory of the frame kernel (bytes); the position array sits at offset 0 so that
-// the entry words are ready-made shared-memory addresses
+// the slot fields of the entry words are ready-made byte offsets
 constexpr int VL_QCAP = 1024;                                          // ambiguous pairs parked per tile and frame
 constexpr int VL_SM_POS = 0;                                           // float4 [VL_MAX_SLOTS + 1]
-constexpr int VL_SM_CNT = VL_SM_POS + (VL_MAX_SLOTS + 1) * 16;         // u32 [VL_MAX_ENTRIES / 4]
-constexpr int VL_SM_RES = VL_SM_CNT + VL_MAX_ENTRIES;                  // u8 [VL_MAX_SEGS]
-constexpr int VL_SM_FLAG = VL_SM_RES + VL_MAX_SEGS;                    // u32 [2][VL_MAX_SEGS / 32] (frame parity)
-constexpr int VL_SM_ROWB = VL_SM_FLAG + 2 * (VL_MAX_SEGS / 8);         // u16 [VL_MAX_ROWS]
-constexpr int VL_SM_QUEUE = VL_SM_ROWB + VL_MAX_ROWS * 2;              // uint2 [VL_QCAP]
+constexpr int VL_SM_CNT = VL_SM_POS + (VL_MAX_SLOTS + 1) * 16;         // u32 [VL_MAX_ENTRIES / 4]: byte counters
+constexpr int VL_SM_RES = VL_SM_CNT + VL_MAX_ENTRIES;                  // u8 [VL_MAX_SEGS]: frames in which the pair was seen
+constexpr int VL_SM_FLAG = VL_SM_RES + VL_MAX_SEGS;                    // u8 [2][VL_MAX_SEGS] "seen in this frame" (frame parity)
+constexpr int VL_SM_QUEUE = VL_SM_FLAG + 2 * VL_MAX_SEGS;              // uint2 [VL_QCAP]
 constexpr int VL_SM_HDR = VL_SM_QUEUE + VL_QCAP * 8;                   // double[18], float4[27], misc
 constexpr int VL_SM_TOTAL = VL_SM_HDR + 18 * 8 + 27 * 16 + 64;
+static_assert(VL_SM_POS == 0, "entry words hold byte offsets from the start of the position array");
 static_assert(VL_SM_TOTAL <= 232448, "frame kernel exceeds the 227 KB of shared memory a CTA can have");
+static_assert(VL_MAX_SEGS <= (1 << VL_SEG_BITS) && VL_MAX_ENTRIES <= (1 << 17), "parked-pair word layout");
 
-__device__ __forceinline__ float4 vl_lds128(unsigned byte_off)
-{
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(byte_off));
-    return v;
-}
-
-__device__ __forceinline__ int vl_lds32i(unsigned byte_off)
-{
-    int v;
-    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(byte_off));
-    return v;
-}
-
-// Exact decision of one parked (ambiguous) list entry and its accounting.  e.x = entry word (slot
-// byte offsets), e.y = row << 7 | lane << 2 | step of the entry inside its tile.  MDTraj's
-// arithmetic on the RAW coordinates of the frame, direction slot i -> slot j (the lower -> higher
-// position of the list's cell order; DESIGN.md "direction").  The counters of an entry belong to
-// the lane that walks it, which may be at work on the same word: shared-memory atomics here.
+// Exact decision of one parked (ambiguous) list entry and its accounting.
+//   e.x = owner slot byte offset | (partner slot byte offset | direction) << 16
+//   e.y = byte-counter index of the entry inside its tile (row * 128 + lane * 4 + step) | segment << 17
+// MDTraj's arithmetic on the RAW coordinates of the frame, always in the direction p -> q of the
+// builder's cell order (direction bit set: partner -> owner; DESIGN.md "direction").  The counter
+// word of an entry may be shared with three other parked entries: shared-memory atomic.
 __device__ __forceinline__ void vl_exact_account(uint2 e, const float* __restrict__ frame, const NlBox& B, float c2,
-                                                 unsigned pos_base, unsigned* cnt32, unsigned* segflag,
-                                                 const unsigned short* rowb)
+                                                 const unsigned char* smem, unsigned* cnt32, unsigned char* segflag)
 {
-    const float* pa = frame + 3 * (size_t)vl_lds32i(pos_base + (e.x & 0xffffu) + 12u);
-    const float* pb = frame + 3 * (size_t)vl_lds32i(pos_base + (e.x >> 16) + 12u);
+    const unsigned own = e.x & 0xffffu, part = (e.x >> 16) & 0xfff0u, rev = (e.x >> 16) & 1u;
+    const int ia = __float_as_int(reinterpret_cast<const float4*>(smem + own)->w);
+    const int ib = __float_as_int(reinterpret_cast<const float4*>(smem + part)->w);
+    const float* pa = frame + 3 * (size_t)(rev ? ib : ia);
+    const float* pb = frame + 3 * (size_t)(rev ? ia : ib);
     const float d2x = nl_d2_dyn(__ldg(pa), __ldg(pa + 1), __ldg(pa + 2), __ldg(pb), __ldg(pb + 1), __ldg(pb + 2), B);
     if (d2x <= c2) {
-        const unsigned row = e.y >> 7, ln = (e.y >> 2) & 31u, q = e.y & 3u;
-        atomicAdd(&cnt32[row * 32u + ln], 1u << (8u * q));
-        vl_reds_or(&segflag[rowb[row]], 1u << ln);
+        const unsigned idx = e.y & 0x1ffffu;
+        atomicAdd(&cnt32[idx >> 2], 1u << (8u * (idx & 3u)));
+        segflag[e.y >> 17] = 1;
     }
 }
 
@@ -919,17 +972,15 @@ __global__ void __launch_bounds__(VL_THREADS, 1) vl_frames(const VlFrameParams p
     float4* pos = reinterpret_cast<float4*>(smem + VL_SM_POS);
     unsigned* cnt32 = reinterpret_cast<unsigned*>(smem + VL_SM_CNT);
     unsigned char* rescnt = smem + VL_SM_RES;
-    unsigned* segflag2 = reinterpret_cast<unsigned*>(smem + VL_SM_FLAG);       // [2][VL_MAX_SEGS / 32]
-    unsigned short* rowb = reinterpret_cast<unsigned short*>(smem + VL_SM_ROWB);
+    unsigned char* segflag2 = smem + VL_SM_FLAG;                               // [2][VL_MAX_SEGS]
     uint2* queue = reinterpret_cast<uint2*>(smem + VL_SM_QUEUE);
     double* hs = reinterpret_cast<double*>(smem + VL_SM_HDR);                  // hinv[9], h[9]
     float4* shift_s = reinterpret_cast<float4*>(smem + VL_SM_HDR + 18 * 8);
-    // [0] item, [1] row counter, [2 + parity] parked pairs of the frame with that parity
+    // [0] item, [2 + parity] parked pairs of the frame with that parity
     int* misc = reinterpret_cast<int*>(smem + VL_SM_HDR + 18 * 8 + 27 * 16);
     const VlHeader& H = *L.hdr;
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (!H.valid) return;                       // every frame is on the fall-back list (vl_all_tripped)
-    const unsigned pos_base = (unsigned)__cvta_generic_to_shared(pos);
     if (tid < 18) hs[tid] = tid < 9 ? H.hinv[tid] : H.h[tid - 9];
     if (tid >= 32 && tid < 32 + 27) shift_s[tid - 32] = H.shift[tid - 32];
     const int periodic = H.periodic;
@@ -959,12 +1010,14 @@ __global__ void __launch_bounds__(VL_THREADS, 1) vl_frames(const VlFrameParams p
         const long long fa = chunk * item_frames, fb = min(p.n_frames, fa + item_frames);
         const VlTile T = L.tiles[t];
         if (T.n_rows == 0) continue;
-        const int flag_words = (T.n_segs + 31) / 32;
-        // ---- tile set-up: counters, row -> bundle table, this thread's slots ----------------
+        const int seg_words = (T.n_segs + 3) / 4;
+        // ---- tile set-up: counters, flags, this thread's slots ---------------------------------
         for (int w = tid; w < T.n_rows * (VL_ROW / 4); w += VL_THREADS) cnt32[w] = 0u;
-        for (int w = tid; w < (T.n_segs + 3) / 4; w += VL_THREADS) reinterpret_cast<unsigned*>(rescnt)[w] = 0u;
-        for (int w = tid; w < flag_words; w += VL_THREADS) { segflag2[w] = 0u; segflag2[VL_MAX_SEGS / 32 + w] = 0u; }
-        for (int w = tid; w < T.n_rows; w += VL_THREADS) rowb[w] = L.row_bundle[T.row0 + w];
+        for (int w = tid; w < seg_words; w += VL_THREADS) {
+            reinterpret_cast<unsigned*>(rescnt)[w] = 0u;
+            reinterpret_cast<unsigned*>(segflag2)[w] = 0u;
+            reinterpret_cast<unsigned*>(segflag2 + VL_MAX_SEGS)[w] = 0u;
+        }
         if (tid == 0) pos[T.n_slots] = make_float4(3.0e18f, 0.f, 0.f, 0.f);      // the "far" slot of padding entries
         // per slot only the word (atom | shift id << 24) and the prefetched raw coordinates stay in
         // registers across the pair phase; the reference position is re-read (L2) every frame
@@ -983,7 +1036,9 @@ __global__ void __launch_bounds__(VL_THREADS, 1) vl_frames(const VlFrameParams p
             }
         }
         const uint4* rows4 = reinterpret_cast<const uint4*>(L.entries + (size_t)T.row0 * VL_ROW);
+        const unsigned short* rown = L.row_owner + (size_t)T.row0 * 32;
         const int n_rows = T.n_rows;
+        const unsigned far_off = (unsigned)T.n_slots * 16u;
         // Per frame f: [phase 1] the pairs frame f-1 could not decide by screening (parked in
         // `queue`) are decided exactly, one per thread, while every thread brings its slots of frame
         // f into `pos`; barrier; [phase 2] the residue pairs seen in frame f-1 are folded into their
@@ -991,29 +1046,23 @@ __global__ void __launch_bounds__(VL_THREADS, 1) vl_frames(const VlFrameParams p
         // counter alternate between two copies with the parity of the frame.
         for (long long f = fa; f <= fb; f++) {
             const int par = (int)((f - fa) & 1);
-            unsigned* flag_cur = segflag2 + par * (VL_MAX_SEGS / 32);
-            unsigned* flag_prev = segflag2 + (par ^ 1) * (VL_MAX_SEGS / 32);
+            unsigned char* flag_cur = segflag2 + par * VL_MAX_SEGS;
+            unsigned char* flag_prev = segflag2 + (par ^ 1) * VL_MAX_SEGS;
             // ---- phase 1a: parked pairs of the previous frame -----------------------------------
             const int parked = f > fa ? min(misc[2 + (par ^ 1)], VL_QCAP) : 0;
             if (parked > 0) {
                 const float* prev = p.xyz + (size_t)(f - 1) * (size_t)p.n * 3;
                 for (int w = tid; w < parked; w += VL_THREADS)
-                    vl_exact_account(queue[w], prev, B, p.c2, pos_base, cnt32, flag_prev, rowb);
+                    vl_exact_account(queue[w], prev, B, p.c2, smem, cnt32, flag_prev);
             }
             if (f == fb) {
                 // after the last frame: fold its flags once the parked pairs are in
                 __syncthreads();
-                for (int w = tid; w < flag_words; w += VL_THREADS) {
-                    unsigned m = flag_prev[w];
-                    while (m) {
-                        const int b = __ffs(m) - 1;
-                        m &= m - 1;
-                        rescnt[w * 32 + b]++;
-                    }
-                }
+                for (int w = tid; w < seg_words; w += VL_THREADS)
+                    reinterpret_cast<unsigned*>(rescnt)[w] += reinterpret_cast<const unsigned*>(flag_prev)[w];
                 break;
             }
-            if (tid == 0) { misc[1] = 0; misc[2 + par] = 0; }
+            if (tid == 0) misc[2 + par] = 0;
             // ---- phase 1b: this frame's slots: unwrap next to the reference, guard ---------------
             // (a frame is re-done by the fall back as a WHOLE: lists with several tiles take the
             // decision from the guard pass vl_guard, which looks at every atom of the frame; a
@@ -1047,16 +1096,13 @@ __global__ void __launch_bounds__(VL_THREADS, 1) vl_frames(const VlFrameParams p
                 }
             }
             trip = __syncthreads_or(trip);
-            // ---- phase 2a: residue pairs seen in the previous frame (set semantics per frame) ----
-            for (int w = tid; w < flag_words; w += VL_THREADS) {
-                unsigned m = flag_prev[w];
+            // ---- phase 2a: residue pairs seen in the previous frame (set semantics per frame:
+            //      a flag byte is 0 or 1, the counters are bytes too: packed add, no carries) -------
+            for (int w = tid; w < seg_words; w += VL_THREADS) {
+                const unsigned m = reinterpret_cast<const unsigned*>(flag_prev)[w];
                 if (m) {
-                    flag_prev[w] = 0u;
-                    while (m) {
-                        const int b = __ffs(m) - 1;
-                        m &= m - 1;
-                        rescnt[w * 32 + b]++;
-                    }
+                    reinterpret_cast<unsigned*>(flag_prev)[w] = 0u;
+                    reinterpret_cast<unsigned*>(rescnt)[w] += m;
                 }
             }
             if (trip) {
@@ -1067,101 +1113,84 @@ __global__ void __launch_bounds__(VL_THREADS, 1) vl_frames(const VlFrameParams p
                 __syncthreads();
                 continue;
             }
-            // ---- phase 2b: warps pull rows, VL_FETCH_ROWS at a time; the entry words of the next
-            //      trip are requested from L2 before the current ones are worked on ------------------
+            // ---- phase 2b: warp w walks the rows w, w + 32, ...; lane l of a row walks four partners
+            //      of ITS owner atom, whose position stays in registers; the entry words of the next
+            //      row are requested from L2 before the current ones are worked on ------------------
             const float* frame = p.xyz + (size_t)f * (size_t)p.n * 3;
-            int r = 0;
-            if (lane == 0) r = vl_atoms_add(&misc[1], VL_FETCH_ROWS);
-            r = __shfl_sync(0xffffffffu, r, 0);
-            uint4 cur[VL_FETCH_ROWS];
-#pragma unroll
-            for (int k = 0; k < VL_FETCH_ROWS; k++)
-                cur[k] = r + k < n_rows ? __ldg(&rows4[(size_t)(r + k) * 32 + lane]) : make_uint4(0u, 0u, 0u, 0u);
-            unsigned prev_i = 0xffffffffu;           // first atom of the previous entry: its position is still in `a`
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            int r = warp;
+            uint4 cur = make_uint4(far_off, far_off, far_off, far_off);
+            unsigned own = 0u;
+            if (r < n_rows) { cur = __ldg(&rows4[(size_t)r * 32 + lane]); own = __ldg(&rown[(size_t)r * 32 + lane]); }
             while (r < n_rows) {
-                int rn = 0;
-                if (lane == 0) rn = vl_atoms_add(&misc[1], VL_FETCH_ROWS);
-                rn = __shfl_sync(0xffffffffu, rn, 0);
-                uint4 nxt[VL_FETCH_ROWS];
+                const int rn = r + VL_THREADS / 32;
+                uint4 nxt = cur;
+                unsigned nown = own;
+                if (rn < n_rows) { nxt = __ldg(&rows4[(size_t)rn * 32 + lane]); nown = __ldg(&rown[(size_t)rn * 32 + lane]); }
+                const float4 a = *reinterpret_cast<const float4*>(smem + own);
+                const unsigned ew[4] = {cur.x, cur.y, cur.z, cur.w};
+                float4 b[4];
 #pragma unroll
-                for (int k = 0; k < VL_FETCH_ROWS; k++)
-                    nxt[k] = rn + k < n_rows ? __ldg(&rows4[(size_t)(rn + k) * 32 + lane]) : make_uint4(0u, 0u, 0u, 0u);
-                unsigned amb = 0u;                   // bit 4 k + q: entry q of row r + k is ambiguous
+                for (int q = 0; q < 4; q++) b[q] = *reinterpret_cast<const float4*>(smem + (ew[q] & 0xfff0u));
+                unsigned c = 0u, amb = 0u;
 #pragma unroll
-                for (int k = 0; k < VL_FETCH_ROWS; k++) {
-                    if (r + k >= n_rows) break;
-                    const unsigned ew[4] = {cur[k].x, cur[k].y, cur[k].z, cur[k].w};
-                    unsigned c = 0u;
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const unsigned oi = ew[q] & 0xffffu, oj = ew[q] >> 16;
-                        if (oi != prev_i) { a = vl_lds128(pos_base + oi); prev_i = oi; }
-                        const float4 b = vl_lds128(pos_base + oj);
-                        const float dx = __fsub_rn(b.x, a.x), dy = __fsub_rn(b.y, a.y), dz = __fsub_rn(b.z, a.z);
-                        const float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
-                        // d2 <= c2_lo: certain contact; c2_lo < d2 < c2_hi: AMBIGUOUS, parked and decided
-                        // by MDTraj's arithmetic in phase 1a of the next frame
-                        const bool hit = d2 <= c2_lo;
-                        amb |= (d2 < c2_hi && !hit) ? (1u << (4 * k + q)) : 0u;
-                        c += hit ? (1u << (8 * q)) : 0u;
-                        if ((FLAGS & VL_AUDIT) && oj != (unsigned)T.n_slots * 16u) {
-                            // audit: the exact arithmetic on EVERY listed pair; the screen's decision
-                            // must agree wherever it takes one
-                            const float* pa = frame + 3 * (size_t)__float_as_int(a.w);
-                            const float* pb = frame + 3 * (size_t)__float_as_int(b.w);
-                            const bool exact = nl_d2_dyn(__ldg(pa), __ldg(pa + 1), __ldg(pa + 2), __ldg(pb),
-                                                         __ldg(pb + 1), __ldg(pb + 2), B) <= p.c2;
-                            audited++;
-                            if ((hit && !exact) || (!(d2 < c2_hi) && exact)) disagreements++;
-                        }
+                for (int q = 0; q < 4; q++) {
+                    const float dx = __fsub_rn(b[q].x, a.x), dy = __fsub_rn(b[q].y, a.y), dz = __fsub_rn(b[q].z, a.z);
+                    const float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+                    // d2 <= c2_lo: certain contact; c2_lo < d2 < c2_hi: AMBIGUOUS, parked and decided
+                    // by MDTraj's arithmetic in phase 1a of the next frame
+                    const bool hit = d2 <= c2_lo;
+                    if (hit) {
+                        flag_cur[ew[q] >> 16] = 1;       // this residue pair was seen in this frame
+                        c += 1u << (8 * q);
                     }
-                    const unsigned m = __ballot_sync(0xffffffffu, c != 0u);
-                    if (c) cnt32[(r + k) * 32 + lane] += c;
-                    // the lanes of a row are the segments 32 b + lane of its bundle b: one flag word per
-                    // bundle (other rows of the bundle may be setting it at the same time)
-                    if (lane == 0 && m) {
-                        unsigned* fw = &flag_cur[rowb[r + k]];
-                        if ((*(volatile unsigned*)fw & m) != m) vl_reds_or(fw, m);
+                    amb |= (d2 < c2_hi && !hit) ? (1u << q) : 0u;
+                    if ((FLAGS & VL_AUDIT) && (ew[q] & 0xfff0u) != far_off) {
+                        // audit: the exact arithmetic on EVERY listed pair; the screen's decision
+                        // must agree wherever it takes one
+                        const int ia = __float_as_int(a.w), ib = __float_as_int(b[q].w);
+                        const bool rev = (ew[q] & 1u) != 0u;
+                        const float* pa = frame + 3 * (size_t)(rev ? ib : ia);
+                        const float* pb = frame + 3 * (size_t)(rev ? ia : ib);
+                        const bool exact = nl_d2_dyn(__ldg(pa), __ldg(pa + 1), __ldg(pa + 2), __ldg(pb),
+                                                     __ldg(pb + 1), __ldg(pb + 2), B) <= p.c2;
+                        audited++;
+                        if ((hit && !exact) || (!(d2 < c2_hi) && exact)) disagreements++;
                     }
                 }
+                if (c) cnt32[r * 32 + lane] += c;        // the entry's byte counters belong to this thread
                 if (amb) {
                     // park (rare, divergent); a full queue decides on the spot
 #pragma unroll
-                    for (int k = 0; k < VL_FETCH_ROWS; k++) {
-                        const unsigned ew[4] = {cur[k].x, cur[k].y, cur[k].z, cur[k].w};
-#pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            if (amb & (1u << (4 * k + q))) {
-                                const uint2 e = make_uint2(ew[q], ((unsigned)(r + k) << 7) | ((unsigned)lane << 2) | (unsigned)q);
-                                const int w = vl_atoms_add(&misc[2 + par], 1);
-                                if (w < VL_QCAP) queue[w] = e;
-                                else vl_exact_account(e, frame, B, p.c2, pos_base, cnt32, flag_cur, rowb);
-                            }
+                    for (int q = 0; q < 4; q++) {
+                        if (amb & (1u << q)) {
+                            const uint2 e = make_uint2(own | (ew[q] << 16),
+                                                       (unsigned)(r * VL_ROW + lane * 4 + q) | ((ew[q] >> 16) << 17));
+                            const int w = vl_atoms_add(&misc[2 + par], 1);
+                            if (w < VL_QCAP) queue[w] = e;
+                            else vl_exact_account(e, frame, B, p.c2, smem, cnt32, flag_cur);
                         }
                     }
                 }
                 r = rn;
-#pragma unroll
-                for (int k = 0; k < VL_FETCH_ROWS; k++) cur[k] = nxt[k];
+                cur = nxt;
+                own = nown;
             }
             __syncthreads();
         }
         __syncthreads();
         // ---- end of the item: flush the counters ------------------------------------------------
         if (p.atom_table != nullptr) {
-            const unsigned* ent = L.entries + (size_t)T.row0 * VL_ROW;
             for (int w = tid; w < T.n_rows * (VL_ROW / 4); w += VL_THREADS) {
                 const unsigned c = cnt32[w];
                 if (c == 0u) continue;
-                const uint4 e4 = *reinterpret_cast<const uint4*>(ent + (size_t)w * 4);
+                const uint4 e4 = rows4[w];
                 const unsigned ew[4] = {e4.x, e4.y, e4.z, e4.w};
+                const unsigned ia = L.slot_word[T.slot0 + ((unsigned)rown[w] >> 4)] & 0xffffffu;
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     const unsigned cq = (c >> (8 * q)) & 0xffu;
                     if (cq) {
-                        const unsigned ia = L.slot_word[T.slot0 + ((ew[q] & 0xffffu) >> 4)] & 0xffffffu;
-                        const unsigned ib = L.slot_word[T.slot0 + (ew[q] >> 20)] & 0xffffffu;
+                        const unsigned ib = L.slot_word[T.slot0 + ((ew[q] & 0xfff0u) >> 4)] & 0xffffffu;
                         const unsigned lo = min(ia, ib), hi = max(ia, ib);
                         atomicAdd(&p.atom_table[(size_t)lo * (size_t)p.n + (size_t)hi], cq);
                     }
@@ -1302,7 +1331,7 @@ inline int vl_ensure(VlScratch& S, int n, int n_res_c, std::string& err)
         VL_CK(cudaMalloc(&S.L.tiles, sizeof(VlTile) * VL_MAX_TILES));
         VL_CK(cudaMalloc(&S.L.slot_word, sizeof(unsigned) * (size_t)S.L.slot_cap));
         VL_CK(cudaMalloc(&S.L.slot_ref, sizeof(float4) * (size_t)S.L.slot_cap));
-        VL_CK(cudaMalloc(&S.L.row_bundle, sizeof(unsigned short) * (size_t)S.L.row_cap));
+        VL_CK(cudaMalloc(&S.L.row_owner, sizeof(unsigned short) * (size_t)S.L.row_cap * 32));
         VL_CK(cudaMalloc(&S.L.entries, sizeof(unsigned) * (size_t)S.L.row_cap * VL_ROW));
         VL_CK(cudaMalloc(&S.L.seg_pair, sizeof(uint2) * (size_t)E));
         VL_CK(cudaMalloc(&S.ref_raw, sizeof(float4) * (size_t)n));
@@ -1325,7 +1354,13 @@ inline int vl_ensure(VlScratch& S, int n, int n_res_c, std::string& err)
         VL_CK(cudaMalloc(&S.seg_key, 8 * (size_t)E));
         VL_CK(cudaMalloc(&S.seg_len, 4 * (size_t)E));
         VL_CK(cudaMalloc(&S.seg_start, 4 * (size_t)(E + 1)));
-        VL_CK(cudaMalloc(&S.n_runs, 4 * 2));
+        VL_CK(cudaMalloc(&S.n_runs, 4 * 3));
+        VL_CK(cudaMalloc(&S.own_key, 8 * (size_t)E));
+        VL_CK(cudaMalloc(&S.own_val, 8 * (size_t)E));
+        VL_CK(cudaMalloc(&S.list_key, 8 * (size_t)E));
+        VL_CK(cudaMalloc(&S.list_len, 4 * (size_t)E));
+        VL_CK(cudaMalloc(&S.list_start, 4 * (size_t)(E + 1)));
+        VL_CK(cudaMalloc(&S.tile_list0, 4 * (VL_MAX_TILES + 1)));
         VL_CK(cudaMalloc(&S.slot_uniq, 8 * (size_t)(2 * E + n)));
         VL_CK(cudaMalloc(&S.tile_seg0, 4 * (VL_MAX_TILES + 1)));
         VL_CK(cudaMalloc(&S.tile_bundle0, 4 * (VL_MAX_TILES + 1)));
@@ -1374,21 +1409,37 @@ inline int vl_build(const VlJob& job, VlScratch& S, cudaStream_t st, std::string
     vl_pairs<<<(n + 7) / 8, 256, 0, st>>>(S.L.hdr, n, job.n_ignored, S.sref, S.smeta, S.scell, S.cellptr, S.tile_of_res,
                                           S.rec_key[0], S.rec_val[0], E);
     vl_after_pairs<<<1, 1, 0, st>>>(S.L.hdr, E);
+    // sort 1: by tile and residue pair -> segments (the residue pairs of every tile)
     size_t tb = S.cub_bytes;
     VL_CK(cub::DeviceRadixSort::SortPairs(S.cub_tmp, tb, S.rec_key[0], S.rec_key[1], S.rec_val[0], S.rec_val[1], (int)E, 0,
                                           2 * rbits + tbits, st));
     VL_CK(cudaMemsetAsync(S.seg_len, 0, 4 * (size_t)E, st));
-    VL_CK(cudaMemsetAsync(S.n_runs, 0, 8, st));
+    VL_CK(cudaMemsetAsync(S.list_len, 0, 4 * (size_t)E, st));
+    VL_CK(cudaMemsetAsync(S.n_runs, 0, 12, st));
     tb = S.cub_bytes;
     VL_CK(cub::DeviceRunLengthEncode::Encode(S.cub_tmp, tb, S.rec_key[1], S.seg_key, S.seg_len, S.n_runs, (int)E, st));
-    vl_after_rle<<<1, 1, 0, st>>>(S.L.hdr, S.seg_key, S.n_runs);
+    vl_after_rle<<<1, 1, 0, st>>>(S.L.hdr, S.seg_key, S.n_runs, 0);
     tb = S.cub_bytes;
     VL_CK(cub::DeviceScan::ExclusiveSum(S.cub_tmp, tb, S.seg_len, S.seg_start, (int)E, st));
-    vl_seg_sortkeys<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(S.L.hdr, S.seg_key, S.seg_len, S.skey[0], S.sval[0], E);
+    vl_tile_segs<<<(VL_MAX_TILES + 1 + 255) / 256, 256, 0, st>>>(S.L.hdr, S.L.tiles, S.seg_key, S.tile_seg0);
+    vl_seg_fill<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(S.L.hdr, S.seg_key, S.L.seg_pair, E);
+    // sort 2 (stable): by tile and owner atom -> owner lists, each still ordered by residue pair
+    vl_owner_keys<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(S.L.hdr, S.rec_key[1], S.rec_val[1], S.seg_start, S.tile_seg0,
+                                                               S.rec_key[0], S.rec_val[0], E);
+    tb = S.cub_bytes;
+    VL_CK(cub::DeviceRadixSort::SortPairs(S.cub_tmp, tb, S.rec_key[0], S.own_key, S.rec_val[0], S.own_val, (int)E, 0,
+                                          abits + tbits, st));
+    tb = S.cub_bytes;
+    VL_CK(cub::DeviceRunLengthEncode::Encode(S.cub_tmp, tb, S.own_key, S.list_key, S.list_len, S.n_runs + 2, (int)E, st));
+    vl_after_rle<<<1, 1, 0, st>>>(S.L.hdr, S.list_key, S.n_runs + 2, 1);
+    tb = S.cub_bytes;
+    VL_CK(cub::DeviceScan::ExclusiveSum(S.cub_tmp, tb, S.list_len, S.list_start, (int)E, st));
+    // bundles: the lists of a tile sorted by length, 32 to a bundle
+    vl_list_sortkeys<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(S.L.hdr, S.list_key, S.list_len, S.skey[0], S.sval[0], E);
     tb = S.cub_bytes;
     VL_CK(cub::DeviceRadixSort::SortPairs(S.cub_tmp, tb, S.skey[0], S.skey[1], S.sval[0], S.sval[1], (int)E, 0,
                                           VL_LEN_BITS + tbits, st));
-    vl_layout<<<1, 1024, 0, st>>>(S.L.hdr, S.L.tiles, S.skey[1], S.sval[1], S.seg_len, S.tile_seg0, S.tile_bundle0,
+    vl_layout<<<1, 1024, 0, st>>>(S.L.hdr, S.L.tiles, S.skey[1], S.sval[1], S.list_len, S.tile_list0, S.tile_bundle0,
                                   S.bundle_row0, S.bundle_cap, S.L.row_cap);
     const long long n_keys = 2 * E + n;
     vl_slot_keys<<<(unsigned)((std::max<long long>(E, n) + 255) / 256), 256, 0, st>>>(S.L.hdr, S.rec_key[1], S.rec_val[1],
@@ -1401,12 +1452,11 @@ inline int vl_build(const VlJob& job, VlScratch& S, cudaStream_t st, std::string
                                                                    S.L.slot_cap);
     vl_slot_fill<<<(unsigned)((S.L.slot_cap + 255) / 256), 256, 0, st>>>(S.L.hdr, S.slot_uniq, S.ref_w, S.L.slot_word,
                                                                          S.L.slot_ref, S.L.slot_cap);
-    vl_seg_fill<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(S.L.hdr, S.sval[1], S.seg_key, S.L.seg_pair, E);
     vl_fill<<<(unsigned)S.L.row_cap, VL_ROW, 0, st>>>(S.L.hdr, S.L.tiles, S.tile_bundle0, S.bundle_row0, S.sval[1],
-                                                      S.seg_len, S.seg_start, S.rec_val[1], S.slot_uniq, S.tile_slot0,
-                                                      S.L.row_bundle, S.L.entries);
+                                                      S.list_len, S.list_start, S.list_key, S.own_val, S.slot_uniq,
+                                                      S.tile_slot0, S.L.row_owner, S.L.entries);
     VL_CK(cudaGetLastError());
-    launches += 24;
+    launches += 30;
     return 0;
 }
 
