@@ -68,8 +68,9 @@ constexpr int VL_MAX_SLOTS = VL_THREADS * VL_SPT - 1;    // + 1 "far" slot for p
 constexpr int VL_ROW = 128;                              // entries per row: 32 lanes x 4 steps
 constexpr int VL_MAX_ROWS = 768;                         // per tile
 constexpr int VL_MAX_ENTRIES = VL_MAX_ROWS * VL_ROW;     // 98 304 byte counters
-constexpr int VL_MAX_SEGS = 16384;                       // residue pairs per tile
-constexpr int VL_SEG_BITS = 14;                          // bits of a tile-relative segment id
+constexpr int VL_MAX_SEGS = 24576;                       // residue pairs per tile
+constexpr int VL_SEG_BITS = 15;                          // bits of a tile-relative segment id
+constexpr int VL_SLOT_BYTES = 8;                         // a slot of the frame kernel: three 16-bit grid coordinates
 constexpr int VL_MAX_TILES = 4096;
 constexpr int VL_MAXC = 1 << 17;                         // cells of the list grid
 constexpr int VL_SAMPLES = 16;
@@ -88,6 +89,9 @@ struct VlHeader {
     unsigned d_max_bits, a_max_bits;       // sample maxima (non-negative float bits)
     unsigned bb_lo[3], bb_hi[3];           // bounding box of the reference positions (ordered uints)
     float skin2, rlist, a_assumed, c2_lo, c2_hi;
+    // the frame kernel keeps the positions of a tile as 16-bit fixed-point numbers relative to the
+    // tile's origin (8-byte shared-memory gathers): grid units per nm, thresholds in grid units^2
+    float skin, qscale, c2q_lo, c2q_hi;
     int periodic;
     unsigned box_bits[9];      // the batch's unit cell (compared bit for bit per frame)
     double hinv[9], h[9];
@@ -101,6 +105,7 @@ struct VlTile {
     int seg0, n_segs;          // into seg_pair: the residue pairs of the tile
     int list0, n_lists;        // owner lists of the tile (length-sorted order; builder only)
     int row0, n_rows;          // into entries (rows of VL_ROW words) and row_owner
+    float ox, oy, oz;          // origin of the tile's fixed-point grid (below every slot position the guard admits)
 };
 
 // everything the builder writes and the frame kernel reads (device pointers)
@@ -109,9 +114,10 @@ struct VlList {
     VlTile* tiles;             // [VL_MAX_TILES]
     unsigned* slot_word;       // [slot_cap] atom | shift id << 24
     float4* slot_ref;          // [slot_cap] reference position of the slot's atom (primary cell)
+    unsigned* tile_bb;         // [VL_MAX_TILES][6] bounding box of the tile's slot reference positions (ordered uints)
     unsigned short* row_owner; // [row_cap * 32] slot (byte offset into the position array) of the atom that owns
                                // lane l of the row: the lane walks (a part of) that atom's partner list
-    unsigned* entries;         // [row_cap * VL_ROW] partner slot byte offset (bits 4-15) | direction (bit 0) |
+    unsigned* entries;         // [row_cap * VL_ROW] partner slot byte offset (bits 3-15) | direction (bit 0) |
                                // tile-relative segment (residue pair) << 16
     uint2* seg_pair;           // [entry_cap] {compact residue lo, hi} of every segment
     const float4* ref_w;       // [n] wrapped reference position of every atom (guard pass)
@@ -170,7 +176,7 @@ struct VlScratch {
 inline void vl_free(VlScratch& S)
 {
     cudaFree(S.L.hdr); cudaFree(S.L.tiles); cudaFree(S.L.slot_word); cudaFree(S.L.slot_ref);
-    cudaFree(S.L.row_owner); cudaFree(S.L.entries); cudaFree(S.L.seg_pair);
+    cudaFree(S.L.row_owner); cudaFree(S.L.entries); cudaFree(S.L.seg_pair); cudaFree(S.L.tile_bb);
     cudaFree(S.own_key); cudaFree(S.own_val); cudaFree(S.list_key); cudaFree(S.list_len); cudaFree(S.list_start);
     cudaFree(S.tile_list0);
     cudaFree(S.ref_raw); cudaFree(S.ref_w); cudaFree(S.atomrank); cudaFree(S.cellcnt); cudaFree(S.cellptr);
@@ -355,6 +361,7 @@ __global__ void vl_setup(VlHeader* hdr, const float* box, int n, float cutoff, f
     if (rlist > max_rlist_factor * cutoff) { H.valid = 0; H.fail_code = 3; return; }   // the list would not pay
     // the guard compares in fp32 against a slightly smaller radius than the list was built for
     H.skin2 = skin * skin * 0.9999f;
+    H.skin = skin;
     H.rlist = rlist;
     H.a_assumed = 1.25f * amax + 0.5f;
     float lo[3] = {0.f, 0.f, 0.f}, hi[3] = {0.f, 0.f, 0.f};
@@ -840,8 +847,9 @@ __global__ void __launch_bounds__(256) vl_slot_ranges(VlHeader* hdr, VlTile* __r
 }
 
 __global__ void __launch_bounds__(256) vl_slot_fill(const VlHeader* hdr, const unsigned long long* __restrict__ slot_uniq,
-                                                    const float4* __restrict__ ref_w, unsigned* __restrict__ slot_word,
-                                                    float4* __restrict__ slot_ref, long long slot_cap)
+                                                    const float4* __restrict__ ref_w, const int* __restrict__ tile_slot0,
+                                                    unsigned* __restrict__ slot_word, float4* __restrict__ slot_ref,
+                                                    unsigned* __restrict__ tile_bb, long long slot_cap)
 {
     if (!hdr->valid) return;
     const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -851,6 +859,63 @@ __global__ void __launch_bounds__(256) vl_slot_fill(const VlHeader* hdr, const u
     slot_word[s] = atom | (id << 24);
     const float4 r = ref_w[atom];
     slot_ref[s] = make_float4(r.x, r.y, r.z, 0.f);
+    // bounding box of the tile's slots at their reference positions (lattice shift included)
+    const int t = vl_last_le(tile_slot0, hdr->n_tiles, (int)s);
+    const float4 sh = hdr->shift[id];
+    const float px = __fadd_rn(r.x, sh.x), py = __fadd_rn(r.y, sh.y), pz = __fadd_rn(r.z, sh.z);
+    unsigned* bb = tile_bb + 6 * (size_t)t;
+    atomicMin(&bb[0], vl_ordered(px)); atomicMax(&bb[3], vl_ordered(px));
+    atomicMin(&bb[1], vl_ordered(py)); atomicMax(&bb[4], vl_ordered(py));
+    atomicMin(&bb[2], vl_ordered(pz)); atomicMax(&bb[5], vl_ordered(pz));
+}
+
+__global__ void __launch_bounds__(256) vl_bb_init(unsigned* __restrict__ tile_bb)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < VL_MAX_TILES * 6) tile_bb[i] = (i % 6) < 3 ? 0xffffffffu : 0u;
+}
+
+// Fixed-point grid of the frame kernel (one CTA): every slot position the guard admits lies within
+// `skin` of its reference position, so a tile's positions fit [bb_lo - skin, bb_hi + skin]; the
+// common scale maps the widest tile onto 16 bits.  A position is rounded to the grid once, so a
+// coordinate difference is off by at most one grid step h (plus the fp32 rounding of the scaling,
+// < 0.01 h): |d_grid - d_screen| <= sqrt(3) * 1.02 h =: eq.  Thresholds on the grid distance that
+// keep the screen's guarantees: sqrt(c2q_lo) = sqrt(c2_lo) - eq, sqrt(c2q_hi) =
+// sqrt(c2_hi) + eq, expressed in grid units^2 with a relative allowance of 1e-6 for the fp32
+// evaluation of the squared grid distance (integers below 2^16, three products: < 2e-7).
+__global__ void __launch_bounds__(1024) vl_quant_setup(VlHeader* hdr, VlTile* __restrict__ tiles,
+                                                       const unsigned* __restrict__ tile_bb, float cutoff)
+{
+    if (!hdr->valid) return;
+    __shared__ float wmax[32];
+    const int n_tiles = hdr->n_tiles;
+    const float skin = hdr->skin, pad = skin + 1.0e-3f;
+    float ext = 0.f;
+    for (int t = threadIdx.x; t < n_tiles; t += 1024) {
+        if (tiles[t].n_slots <= 0) continue;
+        const unsigned* bb = tile_bb + 6 * (size_t)t;
+        for (int k = 0; k < 3; k++) {
+            const float lo = vl_unordered(bb[k]), hi = vl_unordered(bb[3 + k]);
+            ext = fmaxf(ext, hi - lo);
+            (k == 0 ? tiles[t].ox : k == 1 ? tiles[t].oy : tiles[t].oz) = lo - pad;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) ext = fmaxf(ext, __shfl_xor_sync(0xffffffffu, ext, d));
+    if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = ext;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 32; w++) ext = fmaxf(ext, wmax[w]);
+        const float range = ext + 2.0f * pad;
+        const float qscale = 65000.0f / range;               // grid units per nm (positions stay below 65 001)
+        const float eq = 1.7320508f * 1.02f / qscale;
+        const float lo = sqrtf(hdr->c2_lo) * 0.999999f - eq, hi = sqrtf(hdr->c2_hi) * 1.000001f + eq;
+        hdr->qscale = qscale;
+        hdr->c2q_lo = lo * lo * qscale * qscale * 0.999998f;
+        hdr->c2q_hi = hi * hi * qscale * qscale * 1.000002f;
+        // a grid too coarse to be useful (huge sparse tiles): every frame falls back
+        if (!(eq < 0.02f * cutoff) || !(lo > 0.f) || !(range < 1.0e6f)) { hdr->valid = 0; hdr->fail_code = 14; }
+    }
 }
 
 // residue pair of every segment
@@ -892,7 +957,7 @@ __global__ void __launch_bounds__(VL_ROW) vl_fill(const VlHeader* hdr, const VlT
     const VlTile T = tiles[t];
     const int lane = threadIdx.x >> 2, step = (R - sh[2]) * 4 + (threadIdx.x & 3);
     const int list_rel = 32 * (g - tile_bundle0[t]) + lane;
-    const unsigned far_off = (unsigned)T.n_slots * 16u;                       // pads never pass the screen
+    const unsigned far_off = (unsigned)T.n_slots * VL_SLOT_BYTES;            // pads never pass the screen
     const int tb = hdr->abits + 5;
     const unsigned long long tkey = (unsigned long long)t << tb;
     const unsigned long long* uniq = slot_uniq + tile_slot0[t];
@@ -900,12 +965,12 @@ __global__ void __launch_bounds__(VL_ROW) vl_fill(const VlHeader* hdr, const VlT
     if (list_rel < T.n_lists) {
         const int l = sval_sorted[T.list0 + list_rel];
         const unsigned long long atom = list_key[l] & ((1ull << hdr->abits) - 1ull);
-        owner = (unsigned)vl_lower_bound(uniq, T.n_slots, tkey | (atom << 5) | (unsigned long long)CT_NOSHIFT) * 16u;
+        owner = (unsigned)vl_lower_bound(uniq, T.n_slots, tkey | (atom << 5) | (unsigned long long)CT_NOSHIFT) * VL_SLOT_BYTES;
         if (step < list_len[l]) {
             const unsigned long long v = own_val[list_start[l] + step];
             const unsigned long long k1 = tkey | ((v & 0xfffffull) << 5) | ((v >> 20) & 31ull);
             const unsigned sj = (unsigned)vl_lower_bound(uniq, T.n_slots, k1);
-            word = (sj * 16u) | (unsigned)((v >> 25) & 1ull) | ((unsigned)(v >> 26) << 16);
+            word = (sj * VL_SLOT_BYTES) | (unsigned)((v >> 25) & 1ull) | ((unsigned)(v >> 26) << 16);
         }
     }
     entries[(size_t)R * VL_ROW + threadIdx.x] = word;
@@ -932,8 +997,8 @@ constexpr int VL_AUDIT = 1;      // template flag: run the exact arithmetic on E
 // dynamic shared memory of the frame kernel (bytes); the position array sits at offset 0 so that
 // the slot fields of the entry words are ready-made byte offsets
 constexpr int VL_QCAP = 1024;                                          // ambiguous pairs parked per tile and frame
-constexpr int VL_SM_POS = 0;                                           // float4 [VL_MAX_SLOTS + 1]
-constexpr int VL_SM_CNT = VL_SM_POS + (VL_MAX_SLOTS + 1) * 16;         // u32 [VL_MAX_ENTRIES / 4]: byte counters
+constexpr int VL_SM_POS = 0;                                           // uint2 [VL_MAX_SLOTS + 1]: x | y << 16, z
+constexpr int VL_SM_CNT = VL_SM_POS + (VL_MAX_SLOTS + 1) * VL_SLOT_BYTES;   // u32 [VL_MAX_ENTRIES / 4]: byte counters
 constexpr int VL_SM_RES = VL_SM_CNT + VL_MAX_ENTRIES;                  // u8 [VL_MAX_SEGS]: frames in which the pair was seen
 constexpr int VL_SM_FLAG = VL_SM_RES + VL_MAX_SEGS;                    // u8 [2][VL_MAX_SEGS] "seen in this frame" (frame parity)
 constexpr int VL_SM_QUEUE = VL_SM_FLAG + 2 * VL_MAX_SEGS;              // uint2 [VL_QCAP]
@@ -941,7 +1006,26 @@ constexpr int VL_SM_HDR = VL_SM_QUEUE + VL_QCAP * 8;                   // double
 constexpr int VL_SM_TOTAL = VL_SM_HDR + 18 * 8 + 27 * 16 + 64;
 static_assert(VL_SM_POS == 0, "entry words hold byte offsets from the start of the position array");
 static_assert(VL_SM_TOTAL <= 232448, "frame kernel exceeds the 227 KB of shared memory a CTA can have");
-static_assert(VL_MAX_SEGS <= (1 << VL_SEG_BITS) && VL_MAX_ENTRIES <= (1 << 17), "parked-pair word layout");
+static_assert(VL_MAX_SEGS <= (1 << VL_SEG_BITS) && VL_MAX_ENTRIES <= (1 << 17) && VL_SEG_BITS + 17 <= 32,
+              "parked-pair word layout");
+static_assert((VL_MAX_SLOTS + 1) * VL_SLOT_BYTES <= 65536, "slot byte offsets are 16-bit fields");
+
+// 32-bit shared-memory accesses by address (the addresses are kept in registers across the row loop)
+__device__ __forceinline__ uint2 vl_lds64(unsigned addr)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void vl_sts8(unsigned addr, unsigned v)
+{
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+// the two 16-bit halves of a word as the exact floats 2^23 + value (one PRMT each): differences of
+// such floats are exact integers
+__device__ __forceinline__ float vl_lo16f(unsigned w) { return __uint_as_float(__byte_perm(w, 0x4b000000u, 0x7610)); }
+__device__ __forceinline__ float vl_hi16f(unsigned w) { return __uint_as_float(__byte_perm(w, 0x4b000000u, 0x7632)); }
+__device__ __forceinline__ float vl_z23f(unsigned w) { return __uint_as_float(w | 0x4b000000u); }
 
 // Exact decision of one parked (ambiguous) list entry and its accounting.
 //   e.x = owner slot byte offset | (partner slot byte offset | direction) << 16
@@ -950,11 +1034,12 @@ static_assert(VL_MAX_SEGS <= (1 << VL_SEG_BITS) && VL_MAX_ENTRIES <= (1 << 17), 
 // builder's cell order (direction bit set: partner -> owner; DESIGN.md "direction").  The counter
 // word of an entry may be shared with three other parked entries: shared-memory atomic.
 __device__ __forceinline__ void vl_exact_account(uint2 e, const float* __restrict__ frame, const NlBox& B, float c2,
-                                                 const unsigned char* smem, unsigned* cnt32, unsigned char* segflag)
+                                                 const unsigned* __restrict__ tile_slot_word, unsigned* cnt32,
+                                                 unsigned char* segflag)
 {
-    const unsigned own = e.x & 0xffffu, part = (e.x >> 16) & 0xfff0u, rev = (e.x >> 16) & 1u;
-    const int ia = __float_as_int(reinterpret_cast<const float4*>(smem + own)->w);
-    const int ib = __float_as_int(reinterpret_cast<const float4*>(smem + part)->w);
+    const unsigned own = (e.x & 0xffffu) / VL_SLOT_BYTES, part = ((e.x >> 16) & 0xfff8u) / VL_SLOT_BYTES;
+    const unsigned rev = (e.x >> 16) & 1u;
+    const unsigned ia = __ldg(&tile_slot_word[own]) & 0xffffffu, ib = __ldg(&tile_slot_word[part]) & 0xffffffu;
     const float* pa = frame + 3 * (size_t)(rev ? ib : ia);
     const float* pb = frame + 3 * (size_t)(rev ? ia : ib);
     const float d2x = nl_d2_dyn(__ldg(pa), __ldg(pa + 1), __ldg(pa + 2), __ldg(pb), __ldg(pb + 1), __ldg(pb + 2), B);
@@ -969,7 +1054,7 @@ template <int FLAGS>
 __global__ void __launch_bounds__(VL_THREADS, 1) vl_frames(const VlFrameParams p, const VlList L, const VlRun R)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    float4* pos = reinterpret_cast<float4*>(smem + VL_SM_POS);
+    uint2* pos = reinterpret_cast<uint2*>(smem + VL_SM_POS);
     unsigned* cnt32 = reinterpret_cast<unsigned*>(smem + VL_SM_CNT);
     unsigned char* rescnt = smem + VL_SM_RES;
     unsigned char* segflag2 = smem + VL_SM_FLAG;                               // [2][VL_MAX_SEGS]
@@ -981,10 +1066,11 @@ __global__ void __launch_bounds__(VL_THREADS, 1) vl_frames(const VlFrameParams p
     const VlHeader& H = *L.hdr;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (!H.valid) return;                       // every frame is on the fall-back list (vl_all_tripped)
+    const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem);
     if (tid < 18) hs[tid] = tid < 9 ? H.hinv[tid] : H.h[tid - 9];
     if (tid >= 32 && tid < 32 + 27) shift_s[tid - 32] = H.shift[tid - 32];
     const int periodic = H.periodic;
-    const float skin2 = H.skin2, a_assumed = H.a_assumed, c2_lo = H.c2_lo, c2_hi = H.c2_hi;
+    const float skin2 = H.skin2, a_assumed = H.a_assumed, c2q_lo = H.c2q_lo, c2q_hi = H.c2q_hi, qscale = H.qscale;
     const int n_tiles = H.n_tiles;
     const bool multi_tile = n_tiles > 1;
     // work item = tile x range of frames: about p.rounds items per SM, of equal length, long enough
@@ -1018,19 +1104,21 @@ __global__ void __launch_bounds__(VL_THREADS, 1) vl_frames(const VlFrameParams p
             reinterpret_cast<unsigned*>(segflag2)[w] = 0u;
             reinterpret_cast<unsigned*>(segflag2 + VL_MAX_SEGS)[w] = 0u;
         }
-        if (tid == 0) pos[T.n_slots] = make_float4(3.0e18f, 0.f, 0.f, 0.f);      // the "far" slot of padding entries
+        // the "far" slot of padding entries: z = 2^23 - 1 grid units, beyond every threshold
+        if (tid == 0) pos[T.n_slots] = make_uint2(0u, 0x7fffffu);
         // per slot only the word (atom | shift id << 24) and the prefetched raw coordinates stay in
         // registers across the pair phase; the reference position is re-read (L2) every frame
         unsigned s_word[VL_SPT];
         float raw_x[VL_SPT], raw_y[VL_SPT], raw_z[VL_SPT];
         const float4* slot_ref = L.slot_ref + T.slot0;
+        const unsigned* tile_slot_word = L.slot_word + T.slot0;
 #pragma unroll
         for (int k = 0; k < VL_SPT; k++) {
             const int s = tid + k * VL_THREADS;
             s_word[k] = 0xffffffffu;
             raw_x[k] = raw_y[k] = raw_z[k] = 0.f;
             if (s < T.n_slots) {
-                s_word[k] = L.slot_word[T.slot0 + s];
+                s_word[k] = tile_slot_word[s];
                 const float* q = p.xyz + ((size_t)fa * (size_t)p.n + (size_t)(s_word[k] & 0xffffffu)) * 3;
                 raw_x[k] = __ldg(q); raw_y[k] = __ldg(q + 1); raw_z[k] = __ldg(q + 2);
             }
@@ -1038,7 +1126,7 @@ __global__ void __launch_bounds__(VL_THREADS, 1) vl_frames(const VlFrameParams p
         const uint4* rows4 = reinterpret_cast<const uint4*>(L.entries + (size_t)T.row0 * VL_ROW);
         const unsigned short* rown = L.row_owner + (size_t)T.row0 * 32;
         const int n_rows = T.n_rows;
-        const unsigned far_off = (unsigned)T.n_slots * 16u;
+        const unsigned far_off = (unsigned)T.n_slots * VL_SLOT_BYTES;
         // Per frame f: [phase 1] the pairs frame f-1 could not decide by screening (parked in
         // `queue`) are decided exactly, one per thread, while every thread brings its slots of frame
         // f into `pos`; barrier; [phase 2] the residue pairs seen in frame f-1 are folded into their
@@ -1053,7 +1141,7 @@ __global__ void __launch_bounds__(VL_THREADS, 1) vl_frames(const VlFrameParams p
             if (parked > 0) {
                 const float* prev = p.xyz + (size_t)(f - 1) * (size_t)p.n * 3;
                 for (int w = tid; w < parked; w += VL_THREADS)
-                    vl_exact_account(queue[w], prev, B, p.c2, smem, cnt32, flag_prev);
+                    vl_exact_account(queue[w], prev, B, p.c2, tile_slot_word, cnt32, flag_prev);
             }
             if (f == fb) {
                 // after the last frame: fold its flags once the parked pairs are in
@@ -1063,7 +1151,7 @@ __global__ void __launch_bounds__(VL_THREADS, 1) vl_frames(const VlFrameParams p
                 break;
             }
             if (tid == 0) misc[2 + par] = 0;
-            // ---- phase 1b: this frame's slots: unwrap next to the reference, guard ---------------
+            // ---- phase 1b: this frame's slots: unwrap next to the reference, guard, fixed point ---
             // (a frame is re-done by the fall back as a WHOLE: lists with several tiles take the
             // decision from the guard pass vl_guard, which looks at every atom of the frame; a
             // single tile holds every atom as a slot and decides here)
@@ -1071,8 +1159,6 @@ __global__ void __launch_bounds__(VL_THREADS, 1) vl_frames(const VlFrameParams p
             if (multi_tile) trip = R.frame_flag[f];
             else if (p.box != nullptr && tid < 9)
                 trip = __float_as_uint(__ldg(&p.box[f * 9 + tid])) != H.box_bits[tid];
-            // (the parked pairs above read the atom index in pos[].w while other threads rewrite
-            // their slots: a slot's index never changes, and the 16 bytes are written by one store)
 #pragma unroll
             for (int k = 0; k < VL_SPT; k++) {
                 if (s_word[k] != 0xffffffffu) {
@@ -1087,8 +1173,15 @@ __global__ void __launch_bounds__(VL_THREADS, 1) vl_frames(const VlFrameParams p
                         // (negated comparisons: NaN coordinates trip)
                         trip |= !(ex * ex + ey * ey + ez * ez <= skin2) || !(a <= a_assumed);
                     }
-                    pos[tid + k * VL_THREADS] = make_float4(__fadd_rn(x, sh.x), __fadd_rn(y, sh.y), __fadd_rn(z, sh.z),
-                                                            __int_as_float(atom));
+                    // grid coordinates relative to the tile's origin; in range for every frame the
+                    // guard admits (vl_quant_setup), clamped for the frames it does not
+                    const float gx = __fmul_rn(__fsub_rn(__fadd_rn(x, sh.x), T.ox), qscale),
+                                gy = __fmul_rn(__fsub_rn(__fadd_rn(y, sh.y), T.oy), qscale),
+                                gz = __fmul_rn(__fsub_rn(__fadd_rn(z, sh.z), T.oz), qscale);
+                    const unsigned qx = (unsigned)min(max(__float2int_rn(gx), 0), 65535),
+                                   qy = (unsigned)min(max(__float2int_rn(gy), 0), 65535),
+                                   qz = (unsigned)min(max(__float2int_rn(gz), 0), 65535);
+                    pos[tid + k * VL_THREADS] = make_uint2(qx | (qy << 16), qz);
                     if (f + 1 < fb) {           // prefetch the next frame under the pair phase
                         const float* q = p.xyz + ((size_t)(f + 1) * (size_t)p.n + (size_t)atom) * 3;
                         raw_x[k] = __ldg(q); raw_y[k] = __ldg(q + 1); raw_z[k] = __ldg(q + 2);
@@ -1117,6 +1210,7 @@ __global__ void __launch_bounds__(VL_THREADS, 1) vl_frames(const VlFrameParams p
             //      of ITS owner atom, whose position stays in registers; the entry words of the next
             //      row are requested from L2 before the current ones are worked on ------------------
             const float* frame = p.xyz + (size_t)f * (size_t)p.n * 3;
+            const unsigned flag_addr = smem_base + VL_SM_FLAG + (unsigned)par * VL_MAX_SEGS;
             int r = warp;
             uint4 cur = make_uint4(far_off, far_off, far_off, far_off);
             unsigned own = 0u;
@@ -1126,35 +1220,39 @@ __global__ void __launch_bounds__(VL_THREADS, 1) vl_frames(const VlFrameParams p
                 uint4 nxt = cur;
                 unsigned nown = own;
                 if (rn < n_rows) { nxt = __ldg(&rows4[(size_t)rn * 32 + lane]); nown = __ldg(&rown[(size_t)rn * 32 + lane]); }
-                const float4 a = *reinterpret_cast<const float4*>(smem + own);
                 const unsigned ew[4] = {cur.x, cur.y, cur.z, cur.w};
-                float4 b[4];
+                const uint2 a = vl_lds64(smem_base + own);
+                uint2 b[4];
 #pragma unroll
-                for (int q = 0; q < 4; q++) b[q] = *reinterpret_cast<const float4*>(smem + (ew[q] & 0xfff0u));
+                for (int q = 0; q < 4; q++) b[q] = vl_lds64(smem_base + (ew[q] & 0xfff8u));
+                const float ax = vl_lo16f(a.x), ay = vl_hi16f(a.x), az = vl_z23f(a.y);
                 unsigned c = 0u, amb = 0u;
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
-                    const float dx = __fsub_rn(b[q].x, a.x), dy = __fsub_rn(b[q].y, a.y), dz = __fsub_rn(b[q].z, a.z);
+                    // exact integer differences on the grid, squared distance in grid units^2
+                    const float dx = __fsub_rn(vl_lo16f(b[q].x), ax), dy = __fsub_rn(vl_hi16f(b[q].x), ay),
+                                dz = __fsub_rn(vl_z23f(b[q].y), az);
                     const float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
-                    // d2 <= c2_lo: certain contact; c2_lo < d2 < c2_hi: AMBIGUOUS, parked and decided
+                    // d2 <= c2q_lo: certain contact; c2q_lo < d2 < c2q_hi: AMBIGUOUS, parked and decided
                     // by MDTraj's arithmetic in phase 1a of the next frame
-                    const bool hit = d2 <= c2_lo;
+                    const bool hit = d2 <= c2q_lo;
                     if (hit) {
-                        flag_cur[ew[q] >> 16] = 1;       // this residue pair was seen in this frame
+                        vl_sts8(flag_addr + (ew[q] >> 16), 1u);      // this residue pair was seen in this frame
                         c += 1u << (8 * q);
                     }
-                    amb |= (d2 < c2_hi && !hit) ? (1u << q) : 0u;
-                    if ((FLAGS & VL_AUDIT) && (ew[q] & 0xfff0u) != far_off) {
+                    amb |= (d2 < c2q_hi && !hit) ? (1u << q) : 0u;
+                    if ((FLAGS & VL_AUDIT) && (ew[q] & 0xfff8u) != far_off) {
                         // audit: the exact arithmetic on EVERY listed pair; the screen's decision
                         // must agree wherever it takes one
-                        const int ia = __float_as_int(a.w), ib = __float_as_int(b[q].w);
+                        const unsigned ia = __ldg(&tile_slot_word[own / VL_SLOT_BYTES]) & 0xffffffu,
+                                       ib = __ldg(&tile_slot_word[(ew[q] & 0xfff8u) / VL_SLOT_BYTES]) & 0xffffffu;
                         const bool rev = (ew[q] & 1u) != 0u;
                         const float* pa = frame + 3 * (size_t)(rev ? ib : ia);
                         const float* pb = frame + 3 * (size_t)(rev ? ia : ib);
                         const bool exact = nl_d2_dyn(__ldg(pa), __ldg(pa + 1), __ldg(pa + 2), __ldg(pb),
                                                      __ldg(pb + 1), __ldg(pb + 2), B) <= p.c2;
                         audited++;
-                        if ((hit && !exact) || (!(d2 < c2_hi) && exact)) disagreements++;
+                        if ((hit && !exact) || (!(d2 < c2q_hi) && exact)) disagreements++;
                     }
                 }
                 if (c) cnt32[r * 32 + lane] += c;        // the entry's byte counters belong to this thread
@@ -1167,7 +1265,7 @@ __global__ void __launch_bounds__(VL_THREADS, 1) vl_frames(const VlFrameParams p
                                                        (unsigned)(r * VL_ROW + lane * 4 + q) | ((ew[q] >> 16) << 17));
                             const int w = vl_atoms_add(&misc[2 + par], 1);
                             if (w < VL_QCAP) queue[w] = e;
-                            else vl_exact_account(e, frame, B, p.c2, smem, cnt32, flag_cur);
+                            else vl_exact_account(e, frame, B, p.c2, tile_slot_word, cnt32, flag_cur);
                         }
                     }
                 }
@@ -1185,12 +1283,12 @@ __global__ void __launch_bounds__(VL_THREADS, 1) vl_frames(const VlFrameParams p
                 if (c == 0u) continue;
                 const uint4 e4 = rows4[w];
                 const unsigned ew[4] = {e4.x, e4.y, e4.z, e4.w};
-                const unsigned ia = L.slot_word[T.slot0 + ((unsigned)rown[w] >> 4)] & 0xffffffu;
+                const unsigned ia = tile_slot_word[(unsigned)rown[w] / VL_SLOT_BYTES] & 0xffffffu;
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     const unsigned cq = (c >> (8 * q)) & 0xffu;
                     if (cq) {
-                        const unsigned ib = L.slot_word[T.slot0 + ((ew[q] & 0xfff0u) >> 4)] & 0xffffffu;
+                        const unsigned ib = tile_slot_word[(ew[q] & 0xfff8u) / VL_SLOT_BYTES] & 0xffffffu;
                         const unsigned lo = min(ia, ib), hi = max(ia, ib);
                         atomicAdd(&p.atom_table[(size_t)lo * (size_t)p.n + (size_t)hi], cq);
                     }
@@ -1332,6 +1430,7 @@ inline int vl_ensure(VlScratch& S, int n, int n_res_c, std::string& err)
         VL_CK(cudaMalloc(&S.L.slot_word, sizeof(unsigned) * (size_t)S.L.slot_cap));
         VL_CK(cudaMalloc(&S.L.slot_ref, sizeof(float4) * (size_t)S.L.slot_cap));
         VL_CK(cudaMalloc(&S.L.row_owner, sizeof(unsigned short) * (size_t)S.L.row_cap * 32));
+        VL_CK(cudaMalloc(&S.L.tile_bb, sizeof(unsigned) * VL_MAX_TILES * 6));
         VL_CK(cudaMalloc(&S.L.entries, sizeof(unsigned) * (size_t)S.L.row_cap * VL_ROW));
         VL_CK(cudaMalloc(&S.L.seg_pair, sizeof(uint2) * (size_t)E));
         VL_CK(cudaMalloc(&S.ref_raw, sizeof(float4) * (size_t)n));
@@ -1450,13 +1549,16 @@ inline int vl_build(const VlJob& job, VlScratch& S, cudaStream_t st, std::string
     VL_CK(cub::DeviceSelect::Unique(S.cub_tmp, tb, S.slot_key[1], S.slot_uniq, S.n_runs + 1, (int)n_keys, st));
     vl_slot_ranges<<<(VL_MAX_TILES + 1 + 255) / 256, 256, 0, st>>>(S.L.hdr, S.L.tiles, S.slot_uniq, S.n_runs, S.tile_slot0,
                                                                    S.L.slot_cap);
-    vl_slot_fill<<<(unsigned)((S.L.slot_cap + 255) / 256), 256, 0, st>>>(S.L.hdr, S.slot_uniq, S.ref_w, S.L.slot_word,
-                                                                         S.L.slot_ref, S.L.slot_cap);
+    vl_bb_init<<<(VL_MAX_TILES * 6 + 255) / 256, 256, 0, st>>>(S.L.tile_bb);
+    vl_slot_fill<<<(unsigned)((S.L.slot_cap + 255) / 256), 256, 0, st>>>(S.L.hdr, S.slot_uniq, S.ref_w, S.tile_slot0,
+                                                                         S.L.slot_word, S.L.slot_ref, S.L.tile_bb,
+                                                                         S.L.slot_cap);
+    vl_quant_setup<<<1, 1024, 0, st>>>(S.L.hdr, S.L.tiles, S.L.tile_bb, job.cutoff);
     vl_fill<<<(unsigned)S.L.row_cap, VL_ROW, 0, st>>>(S.L.hdr, S.L.tiles, S.tile_bundle0, S.bundle_row0, S.sval[1],
                                                       S.list_len, S.list_start, S.list_key, S.own_val, S.slot_uniq,
                                                       S.tile_slot0, S.L.row_owner, S.L.entries);
     VL_CK(cudaGetLastError());
-    launches += 30;
+    launches += 32;
     return 0;
 }
 
