@@ -96,6 +96,7 @@ struct cmb_ctx {
     float* h_pinned[2] = {nullptr, nullptr};      // gather staging (cmb_accumulate_host_gather)
     size_t pinned_bytes = 0;
     cudaEvent_t copy_done[2] = {nullptr, nullptr};
+    cudaEvent_t box_ready = nullptr;              // the one copy of all unit cells has landed
     cudaStream_t streams[2] = {nullptr, nullptr};
 
     // sort / min-dist scratch
@@ -116,7 +117,31 @@ struct cmb_ctx {
     long long ovf_cap = 0;
     int last_slot = 0;
     std::map<std::string, int64_t> stats;
+
+    // measurement (option time_kernels): CUDA events around every launch of the pair-list frame kernel, on
+    // the stream it is launched on; the stats vl_frames_ns / vl_frames_timed read and reset them
+    int time_kernels = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kernel_events;
+    size_t kernel_events_used = 0;
+    // host pipeline trace (option stage_trace): events after the copy and after the kernels of every chunk
+    int stage_trace = 0;
+    cudaEvent_t trace_begin = nullptr;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> trace_events;
+    size_t trace_used = 0;
 };
+
+// a recycled pair of timing events
+static int timing_pair(std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& pool, size_t& used, cudaEvent_t* a, cudaEvent_t* b)
+{
+    if (used == pool.size()) {
+        cudaEvent_t x = nullptr, y = nullptr;
+        if (cudaEventCreate(&x) != cudaSuccess || cudaEventCreate(&y) != cudaSuccess) return -1;
+        pool.push_back({x, y});
+    }
+    *a = pool[used].first; *b = pool[used].second;
+    used++;
+    return 0;
+}
 
 static std::string g_create_err;
 
@@ -217,6 +242,10 @@ extern "C" void cmb_ctx_destroy(cmb_ctx* ctx)
         for (int t = 0; t < 2; t++)
             if (ctx->vl_walked[s][t]) cudaEventDestroy(ctx->vl_walked[s][t]);
     }
+    for (auto& e : ctx->kernel_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    for (auto& e : ctx->trace_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    if (ctx->trace_begin) cudaEventDestroy(ctx->trace_begin);
+    if (ctx->box_ready) cudaEventDestroy(ctx->box_ready);
     pg_free(ctx->pg);
     cudaFree(ctx->d_res_anchor);
     cudaFree(ctx->d_vl_audit);
@@ -253,6 +282,8 @@ extern "C" int cmb_set_option(cmb_ctx* ctx, const char* name, int64_t value)
         return CMB_OK;
     }
     if (!strcmp(name, "verlet_audit")) { ctx->verlet_audit = value != 0; return CMB_OK; }
+    if (!strcmp(name, "time_kernels")) { ctx->time_kernels = value != 0; ctx->kernel_events_used = 0; return CMB_OK; }
+    if (!strcmp(name, "stage_trace")) { ctx->stage_trace = value != 0; ctx->trace_used = 0; return CMB_OK; }
     if (!strcmp(name, "prune")) { ctx->prune = value != 0; return CMB_OK; }
     if (!strcmp(name, "verlet_conservative_tiles")) { ctx->vl_conservative = value != 0; return CMB_OK; }
     if (!strcmp(name, "verlet_max_rlist_pct")) {
@@ -280,6 +311,37 @@ extern "C" int cmb_get_stat(cmb_ctx* ctx, const char* name, int64_t* value)
     if (!strcmp(name, "max_cells")) { *value = ctx->fs_maxc; return CMB_OK; }
     if (!strcmp(name, "kernel_launches")) { *value = ctx->stats["kernel_launches"]; return CMB_OK; }
     if (!strcmp(name, "vl_used")) { *value = ctx->last_used_verlet; return CMB_OK; }
+    if (!strcmp(name, "vl_frames_timed")) { *value = (int64_t)ctx->kernel_events_used; return CMB_OK; }
+    if (!strcmp(name, "vl_frames_ns")) {
+        // total duration of the frame-kernel launches timed since the last read (synchronises, resets)
+        CK(cudaSetDevice(ctx->device));
+        CK(cudaDeviceSynchronize());
+        double ms = 0.0;
+        for (size_t k = 0; k < ctx->kernel_events_used; k++) {
+            float t = 0.f;
+            CK(cudaEventElapsedTime(&t, ctx->kernel_events[k].first, ctx->kernel_events[k].second));
+            ms += t;
+        }
+        ctx->kernel_events_used = 0;
+        *value = (int64_t)(ms * 1.0e6);
+        return CMB_OK;
+    }
+    if (!strncmp(name, "trace_", 6)) {
+        // host pipeline trace of the last streamed call: trace_chunks, trace_copy_<c>, trace_done_<c>
+        // (ns after the first copy was issued)
+        if (!strcmp(name, "trace_chunks")) { *value = (int64_t)ctx->trace_used; return CMB_OK; }
+        const bool copy = !strncmp(name, "trace_copy_", 11);
+        const bool done = !strncmp(name, "trace_done_", 11);
+        if (!copy && !done) return fail(ctx, CMB_ERR_ARG, "unknown stat %s", name);
+        const size_t c = (size_t)atoll(name + 11);
+        if (c >= ctx->trace_used || !ctx->trace_begin) return fail(ctx, CMB_ERR_ARG, "no trace for chunk %zu", c);
+        CK(cudaSetDevice(ctx->device));
+        CK(cudaDeviceSynchronize());
+        float t = 0.f;
+        CK(cudaEventElapsedTime(&t, ctx->trace_begin, copy ? ctx->trace_events[c].first : ctx->trace_events[c].second));
+        *value = (int64_t)((double)t * 1.0e6);
+        return CMB_OK;
+    }
     if (!strcmp(name, "pruned_frames")) { *value = ctx->stats["pruned_frames"]; return CMB_OK; }
     if (!strcmp(name, "brute_frames")) { *value = ctx->stats["brute_frames"]; return CMB_OK; }
     if (!strcmp(name, "vl_rebuilds")) { *value = ctx->stats["vl_rebuilds"]; return CMB_OK; }
@@ -630,6 +692,8 @@ static int launch_frames(cmb_ctx* ctx, const FrameJob& job, int slot, cudaStream
             vj.n_ignored = ctx->n_ignored; vj.atom_table = job.atom_table; vj.res_table = job.res_table;
             vj.audit = ctx->verlet_audit; vj.d_audit = ctx->d_vl_audit;
             vj.max_rlist_factor = 0.01f * (float)ctx->verlet_max_rlist_pct;
+            if (ctx->time_kernels && timing_pair(ctx->kernel_events, ctx->kernel_events_used, &vj.t_begin, &vj.t_end) != 0)
+                return fail(ctx, CMB_ERR_CUDA, "cudaEventCreate failed");
             if (build) {
                 // earlier walks of the list this scratch held must be over before it is overwritten
                 for (int t = 0; t < 2; t++)
@@ -770,10 +834,11 @@ extern "C" int cmb_accumulate(cmb_ctx* ctx, const float* d_xyz, const float* d_b
     return launch_frames(ctx, job, ctx->slot, (cudaStream_t)stream);
 }
 
-static int64_t pick_chunk(const cmb_ctx* ctx, int64_t n_frames, int64_t chunk_frames)
+static int64_t pick_chunk(const cmb_ctx* ctx, int64_t n_frames, int64_t chunk_frames, bool* automatic = nullptr)
 {
     const size_t frame_bytes = (size_t)ctx->n * 12;
     if (chunk_frames <= 0 && ctx->stage_chunk_frames > 0) chunk_frames = ctx->stage_chunk_frames;
+    if (automatic) *automatic = chunk_frames <= 0;
     if (chunk_frames <= 0) {
         chunk_frames = (int64_t)((80ull << 20) / frame_bytes);
         // at least four chunks so copies and kernels overlap, but keep every SM busy
@@ -787,10 +852,39 @@ static int64_t pick_chunk(const cmb_ctx* ctx, int64_t n_frames, int64_t chunk_fr
     return chunk_frames;
 }
 
-static int ensure_staging(cmb_ctx* ctx, int64_t chunk_frames, bool with_box)
+// Chunk lengths of a streamed trajectory.  The copies run back to back on the copy engine, which makes
+// two places of the schedule matter when the chunk size is chosen automatically:
+//   head: the pair list is built from the first chunk, by ~30 small dependent launches whose launch
+//         latency grows several-fold while a copy saturates the link; the copy of chunk 2 has to wait
+//         for the kernels of chunk 0 (same staging buffer), so the first chunk is a short one -- the
+//         build then hides under the copy of chunk 1;
+//   tail: the call ends one chunk's worth of kernels after the LAST copy, so the final chunk is split
+//         and only a quarter of it (but enough frames to occupy every SM) is left for that tail.
+static std::vector<int64_t> chunk_schedule(const cmb_ctx* ctx, int64_t n_frames, int64_t chunk_frames, bool automatic)
+{
+    std::vector<int64_t> sizes;
+    const int64_t fill = (int64_t)ctx->sm_count * std::max(1, ctx->fs_ctas_per_sm) * 2;
+    int64_t f0 = 0;
+    if (automatic && n_frames >= 3 * chunk_frames) {
+        const int64_t head = std::max<int64_t>(fill, chunk_frames / 4);
+        if (chunk_frames >= 2 * head) { sizes.push_back(head); f0 = head; }
+    }
+    for (; f0 < n_frames; f0 += chunk_frames) sizes.push_back(std::min<int64_t>(chunk_frames, n_frames - f0));
+    if (automatic && sizes.size() >= 2) {
+        const int64_t last = sizes.back();
+        const int64_t tail = std::max<int64_t>(fill, last / 4);
+        if (last >= 2 * tail) {
+            sizes.back() = last - tail;
+            sizes.push_back(tail);
+        }
+    }
+    return sizes;
+}
+
+static int ensure_staging(cmb_ctx* ctx, int64_t chunk_frames, bool with_box, int64_t box_frames)
 {
     const size_t need_xyz = (size_t)chunk_frames * (size_t)ctx->n * 12;
-    const size_t need_box = (size_t)chunk_frames * 36;
+    const size_t need_box = (size_t)box_frames * 36;
     if (ctx->stage_xyz_bytes < need_xyz) {
         for (int s = 0; s < 2; s++) {
             if (ctx->d_stage_xyz[s]) CK(cudaFree(ctx->d_stage_xyz[s]));
@@ -870,8 +964,13 @@ static int stream_host_frames(cmb_ctx* ctx, const float* h_xyz_full, int n_total
         if (n_threads < 1) n_threads = 1;
     }
     const size_t frame_bytes = (size_t)ctx->n * 12;
-    chunk_frames = pick_chunk(ctx, n_frames, chunk_frames);
-    int rc0 = ensure_staging(ctx, chunk_frames, h_box != nullptr);
+    bool automatic = false;
+    chunk_frames = pick_chunk(ctx, n_frames, chunk_frames, &automatic);
+    const std::vector<int64_t> schedule = chunk_schedule(ctx, n_frames, chunk_frames, automatic);
+    // the unit cells of ALL frames go over in one copy ahead of the first chunk (a small copy per chunk
+    // costs the copy engine ~20 us each while the link is saturated)
+    const bool box_once = h_box != nullptr && (size_t)n_frames * 36 <= ((size_t)256 << 20);
+    int rc0 = ensure_staging(ctx, chunk_frames, h_box != nullptr, box_once ? n_frames : chunk_frames);
     if (rc0 != CMB_OK) return rc0;
     // the chunks share ONE pair list, built from the first chunk (cmb_verlet.cuh: the guard decides
     // frame by frame whether the list still covers a frame, whichever batch it was built from)
@@ -891,10 +990,21 @@ static int stream_host_frames(cmb_ctx* ctx, const float* h_xyz_full, int n_total
         for (int s = 0; s < 2; s++)
             if (!ctx->copy_done[s]) CK(cudaEventCreateWithFlags(&ctx->copy_done[s], cudaEventDisableTiming));
     }
+    if (box_once) {
+        if (!ctx->box_ready) CK(cudaEventCreateWithFlags(&ctx->box_ready, cudaEventDisableTiming));
+        CK(cudaMemcpyAsync(ctx->d_stage_box[0], h_box, (size_t)n_frames * 36, cudaMemcpyHostToDevice, ctx->streams[0]));
+        CK(cudaEventRecord(ctx->box_ready, ctx->streams[0]));
+        CK(cudaStreamWaitEvent(ctx->streams[1], ctx->box_ready, 0));
+    }
     int c = 0;
-    for (int64_t f0 = 0; f0 < n_frames; f0 += chunk_frames, c++) {
+    if (ctx->stage_trace) {
+        ctx->trace_used = 0;
+        if (!ctx->trace_begin) CK(cudaEventCreate(&ctx->trace_begin));
+        CK(cudaEventRecord(ctx->trace_begin, ctx->streams[0]));
+    }
+    for (int64_t f0 = 0; f0 < n_frames; f0 += schedule[c], c++) {
         const int s = c & 1;
-        const int64_t nf = std::min<int64_t>(chunk_frames, n_frames - f0);
+        const int64_t nf = schedule[c];
         const float* src = h_xyz_full + (size_t)f0 * (size_t)ctx->n * 3;
         {   // the frames chunk c - 2 left to the cell kernels still sit in staging buffer s
             int rc = finish_pending(ctx, s);
@@ -908,15 +1018,23 @@ static int stream_host_frames(cmb_ctx* ctx, const float* h_xyz_full, int n_total
         // stream order on streams[s] serialises reuse of staging buffer s
         CK(cudaMemcpyAsync(ctx->d_stage_xyz[s], src, (size_t)nf * frame_bytes, cudaMemcpyHostToDevice, ctx->streams[s]));
         if (!direct) CK(cudaEventRecord(ctx->copy_done[s], ctx->streams[s]));
-        if (h_box)
+        if (h_box && !box_once)
             CK(cudaMemcpyAsync(ctx->d_stage_box[s], h_box + (size_t)f0 * 9, (size_t)nf * 36,
                                cudaMemcpyHostToDevice, ctx->streams[s]));
+        cudaEvent_t t_copy = nullptr, t_done = nullptr;
+        if (ctx->stage_trace) {
+            if (timing_pair(ctx->trace_events, ctx->trace_used, &t_copy, &t_done) != 0)
+                return fail(ctx, CMB_ERR_CUDA, "cudaEventCreate failed");
+            CK(cudaEventRecord(t_copy, ctx->streams[s]));
+        }
         FrameJob job = proto;
-        job.xyz = ctx->d_stage_xyz[s]; job.box = h_box ? ctx->d_stage_box[s] : nullptr;
+        job.xyz = ctx->d_stage_xyz[s];
+        job.box = !h_box ? nullptr : box_once ? ctx->d_stage_box[0] + (size_t)f0 * 9 : ctx->d_stage_box[s];
         job.n_frames = nf; job.frame0 = proto.frame0 + f0;
         job.shared_list = 1;
         int rc = launch_frames(ctx, job, s, ctx->streams[s], true);
         if (rc != CMB_OK) return rc;
+        if (t_done) CK(cudaEventRecord(t_done, ctx->streams[s]));
     }
     for (int s = 0; s < 2; s++) {
         int rc = finish_pending(ctx, s);

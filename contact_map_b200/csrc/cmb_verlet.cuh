@@ -170,7 +170,10 @@ struct VlScratch {
     int* bundle_row0 = nullptr;     // [bundle_cap + 1]
     long long bundle_cap = 0;
     void* cub_tmp = nullptr;
+    void* cub_tmp2 = nullptr;       // temp storage of the slot chain, which runs beside the owner-list chain
     size_t cub_bytes = 0;
+    cudaStream_t aux = nullptr;     // the builder's second stream (vl_build: fork after sort 1, join before vl_fill)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 inline void vl_free(VlScratch& S)
@@ -187,7 +190,10 @@ inline void vl_free(VlScratch& S)
     }
     cudaFree(S.seg_key); cudaFree(S.seg_len); cudaFree(S.seg_start); cudaFree(S.n_runs); cudaFree(S.slot_uniq);
     cudaFree(S.tile_seg0); cudaFree(S.tile_bundle0); cudaFree(S.tile_slot0); cudaFree(S.bundle_row0);
-    cudaFree(S.cub_tmp);
+    cudaFree(S.cub_tmp); cudaFree(S.cub_tmp2);
+    if (S.aux) cudaStreamDestroy(S.aux);
+    if (S.ev_fork) cudaEventDestroy(S.ev_fork);
+    if (S.ev_join) cudaEventDestroy(S.ev_join);
     S = VlScratch();
 }
 
@@ -793,7 +799,7 @@ __global__ void __launch_bounds__(1024) vl_layout(VlHeader* hdr, VlTile* __restr
         const int rows = bundle_row0[b1] - bundle_row0[b0];
         tiles[t].list0 = tile_seg0[t]; tiles[t].n_lists = tile_seg0[t + 1] - tile_seg0[t];
         tiles[t].row0 = bundle_row0[b0]; tiles[t].n_rows = rows;
-        tiles[t].slot0 = 0; tiles[t].n_slots = 0;
+        // (slot0 / n_slots belong to vl_slot_ranges, which runs beside this kernel on the builder's second stream)
         if (rows > VL_MAX_ROWS) { hdr->valid = 0; hdr->fail_code = 11; }
     }
 }
@@ -1077,7 +1083,12 @@ __global__ void __launch_bounds__(VL_THREADS, 1) vl_frames(const VlFrameParams p
     // to amortise the tile set-up / flush and short enough for the byte counters
     long long n_chunks = max(((long long)p.rounds * gridDim.x + n_tiles - 1) / n_tiles,
                              (p.n_frames + VL_ITEM_FRAMES - 1) / VL_ITEM_FRAMES);
-    n_chunks = max(1ll, min(n_chunks, (p.n_frames + VL_MIN_ITEM_FRAMES - 1) / VL_MIN_ITEM_FRAMES));
+    // (a batch too short to give every CTA an item of VL_MIN_ITEM_FRAMES frames -- the tail chunk of a
+    // streamed trajectory -- is cut finer: its latency matters, not its efficiency)
+    long long max_chunks = (p.n_frames + VL_MIN_ITEM_FRAMES - 1) / VL_MIN_ITEM_FRAMES;
+    if (max_chunks * n_tiles < gridDim.x)
+        max_chunks = max(max_chunks, min((long long)gridDim.x / n_tiles, (p.n_frames + 2) / 3));
+    n_chunks = max(1ll, min(n_chunks, max_chunks));
     const long long item_frames = (p.n_frames + n_chunks - 1) / n_chunks;
     n_chunks = (p.n_frames + item_frames - 1) / item_frames;
     const long long n_items = n_chunks * n_tiles;
@@ -1382,6 +1393,7 @@ struct VlJob {
     int audit; unsigned long long* d_audit;
     float max_rlist_factor;      // lists with r_list > factor * cutoff are not built (all frames fall back)
     int conservative_tiles;      // 1: tile size from the pessimistic slot estimate (vl_setup)
+    cudaEvent_t t_begin = nullptr, t_end = nullptr;   // recorded around the frame kernel when set (option time_kernels)
 };
 
 #define VL_CK(call)                                                                  \
@@ -1479,7 +1491,11 @@ inline int vl_ensure(VlScratch& S, int n, int n_res_c, std::string& err)
         cub::DeviceScan::ExclusiveSum(nullptr, t, S.seg_len, S.seg_start, (int)E);
         need = std::max(need, t);
         VL_CK(cudaMalloc(&S.cub_tmp, need + 256));
+        VL_CK(cudaMalloc(&S.cub_tmp2, need + 256));
         S.cub_bytes = need + 256;
+        VL_CK(cudaStreamCreateWithFlags(&S.aux, cudaStreamNonBlocking));
+        VL_CK(cudaEventCreateWithFlags(&S.ev_fork, cudaEventDisableTiming));
+        VL_CK(cudaEventCreateWithFlags(&S.ev_join, cudaEventDisableTiming));
         S.cap_atoms = n;
     }
     return 0;
@@ -1508,13 +1524,38 @@ inline int vl_build(const VlJob& job, VlScratch& S, cudaStream_t st, std::string
     vl_pairs<<<(n + 7) / 8, 256, 0, st>>>(S.L.hdr, n, job.n_ignored, S.sref, S.smeta, S.scell, S.cellptr, S.tile_of_res,
                                           S.rec_key[0], S.rec_val[0], E);
     vl_after_pairs<<<1, 1, 0, st>>>(S.L.hdr, E);
+    VL_CK(cudaMemsetAsync(S.seg_len, 0, 4 * (size_t)E, st));
+    VL_CK(cudaMemsetAsync(S.list_len, 0, 4 * (size_t)E, st));
+    VL_CK(cudaMemsetAsync(S.n_runs, 0, 12, st));
     // sort 1: by tile and residue pair -> segments (the residue pairs of every tile)
     size_t tb = S.cub_bytes;
     VL_CK(cub::DeviceRadixSort::SortPairs(S.cub_tmp, tb, S.rec_key[0], S.rec_key[1], S.rec_val[0], S.rec_val[1], (int)E, 0,
                                           2 * rbits + tbits, st));
-    VL_CK(cudaMemsetAsync(S.seg_len, 0, 4 * (size_t)E, st));
-    VL_CK(cudaMemsetAsync(S.list_len, 0, 4 * (size_t)E, st));
-    VL_CK(cudaMemsetAsync(S.n_runs, 0, 12, st));
+    // From the sorted records two independent chains of small dependent launches follow; they run
+    // side by side (the builder is launch-latency bound):
+    //   aux:  the SLOTS of every tile (atoms and their periodic images): keys, sort, unique, ranges,
+    //         reference positions, fixed-point grid;
+    //   main: segments, owner lists, bundles, row layout.
+    VL_CK(cudaEventRecord(S.ev_fork, st));
+    VL_CK(cudaStreamWaitEvent(S.aux, S.ev_fork, 0));
+    {
+        cudaStream_t sa = S.aux;
+        const long long n_keys = 2 * E + n;
+        vl_slot_keys<<<(unsigned)((std::max<long long>(E, n) + 255) / 256), 256, 0, sa>>>(S.L.hdr, S.rec_key[1], S.rec_val[1],
+                                                                                          S.slot_key[0], E, n);
+        size_t tb2 = S.cub_bytes;
+        VL_CK(cub::DeviceRadixSort::SortKeys(S.cub_tmp2, tb2, S.slot_key[0], S.slot_key[1], (int)n_keys, 0, abits + 5 + tbits, sa));
+        tb2 = S.cub_bytes;
+        VL_CK(cub::DeviceSelect::Unique(S.cub_tmp2, tb2, S.slot_key[1], S.slot_uniq, S.n_runs + 1, (int)n_keys, sa));
+        vl_slot_ranges<<<(VL_MAX_TILES + 1 + 255) / 256, 256, 0, sa>>>(S.L.hdr, S.L.tiles, S.slot_uniq, S.n_runs, S.tile_slot0,
+                                                                       S.L.slot_cap);
+        vl_bb_init<<<(VL_MAX_TILES * 6 + 255) / 256, 256, 0, sa>>>(S.L.tile_bb);
+        vl_slot_fill<<<(unsigned)((S.L.slot_cap + 255) / 256), 256, 0, sa>>>(S.L.hdr, S.slot_uniq, S.ref_w, S.tile_slot0,
+                                                                             S.L.slot_word, S.L.slot_ref, S.L.tile_bb,
+                                                                             S.L.slot_cap);
+        vl_quant_setup<<<1, 1024, 0, sa>>>(S.L.hdr, S.L.tiles, S.L.tile_bb, job.cutoff);
+        VL_CK(cudaEventRecord(S.ev_join, sa));
+    }
     tb = S.cub_bytes;
     VL_CK(cub::DeviceRunLengthEncode::Encode(S.cub_tmp, tb, S.rec_key[1], S.seg_key, S.seg_len, S.n_runs, (int)E, st));
     vl_after_rle<<<1, 1, 0, st>>>(S.L.hdr, S.seg_key, S.n_runs, 0);
@@ -1540,20 +1581,7 @@ inline int vl_build(const VlJob& job, VlScratch& S, cudaStream_t st, std::string
                                           VL_LEN_BITS + tbits, st));
     vl_layout<<<1, 1024, 0, st>>>(S.L.hdr, S.L.tiles, S.skey[1], S.sval[1], S.list_len, S.tile_list0, S.tile_bundle0,
                                   S.bundle_row0, S.bundle_cap, S.L.row_cap);
-    const long long n_keys = 2 * E + n;
-    vl_slot_keys<<<(unsigned)((std::max<long long>(E, n) + 255) / 256), 256, 0, st>>>(S.L.hdr, S.rec_key[1], S.rec_val[1],
-                                                                                      S.slot_key[0], E, n);
-    tb = S.cub_bytes;
-    VL_CK(cub::DeviceRadixSort::SortKeys(S.cub_tmp, tb, S.slot_key[0], S.slot_key[1], (int)n_keys, 0, abits + 5 + tbits, st));
-    tb = S.cub_bytes;
-    VL_CK(cub::DeviceSelect::Unique(S.cub_tmp, tb, S.slot_key[1], S.slot_uniq, S.n_runs + 1, (int)n_keys, st));
-    vl_slot_ranges<<<(VL_MAX_TILES + 1 + 255) / 256, 256, 0, st>>>(S.L.hdr, S.L.tiles, S.slot_uniq, S.n_runs, S.tile_slot0,
-                                                                   S.L.slot_cap);
-    vl_bb_init<<<(VL_MAX_TILES * 6 + 255) / 256, 256, 0, st>>>(S.L.tile_bb);
-    vl_slot_fill<<<(unsigned)((S.L.slot_cap + 255) / 256), 256, 0, st>>>(S.L.hdr, S.slot_uniq, S.ref_w, S.tile_slot0,
-                                                                         S.L.slot_word, S.L.slot_ref, S.L.tile_bb,
-                                                                         S.L.slot_cap);
-    vl_quant_setup<<<1, 1024, 0, st>>>(S.L.hdr, S.L.tiles, S.L.tile_bb, job.cutoff);
+    VL_CK(cudaStreamWaitEvent(st, S.ev_join, 0));
     vl_fill<<<(unsigned)S.L.row_cap, VL_ROW, 0, st>>>(S.L.hdr, S.L.tiles, S.tile_bundle0, S.bundle_row0, S.sval[1],
                                                       S.list_len, S.list_start, S.list_key, S.own_val, S.slot_uniq,
                                                       S.tile_slot0, S.L.row_owner, S.L.entries);
@@ -1592,9 +1620,11 @@ inline int vl_run_frames(const VlJob& job, const VlList& L, const VlRun& R, int 
     p.xyz = job.xyz; p.box = job.box; p.n_frames = job.n_frames; p.n = job.n; p.n_res_c = job.n_res_c; p.c2 = job.c2;
     p.rounds = job.n <= VL_SINGLE_TILE_ATOMS ? 4 : 6;
     p.atom_table = job.atom_table; p.res_table = job.res_table; p.audit = job.d_audit;
+    if (job.t_begin) VL_CK(cudaEventRecord(job.t_begin, st));
     if (job.audit) vl_frames<VL_AUDIT><<<sm_count, VL_THREADS, VL_SM_TOTAL, st>>>(p, L, R);
     else vl_frames<0><<<sm_count, VL_THREADS, VL_SM_TOTAL, st>>>(p, L, R);
     VL_CK(cudaGetLastError());
+    if (job.t_end) VL_CK(cudaEventRecord(job.t_end, st));
     launches += 2;
     return 0;
 }
