@@ -229,6 +229,22 @@ __device__ __forceinline__ void vl_unwrap(const double* hinv, const double* h, i
     oz = (float)((double)pz - (n0 * h[2] + n1 * h[5] + n2 * h[8]));
 }
 
+// The same for a cell whose vectors lie along the axes, in fp32: n = rint((p - r) / L) needs no more
+// than that -- whenever the result passes the guard, (p - r) / L lies within skin / L << 1/2 of the
+// integer both precisions round it to -- and fma(-n, L, p) is the exact p - n L rounded once, which is
+// what the fp64 version computes (L is a float, n L and the difference are exact in fp64).  A frame
+// for which the two could differ fails the guard in both and is re-done by the fall back.
+__device__ __forceinline__ void vl_unwrap_ortho(const float* hf, float px, float py, float pz, float rx, float ry,
+                                                float rz, float& ox, float& oy, float& oz)
+{
+    const float n0 = rintf(__fmul_rn(__fsub_rn(px, rx), hf[0]));
+    const float n1 = rintf(__fmul_rn(__fsub_rn(py, ry), hf[1]));
+    const float n2 = rintf(__fmul_rn(__fsub_rn(pz, rz), hf[2]));
+    ox = __fmaf_rn(-n0, hf[3], px);
+    oy = __fmaf_rn(-n1, hf[4], py);
+    oz = __fmaf_rn(-n2, hf[5], pz);
+}
+
 __device__ __forceinline__ void vl_box_inverse(const float* box9, double* h, double* m)
 {
     for (int k = 0; k < 9; k++) h[k] = (double)box9[k];
@@ -979,7 +995,86 @@ __global__ void __launch_bounds__(VL_ROW) vl_fill(const VlHeader* hdr, const VlT
             word = (sj * VL_SLOT_BYTES) | (unsigned)((v >> 25) & 1ull) | ((unsigned)(v >> 26) << 16);
         }
     }
-    entries[(size_t)R * VL_ROW + threadIdx.x] = word;
+    // Bank balancing.  In step q of the row the 32 lanes gather 32 unrelated 8-byte slots: a half
+    // warp that draws its 16 bank pairs at random needs ~3.1 shared-memory wavefronts where 1 would
+    // do.  The ORDER of the four partners inside a lane's quadruple is free, so lane after lane the
+    // permutation is taken that puts its partners where the half warp has loaded the bank pairs of
+    // the steps least so far (greedy, 24 candidates evaluated by 24 threads): ~2.1 wavefronts.
+    // The lanes of a ROW are free as well (every row carries its own owner slots): the owners are
+    // dealt to the two half warps so that each sees every bank pair as rarely as possible.
+    __shared__ unsigned w_s[VL_ROW];
+    __shared__ unsigned char occ[2][4][16];
+    __shared__ unsigned short own_s[32];
+    __shared__ unsigned char place[32];            // lane of the row -> lane it was computed as
+    if ((threadIdx.x & 3) == 0) own_s[lane] = (unsigned short)owner;
+    (&occ[0][0][0])[threadIdx.x] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned char seen[16];
+        int fill[2] = {0, 0};
+        for (int b = 0; b < 16; b++) seen[b] = 0;
+        for (int l = 0; l < 32; l++) {
+            const int b = (own_s[l] >> 3) & 15;
+            int h = seen[b]++ & 1;                 // members of one bank pair alternate between the halves
+            if (fill[h] == 16) h ^= 1;
+            place[16 * h + fill[h]++] = (unsigned char)l;
+        }
+    }
+    __syncthreads();
+    w_s[threadIdx.x] = word;
+    __syncthreads();
+    word = w_s[4 * place[lane] + (threadIdx.x & 3)];
+    owner = own_s[place[lane]];
+    __syncthreads();
+    w_s[threadIdx.x] = word;
+    __syncthreads();
+    const int hw = threadIdx.x >> 5, ln = threadIdx.x & 31;
+    if (hw < 2) {
+        // permutation ln of (0, 1, 2, 3) in the factorial number system
+        int perm[4] = {0, 1, 2, 3};
+        if (ln < 24) {
+            int pool[4] = {0, 1, 2, 3};
+            int code = ln;
+            const int a = code / 6; code -= 6 * a;
+            const int b = code / 2, c = code - 2 * b;
+            perm[0] = pool[a];
+            for (int k = a; k < 3; k++) pool[k] = pool[k + 1];
+            perm[1] = pool[b];
+            for (int k = b; k < 2; k++) pool[k] = pool[k + 1];
+            perm[2] = pool[c];
+            perm[3] = pool[1 - c];
+        }
+        for (int i = 0; i < 16; i++) {
+            const int L = 16 * hw + i;
+            unsigned e[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) e[q] = w_s[4 * L + q];
+            unsigned cost = 0xffffu;
+            if (ln < 24) {
+                cost = 0u;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const unsigned off = e[perm[q]] & 0xfff8u;
+                    if (off != far_off) cost += occ[hw][q][(off >> 3) & 15u];
+                }
+            }
+            unsigned key = (cost << 5) | (unsigned)ln;
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, d));
+            __syncwarp();
+            if (ln == (int)(key & 31u)) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const unsigned v = e[perm[q]];
+                    w_s[4 * L + q] = v;
+                    if ((v & 0xfff8u) != far_off) occ[hw][q][((v & 0xfff8u) >> 3) & 15u]++;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    entries[(size_t)R * VL_ROW + threadIdx.x] = w_s[threadIdx.x];
     if ((threadIdx.x & 3) == 0) row_owner[(size_t)R * 32 + lane] = (unsigned short)owner;
 }
 
@@ -1069,13 +1164,18 @@ __global__ void __launch_bounds__(VL_THREADS, 1) vl_frames(const VlFrameParams p
     float4* shift_s = reinterpret_cast<float4*>(smem + VL_SM_HDR + 18 * 8);
     // [0] item, [2 + parity] parked pairs of the frame with that parity
     int* misc = reinterpret_cast<int*>(smem + VL_SM_HDR + 18 * 8 + 27 * 16);
+    float* hf = reinterpret_cast<float*>(smem + VL_SM_HDR + 18 * 8 + 27 * 16 + 32);   // 1 / L[3], L[3] of an axis-aligned cell
     const VlHeader& H = *L.hdr;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (!H.valid) return;                       // every frame is on the fall-back list (vl_all_tripped)
     const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem);
     if (tid < 18) hs[tid] = tid < 9 ? H.hinv[tid] : H.h[tid - 9];
     if (tid >= 32 && tid < 32 + 27) shift_s[tid - 32] = H.shift[tid - 32];
+    if (tid >= 64 && tid < 64 + 3) { hf[tid - 64] = (float)H.hinv[4 * (tid - 64)]; hf[tid - 61] = (float)H.h[4 * (tid - 64)]; }
     const int periodic = H.periodic;
+    // axis-aligned periodic cell: the slots are unwrapped in fp32 (vl_unwrap_ortho)
+    const bool ortho = periodic && H.h[1] == 0.0 && H.h[2] == 0.0 && H.h[3] == 0.0 && H.h[5] == 0.0 && H.h[6] == 0.0 &&
+                       H.h[7] == 0.0;
     const float skin2 = H.skin2, a_assumed = H.a_assumed, c2q_lo = H.c2q_lo, c2q_hi = H.c2q_hi, qscale = H.qscale;
     const int n_tiles = H.n_tiles;
     const bool multi_tile = n_tiles > 1;
@@ -1177,7 +1277,8 @@ __global__ void __launch_bounds__(VL_THREADS, 1) vl_frames(const VlFrameParams p
                     const float4 ref = __ldg(&slot_ref[tid + k * VL_THREADS]);
                     const float4 sh = shift_s[s_word[k] >> 24];
                     float x, y, z;
-                    vl_unwrap(hs, hs + 9, periodic, raw_x[k], raw_y[k], raw_z[k], ref.x, ref.y, ref.z, x, y, z);
+                    if (ortho) vl_unwrap_ortho(hf, raw_x[k], raw_y[k], raw_z[k], ref.x, ref.y, ref.z, x, y, z);
+                    else vl_unwrap(hs, hs + 9, periodic, raw_x[k], raw_y[k], raw_z[k], ref.x, ref.y, ref.z, x, y, z);
                     if (!multi_tile) {
                         const float ex = x - ref.x, ey = y - ref.y, ez = z - ref.z;
                         const float a = fmaxf(fabsf(raw_x[k]), fmaxf(fabsf(raw_y[k]), fabsf(raw_z[k])));

@@ -301,3 +301,45 @@ def test_s4_full_size_min_dist_and_nearest_match_oracle(engine, s3):
         best = sorted(zip(d.tolist(), allowed))[0]
         assert near.nearest[int(atom)] == best[1]
         assert near.nearest_distance[int(atom)] == np.float32(best[0])
+
+
+def test_streamed_host_schedule_head_and_tail_chunks(engine):
+    """A pinned host trajectory long enough for the automatic chunk schedule of
+    cmb_accumulate_host (short first chunk that the list is built from, quarter-size tail chunk cut
+    into fine work items, unit cells copied once): same tables as the device entry point, with and
+    without frames that trip the guard inside the head and the tail chunk."""
+    rng = np.random.default_rng(77)
+    system = synth.random_system(rng, 300, n_chains=2, box_kind="ortho", extent=1.9)
+    res, chain, role = system_arrays(system)
+    engine.set_system(res, chain, role, 0.45, 2)
+    assert engine.path_kind == 0
+    F = 8000
+    xyz, box = _dev(engine, system, 0, F)
+    xyz, box = xyz.clone(), box.clone()
+    fill = engine.get_stat("sm_count") * max(1, engine.get_stat("ctas_per_sm")) * 2
+    chunk = max(fill, (F + 3) // 4)                       # 80 MB would hold far more frames of 300 atoms
+    head = max(fill, chunk // 4)
+    want = ([head] if F >= 3 * chunk and chunk >= 2 * head else [])
+    rest = F - sum(want)
+    want += [chunk] * (rest // chunk) + ([rest % chunk] if rest % chunk else [])
+    tail = max(fill, want[-1] // 4)
+    if want[-1] >= 2 * tail:
+        want[-1:] = [want[-1] - tail, tail]
+    for kicked in ((), (3, F - 5, F // 2)):
+        for f in kicked:
+            xyz[f, 11] += 0.5
+        dev_a, dev_r, _ = _accumulate(engine, xyz, box, 1)
+        h_xyz = torch.empty(xyz.shape, dtype=torch.float32, pin_memory=True).copy_(xyz)
+        h_box = torch.empty(box.shape, dtype=torch.float32, pin_memory=True).copy_(box)
+        host_a, host_r = engine.new_tables()
+        engine.set_option("stage_trace", 1)
+        try:
+            engine.accumulate_host(h_xyz.numpy(), h_box.numpy(), host_a, host_r)
+            assert engine.get_stat("trace_chunks") == len(want)
+            done = [engine.get_stat("trace_done_%d" % c) for c in range(len(want))]
+            assert all(d > 0 for d in done)
+        finally:
+            engine.set_option("stage_trace", 0)
+        assert engine.get_stat("vl_used") == 1
+        assert torch.equal(host_a, dev_a) and torch.equal(host_r, dev_r)
+    assert len(want) >= 5 and want[0] < want[1] and want[-1] < want[-2] + want[-1]
