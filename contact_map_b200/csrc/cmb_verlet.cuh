@@ -1098,7 +1098,7 @@ constexpr int VL_AUDIT = 1;      // template flag: run the exact arithmetic on E
 // dynamic shared memory of the frame kernel (bytes); the position array sits at offset 0 so that
 // the slot fields of the entry words are ready-made byte offsets
 constexpr int VL_QCAP = 1024;                                          // ambiguous pairs parked per tile and frame
-constexpr int VL_SM_POS = 0;                                           // uint2 [VL_MAX_SLOTS + 1]: x | y << 16, z
+constexpr int VL_SM_POS = 0;                                           // uint2 [VL_MAX_SLOTS + 1]: x | y << 16, float bits of 2^23 + z
 constexpr int VL_SM_CNT = VL_SM_POS + (VL_MAX_SLOTS + 1) * VL_SLOT_BYTES;   // u32 [VL_MAX_ENTRIES / 4]: byte counters
 constexpr int VL_SM_RES = VL_SM_CNT + VL_MAX_ENTRIES;                  // u8 [VL_MAX_SEGS]: frames in which the pair was seen
 constexpr int VL_SM_FLAG = VL_SM_RES + VL_MAX_SEGS;                    // u8 [2][VL_MAX_SEGS] "seen in this frame" (frame parity)
@@ -1126,7 +1126,8 @@ __device__ __forceinline__ void vl_sts8(unsigned addr, unsigned v)
 // such floats are exact integers
 __device__ __forceinline__ float vl_lo16f(unsigned w) { return __uint_as_float(__byte_perm(w, 0x4b000000u, 0x7610)); }
 __device__ __forceinline__ float vl_hi16f(unsigned w) { return __uint_as_float(__byte_perm(w, 0x4b000000u, 0x7632)); }
-__device__ __forceinline__ float vl_z23f(unsigned w) { return __uint_as_float(w | 0x4b000000u); }
+// (the z word is stored as those float bits already)
+__device__ __forceinline__ float vl_z23f(unsigned w) { return __uint_as_float(w); }
 
 // Exact decision of one parked (ambiguous) list entry and its accounting.
 //   e.x = owner slot byte offset | (partner slot byte offset | direction) << 16
@@ -1216,7 +1217,7 @@ __global__ void __launch_bounds__(VL_THREADS, 1) vl_frames(const VlFrameParams p
             reinterpret_cast<unsigned*>(segflag2 + VL_MAX_SEGS)[w] = 0u;
         }
         // the "far" slot of padding entries: z = 2^23 - 1 grid units, beyond every threshold
-        if (tid == 0) pos[T.n_slots] = make_uint2(0u, 0x7fffffu);
+        if (tid == 0) pos[T.n_slots] = make_uint2(0u, 0x4b7fffffu);
         // per slot only the word (atom | shift id << 24) and the prefetched raw coordinates stay in
         // registers across the pair phase; the reference position is re-read (L2) every frame
         unsigned s_word[VL_SPT];
@@ -1290,10 +1291,12 @@ __global__ void __launch_bounds__(VL_THREADS, 1) vl_frames(const VlFrameParams p
                     const float gx = __fmul_rn(__fsub_rn(__fadd_rn(x, sh.x), T.ox), qscale),
                                 gy = __fmul_rn(__fsub_rn(__fadd_rn(y, sh.y), T.oy), qscale),
                                 gz = __fmul_rn(__fsub_rn(__fadd_rn(z, sh.z), T.oz), qscale);
-                    const unsigned qx = (unsigned)min(max(__float2int_rn(gx), 0), 65535),
-                                   qy = (unsigned)min(max(__float2int_rn(gy), 0), 65535),
-                                   qz = (unsigned)min(max(__float2int_rn(gz), 0), 65535);
-                    pos[tid + k * VL_THREADS] = make_uint2(qx | (qy << 16), qz);
+                    // round to the grid by adding 2^23 (round to nearest even, as cvt.rni would, on the
+                    // FP32 pipe): the sum's bits are 0x4b000000 | grid coordinate
+                    const unsigned qx = __float_as_uint(__fadd_rn(fminf(fmaxf(gx, 0.f), 65535.f), 8388608.f)),
+                                   qy = __float_as_uint(__fadd_rn(fminf(fmaxf(gy, 0.f), 65535.f), 8388608.f)),
+                                   qz = __float_as_uint(__fadd_rn(fminf(fmaxf(gz, 0.f), 65535.f), 8388608.f));
+                    pos[tid + k * VL_THREADS] = make_uint2(__byte_perm(qx, qy, 0x5410), qz);
                     if (f + 1 < fb) {           // prefetch the next frame under the pair phase
                         const float* q = p.xyz + ((size_t)(f + 1) * (size_t)p.n + (size_t)atom) * 3;
                         raw_x[k] = __ldg(q); raw_y[k] = __ldg(q + 1); raw_z[k] = __ldg(q + 2);
