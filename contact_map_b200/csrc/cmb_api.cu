@@ -1382,6 +1382,34 @@ extern "C" int cmb_export_sorted(cmb_ctx* ctx, const void* d_table, int64_t n_el
     return sort_key_bits(ctx, d_packed, cap, 24, 64, st);
 }
 
+__global__ void __launch_bounds__(256) k_unpack_sorted(const unsigned long long* __restrict__ packed,
+                                                       const unsigned long long* __restrict__ d_n, long long cap,
+                                                       long long idx_offset, long long* __restrict__ idx,
+                                                       unsigned int* __restrict__ cnt)
+{
+    const long long n = min((long long)d_n[0], cap);
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long w = packed[k];
+        idx[k] = (long long)(w >> 24) + idx_offset;
+        cnt[k] = (unsigned int)(w & 0xffffffull);
+    }
+}
+
+extern "C" int cmb_unpack_sorted(cmb_ctx* ctx, const uint64_t* d_packed, const uint64_t* d_n, int64_t cap,
+                                 int64_t idx_offset, int64_t* d_idx, uint32_t* d_cnt, void* stream)
+{
+    if (!ctx) return CMB_ERR_ARG;
+    if (!d_packed || !d_n || !d_idx || !d_cnt || cap < 1) return fail(ctx, CMB_ERR_ARG, "bad unpack arguments");
+    CK(cudaSetDevice(ctx->device));
+    const int grid = (int)std::min<long long>((cap + 255) / 256, (long long)ctx->sm_count * 8);
+    k_unpack_sorted<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(d_packed),
+                                                           reinterpret_cast<const unsigned long long*>(d_n), cap, idx_offset,
+                                                           reinterpret_cast<long long*>(d_idx), d_cnt);
+    CK(cudaGetLastError());
+    ctx->stats["kernel_launches"] += 1;
+    return CMB_OK;
+}
+
 extern "C" int cmb_group_contacts(cmb_ctx* ctx, const float* d_xyz, const float* d_box, int64_t n_frames, int n_atoms,
                                   const int32_t* d_atoms, int n_sel, const int32_t* d_pairs,
                                   const int64_t* d_group_ptr, int n_groups, int orthogonal, float cutoff,

@@ -380,10 +380,12 @@ class ContactEngine(object):
         """Sparse export of several count tables with ONE host synchronisation.
 
         Every table is scanned by ``cmb_export_sorted`` into a capacity-sized device buffer of
-        packed (flat index << 24 | count) words, radix-sorted on the device and copied to pinned
-        host memory asynchronously; the stream is synchronised once.  Capacities come from the
-        previous export of a table of the same size (first use: ``count_nonzero``); an overflow
-        triggers one exact retry; counts that do not fit 24 bits fall back to the unpacked export.
+        packed (flat index << 24 | count) words (hashed tables: radix-sorted on the device), split
+        into index and count arrays on the device (``cmb_unpack_sorted``, which reads the entry
+        count there) and copied to pinned host memory asynchronously; the stream is synchronised
+        once.  Capacities come from the previous export of a table of the same size (first use:
+        ``count_nonzero``); an overflow triggers one exact retry; counts that do not fit 24 bits
+        fall back to the unpacked export.
         Returns [(flat index int64[], count uint32[]), ...], each sorted by index.
         """
         fused = self._export_span(tables)
@@ -419,8 +421,8 @@ class ContactEngine(object):
                     n = int(job["h_n"][0])
                 if not isinstance(t, HashTable):
                     hints[t.numel()] = n
-                packed = job["h_packed"][:n].numpy()
-                out.append((packed >> 24, (packed & 0xffffff).astype(np.uint32)))
+                # (the pinned staging buffers are recycled by the next export: hand out copies)
+                out.append((np.array(job["h_idx"][:n].numpy()), np.array(job["h_cnt"][:n].numpy()).view(np.uint32)))
         return out
 
     def export_packed_device(self, tables):
@@ -478,7 +480,7 @@ class ContactEngine(object):
         span.set_(tables[0].untyped_storage(), lo, (hi - lo,))
         (idx, cnt), = self.export_many([span])
         cuts = np.searchsorted(idx, np.asarray(offsets + [hi], dtype=np.int64) - lo)
-        return [(idx[a:b] - (o - lo), cnt[a:b]) for a, b, o in zip(cuts[:-1], cuts[1:], offsets)]
+        return [(idx[a:b] if o == lo else idx[a:b] - (o - lo), cnt[a:b]) for a, b, o in zip(cuts[:-1], cuts[1:], offsets)]
 
     def _export_launch(self, table, cap, slot, to_host=True):
         # staging buffers are keyed by (table size, position in the call) and reused across calls
@@ -489,7 +491,6 @@ class ContactEngine(object):
                 "cap": cap,
                 "d_packed": torch.empty(cap, dtype=torch.int64, device=self.device),
                 "d_n": torch.zeros(2, dtype=torch.int64, device=self.device),
-                "h_packed": torch.empty(cap, dtype=torch.int64, pin_memory=True),
                 "h_n": torch.zeros(2, dtype=torch.int64, pin_memory=True),
             }
             if len(pool) > 8:
@@ -501,7 +502,19 @@ class ContactEngine(object):
                                               _ptr(buf["d_n"]), _stream_ptr(self.device)), "cmb_export_sorted")
         buf["h_n"].copy_(buf["d_n"], non_blocking=True)
         if to_host:
-            buf["h_packed"].copy_(buf["d_packed"], non_blocking=True)
+            if "d_idx" not in buf:
+                buf["d_idx"] = torch.empty(buf["cap"], dtype=torch.int64, device=self.device)
+                buf["d_cnt"] = torch.empty(buf["cap"], dtype=torch.int32, device=self.device)
+                buf["h_idx"] = torch.empty(buf["cap"], dtype=torch.int64, pin_memory=True)
+                buf["h_cnt"] = torch.empty(buf["cap"], dtype=torch.int32, pin_memory=True)
+            self._check(self._L.cmb_unpack_sorted(self._ctx, _ptr(buf["d_packed"]), _ptr(buf["d_n"]), buf["cap"], 0,
+                                                  _ptr(buf["d_idx"]), _ptr(buf["d_cnt"]), _stream_ptr(self.device)),
+                        "cmb_unpack_sorted")
+            # (the capacity is the previous entry count + 25 %: copying all of it costs less than a
+            # second synchronisation to learn the exact count first)
+            k = min(buf["cap"], cap)
+            buf["h_idx"][:k].copy_(buf["d_idx"][:k], non_blocking=True)
+            buf["h_cnt"][:k].copy_(buf["d_cnt"][:k], non_blocking=True)
         return buf
 
     def _export_unpacked(self, table):

@@ -182,6 +182,15 @@ int cmb_export_sorted(cmb_ctx* ctx, const void* d_table, int64_t n_elems, int lo
                       uint64_t* d_packed, uint64_t* d_n, void* stream);
 
 /*
+ * Split the packed words of cmb_export_sorted into the two arrays a host consumer wants (the keys and
+ * values of the reference's Counter, contact_map.py:739-740): d_idx[k] = word >> 24 (+ idx_offset),
+ * d_cnt[k] = word & 0xffffff for k < min(d_n[0], cap).  The entry count is read on the device, so the
+ * call can be queued right behind cmb_export_sorted without a host synchronisation in between.
+ */
+int cmb_unpack_sorted(cmb_ctx* ctx, const uint64_t* d_packed, const uint64_t* d_n, int64_t cap,
+                      int64_t idx_offset, int64_t* d_idx, uint32_t* d_cnt, void* stream);
+
+/*
  * north_star: "any pair within 1 ulp of the cutoff enumerated and reported".
  * Records {frame, lo, hi, d2} (int32,int32,int32,float32 = 16 bytes) of eligible
  * pairs whose d2 is within `ulps` float steps of cutoff^2.
