@@ -1722,7 +1722,9 @@ inline int vl_run_frames(const VlJob& job, const VlList& L, const VlRun& R, int 
     }
     VlFrameParams p;
     p.xyz = job.xyz; p.box = job.box; p.n_frames = job.n_frames; p.n = job.n; p.n_res_c = job.n_res_c; p.c2 = job.c2;
-    p.rounds = job.n <= VL_SINGLE_TILE_ATOMS ? 4 : 6;
+    // single tile: every item costs the same, so one item per SM (static split) wastes nothing on
+    // set-up / flush; lists of many tiles have tiles of different weight and are dealt dynamically
+    p.rounds = job.n <= VL_SINGLE_TILE_ATOMS ? 1 : 6;
     p.atom_table = job.atom_table; p.res_table = job.res_table; p.audit = job.d_audit;
     if (job.t_begin) VL_CK(cudaEventRecord(job.t_begin, st));
     if (job.audit) vl_frames<VL_AUDIT><<<sm_count, VL_THREADS, VL_SM_TOTAL, st>>>(p, L, R);
