@@ -19,26 +19,34 @@
 //        exclusion: contact_map.py:41-60,442-461 -- both are frame independent, so they are
 //        applied HERE and never again) whose reference minimum-image distance is <= r_list is
 //        recorded once, with the lattice shift of its image.
-//     3. the records are sorted by (tile, residue pair): the atom pairs of one residue pair form
-//        a SEGMENT.  Segments are sorted by length and dealt 32 at a time to "bundles"
-//        (lane = segment); a bundle is stored as ROWS of 4 steps x 32 lanes.  A tile is a block of
-//        cells whose segments, atoms ("slots", periodic images of an atom are separate slots
-//        that carry their lattice shift) and counters fit one CTA's shared memory: small systems
-//        are one tile, the 100k-atom system a few hundred.
+//     3. the records are sorted by (tile, residue pair) -- the atom pairs of one residue pair form
+//        a SEGMENT with one "seen in this frame" flag and one counter -- and, stably, by (tile,
+//        owner atom): the partners of one atom form an OWNER LIST.  Owner lists are sorted by
+//        length and dealt 32 at a time to "bundles" (lane = owner); a bundle is stored as ROWS of
+//        4 steps x 32 lanes.  A tile is a block of cells whose segments, atoms ("slots", periodic
+//        images of an atom are separate slots that carry their lattice shift) and counters fit one
+//        CTA's shared memory: small systems are one tile, the 100k-atom system a few hundred.
+//        The slot chain (keys, sort, unique, reference positions, fixed-point grid) runs on a second
+//        stream beside the segment / owner-list / bundle chain; vl_fill joins them and balances the
+//        shared-memory banks of the gathers (order of a lane's four partners, deal of the owners
+//        to the half warps).
 //   frame kernel (persistent CTAs, work item = tile x range of frames):
 //     a. every thread loads its slots' RAW coordinates (prefetched one frame ahead), moves them
-//        to the periodic image next to the slot's reference position (fp64, one rounding) and
-//        checks the GUARD |x - ref| <= skin; a frame that violates it (or whose unit cell differs
-//        from the batch's, or whose coordinates exceed the magnitude the error bound was derived
-//        for) is appended to the fall-back list and skipped;
-//     b. warps pull rows (two at a time, the next two already in flight from L2); a lane walks
-//        the atom pairs of ITS residue pair: two LDS.128 (one when the first atom repeats),
-//        3 FADD + 3 FFMA, two compares; d2 <= c2_lo is a certain contact, c2_lo < d2 < c2_hi is
-//        AMBIGUOUS and decided by MDTraj's exact non-fused arithmetic on the raw coordinates
+//        to the periodic image next to the slot's reference position (one rounding: fp64, or an
+//        fp32 fma for axis-aligned cells), checks the GUARD |x - ref| <= skin -- a frame that
+//        violates it (or whose unit cell differs from the batch's, or whose coordinates exceed the
+//        magnitude the error bound was derived for) is appended to the fall-back list and skipped
+//        -- and stores the position as three 16-bit fixed-point numbers relative to the tile's
+//        origin (8 bytes per slot);
+//     b. warps walk rows; lane l of a row walks four partners of ITS owner atom: one LDS.64 for
+//        the owner, one per partner, exact integer differences on the grid, 1 FMUL + 2 FFMA, two
+//        compares against thresholds widened by the rigorous grid bound (vl_quant_setup);
+//        d2 <= c2q_lo is a certain contact, c2q_lo < d2 < c2q_hi is AMBIGUOUS: parked and decided
+//        one frame later by MDTraj's exact non-fused arithmetic on the raw coordinates
 //        (cmb_math.cuh::nl_d2), exactly as in the cell kernels (same per-batch error bound,
 //        frame_margins); contacts increment a per-entry byte counter in shared memory (the
-//        thread owns the entry: no atomics) and set the lane's "residue pair seen" bit -- the
-//        per-frame set semantics of contact_map.py:601-607,740 without a bitmap;
+//        thread owns the entry: no atomics) and set the byte flag of the entry's residue pair --
+//        the per-frame set semantics of contact_map.py:601-607,740 without a bitmap;
 //     c. after the last frame of the item the counters are flushed with one RED per non-zero
 //        entry (a batch of 64 frames issues ~30x fewer atomics than one per hit).
 //   fall back: the frames on the fall-back list are processed by the cell kernels (which accept

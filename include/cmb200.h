@@ -78,7 +78,10 @@ int cmb_accumulate(cmb_ctx* ctx, const float* d_xyz, const float* d_box, int64_t
  * ordinary array, a memory-mapped file) is first packed by host threads into pinned staging
  * buffers, chunk k + 1 while chunk k is transferred and processed (2.3x faster than letting the
  * driver stage it; cmb_set_option "stage_pageable" 0 switches that off).
- * chunk_frames <= 0 picks a chunk of about 32 MiB.  Synchronous.
+ * chunk_frames <= 0 lets the library choose the schedule: chunks of about 80 MiB (at least four per
+ * call), a short first chunk (the pair list is built from it while the second chunk is copied) and a
+ * quarter-size last chunk (the call ends one chunk's worth of kernels after the last copy).
+ * Synchronous.
  */
 int cmb_accumulate_host(cmb_ctx* ctx, const float* h_xyz, const float* h_box, int64_t n_frames,
                         int64_t chunk_frames, uint32_t* d_atom_table, uint32_t* d_res_table);
