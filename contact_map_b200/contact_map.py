@@ -507,7 +507,15 @@ def _table_kind(table):
 
 def _tables_to_pairs(engine, atom_table, res_table, used):
     """Sparse export of the device tables -> (atom PairTable, residue PairTable) in REAL indices."""
-    return _exports_to_pairs(engine, engine.export_many([atom_table, res_table]), used)
+    views = engine.export_pair_views(atom_table, res_table) if hasattr(engine, "export_pair_views") else None
+    if views is None:
+        return _exports_to_pairs(engine, engine.export_many([atom_table, res_table]), used)
+    # (row, column, count) triples split on the device; the index maps below copy out of the
+    # recycled staging buffers
+    (lo, hi, cnt), (rlo, rhi, rcnt) = views
+    rmap = engine.residue_map.astype(np.int64)
+    return (PairTable(used[lo], used[hi], cnt.astype(np.int64)),
+            PairTable(rmap[rlo], rmap[rhi], rcnt.astype(np.int64)))
 
 
 def _exports_to_pairs(engine, exports, used):

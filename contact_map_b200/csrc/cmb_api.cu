@@ -1410,6 +1410,52 @@ extern "C" int cmb_unpack_sorted(cmb_ctx* ctx, const uint64_t* d_packed, const u
     return CMB_OK;
 }
 
+__global__ void __launch_bounds__(256) k_unpack_pairs(const unsigned long long* __restrict__ packed,
+                                                      const unsigned long long* __restrict__ d_n, long long cap,
+                                                      long long n_cols0, long long off1, long long n_cols1,
+                                                      int* __restrict__ lo, int* __restrict__ hi,
+                                                      unsigned int* __restrict__ cnt, unsigned long long* __restrict__ d_split)
+{
+    const long long n = min((long long)d_n[0], cap);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        // entries of the first table: lower bound of flat index off1 in the sorted words
+        long long a = 0, b = n;
+        while (a < b) {
+            const long long mid = (a + b) >> 1;
+            if ((long long)(packed[mid] >> 24) < off1) a = mid + 1; else b = mid;
+        }
+        d_split[0] = (unsigned long long)a;
+    }
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long w = packed[k];
+        long long idx = (long long)(w >> 24), cols = n_cols0;
+        if (idx >= off1) { idx -= off1; cols = n_cols1; }
+        const long long row = idx / cols;
+        lo[k] = (int)row;
+        hi[k] = (int)(idx - row * cols);
+        cnt[k] = (unsigned int)(w & 0xffffffull);
+    }
+}
+
+extern "C" int cmb_unpack_pairs(cmb_ctx* ctx, const uint64_t* d_packed, const uint64_t* d_n, int64_t cap,
+                                int64_t n_cols0, int64_t off1, int64_t n_cols1, int32_t* d_lo, int32_t* d_hi,
+                                uint32_t* d_cnt, uint64_t* d_split, void* stream)
+{
+    if (!ctx) return CMB_ERR_ARG;
+    if (!d_packed || !d_n || !d_lo || !d_hi || !d_cnt || !d_split || cap < 1 || n_cols0 < 1 || n_cols1 < 1 ||
+        off1 < n_cols0 * n_cols0 || n_cols0 > 0x7fffffffll || n_cols1 > 0x7fffffffll)
+        return fail(ctx, CMB_ERR_ARG, "bad unpack arguments");
+    CK(cudaSetDevice(ctx->device));
+    const int grid = (int)std::min<long long>((cap + 255) / 256, (long long)ctx->sm_count * 8);
+    k_unpack_pairs<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned long long*>(d_packed),
+                                                          reinterpret_cast<const unsigned long long*>(d_n), cap, n_cols0,
+                                                          off1, n_cols1, d_lo, d_hi, d_cnt,
+                                                          reinterpret_cast<unsigned long long*>(d_split));
+    CK(cudaGetLastError());
+    ctx->stats["kernel_launches"] += 1;
+    return CMB_OK;
+}
+
 extern "C" int cmb_group_contacts(cmb_ctx* ctx, const float* d_xyz, const float* d_box, int64_t n_frames, int n_atoms,
                                   const int32_t* d_atoms, int n_sel, const int32_t* d_pairs,
                                   const int64_t* d_group_ptr, int n_groups, int orthogonal, float cutoff,

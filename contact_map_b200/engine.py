@@ -425,6 +425,62 @@ class ContactEngine(object):
                 out.append((np.array(job["h_idx"][:n].numpy()), np.array(job["h_cnt"][:n].numpy()).view(np.uint32)))
         return out
 
+    def export_pair_views(self, atom_table, res_table):
+        """Sparse export of the two dense tables of :meth:`new_tables` as (row, column, count)
+        triples split on the DEVICE (``cmb_unpack_pairs``): one scan of the allocation, one host
+        synchronisation, no host-side divmod over millions of entries.
+
+        Returns ``((lo, hi, cnt), (rlo, rhi, rcnt))`` -- int32 / int32 / uint32 numpy VIEWS of pinned
+        staging buffers that the next export overwrites (callers map them to real indices at once,
+        which copies) -- or ``None`` when the tables are not such a pair or a count does not fit
+        24 bits (callers then use :meth:`export_many`)."""
+        tables = (atom_table, res_table)
+        if any(isinstance(t, HashTable) or not t.is_contiguous() or t.dtype != torch.int32 for t in tables):
+            return None
+        base = atom_table.untyped_storage().data_ptr()
+        n, rc = int(self.n_used), int(self.n_res_c)
+        off0, off1 = atom_table.storage_offset(), res_table.storage_offset()
+        if (res_table.untyped_storage().data_ptr() != base or atom_table.numel() != n * n or
+                res_table.numel() != rc * rc or off0 % 4 or off1 < off0 + n * n or
+                off1 + rc * rc - off0 > 2 * (n * n + rc * rc)):
+            return None
+        span = torch.empty(0, dtype=torch.int32, device=atom_table.device)
+        span.set_(atom_table.untyped_storage(), off0, (off1 + rc * rc - off0,))
+        hints = self.__dict__.setdefault("_export_hint", {})
+        stream = torch.cuda.current_stream(self.device)
+        cap = hints.get(span.numel())
+        with torch.cuda.device(self.device):
+            if cap is None:
+                cap = int(torch.count_nonzero(span).item())
+            cap = max(16, min(span.numel(), cap + cap // 4 + 1024))
+            for attempt in range(2):
+                buf = self._export_launch(span, cap, 0, to_host=False)
+                if "d_lo" not in buf or buf["d_lo"].numel() < buf["cap"]:
+                    for name in ("lo", "hi", "pc"):
+                        buf["d_" + name] = torch.empty(buf["cap"], dtype=torch.int32, device=self.device)
+                        buf["h_" + name] = torch.empty(buf["cap"], dtype=torch.int32, pin_memory=True)
+                    buf["d_split"] = torch.zeros(1, dtype=torch.int64, device=self.device)
+                    buf["h_split"] = torch.zeros(1, dtype=torch.int64, pin_memory=True)
+                self._check(self._L.cmb_unpack_pairs(self._ctx, _ptr(buf["d_packed"]), _ptr(buf["d_n"]), buf["cap"],
+                                                     n, off1 - off0, rc, _ptr(buf["d_lo"]), _ptr(buf["d_hi"]),
+                                                     _ptr(buf["d_pc"]), _ptr(buf["d_split"]),
+                                                     _stream_ptr(self.device)), "cmb_unpack_pairs")
+                buf["h_split"].copy_(buf["d_split"], non_blocking=True)
+                for name in ("lo", "hi", "pc"):
+                    buf["h_" + name][:cap].copy_(buf["d_" + name][:cap], non_blocking=True)
+                stream.synchronize()
+                found, wide = int(buf["h_n"][0]), int(buf["h_n"][1])
+                if wide:
+                    return None
+                if found <= buf["cap"]:
+                    break
+                cap = found                    # capacity guess too small: exact retry
+            hints[span.numel()] = found
+        k = int(buf["h_split"][0])
+        lo, hi = buf["h_lo"][:found].numpy(), buf["h_hi"][:found].numpy()
+        cnt = buf["h_pc"][:found].numpy().view(np.uint32)
+        return (lo[:k], hi[:k], cnt[:k]), (lo[k:], hi[k:], cnt[k:])
+
     def export_packed_device(self, tables):
         """Sparse export that STAYS on the device: for every dense table a sorted int64 tensor of
         packed (flat index << 24 | count) words (``cmb_export_sorted``), or ``None`` for a table

@@ -13,7 +13,7 @@ import numpy as np
 from . import parallel
 from . import trajectory as _trajectory
 from .contact_map import (ContactFrequency, ContactObject, _engine_system, _split_trajectory,
-                          _exports_to_pairs, _table_kind, _used_coordinates)
+                          _exports_to_pairs, _table_kind, _tables_to_pairs, _used_coordinates)
 from .contact_count import PairTable
 from .contact_trajectory import KEY_MAX_FRAMES, KEY_MAX_INDEX, ContactTrajectory, FrameCSR, _build_contacts
 
@@ -74,6 +74,8 @@ class ChunkedContactFrequency(ContactFrequency):
             else:
                 engine.accumulate_host(bx, bb, atom_table, res_table)
         self._table_kind = _table_kind(atom_table)
+        if parallel.world()[1] == 1:
+            return _tables_to_pairs(engine, atom_table, res_table, used)
         exports = parallel.reduce_export(engine, [atom_table, res_table], dst=self._result_rank)
         if exports is None:
             return PairTable.empty(), PairTable.empty()

@@ -194,6 +194,18 @@ int cmb_unpack_sorted(cmb_ctx* ctx, const uint64_t* d_packed, const uint64_t* d_
                       int64_t idx_offset, int64_t* d_idx, uint32_t* d_cnt, void* stream);
 
 /*
+ * The same for the export of ONE scan over an allocation that holds two dense tables (the atom table
+ * of n_cols0 columns at flat index 0, the residue table of n_cols1 columns at flat index off1): every
+ * entry is split into its (row, column) pair on the device -- d_lo[k], d_hi[k] (compact indices, int32),
+ * d_cnt[k] -- and d_split[0] receives the number of entries that belong to the first table (they come
+ * first: the words are sorted).  Replaces the per-key Python loop that fills the reference's Counter
+ * (contact_map.py:739-740) and a host-side divmod over millions of entries.
+ */
+int cmb_unpack_pairs(cmb_ctx* ctx, const uint64_t* d_packed, const uint64_t* d_n, int64_t cap,
+                     int64_t n_cols0, int64_t off1, int64_t n_cols1, int32_t* d_lo, int32_t* d_hi,
+                     uint32_t* d_cnt, uint64_t* d_split, void* stream);
+
+/*
  * north_star: "any pair within 1 ulp of the cutoff enumerated and reported".
  * Records {frame, lo, hi, d2} (int32,int32,int32,float32 = 16 bytes) of eligible
  * pairs whose d2 is within `ulps` float steps of cutoff^2.

@@ -193,3 +193,41 @@ def test_crowded_cells(engine, box_kind):
             assert np.array_equal(dense_from_export(ridx, rcnt, engine.n_res_c), ref_res[np.ix_(rmap, rmap)])
         finally:
             engine.set_option("force_path", -1)
+
+
+@pytest.mark.parametrize("case_id", [0, 4, 7])
+def test_export_pair_views_equals_export_many(engine, case_id):
+    """cmb_unpack_pairs (row / column / count triples split on the device, one scan over both
+    tables) against the packed export split on the host; empty tables, a capacity guess that is too
+    small (exact retry) and counts beyond 24 bits (refused: callers fall back) included."""
+    case = CASES[case_id]
+    system, xyz, box, (atom_res, atom_chain, role), _ = _run_case(engine, case, 300 + case_id)
+    engine.set_system(atom_res, atom_chain, role, case[2], case[3])
+    n, rc = engine.n_used, engine.n_res_c
+    atom_t, res_t = engine.new_tables()
+    (lo, hi, cnt), (rlo, rhi, rcnt) = engine.export_pair_views(atom_t, res_t)
+    assert len(lo) == len(rlo) == 0
+    d_xyz = torch.as_tensor(xyz, device=engine.device)
+    d_box = None if box is None else torch.as_tensor(box, device=engine.device)
+    for rounds in (1, 3):                      # the second pass quadruples the entry count hint's tables
+        for _ in range(rounds):
+            engine.accumulate(d_xyz, d_box, atom_t, res_t)
+        (idx, c), (ridx, rcn) = engine.export_many([atom_t, res_t])
+        (lo, hi, cnt), (rlo, rhi, rcnt) = engine.export_pair_views(atom_t, res_t)
+        assert np.array_equal(lo.astype(np.int64) * n + hi, idx) and np.array_equal(cnt, c)
+        assert np.array_equal(rlo.astype(np.int64) * rc + rhi, ridx) and np.array_equal(rcnt, rcn)
+        assert lo.dtype == np.int32 and cnt.dtype == np.uint32 and len(idx) > 0
+    # a stale, too small capacity hint: one exact retry
+    engine._export_hint.clear()
+    engine._export_pool.clear()
+    small_a, small_r = engine.new_tables()
+    small_a[1] = 5
+    engine.export_pair_views(small_a, small_r)              # hint = 1 entry
+    engine._export_pool.clear()
+    (lo2, hi2, cnt2), (rlo2, _, _) = engine.export_pair_views(atom_t, res_t)
+    assert np.array_equal(lo2.astype(np.int64) * n + hi2, idx) and np.array_equal(cnt2, c) and len(rlo2) == len(ridx)
+    # counts of 2^24 and more do not fit the packed words
+    small_a[1] = 1 << 24
+    assert engine.export_pair_views(small_a, small_r) is None
+    # tables that are not the two views of one allocation
+    assert engine.export_pair_views(atom_t.clone(), res_t) is None
