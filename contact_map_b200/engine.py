@@ -415,7 +415,7 @@ class ContactEngine(object):
                 if wide:
                     out.append(self._export_unpacked(t))
                     continue
-                if n > job["cap"]:            # capacity guess too small: exact retry
+                if n > job["use"]:            # capacity guess too small: exact retry
                     job = self._export_launch(t, n, slot)
                     stream.synchronize()
                     n = int(job["h_n"][0])
@@ -461,7 +461,7 @@ class ContactEngine(object):
                         buf["h_" + name] = torch.empty(buf["cap"], dtype=torch.int32, pin_memory=True)
                     buf["d_split"] = torch.zeros(1, dtype=torch.int64, device=self.device)
                     buf["h_split"] = torch.zeros(1, dtype=torch.int64, pin_memory=True)
-                self._check(self._L.cmb_unpack_pairs(self._ctx, _ptr(buf["d_packed"]), _ptr(buf["d_n"]), buf["cap"],
+                self._check(self._L.cmb_unpack_pairs(self._ctx, _ptr(buf["d_packed"]), _ptr(buf["d_n"]), cap,
                                                      n, off1 - off0, rc, _ptr(buf["d_lo"]), _ptr(buf["d_hi"]),
                                                      _ptr(buf["d_pc"]), _ptr(buf["d_split"]),
                                                      _stream_ptr(self.device)), "cmb_unpack_pairs")
@@ -472,7 +472,7 @@ class ContactEngine(object):
                 found, wide = int(buf["h_n"][0]), int(buf["h_n"][1])
                 if wide:
                     return None
-                if found <= buf["cap"]:
+                if found <= cap:
                     break
                 cap = found                    # capacity guess too small: exact retry
             hints[span.numel()] = found
@@ -506,7 +506,7 @@ class ContactEngine(object):
                     out.append(None)
                     continue
                 n, wide = int(job["h_n"][0]), int(job["h_n"][1])
-                if n > job["cap"] and not wide:
+                if n > job["use"] and not wide:
                     job = self._export_launch(t, n, slot, to_host=False)
                     stream.synchronize()
                     n, wide = int(job["h_n"][0]), int(job["h_n"][1])
@@ -553,8 +553,11 @@ class ContactEngine(object):
                 pool.clear()
             pool[(table.numel(), slot)] = buf
         hashed = isinstance(table, HashTable)
+        # the kernels are given the REQUESTED capacity (the pooled buffers may be larger): entries
+        # beyond it are counted but not written, and only `use` entries are copied to the host
+        buf["use"] = cap
         self._check(self._L.cmb_export_sorted(self._ctx, _table_ptr(table), table.numel(),
-                                              table.log2 if hashed else 0, buf["cap"], _ptr(buf["d_packed"]),
+                                              table.log2 if hashed else 0, cap, _ptr(buf["d_packed"]),
                                               _ptr(buf["d_n"]), _stream_ptr(self.device)), "cmb_export_sorted")
         buf["h_n"].copy_(buf["d_n"], non_blocking=True)
         if to_host:
@@ -563,14 +566,13 @@ class ContactEngine(object):
                 buf["d_cnt"] = torch.empty(buf["cap"], dtype=torch.int32, device=self.device)
                 buf["h_idx"] = torch.empty(buf["cap"], dtype=torch.int64, pin_memory=True)
                 buf["h_cnt"] = torch.empty(buf["cap"], dtype=torch.int32, pin_memory=True)
-            self._check(self._L.cmb_unpack_sorted(self._ctx, _ptr(buf["d_packed"]), _ptr(buf["d_n"]), buf["cap"], 0,
+            self._check(self._L.cmb_unpack_sorted(self._ctx, _ptr(buf["d_packed"]), _ptr(buf["d_n"]), cap, 0,
                                                   _ptr(buf["d_idx"]), _ptr(buf["d_cnt"]), _stream_ptr(self.device)),
                         "cmb_unpack_sorted")
             # (the capacity is the previous entry count + 25 %: copying all of it costs less than a
             # second synchronisation to learn the exact count first)
-            k = min(buf["cap"], cap)
-            buf["h_idx"][:k].copy_(buf["d_idx"][:k], non_blocking=True)
-            buf["h_cnt"][:k].copy_(buf["d_cnt"][:k], non_blocking=True)
+            buf["h_idx"][:cap].copy_(buf["d_idx"][:cap], non_blocking=True)
+            buf["h_cnt"][:cap].copy_(buf["d_cnt"][:cap], non_blocking=True)
         return buf
 
     def _export_unpacked(self, table):
