@@ -73,6 +73,7 @@ struct cmb_ctx {
     VlScratch vl[2];
     int* d_res_anchor = nullptr;              // [n_res_c] first used atom of each compact residue
     int verlet = 1;                           // 0 off, 1 when the batch is long enough, 2 always
+    int verlet_graph = 1;                     // replay the list builder as one CUDA graph (0: plain launches)
     int verlet_audit = 0;                     // run the exact arithmetic on every listed pair and count disagreements
     int verlet_max_rlist_pct = 175;           // lists with r_list above this percentage of the cutoff are not built
     unsigned long long* d_vl_audit = nullptr; // [2] audited pairs, disagreements
@@ -282,6 +283,7 @@ extern "C" int cmb_set_option(cmb_ctx* ctx, const char* name, int64_t value)
         return CMB_OK;
     }
     if (!strcmp(name, "verlet_audit")) { ctx->verlet_audit = value != 0; return CMB_OK; }
+    if (!strcmp(name, "verlet_graph")) { ctx->verlet_graph = value != 0; return CMB_OK; }
     if (!strcmp(name, "time_kernels")) { ctx->time_kernels = value != 0; ctx->kernel_events_used = 0; return CMB_OK; }
     if (!strcmp(name, "stage_trace")) { ctx->stage_trace = value != 0; ctx->trace_used = 0; return CMB_OK; }
     if (!strcmp(name, "prune")) { ctx->prune = value != 0; return CMB_OK; }
@@ -311,6 +313,7 @@ extern "C" int cmb_get_stat(cmb_ctx* ctx, const char* name, int64_t* value)
     if (!strcmp(name, "max_cells")) { *value = ctx->fs_maxc; return CMB_OK; }
     if (!strcmp(name, "kernel_launches")) { *value = ctx->stats["kernel_launches"]; return CMB_OK; }
     if (!strcmp(name, "vl_used")) { *value = ctx->last_used_verlet; return CMB_OK; }
+    if (!strcmp(name, "vl_graph_state")) { *value = ctx->vl[ctx->last_vl_slot].graph_state; return CMB_OK; }
     if (!strcmp(name, "vl_frames_timed")) { *value = (int64_t)ctx->kernel_events_used; return CMB_OK; }
     if (!strcmp(name, "vl_frames_ns")) {
         // total duration of the frame-kernel launches timed since the last read (synchronises, resets)
@@ -700,7 +703,7 @@ static int launch_frames(cmb_ctx* ctx, const FrameJob& job, int slot, cudaStream
                     if (ctx->vl_walked_set[lx][t]) CK(cudaStreamWaitEvent(stream, ctx->vl_walked[lx][t], 0));
                 for (int attempt = 0; attempt < 2; attempt++) {
                     vj.conservative_tiles = ctx->vl_conservative;
-                    rc = vl_build(vj, V, stream, err, launches);
+                    rc = vl_build(vj, V, stream, err, launches, ctx->verlet_graph != 0);
                     if (rc != 0 || ctx->path == 0 || ctx->vl_conservative) break;
                     // lists of several tiles: a tile that overflowed the frame kernel's shared memory
                     // with the optimistic tile size gets the list rebuilt with the pessimistic one

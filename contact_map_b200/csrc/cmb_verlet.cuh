@@ -182,6 +182,14 @@ struct VlScratch {
     size_t cub_bytes = 0;
     cudaStream_t aux = nullptr;     // the builder's second stream (vl_build: fork after sort 1, join before vl_fill)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // the builder as ONE graph launch (vl_build): per-call arguments in device memory, the launch
+    // sequence captured once per set of fixed arguments on the builder's own stream
+    void* d_args = nullptr;         // VlBuildArgs
+    cudaStream_t bs = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    unsigned char gkey[64] = {0};   // VlGraphKey of gexec
+    int graph_state = 0;            // 0 not captured yet, 1 usable, -1 capture failed once: plain launches from then on
 };
 
 inline void vl_free(VlScratch& S)
@@ -198,7 +206,11 @@ inline void vl_free(VlScratch& S)
     }
     cudaFree(S.seg_key); cudaFree(S.seg_len); cudaFree(S.seg_start); cudaFree(S.n_runs); cudaFree(S.slot_uniq);
     cudaFree(S.tile_seg0); cudaFree(S.tile_bundle0); cudaFree(S.tile_slot0); cudaFree(S.bundle_row0);
-    cudaFree(S.cub_tmp); cudaFree(S.cub_tmp2);
+    cudaFree(S.cub_tmp); cudaFree(S.cub_tmp2); cudaFree(S.d_args);
+    if (S.gexec) cudaGraphExecDestroy(S.gexec);
+    if (S.bs) cudaStreamDestroy(S.bs);
+    if (S.ev_in) cudaEventDestroy(S.ev_in);
+    if (S.ev_out) cudaEventDestroy(S.ev_out);
     if (S.aux) cudaStreamDestroy(S.aux);
     if (S.ev_fork) cudaEventDestroy(S.ev_fork);
     if (S.ev_join) cudaEventDestroy(S.ev_join);
@@ -281,9 +293,20 @@ __device__ __forceinline__ void vl_reds_or(unsigned* addr, unsigned v)
 }
 
 // ----- builder kernels --------------------------------------------------------------------
-__global__ void vl_init(VlHeader* hdr, const float* box, int periodic, int rbits, int abits)
+// What changes from one build to the next.  It lives in device memory (copied ahead of the build) so
+// that every launch of the builder has the SAME arguments and the whole builder can be replayed as
+// one CUDA graph (vl_build).
+struct VlBuildArgs {
+    const float* xyz;          // [n_frames][n][3]
+    const float* box;          // [n_frames][9] or nullptr
+    long long n_frames;
+};
+
+__global__ void vl_init(VlHeader* hdr, const VlBuildArgs* __restrict__ args, int rbits, int abits)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const float* box = args->box;
+    const int periodic = box != nullptr;
     VlHeader& H = *hdr;
     H.valid = 1; H.fail_code = 0;
     H.n_tiles = H.n_entries = H.n_segs = H.n_lists = H.n_slots = H.n_bundles = H.n_rows = 0;
@@ -301,12 +324,14 @@ __global__ void vl_init(VlHeader* hdr, const float* box, int periodic, int rbits
 // Reference positions: mean over the sample frames (each unwrapped next to the first sample),
 // largest displacement of a sample from the mean, largest |raw coordinate|, bounding box.
 // 16 lanes per atom (lane = sample), 8 atoms per block.
-__global__ void __launch_bounds__(128) vl_sample(VlHeader* hdr, const float* __restrict__ xyz,
-                                                 const float* __restrict__ box, long long n_frames, int n,
+__global__ void __launch_bounds__(128) vl_sample(VlHeader* hdr, const VlBuildArgs* __restrict__ args, int n,
                                                  float4* __restrict__ ref_raw)
 {
     __shared__ double hs[18];
     __shared__ int box_ok;
+    const float* __restrict__ xyz = args->xyz;
+    const float* __restrict__ box = args->box;
+    const long long n_frames = args->n_frames;
     const int n_samp = (int)(n_frames < VL_SAMPLES ? n_frames : VL_SAMPLES);
     if (threadIdx.x < 18) hs[threadIdx.x] = threadIdx.x < 9 ? hdr->hinv[threadIdx.x] : hdr->h[threadIdx.x - 9];
     if (threadIdx.x == 0) {
@@ -378,10 +403,11 @@ __global__ void __launch_bounds__(128) vl_sample(VlHeader* hdr, const float* __r
 }
 
 // skin, list radius, error bound, list grid, tiling (one thread)
-__global__ void vl_setup(VlHeader* hdr, const float* box, int n, float cutoff, float c2, float max_rlist_factor,
-                         int conservative_tiles)
+__global__ void vl_setup(VlHeader* hdr, const VlBuildArgs* __restrict__ args, int n, float cutoff, float c2,
+                         float max_rlist_factor, int conservative_tiles)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const float* box = args->box;
     VlHeader& H = *hdr;
     if (!H.valid) return;
     const float dmax = __uint_as_float(H.d_max_bits), amax = __uint_as_float(H.a_max_bits);
@@ -1605,6 +1631,10 @@ inline int vl_ensure(VlScratch& S, int n, int n_res_c, std::string& err)
         VL_CK(cudaMalloc(&S.cub_tmp, need + 256));
         VL_CK(cudaMalloc(&S.cub_tmp2, need + 256));
         S.cub_bytes = need + 256;
+        VL_CK(cudaMalloc(&S.d_args, 64));
+        VL_CK(cudaStreamCreateWithFlags(&S.bs, cudaStreamNonBlocking));
+        VL_CK(cudaEventCreateWithFlags(&S.ev_in, cudaEventDisableTiming));
+        VL_CK(cudaEventCreateWithFlags(&S.ev_out, cudaEventDisableTiming));
         VL_CK(cudaStreamCreateWithFlags(&S.aux, cudaStreamNonBlocking));
         VL_CK(cudaEventCreateWithFlags(&S.ev_fork, cudaEventDisableTiming));
         VL_CK(cudaEventCreateWithFlags(&S.ev_join, cudaEventDisableTiming));
@@ -1613,19 +1643,19 @@ inline int vl_ensure(VlScratch& S, int n, int n_res_c, std::string& err)
     return 0;
 }
 
-// Build the list of a batch (asynchronous, everything stays on the device).
-inline int vl_build(const VlJob& job, VlScratch& S, cudaStream_t st, std::string& err, int& launches)
+// The launch sequence of the builder on stream `st` (per-call arguments: S.d_args).
+inline int vl_build_body(const VlJob& job, VlScratch& S, cudaStream_t st, std::string& err, int& launches)
 {
     const int n = job.n;
     const long long E = S.entry_cap;
-    const int periodic = job.box != nullptr;
+    const VlBuildArgs* args = reinterpret_cast<const VlBuildArgs*>(S.d_args);
     const bool single = n <= VL_SINGLE_TILE_ATOMS;
     // sort keys only carry the bits their fields need (fewer radix passes); the all-ones padding
     // still sorts last: no live key has all of its compared bits set
     const int rbits = vl_bits(job.n_res_c + 1), abits = vl_bits(n + 1), tbits = single ? 0 : 12;
-    vl_init<<<1, 1, 0, st>>>(S.L.hdr, job.box, periodic, rbits, abits);
-    vl_sample<<<(n + 7) / 8, 128, 0, st>>>(S.L.hdr, job.xyz, job.box, job.n_frames, n, S.ref_raw);
-    vl_setup<<<1, 1, 0, st>>>(S.L.hdr, job.box, n, job.cutoff, job.c2, job.max_rlist_factor, job.conservative_tiles);
+    vl_init<<<1, 1, 0, st>>>(S.L.hdr, args, rbits, abits);
+    vl_sample<<<(n + 7) / 8, 128, 0, st>>>(S.L.hdr, args, n, S.ref_raw);
+    vl_setup<<<1, 1, 0, st>>>(S.L.hdr, args, n, job.cutoff, job.c2, job.max_rlist_factor, job.conservative_tiles);
     vl_zero_cells<<<64, 256, 0, st>>>(S.L.hdr, S.cellcnt);
     vl_bin<<<(n + 255) / 256, 256, 0, st>>>(S.L.hdr, n, S.ref_raw, S.ref_w, S.atomrank, S.cellcnt);
     vl_scan_cells<<<1, 1024, 0, st>>>(S.L.hdr, S.cellcnt, S.cellptr, n);
@@ -1700,6 +1730,72 @@ inline int vl_build(const VlJob& job, VlScratch& S, cudaStream_t st, std::string
     VL_CK(cudaGetLastError());
     launches += 32;
     return 0;
+}
+
+// everything a captured builder graph has baked in
+struct VlGraphKey {
+    int n, n_res_c, n_ignored, conservative_tiles;
+    float cutoff, c2, max_rlist_factor;
+    const void* meta; const void* res_anchor;
+    long long entry_cap;
+};
+static_assert(sizeof(VlGraphKey) <= 64, "VlScratch::gkey");
+
+// Build the list of a batch (asynchronous, everything stays on the device).  The builder is ~35
+// small dependent launches: issued one by one they cost the host 4-10 us each (more than the
+// kernels take on a busy host, several times more while a host-to-device copy saturates the link),
+// so the sequence is captured ONCE per system into a CUDA graph on the builder's own stream (the
+// caller's may be the legacy default stream, which cannot be captured) and replayed with one launch;
+// what differs between builds is read from S.d_args.  If capturing fails the launches are issued
+// directly, as before.
+inline int vl_build(const VlJob& job, VlScratch& S, cudaStream_t st, std::string& err, int& launches, bool use_graph = true)
+{
+    VlBuildArgs a;
+    a.xyz = job.xyz; a.box = job.box; a.n_frames = job.n_frames;
+    if (use_graph && S.graph_state >= 0) {
+        VlGraphKey key;
+        memset(&key, 0, sizeof(key));
+        key.n = job.n; key.n_res_c = job.n_res_c; key.n_ignored = job.n_ignored; key.conservative_tiles = job.conservative_tiles;
+        key.cutoff = job.cutoff; key.c2 = job.c2; key.max_rlist_factor = job.max_rlist_factor;
+        key.meta = job.meta; key.res_anchor = job.res_anchor; key.entry_cap = S.entry_cap;
+        VL_CK(cudaEventRecord(S.ev_in, st));
+        VL_CK(cudaStreamWaitEvent(S.bs, S.ev_in, 0));
+        // (pageable source: the driver has taken its copy of `a` when the call returns)
+        VL_CK(cudaMemcpyAsync(S.d_args, &a, sizeof(a), cudaMemcpyHostToDevice, S.bs));
+        if (S.gexec == nullptr || memcmp(&key, S.gkey, sizeof(key)) != 0) {
+            if (S.gexec) { cudaGraphExecDestroy(S.gexec); S.gexec = nullptr; }
+            cudaGraph_t graph = nullptr;
+            int dummy = 0;
+            std::string cerr;
+            bool ok = cudaStreamBeginCapture(S.bs, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (ok) {
+                ok = vl_build_body(job, S, S.bs, cerr, dummy) == 0;
+                ok = (cudaStreamEndCapture(S.bs, &graph) == cudaSuccess) && ok && graph != nullptr;
+            }
+            if (ok) ok = cudaGraphInstantiate(&S.gexec, graph, 0) == cudaSuccess;
+            if (graph) cudaGraphDestroy(graph);
+            if (!ok) {
+                cudaGetLastError();
+                if (S.gexec) { cudaGraphExecDestroy(S.gexec); S.gexec = nullptr; }
+                S.graph_state = -1;
+            } else {
+                memcpy(S.gkey, &key, sizeof(key));
+                S.graph_state = 1;
+            }
+        }
+        if (S.graph_state == 1) {
+            VL_CK(cudaGraphLaunch(S.gexec, S.bs));
+            VL_CK(cudaEventRecord(S.ev_out, S.bs));
+            VL_CK(cudaStreamWaitEvent(st, S.ev_out, 0));
+            launches += 32;
+            return 0;
+        }
+        // capture failed: the argument copy below is ordered behind the one queued on S.bs
+        VL_CK(cudaEventRecord(S.ev_out, S.bs));
+        VL_CK(cudaStreamWaitEvent(st, S.ev_out, 0));
+    }
+    VL_CK(cudaMemcpyAsync(S.d_args, &a, sizeof(a), cudaMemcpyHostToDevice, st));
+    return vl_build_body(job, S, st, err, launches);
 }
 
 // Walk a list over the frames of the job; frames that cannot use it end up on R.tripped (count in

@@ -343,3 +343,24 @@ def test_streamed_host_schedule_head_and_tail_chunks(engine):
         assert engine.get_stat("vl_used") == 1
         assert torch.equal(host_a, dev_a) and torch.equal(host_r, dev_r)
     assert len(want) >= 5 and want[0] < want[1] and want[-1] < want[-2] + want[-1]
+
+
+def test_builder_graph_equals_plain_launches(engine):
+    """The list builder replayed as one CUDA graph (default) against the same launches issued one
+    by one: identical tables, on a single-tile and on a many-tile system, across repeated calls
+    with different batches (the per-call arguments are read from device memory) and after a change
+    of system (the graph is captured again)."""
+    for system, frames in ((synth.kras_like(), 300), (synth.solvated_triclinic(n_atoms=7000, lattice=20), 40)):
+        res, chain, role = system_arrays(system)
+        engine.set_system(res, chain, role, 0.45, 2)
+        for f0 in (0, 1000):
+            xyz, box = _dev(engine, system, f0, frames)
+            engine.set_option("verlet_graph", 0)
+            try:
+                plain_a, plain_r, st0 = _accumulate(engine, xyz, box, 2)
+            finally:
+                engine.set_option("verlet_graph", 1)
+            graph_a, graph_r, st1 = _accumulate(engine, xyz, box, 2)
+            assert st0["vl_valid"] == 1 and st1["vl_valid"] == 1 and st0["vl_entries"] == st1["vl_entries"]
+            assert engine.get_stat("vl_graph_state") == 1
+            assert torch.equal(plain_a, graph_a) and torch.equal(plain_r, graph_r)
