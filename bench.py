@@ -423,6 +423,8 @@ def extra_legs(engine, fp32_peak, budget_s=150.0):
         n_diff = len(diff.atom_contacts.counter)
         t2 = time.perf_counter()
         legs[name + "_api_host"] = {"frames": F, "ContactTrajectory_frames_per_s": F / (t1 - t0),
+                                    "graph_captures": engine.get_stat("vl_graph_captures"),
+                                    "graph_capture_ms": engine.get_stat("vl_graph_capture_us") * 1e-3,
                                     "two_ContactFrequency_plus_ContactDifference_s": t2 - t1,
                                     "difference_pairs": n_diff, "frames_in_trajectory": len(ct)}
         del xyz, box, h_xyz, h_box, traj, ct

@@ -314,6 +314,8 @@ extern "C" int cmb_get_stat(cmb_ctx* ctx, const char* name, int64_t* value)
     if (!strcmp(name, "kernel_launches")) { *value = ctx->stats["kernel_launches"]; return CMB_OK; }
     if (!strcmp(name, "vl_used")) { *value = ctx->last_used_verlet; return CMB_OK; }
     if (!strcmp(name, "vl_graph_state")) { *value = ctx->vl[ctx->last_vl_slot].graph_state; return CMB_OK; }
+    if (!strcmp(name, "vl_graph_captures")) { *value = ctx->vl[0].captures + ctx->vl[1].captures; return CMB_OK; }
+    if (!strcmp(name, "vl_graph_capture_us")) { *value = ctx->vl[0].capture_us + ctx->vl[1].capture_us; return CMB_OK; }
     if (!strcmp(name, "vl_frames_timed")) { *value = (int64_t)ctx->kernel_events_used; return CMB_OK; }
     if (!strcmp(name, "vl_frames_ns")) {
         // total duration of the frame-kernel launches timed since the last read (synchronises, resets)

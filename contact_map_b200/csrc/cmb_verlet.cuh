@@ -64,6 +64,8 @@
 #pragma once
 #include <cub/cub.cuh>
 
+#include <chrono>
+#include <cstring>
 #include <string>
 
 #include "cmb_cells.cuh"
@@ -190,6 +192,7 @@ struct VlScratch {
     cudaGraphExec_t gexec = nullptr;
     unsigned char gkey[64] = {0};   // VlGraphKey of gexec
     int graph_state = 0;            // 0 not captured yet, 1 usable, -1 capture failed once: plain launches from then on
+    long long captures = 0, capture_us = 0;   // diagnostics: graphs captured, host time spent capturing + instantiating
 };
 
 inline void vl_free(VlScratch& S)
@@ -1564,10 +1567,13 @@ inline int vl_run_ensure(VlRun& R, long long n_frames, std::string& err)
     return 0;
 }
 
-inline int vl_ensure(VlScratch& S, int n, int n_res_c, std::string& err)
+inline int vl_ensure(VlScratch& S, int n_atoms, int n_res_c, std::string& err)
 {
-    if (S.cap_atoms < n) {
+    if (S.cap_atoms < n_atoms) {
         vl_free(S);
+        // (sized with head room: re-allocating ~60 buffers, three streams and the builder graph for a
+        // system that is a few atoms larger than the last one costs 30 - 150 ms)
+        const int n = (int)std::min<long long>(std::max<long long>(4096, (long long)n_atoms + n_atoms / 4), 0x3fffffff);
         const long long E = std::max<long long>((long long)n * 80, 1 << 15);
         if (2 * E + n > 0x7fffffffll) { err = "system too large for the pair-list path"; return -4; }
         S.entry_cap = E;
@@ -1647,7 +1653,9 @@ inline int vl_ensure(VlScratch& S, int n, int n_res_c, std::string& err)
 inline int vl_build_body(const VlJob& job, VlScratch& S, cudaStream_t st, std::string& err, int& launches)
 {
     const int n = job.n;
-    const long long E = S.entry_cap;
+    // (the scratch is allocated with head room; the capacity-sized sorts and scans only cover what a
+    // system of this size can need)
+    const long long E = std::min<long long>(S.entry_cap, std::max<long long>((long long)n * 80, 1 << 15));
     const VlBuildArgs* args = reinterpret_cast<const VlBuildArgs*>(S.d_args);
     const bool single = n <= VL_SINGLE_TILE_ATOMS;
     // sort keys only carry the bits their fields need (fewer radix passes); the all-ones padding
@@ -1763,6 +1771,7 @@ inline int vl_build(const VlJob& job, VlScratch& S, cudaStream_t st, std::string
         // (pageable source: the driver has taken its copy of `a` when the call returns)
         VL_CK(cudaMemcpyAsync(S.d_args, &a, sizeof(a), cudaMemcpyHostToDevice, S.bs));
         if (S.gexec == nullptr || memcmp(&key, S.gkey, sizeof(key)) != 0) {
+            const auto t_capture = std::chrono::steady_clock::now();
             if (S.gexec) { cudaGraphExecDestroy(S.gexec); S.gexec = nullptr; }
             cudaGraph_t graph = nullptr;
             int dummy = 0;
@@ -1782,6 +1791,8 @@ inline int vl_build(const VlJob& job, VlScratch& S, cudaStream_t st, std::string
                 memcpy(S.gkey, &key, sizeof(key));
                 S.graph_state = 1;
             }
+            S.captures++;
+            S.capture_us += std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_capture).count();
         }
         if (S.graph_state == 1) {
             VL_CK(cudaGraphLaunch(S.gexec, S.bs));
