@@ -88,7 +88,7 @@ struct cmb_ctx {
     bool vl_walked_set[2][2] = {{false, false}, {false, false}};
     cudaEvent_t vl_info_ready[2] = {nullptr, nullptr};       // read-back of slot s's walk has landed
     // the large path's fall back of a streamed chunk is finished when its stream slot comes round again
-    struct Pending { bool active = false; bool info = false; FrameJob job; cudaStream_t stream = nullptr; int list = 0; } pending[2];
+    struct Pending { bool active = false; bool info = false; bool built = false; FrameJob job; cudaStream_t stream = nullptr; int list = 0; } pending[2];
 
     // host pipeline
     float* d_stage_xyz[2] = {nullptr, nullptr};
@@ -616,6 +616,15 @@ static int finish_pending(cmb_ctx* ctx, int slot)
     CK(cudaEventSynchronize(ctx->vl_info_ready[slot]));
     const int n_trip = R.h_info[0];
     if (P.job.shared_list && n_trip * 8 > P.job.n_frames) ctx->vl_shared_stale = 1;
+    if (P.built && !ctx->vl_conservative && R.h_info[1] == 0 && R.h_info[2] >= 9 && R.h_info[2] <= 13) {
+        // the list this chunk built overflowed a tile with the optimistic tile size (its frames all
+        // came back on the fall-back list): the next chunk rebuilds it with the pessimistic one
+        ctx->vl_conservative = 1;
+        ctx->vl_shared_stale = 1;
+        ctx->stats["vl_rebuilds"] += 1;
+        ctx->stats["vl_rebuild_code"] = R.h_info[2];
+    }
+    P.built = false;
     if (n_trip == 0) return CMB_OK;
     std::vector<int> trip((size_t)n_trip);
     CK(cudaMemcpy(trip.data(), R.tripped, sizeof(int) * (size_t)n_trip, cudaMemcpyDeviceToHost));
@@ -655,6 +664,7 @@ static int launch_frames(cmb_ctx* ctx, const FrameJob& job, int slot, cudaStream
     //      unusable) come back on a device-side list and run through the cell kernels below --------
     const int* frame_list = nullptr;
     const int* frame_count = nullptr;
+    bool built_unchecked = false;          // a list was built and its validity has not been looked at yet
     ctx->last_used_verlet = 0;
     {
         const bool plain = !job.atom_keys && !job.res_keys && job.boundary_ulps == 0 && !ctx->count_tests &&
@@ -711,6 +721,13 @@ static int launch_frames(cmb_ctx* ctx, const FrameJob& job, int slot, cudaStream
                     // with the optimistic tile size gets the list rebuilt with the pessimistic one
                     CK(cudaMemcpyAsync(R.h_info + 1, &V.L.hdr->valid, sizeof(int), cudaMemcpyDeviceToHost, stream));
                     CK(cudaMemcpyAsync(R.h_info + 2, &V.L.hdr->fail_code, sizeof(int), cudaMemcpyDeviceToHost, stream));
+                    if (job.shared_list && defer_fallback) {
+                        // streamed trajectory: never wait for the device here (the copy of the next
+                        // chunk would be issued late); an overflowing list sends all its frames to the
+                        // fall back, and finish_pending() switches the tile size for the next build
+                        built_unchecked = true;
+                        break;
+                    }
                     CK(cudaStreamSynchronize(stream));
                     if (R.h_info[1] != 0 || R.h_info[2] < 9 || R.h_info[2] > 13) break;
                     ctx->vl_conservative = 1;
@@ -784,7 +801,7 @@ static int launch_frames(cmb_ctx* ctx, const FrameJob& job, int slot, cudaStream
         cmb_ctx::Pending& P = ctx->pending[slot];
         CK(cudaMemcpyAsync(ctx->vl_run[slot].h_info, frame_count, sizeof(int), cudaMemcpyDeviceToHost, stream));
         CK(cudaEventRecord(ctx->vl_info_ready[slot], stream));
-        P.active = true; P.job = job; P.stream = stream;
+        P.active = true; P.job = job; P.stream = stream; P.built = built_unchecked;
         return defer_fallback ? CMB_OK : finish_pending(ctx, slot);
     }
     std::vector<std::pair<long long, long long>> runs;
@@ -868,16 +885,19 @@ static int64_t pick_chunk(const cmb_ctx* ctx, int64_t n_frames, int64_t chunk_fr
 static std::vector<int64_t> chunk_schedule(const cmb_ctx* ctx, int64_t n_frames, int64_t chunk_frames, bool automatic)
 {
     std::vector<int64_t> sizes;
+    // fewest frames worth a chunk of their own: the fused kernels parallelise over frames, the
+    // global-memory sizes over tiles x frames (and their list build outlasts the copy of a small chunk)
     const int64_t fill = (int64_t)ctx->sm_count * std::max(1, ctx->fs_ctas_per_sm) * 2;
+    const bool large = ctx->path == 1;
     int64_t f0 = 0;
     if (automatic && n_frames >= 3 * chunk_frames) {
-        const int64_t head = std::max<int64_t>(fill, chunk_frames / 4);
+        const int64_t head = large ? 32 : std::max<int64_t>(fill, chunk_frames / 4);
         if (chunk_frames >= 2 * head) { sizes.push_back(head); f0 = head; }
     }
     for (; f0 < n_frames; f0 += chunk_frames) sizes.push_back(std::min<int64_t>(chunk_frames, n_frames - f0));
     if (automatic && sizes.size() >= 2) {
         const int64_t last = sizes.back();
-        const int64_t tail = std::max<int64_t>(fill, last / 4);
+        const int64_t tail = std::max<int64_t>(large ? 32 : fill, last / 4);
         if (last >= 2 * tail) {
             sizes.back() = last - tail;
             sizes.push_back(tail);

@@ -1,7 +1,7 @@
 """Timeline of one streamed host call (option stage_trace): when the copy and the kernels of every
 chunk finish, relative to the first copy being issued.
 
-    python tools/e2e_trace.py [chunk_frames ...]
+    python tools/e2e_trace.py [s1|s3] [chunk_frames ...]
 """
 import os, sys, time, warnings
 import numpy as np, torch
@@ -9,7 +9,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from contact_map_b200 import synth
 from contact_map_b200.engine import get_engine
 warnings.simplefilter("ignore")
-system = synth.kras_like(); top = system.topology; n = top.n_atoms; F = 10000
+which = "s1"
+if len(sys.argv) > 1 and sys.argv[1] in ("s1", "s3"):
+    which = sys.argv.pop(1)
+system = synth.kras_like() if which == "s1" else synth.solvated_triclinic(n_atoms=100000)
+top = system.topology; n = top.n_atoms; F = 10000 if which == "s1" else 2048
 engine = get_engine(0); dev = engine.device
 atom_res, atom_chain = top.atom_residue_chain()
 engine.set_system(atom_res, atom_chain, np.full(n, 3, np.uint8), 0.45, 2)
@@ -32,6 +36,6 @@ for chunk in [int(a) for a in sys.argv[1:]] or [0, 5000, 1250]:
     k = engine.get_stat("trace_chunks")
     print("chunk_frames %d: host call %.3f ms, frame kernels %.3f ms in %d launches" %
           (chunk, dt * 1e3, engine.get_stat("vl_frames_ns") * 1e-6, k))
-    for c in range(k):
+    for c in (range(k) if k <= 12 else list(range(6)) + list(range(k - 4, k))):
         print("   chunk %d: copy issued+done at %.3f ms, kernels done at %.3f ms" %
               (c, engine.get_stat("trace_copy_%d" % c) * 1e-6, engine.get_stat("trace_done_%d" % c) * 1e-6))
