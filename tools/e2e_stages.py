@@ -8,7 +8,9 @@ from contact_map_b200 import synth, parallel
 from contact_map_b200.engine import get_engine
 from contact_map_b200.contact_map import _engine_system, _split_trajectory, _used_coordinates, _exports_to_pairs, ContactObject
 warnings.simplefilter("ignore")
-system = synth.kras_like(); top = system.topology; n = top.n_atoms; F = 10000
+which = sys.argv[1] if len(sys.argv) > 1 else "s1"
+system = synth.kras_like() if which == "s1" else synth.solvated_triclinic(n_atoms=100000)
+top = system.topology; n = top.n_atoms; F = 10000 if which == "s1" else 4096
 engine = get_engine(0); dev = engine.device
 atom_res, atom_chain = top.atom_residue_chain()
 engine.set_system(atom_res, atom_chain, np.full(n, 3, np.uint8), 0.45, 2)
@@ -25,7 +27,7 @@ for _ in range(3):
 acc = {}
 def lap(name, t0):
     t = time.perf_counter(); acc[name] = acc.get(name, 0.0) + (t - t0); return t
-R = 10
+R = 10 if which == "s1" else 3
 for _ in range(R):
     torch.cuda.synchronize()
     t = time.perf_counter()
@@ -38,8 +40,9 @@ for _ in range(R):
     a, r = engine.new_tables(); t = lap("new_tables", t)
     nf = parallel.reduce_frame_count(xyz.shape[0], engine.device); t = lap("reduce_frame_count", t)
     engine.accumulate_host(xyz, box, a, r); t = lap("accumulate_host", t)
-    ex = parallel.reduce_export(engine, [a, r], dst=0); t = lap("reduce_export", t)
-    pairs = _exports_to_pairs(engine, ex, used); t = lap("_exports_to_pairs", t)
+    from contact_map_b200.contact_map import _tables_to_pairs
+    pairs = _tables_to_pairs(engine, a, r, used); t = lap("_tables_to_pairs", t)
+    del a, r, pairs; t = lap("free", t)
     torch.cuda.synchronize(); t = lap("final sync", t)
 tot = 0.0
 for k, v in acc.items():
