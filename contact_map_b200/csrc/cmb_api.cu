@@ -76,6 +76,8 @@ struct cmb_ctx {
     int verlet_graph = 1;                     // replay the list builder as one CUDA graph (0: plain launches)
     int verlet_audit = 0;                     // run the exact arithmetic on every listed pair and count disagreements
     int verlet_max_rlist_pct = 175;           // lists with r_list above this percentage of the cutoff are not built
+    int verlet_tile_share_pct = 60;           // optimistic tile sizing: share of the shell atoms counted as slots (tests lower it
+                                              // to provoke the overflow -> pessimistic rebuild path)
     unsigned long long* d_vl_audit = nullptr; // [2] audited pairs, disagreements
     int last_used_verlet = 0;
     int last_vl_slot = 0;
@@ -284,6 +286,11 @@ extern "C" int cmb_set_option(cmb_ctx* ctx, const char* name, int64_t value)
     }
     if (!strcmp(name, "verlet_audit")) { ctx->verlet_audit = value != 0; return CMB_OK; }
     if (!strcmp(name, "verlet_graph")) { ctx->verlet_graph = value != 0; return CMB_OK; }
+    if (!strcmp(name, "verlet_tile_share_pct")) {
+        if (value < 0 || value > 100) return fail(ctx, CMB_ERR_ARG, "verlet_tile_share_pct out of range");
+        ctx->verlet_tile_share_pct = (int)value;
+        return CMB_OK;
+    }
     if (!strcmp(name, "time_kernels")) { ctx->time_kernels = value != 0; ctx->kernel_events_used = 0; return CMB_OK; }
     if (!strcmp(name, "stage_trace")) { ctx->stage_trace = value != 0; ctx->trace_used = 0; return CMB_OK; }
     if (!strcmp(name, "prune")) { ctx->prune = value != 0; return CMB_OK; }
@@ -707,6 +714,7 @@ static int launch_frames(cmb_ctx* ctx, const FrameJob& job, int slot, cudaStream
             vj.n_ignored = ctx->n_ignored; vj.atom_table = job.atom_table; vj.res_table = job.res_table;
             vj.audit = ctx->verlet_audit; vj.d_audit = ctx->d_vl_audit;
             vj.max_rlist_factor = 0.01f * (float)ctx->verlet_max_rlist_pct;
+            vj.tile_share = 0.01f * (float)ctx->verlet_tile_share_pct;
             if (ctx->time_kernels && timing_pair(ctx->kernel_events, ctx->kernel_events_used, &vj.t_begin, &vj.t_end) != 0)
                 return fail(ctx, CMB_ERR_CUDA, "cudaEventCreate failed");
             if (build) {

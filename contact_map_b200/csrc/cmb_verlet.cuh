@@ -525,6 +525,75 @@ __global__ void __launch_bounds__(1024) vl_scan_cells(const VlHeader* hdr, const
     if (threadIdx.x == 0) cellptr[ncell] = n;
 }
 
+// Tile edge from the ACTUAL occupancy of the list cells (lists of several tiles; vl_setup's choice
+// from the average density stands for systems that fill their cell evenly and is replaced here).
+// For every candidate edge t, largest first, every tile's slots are estimated as its own atoms plus a
+// share of the atoms in the one-cell shell around it -- a pair belongs to the tile of its lower
+// residue, so about half of the shell shows up as partners (0.6 with allowance; the pessimistic
+// rebuild after an overflow counts the whole shell) -- and the largest t whose FULLEST tile fits the
+// frame kernel's shared memory is taken.  A protein in vacuum or a membrane slab no longer gets the
+// tile size of its average density.
+__global__ void __launch_bounds__(1024) vl_pick_tiles(VlHeader* hdr, const int* __restrict__ cellptr, int n,
+                                                      int conservative_tiles, float optimistic_share)
+{
+    if (!hdr->valid || n <= VL_SINGLE_TILE_ATOMS) return;
+    __shared__ int s_max, s_pick;
+    const GridS& G = hdr->grid;
+    const int nx = G.nx, ny = G.ny, nz = G.nz, periodic = G.periodic;
+    const float share = conservative_tiles ? 1.0f : optimistic_share;
+    if (threadIdx.x == 0) s_pick = 0;
+    for (int t = 6; t >= 1; t--) {
+        const int ntx = (nx + t - 1) / t, nty = (ny + t - 1) / t, ntz = (nz + t - 1) / t;
+        const long long nt = (long long)ntx * nty * ntz;
+        const bool feasible = nt <= VL_MAX_TILES;
+        if (threadIdx.x == 0) s_max = 0;
+        __syncthreads();
+        if (feasible) {
+            float worst = 0.f;
+            for (int tile = threadIdx.x; tile < (int)nt; tile += 1024) {
+                const int tyz = tile / ntx, tx = tile - tyz * ntx, tz = tyz / nty, ty = tyz - tz * nty;
+                const int x0 = tx * t, x1 = min(x0 + t, nx), y0 = ty * t, y1 = min(y0 + t, ny), z0 = tz * t,
+                          z1 = min(z0 + t, nz);
+                int own = 0, all = 0;
+                for (int z = z0 - 1; z <= z1; z++) {
+                    if (!periodic && (z < 0 || z >= nz)) continue;
+                    const int cz = (z + nz) % nz;
+                    for (int y = y0 - 1; y <= y1; y++) {
+                        if (!periodic && (y < 0 || y >= ny)) continue;
+                        const int cy = (y + ny) % ny;
+                        for (int x = x0 - 1; x <= x1; x++) {
+                            if (!periodic && (x < 0 || x >= nx)) continue;
+                            const int c = (cz * ny + cy) * nx + (x + nx) % nx;
+                            const int cnt = cellptr[c + 1] - cellptr[c];
+                            all += cnt;
+                            if (z >= z0 && z < z1 && y >= y0 && y < y1 && x >= x0 && x < x1) own += cnt;
+                        }
+                    }
+                }
+                worst = fmaxf(worst, (float)own + share * (float)(all - own));
+            }
+            atomicMax(&s_max, (int)(worst * 1.05f) + 1);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && feasible) {
+            const float est = (float)s_max;
+            // (rows: ~ 0.19 per slot of such a tile, as in vl_setup)
+            if (est <= (float)VL_MAX_SLOTS && (conservative_tiles || est * 0.19f <= (float)VL_MAX_ROWS)) s_pick = t;
+        }
+        __syncthreads();
+        if (s_pick) break;
+    }
+    if (threadIdx.x == 0) {
+        VlHeader& H = *hdr;
+        const int t = s_pick ? s_pick : 1;
+        H.tdim = t;
+        H.ntx = (nx + t - 1) / t; H.nty = (ny + t - 1) / t; H.ntz = (nz + t - 1) / t;
+        const long long nt = (long long)H.ntx * H.nty * H.ntz;
+        if (nt > VL_MAX_TILES) { H.valid = 0; H.fail_code = 6; return; }
+        H.n_tiles = (int)nt;
+    }
+}
+
 __global__ void __launch_bounds__(256) vl_scatter(const VlHeader* hdr, int n, const float4* __restrict__ ref_w,
                                                   const int* __restrict__ atomrank, const int* __restrict__ cellptr,
                                                   const int2* __restrict__ meta, float4* __restrict__ sref,
@@ -1534,7 +1603,8 @@ struct VlJob {
     unsigned int* atom_table; unsigned int* res_table;
     int audit; unsigned long long* d_audit;
     float max_rlist_factor;      // lists with r_list > factor * cutoff are not built (all frames fall back)
-    int conservative_tiles;      // 1: tile size from the pessimistic slot estimate (vl_setup)
+    int conservative_tiles;      // 1: tile size from the pessimistic slot estimate (vl_setup, vl_pick_tiles)
+    float tile_share = 0.6f;     // optimistic estimate: share of a tile's shell atoms that become its slots
     cudaEvent_t t_begin = nullptr, t_end = nullptr;   // recorded around the frame kernel when set (option time_kernels)
 };
 
@@ -1668,6 +1738,7 @@ inline int vl_build_body(const VlJob& job, VlScratch& S, cudaStream_t st, std::s
     vl_zero_cells<<<64, 256, 0, st>>>(S.L.hdr, S.cellcnt);
     vl_bin<<<(n + 255) / 256, 256, 0, st>>>(S.L.hdr, n, S.ref_raw, S.ref_w, S.atomrank, S.cellcnt);
     vl_scan_cells<<<1, 1024, 0, st>>>(S.L.hdr, S.cellcnt, S.cellptr, n);
+    vl_pick_tiles<<<1, 1024, 0, st>>>(S.L.hdr, S.cellptr, n, job.conservative_tiles, job.tile_share);
     vl_scatter<<<(n + 255) / 256, 256, 0, st>>>(S.L.hdr, n, S.ref_w, S.atomrank, S.cellptr, job.meta, S.sref, S.smeta,
                                                 S.scell);
     vl_res_tiles<<<(job.n_res_c + 255) / 256, 256, 0, st>>>(S.L.hdr, job.n_res_c, job.res_anchor, S.ref_w, S.tile_of_res);
@@ -1737,14 +1808,14 @@ inline int vl_build_body(const VlJob& job, VlScratch& S, cudaStream_t st, std::s
                                                       S.list_len, S.list_start, S.list_key, S.own_val, S.slot_uniq,
                                                       S.tile_slot0, S.L.row_owner, S.L.entries);
     VL_CK(cudaGetLastError());
-    launches += 32;
+    launches += 33;
     return 0;
 }
 
 // everything a captured builder graph has baked in
 struct VlGraphKey {
     int n, n_res_c, n_ignored, conservative_tiles;
-    float cutoff, c2, max_rlist_factor;
+    float cutoff, c2, max_rlist_factor, tile_share;
     const void* meta; const void* res_anchor;
     long long entry_cap;
 };
@@ -1765,7 +1836,7 @@ inline int vl_build(const VlJob& job, VlScratch& S, cudaStream_t st, std::string
         VlGraphKey key;
         memset(&key, 0, sizeof(key));
         key.n = job.n; key.n_res_c = job.n_res_c; key.n_ignored = job.n_ignored; key.conservative_tiles = job.conservative_tiles;
-        key.cutoff = job.cutoff; key.c2 = job.c2; key.max_rlist_factor = job.max_rlist_factor;
+        key.cutoff = job.cutoff; key.c2 = job.c2; key.max_rlist_factor = job.max_rlist_factor; key.tile_share = job.tile_share;
         key.meta = job.meta; key.res_anchor = job.res_anchor; key.entry_cap = S.entry_cap;
         VL_CK(cudaEventRecord(S.ev_in, st));
         VL_CK(cudaStreamWaitEvent(S.bs, S.ev_in, 0));
@@ -1799,7 +1870,7 @@ inline int vl_build(const VlJob& job, VlScratch& S, cudaStream_t st, std::string
             VL_CK(cudaGraphLaunch(S.gexec, S.bs));
             VL_CK(cudaEventRecord(S.ev_out, S.bs));
             VL_CK(cudaStreamWaitEvent(st, S.ev_out, 0));
-            launches += 32;
+            launches += 33;
             return 0;
         }
         // capture failed: the argument copy below is ordered behind the one queued on S.bs

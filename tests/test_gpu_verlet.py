@@ -367,11 +367,13 @@ def test_builder_graph_equals_plain_launches(engine):
 
 
 def test_optimistic_tiles_overflow_rebuilds_the_list(engine):
-    """Atoms that fill one corner of a larger unit cell: the optimistic tile size (from the average
-    density) overflows the tiles of the occupied region and the list is built again with the
-    pessimistic size -- synchronously for a device batch, one chunk later (never waiting for the
-    device) for a streamed host trajectory, whose frames meanwhile run through the fall back; a list
-    that still does not fit sends every frame there.  Same tables as the cell kernels either way."""
+    """The tile edge comes from the occupancy of the list cells, counting only a share of every
+    tile's shell atoms as slots; with that share set far too low the tiles overflow and the list is
+    built again with the whole shell counted -- synchronously for a device batch, one chunk later
+    (never waiting for the device) for a streamed host trajectory, whose first frames meanwhile run
+    through the fall back.  Same tables as the cell kernels either way.  Atoms that fill one corner of
+    a larger unit cell (2.2 x the volume) get a usable list as well: the estimate looks at the
+    fullest tile, not at the average density."""
     system = synth.solvated_triclinic(n_atoms=20000, lattice=28)
     system.image_shifts = False                           # (the shifts are lattice vectors of the ORIGINAL cell)
     res, chain, role = system_arrays(system)
@@ -379,16 +381,24 @@ def test_optimistic_tiles_overflow_rebuilds_the_list(engine):
     assert engine.path_kind == 1
     F = 96
     xyz, box = _dev(engine, system, 0, F)
-    box = (box * 1.3).contiguous()                        # same atoms, 2.2 times the volume
+    box = (box * 1.3).contiguous()
     cells_a, cells_r, _ = _accumulate(engine, xyz, box, 0)
     try:
         engine.set_option("verlet_conservative_tiles", 0)
         before = engine.get_stat("vl_rebuilds")
         list_a, list_r, st = _accumulate(engine, xyz, box, 2)
+        assert st["vl_valid"] == 1 and st["vl_tripped"] == 0 and st["vl_tiles"] > 1
+        assert engine.get_stat("vl_rebuilds") == before and engine.get_stat("vl_conservative") == 0
+        assert torch.equal(cells_a, list_a) and torch.equal(cells_r, list_r)
+        tiles_optimistic = st["vl_tiles"]
+        # an estimate that is far too optimistic: overflow, pessimistic rebuild
+        engine.set_option("verlet_tile_share_pct", 0)
+        list_a, list_r, st = _accumulate(engine, xyz, box, 2)
         assert engine.get_stat("vl_rebuilds") == before + 1 and engine.get_stat("vl_conservative") == 1
         assert engine.get_stat("vl_rebuild_code") in (9, 10, 11, 12, 13)
+        assert st["vl_valid"] == 1 and st["vl_tripped"] == 0 and st["vl_tiles"] >= tiles_optimistic
         assert torch.equal(cells_a, list_a) and torch.equal(cells_r, list_r)
-        # streamed: chunks of 24 frames share one list
+        # streamed: chunks of 24 frames share one list; the first ones meet the overflowing list
         engine.set_option("verlet_conservative_tiles", 0)
         before = engine.get_stat("vl_rebuilds")
         h_xyz = torch.empty(xyz.shape, dtype=torch.float32, pin_memory=True).copy_(xyz)
@@ -398,7 +408,9 @@ def test_optimistic_tiles_overflow_rebuilds_the_list(engine):
         engine.accumulate_host(h_xyz.numpy(), h_box.numpy(), host_a, host_r, chunk_frames=24)
         torch.cuda.synchronize()
         assert engine.get_stat("vl_rebuilds") == before + 1 and engine.get_stat("vl_conservative") == 1
+        assert engine.get_stat("vl_valid") == 1
         assert torch.equal(cells_a, host_a) and torch.equal(cells_r, host_r)
     finally:
         engine.set_option("verlet", 1)
+        engine.set_option("verlet_tile_share_pct", 60)
         engine.set_option("verlet_conservative_tiles", 0)
