@@ -31,7 +31,7 @@ EXPORTS = [
     "cmb_hash_rehash", "cmb_hash_overflow_buffer", "cmb_hash_add", "cmb_export_sorted", "cmb_group_contacts",
     "cmb_min_dist_pairs", "cmb_frame_contacts_host", "cmb_keys_to_csr", "cmb_screen_audit", "cmb_device_alloc", "cmb_device_free", "cmb_device_zero",
     "cmb_copy_to_host", "cmb_copy_to_device", "cmb_nccl_unique_id", "cmb_nccl_comm_create", "cmb_nccl_comm_destroy",
-    "cmb_reduce", "cmb_unpack_sorted", "cmb_unpack_pairs",
+    "cmb_reduce", "cmb_unpack_sorted", "cmb_unpack_pairs", "cmb_wait_for_stream",
 ]
 
 
@@ -120,6 +120,8 @@ def lib():
     L.cmb_export_sorted.argtypes = [vp, vp, i64, i32, i64, vp, vp, vp]
     L.cmb_unpack_sorted.restype = i32
     L.cmb_unpack_sorted.argtypes = [vp, vp, vp, i64, i64, vp, vp, vp]
+    L.cmb_wait_for_stream.restype = i32
+    L.cmb_wait_for_stream.argtypes = [vp, vp]
     L.cmb_unpack_pairs.restype = i32
     L.cmb_unpack_pairs.argtypes = [vp, vp, vp, i64, i64, i64, i64, vp, vp, vp, vp, vp]
     L.cmb_group_contacts.restype = i32

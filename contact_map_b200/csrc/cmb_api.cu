@@ -100,6 +100,8 @@ struct cmb_ctx {
     size_t pinned_bytes = 0;
     cudaEvent_t copy_done[2] = {nullptr, nullptr};
     cudaEvent_t box_ready = nullptr;              // the one copy of all unit cells has landed
+    cudaEvent_t ext_ready = nullptr;              // cmb_wait_for_stream: what the caller queued before the next host call
+    bool ext_ready_pending = false;
     cudaStream_t streams[2] = {nullptr, nullptr};
 
     // sort / min-dist scratch
@@ -249,6 +251,7 @@ extern "C" void cmb_ctx_destroy(cmb_ctx* ctx)
     for (auto& e : ctx->trace_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     if (ctx->trace_begin) cudaEventDestroy(ctx->trace_begin);
     if (ctx->box_ready) cudaEventDestroy(ctx->box_ready);
+    if (ctx->ext_ready) cudaEventDestroy(ctx->ext_ready);
     pg_free(ctx->pg);
     cudaFree(ctx->d_res_anchor);
     cudaFree(ctx->d_vl_audit);
@@ -1030,6 +1033,7 @@ static int stream_host_frames(cmb_ctx* ctx, const float* h_xyz_full, int n_total
         CK(cudaStreamWaitEvent(ctx->streams[1], ctx->box_ready, 0));
     }
     int c = 0;
+    bool ext_waited[2] = {false, false};
     if (ctx->stage_trace) {
         ctx->trace_used = 0;
         if (!ctx->trace_begin) CK(cudaEventCreate(&ctx->trace_begin));
@@ -1054,6 +1058,11 @@ static int stream_host_frames(cmb_ctx* ctx, const float* h_xyz_full, int n_total
         if (h_box && !box_once)
             CK(cudaMemcpyAsync(ctx->d_stage_box[s], h_box + (size_t)f0 * 9, (size_t)nf * 36,
                                cudaMemcpyHostToDevice, ctx->streams[s]));
+        if (ctx->ext_ready_pending && !ext_waited[s]) {
+            // the caller's earlier work (zero-filling the tables): kernels wait for it, the copy above did not
+            CK(cudaStreamWaitEvent(ctx->streams[s], ctx->ext_ready, 0));
+            ext_waited[s] = true;
+        }
         cudaEvent_t t_copy = nullptr, t_done = nullptr;
         if (ctx->stage_trace) {
             if (timing_pair(ctx->trace_events, ctx->trace_used, &t_copy, &t_done) != 0)
@@ -1075,6 +1084,17 @@ static int stream_host_frames(cmb_ctx* ctx, const float* h_xyz_full, int n_total
     }
     CK(cudaStreamSynchronize(ctx->streams[0]));
     CK(cudaStreamSynchronize(ctx->streams[1]));
+    ctx->ext_ready_pending = false;
+    return CMB_OK;
+}
+
+extern "C" int cmb_wait_for_stream(cmb_ctx* ctx, void* stream)
+{
+    if (!ctx) return CMB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->ext_ready) CK(cudaEventCreateWithFlags(&ctx->ext_ready, cudaEventDisableTiming));
+    CK(cudaEventRecord(ctx->ext_ready, (cudaStream_t)stream));
+    ctx->ext_ready_pending = true;
     return CMB_OK;
 }
 

@@ -325,8 +325,8 @@ class ContactEngine(object):
                 raise TypeError("box must be C-contiguous float32")
             if box_np.size != xyz_np.shape[0] * 9:
                 raise ValueError("box must have shape [n_frames, 3, 3]")
-        torch.cuda.current_stream(self.device).synchronize()   # tables may still be zero-filling
         if self._set_table_mode(atom_table, res_table):
+            torch.cuda.current_stream(self.device).synchronize()   # tables may still be zero-filling
             self._hash_presize_host(xyz_np[:1], box_np, atom_table, res_table)
             for a, b in self._hashed_schedule(xyz_np.shape[0]):
                 self._set_table_mode(atom_table, res_table)
@@ -336,6 +336,9 @@ class ContactEngine(object):
                                                         _table_ptr(res_table)), "cmb_accumulate_host")
                 self._hash_maintain((atom_table, res_table))
             return
+        # (the tables may still be zero-filling on torch's stream: the kernels wait for that, the
+        # first host-to-device copies do not)
+        self._check(self._L.cmb_wait_for_stream(self._ctx, _stream_ptr(self.device)), "cmb_wait_for_stream")
         self._check(self._L.cmb_accumulate_host(self._ctx, _ptr(xyz_np), _ptr(box_np),
                                                 xyz_np.shape[0], int(chunk_frames),
                                                 _ptr(atom_table), _ptr(res_table)),
@@ -356,8 +359,8 @@ class ContactEngine(object):
         if box_np is not None and (box_np.dtype != np.float32 or not box_np.flags["C_CONTIGUOUS"]
                                    or box_np.size != xyz_np.shape[0] * 9):
             raise TypeError("box must be C-contiguous float32 [n_frames, 3, 3]")
-        torch.cuda.current_stream(self.device).synchronize()
         if self._set_table_mode(atom_table, res_table):
+            torch.cuda.current_stream(self.device).synchronize()
             self._hash_presize_host(np.ascontiguousarray(xyz_np[:1][:, used]), box_np, atom_table, res_table)
             for a, b in self._hashed_schedule(xyz_np.shape[0]):
                 self._set_table_mode(atom_table, res_table)
@@ -367,6 +370,7 @@ class ContactEngine(object):
                     _table_ptr(atom_table), _table_ptr(res_table)), "cmb_accumulate_host_gather")
                 self._hash_maintain((atom_table, res_table))
             return
+        self._check(self._L.cmb_wait_for_stream(self._ctx, _stream_ptr(self.device)), "cmb_wait_for_stream")
         self._check(self._L.cmb_accumulate_host_gather(self._ctx, _ptr(xyz_np), xyz_np.shape[1], _ptr(used),
                                                        _ptr(box_np), xyz_np.shape[0], int(chunk_frames),
                                                        int(n_threads), _ptr(atom_table), _ptr(res_table)),

@@ -87,6 +87,15 @@ int cmb_accumulate_host(cmb_ctx* ctx, const float* h_xyz, const float* h_box, in
                         int64_t chunk_frames, uint32_t* d_atom_table, uint32_t* d_res_table);
 
 /*
+ * The host entry points run on the context's own streams.  A caller that has queued work on ITS
+ * stream which the next host call depends on (typically: zero-filling the count tables) either
+ * synchronises that stream first or calls this: the kernels of the next cmb_accumulate_host /
+ * cmb_accumulate_host_gather call wait for everything queued on `stream` so far, its first
+ * host-to-device copies do not (they only fill staging buffers).
+ */
+int cmb_wait_for_stream(cmb_ctx* ctx, void* stream);
+
+/*
  * Trajectory ingest: like cmb_accumulate_host, but h_xyz_full holds ALL atoms,
  * [n_frames][n_total][3], and the used atoms (h_used[n_used], ascending atom indices) are gathered
  * on the fly: host threads pack chunk k+1 into pinned staging while chunk k is copied and
