@@ -727,9 +727,10 @@ static int launch_frames(cmb_ctx* ctx, const FrameJob& job, int slot, cudaStream
                 for (int attempt = 0; attempt < 2; attempt++) {
                     vj.conservative_tiles = ctx->vl_conservative;
                     rc = vl_build(vj, V, stream, err, launches, ctx->verlet_graph != 0);
-                    if (rc != 0 || ctx->path == 0 || ctx->vl_conservative) break;
+                    if (rc != 0 || ctx->n <= VL_SINGLE_TILE_ATOMS || ctx->vl_conservative) break;
                     // lists of several tiles: a tile that overflowed the frame kernel's shared memory
                     // with the optimistic tile size gets the list rebuilt with the pessimistic one
+                    if (job.shared_list && defer_fallback && ctx->path == 0) break;   // (streamed, fused-kernel sizes: no retry)
                     CK(cudaMemcpyAsync(R.h_info + 1, &V.L.hdr->valid, sizeof(int), cudaMemcpyDeviceToHost, stream));
                     CK(cudaMemcpyAsync(R.h_info + 2, &V.L.hdr->fail_code, sizeof(int), cudaMemcpyDeviceToHost, stream));
                     if (job.shared_list && defer_fallback) {

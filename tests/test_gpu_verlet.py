@@ -58,7 +58,7 @@ def _tables_np(engine, atom_t, res_t):
     return (atom_t.cpu().numpy().view(np.uint32).reshape(n, n), res_t.cpu().numpy().view(np.uint32).reshape(rc, rc))
 
 
-@pytest.mark.parametrize("case", ["s1", "ligand", "ortho", "triclinic", "open", "n0"])
+@pytest.mark.parametrize("case", ["s1", "ligand", "ortho", "triclinic", "open", "n0", "tiles5000"])
 def test_pair_list_path_matches_oracle(engine, case):
     """List valid, no trips: bit-equal to the oracle's dense tables (and to the cell kernels on
     the whole batch); the audit mode finds no pair where the screen and MDTraj's arithmetic
@@ -70,6 +70,9 @@ def test_pair_list_path_matches_oracle(engine, case):
     elif case == "ligand":
         system, frames, check = synth.binding_system(ligand=True), 300, 12
         query, hay = system.query, system.haystack
+    elif case == "tiles5000":
+        # fused-kernel size (path 0) but more atoms than one tile holds: several tiles, guard pass
+        system, frames, check = synth.solvated_triclinic(n_atoms=5000, lattice=18), 260, 6
     elif case == "n0":
         system, frames, check, n_ignored = synth.random_system(rng, 800, n_chains=2, box_kind="ortho", extent=2.6), 260, 16, 0
     else:
@@ -85,6 +88,7 @@ def test_pair_list_path_matches_oracle(engine, case):
     assert st0["vl_used"] == 0
     list_a, list_r, st = _accumulate(engine, xyz, box, 2)
     assert st["vl_used"] == 1 and st["vl_valid"] == 1 and st["vl_tripped"] == 0 and st["vl_entries"] > 0
+    assert (st["vl_tiles"] > 1) == (case == "tiles5000")
     assert torch.equal(cells_a, list_a) and torch.equal(cells_r, list_r)
     # a short batch of its own (its own list) against the oracle
     xs, bs = xyz[:check].contiguous(), None if box is None else box[:check].contiguous()
