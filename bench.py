@@ -15,7 +15,12 @@ fixed per-GPU work (weak scaling): every rank owns 10 000 different frames.
 bit-reproducible generator).  `e2e` goes through the public API
 (`ChunkedContactFrequency(trajectory)`) with the coordinates in PINNED HOST memory: host->device
 copies, kernels, reduce, export and the device->host read of the sparse result are all inside
-the timed region.
+the timed region.  `roofline` is the HBM view of the dominant kernel: algorithmic bytes of one
+launch over that kernel's own duration, taken from CUDA events the library records around every
+`vl_frames` launch on the stream it launches on (`kernel_ms`; `accumulate_ms` is the whole
+`cmb_accumulate`, list build included); `roofline.fp32_pipe` is SURVEY 8d's work-equivalent FP32
+view.  `legs` (N = 1) are short runs of the other BASELINE.json configs; `--workload s3` makes
+configs[3] (100 000 atoms) the timed workload.
 """
 import os
 import sys
