@@ -408,7 +408,7 @@ def extra_legs(engine, fp32_peak, budget_s=150.0):
         F = 20000
         xyz, box = device_frames(engine, system, 0, F)
         engine.frame_contacts(xyz, box, frame0=0)               # sizes the key buffers
-        ms, (ak, rk) = timed_ms(lambda: engine.frame_contacts(xyz, box, frame0=0), repeat=2)
+        ms, (ak, rk) = timed_ms(lambda: engine.frame_contacts(xyz, box, frame0=0), repeat=3)
         legs[name + "_contact_trajectory"] = {
             "frames": F, "n_atoms": system.n_atoms, "frames_per_s": F / ms * 1e3, "atom_keys": int(len(ak)),
             "residue_keys": int(len(rk)), "includes": "key emission kernel, radix sort, D2H of the sorted keys"}
