@@ -15,14 +15,41 @@ import numpy as np
 
 
 class PairTable(object):
-    """Sparse symmetric table over unordered index pairs: arrays ``i < j`` and ``value``."""
+    """Sparse symmetric table over unordered index pairs: arrays ``i < j`` and ``value``.
 
-    __slots__ = ("i", "j", "value")
+    ``i`` / ``j`` are int64 and integer values int64 for every reader.  The GPU export hands over
+    int32 arrays (3.9 M pairs on the 100 000-atom system: fresh int64 copies of them cost more host
+    time than the export itself); they are kept as they come and widened on first access."""
+
+    __slots__ = ("_i", "_j", "_value")
 
     def __init__(self, i, j, value):
-        self.i = np.asarray(i, dtype=np.int64)
-        self.j = np.asarray(j, dtype=np.int64)
-        self.value = np.asarray(value)
+        self._i = self._index_array(i)
+        self._j = self._index_array(j)
+        self._value = np.asarray(value)
+
+    @staticmethod
+    def _index_array(a):
+        a = np.asarray(a)
+        return a if a.dtype in (np.int32, np.int64) else a.astype(np.int64)
+
+    @property
+    def i(self):
+        if self._i.dtype != np.int64:
+            self._i = self._i.astype(np.int64)
+        return self._i
+
+    @property
+    def j(self):
+        if self._j.dtype != np.int64:
+            self._j = self._j.astype(np.int64)
+        return self._j
+
+    @property
+    def value(self):
+        if self._value.dtype in (np.int32, np.uint32):
+            self._value = self._value.astype(np.int64)
+        return self._value
 
     @classmethod
     def empty(cls, dtype=np.int64):
@@ -42,7 +69,7 @@ class PairTable(object):
         return cls(i, j, value)
 
     def __len__(self):
-        return int(self.i.shape[0])
+        return int(self._i.shape[0])
 
     def to_counter(self):
         """``Counter{frozenset({i, j}): value}`` with plain Python ints / floats."""

@@ -513,9 +513,13 @@ def _tables_to_pairs(engine, atom_table, res_table, used):
     # (row, column, count) triples split on the device; the index maps below copy out of the
     # recycled staging buffers
     (lo, hi, cnt), (rlo, rhi, rcnt) = views
-    rmap = engine.residue_map.astype(np.int64)
-    return (PairTable(used[lo], used[hi], cnt.astype(np.int64)),
-            PairTable(rmap[rlo], rmap[rhi], rcnt.astype(np.int64)))
+    rmap = engine.residue_map
+    # (int32 wherever the indices allow: PairTable widens on first access)
+    small = used.shape[0] == 0 or int(used[-1]) < 2 ** 31
+    umap = used.astype(np.int32) if small else used
+    rmap = rmap.astype(np.int32) if rmap.shape[0] == 0 or int(rmap.max()) < 2 ** 31 else rmap.astype(np.int64)
+    return (PairTable(umap[lo], umap[hi], np.array(cnt).view(np.int32)),
+            PairTable(rmap[rlo], rmap[rhi], np.array(rcnt).view(np.int32)))
 
 
 def _exports_to_pairs(engine, exports, used):
