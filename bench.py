@@ -677,6 +677,12 @@ def run_ours(args):
                       "achieved_lane_ops_per_s": fp32_lane_ops,
                       "peak_lane_ops_per_s": fp32_peak, "frac": fp32_lane_ops / fp32_peak,
                       "time_basis": "accumulate_ms (list build included)",
+                      "executed": (None if not (dominant == "vl_frames" and list_stats.get("entries")) else {
+                          "listed_pairs_per_launch": float(list_stats["entries"]) * F,
+                          "listed_pairs_per_s": float(list_stats["entries"]) * F / (kernel_ms / 1e3),
+                          "note": "what the frame kernel actually walks: the skin-padded pair list (one 6-flop screen "
+                                  "per listed pair and frame), against candidate_pairs_per_launch canonical candidates; "
+                                  "a work-equivalent frac above 1 means the list skips more work than the pipe could do"}),
                       "definition": "frames/s x canonical candidate pairs (cutoff-sized cells, 27-cell half "
                                     "shell) x %d lane-ops (SURVEY 8d, %s) of the reference arithmetic / FP32 pipe "
                                     "peak; work-equivalent throughput, not pipe utilisation" % (ops, box_kind),
