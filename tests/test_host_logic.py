@@ -283,3 +283,27 @@ def test_memory_mapped_npy_reader_is_lazy(tmp_path):
     with pytest.raises(IOError):
         np.save(str(tmp_path / "bad.npy"), traj.xyz.astype(np.float64))
         cm.load(str(tmp_path / "bad.npy"), top=traj)
+
+
+def test_pair_table_widens_int32_arrays_lazily():
+    """The GPU export hands PairTable int32 index / count arrays; every reader sees int64 (no int32
+    overflow in packed keys), the stored arrays are only widened when they are first read."""
+    from contact_map_b200.contact_count import PairTable
+    i = np.array([0, 70000, 99998], dtype=np.int32)
+    j = np.array([5, 99999, 99999], dtype=np.int32)
+    v = np.array([3, 1, 4096], dtype=np.uint32).view(np.int32)
+    t = PairTable(i, j, v)
+    assert len(t) == 3 and t._i.dtype == np.int32 and t._value.dtype == np.int32      # untouched so far
+    assert t.i.dtype == np.int64 and t.j.dtype == np.int64 and t.value.dtype == np.int64
+    assert t._i.dtype == np.int64                                                     # widened once, kept
+    packed = t._packed(100000)
+    assert packed.dtype == np.int64 and packed[1] == 70000 * 100000 + 99999            # would overflow int32
+    both = t.combine(PairTable(np.array([0]), np.array([5]), np.array([2])))
+    assert both.to_counter() == {frozenset((0, 5)): 5, frozenset((70000, 99999)): 1, frozenset((99998, 99999)): 4096}
+    minus = t.combine(PairTable(np.array([0]), np.array([5]), np.array([3])), sign=-1)
+    assert frozenset((0, 5)) not in minus.to_counter()
+    assert t.scaled(4).value.dtype == np.float64 and t.scaled(4).value[0] == 0.75
+    assert t.restricted(np.array([0, 5])).to_counter() == {frozenset((0, 5)): 3}
+    # other dtypes are normalised at construction, floats stay floats
+    u = PairTable(np.array([1], dtype=np.uint8), [2], np.array([0.5]))
+    assert u.i.dtype == np.int64 and u.j.dtype == np.int64 and u.value.dtype == np.float64
